@@ -1,0 +1,100 @@
+// Shared host/device helpers for libchromo_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/chromoformer_b200.h"
+
+namespace chromo {
+
+// ---------------------------------------------------------------- errors ----
+void set_error(const char* fmt, ...);
+#define CHROMO_CHECK_LAUNCH(what)                                              \
+    do {                                                                       \
+        cudaError_t e__ = cudaGetLastError();                                  \
+        if (e__ != cudaSuccess) {                                              \
+            chromo::set_error("%s: %s", what, cudaGetErrorString(e__));        \
+            return CHROMO_ECUDA;                                               \
+        }                                                                      \
+    } while (0)
+#define CHROMO_TRY(expr)                                                       \
+    do {                                                                       \
+        int rc__ = (expr);                                                     \
+        if (rc__ != CHROMO_OK) return rc__;                                    \
+    } while (0)
+
+// --------------------------------------------------- parameter layout -------
+// Offsets (in floats) into the flat parameter / gradient buffers.
+struct AttnOff {      // MultiHeadAttention (modules.py:8-26) / PairwiseMultiHeadAttention (modules.py:127-148)
+    int64_t gamma_f, w_bias, att, p_att, c_att, ffw, ffb, lnw, lnb;
+};
+struct FfnOff {       // FeedForward (modules.py:91-97)
+    int64_t l1w, l1b, l2w, l2b, lnw, lnb;
+};
+struct EmbedOff {     // EmbeddingTransformer (net.py:9-21)
+    int64_t lin_proj;
+    AttnOff att[CHROMO_MAX_LAYERS];
+    FfnOff ffn[CHROMO_MAX_LAYERS];
+};
+struct PairOff {      // PairwiseInteractionTransformer (net.py:62-95)
+    int64_t lnw, lnb, lin_proj_p, lin_proj_pcre;
+    AttnOff att[CHROMO_MAX_LAYERS];
+    FfnOff ffn[CHROMO_MAX_LAYERS];
+};
+struct RegOff {       // RegulationTransformer (net.py:142-150)
+    AttnOff att[CHROMO_MAX_LAYERS];
+    FfnOff ffn[CHROMO_MAX_LAYERS];
+};
+struct ParamInfo {
+    std::string name;
+    int64_t offset, numel;
+    bool used;
+};
+struct ParamLayout {
+    EmbedOff embed[CHROMO_MAX_RES];
+    PairOff pw[CHROMO_MAX_RES];
+    RegOff reg[CHROMO_MAX_RES];
+    int64_t fc0w, fc0b, fc2w, fc2b;
+    int64_t total, active;
+    int64_t embed_stride, pw_stride, reg_stride;   // distance between resolutions
+    std::vector<ParamInfo> infos;
+};
+int validate_config(const chromo_config_t* cfg);
+const ParamLayout& get_layout(const chromo_config_t* cfg);
+
+// --------------------------------------------------- workspace layout -------
+struct WsLayout {
+    int B, I, S, R, T, D;
+    int training;
+    int64_t res_stride;   // per-resolution block stride (n-independent buffers)
+    // embed (single layer)
+    int64_t e_hc, e_q, e_qk, e_cbar, e_xbar, e_av, e_preU, e_u, e_f, e_preY;
+    // pairwise
+    int64_t p_pp;
+    int64_t p_slot;       // stride between pairwise layer slots
+    int64_t p_q, p_qk, p_cbar, p_xbar, p_av, p_preU, p_u, p_f, p_preY, p_out;
+    // regulation
+    int64_t r_xin;
+    int64_t r_slot;
+    int64_t r_proj, r_att, r_prob, r_preU, r_u, r_f, r_preY, r_out;
+    // resolution-dependent (probabilities over bins)
+    int64_t e_p[CHROMO_MAX_RES];
+    int64_t p_p[CHROMO_MAX_RES];      // + slot * p_p_slot[r]
+    int64_t p_p_slot[CHROMO_MAX_RES];
+    // head
+    int64_t h_z, h_h1;
+    // backward scratch (training only)
+    int64_t g_base;
+    int64_t total;
+    int pslots, rslots;
+    inline int pslot(int l) const { return training ? l : (l & 1); }
+    inline int rslot(int l) const { return training ? l : (l & 1); }
+};
+WsLayout make_ws_layout(const chromo_config_t* cfg, int batch, int flags);
+
+static inline int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }
+
+}  // namespace chromo

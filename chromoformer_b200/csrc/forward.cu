@@ -1,0 +1,538 @@
+// Forward pass of ChromoformerBase.forward (net.py:332-380), exact-pruned:
+//
+//  * Embedding (net.py:31-59) and Pairwise-Interaction (net.py:105-139) outputs
+//    are consumed only at the centre bin c = n/2 (net.py:59,138) and nothing
+//    after the Embedding layer's own attention mixes promoter positions, so only
+//    the centre QUERY row is evaluated.
+//  * With a single query, K/V = (x W_in^T + PE) W_kv^T never needs to be
+//    materialised:   score_j = (W_k^T q) . (W_in x_j + PE_j)
+//                    sum_j p_j v_j = W_v (W_in sum_j p_j x_j + sum_j p_j PE_j)
+//    i.e. two shared-operand GEMMs against the sinusoid table PE [n,128] plus a
+//    rank-n_feats term per region.  Pure re-association of the reference math
+//    (modules.py:48-77,159-189): no approximation, differentiable as is.
+//
+// Everything is FP32 here; the tcgen05 BF16 engine (umma_gemm.cu) replaces the
+// large projections when CHROMO_F_BF16 is set.
+#include <string.h>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "kernels.cuh"
+
+namespace chromo {
+
+// --------------------------------------------------------------- kernels ----
+
+// Hc[b,:] = W_lp x_p[b,c,:] + PE[c,:]        (net.py:42,47-53 at the centre bin)
+__global__ void centre_embed_kernel(CentreEmbedArgs a) {
+    const int r = blockIdx.y;
+    const int n = a.n[r], c = n / 2, D = a.D, F = a.F;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= a.B * D) return;
+    const int b = idx / D, d = idx % D;
+    const float* x = a.x[r] + ((long long)b * n + c) * F;
+    const float* w = a.w + r * a.w_stride + (long long)d * F;
+    float s = a.pe[r][(long long)c * D + d];
+    for (int f = 0; f < F; ++f) s = fmaf(w[f], x[f], s);
+    a.out[r * a.out_stride + idx] = s;
+}
+
+// Single-query attention row (one warp per (region, head)):
+//   s_j = (Spe[j] + u . x_j) * scale, u = W_in^T qk;  masked -> -1e9;  p = softmax(s)
+//   xbar = sum_j p_j x_j;   cbar_init = W_in xbar   (the PE part is added by a GEMM)
+// modules.py:58-61,71-77 / 170-189 restricted to the centre query.
+__global__ void __launch_bounds__(256) attn_rows_kernel(AttnRowsArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= a.rows) return;
+    const int region = warp / a.H;
+    const int n = a.n, F = a.F, D = a.D;
+    const float* qk = a.qk + (long long)warp * D;
+    float* P = a.P + (long long)warp * n;
+    const float* x = a.x + (long long)(region / a.x_div) * n * F;
+    const uint8_t* mk = a.mask + (long long)region * a.mask_stride + a.mask_row_offset;
+
+    // u[f] = sum_d W[d,f] qk[d]
+    float u[8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) u[f] = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        const float q = qk[d];
+        const float* w = a.w_in + (long long)d * F;
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+            if (f < F) u[f] = fmaf(w[f], q, u[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < 8; ++f)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) u[f] += __shfl_xor_sync(0xffffffffu, u[f], o);
+
+    // pass 1: scores + max
+    float mx = -INFINITY;
+    for (int j = lane; j < n; j += 32) {
+        const float* xj = x + (long long)j * F;
+        float s = P[j];
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+            if (f < F) s = fmaf(u[f], xj[f], s);
+        s *= a.scale;
+        if (mk[j]) s = -1e9f;
+        P[j] = s;
+        mx = fmaxf(mx, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // pass 2: exp + sum
+    float sum = 0.f;
+    for (int j = lane; j < n; j += 32) {
+        const float e = expf(P[j] - mx);
+        P[j] = e;
+        sum += e;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float inv = 1.f / sum;
+    // pass 3: normalise + xbar
+    float xb[8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) xb[f] = 0.f;
+    for (int j = lane; j < n; j += 32) {
+        const float p = P[j] * inv;
+        P[j] = p;
+        const float* xj = x + (long long)j * F;
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+            if (f < F) xb[f] = fmaf(p, xj[f], xb[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < 8; ++f)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) xb[f] += __shfl_xor_sync(0xffffffffu, xb[f], o);
+    if (lane < 8) a.xbar[(long long)warp * 8 + lane] = lane < F ? xb[lane] : 0.f;
+    float* cb = a.cbar + (long long)warp * D;
+    for (int d = lane; d < D; d += 32) {
+        const float* w = a.w_in + (long long)d * F;
+        float s = 0.f;
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+            if (f < F) s = fmaf(w[f], xb[f], s);
+        cb[d] = s;
+    }
+}
+
+// Regulation self-attention (modules.py:37-46,58-82): one warp per (gene, head),
+// lane = channel within the 32-wide head.  proj = [q | k | v | gate].
+template <int SMAX>
+__global__ void __launch_bounds__(256) reg_attention_kernel(RegAttnArgs a) {
+    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int warps_per_block = blockDim.x >> 5;
+    const long long gw = (long long)blockIdx.x * warps_per_block + warp_in_block;
+    const int z = blockIdx.y;
+    const int S = a.S, H = a.H, dm = 32 * H;
+    if (gw >= (long long)a.B * H) return;
+    const int b = (int)(gw / H), h = (int)(gw % H);
+    const float* proj = a.proj + z * a.proj_zstride + (long long)b * S * 4 * dm;
+    float q[SMAX], k[SMAX], v[SMAX], gt[SMAX];
+#pragma unroll
+    for (int i = 0; i < SMAX; ++i) {
+        if (i < S) {
+            const float* row = proj + (long long)i * 4 * dm + h * 32 + lane;
+            q[i] = row[0]; k[i] = row[dm]; v[i] = row[2 * dm]; gt[i] = row[3 * dm];
+        } else { q[i] = k[i] = v[i] = gt[i] = 0.f; }
+    }
+    const float gamma = a.gamma_f[z * a.gamma_zstride + h];
+    const float* freq = a.freq + (long long)b * S * S;
+    const uint8_t* mask = a.imask[z] + (long long)b * S * S;
+    float* prob = a.prob ? a.prob + z * a.prob_zstride + ((long long)b * H + h) * S * S : nullptr;
+    float* out = a.out + z * a.out_zstride + (long long)b * S * dm + h * 32 + lane;
+    const float scale = 0.17677669529663687f;   // 1/sqrt(32)
+#pragma unroll
+    for (int i = 0; i < SMAX; ++i) {
+        if (i >= S) break;
+        float s[SMAX];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < SMAX; ++j) {
+            if (j >= S) { s[j] = -INFINITY; continue; }
+            float t = q[i] * k[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            t = t * scale + gamma * freq[i * S + j];
+            if (mask[i * S + j]) t = -1e9f;
+            s[j] = t;
+            mx = fmaxf(mx, t);
+        }
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < SMAX; ++j) {
+            if (j < S) { s[j] = expf(s[j] - mx); sum += s[j]; }
+        }
+        const float inv = 1.f / sum;
+        float o = 0.f;
+#pragma unroll
+        for (int j = 0; j < SMAX; ++j) {
+            if (j < S) {
+                const float p = s[j] * inv;
+                o = fmaf(p, v[j], o);
+                if (prob && lane == 0) prob[i * S + j] = p;
+            }
+        }
+        const float sg = 1.f / (1.f + expf(-gt[i]));
+        out[(long long)i * dm] = o * sg;
+    }
+}
+
+// z[b, r*D + d] = X_out_r[b, 0, d] + X_in_r[b, 0, d]           (net.py:377-378)
+__global__ void head_gather_kernel(HeadGatherArgs a) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    const int W = a.n_res * a.D;
+    if (idx >= a.B * W) return;
+    const int b = idx / W, c = idx % W, r = c / a.D, d = c % a.D;
+    const long long row = (long long)b * a.S * a.D + d;
+    a.z[idx] = a.xout[r * a.zstride + row] + a.xin[r * a.zstride + row];
+}
+
+// ------------------------------------------------------------ launchers -----
+int launch_reg_attention(const RegAttnArgs& a, int nz, cudaStream_t st) {
+    const int wpb = 8;
+    dim3 grid((unsigned)(((long long)a.B * a.H + wpb - 1) / wpb), nz);
+    if (a.S <= 9) reg_attention_kernel<9><<<grid, wpb * 32, 0, st>>>(a);
+    else reg_attention_kernel<17><<<grid, wpb * 32, 0, st>>>(a);
+    CHROMO_CHECK_LAUNCH("reg_attention");
+    return CHROMO_OK;
+}
+
+int launch_attn_rows(const AttnRowsArgs& a, cudaStream_t st) {
+    const int wpb = 8;
+    attn_rows_kernel<<<(a.rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(a);
+    CHROMO_CHECK_LAUNCH("attn_rows");
+    return CHROMO_OK;
+}
+
+// Single-query attention block shared by Embedding and Pairwise layers:
+// Q[rows,dm] -> Av[rows,dm].   w_k / w_v: [dm, D] slices of att/c_att.weight.
+int single_query_attention(const SqaArgs& s, cudaStream_t st) {
+    const int dh = s.dm / s.H, D = s.D;
+    // QK[(row,h), :] = W_k[h]^T Q[row, h]                                  (NN GEMM per head)
+    {
+        GemmArgs g = gemm_args();
+        g.A = s.q; g.lda = s.dm; g.sA2 = dh;
+        g.B = s.w_k; g.ldb = D; g.sB2 = (long long)dh * D;
+        g.C = s.qk; g.ldc = s.H * D; g.sC2 = D;
+        g.M = s.rows; g.N = D; g.K = dh; g.zdiv = s.H;
+        CHROMO_TRY(gemm_launch(g, true, false, s.H, st));
+    }
+    // Spe[(row,h), j] = QK[(row,h), :] . PE[j, :]                          (NT GEMM vs the table)
+    {
+        GemmArgs g = gemm_args();
+        g.A = s.qk; g.lda = D;
+        g.B = s.pe; g.ldb = D;
+        g.C = s.P; g.ldc = s.n;
+        g.M = s.rows * s.H; g.N = s.n; g.K = D;
+        CHROMO_TRY(gemm_launch(g, true, true, 1, st));
+    }
+    {
+        AttnRowsArgs a;
+        a.rows = s.rows * s.H; a.H = s.H; a.n = s.n; a.F = s.F; a.D = D;
+        a.qk = s.qk; a.P = s.P; a.x = s.x; a.x_div = 1;
+        a.mask = s.mask; a.mask_stride = s.mask_stride; a.mask_row_offset = s.mask_row_offset;
+        a.w_in = s.w_in; a.scale = 1.f / sqrtf((float)dh);
+        a.xbar = s.xbar; a.cbar = s.cbar;
+        CHROMO_TRY(launch_attn_rows(a, st));
+    }
+    // Cbar += P . PE                                                        (NN GEMM, K = n)
+    {
+        GemmArgs g = gemm_args();
+        g.A = s.P; g.lda = s.n;
+        g.B = s.pe; g.ldb = D;
+        g.C = s.cbar; g.ldc = D; g.accumulate = 1;
+        g.M = s.rows * s.H; g.N = D; g.K = s.n;
+        CHROMO_TRY(gemm_launch(g, true, false, 1, st));
+    }
+    // Av[row, h*dh + e] = W_v[h*dh + e, :] . Cbar[(row,h), :]               (NT GEMM per head)
+    {
+        GemmArgs g = gemm_args();
+        g.A = s.cbar; g.lda = s.H * D; g.sA2 = D;
+        g.B = s.w_v; g.ldb = D; g.sB2 = (long long)dh * D;
+        g.C = s.av; g.ldc = s.dm; g.sC2 = dh;
+        g.M = s.rows; g.N = dh; g.K = D; g.zdiv = s.H;
+        CHROMO_TRY(gemm_launch(g, true, true, s.H, st));
+    }
+    return CHROMO_OK;
+}
+
+static int forward_impl(const chromo_config_t* c, const float* P, const chromo_batch_t* in, float* logits,
+                        float* ws, const WsLayout& w, int flags, cudaStream_t st) {
+    const ParamLayout& L = get_layout(c);
+    const int B = w.B, I = w.I, S = w.S, R = w.R, T = w.T, D = w.D, F = c->n_feats;
+    const int NR = c->n_res;
+    const bool train = w.training;
+    const long long RS = w.res_stride;
+
+    // ---------------- Embedding transformer, centre query (net.py:31-59) ----
+    {
+        CentreEmbedArgs a;
+        a.B = B; a.D = D; a.F = F;
+        for (int r = 0; r < NR; ++r) { a.x[r] = in->x_p[r]; a.pe[r] = in->pos_enc[r]; a.n[r] = c->n_bins[r]; }
+        a.w = P + L.embed[0].lin_proj; a.w_stride = L.embed_stride;
+        a.out = ws + w.e_hc; a.out_stride = RS;
+        dim3 grid((B * D + 255) / 256, NR);
+        centre_embed_kernel<<<grid, 256, 0, st>>>(a);
+        CHROMO_CHECK_LAUNCH("centre_embed");
+    }
+    const AttnOff& ea = L.embed[0].att[0];
+    const FfnOff& ef = L.embed[0].ffn[0];
+    const int dme = c->embed_d_model;
+    {   // Q = Hc W_q^T
+        GemmArgs g = gemm_args();
+        g.A = ws + w.e_hc; g.lda = D; g.sA1 = RS;
+        g.B = P + ea.att; g.ldb = D; g.sB1 = L.embed_stride;
+        g.C = ws + w.e_q; g.ldc = dme; g.sC1 = RS;
+        g.M = B; g.N = dme; g.K = D;
+        CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+    }
+    for (int r = 0; r < NR; ++r) {
+        SqaArgs s;
+        s.rows = B; s.H = c->embed_heads; s.dm = dme; s.D = D; s.n = c->n_bins[r]; s.F = F;
+        s.q = ws + r * RS + w.e_q;
+        s.w_k = P + L.embed[r].att[0].att + (long long)dme * D;
+        s.w_v = P + L.embed[r].att[0].att + (long long)2 * dme * D;
+        s.w_in = P + L.embed[r].lin_proj;
+        s.pe = in->pos_enc[r];
+        s.x = in->x_p[r];
+        s.mask = in->mask_p[r]; s.mask_stride = in->mask_p_stride[r]; s.mask_row_offset = in->mask_p_row_offset[r];
+        s.qk = ws + r * RS + w.e_qk; s.P = ws + w.e_p[r]; s.xbar = ws + r * RS + w.e_xbar;
+        s.cbar = ws + r * RS + w.e_cbar; s.av = ws + r * RS + w.e_av;
+        CHROMO_TRY(single_query_attention(s, st));
+    }
+    {   // U = LN(Hc + Av W_o^T + b_o)                            modules.py:29-30
+        GemmArgs g = gemm_args();
+        g.A = ws + w.e_av; g.lda = dme; g.sA1 = RS;
+        g.B = P + ea.ffw; g.ldb = dme; g.sB1 = L.embed_stride;
+        g.C = ws + w.e_u; g.ldc = D; g.sC1 = RS;
+        g.M = B; g.N = D; g.K = dme;
+        g.epi = EPI_BIAS_RES_LN; g.bias = P + ea.ffb; g.sBias1 = L.embed_stride;
+        g.res = ws + w.e_hc; g.ldres = D; g.sRes1 = RS;
+        g.gamma = P + ea.lnw; g.beta = P + ea.lnb; g.sLn1 = L.embed_stride;
+        if (train) { g.pre = ws + w.e_preU; g.sPre1 = RS; }
+        CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+    }
+    {   // F = relu(U W_1^T + b_1)                                modules.py:100-101
+        GemmArgs g = gemm_args();
+        g.A = ws + w.e_u; g.lda = D; g.sA1 = RS;
+        g.B = P + ef.l1w; g.ldb = D; g.sB1 = L.embed_stride;
+        g.C = ws + w.e_f; g.ldc = c->embed_d_ff; g.sC1 = RS;
+        g.M = B; g.N = c->embed_d_ff; g.K = D;
+        g.epi = EPI_BIAS_RELU; g.bias = P + ef.l1b; g.sBias1 = L.embed_stride;
+        CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+    }
+    {   // Y = LN(U + F W_2^T + b_2) -> X_in[b, 0, :]              net.py:359-368
+        GemmArgs g = gemm_args();
+        g.A = ws + w.e_f; g.lda = c->embed_d_ff; g.sA1 = RS;
+        g.B = P + ef.l2w; g.ldb = c->embed_d_ff; g.sB1 = L.embed_stride;
+        g.C = ws + w.r_xin; g.ldc = D; g.sC1 = RS; g.c_div = 1; g.c_mul = S; g.c_add = 0;
+        g.M = B; g.N = D; g.K = c->embed_d_ff;
+        g.epi = EPI_BIAS_RES_LN; g.bias = P + ef.l2b; g.sBias1 = L.embed_stride;
+        g.res = ws + w.e_u; g.ldres = D; g.sRes1 = RS;
+        g.gamma = P + ef.lnw; g.beta = P + ef.lnb; g.sLn1 = L.embed_stride;
+        if (train) { g.pre = ws + w.e_preY; g.sPre1 = RS; }
+        CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+    }
+
+    // ---------------- Pairwise Interaction transformer (net.py:105-139) -----
+    const int dmp = c->pw_d_model, Hp = c->pw_heads;
+    {   // PP = Y_c W_lpp^T   (identical for the I slots of a gene, net.py:114-118)
+        GemmArgs g = gemm_args();
+        g.A = ws + w.r_xin; g.lda = S * D; g.sA1 = RS;
+        g.B = P + L.pw[0].lin_proj_p; g.ldb = D; g.sB1 = L.pw_stride;
+        g.C = ws + w.p_pp; g.ldc = D; g.sC1 = RS;
+        g.M = B; g.N = D; g.K = D;
+        CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+    }
+    for (int l = 0; l < c->pw_layers; ++l) {
+        const AttnOff& pa = L.pw[0].att[l];
+        const FfnOff& pf = L.pw[0].ffn[l];
+        const long long so = (long long)w.pslot(l) * w.p_slot;
+        const float* pin = l == 0 ? ws + w.p_pp : ws + w.p_out + (long long)w.pslot(l - 1) * w.p_slot;
+        const int pin_div = l == 0 ? I : 1;
+        const bool last = l == c->pw_layers - 1;
+        {   // Q = P_l W_q^T                                       modules.py:159
+            GemmArgs g = gemm_args();
+            g.A = pin; g.lda = D; g.sA1 = RS; g.a_div = pin_div;
+            g.B = P + pa.p_att; g.ldb = D; g.sB1 = L.pw_stride;
+            g.C = ws + w.p_q + so; g.ldc = dmp; g.sC1 = RS;
+            g.M = R; g.N = dmp; g.K = D;
+            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+        }
+        for (int r = 0; r < NR; ++r) {
+            SqaArgs s;
+            s.rows = R; s.H = Hp; s.dm = dmp; s.D = D; s.n = c->n_bins[r]; s.F = F;
+            s.q = ws + r * RS + w.p_q + so;
+            s.w_k = P + L.pw[r].att[l].c_att;
+            s.w_v = P + L.pw[r].att[l].c_att + (long long)dmp * D;
+            s.w_in = P + L.pw[r].lin_proj_pcre;
+            s.pe = in->pos_enc[r];
+            s.x = in->x_pcre[r];
+            s.mask = in->mask_pcre[r]; s.mask_stride = in->mask_pcre_stride[r];
+            s.mask_row_offset = in->mask_pcre_row_offset[r];
+            s.qk = ws + r * RS + w.p_qk + so;
+            s.P = ws + w.p_p[r] + (long long)w.pslot(l) * w.p_p_slot[r];
+            s.xbar = ws + r * RS + w.p_xbar + so;
+            s.cbar = ws + r * RS + w.p_cbar + so; s.av = ws + r * RS + w.p_av + so;
+            CHROMO_TRY(single_query_attention(s, st));
+        }
+        {   // U = LN(P_l + Av W_o^T + b_o)                        modules.py:150-152
+            GemmArgs g = gemm_args();
+            g.A = ws + w.p_av + so; g.lda = dmp; g.sA1 = RS;
+            g.B = P + pa.ffw; g.ldb = dmp; g.sB1 = L.pw_stride;
+            g.C = ws + w.p_u + so; g.ldc = D; g.sC1 = RS;
+            g.M = R; g.N = D; g.K = dmp;
+            g.epi = EPI_BIAS_RES_LN; g.bias = P + pa.ffb; g.sBias1 = L.pw_stride;
+            g.res = pin; g.ldres = D; g.res_div = pin_div; g.sRes1 = RS;
+            g.gamma = P + pa.lnw; g.beta = P + pa.lnb; g.sLn1 = L.pw_stride;
+            if (train) { g.pre = ws + w.p_preU + so; g.sPre1 = RS; }
+            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+        }
+        {
+            GemmArgs g = gemm_args();
+            g.A = ws + w.p_u + so; g.lda = D; g.sA1 = RS;
+            g.B = P + pf.l1w; g.ldb = D; g.sB1 = L.pw_stride;
+            g.C = ws + w.p_f + so; g.ldc = c->pw_d_ff; g.sC1 = RS;
+            g.M = R; g.N = c->pw_d_ff; g.K = D;
+            g.epi = EPI_BIAS_RELU; g.bias = P + pf.l1b; g.sBias1 = L.pw_stride;
+            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+        }
+        {   // P_{l+1} = LN(U + F W_2^T + b_2); the last layer lands in X_in[b, 1+i, :]
+            GemmArgs g = gemm_args();
+            g.A = ws + w.p_f + so; g.lda = c->pw_d_ff; g.sA1 = RS;
+            g.B = P + pf.l2w; g.ldb = c->pw_d_ff; g.sB1 = L.pw_stride;
+            if (last) { g.C = ws + w.r_xin; g.c_div = I; g.c_mul = S; g.c_add = 1; }
+            else g.C = ws + w.p_out + so;
+            g.ldc = D; g.sC1 = RS;
+            g.M = R; g.N = D; g.K = c->pw_d_ff;
+            g.epi = EPI_BIAS_RES_LN; g.bias = P + pf.l2b; g.sBias1 = L.pw_stride;
+            g.res = ws + w.p_u + so; g.ldres = D; g.sRes1 = RS;
+            g.gamma = P + pf.lnw; g.beta = P + pf.lnb; g.sLn1 = L.pw_stride;
+            if (train) { g.pre = ws + w.p_preY + so; g.sPre1 = RS; }
+            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+        }
+    }
+
+    // ---------------- Regulation transformer (net.py:152-153) ---------------
+    const int dmr = c->reg_d_model, Hr = c->reg_heads;
+    for (int l = 0; l < c->reg_layers; ++l) {
+        const AttnOff& ra = L.reg[0].att[l];
+        const FfnOff& rf = L.reg[0].ffn[l];
+        const long long so = (long long)w.rslot(l) * w.r_slot;
+        const float* xin = l == 0 ? ws + w.r_xin : ws + w.r_out + (long long)w.rslot(l - 1) * w.r_slot;
+        {   // proj = X W_att^T  (q|k|v|gate)                       modules.py:38
+            GemmArgs g = gemm_args();
+            g.A = xin; g.lda = D; g.sA1 = RS;
+            g.B = P + ra.att; g.ldb = D; g.sB1 = L.reg_stride;
+            g.C = ws + w.r_proj + so; g.ldc = 4 * dmr; g.sC1 = RS;
+            g.M = T; g.N = 4 * dmr; g.K = D;
+            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+        }
+        {
+            RegAttnArgs a;
+            a.B = B; a.S = S; a.H = Hr;
+            a.proj = ws + w.r_proj + so; a.proj_zstride = RS;
+            a.gamma_f = P + ra.gamma_f; a.gamma_zstride = L.reg_stride;
+            a.freq = in->freq;
+            for (int r = 0; r < NR; ++r) a.imask[r] = in->imask[r];
+            a.prob = train ? ws + w.r_prob + so : nullptr; a.prob_zstride = RS;
+            a.out = ws + w.r_att + so; a.out_zstride = RS;
+            CHROMO_TRY(launch_reg_attention(a, NR, st));
+        }
+        {
+            GemmArgs g = gemm_args();
+            g.A = ws + w.r_att + so; g.lda = dmr; g.sA1 = RS;
+            g.B = P + ra.ffw; g.ldb = dmr; g.sB1 = L.reg_stride;
+            g.C = ws + w.r_u + so; g.ldc = D; g.sC1 = RS;
+            g.M = T; g.N = D; g.K = dmr;
+            g.epi = EPI_BIAS_RES_LN; g.bias = P + ra.ffb; g.sBias1 = L.reg_stride;
+            g.res = xin; g.ldres = D; g.sRes1 = RS;
+            g.gamma = P + ra.lnw; g.beta = P + ra.lnb; g.sLn1 = L.reg_stride;
+            if (train) { g.pre = ws + w.r_preU + so; g.sPre1 = RS; }
+            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+        }
+        {
+            GemmArgs g = gemm_args();
+            g.A = ws + w.r_u + so; g.lda = D; g.sA1 = RS;
+            g.B = P + rf.l1w; g.ldb = D; g.sB1 = L.reg_stride;
+            g.C = ws + w.r_f + so; g.ldc = c->reg_d_ff; g.sC1 = RS;
+            g.M = T; g.N = c->reg_d_ff; g.K = D;
+            g.epi = EPI_BIAS_RELU; g.bias = P + rf.l1b; g.sBias1 = L.reg_stride;
+            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+        }
+        {
+            GemmArgs g = gemm_args();
+            g.A = ws + w.r_f + so; g.lda = c->reg_d_ff; g.sA1 = RS;
+            g.B = P + rf.l2w; g.ldb = c->reg_d_ff; g.sB1 = L.reg_stride;
+            g.C = ws + w.r_out + so; g.ldc = D; g.sC1 = RS;
+            g.M = T; g.N = D; g.K = c->reg_d_ff;
+            g.epi = EPI_BIAS_RES_LN; g.bias = P + rf.l2b; g.sBias1 = L.reg_stride;
+            g.res = ws + w.r_u + so; g.ldres = D; g.sRes1 = RS;
+            g.gamma = P + rf.lnw; g.beta = P + rf.lnb; g.sLn1 = L.reg_stride;
+            if (train) { g.pre = ws + w.r_preY + so; g.sPre1 = RS; }
+            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+        }
+    }
+
+    // ---------------- head (net.py:377-380) ---------------------------------
+    {
+        HeadGatherArgs a;
+        a.B = B; a.S = S; a.D = D; a.n_res = NR;
+        a.xout = ws + w.r_out + (long long)w.rslot(c->reg_layers - 1) * w.r_slot;
+        a.xin = ws + w.r_xin; a.zstride = RS; a.z = ws + w.h_z;
+        head_gather_kernel<<<(B * NR * D + 255) / 256, 256, 0, st>>>(a);
+        CHROMO_CHECK_LAUNCH("head_gather");
+    }
+    {
+        GemmArgs g = gemm_args();
+        g.A = ws + w.h_z; g.lda = NR * D;
+        g.B = P + L.fc0w; g.ldb = NR * D;
+        g.C = ws + w.h_h1; g.ldc = c->d_head;
+        g.M = B; g.N = c->d_head; g.K = NR * D;
+        g.epi = EPI_BIAS_RELU; g.bias = P + L.fc0b;
+        CHROMO_TRY(gemm_launch(g, true, true, 1, st));
+    }
+    {
+        GemmArgs g = gemm_args();
+        g.A = ws + w.h_h1; g.lda = c->d_head;
+        g.B = P + L.fc2w; g.ldb = c->d_head;
+        g.C = logits; g.ldc = c->n_out;
+        g.M = B; g.N = c->n_out; g.K = c->d_head;
+        g.epi = EPI_BIAS; g.bias = P + L.fc2b;
+        CHROMO_TRY(gemm_launch(g, true, true, 1, st));
+    }
+    (void)flags;
+    return CHROMO_OK;
+}
+
+}  // namespace chromo
+
+using namespace chromo;
+
+extern "C" int chromo_forward(const chromo_config_t* cfg, const float* params, const chromo_batch_t* in,
+                              float* logits, float* workspace, int64_t workspace_floats, int32_t flags,
+                              void* stream) {
+    CHROMO_TRY(validate_config(cfg));
+    if (!params || !in || !logits || !workspace) { set_error("null pointer argument"); return CHROMO_EINVAL; }
+    if (in->batch < 1) { set_error("batch must be >= 1"); return CHROMO_EINVAL; }
+    for (int r = 0; r < cfg->n_res; ++r) {
+        if (!in->x_p[r] || !in->x_pcre[r] || !in->mask_p[r] || !in->mask_pcre[r] || !in->imask[r] ||
+            !in->pos_enc[r]) {
+            set_error("null input tensor for resolution %d", r);
+            return CHROMO_EINVAL;
+        }
+    }
+    if (!in->freq) { set_error("null interaction_freq"); return CHROMO_EINVAL; }
+    WsLayout w = make_ws_layout(cfg, in->batch, flags);
+    if (workspace_floats < w.total) {
+        set_error("workspace too small: need %lld floats, got %lld", (long long)w.total, (long long)workspace_floats);
+        return CHROMO_ENOMEM;
+    }
+    return forward_impl(cfg, params, in, logits, workspace, w, flags, (cudaStream_t)stream);
+}

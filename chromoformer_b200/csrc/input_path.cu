@@ -1,0 +1,160 @@
+// Input path: ChromoformerDataset._bin_and_pad / _get_region_representation
+// (data.py:68-113) for a batch of regions, every resolution in one launch.
+//
+// HBM-bound byte work: 2 B read per (feature, bp); the per-region FP16 row is
+// staged in shared memory ONCE with 16-byte vector loads (a row is re-used by
+// all resolutions, where the reference re-loads the .npy per bin size,
+// data.py:104) and each warp then reduces whole bins out of shared memory.
+#include <cuda_fp16.h>
+
+#include "common.cuh"
+
+namespace chromo {
+
+constexpr int BIN_THREADS = 256;
+constexpr int BIN_CHUNK = 16384;          // bp staged per pass (32 KB of FP16)
+constexpr int BIN_MAX_RES = CHROMO_MAX_RES;
+
+struct BinArgs {
+    const __half* raw;
+    const chromo_region_t* regions;
+    int n_regions, F, n_res;
+    int bin[BIN_MAX_RES];
+    int nb[BIN_MAX_RES];                  // max bins per resolution
+    float* feats[BIN_MAX_RES];
+    int* spans;
+};
+
+// grid = (F, n_regions); one CTA per (region, feature) row.
+__global__ void __launch_bounds__(BIN_THREADS) bin_regions_kernel(BinArgs a) {
+    __shared__ __align__(16) __half stage[BIN_CHUNK];
+    const int f = blockIdx.x, reg = blockIdx.y;
+    const chromo_region_t rg = a.regions[reg];
+    const __half* row = a.raw + rg.offset + (long long)f * rg.length + rg.start;
+    const int W = rg.width;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = BIN_THREADS / 32;
+
+    // zero-fill the padded output rows + spans first (each CTA owns feature f)
+    for (int r = 0; r < a.n_res; ++r) {
+        const int n = a.nb[r];
+        int nbins = (W + a.bin[r] - 1) / a.bin[r];
+        if (nbins > n) nbins = n;
+        const int lp = (n - nbins + 1) / 2, rp = (n - nbins) / 2;
+        const int first = rg.flip ? rp : lp;      // left pad after the optional flip
+        float* out = a.feats[r] + (long long)reg * n * a.F + f;
+        for (int p = threadIdx.x; p < n; p += BIN_THREADS)
+            if (p < first || p >= first + nbins) out[(long long)p * a.F] = 0.f;
+        if (f == 0 && threadIdx.x == 0) {
+            a.spans[((long long)r * a.n_regions + reg) * 2 + 0] = first;
+            a.spans[((long long)r * a.n_regions + reg) * 2 + 1] = nbins;
+        }
+    }
+
+    // chunk size is a multiple of every bin size <= BIN_CHUNK we meet in practice
+    // (100, 500, 2000 | 16000); compute the largest common multiple that fits.
+    int chunk = BIN_CHUNK;
+    {
+        // lcm of the bin sizes, capped: fall back to per-resolution chunking otherwise
+        long long l = 1;
+        for (int r = 0; r < a.n_res; ++r) {
+            long long x = l, y = a.bin[r];
+            while (y) { long long t = x % y; x = y; y = t; }
+            l = l / x * a.bin[r];
+            if (l > BIN_CHUNK) break;
+        }
+        if (l <= BIN_CHUNK) chunk = (int)(BIN_CHUNK / l * l);
+        else chunk = 0;
+    }
+
+    if (chunk > 0) {
+        for (int c0 = 0; c0 < W; c0 += chunk) {
+            const int len = min(chunk, W - c0);
+            const __half* src = row + c0;
+            // vectorised staging: 8 halves (16 B) per thread when aligned
+            const int mis = (int)((reinterpret_cast<uintptr_t>(src) & 15) / 2);
+            const int head = mis ? min(len, 8 - mis) : 0;
+            for (int i = threadIdx.x; i < head; i += BIN_THREADS) stage[i] = src[i];
+            const int nvec = (len - head) / 8;
+            // keep shared destination aligned as well: shift by `head` only if head % 8 == 0
+            if (head == 0) {
+                const uint4* s4 = reinterpret_cast<const uint4*>(src);
+                uint4* d4 = reinterpret_cast<uint4*>(stage);
+                for (int i = threadIdx.x; i < nvec; i += BIN_THREADS) d4[i] = __ldg(s4 + i);
+            } else {
+                for (int i = threadIdx.x; i < nvec * 8; i += BIN_THREADS) stage[head + i] = src[head + i];
+            }
+            for (int i = head + nvec * 8 + threadIdx.x; i < len; i += BIN_THREADS) stage[i] = src[i];
+            __syncthreads();
+            for (int r = 0; r < a.n_res; ++r) {
+                const int bs = a.bin[r], n = a.nb[r];
+                int nbins = (W + bs - 1) / bs;
+                if (nbins > n) nbins = n;
+                const int lp = (n - nbins + 1) / 2;
+                const int b0 = c0 / bs, bcnt = (len + bs - 1) / bs;
+                float* out = a.feats[r] + (long long)reg * n * a.F + f;
+                for (int b = warp; b < bcnt; b += nwarps) {
+                    const int gb = b0 + b;
+                    if (gb >= nbins) break;
+                    const int s = b * bs, e = min(s + bs, len);
+                    float acc = 0.f;
+                    for (int i = s + lane; i < e; i += 32) acc += __half2float(stage[i]);
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                    if (lane == 0) {
+                        const float mean = acc / (float)(e - s);
+                        int pos = lp + gb;
+                        if (rg.flip) pos = n - 1 - pos;
+                        out[(long long)pos * a.F] = logf(mean + 1.f);
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    } else {
+        // generic bin sizes: straight from global memory, one warp per bin
+        for (int r = 0; r < a.n_res; ++r) {
+            const int bs = a.bin[r], n = a.nb[r];
+            int nbins = (W + bs - 1) / bs;
+            if (nbins > n) nbins = n;
+            const int lp = (n - nbins + 1) / 2;
+            float* out = a.feats[r] + (long long)reg * n * a.F + f;
+            for (int b = warp; b < nbins; b += nwarps) {
+                const int s = b * bs, e = min(s + bs, W);
+                float acc = 0.f;
+                for (int i = s + lane; i < e; i += 32) acc += __half2float(row[i]);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+                if (lane == 0) {
+                    const float mean = acc / (float)(e - s);
+                    int pos = lp + b;
+                    if (rg.flip) pos = n - 1 - pos;
+                    out[(long long)pos * a.F] = logf(mean + 1.f);
+                }
+            }
+        }
+    }
+}
+
+}  // namespace chromo
+
+using namespace chromo;
+
+extern "C" int chromo_bin_regions(const uint16_t* raw, const chromo_region_t* regions, int32_t n_regions,
+                                  int32_t n_feats, int32_t n_res, const int32_t* bin_sizes,
+                                  const int32_t* n_bins, float* const* feats, int32_t* spans, void* stream) {
+    if (!raw || !regions || !bin_sizes || !n_bins || !feats || !spans) { set_error("bin_regions: null argument"); return CHROMO_EINVAL; }
+    if (n_res < 1 || n_res > BIN_MAX_RES || n_feats < 1 || n_feats > 65535) { set_error("bin_regions: bad n_res / n_feats"); return CHROMO_EINVAL; }
+    if (n_regions < 0 || n_regions > 65535) { set_error("bin_regions: at most 65535 regions per call"); return CHROMO_EINVAL; }
+    if (n_regions == 0) return CHROMO_OK;
+    BinArgs a;
+    a.raw = reinterpret_cast<const __half*>(raw);
+    a.regions = regions; a.n_regions = n_regions; a.F = n_feats; a.n_res = n_res; a.spans = spans;
+    for (int r = 0; r < n_res; ++r) {
+        if (bin_sizes[r] < 1 || n_bins[r] < 1 || !feats[r]) { set_error("bin_regions: bad resolution %d", r); return CHROMO_EINVAL; }
+        a.bin[r] = bin_sizes[r]; a.nb[r] = n_bins[r]; a.feats[r] = feats[r];
+    }
+    dim3 grid(n_feats, n_regions);
+    bin_regions_kernel<<<grid, BIN_THREADS, 0, (cudaStream_t)stream>>>(a);
+    CHROMO_CHECK_LAUNCH("bin_regions");
+    return CHROMO_OK;
+}

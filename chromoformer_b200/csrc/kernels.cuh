@@ -1,0 +1,61 @@
+// Argument blocks of the non-GEMM kernels (passed by value).
+#pragma once
+#include "common.cuh"
+
+namespace chromo {
+
+struct CentreEmbedArgs {
+    int B, D, F;
+    const float* x[CHROMO_MAX_RES];
+    const float* pe[CHROMO_MAX_RES];
+    int n[CHROMO_MAX_RES];
+    const float* w; long long w_stride;
+    float* out; long long out_stride;
+};
+
+struct AttnRowsArgs {
+    int rows, H, n, F, D;
+    const float* qk;      // [rows, D]
+    float* P;             // [rows, n]  in: PE part of the scores, out: probabilities
+    const float* x;       // [regions / x_div, n, F]
+    int x_div;
+    const uint8_t* mask; long long mask_stride, mask_row_offset;
+    const float* w_in;    // [D, F]
+    float scale;
+    float* xbar;          // [rows, 8]
+    float* cbar;          // [rows, D]  <- W_in xbar
+};
+
+struct RegAttnArgs {
+    int B, S, H;
+    const float* proj; long long proj_zstride;
+    const float* gamma_f; long long gamma_zstride;
+    const float* freq;
+    const uint8_t* imask[CHROMO_MAX_RES];
+    float* prob; long long prob_zstride;
+    float* out; long long out_zstride;
+};
+
+struct HeadGatherArgs {
+    int B, S, D, n_res;
+    const float* xout; const float* xin; long long zstride;
+    float* z;
+};
+
+// single-query attention block (forward)
+struct SqaArgs {
+    int rows, H, dm, D, n, F;
+    const float* q;                 // [rows, dm]
+    const float* w_k; const float* w_v;   // [dm, D] each
+    const float* w_in;              // [D, F]
+    const float* pe;                // [n, D]
+    const float* x;                 // [rows, n, F]
+    const uint8_t* mask; long long mask_stride, mask_row_offset;
+    float* qk; float* P; float* xbar; float* cbar; float* av;
+};
+
+int launch_reg_attention(const RegAttnArgs& a, int nz, cudaStream_t st);
+int launch_attn_rows(const AttnRowsArgs& a, cudaStream_t st);
+int single_query_attention(const SqaArgs& s, cudaStream_t st);
+
+}  // namespace chromo

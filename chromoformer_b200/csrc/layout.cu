@@ -1,0 +1,292 @@
+// Flat parameter layout + workspace layout + error plumbing (host only).
+#include <stdarg.h>
+#include <string.h>
+
+#include <map>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace chromo {
+
+static thread_local char g_err[512] = "";
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int validate_config(const chromo_config_t* c) {
+    if (!c) { set_error("null config"); return CHROMO_EINVAL; }
+#define REQ(cond, msg)                                                        \
+    if (!(cond)) { set_error("unsupported config: %s", msg); return CHROMO_EINVAL; }
+    REQ(c->d_emb == 128, "d_emb must be 128 (LayerNorm/row kernels are specialised for it)");
+    REQ(c->n_feats >= 1 && c->n_feats <= 8, "n_feats must be in [1,8]");
+    REQ(c->n_res >= 1 && c->n_res <= CHROMO_MAX_RES, "n_res must be in [1,4]");
+    REQ(c->i_max >= 1 && c->i_max <= 16, "i_max must be in [1,16]");
+    REQ(c->n_out >= 1 && c->n_out <= 16, "n_out must be in [1,16]");
+    REQ(c->d_head >= 4 && c->d_head % 4 == 0 && c->d_head <= 1024, "d_head must be a multiple of 4");
+    // The Embedding transformer is evaluated for the centre query row only
+    // (net.py:59); that is exact for a single layer, which is the only depth the
+    // reference configs use (configs/default.yaml:19).
+    REQ(c->embed_layers == 1, "embed.n_layers must be 1");
+    REQ(c->embed_d_model == c->d_emb, "embed.d_model must equal d_emb (net.py:305)");
+    REQ(c->embed_heads >= 1 && c->embed_heads <= 8 && c->embed_d_model % c->embed_heads == 0,
+        "embed.n_heads must divide embed.d_model");
+    REQ((c->embed_d_model / c->embed_heads) % 4 == 0, "embed head width must be a multiple of 4");
+    REQ(c->embed_d_ff % 4 == 0 && c->embed_d_ff >= 4, "embed.d_ff must be a multiple of 4");
+    REQ(c->pw_layers >= 1 && c->pw_layers <= CHROMO_MAX_LAYERS, "pairwise.n_layers in [1,8]");
+    REQ(c->pw_heads >= 1 && c->pw_heads <= 8 && c->pw_d_model % c->pw_heads == 0,
+        "pairwise.n_heads must divide pairwise.d_model");
+    REQ(c->pw_d_model == c->d_emb, "pairwise.d_model must equal d_emb (net.py:86-89)");
+    REQ((c->pw_d_model / c->pw_heads) % 4 == 0, "pairwise head width must be a multiple of 4");
+    REQ(c->pw_d_ff % 4 == 0 && c->pw_d_ff >= 4, "pairwise.d_ff must be a multiple of 4");
+    REQ(c->reg_layers >= 1 && c->reg_layers <= CHROMO_MAX_LAYERS, "regulation.n_layers in [1,8]");
+    REQ(c->reg_heads >= 1 && c->reg_heads <= 32 && c->reg_d_model == 32 * c->reg_heads,
+        "regulation head width (d_model / n_heads) must be 32");
+    REQ(c->reg_d_ff % 4 == 0 && c->reg_d_ff >= 4, "regulation.d_ff must be a multiple of 4");
+    for (int r = 0; r < c->n_res; ++r)
+        REQ(c->n_bins[r] >= 1 && c->n_bins[r] <= 4096, "n_bins must be in [1,4096]");
+#undef REQ
+    return CHROMO_OK;
+}
+
+namespace {
+
+struct Builder {
+    ParamLayout* L;
+    int pass;            // 0: used tensors, 1: unused tensors
+    int64_t cursor;
+    void add(const std::string& name, int64_t numel, bool used, int64_t* slot) {
+        if ((pass == 0) != used) return;
+        *slot = cursor;
+        L->infos.push_back({name, cursor, numel, used});
+        cursor = align4(cursor + numel);
+    }
+};
+
+void ffn(Builder& b, const std::string& p, int d_emb, int d_ff, FfnOff* f) {
+    b.add(p + "l1.weight", (int64_t)d_ff * d_emb, true, &f->l1w);
+    b.add(p + "l1.bias", d_ff, true, &f->l1b);
+    b.add(p + "l2.weight", (int64_t)d_emb * d_ff, true, &f->l2w);
+    b.add(p + "l2.bias", d_emb, true, &f->l2b);
+    b.add(p + "ln.weight", d_emb, true, &f->lnw);
+    b.add(p + "ln.bias", d_emb, true, &f->lnb);
+}
+
+void build(const chromo_config_t* c, ParamLayout* L) {
+    Builder b{L, 0, 0};
+    const int D = c->d_emb, F = c->n_feats;
+    for (int pass = 0; pass < 2; ++pass) {
+        b.pass = pass;
+        for (int r = 0; r < c->n_res; ++r) {
+            std::string p = "embed." + std::to_string(r) + ".";
+            EmbedOff& e = L->embed[r];
+            b.add(p + "lin_proj.weight", (int64_t)D * F, true, &e.lin_proj);
+            for (int l = 0; l < c->embed_layers; ++l) {
+                std::string q = p + "transformer.layers." + std::to_string(l) + ".";
+                AttnOff& a = e.att[l];
+                b.add(q + "self_att.gamma_f", c->embed_heads, false, &a.gamma_f);
+                b.add(q + "self_att.w_bias.weight", 2 * c->embed_heads, false, &a.w_bias);
+                b.add(q + "self_att.att.weight", (int64_t)3 * c->embed_d_model * D, true, &a.att);
+                b.add(q + "self_att.ff.weight", (int64_t)D * c->embed_d_model, true, &a.ffw);
+                b.add(q + "self_att.ff.bias", D, true, &a.ffb);
+                b.add(q + "self_att.ln.weight", D, true, &a.lnw);
+                b.add(q + "self_att.ln.bias", D, true, &a.lnb);
+                ffn(b, q + "ff.", D, c->embed_d_ff, &e.ffn[l]);
+            }
+        }
+        for (int r = 0; r < c->n_res; ++r) {
+            std::string p = "pairwise_interaction." + std::to_string(r) + ".";
+            PairOff& e = L->pw[r];
+            b.add(p + "ln.weight", D, false, &e.lnw);
+            b.add(p + "ln.bias", D, false, &e.lnb);
+            b.add(p + "lin_proj_p.weight", (int64_t)D * D, true, &e.lin_proj_p);
+            b.add(p + "lin_proj_pcre.weight", (int64_t)D * F, true, &e.lin_proj_pcre);
+            for (int l = 0; l < c->pw_layers; ++l) {
+                std::string q = p + "transformer.layers." + std::to_string(l) + ".";
+                AttnOff& a = e.att[l];
+                b.add(q + "self_att.gamma_f", c->pw_heads, false, &a.gamma_f);
+                b.add(q + "self_att.p_att.weight", (int64_t)c->pw_d_model * D, true, &a.p_att);
+                b.add(q + "self_att.c_att.weight", (int64_t)2 * c->pw_d_model * D, true, &a.c_att);
+                b.add(q + "self_att.ff.weight", (int64_t)D * c->pw_d_model, true, &a.ffw);
+                b.add(q + "self_att.ff.bias", D, true, &a.ffb);
+                b.add(q + "self_att.ln.weight", D, true, &a.lnw);
+                b.add(q + "self_att.ln.bias", D, true, &a.lnb);
+                ffn(b, q + "ff.", D, c->pw_d_ff, &e.ffn[l]);
+            }
+        }
+        for (int r = 0; r < c->n_res; ++r) {
+            std::string p = "regulation." + std::to_string(r) + ".";
+            RegOff& e = L->reg[r];
+            for (int l = 0; l < c->reg_layers; ++l) {
+                std::string q = p + "transformer.layers." + std::to_string(l) + ".";
+                AttnOff& a = e.att[l];
+                b.add(q + "self_att.gamma_f", c->reg_heads, true, &a.gamma_f);
+                b.add(q + "self_att.w_bias.weight", 2 * c->reg_heads, false, &a.w_bias);
+                b.add(q + "self_att.att.weight", (int64_t)4 * c->reg_d_model * D, true, &a.att);
+                b.add(q + "self_att.ff.weight", (int64_t)D * c->reg_d_model, true, &a.ffw);
+                b.add(q + "self_att.ff.bias", D, true, &a.ffb);
+                b.add(q + "self_att.ln.weight", D, true, &a.lnw);
+                b.add(q + "self_att.ln.bias", D, true, &a.lnb);
+                ffn(b, q + "ff.", D, c->reg_d_ff, &e.ffn[l]);
+            }
+        }
+        b.add("fc_head.0.weight", (int64_t)c->d_head * c->n_res * D, true, &L->fc0w);
+        b.add("fc_head.0.bias", c->d_head, true, &L->fc0b);
+        b.add("fc_head.2.weight", (int64_t)c->n_out * c->d_head, true, &L->fc2w);
+        b.add("fc_head.2.bias", c->n_out, true, &L->fc2b);
+        if (pass == 0) L->active = b.cursor;
+    }
+    L->total = b.cursor;
+    L->embed_stride = c->n_res > 1 ? L->embed[1].lin_proj - L->embed[0].lin_proj : 0;
+    L->pw_stride = c->n_res > 1 ? L->pw[1].lin_proj_p - L->pw[0].lin_proj_p : 0;
+    L->reg_stride = c->n_res > 1 ? L->reg[1].att[0].att - L->reg[0].att[0].att : 0;
+}
+
+struct CfgKey {
+    int32_t v[18];
+    bool operator<(const CfgKey& o) const { return memcmp(v, o.v, sizeof(v)) < 0; }
+};
+
+}  // namespace
+
+const ParamLayout& get_layout(const chromo_config_t* c) {
+    // n_bins does not influence the parameter layout.
+    static std::mutex mu;
+    static std::map<CfgKey, ParamLayout*> cache;
+    CfgKey k;
+    memcpy(k.v, c, sizeof(k.v));
+    std::lock_guard<std::mutex> g(mu);
+    auto it = cache.find(k);
+    if (it != cache.end()) return *it->second;
+    ParamLayout* L = new ParamLayout();
+    memset((void*)L->embed, 0, sizeof(L->embed));
+    memset((void*)L->pw, 0, sizeof(L->pw));
+    memset((void*)L->reg, 0, sizeof(L->reg));
+    build(c, L);
+    cache[k] = L;
+    return *L;
+}
+
+WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
+    WsLayout w;
+    memset(&w, 0, sizeof(w));
+    const int B = batch, I = c->i_max, S = I + 1, D = c->d_emb;
+    const int R = B * I, T = B * S;
+    w.B = B; w.I = I; w.S = S; w.R = R; w.T = T; w.D = D;
+    w.training = (flags & CHROMO_F_TRAINING) ? 1 : 0;
+    w.pslots = w.training ? c->pw_layers : (c->pw_layers < 2 ? c->pw_layers : 2);
+    w.rslots = w.training ? c->reg_layers : (c->reg_layers < 2 ? c->reg_layers : 2);
+    int64_t cur = 0;
+    auto take = [&](int64_t n) { int64_t o = cur; cur = align4(cur + n); return o; };
+    const int He = c->embed_heads, Hp = c->pw_heads, Hr = c->reg_heads;
+    // ---- per-resolution block
+    w.e_hc = take((int64_t)B * D);
+    w.e_q = take((int64_t)B * c->embed_d_model);
+    w.e_qk = take((int64_t)B * He * D);
+    w.e_cbar = take((int64_t)B * He * D);
+    w.e_xbar = take((int64_t)B * He * 8);
+    w.e_av = take((int64_t)B * c->embed_d_model);
+    w.e_preU = take((int64_t)B * D);
+    w.e_u = take((int64_t)B * D);
+    w.e_f = take((int64_t)B * c->embed_d_ff);
+    w.e_preY = take((int64_t)B * D);
+    w.p_pp = take((int64_t)B * D);
+    {
+        int64_t s0 = cur;
+        w.p_q = take((int64_t)R * c->pw_d_model) - s0;
+        w.p_qk = take((int64_t)R * Hp * D) - s0;
+        w.p_cbar = take((int64_t)R * Hp * D) - s0;
+        w.p_xbar = take((int64_t)R * Hp * 8) - s0;
+        w.p_av = take((int64_t)R * c->pw_d_model) - s0;
+        w.p_preU = take((int64_t)R * D) - s0;
+        w.p_u = take((int64_t)R * D) - s0;
+        w.p_f = take((int64_t)R * c->pw_d_ff) - s0;
+        w.p_preY = take((int64_t)R * D) - s0;
+        w.p_out = take((int64_t)R * D) - s0;
+        w.p_slot = cur - s0;
+        // make offsets absolute for slot 0
+        w.p_q += s0; w.p_qk += s0; w.p_cbar += s0; w.p_xbar += s0; w.p_av += s0;
+        w.p_preU += s0; w.p_u += s0; w.p_f += s0; w.p_preY += s0; w.p_out += s0;
+        cur = s0 + w.p_slot * w.pslots;
+    }
+    w.r_xin = take((int64_t)T * D);
+    {
+        int64_t s0 = cur;
+        w.r_proj = take((int64_t)T * 4 * c->reg_d_model);
+        w.r_att = take((int64_t)T * c->reg_d_model);
+        w.r_prob = take((int64_t)B * Hr * S * S);
+        w.r_preU = take((int64_t)T * D);
+        w.r_u = take((int64_t)T * D);
+        w.r_f = take((int64_t)T * c->reg_d_ff);
+        w.r_preY = take((int64_t)T * D);
+        w.r_out = take((int64_t)T * D);
+        w.r_slot = cur - s0;
+        cur = s0 + w.r_slot * w.rslots;
+    }
+    w.res_stride = cur;
+    cur = w.res_stride * c->n_res;
+    // ---- resolution-dependent buffers
+    for (int r = 0; r < c->n_res; ++r) {
+        w.e_p[r] = take((int64_t)B * He * c->n_bins[r]);
+        w.p_p_slot[r] = align4((int64_t)R * Hp * c->n_bins[r]);
+        w.p_p[r] = take(w.p_p_slot[r] * w.pslots);
+    }
+    w.h_z = take((int64_t)B * c->n_res * D);
+    w.h_h1 = take((int64_t)B * c->d_head);
+    w.g_base = cur;
+    if (w.training) {
+        // backward scratch: generous bound, carved up in backward.cu
+        int64_t per_res = (int64_t)T * (4 * c->reg_d_model + c->reg_d_model + c->reg_d_ff + 4 * D) +
+                          (int64_t)R * (2 * Hp * D + 2 * c->pw_d_model + c->pw_d_ff + 6 * D + Hp * 8) +
+                          (int64_t)B * (2 * He * D + 2 * c->embed_d_model + c->embed_d_ff + 8 * D + He * 8);
+        int64_t nmax = 0;
+        for (int r = 0; r < c->n_res; ++r) nmax = nmax > c->n_bins[r] ? nmax : c->n_bins[r];
+        int64_t probs = (int64_t)R * Hp * nmax + (int64_t)B * He * nmax;
+        cur += align4(per_res) * c->n_res + align4(probs) * c->n_res +
+               (int64_t)B * (c->n_res * D + c->d_head + 64) + 1024;
+    }
+    w.total = cur;
+    return w;
+}
+
+}  // namespace chromo
+
+using namespace chromo;
+
+extern "C" {
+
+int chromo_abi_version(void) { return CHROMO_ABI_VERSION; }
+const char* chromo_last_error(void) { return g_err; }
+
+int64_t chromo_param_total(const chromo_config_t* cfg) {
+    if (validate_config(cfg) != CHROMO_OK) return CHROMO_EINVAL;
+    return get_layout(cfg).total;
+}
+int64_t chromo_param_active(const chromo_config_t* cfg) {
+    if (validate_config(cfg) != CHROMO_OK) return CHROMO_EINVAL;
+    return get_layout(cfg).active;
+}
+int32_t chromo_param_count(const chromo_config_t* cfg) {
+    if (validate_config(cfg) != CHROMO_OK) return CHROMO_EINVAL;
+    return (int32_t)get_layout(cfg).infos.size();
+}
+int64_t chromo_param_info(const chromo_config_t* cfg, int32_t idx, char* buf, int32_t buflen,
+                          int64_t* numel) {
+    if (validate_config(cfg) != CHROMO_OK) return CHROMO_EINVAL;
+    const ParamLayout& L = get_layout(cfg);
+    if (idx < 0 || idx >= (int32_t)L.infos.size()) { set_error("param index out of range"); return CHROMO_EINVAL; }
+    const ParamInfo& p = L.infos[idx];
+    if (buf && buflen > 0) { strncpy(buf, p.name.c_str(), buflen - 1); buf[buflen - 1] = 0; }
+    if (numel) *numel = p.numel;
+    return p.offset;
+}
+int64_t chromo_workspace_floats(const chromo_config_t* cfg, int32_t batch, int32_t flags) {
+    if (validate_config(cfg) != CHROMO_OK) return CHROMO_EINVAL;
+    if (batch < 1) { set_error("batch must be >= 1"); return CHROMO_EINVAL; }
+    return make_ws_layout(cfg, batch, flags).total;
+}
+
+}  // extern "C"

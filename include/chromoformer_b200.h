@@ -1,0 +1,142 @@
+/*
+ * chromoformer_b200.h — C ABI of libchromo_b200.so (sm_100a).
+ *
+ * The reference (dohlee/chromoformer) has no FFI layer: its hot path is the
+ * PyTorch-eager forward of chromoformer/net.py + chromoformer/modules.py, the
+ * autograd backward / torch.optim.AdamW step of chromoformer/train.py and the
+ * numpy input path of chromoformer/data.py.  This header is the boundary a
+ * maintainer binds instead of those ATen call sites (ctypes stub shown in
+ * INTEGRATION.md).  Every entry point
+ *   - takes plain device pointers, sizes and a cudaStream_t passed as void*,
+ *   - never allocates, never synchronises the device, never touches the host
+ *     copy of a tensor: workspaces are caller-owned device buffers,
+ *   - returns 0 on success, a negative CHROMO_E* code otherwise
+ *     (chromo_last_error() gives the text).
+ *
+ * All floating point tensors are FP32, row-major, contiguous unless a stride
+ * argument says otherwise.  Masks are one byte per element (torch.bool).
+ */
+#ifndef CHROMOFORMER_B200_H
+#define CHROMOFORMER_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CHROMO_ABI_VERSION 1
+#define CHROMO_MAX_RES 4      /* resolutions (bin sizes) per model          */
+#define CHROMO_MAX_LAYERS 8   /* layers per sub-transformer                 */
+
+#define CHROMO_OK 0
+#define CHROMO_EINVAL (-1)    /* unsupported configuration / bad argument   */
+#define CHROMO_ENOMEM (-2)    /* workspace too small                        */
+#define CHROMO_ECUDA (-3)     /* a CUDA launch failed                       */
+
+/* flags for chromo_forward */
+#define CHROMO_F_TRAINING 1   /* keep every activation the backward needs   */
+#define CHROMO_F_BF16 2       /* dense projections on tcgen05 (BF16 operands,
+                                 FP32 accumulate); default is strict FP32   */
+
+/* Hyper-parameters: the config.yaml schema of chromoformer/configs/default.yaml:11-32
+ * plus the number of bins per resolution (w_max // binsize, data.py:140).     */
+typedef struct chromo_config {
+    int32_t n_feats;      /* 7 histone marks                         net.py:276 */
+    int32_t d_emb;        /* 128                                     net.py:277 */
+    int32_t d_head;       /* 128  fc_head hidden width               net.py:278 */
+    int32_t n_out;        /* 2 = classifier (net.py:329), 1 = regressor (net.py:427) */
+    int32_t n_res;        /* number of bin sizes, 3                  net.py:297 */
+    int32_t i_max;        /* pCRE slots per gene, 8                  data.py:30 */
+    int32_t embed_layers, embed_heads, embed_d_model, embed_d_ff;   /* net.py:279-284 */
+    int32_t pw_layers, pw_heads, pw_d_model, pw_d_ff;               /* net.py:285-290 */
+    int32_t reg_layers, reg_heads, reg_d_model, reg_d_ff;           /* net.py:291-296 */
+    int32_t n_bins[CHROMO_MAX_RES];   /* 20, 80, 400 for bin sizes 2000, 500, 100 */
+} chromo_config_t;
+
+/* One batch of genes as ChromoformerBase.forward receives it (net.py:332-340).
+ * Only the centre query row (bin n/2) of each pad mask can influence the
+ * logits (net.py:59, net.py:138), so a mask is described by a base pointer, a
+ * per-region stride and the byte offset of that row:
+ *   full  [B,I,1,n,n] bool tensor : stride = n*n, row_offset = (n/2)*n
+ *   compact [B,I,n] centre rows   : stride = n,   row_offset = 0            */
+typedef struct chromo_batch {
+    int32_t batch;                                   /* genes B                          */
+    const float*   x_p[CHROMO_MAX_RES];              /* [B,1,n,F]  promoter_feats[r]     */
+    const float*   x_pcre[CHROMO_MAX_RES];           /* [B,I,n,F]  pcre_feats[r]         */
+    const uint8_t* mask_p[CHROMO_MAX_RES];           /* promoter_pad_masks[r]            */
+    int64_t        mask_p_stride[CHROMO_MAX_RES];
+    int64_t        mask_p_row_offset[CHROMO_MAX_RES];
+    const uint8_t* mask_pcre[CHROMO_MAX_RES];        /* pcre_pad_masks[r]                */
+    int64_t        mask_pcre_stride[CHROMO_MAX_RES];
+    int64_t        mask_pcre_row_offset[CHROMO_MAX_RES];
+    const uint8_t* imask[CHROMO_MAX_RES];            /* [B,1,S,S]  interaction_masks[r]  */
+    const float*   freq;                             /* [B,S,S]    interaction_freq      */
+    const float*   pos_enc[CHROMO_MAX_RES];          /* [n,d_emb]  sinusoid table, net.py:23-29 */
+} chromo_batch_t;
+
+/* ---- library / layout ---------------------------------------------------- */
+int         chromo_abi_version(void);
+const char* chromo_last_error(void);
+
+/* Flat FP32 parameter buffer.  Tensors that receive gradients come first
+ * ([0, chromo_param_active)), the 36 structurally unused ones (w_bias.weight,
+ * embed/pairwise gamma_f, pairwise ln.*) after them.  Names are the
+ * reference state_dict keys of the dict layout, e.g.
+ * "regulation.2.transformer.layers.0.self_att.att.weight" with the resolution
+ * given as its INDEX (0..n_res-1), not its bin size.                          */
+int64_t chromo_param_total(const chromo_config_t* cfg);
+int64_t chromo_param_active(const chromo_config_t* cfg);
+int32_t chromo_param_count(const chromo_config_t* cfg);
+/* name of tensor idx into buf; returns its offset (floats), numel in *numel  */
+int64_t chromo_param_info(const chromo_config_t* cfg, int32_t idx, char* buf, int32_t buflen,
+                          int64_t* numel);
+
+/* ---- forward: net.py:332-380 (and the flat-API twin net.py:228-270) ------- */
+int64_t chromo_workspace_floats(const chromo_config_t* cfg, int32_t batch, int32_t flags);
+int chromo_forward(const chromo_config_t* cfg, const float* params, const chromo_batch_t* in,
+                   float* logits /* [B,n_out] */, float* workspace, int64_t workspace_floats,
+                   int32_t flags, void* stream);
+
+/* ---- backward: autograd of the same graph (train.py:195) ------------------
+ * `workspace` must be the buffer a CHROMO_F_TRAINING forward of the same batch
+ * filled.  grads ([chromo_param_total] floats) is ACCUMULATED into (+=).       */
+int chromo_backward(const chromo_config_t* cfg, const float* params, const chromo_batch_t* in,
+                    const float* dlogits /* [B,n_out] */, float* grads, float* workspace,
+                    int64_t workspace_floats, int32_t flags, void* stream);
+
+/* ---- losses: train.py:156,193 (mean reduction); write loss[0] and dlogits -- */
+int chromo_mse_loss(const float* logits, const float* target, int32_t count, float grad_scale,
+                    float* loss, float* dlogits, void* stream);
+int chromo_ce_loss(const float* logits, const int64_t* labels, int32_t batch, int32_t n_classes,
+                   float grad_scale, float* loss, float* dlogits, void* stream);
+
+/* ---- fused AdamW: torch.optim.AdamW as used at train.py:157,196 ------------
+ * One launch over a flat range: decoupled weight decay, bias correction from
+ * `step` (1-based), grads optionally pre-scaled (DP mean).                    */
+int chromo_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
+                 int64_t count, float lr, float beta1, float beta2, float eps,
+                 float weight_decay, int32_t step, float grad_scale, void* stream);
+
+/* ---- input path: data.py:68-113 -------------------------------------------
+ * Bins raw per-bp depth (FP16 [F,L] per region, regions concatenated in one
+ * device buffer) at every resolution: mean over <=bin bp, ln(x+1), centre pad,
+ * optional strand flip; writes feats[r] as [regions,n_r,F] and the valid-bin
+ * span (left_pad, n_bins) per region and resolution.                          */
+typedef struct chromo_region {
+    int64_t offset;     /* element offset of this region's [F,L] block in `raw`      */
+    int32_t length;     /* L in bp (row stride)                                       */
+    int32_t start;      /* first bp used (crop, data.py:106-107)                      */
+    int32_t width;      /* bp used after cropping                                     */
+    int32_t flip;       /* 1 = '-' strand promoter (data.py:110-113)                  */
+} chromo_region_t;
+int chromo_bin_regions(const uint16_t* raw /* fp16 bits */, const chromo_region_t* regions,
+                       int32_t n_regions, int32_t n_feats, int32_t n_res,
+                       const int32_t* bin_sizes, const int32_t* n_bins,
+                       float* const* feats /* n_res device ptrs */, int32_t* spans /* [n_res,regions,2] */,
+                       void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CHROMOFORMER_B200_H */
