@@ -1,0 +1,238 @@
+"""Input path: the reference's ``ChromoformerDataset`` (data.py:23-215) re-built.
+
+Two consumers:
+
+* ``ChromoformerDataset`` — same constructor, same item schema (data.py:124-212) so the
+  reference's DataLoader-based scripts keep working.  Each ``.npy`` is read once per gene
+  (the reference re-reads it per bin size, data.py:104) and bins are reduced with
+  ``np.add.reduceat`` instead of a Python loop per bin (data.py:80-84).
+* ``bin_regions_device`` / ``GeneBatcher`` — the device path: raw FP16 depth is shipped to the
+  GPU and binned for every resolution by ``chromo_bin_regions`` (csrc/input_path.cu); pad
+  masks are produced as centre rows from the valid spans instead of n x n booleans.
+"""
+import ctypes
+import math
+import os
+
+import numpy as np
+import pandas as pd
+import torch
+from torch.utils.data import Dataset
+
+from . import _lib
+
+__all__ = ["ChromoformerDataset", "bin_regions_device", "GeneBatcher"]
+
+
+def _parse_interval(text):
+    chrom, span = text.split(":")
+    start, end = span.split("-")
+    return chrom, int(start), int(end)
+
+
+def _bin_log_mean(x, bin_size):
+    """[F, L] float32 -> [F, ceil(L/bin)] of ln(mean + 1) (data.py:75-84); last bin may be partial."""
+    length = x.shape[1]
+    edges = np.arange(0, length, bin_size)
+    sums = np.add.reduceat(x, edges, axis=1, dtype=np.float32)
+    counts = np.minimum(bin_size, length - edges).astype(np.float32)
+    return np.log(sums / counts + np.float32(1.0))
+
+
+def _centre_pad(binned, max_n_bins):
+    n_bins = binned.shape[1]
+    left = math.ceil((max_n_bins - n_bins) / 2)
+    out = np.zeros((binned.shape[0], max_n_bins), dtype=np.float32)
+    out[:, left:left + n_bins] = binned
+    return out, left, n_bins, max_n_bins - n_bins - left
+
+
+class ChromoformerDataset(Dataset):
+    def __init__(self, meta, npy_dir, target_genes, n_feats=7, i_max=8, binsizes=(2000, 500, 100),
+                 w_prom=40000, w_max=40000, regression=False):
+        super().__init__()
+        self.npy_dir, self.n_feats = npy_dir, n_feats
+        self.target_genes = list(target_genes)
+        self.meta = pd.read_csv(meta) if isinstance(meta, (str, os.PathLike)) else meta
+        self.regression = regression
+        self.i_max, self.w_prom, self.w_max = i_max, w_prom, w_max
+        self.binsizes = [int(b) for b in binsizes]
+        self.ensg2label, self.ensg2tss, self.ensg2pcres, self.ensg2scores = {}, {}, {}, {}
+        for r in self.meta.itertuples(index=False):
+            self.ensg2label[r.gene_id] = np.log2(r.expression + 1) if regression else r.label
+            self.ensg2tss[r.gene_id] = (r.chrom, r.start, r.end, r.strand)
+            if isinstance(r.neighbors, str) and r.neighbors:
+                self.ensg2pcres[r.gene_id] = r.neighbors.split(";")
+                self.ensg2scores[r.gene_id] = [float(s) for s in str(r.scores).split(";")]
+            else:
+                self.ensg2pcres[r.gene_id], self.ensg2scores[r.gene_id] = [], []
+
+    def __len__(self):
+        return len(self.target_genes)
+
+    # -- raw access ---------------------------------------------------------------------
+    def region_path(self, chrom, start, end):
+        return f"{self.npy_dir}/{chrom}:{start}-{end}.npy"
+
+    def gene_regions(self, gene):
+        """[(path, crop_start, crop_width, flip)] promoter first, then its pCREs (data.py:136-178)."""
+        chrom, start, _, strand = self.ensg2tss[gene]
+        half = self.w_prom // 2
+        out = [(self.region_path(chrom, start - 20000, start + 20000), 20000 - half, 2 * half, strand != "+")]
+        for name in self.ensg2pcres[gene]:
+            c, s, e = _parse_interval(name)
+            out.append((self.region_path(c, s, e), 0, None, False))
+        return out
+
+    def _label(self, gene):
+        if self.regression:
+            return torch.tensor(self.ensg2label[gene]).float()
+        return torch.tensor(self.ensg2label[gene]).long()
+
+    # -- reference-compatible items -------------------------------------------------------
+    def __getitem__(self, i):
+        gene = self.target_genes[i]
+        scores = self.ensg2scores[gene]
+        regions = self.gene_regions(gene)
+        k = len(regions) - 1
+        if k > self.i_max:
+            raise ValueError(f"{gene}: {k} pCREs > i_max={self.i_max}; truncate the metadata (data.py:122)")
+        raws = []
+        for path, start, width, _ in regions:
+            a = np.load(path).astype(np.float32)
+            raws.append(a[:, start:start + width] if width is not None else a)
+        S = self.i_max + 1
+        item = {"label": self._label(gene), "promoter_feats": {}, "promoter_pad_masks": {}, "pcre_feats": {},
+                "pcre_pad_masks": {}, "interaction_masks": {}}
+        freq = torch.zeros(S, S)
+        for j, s in enumerate(scores):
+            freq[0, j + 1] = s
+        imask = torch.ones(1, S, S, dtype=torch.bool)
+        imask[0, :k + 1, :k + 1] = False
+        for b in self.binsizes:
+            n = self.w_max // b
+            xp, lp, nbp, rp = _centre_pad(_bin_log_mean(raws[0], b), n)
+            if regions[0][3]:
+                xp, lp = xp[:, ::-1], rp
+            mp = torch.ones(1, 1, n, n, dtype=torch.bool)
+            mp[0, 0, lp:lp + nbp, lp:lp + nbp] = False
+            xc = np.zeros((self.i_max, n, self.n_feats), dtype=np.float32)
+            mc = torch.ones(self.i_max, 1, n, n, dtype=torch.bool)
+            for j in range(k):
+                c, lc, nbc, _ = _centre_pad(_bin_log_mean(raws[1 + j], b), n)
+                xc[j] = c.T
+                mc[j, 0, lp:lp + nbp, lc:lc + nbc] = False
+            item["promoter_feats"][b] = torch.from_numpy(np.ascontiguousarray(xp.T)[None])
+            item["promoter_pad_masks"][b] = mp
+            item["pcre_feats"][b] = torch.from_numpy(xc)
+            item["pcre_pad_masks"][b] = mc
+            item["interaction_masks"][b] = imask.clone()
+        item["interaction_freq"] = freq
+        return item
+
+
+# ------------------------------------------------------------------------------ device path
+def bin_regions_device(regions, binsizes, w_max, device="cuda", stream=None):
+    """regions: [(fp16 ndarray [F,L], crop_start, crop_width, flip)] -> (feats, spans) where
+    feats[r] is [n_regions, n_r, F] float32 and spans[r] is [n_regions, 2] int32 (first valid bin, count)."""
+    lib = _lib.load()
+    n_reg = len(regions)
+    F = regions[0][0].shape[0]
+    total = sum(int(a.shape[1]) for a, *_ in regions) * F
+    total += (-total) % 8
+    host = torch.empty(total, dtype=torch.float16, pin_memory=torch.cuda.is_available())
+    table = np.zeros(n_reg, dtype=[("offset", "<i8"), ("length", "<i4"), ("start", "<i4"), ("width", "<i4"),
+                                   ("flip", "<i4")])
+    hv = host.numpy()
+    cur = 0
+    for i, (a, start, width, flip) in enumerate(regions):
+        L = int(a.shape[1])
+        if a.dtype != np.float16 or a.shape[0] != F:
+            raise ValueError("regions must be float16 [F, L] arrays with the same F")
+        start = max(0, int(start))
+        width = L - start if width is None else min(int(width), L - start)
+        hv[cur:cur + F * L] = a.reshape(-1)
+        table[i] = (cur, L, start, width, 1 if flip else 0)
+        cur += F * L
+    dev = torch.device(device)
+    raw = host.to(dev, non_blocking=True)
+    tab = torch.from_numpy(table.view(np.uint8).reshape(-1)).to(dev)
+    nb = [int(w_max) // int(b) for b in binsizes]
+    feats = [torch.empty(n_reg, n, F, dtype=torch.float32, device=dev) for n in nb]
+    spans = torch.empty(len(nb), n_reg, 2, dtype=torch.int32, device=dev)
+    ptrs = (ctypes.c_void_p * len(nb))(*[f.data_ptr() for f in feats])
+    bins_c = (ctypes.c_int32 * len(nb))(*[int(b) for b in binsizes])
+    nb_c = (ctypes.c_int32 * len(nb))(*nb)
+    st = torch.cuda.current_stream(dev).cuda_stream if stream is None else stream
+    _lib.check(lib.chromo_bin_regions(raw.data_ptr(), tab.data_ptr(), n_reg, F, len(nb), bins_c, nb_c, ptrs,
+                                      spans.data_ptr(), st), "chromo_bin_regions")
+    return feats, [spans[r] for r in range(len(nb))]
+
+
+class GeneBatcher:
+    """Raw ``.npy`` regions of a list of genes -> one device batch in the model's input format
+    (centre-row pad masks), binned on the GPU.  Region files are read once and cached."""
+
+    def __init__(self, dataset, device="cuda", cache=True):
+        self.ds, self.device = dataset, torch.device(device)
+        self._cache = {} if cache else None
+
+    def _load(self, path):
+        if self._cache is None:
+            return np.load(path)
+        a = self._cache.get(path)
+        if a is None:
+            a = self._cache[path] = np.load(path)
+        return a
+
+    def batch(self, indices):
+        ds = self.ds
+        I, S = ds.i_max, ds.i_max + 1
+        regions, owner, slot = [], [], []
+        freq = torch.zeros(len(indices), S, S)
+        k = torch.zeros(len(indices), dtype=torch.long)
+        labels = []
+        for g, i in enumerate(indices):
+            gene = ds.target_genes[i]
+            regs = ds.gene_regions(gene)
+            if len(regs) - 1 > I:
+                raise ValueError(f"{gene}: more pCREs than i_max")
+            for j, (path, start, width, flip) in enumerate(regs):
+                regions.append((self._load(path), start, width, flip))
+                owner.append(g); slot.append(j)
+            k[g] = len(regs) - 1
+            for j, s in enumerate(ds.ensg2scores[gene]):
+                freq[g, 0, j + 1] = s
+            labels.append(ds._label(gene))
+        feats, spans = bin_regions_device(regions, ds.binsizes, ds.w_max, self.device)
+        dev = self.device
+        owner_t = torch.tensor(owner, device=dev); slot_t = torch.tensor(slot, device=dev)
+        B = len(indices)
+        out = {"promoter_feats": {}, "promoter_pad_masks": {}, "pcre_feats": {}, "pcre_pad_masks": {},
+               "interaction_masks": {}}
+        is_p = slot_t == 0
+        kd = k.to(dev)
+        idx = torch.arange(S, device=dev)
+        inside = (idx.view(1, S, 1) <= kd.view(B, 1, 1)) & (idx.view(1, 1, S) <= kd.view(B, 1, 1))
+        for r, b in enumerate(ds.binsizes):
+            n = ds.w_max // b
+            F = feats[r].shape[2]
+            out["promoter_feats"][b] = feats[r][is_p].view(B, 1, n, F)
+            xc = torch.zeros(B, I, n, F, device=dev)
+            xc[owner_t[~is_p], slot_t[~is_p] - 1] = feats[r][~is_p]
+            out["pcre_feats"][b] = xc
+            pos = torch.arange(n, device=dev).view(1, n)
+            sp = spans[r].long()
+            valid = (pos >= sp[:, :1]) & (pos < sp[:, :1] + sp[:, 1:2])                  # [regions, n]
+            vp = valid[is_p]                                                             # [B, n]
+            # centre query row of data.py:156-162 / 180-185: masked unless the centre bin itself is valid
+            centre_ok = vp[:, n // 2].view(B, 1, 1)
+            out["promoter_pad_masks"][b] = ~(vp.view(B, 1, n) & centre_ok)
+            vc = torch.zeros(B, I, n, dtype=torch.bool, device=dev)
+            vc[owner_t[~is_p], slot_t[~is_p] - 1] = valid[~is_p]
+            out["pcre_pad_masks"][b] = ~(vc & centre_ok)
+            out["interaction_masks"][b] = (~inside).unsqueeze(1)
+        out["interaction_freq"] = freq.to(dev)
+        out["label"] = torch.stack(labels).to(dev)
+        out["n_partners"] = kd
+        return out

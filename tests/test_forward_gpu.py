@@ -1,0 +1,155 @@
+"""GPU parity of the sm_100a forward (through the C ABI) against the CPU oracle and the
+committed reference goldens.  Tolerances: strict-FP32 path 5e-5 abs on logits (re-associated
+FP32 sums); BF16 tensor path 1e-2 abs (BASELINE.json north_star)."""
+import numpy as np
+import pytest
+import torch
+
+from _util import BINS, KWS, as_dict, demo_batch, golden, smoke_inputs
+from chromoformer_b200 import Chromoformer, ChromoformerClassifier, ChromoformerRegressor, synthetic
+from oracle import chromoformer_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+FP32_TOL = 5e-5
+
+
+def _mk(cls=ChromoformerClassifier, seed=123):
+    return cls(7, 128, 128, dict(KWS[0]), dict(KWS[1]), dict(KWS[2]), seed=seed)
+
+
+def _sd(model):
+    return {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+
+
+def _run(model, batch):
+    model.cuda().eval()
+    with torch.no_grad():
+        return model(*synthetic.forward_args(batch, "cuda")).cpu()
+
+
+def test_demo_goldens_through_cuda():
+    """config[0]: the 100 demo genes, untrained seed-123 classifier -> demo/random_prediction.out."""
+    from sklearn import metrics
+    g = golden("demo_logits.npz")
+    model = _mk()
+    batch = demo_batch(0, 100)
+    got = _run(model, batch).numpy()
+    assert np.abs(got - g["logits"]).max() < FP32_TOL
+    pred = 1.0 / (1.0 + np.exp(-got[:, 1].astype(np.float64)))
+    assert np.abs(pred - g["random_prediction"]).max() < 2e-5
+    labels = batch["labels"].numpy()
+    assert round(metrics.roc_auc_score(labels, pred), 3) == 0.572
+    assert round(metrics.average_precision_score(labels, pred), 3) == 0.590
+    assert metrics.accuracy_score(labels, (pred > 0.5).astype(int)) == 0.49
+    # centre-row masks give the identical result
+    got2 = _run(model, demo_batch(0, 100, full_masks=False)).numpy()
+    assert np.array_equal(got, got2)
+
+
+def test_known_answers_of_net_main():
+    """net.py:558-568 through all three public classes."""
+    g = golden("smoke_main.npz")
+    m0, m1, m2 = Chromoformer(), ChromoformerClassifier(), ChromoformerRegressor()
+    x_p, m_p, x_c, m_c, i_m, freq = smoke_inputs()
+    chk = np.array([x_p[2].double().sum().item(), x_c[2].double().sum().item(), freq.double().sum().item(),
+                    float(sum(int(m.sum()) for m in m_c))])
+    if not np.allclose(chk, g["input_checksum"], rtol=0, atol=1e-9):
+        pytest.skip("torch RNG stream differs from the fixture's")
+    cu = lambda lst: [t.cuda() for t in lst]
+    x_p, m_p, x_c, m_c, i_m, freq = cu(x_p), cu(m_p), cu(x_c), cu(m_c), cu(i_m), freq.cuda()
+    flat = []
+    for r in range(3):
+        flat += [x_p[r], m_p[r], x_c[r], m_c[r], i_m[r]]
+    with torch.no_grad():
+        o0 = m0.cuda()(*flat, freq).cpu()
+        o1 = m1.cuda()(as_dict(x_p), as_dict(m_p), as_dict(x_c), as_dict(m_c), as_dict(i_m), freq).cpu()
+        o2 = m2.cuda()(as_dict(x_p), as_dict(m_p), as_dict(x_c), as_dict(m_c), as_dict(i_m), freq).cpu()
+    assert abs(o0.sum().item() + 3.1917) < 1e-4 and abs(o1.sum().item() + 3.1917) < 1e-4
+    assert abs(o2.sum().item() + 0.1900) < 1e-4
+    assert np.abs(o0.numpy() - g["legacy"]).max() < FP32_TOL
+    assert np.abs(o1.numpy() - g["classifier"]).max() < FP32_TOL
+    assert np.abs(o2.numpy() - g["regressor"]).max() < FP32_TOL
+
+
+@pytest.mark.parametrize("ragged,stress,seed,n", [(False, False, 1, 5), (True, False, 2, 9), (True, True, 3, 33)])
+def test_synthetic_vs_oracle(ragged, stress, seed, n):
+    """config[1]/[3]: dense and ragged (0..8 pCREs, variable lengths) batches, odd batch sizes."""
+    model = _mk(ChromoformerRegressor if seed == 2 else ChromoformerClassifier, seed=seed)
+    batch = synthetic.make_batch(n, ragged=ragged, full_masks=True, seed=seed, stress=stress)
+    want = oracle.chromoformer_forward(_sd(model), *synthetic.forward_args(batch))
+    got = _run(model, batch)
+    assert (got - want).abs().max().item() < FP32_TOL
+
+
+def test_stress_scaled_weights():
+    """Weights scaled to trained-like logit ranges: 2-D weights x2, last layer x8."""
+    model = _mk(seed=9)
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() == 2:
+                p.mul_(8.0 if name == "fc_head.2.weight" else 2.0)
+    batch = synthetic.make_batch(6, ragged=True, full_masks=True, seed=5, stress=True)
+    want = oracle.chromoformer_forward(_sd(model), *synthetic.forward_args(batch))
+    got = _run(model, batch)
+    assert want.abs().max().item() > 1.0
+    assert (got - want).abs().max().item() < 5e-4 * max(1.0, want.abs().max().item())
+
+
+def test_imax16_ablation():
+    """config[3]: i_max = 16 (17-token Regulation attention)."""
+    model = _mk(seed=4)
+    batch = synthetic.make_batch(3, i_max=16, ragged=True, full_masks=True, seed=6)
+    want = oracle.chromoformer_forward(_sd(model), *synthetic.forward_args(batch))
+    got = _run(model, batch)
+    assert (got - want).abs().max().item() < FP32_TOL
+
+
+def test_arbitrary_masks_and_empty_rows():
+    """randn().bool() style masks (almost all True -> uniform attention rows) and all-False masks."""
+    model = _mk(seed=8)
+    batch = synthetic.make_batch(4, ragged=False, full_masks=True, seed=8)
+    gen = torch.Generator().manual_seed(0)
+    for b in BINS:
+        n = 40000 // b
+        batch["promoter_pad_masks"][b] = torch.rand(4, 1, 1, n, n, generator=gen) < 0.3
+        batch["pcre_pad_masks"][b] = torch.rand(4, 8, 1, n, n, generator=gen) < 0.7
+        batch["interaction_masks"][b] = torch.rand(4, 1, 9, 9, generator=gen) < 0.5
+    batch["pcre_pad_masks"][100][1] = True        # a fully masked gene
+    batch["interaction_masks"][500][2] = True
+    batch["interaction_freq"] = torch.randn(4, 9, 9, generator=gen)
+    want = oracle.chromoformer_forward(_sd(model), *synthetic.forward_args(batch))
+    got = _run(model, batch)
+    assert (got - want).abs().max().item() < FP32_TOL
+
+
+def test_full_sweep_size_properties():
+    """BASELINE size (18,955 genes): chunk-invariance and permutation-equivariance of the batch."""
+    from chromoformer_b200.engine import InferenceEngine
+    model = _mk(seed=123).cuda().eval()
+    n = 18955
+    batch = synthetic.make_batch(n, ragged=True, seed=0)
+    eng = InferenceEngine(model, chunk=4096)
+    dev = eng.to_device(batch)
+    a = eng.predict_device(dev).cpu()
+    eng2 = InferenceEngine(model, chunk=1000)
+    b = eng2.predict_device(dev).cpu()
+    assert a.shape == (n, 2) and torch.isfinite(a).all()
+    assert torch.equal(a, b)                                         # chunking never changes a gene's result
+    perm = torch.randperm(512, generator=torch.Generator().manual_seed(1))
+    sub = synthetic.slice_batch(batch, 0, 512)
+    shuf = {k: ({bb: t[perm] for bb, t in v.items()} if isinstance(v, dict) else v[perm]) for k, v in sub.items()}
+    c = eng.predict_device(eng.to_device(shuf)).cpu()
+    assert torch.equal(c, a[:512][perm])
+    # dummy pCRE slots never influence the logits
+    noisy = synthetic.slice_batch(batch, 0, 256)
+    noisy = {k: ({bb: t.clone() for bb, t in v.items()} if isinstance(v, dict) else v.clone()) for k, v in noisy.items()}
+    k = noisy["n_partners"]
+    dummy = torch.arange(8).view(1, 8) >= k.view(-1, 1)
+    for bb in BINS:
+        x = noisy["pcre_feats"][bb]
+        x[dummy] = 5.0 * torch.randn_like(x[dummy])
+    d = eng.predict_device(eng.to_device(noisy)).cpu()
+    assert torch.equal(d, a[:256])
+    # host path == device path
+    e = eng.predict_host(synthetic.slice_batch(batch, 0, 5000))
+    assert torch.equal(e, a[:5000])
