@@ -1,11 +1,628 @@
-// Backward pass (placeholder until the hand-written gradients land).
+// Hand-written backward of the pruned forward in forward.cu (autograd of
+// net.py:332-380 as exercised by train.py:195).  Gradients are ACCUMULATED into
+// the flat gradient buffer, which shares the parameter layout.
+//
+// One [rows,128] gradient buffer per stage flows backwards in place through the
+// post-LN residual sub-layers:
+//     y = LN(x + f(x)):   g <- LN'(g);  (weight grads of f);  g <- g + f'(g)
+// Every dense contraction reuses the batched GEMM (data grads: NN form, weight
+// grads: A^T form with split-K atomics).
+#include <string.h>
+
 #include "common.cuh"
+#include "gemm_simt.cuh"
+#include "kernels.cuh"
+
+namespace chromo {
+
+// ------------------------------------------------------------------ kernels --
+
+// LayerNorm backward, in place on g (dy -> dz); one warp per row of 128.
+struct LnBwdArgs {
+    int M;
+    const float* pre; long long pre_z;
+    float* g; long long g_z;
+    const float* gamma; float* dgamma; float* dbeta; long long p_z;
+};
+__global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
+    __shared__ float s_dg[8][128];
+    __shared__ float s_db[8][128];
+    const int z = blockIdx.y;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float* pre = a.pre + z * a.pre_z;
+    float* g = a.g + z * a.g_z;
+    const float4 ga = *reinterpret_cast<const float4*>(a.gamma + z * a.p_z + lane * 4);
+    float dg[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
+    for (int m = blockIdx.x * 8 + warp; m < a.M; m += gridDim.x * 8) {
+        const float4 zv = *reinterpret_cast<const float4*>(pre + (long long)m * 128 + lane * 4);
+        float4 dy = *reinterpret_cast<float4*>(g + (long long)m * 128 + lane * 4);
+        float s = zv.x + zv.y + zv.z + zv.w;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+        const float mean = s * (1.f / 128.f);
+        const float c0 = zv.x - mean, c1 = zv.y - mean, c2 = zv.z - mean, c3 = zv.w - mean;
+        float q = c0 * c0 + c1 * c1 + c2 * c2 + c3 * c3;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+        const float rstd = rsqrtf(q * (1.f / 128.f) + 1e-5f);
+        const float x0 = c0 * rstd, x1 = c1 * rstd, x2 = c2 * rstd, x3 = c3 * rstd;
+        dg[0] += dy.x * x0; dg[1] += dy.y * x1; dg[2] += dy.z * x2; dg[3] += dy.w * x3;
+        db[0] += dy.x; db[1] += dy.y; db[2] += dy.z; db[3] += dy.w;
+        const float g0 = dy.x * ga.x, g1 = dy.y * ga.y, g2 = dy.z * ga.z, g3 = dy.w * ga.w;
+        float sg = g0 + g1 + g2 + g3;
+        float sgx = g0 * x0 + g1 * x1 + g2 * x2 + g3 * x3;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            sg += __shfl_xor_sync(0xffffffffu, sg, o);
+            sgx += __shfl_xor_sync(0xffffffffu, sgx, o);
+        }
+        const float mg = sg * (1.f / 128.f), mgx = sgx * (1.f / 128.f);
+        dy.x = rstd * (g0 - mg - x0 * mgx);
+        dy.y = rstd * (g1 - mg - x1 * mgx);
+        dy.z = rstd * (g2 - mg - x2 * mgx);
+        dy.w = rstd * (g3 - mg - x3 * mgx);
+        *reinterpret_cast<float4*>(g + (long long)m * 128 + lane * 4) = dy;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { s_dg[warp][lane * 4 + k] = dg[k]; s_db[warp][lane * 4 + k] = db[k]; }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float x = 0.f, y = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { x += s_dg[w][threadIdx.x]; y += s_db[w][threadIdx.x]; }
+        atomicAdd(a.dgamma + z * a.p_z + threadIdx.x, x);
+        atomicAdd(a.dbeta + z * a.p_z + threadIdx.x, y);
+    }
+}
+
+// g *= (f > 0)
+__global__ void relu_bwd_kernel(float* g, const float* f, long long count, long long g_z, long long f_z) {
+    const int z = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count && !(f[z * f_z + i] > 0.f)) g[z * g_z + i] = 0.f;
+}
+
+// out[n] += sum_m dY[m, n]      (bias gradients)
+__global__ void __launch_bounds__(256) colsum_kernel(const float* dY, int M, int N, int ld, long long dy_z,
+                                                     float* out, long long out_z, int rows_per_block) {
+    const int z = blockIdx.z;
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const int m0 = blockIdx.y * rows_per_block, m1 = min(M, m0 + rows_per_block);
+    const float* p = dY + z * dy_z + n;
+    float s = 0.f;
+    for (int m = m0; m < m1; ++m) s += p[(long long)m * ld];
+    atomicAdd(out + z * out_z + n, s);
+}
+
+// dst[m, :] (=|+=) src[(m / div) * mul + m % div + add, :]   (128-wide rows)
+__global__ void gather_rows_kernel(float* dst, long long dst_z, const float* src, long long src_z, int M, int div,
+                                   int mul, int add) {
+    const int z = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // float4 index
+    if (i >= (long long)M * 32) return;
+    const int m = (int)(i / 32), c = (int)(i % 32);
+    const long long srow = (long long)(m / div) * mul + (m % div) + add;
+    reinterpret_cast<float4*>(dst + z * dst_z)[i] = reinterpret_cast<const float4*>(src + z * src_z)[srow * 32 + c];
+}
+
+// dst[b, :] = sum_i src[b * I + i, :]
+__global__ void slot_sum_kernel(float* dst, long long dst_z, const float* src, long long src_z, int B, int I) {
+    const int z = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * 32) return;
+    const int b = (int)(i / 32), c = (int)(i % 32);
+    const float4* s = reinterpret_cast<const float4*>(src + z * src_z) + (long long)b * I * 32 + c;
+    float4 acc = make_float4(0, 0, 0, 0);
+    for (int k = 0; k < I; ++k) {
+        const float4 v = s[(long long)k * 32];
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+    reinterpret_cast<float4*>(dst + z * dst_z)[i] = acc;
+}
+
+// Head fan-out: g_reg[b*S + 0, :] = dz[b, r*D:(r+1)*D], other rows 0          (net.py:377)
+__global__ void head_scatter_kernel(float* g, long long g_z, const float* dz, int B, int S, int D, int n_res) {
+    const int z = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (long long)B * S * D) return;
+    const int d = (int)(i % D);
+    const long long row = i / D;
+    const int b = (int)(row / S), s = (int)(row % S);
+    g[z * g_z + i] = s == 0 ? dz[(long long)b * n_res * D + z * D + d] : 0.f;
+}
+// g[b*S + 0, :] += dz[b, r*D:(r+1)*D]                                        (residual, net.py:378)
+__global__ void head_residual_kernel(float* g, long long g_z, const float* dz, int B, int S, int D, int n_res) {
+    const int z = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * D) return;
+    const int b = i / D, d = i % D;
+    g[z * g_z + (long long)b * S * D + d] += dz[(long long)b * n_res * D + z * D + d];
+}
+
+// Backward of reg_attention_kernel.  One warp per (gene, head), lane = channel.
+template <int SMAX>
+__global__ void __launch_bounds__(256) reg_attention_bwd_kernel(RegAttnBwdArgs a) {
+    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
+    const int z = blockIdx.y;
+    const int S = a.S, H = a.H, dm = 32 * H;
+    if (gw >= (long long)a.B * H) return;
+    const int b = (int)(gw / H), h = (int)(gw % H);
+    const float* proj = a.proj + z * a.proj_z + (long long)b * S * 4 * dm + h * 32 + lane;
+    float* dproj = a.dproj + z * a.dproj_z + (long long)b * S * 4 * dm + h * 32 + lane;
+    const float* dout = a.dout + z * a.dout_z + (long long)b * S * dm + h * 32 + lane;
+    const float* prob = a.prob + z * a.prob_z + ((long long)b * H + h) * S * S;
+    const float* freq = a.freq + (long long)b * S * S;
+    const uint8_t* mask = a.imask[z] + (long long)b * S * S;
+    const float scale = 0.17677669529663687f;
+    float q[SMAX], k[SMAX], v[SMAX], dk[SMAX], dv[SMAX];
+#pragma unroll
+    for (int i = 0; i < SMAX; ++i) {
+        if (i < S) {
+            const float* row = proj + (long long)i * 4 * dm;
+            q[i] = row[0]; k[i] = row[dm]; v[i] = row[2 * dm];
+        } else { q[i] = k[i] = v[i] = 0.f; }
+        dk[i] = 0.f; dv[i] = 0.f;
+    }
+    float dgam = 0.f;
+#pragma unroll
+    for (int i = 0; i < SMAX; ++i) {
+        if (i >= S) break;
+        float p[SMAX], dp[SMAX];
+        float av = 0.f;
+#pragma unroll
+        for (int j = 0; j < SMAX; ++j) {
+            p[j] = j < S ? prob[i * S + j] : 0.f;
+            av = fmaf(p[j], v[j], av);
+        }
+        const float gt = proj[(long long)i * 4 * dm + 3 * dm];
+        const float sg = 1.f / (1.f + expf(-gt));
+        const float d_o = dout[(long long)i * dm];
+        const float da = d_o * sg;
+        dproj[(long long)i * 4 * dm + 3 * dm] = d_o * av * sg * (1.f - sg);
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < SMAX; ++j) {
+            if (j >= S) { dp[j] = 0.f; continue; }
+            float t = da * v[j];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+            dp[j] = t;
+            dot = fmaf(p[j], t, dot);
+            dv[j] = fmaf(p[j], da, dv[j]);
+        }
+        float dq = 0.f;
+#pragma unroll
+        for (int j = 0; j < SMAX; ++j) {
+            if (j >= S) continue;
+            const float ds = mask[i * S + j] ? 0.f : p[j] * (dp[j] - dot);
+            dgam = fmaf(ds, freq[i * S + j], dgam);
+            dq = fmaf(ds, k[j], dq);
+            dk[j] = fmaf(ds, q[i], dk[j]);
+        }
+        dproj[(long long)i * 4 * dm] = dq * scale;
+    }
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+        if (j < S) {
+            dproj[(long long)j * 4 * dm + dm] = dk[j] * scale;
+            dproj[(long long)j * 4 * dm + 2 * dm] = dv[j];
+        }
+    }
+    if (lane == 0) atomicAdd(a.dgamma_f + z * a.dgamma_z + h, dgam);
+}
+
+// Backward of attn_rows_kernel; one warp per (region, head).
+//   in : dS[j] = dCbar . PE_j (from a GEMM), P, dCbar, x, mask
+//   out: dS[j] = gradient wrt the pre-scale score, dU8 = sum_j dS_j x_j,
+//        dQK_init = W_in dU  (the PE part is added by a GEMM)
+__global__ void __launch_bounds__(256) attn_rows_bwd_kernel(AttnRowsBwdArgs a) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= a.rows) return;
+    const int region = warp / a.H;
+    const int n = a.n, F = a.F, D = a.D;
+    const float* P = a.P + (long long)warp * n;
+    float* dS = a.dS + (long long)warp * n;
+    const float* dcb = a.dcbar + (long long)warp * D;
+    const float* x = a.x + (long long)region * n * F;
+    const uint8_t* mk = a.mask + (long long)region * a.mask_stride + a.mask_row_offset;
+    float dxb[8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) dxb[f] = 0.f;
+    for (int d = lane; d < D; d += 32) {
+        const float c = dcb[d];
+        const float* w = a.w_in + (long long)d * F;
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+            if (f < F) dxb[f] = fmaf(w[f], c, dxb[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < 8; ++f)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) dxb[f] += __shfl_xor_sync(0xffffffffu, dxb[f], o);
+    float dot = 0.f;
+    for (int j = lane; j < n; j += 32) {
+        const float* xj = x + (long long)j * F;
+        float dp = dS[j];
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+            if (f < F) dp = fmaf(dxb[f], xj[f], dp);
+        dS[j] = dp;
+        dot = fmaf(P[j], dp, dot);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    float du[8];
+#pragma unroll
+    for (int f = 0; f < 8; ++f) du[f] = 0.f;
+    for (int j = lane; j < n; j += 32) {
+        const float ds = mk[j] ? 0.f : P[j] * (dS[j] - dot) * a.scale;
+        dS[j] = ds;
+        const float* xj = x + (long long)j * F;
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+            if (f < F) du[f] = fmaf(ds, xj[f], du[f]);
+    }
+#pragma unroll
+    for (int f = 0; f < 8; ++f)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) du[f] += __shfl_xor_sync(0xffffffffu, du[f], o);
+    if (lane < 8) a.dU8[(long long)warp * 8 + lane] = lane < F ? du[lane] : 0.f;
+    float* dqk = a.dqk + (long long)warp * D;
+    for (int d = lane; d < D; d += 32) {
+        const float* w = a.w_in + (long long)d * F;
+        float s = 0.f;
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+            if (f < F) s = fmaf(w[f], du[f], s);
+        dqk[d] = s;
+    }
+}
+
+// ------------------------------------------------------------ host helpers ---
+namespace {
+
+struct Ctx {
+    cudaStream_t st;
+    int NR;
+};
+
+inline int ksplit_for(int K) {
+    int s = (K + 255) / 256;
+    return s < 1 ? 1 : (s > 16 ? 16 : s);
+}
+
+// dX (=|+=) dY W        dY [M,N] (ld ldy), W [N,K] row-major, dX [M,K] (ld lddx)
+int bwd_data(const Ctx& c, const float* dY, int ldy, long long dy_z, const float* W, long long w_z, float* dX,
+             int lddx, long long dx_z, int M, int N, int K, bool accumulate, int nz) {
+    GemmArgs g = gemm_args();
+    g.A = dY; g.lda = ldy; g.sA1 = dy_z;
+    g.B = W; g.ldb = K; g.sB1 = w_z;
+    g.C = dX; g.ldc = lddx; g.sC1 = dx_z;
+    g.M = M; g.N = K; g.K = N; g.accumulate = accumulate ? 1 : 0;
+    return gemm_launch(g, true, false, nz, c.st);
+}
+
+// dW += dY^T X          dY [M,N], X [M/x_div rows broadcast, K] (ld ldx), dW [N,K] row-major
+int bwd_weight(const Ctx& c, const float* dY, int ldy, long long dy_z, const float* X, int ldx, int x_div,
+               long long x_z, float* dW, int lddw, long long dw_z, int M, int N, int K, int nz) {
+    GemmArgs g = gemm_args();
+    g.A = dY; g.lda = ldy; g.sA1 = dy_z;
+    g.B = X; g.ldb = ldx; g.b_div = x_div; g.sB1 = x_z;
+    g.C = dW; g.ldc = lddw; g.sC1 = dw_z;
+    g.M = N; g.N = K; g.K = M;
+    g.ksplit = ksplit_for(M);
+    g.accumulate = 1;
+    return gemm_launch(g, false, false, nz, c.st);
+}
+
+int bwd_bias(const Ctx& c, const float* dY, int ld, long long dy_z, float* db, long long db_z, int M, int N,
+             int nz) {
+    const int rpb = 64;
+    dim3 grid((N + 127) / 128, (M + rpb - 1) / rpb, nz);
+    colsum_kernel<<<grid, 128, 0, c.st>>>(dY, M, N, ld, dy_z, db, db_z, rpb);
+    CHROMO_CHECK_LAUNCH("colsum");
+    return CHROMO_OK;
+}
+
+int ln_bwd(const Ctx& c, const float* pre, long long pre_z, float* g, long long g_z, const float* gamma,
+           float* dgamma, float* dbeta, long long p_z, int M, int nz) {
+    LnBwdArgs a{M, pre, pre_z, g, g_z, gamma, dgamma, dbeta, p_z};
+    int blocks = (M + 7) / 8;
+    if (blocks > 296) blocks = 296;
+    ln_bwd_kernel<<<dim3(blocks, nz), 256, 0, c.st>>>(a);
+    CHROMO_CHECK_LAUNCH("ln_bwd");
+    return CHROMO_OK;
+}
+
+int relu_bwd(const Ctx& c, float* g, long long g_z, const float* f, long long f_z, long long count, int nz) {
+    relu_bwd_kernel<<<dim3((unsigned)((count + 255) / 256), nz), 256, 0, c.st>>>(g, f, count, g_z, f_z);
+    CHROMO_CHECK_LAUNCH("relu_bwd");
+    return CHROMO_OK;
+}
+
+// Backward of  y = LN(u + W2 relu(W1 u + b1) + b2)  in place on g [M,128].
+int ffn_bwd(const Ctx& c, const float* P, float* G, const FfnOff& f, long long p_z, int dff, const float* u,
+            const float* fact, const float* preY, long long act_z, float* g, float* dF, long long g_z, int M) {
+    const int D = 128, nz = c.NR;
+    CHROMO_TRY(ln_bwd(c, preY, act_z, g, g_z, P + f.lnw, G + f.lnw, G + f.lnb, p_z, M, nz));
+    CHROMO_TRY(bwd_weight(c, g, D, g_z, fact, dff, 1, act_z, G + f.l2w, dff, p_z, M, D, dff, nz));
+    CHROMO_TRY(bwd_bias(c, g, D, g_z, G + f.l2b, p_z, M, D, nz));
+    CHROMO_TRY(bwd_data(c, g, D, g_z, P + f.l2w, p_z, dF, dff, g_z, M, D, dff, false, nz));
+    CHROMO_TRY(relu_bwd(c, dF, g_z, fact, act_z, (long long)M * dff, nz));
+    CHROMO_TRY(bwd_weight(c, dF, dff, g_z, u, D, 1, act_z, G + f.l1w, D, p_z, M, dff, D, nz));
+    CHROMO_TRY(bwd_bias(c, dF, dff, g_z, G + f.l1b, p_z, M, dff, nz));
+    CHROMO_TRY(bwd_data(c, dF, dff, g_z, P + f.l1w, p_z, g, D, g_z, M, dff, D, true, nz));
+    return CHROMO_OK;
+}
+
+struct SqaBwd {
+    int rows, H, dm, D, n, F;
+    const float* q; const float* qk; const float* P; const float* xbar; const float* cbar;
+    const float* w_k; const float* w_v; const float* w_in; const float* pe; const float* x;
+    const uint8_t* mask; long long mask_stride, mask_row_offset;
+    float* g_wk; float* g_wv; float* g_win;
+    const float* dAv; float* dQ;
+    float* dCbar; float* dQK; float* dU8; float* dS;
+};
+
+int sqa_bwd(const Ctx& c, const SqaBwd& s) {
+    const int dh = s.dm / s.H, D = s.D, RH = s.rows * s.H;
+    {   // dCbar[(r,h), :] = dAv[r, h] W_v[h]
+        GemmArgs g = gemm_args();
+        g.A = s.dAv; g.lda = s.dm; g.sA2 = dh;
+        g.B = s.w_v; g.ldb = D; g.sB2 = (long long)dh * D;
+        g.C = s.dCbar; g.ldc = s.H * D; g.sC2 = D;
+        g.M = s.rows; g.N = D; g.K = dh; g.zdiv = s.H;
+        CHROMO_TRY(gemm_launch(g, true, false, s.H, c.st));
+    }
+    {   // dW_v[h] += dAv[:, h]^T Cbar[(:,h), :]
+        GemmArgs g = gemm_args();
+        g.A = s.dAv; g.lda = s.dm; g.sA2 = dh;
+        g.B = s.cbar; g.ldb = s.H * D; g.sB2 = D;
+        g.C = s.g_wv; g.ldc = D; g.sC2 = (long long)dh * D;
+        g.M = dh; g.N = D; g.K = s.rows; g.zdiv = s.H; g.accumulate = 1; g.ksplit = ksplit_for(s.rows);
+        CHROMO_TRY(gemm_launch(g, false, false, s.H, c.st));
+    }
+    {   // dP (PE part) = dCbar PE^T
+        GemmArgs g = gemm_args();
+        g.A = s.dCbar; g.lda = D; g.B = s.pe; g.ldb = D; g.C = s.dS; g.ldc = s.n;
+        g.M = RH; g.N = s.n; g.K = D;
+        CHROMO_TRY(gemm_launch(g, true, true, 1, c.st));
+    }
+    {
+        AttnRowsBwdArgs a;
+        a.rows = RH; a.H = s.H; a.n = s.n; a.F = s.F; a.D = D;
+        a.P = s.P; a.dS = s.dS; a.dcbar = s.dCbar; a.x = s.x;
+        a.mask = s.mask; a.mask_stride = s.mask_stride; a.mask_row_offset = s.mask_row_offset;
+        a.w_in = s.w_in; a.scale = 1.f / sqrtf((float)dh); a.dU8 = s.dU8; a.dqk = s.dQK;
+        attn_rows_bwd_kernel<<<(RH + 7) / 8, 256, 0, c.st>>>(a);
+        CHROMO_CHECK_LAUNCH("attn_rows_bwd");
+    }
+    // dW_in += dCbar^T xbar + QK^T dU
+    CHROMO_TRY(bwd_weight(c, s.dCbar, D, 0, s.xbar, 8, 1, 0, s.g_win, s.F, 0, RH, D, s.F, 1));
+    CHROMO_TRY(bwd_weight(c, s.qk, D, 0, s.dU8, 8, 1, 0, s.g_win, s.F, 0, RH, D, s.F, 1));
+    {   // dQK += dS PE
+        GemmArgs g = gemm_args();
+        g.A = s.dS; g.lda = s.n; g.B = s.pe; g.ldb = D; g.C = s.dQK; g.ldc = D; g.accumulate = 1;
+        g.M = RH; g.N = D; g.K = s.n;
+        CHROMO_TRY(gemm_launch(g, true, false, 1, c.st));
+    }
+    {   // dQ[r, h] = W_k[h] dQK[(r,h), :]
+        GemmArgs g = gemm_args();
+        g.A = s.dQK; g.lda = s.H * D; g.sA2 = D;
+        g.B = s.w_k; g.ldb = D; g.sB2 = (long long)dh * D;
+        g.C = s.dQ; g.ldc = s.dm; g.sC2 = dh;
+        g.M = s.rows; g.N = dh; g.K = D; g.zdiv = s.H;
+        CHROMO_TRY(gemm_launch(g, true, true, s.H, c.st));
+    }
+    {   // dW_k[h] += Q[:, h]^T dQK[(:,h), :]
+        GemmArgs g = gemm_args();
+        g.A = s.q; g.lda = s.dm; g.sA2 = dh;
+        g.B = s.dQK; g.ldb = s.H * D; g.sB2 = D;
+        g.C = s.g_wk; g.ldc = D; g.sC2 = (long long)dh * D;
+        g.M = dh; g.N = D; g.K = s.rows; g.zdiv = s.H; g.accumulate = 1; g.ksplit = ksplit_for(s.rows);
+        CHROMO_TRY(gemm_launch(g, false, false, s.H, c.st));
+    }
+    return CHROMO_OK;
+}
+
+}  // namespace
+
+static int backward_impl(const chromo_config_t* c, const float* P, const chromo_batch_t* in, const float* dlogits,
+                         float* G, float* ws, const WsLayout& w, cudaStream_t st) {
+    const ParamLayout& L = get_layout(c);
+    const int B = w.B, I = w.I, S = w.S, R = w.R, T = w.T, D = w.D, F = c->n_feats, NR = c->n_res;
+    const long long RS = w.res_stride;
+    const int dme = c->embed_d_model, He = c->embed_heads, dffe = c->embed_d_ff;
+    const int dmp = c->pw_d_model, Hp = c->pw_heads, dffp = c->pw_d_ff;
+    const int dmr = c->reg_d_model, Hr = c->reg_heads, dffr = c->reg_d_ff;
+    Ctx cx{st, NR};
+
+    // ---- gradient scratch ---------------------------------------------------
+    int64_t cur = w.g_base;
+    auto take = [&](int64_t n) { int64_t o = cur; cur = align4(cur + n); return o; };
+    const int64_t blk0 = cur;
+    const int64_t o_gR = take((int64_t)T * D), o_dFr = take((int64_t)T * dffr), o_dAtt = take((int64_t)T * dmr),
+                  o_dProj = take((int64_t)T * 4 * dmr);
+    const int64_t o_gP = take((int64_t)R * D), o_dFp = take((int64_t)R * dffp), o_dAvp = take((int64_t)R * dmp),
+                  o_dQp = take((int64_t)R * dmp), o_dCbP = take((int64_t)R * Hp * D),
+                  o_dQKp = take((int64_t)R * Hp * D), o_dU8p = take((int64_t)R * Hp * 8),
+                  o_dPP = take((int64_t)B * D);
+    const int64_t o_gE = take((int64_t)B * D), o_dFe = take((int64_t)B * dffe), o_dAve = take((int64_t)B * dme),
+                  o_dQe = take((int64_t)B * dme), o_dCbE = take((int64_t)B * He * D),
+                  o_dQKe = take((int64_t)B * He * D), o_dU8e = take((int64_t)B * He * 8);
+    const long long GS = cur - blk0;
+    cur = blk0 + GS * NR;
+    int64_t o_dSp[CHROMO_MAX_RES], o_dSe[CHROMO_MAX_RES];
+    for (int r = 0; r < NR; ++r) {
+        o_dSp[r] = take((int64_t)R * Hp * c->n_bins[r]);
+        o_dSe[r] = take((int64_t)B * He * c->n_bins[r]);
+    }
+    const int64_t o_dz = take((int64_t)B * NR * D), o_dh1 = take((int64_t)B * c->d_head);
+    if (cur > w.total) { set_error("internal: backward scratch exceeds workspace"); return CHROMO_ENOMEM; }
+
+    // ---- head (net.py:377-380) ------------------------------------------------
+    {
+        Ctx c1{st, 1};
+        const int dh = c->d_head, no = c->n_out;
+        CHROMO_TRY(bwd_weight(c1, dlogits, no, 0, ws + w.h_h1, dh, 1, 0, G + L.fc2w, dh, 0, B, no, dh, 1));
+        CHROMO_TRY(bwd_bias(c1, dlogits, no, 0, G + L.fc2b, 0, B, no, 1));
+        CHROMO_TRY(bwd_data(c1, dlogits, no, 0, P + L.fc2w, 0, ws + o_dh1, dh, 0, B, no, dh, false, 1));
+        CHROMO_TRY(relu_bwd(c1, ws + o_dh1, 0, ws + w.h_h1, 0, (long long)B * dh, 1));
+        CHROMO_TRY(bwd_weight(c1, ws + o_dh1, dh, 0, ws + w.h_z, NR * D, 1, 0, G + L.fc0w, NR * D, 0, B, dh, NR * D, 1));
+        CHROMO_TRY(bwd_bias(c1, ws + o_dh1, dh, 0, G + L.fc0b, 0, B, dh, 1));
+        CHROMO_TRY(bwd_data(c1, ws + o_dh1, dh, 0, P + L.fc0w, 0, ws + o_dz, NR * D, 0, B, dh, NR * D, false, 1));
+        head_scatter_kernel<<<dim3((unsigned)(((long long)T * D + 255) / 256), NR), 256, 0, st>>>(
+            ws + o_gR, GS, ws + o_dz, B, S, D, NR);
+        CHROMO_CHECK_LAUNCH("head_scatter");
+    }
+
+    // ---- Regulation transformer ------------------------------------------------
+    float* gR = ws + o_gR;
+    for (int l = c->reg_layers - 1; l >= 0; --l) {
+        const AttnOff& ra = L.reg[0].att[l];
+        const FfnOff& rf = L.reg[0].ffn[l];
+        const long long so = (long long)w.rslot(l) * w.r_slot;
+        const float* xin = l == 0 ? ws + w.r_xin : ws + w.r_out + (long long)w.rslot(l - 1) * w.r_slot;
+        CHROMO_TRY(ffn_bwd(cx, P, G, rf, L.reg_stride, dffr, ws + w.r_u + so, ws + w.r_f + so, ws + w.r_preY + so, RS,
+                           gR, ws + o_dFr, GS, T));
+        CHROMO_TRY(ln_bwd(cx, ws + w.r_preU + so, RS, gR, GS, P + ra.lnw, G + ra.lnw, G + ra.lnb, L.reg_stride, T, NR));
+        CHROMO_TRY(bwd_weight(cx, gR, D, GS, ws + w.r_att + so, dmr, 1, RS, G + ra.ffw, dmr, L.reg_stride, T, D, dmr, NR));
+        CHROMO_TRY(bwd_bias(cx, gR, D, GS, G + ra.ffb, L.reg_stride, T, D, NR));
+        CHROMO_TRY(bwd_data(cx, gR, D, GS, P + ra.ffw, L.reg_stride, ws + o_dAtt, dmr, GS, T, D, dmr, false, NR));
+        {
+            RegAttnBwdArgs a;
+            a.B = B; a.S = S; a.H = Hr;
+            a.proj = ws + w.r_proj + so; a.proj_z = RS;
+            a.prob = ws + w.r_prob + so; a.prob_z = RS;
+            a.dout = ws + o_dAtt; a.dout_z = GS;
+            a.dproj = ws + o_dProj; a.dproj_z = GS;
+            a.freq = in->freq;
+            for (int r = 0; r < NR; ++r) a.imask[r] = in->imask[r];
+            a.dgamma_f = G + ra.gamma_f; a.dgamma_z = L.reg_stride;
+            dim3 grid((unsigned)(((long long)B * Hr + 7) / 8), NR);
+            if (S <= 9) reg_attention_bwd_kernel<9><<<grid, 256, 0, st>>>(a);
+            else reg_attention_bwd_kernel<17><<<grid, 256, 0, st>>>(a);
+            CHROMO_CHECK_LAUNCH("reg_attention_bwd");
+        }
+        CHROMO_TRY(bwd_weight(cx, ws + o_dProj, 4 * dmr, GS, xin, D, 1, RS, G + ra.att, D, L.reg_stride, T, 4 * dmr, D, NR));
+        CHROMO_TRY(bwd_data(cx, ws + o_dProj, 4 * dmr, GS, P + ra.att, L.reg_stride, gR, D, GS, T, 4 * dmr, D, true, NR));
+    }
+    // gR is now dX_in (without the residual of net.py:378)
+    head_residual_kernel<<<dim3((B * D + 255) / 256, NR), 256, 0, st>>>(gR, GS, ws + o_dz, B, S, D, NR);
+    CHROMO_CHECK_LAUNCH("head_residual");
+
+    // ---- Pairwise Interaction transformer ---------------------------------------
+    float* gP = ws + o_gP;
+    gather_rows_kernel<<<dim3((unsigned)(((long long)R * 32 + 255) / 256), NR), 256, 0, st>>>(gP, GS, gR, GS, R, I, S, 1);
+    CHROMO_CHECK_LAUNCH("gather_pairwise");
+    for (int l = c->pw_layers - 1; l >= 0; --l) {
+        const AttnOff& pa = L.pw[0].att[l];
+        const FfnOff& pf = L.pw[0].ffn[l];
+        const long long so = (long long)w.pslot(l) * w.p_slot;
+        const float* pin = l == 0 ? ws + w.p_pp : ws + w.p_out + (long long)w.pslot(l - 1) * w.p_slot;
+        const int pin_div = l == 0 ? I : 1;
+        CHROMO_TRY(ffn_bwd(cx, P, G, pf, L.pw_stride, dffp, ws + w.p_u + so, ws + w.p_f + so, ws + w.p_preY + so, RS,
+                           gP, ws + o_dFp, GS, R));
+        CHROMO_TRY(ln_bwd(cx, ws + w.p_preU + so, RS, gP, GS, P + pa.lnw, G + pa.lnw, G + pa.lnb, L.pw_stride, R, NR));
+        CHROMO_TRY(bwd_weight(cx, gP, D, GS, ws + w.p_av + so, dmp, 1, RS, G + pa.ffw, dmp, L.pw_stride, R, D, dmp, NR));
+        CHROMO_TRY(bwd_bias(cx, gP, D, GS, G + pa.ffb, L.pw_stride, R, D, NR));
+        CHROMO_TRY(bwd_data(cx, gP, D, GS, P + pa.ffw, L.pw_stride, ws + o_dAvp, dmp, GS, R, D, dmp, false, NR));
+        for (int r = 0; r < NR; ++r) {
+            SqaBwd s;
+            s.rows = R; s.H = Hp; s.dm = dmp; s.D = D; s.n = c->n_bins[r]; s.F = F;
+            s.q = ws + r * RS + w.p_q + so; s.qk = ws + r * RS + w.p_qk + so;
+            s.P = ws + w.p_p[r] + (long long)w.pslot(l) * w.p_p_slot[r];
+            s.xbar = ws + r * RS + w.p_xbar + so; s.cbar = ws + r * RS + w.p_cbar + so;
+            const int64_t catt = L.pw[r].att[l].c_att;
+            s.w_k = P + catt; s.w_v = P + catt + (long long)dmp * D; s.w_in = P + L.pw[r].lin_proj_pcre;
+            s.pe = in->pos_enc[r]; s.x = in->x_pcre[r];
+            s.mask = in->mask_pcre[r]; s.mask_stride = in->mask_pcre_stride[r];
+            s.mask_row_offset = in->mask_pcre_row_offset[r];
+            s.g_wk = G + catt; s.g_wv = G + catt + (long long)dmp * D; s.g_win = G + L.pw[r].lin_proj_pcre;
+            s.dAv = ws + r * GS + o_dAvp; s.dQ = ws + r * GS + o_dQp;
+            s.dCbar = ws + r * GS + o_dCbP; s.dQK = ws + r * GS + o_dQKp; s.dU8 = ws + r * GS + o_dU8p;
+            s.dS = ws + o_dSp[r];
+            CHROMO_TRY(sqa_bwd(cx, s));
+        }
+        CHROMO_TRY(bwd_weight(cx, ws + o_dQp, dmp, GS, pin, D, pin_div, RS, G + pa.p_att, D, L.pw_stride, R, dmp, D, NR));
+        CHROMO_TRY(bwd_data(cx, ws + o_dQp, dmp, GS, P + pa.p_att, L.pw_stride, gP, D, GS, R, dmp, D, true, NR));
+    }
+    // gP = dP_0 per (gene, slot); P_0 = PP[gene] for every slot (net.py:114-118)
+    slot_sum_kernel<<<dim3((unsigned)(((long long)B * 32 + 255) / 256), NR), 256, 0, st>>>(ws + o_dPP, GS, gP, GS, B, I);
+    CHROMO_CHECK_LAUNCH("slot_sum");
+    CHROMO_TRY(bwd_weight(cx, ws + o_dPP, D, GS, ws + w.r_xin, S * D, 1, RS, G + L.pw[0].lin_proj_p, D, L.pw_stride, B, D, D, NR));
+    {   // dX_in[b, 0, :] += dPP W_lpp
+        GemmArgs g = gemm_args();
+        g.A = ws + o_dPP; g.lda = D; g.sA1 = GS;
+        g.B = P + L.pw[0].lin_proj_p; g.ldb = D; g.sB1 = L.pw_stride;
+        g.C = gR; g.ldc = D; g.sC1 = GS; g.c_div = 1; g.c_mul = S; g.c_add = 0; g.accumulate = 1;
+        g.M = B; g.N = D; g.K = D;
+        CHROMO_TRY(gemm_launch(g, true, false, NR, st));
+    }
+
+    // ---- Embedding transformer ----------------------------------------------------
+    float* gE = ws + o_gE;
+    gather_rows_kernel<<<dim3((unsigned)(((long long)B * 32 + 255) / 256), NR), 256, 0, st>>>(gE, GS, gR, GS, B, 1, S, 0);
+    CHROMO_CHECK_LAUNCH("gather_embed");
+    {
+        const AttnOff& ea = L.embed[0].att[0];
+        const FfnOff& ef = L.embed[0].ffn[0];
+        CHROMO_TRY(ffn_bwd(cx, P, G, ef, L.embed_stride, dffe, ws + w.e_u, ws + w.e_f, ws + w.e_preY, RS, gE,
+                           ws + o_dFe, GS, B));
+        CHROMO_TRY(ln_bwd(cx, ws + w.e_preU, RS, gE, GS, P + ea.lnw, G + ea.lnw, G + ea.lnb, L.embed_stride, B, NR));
+        CHROMO_TRY(bwd_weight(cx, gE, D, GS, ws + w.e_av, dme, 1, RS, G + ea.ffw, dme, L.embed_stride, B, D, dme, NR));
+        CHROMO_TRY(bwd_bias(cx, gE, D, GS, G + ea.ffb, L.embed_stride, B, D, NR));
+        CHROMO_TRY(bwd_data(cx, gE, D, GS, P + ea.ffw, L.embed_stride, ws + o_dAve, dme, GS, B, D, dme, false, NR));
+        for (int r = 0; r < NR; ++r) {
+            SqaBwd s;
+            s.rows = B; s.H = He; s.dm = dme; s.D = D; s.n = c->n_bins[r]; s.F = F;
+            s.q = ws + r * RS + w.e_q; s.qk = ws + r * RS + w.e_qk; s.P = ws + w.e_p[r];
+            s.xbar = ws + r * RS + w.e_xbar; s.cbar = ws + r * RS + w.e_cbar;
+            const int64_t att = L.embed[r].att[0].att;
+            s.w_k = P + att + (long long)dme * D; s.w_v = P + att + (long long)2 * dme * D;
+            s.w_in = P + L.embed[r].lin_proj;
+            s.pe = in->pos_enc[r]; s.x = in->x_p[r];
+            s.mask = in->mask_p[r]; s.mask_stride = in->mask_p_stride[r]; s.mask_row_offset = in->mask_p_row_offset[r];
+            s.g_wk = G + att + (long long)dme * D; s.g_wv = G + att + (long long)2 * dme * D;
+            s.g_win = G + L.embed[r].lin_proj;
+            s.dAv = ws + r * GS + o_dAve; s.dQ = ws + r * GS + o_dQe;
+            s.dCbar = ws + r * GS + o_dCbE; s.dQK = ws + r * GS + o_dQKe; s.dU8 = ws + r * GS + o_dU8e;
+            s.dS = ws + o_dSe[r];
+            CHROMO_TRY(sqa_bwd(cx, s));
+        }
+        // W_q is rows [0, dme) of att.weight
+        CHROMO_TRY(bwd_weight(cx, ws + o_dQe, dme, GS, ws + w.e_hc, D, 1, RS, G + ea.att, D, L.embed_stride, B, dme, D, NR));
+        CHROMO_TRY(bwd_data(cx, ws + o_dQe, dme, GS, P + ea.att, L.embed_stride, gE, D, GS, B, dme, D, true, NR));
+        // gE = dHc;  Hc = W_lp x_c + PE_c  ->  dW_lp += dHc^T x_p[:, c, :]
+        for (int r = 0; r < NR; ++r) {
+            const int n = c->n_bins[r];
+            Ctx c1{st, 1};
+            CHROMO_TRY(bwd_weight(c1, gE + r * GS, D, 0, in->x_p[r] + (long long)(n / 2) * F, n * F, 1, 0,
+                                  G + L.embed[r].lin_proj, F, 0, B, D, F, 1));
+        }
+    }
+    return CHROMO_OK;
+}
+
+}  // namespace chromo
+
 using namespace chromo;
+
 extern "C" int chromo_backward(const chromo_config_t* cfg, const float* params, const chromo_batch_t* in,
                                const float* dlogits, float* grads, float* workspace, int64_t workspace_floats,
                                int32_t flags, void* stream) {
-    (void)cfg; (void)params; (void)in; (void)dlogits; (void)grads; (void)workspace; (void)workspace_floats;
-    (void)flags; (void)stream;
-    set_error("chromo_backward: not implemented yet");
-    return CHROMO_EINVAL;
+    CHROMO_TRY(validate_config(cfg));
+    if (!params || !in || !dlogits || !grads || !workspace) { set_error("null pointer argument"); return CHROMO_EINVAL; }
+    if (!(flags & CHROMO_F_TRAINING)) { set_error("chromo_backward needs the CHROMO_F_TRAINING workspace"); return CHROMO_EINVAL; }
+    if (in->batch < 1) { set_error("batch must be >= 1"); return CHROMO_EINVAL; }
+    WsLayout w = make_ws_layout(cfg, in->batch, flags);
+    if (workspace_floats < w.total) {
+        set_error("workspace too small: need %lld floats, got %lld", (long long)w.total, (long long)workspace_floats);
+        return CHROMO_ENOMEM;
+    }
+    return backward_impl(cfg, params, in, dlogits, grads, workspace, w, (cudaStream_t)stream);
 }

@@ -12,6 +12,8 @@
 // blockIdx.z enumerates (z1, z2, ksplit) with two-level strides so that one
 // launch covers e.g. all resolutions x all heads.
 #pragma once
+#include <string.h>
+
 #include "common.cuh"
 
 namespace chromo {
@@ -25,6 +27,7 @@ struct GemmArgs {
     int zdiv;                                  // z = z1 * zdiv + z2
     long long sA1, sA2, sB1, sB2, sC1, sC2;
     int a_div;                                 // A row broadcast (>=1)
+    int b_div;                                 // B k-index broadcast when !B_KC (>=1)
     int epi;
     const float* bias; long long sBias1, sBias2;
     const float* res; int ldres; int res_div; long long sRes1;
@@ -39,7 +42,7 @@ struct GemmArgs {
 static inline GemmArgs gemm_args() {
     GemmArgs g;
     memset(&g, 0, sizeof(g));
-    g.zdiv = 1; g.a_div = 1; g.res_div = 1; g.c_div = 1; g.c_mul = 1; g.c_add = 0;
+    g.zdiv = 1; g.a_div = 1; g.b_div = 1; g.res_div = 1; g.c_div = 1; g.c_mul = 1; g.c_add = 0;
     g.alpha = 1.f; g.ksplit = 1;
     return g;
 }
@@ -80,7 +83,7 @@ __device__ __forceinline__ void gemm_load_tile(float (*S)[BD + GEMM_PAD], const 
             const int gk = k0 + k, gd = d0 + dq;
             float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gk < kend && gd < Dmax) {
-                const float* p = src + (long long)gk * ld + gd;
+                const float* p = src + (long long)(gk / div) * ld + gd;
                 if (gd + 3 < Dmax && ((reinterpret_cast<uintptr_t>(p) & 15) == 0)) {
                     val = *reinterpret_cast<const float4*>(p);
                 } else {
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_simt_kernel(const GemmArgs 
 
     for (int k0 = kbeg; k0 < kend; k0 += GEMM_BK) {
         gemm_load_tile<BM, A_KC>(As, A, g.lda, m0, g.M, k0, kend, A_KC ? g.a_div : 1, tid);
-        gemm_load_tile<BN, B_KC>(Bs, B, g.ldb, n0, g.N, k0, kend, 1, tid);
+        gemm_load_tile<BN, B_KC>(Bs, B, g.ldb, n0, g.N, k0, kend, B_KC ? 1 : g.b_div, tid);
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < GEMM_BK; ++kk) {

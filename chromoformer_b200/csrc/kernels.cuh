@@ -42,6 +42,30 @@ struct HeadGatherArgs {
     float* z;
 };
 
+struct RegAttnBwdArgs {
+    int B, S, H;
+    const float* proj; long long proj_z;
+    const float* prob; long long prob_z;
+    const float* dout; long long dout_z;
+    float* dproj; long long dproj_z;
+    const float* freq;
+    const uint8_t* imask[CHROMO_MAX_RES];
+    float* dgamma_f; long long dgamma_z;
+};
+
+struct AttnRowsBwdArgs {
+    int rows, H, n, F, D;
+    const float* P;       // [rows, n] probabilities
+    float* dS;            // [rows, n] in: dCbar . PE_j, out: d(pre-scale score)
+    const float* dcbar;   // [rows, D]
+    const float* x;       // [regions, n, F]
+    const uint8_t* mask; long long mask_stride, mask_row_offset;
+    const float* w_in;    // [D, F]
+    float scale;
+    float* dU8;           // [rows, 8]
+    float* dqk;           // [rows, D] <- W_in dU
+};
+
 // single-query attention block (forward)
 struct SqaArgs {
     int rows, H, dm, D, n, F;

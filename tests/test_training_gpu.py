@@ -1,0 +1,150 @@
+"""GPU parity of the hand-written backward + fused AdamW (train.py:182-196) against the oracle's
+autograd and the reference-generated training goldens.  Tolerance: per-tensor max-abs error
+<= 2e-4 of that tensor's max-abs gradient (FP32, re-associated sums and atomics)."""
+import numpy as np
+import pytest
+import torch
+
+from _util import KWS, golden
+from chromoformer_b200 import ChromoformerClassifier, ChromoformerRegressor, synthetic
+from chromoformer_b200.optim import FusedAdamW
+from oracle import chromoformer_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+REL = 2e-4
+
+
+def _mk(cls, seed=123):
+    return cls(7, 128, 128, dict(KWS[0]), dict(KWS[1]), dict(KWS[2]), seed=seed)
+
+
+def _check_grads(model, grads_o, rel=REL):
+    worst = ("", 0.0)
+    for name, p in model.named_parameters():
+        g = grads_o[name]
+        if g is None:
+            assert p.grad is None, f"{name} must not receive a gradient (SURVEY A.4)"
+            continue
+        assert p.grad is not None, name
+        scale = max(g.abs().max().item(), 1e-7)
+        err = (p.grad.cpu() - g).abs().max().item() / scale
+        if err > worst[1]:
+            worst = (name, err)
+    assert worst[1] < rel, worst
+    return worst
+
+
+@pytest.mark.parametrize("tag,ragged,i_max,n", [("reg", True, 8, 6), ("clf", False, 8, 3), ("reg", True, 16, 2)])
+def test_gradients_vs_oracle(tag, ragged, i_max, n):
+    cls = ChromoformerRegressor if tag == "reg" else ChromoformerClassifier
+    model = _mk(cls, seed=11)
+    sd = {k: v.detach().clone() for k, v in model.named_parameters()}
+    batch = synthetic.make_batch(n, i_max=i_max, ragged=ragged, full_masks=True, seed=21, stress=True)
+    target = batch["labels_reg"].view(-1, 1) if tag == "reg" else batch["labels_clf"]
+    loss_o, logits_o, grads_o = oracle.forward_backward(sd, synthetic.forward_args(batch), target, tag == "reg")
+    model.cuda().train()
+    out = model(*synthetic.forward_args(batch, "cuda"))
+    crit = torch.nn.MSELoss() if tag == "reg" else torch.nn.CrossEntropyLoss()
+    loss = crit(out, target.cuda())
+    loss.backward()
+    assert (out.detach().cpu() - logits_o).abs().max().item() < 5e-5
+    assert abs(loss.item() - loss_o.item()) < 1e-5
+    _check_grads(model, grads_o)
+
+
+def test_gradient_accumulation_and_zero_grad():
+    model = _mk(ChromoformerRegressor, seed=3).cuda().train()
+    b1 = synthetic.make_batch(3, ragged=True, seed=1)
+    b2 = synthetic.make_batch(5, ragged=True, seed=2)
+
+    def run(b):
+        out = model(*synthetic.forward_args(b, "cuda"))
+        torch.nn.functional.mse_loss(out, b["labels_reg"].view(-1, 1).cuda()).backward()
+
+    run(b1)
+    g1 = model.flat_grads.clone()
+    model.zero_grad(set_to_none=True)
+    run(b2)
+    g2 = model.flat_grads.clone()
+    model.zero_grad(set_to_none=True)
+    run(b1); run(b2)                     # accumulate
+    both = model.flat_grads.clone()
+    assert torch.allclose(both, g1 + g2, rtol=1e-4, atol=1e-7)
+    model.zero_grad(set_to_none=False)   # zero in place
+    run(b1)
+    assert torch.allclose(model.flat_grads, g1, rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("tag", ["reg", "clf"])
+def test_training_goldens_with_fused_adamw(tag):
+    """Three optimisation steps reproduce the unmodified reference (tests/golden/train_golden.npz)."""
+    g = golden("train_golden.npz")
+    batch = synthetic.make_batch(6, ragged=True, full_masks=True, seed=7)
+    chk = np.array([batch["pcre_feats"][100].double().sum().item(), batch["interaction_freq"].double().sum().item(),
+                    float(batch["n_partners"].sum())])
+    if not np.allclose(chk, g["input_checksum"], rtol=0, atol=1e-9):
+        pytest.skip("torch RNG stream differs from the fixture's")
+    cls = ChromoformerRegressor if tag == "reg" else ChromoformerClassifier
+    model = _mk(cls).cuda().train()
+    names = [n for n, _ in model.named_parameters()]
+    assert names == list(g["param_names"])
+    opt = FusedAdamW(model, lr=3e-5)
+    opt.zero_grad(); opt.step()                       # train.py:160-161: a step before any gradient exists
+    crit = torch.nn.MSELoss() if tag == "reg" else torch.nn.CrossEntropyLoss()
+    target = (batch["labels_reg"].view(-1, 1) if tag == "reg" else batch["labels_clf"]).cuda()
+    args = synthetic.forward_args(batch, "cuda")
+    for step in range(3):
+        opt.zero_grad()
+        out = model(*args)
+        loss = crit(out, target)
+        loss.backward()
+        assert abs(loss.item() - g[f"{tag}_losses"][step]) < 5e-6, (step, loss.item())
+        if step == 0:
+            assert np.abs(out.detach().cpu().numpy() - g[f"{tag}_logits"]).max() < 5e-5
+            has = np.array([p.grad is not None for p in model.parameters()])
+            assert (has == g[f"{tag}_has_grad"]).all()
+            gn = np.array([0.0 if p.grad is None else p.grad.double().norm().item() for p in model.parameters()])
+            assert np.allclose(gn, g[f"{tag}_grad_norm"], rtol=5e-4, atol=1e-9)
+            params = dict(model.named_parameters())
+            for key in g.files:
+                if key.startswith(f"{tag}_grad::"):
+                    ref = g[key]
+                    got = params[key.split("::")[1]].grad.cpu().numpy()
+                    assert np.abs(got - ref).max() <= REL * max(1e-6, np.abs(ref).max()), key
+        opt.step()
+    ps = np.array([p.detach().double().sum().item() for p in model.parameters()])
+    assert np.allclose(ps, g[f"{tag}_param_sum_after3"], rtol=0, atol=5e-5)
+    params = dict(model.named_parameters())
+    for key in ("fc_head.0.bias", "embed.100.lin_proj.weight"):
+        assert np.abs(params[key].detach().cpu().numpy() - g[f"{tag}_param_after3::{key}"]).max() < 2e-7
+    # stock state_dict layout: 334 entries {step, exp_avg, exp_avg_sq}, one param group
+    sd = opt.state_dict()
+    assert len(sd["state"]) == 334 and len(sd["param_groups"]) == 1
+    st = next(iter(sd["state"].values()))
+    assert set(st) == {"step", "exp_avg", "exp_avg_sq"} and float(st["step"]) == 3.0
+
+
+def test_stock_torch_adamw_and_steplr_run_unchanged():
+    """train.py:157-158,196,344 with the stock optimiser: identical trajectory to FusedAdamW."""
+    batch = synthetic.make_batch(4, ragged=True, seed=5)
+    args = synthetic.forward_args(batch, "cuda")
+    target = batch["labels_clf"].cuda()
+    finals = []
+    for fused in (False, True):
+        model = _mk(ChromoformerClassifier, seed=42).cuda().train()
+        opt = FusedAdamW(model, lr=3e-5) if fused else torch.optim.AdamW(model.parameters(), lr=3e-5)
+        sched = torch.optim.lr_scheduler.StepLR(opt, step_size=1, gamma=0.87)
+        opt.zero_grad(); opt.step()
+        for _ in range(3):
+            opt.zero_grad()
+            loss = torch.nn.functional.cross_entropy(model(*args), target)
+            loss.backward()
+            opt.step()
+            sched.step()
+        finals.append(model.flat_params.clone())
+        assert abs(opt.param_groups[0]["lr"] - 3e-5 * 0.87 ** 3) < 1e-12
+    assert (finals[0] - finals[1]).abs().max().item() < 2e-7
+    # the 36 grad-less tensors are bit-identical to their initial values
+    fresh = _mk(ChromoformerClassifier, seed=42)
+    tail = slice(fresh.n_active, None)
+    assert torch.equal(finals[1][tail].cpu(), fresh.flat_params[tail])
