@@ -1,0 +1,298 @@
+#!/usr/bin/env python
+"""Headline benchmark (BASELINE.json): Chromoformer-clf default config, inference over 18,955
+synthetic genes per GPU (configs[1]); genes/s, weak scaling over N GPUs with no collective.
+
+    python bench.py [--gpus N --steps K --warmup W] [--mode infer|train] [--impl reference]
+
+One JSON line on rank 0.  A "step" is one full sweep of the hot path over this rank's 18,955
+genes.  `value` = genes of all ranks / max-over-ranks device time with inputs resident in HBM;
+`e2e` = the same sweep through the public host API (pinned host buffers, H2D + D2H inside the
+timed region).  `roofline` is for the dominant kernel (the batched dense projection of the
+Regulation stack) timed alone with CUDA events; `cpu_baseline` / `--impl reference` time the
+CPU oracle (a port of the reference's PyTorch-eager algorithm as written) on the host cores.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_GENES = 18955
+KWS = ({"n_layers": 1, "n_heads": 2, "d_model": 128, "d_ff": 128},
+       {"n_layers": 2, "n_heads": 2, "d_model": 128, "d_ff": 256},
+       {"n_layers": 6, "n_heads": 8, "d_model": 256, "d_ff": 256})
+BINS = (2000, 500, 100)
+REF_FLOPS_PER_GENE = 3862328832          # as-written forward, SURVEY §8d tier A
+
+
+def executed_flops_per_gene(i_max=8, n_bins=(20, 80, 400), F=7, D=128):
+    """FLOPs (2 x MAC) per gene of the formulation forward.cu actually executes."""
+    e, p, r = KWS
+    S = i_max + 1
+    mac = 0
+    for n in n_bins:
+        He, dme, dffe = e["n_heads"], D, e["d_ff"]
+        sqa = lambda H, dm: dm * D + H * n * D + H * (2 * n * F + 2 * D * F) + H * n * D + dm * D
+        mac += F * D + D * dme + sqa(He, dme) + dme * D + 2 * D * dffe                      # embedding, 1 row
+        Hp, dmp, dffp = p["n_heads"], p["d_model"], p["d_ff"]
+        mac += D * D + p["n_layers"] * i_max * (D * dmp + sqa(Hp, dmp) + dmp * D + 2 * D * dffp)
+        Hr, dmr, dffr = r["n_heads"], r["d_model"], r["d_ff"]
+        mac += r["n_layers"] * (S * (4 * dmr * D + dmr * D + 2 * D * dffr) + Hr * S * S * 32 * 2)
+    mac += len(n_bins) * D * 128 + 128 * 2
+    return 2 * mac
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_model(cls, seed=123):
+    return cls(7, 128, 128, dict(KWS[0]), dict(KWS[1]), dict(KWS[2]), seed=seed)
+
+
+# ------------------------------------------------------------------------------- CPU arm
+def cpu_oracle_genes_per_s(n_sample, iters, threads):
+    """Reference algorithm as written (oracle port) on the host cores, bounded sample."""
+    import torch
+    from chromoformer_b200 import ChromoformerClassifier, synthetic
+    from oracle import chromoformer_oracle as oracle
+    torch.set_num_threads(threads)
+    model = make_model(ChromoformerClassifier)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = synthetic.make_batch(n_sample, ragged=False, full_masks=True, seed=0)
+    args = synthetic.forward_args(batch)
+    with torch.no_grad():
+        oracle.chromoformer_forward(sd, *args)                    # warm-up
+        t0 = time.perf_counter()
+        for _ in range(iters):
+            oracle.chromoformer_forward(sd, *args)
+        dt = time.perf_counter() - t0
+    return n_sample * iters / dt, dt / iters
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_sample = 32
+    # W warm-ups + K steps of a bounded sample, capped to stay within a few minutes
+    _, per = cpu_oracle_genes_per_s(n_sample, 1, threads)
+    iters = max(1, min(args.steps, int(60.0 / max(per, 1e-3))))
+    gps, per = cpu_oracle_genes_per_s(n_sample, iters, threads)
+    line = {"impl": "reference", "metric": "genes/sec inference", "value": gps, "unit": "genes/s",
+            "n_gpus": args.gpus, "steps": iters, "warmup": 1, "ms_per_step": per * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
+            "config": workload_config(args),
+            "cpu_baseline": {"value": gps, "unit": "genes/s", "cores": threads, "kind": "port",
+                             "sample": f"{n_sample} dense synthetic genes x {iters} passes of the as-written forward "
+                                       "(oracle/chromoformer_oracle.py, torch CPU FP32)"},
+            "e2e": {"value": gps, "unit": "genes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": "Chromoformer-clf default config (i_max=8, binsizes 2000/500/100, 7 marks) inference over "
+                        "18,955 synthetic genes per GPU", "genes_per_gpu": N_GENES, "chunk": args.chunk,
+            "i_max": 8, "l2_policy": "inputs (2.5 GB/GPU) larger than L2; no flush needed",
+            "precision": args.precision}
+
+
+# ------------------------------------------------------------------------------- GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--mode", choices=["infer", "train"], default="infer")
+    ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
+    ap.add_argument("--chunk", type=int, default=4096)
+    ap.add_argument("--precision", choices=["fp32", "bf16"], default="fp32")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from chromoformer_b200 import ChromoformerClassifier, ChromoformerRegressor, _lib, synthetic
+    from chromoformer_b200.engine import InferenceEngine, batch_nbytes, pin_batch
+    from chromoformer_b200.trainer import TrainStep
+
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    peaks = load_peaks()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1)) / steps
+
+    # ---------------- inference: device-resident sweep ----------------------------------
+    model = make_model(ChromoformerClassifier).cuda().eval()
+    model.precision = args.precision
+    host = synthetic.make_batch(N_GENES, ragged=False, seed=rank)        # dense: k = 8, full-length pCREs
+    eng = InferenceEngine(model, chunk=args.chunk)
+    resident = eng.to_device(host)
+    out = torch.empty(N_GENES, 2, device=dev)
+    sampler = ClockSampler(local)
+    eng.predict_device(resident, out)                                       # first touch / workspace allocation
+    torch.cuda.synchronize()
+    lib.chromo_launch_counter(1)
+    eng.predict_device(resident, out)
+    launches_per_step = int(lib.chromo_launch_counter(1))
+    if rank == 0:
+        sampler.start()
+    ms = timed(lambda: eng.predict_device(resident, out), args.steps, args.warmup)
+    clocks = sampler.stop() if rank == 0 else None
+    genes_per_s = world * N_GENES / (ms * 1e-3)
+
+    # ---------------- inference: end-to-end through the host API ---------------------------
+    pinned = pin_batch(host)
+    h2d = batch_nbytes(pinned)
+    ms_e2e = timed(lambda: eng.predict_host(pinned), max(2, args.steps // 2), 3)
+    e2e = {"value": world * N_GENES / (ms_e2e * 1e-3), "unit": "genes/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": N_GENES * 2 * 4, "ms_per_step": ms_e2e}
+
+    # ---------------- dominant kernel alone: Regulation fused projection -------------------
+    T = args.chunk * 9
+    x = torch.randn(3, T, 128, device=dev)
+    wgt = torch.randn(3, 1024, 128, device=dev)
+    y = torch.empty(3, T, 1024, device=dev)
+    st = torch.cuda.current_stream().cuda_stream
+    flags = _lib.F_BF16 if args.precision == "bf16" else 0
+
+    def one_linear():
+        _lib.check(lib.chromo_linear(x.data_ptr(), wgt.data_ptr(), None, y.data_ptr(), T, 1024, 128, 0, 3,
+                                     T * 128, 1024 * 128, 0, T * 1024, flags, st), "chromo_linear")
+    ms_k = timed(one_linear, 20, 5)
+    flops_k = 2.0 * 3 * T * 1024 * 128
+    ach = flops_k / (ms_k * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "gemm_simt_kernel<64,64> as launched for regulation.*.self_att.att "
+                                             f"(M={T}, N=1024, K=128, 3 resolutions)",
+                "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
+                "traffic": None, "peak_source": peaks["source"] + " burst (kernel timed alone)",
+                "ms_per_launch": ms_k,
+                "whole_forward": {"executed_flops_per_gene": executed_flops_per_gene(),
+                                  "achieved_tflops": executed_flops_per_gene() * genes_per_s / world / 1e12,
+                                  "reference_equivalent_tflops": REF_FLOPS_PER_GENE * genes_per_s / world / 1e12,
+                                  "algorithmic_bytes_per_gene": 126000 + 4500 + 324 * 4,
+                                  "achieved_gbs": (126000 + 4500 + 1296) * genes_per_s / world / 1e9,
+                                  "hbm_peak_gbs": peaks["hbm_gbs"]}}
+
+    # ---------------- training step (configs[2]): fwd + bwd + AdamW, DP all-reduce ----------
+    train = None
+    if not args.no_train:
+        reg = make_model(ChromoformerRegressor).cuda().train()
+        reg.precision = args.precision
+        tb = synthetic.make_batch(64, ragged=False, seed=100 + rank)
+        tdev = {k: ({b: t.to(dev) for b, t in v.items()} if isinstance(v, dict) else v.to(dev)) for k, v in tb.items()}
+        target = tdev["labels_reg"].view(-1, 1)
+        step = TrainStep(reg, lr=3e-5, regression=True)
+        lib.chromo_launch_counter(1)
+        step(tdev, target)
+        train_launches = int(lib.chromo_launch_counter(1))
+        ms_t = timed(lambda: step(tdev, target), 20, 5)
+        train = {"metric": "train samples/sec", "value": world * 64 / (ms_t * 1e-3), "unit": "samples/s",
+                 "ms_per_step": ms_t, "per_gpu_batch": 64, "model": "Chromoformer-reg", "gpu_launches": train_launches,
+                 "collective": "nccl all_reduce of %d fp32 grads" % reg.n_active if world > 1 else "none (1 GPU)",
+                 "loss": float(step.loss.item())}
+
+    # ---------------- CPU baseline (rank 0, N = 1 only) -------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        gps, per = cpu_oracle_genes_per_s(32, 1, threads)
+        iters = max(1, min(8, int(15.0 / max(per, 1e-3))))
+        gps, per = cpu_oracle_genes_per_s(32, iters, threads)
+        cpu = {"value": gps, "unit": "genes/s", "cores": threads, "kind": "port",
+               "sample": f"32 dense synthetic genes x {iters} passes of the as-written forward (oracle port, torch CPU FP32)"}
+
+    if rank == 0:
+        line = {"metric": "genes/sec inference", "value": genes_per_s, "unit": "genes/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+                "config": workload_config(args), "clocks": clocks, "e2e": e2e,
+                "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+                "roofline": roofline, "cpu_baseline": cpu, "train": train}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

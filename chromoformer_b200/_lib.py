@@ -69,6 +69,9 @@ EXPORTS = {
     "chromo_workspace_floats": (c_int64, [POINTER(Config), c_int32, c_int32]),
     "chromo_forward": (c_int32, [POINTER(Config), c_void_p, POINTER(Batch), c_void_p, c_void_p, c_int64,
                                  c_int32, c_void_p]),
+    "chromo_linear": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p]),
+    "chromo_launch_counter": (c_int64, [c_int32]),
     "chromo_backward": (c_int32, [POINTER(Config), c_void_p, POINTER(Batch), c_void_p, c_void_p, c_void_p,
                                   c_int64, c_int32, c_void_p]),
     "chromo_mse_loss": (c_int32, [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_void_p]),

@@ -12,8 +12,10 @@ namespace chromo {
 
 // ---------------------------------------------------------------- errors ----
 void set_error(const char* fmt, ...);
+void count_launch();
 #define CHROMO_CHECK_LAUNCH(what)                                              \
     do {                                                                       \
+        chromo::count_launch();                                                \
         cudaError_t e__ = cudaGetLastError();                                  \
         if (e__ != cudaSuccess) {                                              \
             chromo::set_error("%s: %s", what, cudaGetErrorString(e__));        \

@@ -536,3 +536,18 @@ extern "C" int chromo_forward(const chromo_config_t* cfg, const float* params, c
     }
     return forward_impl(cfg, params, in, logits, workspace, w, flags, (cudaStream_t)stream);
 }
+
+extern "C" int chromo_linear(const float* x, const float* w, const float* bias, float* y, int32_t m, int32_t n,
+                             int32_t k, int32_t relu, int32_t batches, int64_t x_stride, int64_t w_stride,
+                             int64_t bias_stride, int64_t y_stride, int32_t flags, void* stream) {
+    if (!x || !w || !y || m < 1 || n < 1 || k < 1 || batches < 1) { set_error("chromo_linear: bad argument"); return CHROMO_EINVAL; }
+    GemmArgs g = gemm_args();
+    g.A = x; g.lda = k; g.sA1 = x_stride;
+    g.B = w; g.ldb = k; g.sB1 = w_stride;
+    g.C = y; g.ldc = n; g.sC1 = y_stride;
+    g.M = m; g.N = n; g.K = k;
+    g.bias = bias; g.sBias1 = bias_stride;
+    g.epi = relu ? EPI_BIAS_RELU : (bias ? EPI_BIAS : EPI_PLAIN);
+    (void)flags;
+    return gemm_launch(g, true, true, batches, (cudaStream_t)stream);
+}

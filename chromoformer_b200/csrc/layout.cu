@@ -2,12 +2,14 @@
 #include <stdarg.h>
 #include <string.h>
 
+#include <atomic>
 #include <map>
 #include <mutex>
 
 #include "common.cuh"
 
 namespace chromo {
+long long launch_counter(bool reset);
 
 static thread_local char g_err[512] = "";
 void set_error(const char* fmt, ...) {
@@ -16,6 +18,10 @@ void set_error(const char* fmt, ...) {
     vsnprintf(g_err, sizeof(g_err), fmt, ap);
     va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+long long launch_counter(bool reset) { return reset ? g_launches.exchange(0) : g_launches.load(); }
 
 int validate_config(const chromo_config_t* c) {
     if (!c) { set_error("null config"); return CHROMO_EINVAL; }
@@ -259,6 +265,7 @@ using namespace chromo;
 extern "C" {
 
 int chromo_abi_version(void) { return CHROMO_ABI_VERSION; }
+int64_t chromo_launch_counter(int32_t reset) { return chromo::launch_counter(reset != 0); }
 const char* chromo_last_error(void) { return g_err; }
 
 int64_t chromo_param_total(const chromo_config_t* cfg) {

@@ -483,6 +483,7 @@ class Chromoformer(_ChromoformerCore):
                  w_max=40000):
         super().__init__()
         torch.manual_seed(seed)
+        self.binsizes = list(self._BINS)
         for b in self._BINS:
             setattr(self, f"embed{b}", EmbeddingTransformer(n_feats, embed_n_layers, embed_n_heads,
                                                             embed_d_model, embed_d_ff))

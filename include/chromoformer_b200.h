@@ -98,6 +98,17 @@ int chromo_forward(const chromo_config_t* cfg, const float* params, const chromo
                    float* logits /* [B,n_out] */, float* workspace, int64_t workspace_floats,
                    int32_t flags, void* stream);
 
+/* ---- one dense layer: nn.Linear (+ReLU) as at modules.py:38,100,159-160, net.py:326-330 --
+ * y[z] = act(x[z] W[z]^T + b[z]) for z < batches; x [m,k], W [n,k], y [m,n] row-major.
+ * The same kernel the forward uses for every projection; exposed so that a single
+ * contraction can be tested and timed in isolation.                                    */
+int chromo_linear(const float* x, const float* w, const float* bias, float* y, int32_t m, int32_t n,
+                  int32_t k, int32_t relu, int32_t batches, int64_t x_stride, int64_t w_stride,
+                  int64_t bias_stride, int64_t y_stride, int32_t flags, void* stream);
+
+/* Number of kernel launches issued by this library since the last reset (process-wide). */
+int64_t chromo_launch_counter(int32_t reset);
+
 /* ---- backward: autograd of the same graph (train.py:195) ------------------
  * `workspace` must be the buffer a CHROMO_F_TRAINING forward of the same batch
  * filled.  grads ([chromo_param_total] floats) is ACCUMULATED into (+=).       */
