@@ -13,6 +13,7 @@ MAX_RES = 4
 MAX_LAYERS = 8
 F_TRAINING = 1
 F_BF16 = 2
+F_PACKED = 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libchromo_b200.so")
@@ -71,6 +72,7 @@ EXPORTS = {
                                  c_int32, c_void_p]),
     "chromo_linear": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                 c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p]),
+    "chromo_pack_linear_weight": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p]),
     "chromo_launch_counter": (c_int64, [c_int32]),
     "chromo_backward": (c_int32, [POINTER(Config), c_void_p, POINTER(Batch), c_void_p, c_void_p, c_void_p,
                                   c_int64, c_int32, c_void_p]),

@@ -88,6 +88,8 @@ struct WsLayout {
     int64_t p_p_slot[CHROMO_MAX_RES];
     // head
     int64_t h_z, h_h1;
+    // BF16 tensor path: packed parameter mirror + packed position tables (float offsets)
+    int64_t bf_params, bf_pe[CHROMO_MAX_RES], bf_pet[CHROMO_MAX_RES];
     // backward scratch (training only)
     int64_t g_base;
     int64_t total;

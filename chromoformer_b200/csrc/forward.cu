@@ -18,6 +18,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "kernels.cuh"
+#include "umma_gemm.cuh"
 
 namespace chromo {
 
@@ -230,7 +231,8 @@ int single_query_attention(const SqaArgs& s, cudaStream_t st) {
         g.B = s.pe; g.ldb = D;
         g.C = s.P; g.ldc = s.n;
         g.M = s.rows * s.H; g.N = s.n; g.K = D;
-        CHROMO_TRY(gemm_launch(g, true, true, 1, st));
+        if (s.pe_pk && g.M >= 64 && s.n % 16 == 0 && umma_supported(g)) CHROMO_TRY(umma_launch(g, s.pe_pk, 1, st));
+        else CHROMO_TRY(gemm_launch(g, true, true, 1, st));
     }
     {
         AttnRowsArgs a;
@@ -248,7 +250,8 @@ int single_query_attention(const SqaArgs& s, cudaStream_t st) {
         g.B = s.pe; g.ldb = D;
         g.C = s.cbar; g.ldc = D; g.accumulate = 1;
         g.M = s.rows * s.H; g.N = D; g.K = s.n;
-        CHROMO_TRY(gemm_launch(g, true, false, 1, st));
+        if (s.pet_pk && g.M >= 64 && s.n % 16 == 0 && umma_supported(g)) CHROMO_TRY(umma_launch(g, s.pet_pk, 1, st));
+        else CHROMO_TRY(gemm_launch(g, true, false, 1, st));
     }
     // Av[row, h*dh + e] = W_v[h*dh + e, :] . Cbar[(row,h), :]               (NT GEMM per head)
     {
@@ -262,6 +265,52 @@ int single_query_attention(const SqaArgs& s, cudaStream_t st) {
     return CHROMO_OK;
 }
 
+// BF16 mirror of every weight the tcgen05 engine consumes, in UMMA tile order, at the same
+// element offsets as the FP32 parameters; plus the position table as a weight ([n,D]) and
+// transposed ([D,n]) for the two shared-operand GEMMs of the single-query attention.
+static int pack_all_weights(const chromo_config_t* c, const ParamLayout& L, const float* P, __nv_bfloat16* packed,
+                            float* ws, const WsLayout& w, const chromo_batch_t* in, cudaStream_t st) {
+    const int D = c->d_emb, NR = c->n_res;
+    auto pk = [&](int64_t off, int N, int K, long long zs, int nz) -> int {
+        const int nt = umma_tile_n(N);
+        if (nt == 0 || K % 16 != 0) return CHROMO_OK;        // this weight stays on the FP32 path
+        return pack_weights(P + off, packed + off, N, K, nt, zs, nz, false, K, st);
+    };
+    const AttnOff& ea = L.embed[0].att[0];
+    const FfnOff& ef = L.embed[0].ffn[0];
+    CHROMO_TRY(pk(ea.att, c->embed_d_model, D, L.embed_stride, NR));          // W_q rows only
+    CHROMO_TRY(pk(ea.ffw, D, c->embed_d_model, L.embed_stride, NR));
+    CHROMO_TRY(pk(ef.l1w, c->embed_d_ff, D, L.embed_stride, NR));
+    CHROMO_TRY(pk(ef.l2w, D, c->embed_d_ff, L.embed_stride, NR));
+    CHROMO_TRY(pk(L.pw[0].lin_proj_p, D, D, L.pw_stride, NR));
+    for (int l = 0; l < c->pw_layers; ++l) {
+        const AttnOff& a = L.pw[0].att[l];
+        const FfnOff& f = L.pw[0].ffn[l];
+        CHROMO_TRY(pk(a.p_att, c->pw_d_model, D, L.pw_stride, NR));
+        CHROMO_TRY(pk(a.ffw, D, c->pw_d_model, L.pw_stride, NR));
+        CHROMO_TRY(pk(f.l1w, c->pw_d_ff, D, L.pw_stride, NR));
+        CHROMO_TRY(pk(f.l2w, D, c->pw_d_ff, L.pw_stride, NR));
+    }
+    for (int l = 0; l < c->reg_layers; ++l) {
+        const AttnOff& a = L.reg[0].att[l];
+        const FfnOff& f = L.reg[0].ffn[l];
+        CHROMO_TRY(pk(a.att, 4 * c->reg_d_model, D, L.reg_stride, NR));
+        CHROMO_TRY(pk(a.ffw, D, c->reg_d_model, L.reg_stride, NR));
+        CHROMO_TRY(pk(f.l1w, c->reg_d_ff, D, L.reg_stride, NR));
+        CHROMO_TRY(pk(f.l2w, D, c->reg_d_ff, L.reg_stride, NR));
+    }
+    CHROMO_TRY(pk(L.fc0w, c->d_head, NR * D, 0, 1));
+    for (int r = 0; r < NR; ++r) {
+        const int n = c->n_bins[r];
+        if (n % 16 != 0) continue;
+        CHROMO_TRY(pack_weights(in->pos_enc[r], reinterpret_cast<__nv_bfloat16*>(ws + w.bf_pe[r]), n, D,
+                                umma_tile_n(n), 0, 1, false, D, st));
+        CHROMO_TRY(pack_weights(in->pos_enc[r], reinterpret_cast<__nv_bfloat16*>(ws + w.bf_pet[r]), D, n,
+                                umma_tile_n(D), 0, 1, true, D, st));
+    }
+    return CHROMO_OK;
+}
+
 static int forward_impl(const chromo_config_t* c, const float* P, const chromo_batch_t* in, float* logits,
                         float* ws, const WsLayout& w, int flags, cudaStream_t st) {
     const ParamLayout& L = get_layout(c);
@@ -269,6 +318,15 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     const int NR = c->n_res;
     const bool train = w.training;
     const long long RS = w.res_stride;
+    const bool bf16 = (flags & CHROMO_F_BF16) != 0;
+    __nv_bfloat16* packed = bf16 ? reinterpret_cast<__nv_bfloat16*>(ws + w.bf_params) : nullptr;
+    // Dense projection: tcgen05 BF16 engine when requested and the shape qualifies, FP32 SIMT otherwise.
+    auto lin = [&](const GemmArgs& g, int nz) -> int {
+        if (bf16 && g.M >= 64 && g.B >= P && g.B < P + L.total && umma_supported(g))
+            return umma_launch(g, packed + (g.B - P), nz, st);
+        return gemm_launch(g, true, true, nz, st);
+    };
+    if (bf16 && !(flags & CHROMO_F_PACKED)) CHROMO_TRY(pack_all_weights(c, L, P, packed, ws, w, in, st));
 
     // ---------------- Embedding transformer, centre query (net.py:31-59) ----
     {
@@ -290,7 +348,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         g.B = P + ea.att; g.ldb = D; g.sB1 = L.embed_stride;
         g.C = ws + w.e_q; g.ldc = dme; g.sC1 = RS;
         g.M = B; g.N = dme; g.K = D;
-        CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+        CHROMO_TRY(lin(g, NR));
     }
     for (int r = 0; r < NR; ++r) {
         SqaArgs s;
@@ -302,6 +360,8 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         s.pe = in->pos_enc[r];
         s.x = in->x_p[r];
         s.mask = in->mask_p[r]; s.mask_stride = in->mask_p_stride[r]; s.mask_row_offset = in->mask_p_row_offset[r];
+        s.pe_pk = bf16 ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pe[r]) : nullptr;
+        s.pet_pk = bf16 ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pet[r]) : nullptr;
         s.qk = ws + r * RS + w.e_qk; s.P = ws + w.e_p[r]; s.xbar = ws + r * RS + w.e_xbar;
         s.cbar = ws + r * RS + w.e_cbar; s.av = ws + r * RS + w.e_av;
         CHROMO_TRY(single_query_attention(s, st));
@@ -316,7 +376,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         g.res = ws + w.e_hc; g.ldres = D; g.sRes1 = RS;
         g.gamma = P + ea.lnw; g.beta = P + ea.lnb; g.sLn1 = L.embed_stride;
         if (train) { g.pre = ws + w.e_preU; g.sPre1 = RS; }
-        CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+        CHROMO_TRY(lin(g, NR));
     }
     {   // F = relu(U W_1^T + b_1)                                modules.py:100-101
         GemmArgs g = gemm_args();
@@ -325,7 +385,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         g.C = ws + w.e_f; g.ldc = c->embed_d_ff; g.sC1 = RS;
         g.M = B; g.N = c->embed_d_ff; g.K = D;
         g.epi = EPI_BIAS_RELU; g.bias = P + ef.l1b; g.sBias1 = L.embed_stride;
-        CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+        CHROMO_TRY(lin(g, NR));
     }
     {   // Y = LN(U + F W_2^T + b_2) -> X_in[b, 0, :]              net.py:359-368
         GemmArgs g = gemm_args();
@@ -337,7 +397,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         g.res = ws + w.e_u; g.ldres = D; g.sRes1 = RS;
         g.gamma = P + ef.lnw; g.beta = P + ef.lnb; g.sLn1 = L.embed_stride;
         if (train) { g.pre = ws + w.e_preY; g.sPre1 = RS; }
-        CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+        CHROMO_TRY(lin(g, NR));
     }
 
     // ---------------- Pairwise Interaction transformer (net.py:105-139) -----
@@ -348,7 +408,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         g.B = P + L.pw[0].lin_proj_p; g.ldb = D; g.sB1 = L.pw_stride;
         g.C = ws + w.p_pp; g.ldc = D; g.sC1 = RS;
         g.M = B; g.N = D; g.K = D;
-        CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+        CHROMO_TRY(lin(g, NR));
     }
     for (int l = 0; l < c->pw_layers; ++l) {
         const AttnOff& pa = L.pw[0].att[l];
@@ -363,7 +423,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.B = P + pa.p_att; g.ldb = D; g.sB1 = L.pw_stride;
             g.C = ws + w.p_q + so; g.ldc = dmp; g.sC1 = RS;
             g.M = R; g.N = dmp; g.K = D;
-            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+            CHROMO_TRY(lin(g, NR));
         }
         for (int r = 0; r < NR; ++r) {
             SqaArgs s;
@@ -376,6 +436,8 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             s.x = in->x_pcre[r];
             s.mask = in->mask_pcre[r]; s.mask_stride = in->mask_pcre_stride[r];
             s.mask_row_offset = in->mask_pcre_row_offset[r];
+            s.pe_pk = bf16 ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pe[r]) : nullptr;
+            s.pet_pk = bf16 ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pet[r]) : nullptr;
             s.qk = ws + r * RS + w.p_qk + so;
             s.P = ws + w.p_p[r] + (long long)w.pslot(l) * w.p_p_slot[r];
             s.xbar = ws + r * RS + w.p_xbar + so;
@@ -392,7 +454,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.res = pin; g.ldres = D; g.res_div = pin_div; g.sRes1 = RS;
             g.gamma = P + pa.lnw; g.beta = P + pa.lnb; g.sLn1 = L.pw_stride;
             if (train) { g.pre = ws + w.p_preU + so; g.sPre1 = RS; }
-            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+            CHROMO_TRY(lin(g, NR));
         }
         {
             GemmArgs g = gemm_args();
@@ -401,7 +463,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.C = ws + w.p_f + so; g.ldc = c->pw_d_ff; g.sC1 = RS;
             g.M = R; g.N = c->pw_d_ff; g.K = D;
             g.epi = EPI_BIAS_RELU; g.bias = P + pf.l1b; g.sBias1 = L.pw_stride;
-            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+            CHROMO_TRY(lin(g, NR));
         }
         {   // P_{l+1} = LN(U + F W_2^T + b_2); the last layer lands in X_in[b, 1+i, :]
             GemmArgs g = gemm_args();
@@ -415,7 +477,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.res = ws + w.p_u + so; g.ldres = D; g.sRes1 = RS;
             g.gamma = P + pf.lnw; g.beta = P + pf.lnb; g.sLn1 = L.pw_stride;
             if (train) { g.pre = ws + w.p_preY + so; g.sPre1 = RS; }
-            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+            CHROMO_TRY(lin(g, NR));
         }
     }
 
@@ -432,7 +494,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.B = P + ra.att; g.ldb = D; g.sB1 = L.reg_stride;
             g.C = ws + w.r_proj + so; g.ldc = 4 * dmr; g.sC1 = RS;
             g.M = T; g.N = 4 * dmr; g.K = D;
-            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+            CHROMO_TRY(lin(g, NR));
         }
         {
             RegAttnArgs a;
@@ -455,7 +517,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.res = xin; g.ldres = D; g.sRes1 = RS;
             g.gamma = P + ra.lnw; g.beta = P + ra.lnb; g.sLn1 = L.reg_stride;
             if (train) { g.pre = ws + w.r_preU + so; g.sPre1 = RS; }
-            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+            CHROMO_TRY(lin(g, NR));
         }
         {
             GemmArgs g = gemm_args();
@@ -464,7 +526,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.C = ws + w.r_f + so; g.ldc = c->reg_d_ff; g.sC1 = RS;
             g.M = T; g.N = c->reg_d_ff; g.K = D;
             g.epi = EPI_BIAS_RELU; g.bias = P + rf.l1b; g.sBias1 = L.reg_stride;
-            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+            CHROMO_TRY(lin(g, NR));
         }
         {
             GemmArgs g = gemm_args();
@@ -476,7 +538,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.res = ws + w.r_u + so; g.ldres = D; g.sRes1 = RS;
             g.gamma = P + rf.lnw; g.beta = P + rf.lnb; g.sLn1 = L.reg_stride;
             if (train) { g.pre = ws + w.r_preY + so; g.sPre1 = RS; }
-            CHROMO_TRY(gemm_launch(g, true, true, NR, st));
+            CHROMO_TRY(lin(g, NR));
         }
     }
 
@@ -496,7 +558,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         g.C = ws + w.h_h1; g.ldc = c->d_head;
         g.M = B; g.N = c->d_head; g.K = NR * D;
         g.epi = EPI_BIAS_RELU; g.bias = P + L.fc0b;
-        CHROMO_TRY(gemm_launch(g, true, true, 1, st));
+        CHROMO_TRY(lin(g, 1));
     }
     {
         GemmArgs g = gemm_args();
@@ -505,7 +567,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         g.C = logits; g.ldc = c->n_out;
         g.M = B; g.N = c->n_out; g.K = c->d_head;
         g.epi = EPI_BIAS; g.bias = P + L.fc2b;
-        CHROMO_TRY(gemm_launch(g, true, true, 1, st));
+        CHROMO_TRY(lin(g, 1));
     }
     (void)flags;
     return CHROMO_OK;
@@ -548,6 +610,17 @@ extern "C" int chromo_linear(const float* x, const float* w, const float* bias, 
     g.M = m; g.N = n; g.K = k;
     g.bias = bias; g.sBias1 = bias_stride;
     g.epi = relu ? EPI_BIAS_RELU : (bias ? EPI_BIAS : EPI_PLAIN);
-    (void)flags;
+    if (flags & CHROMO_F_BF16) {
+        if (!umma_supported(g)) { set_error("chromo_linear: shape not supported by the BF16 tensor path"); return CHROMO_EINVAL; }
+        return umma_launch(g, reinterpret_cast<const __nv_bfloat16*>(w), batches, (cudaStream_t)stream);
+    }
     return gemm_launch(g, true, true, batches, (cudaStream_t)stream);
+}
+
+extern "C" int chromo_pack_linear_weight(const float* w, uint16_t* packed, int32_t n, int32_t k, int32_t batches,
+                                         int64_t w_stride, void* stream) {
+    if (!w || !packed || n < 1 || k < 1 || batches < 1) { set_error("chromo_pack_linear_weight: bad argument"); return CHROMO_EINVAL; }
+    const int nt = umma_tile_n(n);
+    if (nt == 0 || k % 16 != 0) { set_error("chromo_pack_linear_weight: n must be a multiple of 16 with a tile <= 256, k a multiple of 16"); return CHROMO_EINVAL; }
+    return pack_weights(w, reinterpret_cast<__nv_bfloat16*>(packed), n, k, nt, w_stride, batches, false, k, (cudaStream_t)stream);
 }

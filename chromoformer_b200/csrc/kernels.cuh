@@ -1,5 +1,7 @@
 // Argument blocks of the non-GEMM kernels (passed by value).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace chromo {
@@ -76,6 +78,8 @@ struct SqaArgs {
     const float* x;                 // [rows, n, F]
     const uint8_t* mask; long long mask_stride, mask_row_offset;
     float* qk; float* P; float* xbar; float* cbar; float* av;
+    const __nv_bfloat16* pe_pk = nullptr;   // BF16 tensor path: PE packed as a [n,D] weight
+    const __nv_bfloat16* pet_pk = nullptr;  //                   PE^T packed as a [D,n] weight
 };
 
 int launch_reg_attention(const RegAttnArgs& a, int nz, cudaStream_t st);

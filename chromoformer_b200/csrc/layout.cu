@@ -68,7 +68,7 @@ struct Builder {
         if ((pass == 0) != used) return;
         *slot = cursor;
         L->infos.push_back({name, cursor, numel, used});
-        cursor = align4(cursor + numel);
+        cursor = (cursor + numel + 7) & ~int64_t(7);   // 16-byte aligned in the BF16 mirror too (TMA bulk)
     }
 };
 
@@ -242,6 +242,16 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
     }
     w.h_z = take((int64_t)B * c->n_res * D);
     w.h_h1 = take((int64_t)B * c->d_head);
+    if (flags & CHROMO_F_BF16) {
+        // BF16 mirror of the flat parameters in UMMA tile order (same element offsets) and
+        // the packed position tables (PE [n,D] as a weight, and its transpose).
+        w.bf_params = take((get_layout(c).total + 1) / 2 + 8);
+        for (int r = 0; r < c->n_res; ++r) {
+            const int64_t n16 = (c->n_bins[r] + 15) / 16 * 16;
+            w.bf_pe[r] = take((n16 * D + 1) / 2 + 8);
+            w.bf_pet[r] = take((n16 * D + 1) / 2 + 8);
+        }
+    }
     w.g_base = cur;
     if (w.training) {
         // backward scratch: generous bound, carved up in backward.cu

@@ -1,0 +1,366 @@
+// BF16 tensor-core engine for the dense projections (sm_100a: tcgen05 + TMEM + TMA bulk).
+//
+//   C[z][row(m), n] = epi( sum_k bf16(A[z][m, k]) * bf16(W[z][n, k]) )      FP32 accumulate
+//
+// * A (activations) stays FP32 in HBM: it is converted to BF16 while being staged into
+//   shared memory in the canonical K-major no-swizzle UMMA layout (8x8 core matrices).
+// * W (nn.Linear weight [N,K]) is pre-packed once per parameter version into that same
+//   layout (pack_weights), so one 1-D TMA bulk copy (cp.async.bulk, mbarrier complete_tx)
+//   brings a whole [NT x K] tile into shared memory.
+// * One CTA = one 128-row M tile x one NT-column N tile: K/16 tcgen05.mma (M=128, N=NT,
+//   K=16) issued by a single thread accumulate into TMEM; tcgen05.commit signals the four
+//   epilogue warps, which read their 32 TMEM lanes with tcgen05.ld and apply the fused
+//   epilogue (bias / ReLU / bias+residual+LayerNorm) straight from registers.
+// K is small (128..400) on this path, so there is no K pipeline inside a CTA; overlap comes
+// from two resident CTAs per SM (A/B staging of one under the MMA/epilogue of the other).
+#include <cuda_bf16.h>
+#include <stdlib.h>
+
+#include "common.cuh"
+#include "gemm_simt.cuh"
+#include "umma_gemm.cuh"
+
+namespace chromo {
+
+// ------------------------------------------------------------------ PTX wrappers ----
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)),
+                 "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// 32 lanes x 32 consecutive FP32 columns -> 32 registers per thread (thread = TMEM lane)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+          "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+          "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, no swizzle: (row r, col k) of a [rows x K] BF16 tile lives at
+//   (r/8) * (K/8) * 128 + (k/8) * 128 + (r%8) * 16 + (k%8) * 2   bytes
+// i.e. [rows/8][K/8] core matrices of 8 rows x 16 bytes.  LBO (K direction) = 128 B,
+// SBO (8-row groups) = K * 16 B.   (cute::UMMA::SmemDescriptor, version 1 = sm_100.)
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= 1ull << 46;     // descriptor version (Blackwell)
+    return d;            // base_offset 0, lbo_mode 0, layout SWIZZLE_NONE (0)
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+    // c=F32 (bits 4-5 = 1), a=b=BF16 (bits 7-9, 10-12 = 1), K-major A and B, N>>3 @17, M>>4 @24
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) |
+           (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// ------------------------------------------------------------------ weight packing --
+// src FP32 [N,K] row-major -> dst BF16, tiles of NT rows, each [NT/8][K/8][8][8].
+__global__ void pack_weights_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int K,
+                                    int NT, long long z_stride, int transposed, int ld_src) {
+    const int z = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one 8-element K chunk
+    const int KC = K / 8;
+    if (i >= (long long)N * KC) return;
+    const int n = (int)(i / KC), kc = (int)(i % KC);
+    const float* s = src + z * z_stride;
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = kc * 8 + j;
+        const float x = transposed ? s[(long long)k * ld_src + n] : s[(long long)n * ld_src + k];
+        v[j] = __float2bfloat16_rn(x);
+    }
+    const int t = n / NT, r = n % NT;
+    const long long off = (long long)t * NT * K + ((long long)(r / 8) * KC + kc) * 64 + (r % 8) * 8;
+    *reinterpret_cast<uint4*>(dst + z * z_stride + off) = *reinterpret_cast<const uint4*>(v);
+}
+
+int pack_weights(const float* src, __nv_bfloat16* dst, int N, int K, int NT, long long z_stride, int nz,
+                 bool transposed, int ld_src, cudaStream_t st) {
+    if (K % 8 != 0 || N % NT != 0 || NT % 8 != 0) { set_error("pack_weights: bad shape"); return CHROMO_EINVAL; }
+    const long long units = (long long)N * (K / 8);
+    pack_weights_kernel<<<dim3((unsigned)((units + 255) / 256), nz), 256, 0, st>>>(src, dst, N, K, NT, z_stride,
+                                                                                    transposed ? 1 : 0, ld_src);
+    CHROMO_CHECK_LAUNCH("pack_weights");
+    return CHROMO_OK;
+}
+
+// ------------------------------------------------------------------ the GEMM kernel --
+constexpr int UM = 128;           // rows per CTA = UMMA M = TMEM lanes
+constexpr int UTHREADS = 128;
+constexpr size_t UMMA_SMEM_MAX = 225 * 1024;   // of the 227 KB a CTA may opt in to
+
+struct UmmaArgs {
+    GemmArgs g;
+    const __nv_bfloat16* Bp;      // packed weights (same z strides as g.B)
+    int NT;                       // N tile (multiple of 16, <= 256, divides N)
+    int tmem_cols;                // power of two >= max(32, NT)
+    int swap_lbo_sbo;             // debug: alternative descriptor convention
+};
+
+__global__ void __launch_bounds__(UTHREADS) umma_linear_kernel(const UmmaArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const GemmArgs& g = a.g;
+    const int K = g.K, NT = a.NT;
+    __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem);
+    __nv_bfloat16* sB = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)UM * K * 2);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)(UM + NT) * K * 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int m0 = blockIdx.y * UM, nt = blockIdx.x, n0 = nt * NT;
+    const int z1 = blockIdx.z / g.zdiv, z2 = blockIdx.z % g.zdiv;
+    const float* A = g.A + z1 * g.sA1 + z2 * g.sA2;
+    const __nv_bfloat16* Bp = a.Bp + z1 * g.sB1 + z2 * g.sB2 + (long long)nt * NT * K;
+    float* C = g.C + z1 * g.sC1 + z2 * g.sC2;
+
+    if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (tid == 0) {   // weights: one TMA bulk copy of the pre-packed [NT x K] tile
+        const uint32_t bytes = (uint32_t)NT * K * 2;
+        mbar_expect_tx(&bars[0], bytes);
+        tma_bulk_g2s(sB, Bp, bytes, &bars[0]);
+    }
+
+    // activations: FP32 -> BF16 into the canonical layout.  A warp covers 8 rows x 32 columns
+    // per step (lane -> row lane/4, 8-column chunk lane%4): 128-byte coalesced global segments,
+    // conflict-free 16-byte shared stores.
+    {
+        const int KC = K / 8;
+        const int units = (UM / 8) * ((KC + 3) / 4);     // (row group, group of 4 chunks)
+        for (int u = warp; u < units; u += UTHREADS / 32) {
+            const int rg = u % (UM / 8), cg = u / (UM / 8);
+            const int r = rg * 8 + (lane >> 2), kc = cg * 4 + (lane & 3);
+            if (kc >= KC) continue;
+            const int m = m0 + r;
+            uint4 packed = make_uint4(0, 0, 0, 0);
+            if (m < g.M) {
+                const float* p = A + (long long)(m / g.a_div) * g.lda + kc * 8;
+                const float4 x0 = *reinterpret_cast<const float4*>(p);
+                const float4 x1 = *reinterpret_cast<const float4*>(p + 4);
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(x0.x, x0.y), b1 = __floats2bfloat162_rn(x0.z, x0.w);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(x1.x, x1.y), b3 = __floats2bfloat162_rn(x1.z, x1.w);
+                packed.x = *reinterpret_cast<uint32_t*>(&b0); packed.y = *reinterpret_cast<uint32_t*>(&b1);
+                packed.z = *reinterpret_cast<uint32_t*>(&b2); packed.w = *reinterpret_cast<uint32_t*>(&b3);
+            }
+            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(sA) + ((size_t)(r >> 3) * KC + kc) * 128 +
+                                      (r & 7) * 16) = packed;
+        }
+    }
+    fence_async_smem();
+    __syncthreads();
+
+    if (tid == 0) {
+        mbar_wait(&bars[0], 0);
+        tc_fence_after();
+        const uint32_t idesc = umma_idesc_bf16(UM, NT);
+        const uint32_t lbo = a.swap_lbo_sbo ? (uint32_t)K * 16 : 128u;
+        const uint32_t sbo = a.swap_lbo_sbo ? 128u : (uint32_t)K * 16;
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        for (int k = 0; k < K / 16; ++k) {
+            const uint64_t ad = umma_smem_desc(a0 + k * 256, lbo, sbo);
+            const uint64_t bd = umma_smem_desc(b0 + k * 256, lbo, sbo);
+            umma_bf16(tmem_base, ad, bd, idesc, k > 0 ? 1u : 0u);
+        }
+        umma_commit(&bars[1]);
+    }
+    __syncwarp();
+    mbar_wait(&bars[1], 0);
+    tc_fence_after();
+
+    // ------------------------------------------------------------------ epilogue ----
+    const int m = m0 + warp * 32 + lane;                 // this thread's row = its TMEM lane
+    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const bool ok = m < g.M;
+    const long long crow = ok ? (long long)(m / g.c_div) * g.c_mul + (m % g.c_div) + g.c_add : 0;
+    const float* bias = g.bias ? g.bias + z1 * g.sBias1 + z2 * g.sBias2 : nullptr;
+    float v[32];
+    if (g.epi == EPI_BIAS_RES_LN) {
+        // N == NT == 128: the thread owns the whole row.  Pass 1: statistics, pass 2: write.
+        const float* res = g.res + z1 * g.sRes1 + (ok ? (long long)(m / g.res_div) * g.ldres : 0);
+        const float* gamma = g.gamma + z1 * g.sLn1;
+        const float* beta = g.beta + z1 * g.sLn1;
+        float* pre = (g.pre && ok) ? g.pre + z1 * g.sPre1 + (long long)m * g.N : nullptr;
+        float sum = 0.f, sq = 0.f;
+        for (int c = 0; c < 128; c += 32) {
+            tmem_ld32(trow + c, v);
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(res + c + j);
+                    const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + c + j) : make_float4(0, 0, 0, 0);
+                    const float t0 = v[j] + b4.x + r4.x, t1 = v[j + 1] + b4.y + r4.y;
+                    const float t2 = v[j + 2] + b4.z + r4.z, t3 = v[j + 3] + b4.w + r4.w;
+                    sum += (t0 + t1) + (t2 + t3);
+                    sq += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
+                    if (pre) *reinterpret_cast<float4*>(pre + c + j) = make_float4(t0, t1, t2, t3);
+                }
+            }
+        }
+        const float mean = sum * (1.f / 128.f);
+        const float var = fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + 1e-5f);
+        for (int c = 0; c < 128; c += 32) {
+            tmem_ld32(trow + c, v);
+            if (ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 r4 = *reinterpret_cast<const float4*>(res + c + j);
+                    const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + c + j) : make_float4(0, 0, 0, 0);
+                    const float4 ga = *reinterpret_cast<const float4*>(gamma + c + j);
+                    const float4 be = *reinterpret_cast<const float4*>(beta + c + j);
+                    float4 o;
+                    o.x = (v[j] + b4.x + r4.x - mean) * rstd * ga.x + be.x;
+                    o.y = (v[j + 1] + b4.y + r4.y - mean) * rstd * ga.y + be.y;
+                    o.z = (v[j + 2] + b4.z + r4.z - mean) * rstd * ga.z + be.z;
+                    o.w = (v[j + 3] + b4.w + r4.w - mean) * rstd * ga.w + be.w;
+                    *reinterpret_cast<float4*>(C + crow * g.ldc + c + j) = o;
+                }
+            }
+        }
+    } else {
+        for (int c = 0; c < NT; c += 32) {
+            tmem_ld32(trow + c, v);          // columns beyond NT (NT % 32 != 0) are ignored below
+            if (!ok) continue;
+            float* out = C + crow * g.ldc + n0 + c;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                if (c + j >= NT) break;
+                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                if (g.epi != EPI_PLAIN && bias) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + c + j);
+                    o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+                }
+                if (g.epi == EPI_BIAS_RELU) {
+                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+                }
+                if (g.accumulate) {
+                    const float4 old = *reinterpret_cast<const float4*>(out + j);
+                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                }
+                *reinterpret_cast<float4*>(out + j) = o;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+static int choose_nt(int N) {
+    if (N % 16 != 0) return 0;
+    if (N <= 256) return N;
+    for (int nt = 256; nt >= 16; nt -= 16)
+        if (N % nt == 0) return nt;
+    return 0;
+}
+
+int umma_tile_n(int N) { return choose_nt(N); }
+
+bool umma_supported(const GemmArgs& g) {
+    if (g.K % 16 != 0 || g.K < 16 || g.ksplit != 1) return false;
+    const int nt = choose_nt(g.N);
+    if (nt == 0) return false;
+    if ((size_t)(UM + nt) * g.K * 2 + 64 > UMMA_SMEM_MAX) return false;
+    if (g.lda % 4 != 0 || g.ldc % 4 != 0) return false;
+    if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.C) & 15)) return false;
+    if (g.epi == EPI_BIAS_RES_LN && (g.N != 128 || g.accumulate)) return false;
+    return true;
+}
+
+int umma_launch(const GemmArgs& g, const __nv_bfloat16* Bp, int nz, cudaStream_t st) {
+    static int swap = -1;
+    if (swap < 0) {
+        const char* e = getenv("CHROMO_UMMA_SWAP");
+        swap = (e && e[0] == '1') ? 1 : 0;
+    }
+    UmmaArgs a;
+    a.g = g; a.Bp = Bp; a.NT = choose_nt(g.N);
+    a.tmem_cols = 32;
+    while (a.tmem_cols < a.NT) a.tmem_cols *= 2;
+    a.swap_lbo_sbo = swap;
+    const size_t smem = (size_t)(UM + a.NT) * g.K * 2 + 64;
+    static size_t configured = 0;
+    if (smem > configured) {
+        cudaError_t e = cudaFuncSetAttribute(umma_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX);
+        if (e != cudaSuccess) { set_error("umma smem attribute: %s", cudaGetErrorString(e)); return CHROMO_ECUDA; }
+        configured = UMMA_SMEM_MAX;
+    }
+    dim3 grid(g.N / a.NT, (g.M + UM - 1) / UM, nz);
+    umma_linear_kernel<<<grid, UTHREADS, smem, st>>>(a);
+    CHROMO_CHECK_LAUNCH("umma_linear");
+    return CHROMO_OK;
+}
+
+}  // namespace chromo

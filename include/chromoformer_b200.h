@@ -38,6 +38,9 @@ extern "C" {
 #define CHROMO_F_TRAINING 1   /* keep every activation the backward needs   */
 #define CHROMO_F_BF16 2       /* dense projections on tcgen05 (BF16 operands,
                                  FP32 accumulate); default is strict FP32   */
+#define CHROMO_F_PACKED 4     /* with CHROMO_F_BF16: the workspace already holds
+                                 the packed BF16 weights of THESE parameters
+                                 (left there by a previous call) - skip packing */
 
 /* Hyper-parameters: the config.yaml schema of chromoformer/configs/default.yaml:11-32
  * plus the number of bins per resolution (w_max // binsize, data.py:140).     */
@@ -105,6 +108,10 @@ int chromo_forward(const chromo_config_t* cfg, const float* params, const chromo
 int chromo_linear(const float* x, const float* w, const float* bias, float* y, int32_t m, int32_t n,
                   int32_t k, int32_t relu, int32_t batches, int64_t x_stride, int64_t w_stride,
                   int64_t bias_stride, int64_t y_stride, int32_t flags, void* stream);
+/* With CHROMO_F_BF16, `w` of chromo_linear must point at weights packed by this call
+ * (BF16, UMMA K-major core-matrix tiles; n*k elements per batch, same strides in elements). */
+int chromo_pack_linear_weight(const float* w, uint16_t* packed, int32_t n, int32_t k, int32_t batches,
+                              int64_t w_stride, void* stream);
 
 /* Number of kernel launches issued by this library since the last reset (process-wide). */
 int64_t chromo_launch_counter(int32_t reset);
