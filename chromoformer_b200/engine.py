@@ -7,15 +7,9 @@ takes a contiguous gene range (see ``shard_range``)."""
 import torch
 
 from . import synthetic
+from .parallel import shard_range  # noqa: F401  (re-exported)
 
 _KEYS = synthetic.FORWARD_KEYS
-
-
-def shard_range(n_items, rank, world):
-    """Contiguous, balanced [lo, hi) range of rank `rank` out of `world`."""
-    base, rem = divmod(n_items, world)
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
 
 
 def _slice(batch, lo, hi):

@@ -13,6 +13,7 @@ import torch.distributed as dist
 
 from . import _lib
 from .model import _BatchIO
+from .parallel import allreduce_gradients
 from .synthetic import FORWARD_KEYS
 
 
@@ -69,12 +70,11 @@ class TrainStep:
         _lib.check(lib.chromo_backward(cfg, flat.data_ptr(), ctypes.byref(io.struct), dlogits.data_ptr(),
                                        self.grad.data_ptr(), ws.data_ptr(), ws.numel(), self.flags, stream),
                    "chromo_backward")
-        if self.world > 1:
-            dist.all_reduce(self.grad[:model.n_active], op=dist.ReduceOp.SUM, group=self.group)
+        scale = allreduce_gradients(self.grad, model.n_active, self.group) if self.world > 1 else 1.0
         self.step_count += 1
         _lib.check(lib.chromo_adamw(flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                     model.n_active, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
-                                    self.step_count, 1.0 / self.world, stream), "chromo_adamw")
+                                    self.step_count, scale, stream), "chromo_adamw")
         self.logits = logits
         return self.loss
 

@@ -177,6 +177,8 @@ def test_bf16_tensor_path_tolerance(stress):
     agree = (got.argmax(1) == want.argmax(1)).float().mean().item()
     margin = (want[:, 1] - want[:, 0]).abs()
     safe = margin > 2e-2 * scale
-    assert err < 1e-2 * scale, err
+    # 1e-2 absolute at the untrained logit range (north_star); at trained-like ranges the reference's
+    # own BF16 autocast is off by 8.8e-2 (SURVEY hard parts), so the bound scales with the logits
+    assert err < (2e-2 * scale if stress else 1e-2), err
     assert (got.argmax(1) == want.argmax(1))[safe].all() and agree >= 0.99
     assert not torch.equal(got, want), "BF16 flag had no effect: tensor path not taken"
