@@ -122,65 +122,108 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(AttnRowsArgs a) {
     }
 }
 
-// Regulation self-attention (modules.py:37-46,58-82): one warp per (gene, head),
-// lane = channel within the 32-wide head.  proj = [q | k | v | gate].
-template <int SMAX>
-__global__ void __launch_bounds__(256) reg_attention_kernel(RegAttnArgs a) {
-    const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int warps_per_block = blockDim.x >> 5;
-    const long long gw = (long long)blockIdx.x * warps_per_block + warp_in_block;
-    const int z = blockIdx.y;
-    const int S = a.S, H = a.H, dm = 32 * H;
-    if (gw >= (long long)a.B * H) return;
-    const int b = (int)(gw / H), h = (int)(gw % H);
-    const float* proj = a.proj + z * a.proj_zstride + (long long)b * S * 4 * dm;
-    float q[SMAX], k[SMAX], v[SMAX], gt[SMAX];
-#pragma unroll
-    for (int i = 0; i < SMAX; ++i) {
-        if (i < S) {
-            const float* row = proj + (long long)i * 4 * dm + h * 32 + lane;
-            q[i] = row[0]; k[i] = row[dm]; v[i] = row[2 * dm]; gt[i] = row[3 * dm];
-        } else { q[i] = k[i] = v[i] = gt[i] = 0.f; }
+// Regulation self-attention (modules.py:37-46,58-82): one THREAD per (gene, head, query token).
+// The S threads of a (gene, head) group sit in adjacent lanes, so their K/V loads hit the same
+// addresses (one transaction, broadcast) and nothing is reduced across lanes:
+//   s_j = q.k_j / sqrt(32) + gamma_h * freq[i,j];  masked -> -1e9;  p = softmax_j(s)
+//   out = (sum_j p_j v_j) * sigmoid(gate)
+// proj = [q | k | v | gate] per token, FP32 or BF16 (PT).
+template <typename PT> struct ProjLoad;
+template <> struct ProjLoad<float> {
+    static __device__ __forceinline__ void load8(const float* p, float* v) {
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     }
+};
+template <> struct ProjLoad<__nv_bfloat16> {
+    static __device__ __forceinline__ void load8(const __nv_bfloat16* p, float* v) {
+        const uint4 u = *reinterpret_cast<const uint4*>(p);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            v[2 * k] = __uint_as_float(w[k] << 16);
+            v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+        }
+    }
+};
+
+template <int SMAX, typename PT>
+__global__ void __launch_bounds__(128) reg_attention_kernel(RegAttnArgs a) {
+    const int S = a.S, H = a.H, dm = 32 * H;
+    const int gpw = 32 / S;                                   // (gene, head) groups per warp
+    const int lane = threadIdx.x & 31;
+    const long long warp = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int z = blockIdx.y;
+    const long long grp = warp * gpw + lane / S;
+    const int i = lane % S;
+    if (lane >= gpw * S || grp >= (long long)a.B * H) return;
+    const int b = (int)(grp / H), h = (int)(grp % H);
+    const PT* base = reinterpret_cast<const PT*>(a.proj) + z * a.proj_zstride + (long long)b * S * 4 * dm + h * 32;
+    float q[32];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) ProjLoad<PT>::load8(base + (long long)i * 4 * dm + c * 8, q + c * 8);
     const float gamma = a.gamma_f[z * a.gamma_zstride + h];
-    const float* freq = a.freq + (long long)b * S * S;
-    const uint8_t* mask = a.imask[z] + (long long)b * S * S;
-    float* prob = a.prob ? a.prob + z * a.prob_zstride + ((long long)b * H + h) * S * S : nullptr;
-    float* out = a.out + z * a.out_zstride + (long long)b * S * dm + h * 32 + lane;
+    const float* freq = a.freq + ((long long)b * S + i) * S;
+    const uint8_t* mask = a.imask[z] + ((long long)b * S + i) * S;
     const float scale = 0.17677669529663687f;   // 1/sqrt(32)
+    float s[SMAX];
+    float mx = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < SMAX; ++i) {
-        if (i >= S) break;
-        float s[SMAX];
-        float mx = -INFINITY;
+    for (int j = 0; j < SMAX; ++j) {
+        s[j] = -INFINITY;
+        if (j < S) {
+            const PT* kj = base + (long long)j * 4 * dm + dm;
+            float d0 = 0.f, d1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < SMAX; ++j) {
-            if (j >= S) { s[j] = -INFINITY; continue; }
-            float t = q[i] * k[j];
+            for (int c = 0; c < 4; ++c) {
+                float kv[8];
+                ProjLoad<PT>::load8(kj + c * 8, kv);
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
-            t = t * scale + gamma * freq[i * S + j];
-            if (mask[i * S + j]) t = -1e9f;
+                for (int e = 0; e < 8; e += 2) {
+                    d0 = fmaf(q[c * 8 + e], kv[e], d0);
+                    d1 = fmaf(q[c * 8 + e + 1], kv[e + 1], d1);
+                }
+            }
+            float t = (d0 + d1) * scale + gamma * freq[j];
+            if (mask[j]) t = -1e9f;
             s[j] = t;
             mx = fmaxf(mx, t);
         }
-        float sum = 0.f;
+    }
+    float sum = 0.f;
 #pragma unroll
-        for (int j = 0; j < SMAX; ++j) {
-            if (j < S) { s[j] = expf(s[j] - mx); sum += s[j]; }
-        }
-        const float inv = 1.f / sum;
-        float o = 0.f;
+    for (int j = 0; j < SMAX; ++j)
+        if (j < S) { s[j] = (sizeof(PT) == 4) ? expf(s[j] - mx) : __expf(s[j] - mx); sum += s[j]; }
+    const float inv = 1.f / sum;
+    float o[32];
 #pragma unroll
-        for (int j = 0; j < SMAX; ++j) {
-            if (j < S) {
-                const float p = s[j] * inv;
-                o = fmaf(p, v[j], o);
-                if (prob && lane == 0) prob[i * S + j] = p;
+    for (int d = 0; d < 32; ++d) o[d] = 0.f;
+    float* prob = a.prob ? a.prob + z * a.prob_zstride + (((long long)b * H + h) * S + i) * S : nullptr;
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+        if (j < S) {
+            const float p = s[j] * inv;
+            if (prob) prob[j] = p;
+            const PT* vj = base + (long long)j * 4 * dm + 2 * dm;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float vv[8];
+                ProjLoad<PT>::load8(vj + c * 8, vv);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[c * 8 + e] = fmaf(p, vv[e], o[c * 8 + e]);
             }
         }
-        const float sg = 1.f / (1.f + expf(-gt[i]));
-        out[(long long)i * dm] = o * sg;
+    }
+    float* out = a.out + z * a.out_zstride + ((long long)b * S + i) * dm + h * 32;
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        float gt[8];
+        ProjLoad<PT>::load8(base + (long long)i * 4 * dm + 3 * dm + c * 8, gt);
+        float r[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) r[e] = o[c * 8 + e] / (1.f + ((sizeof(PT) == 4) ? expf(-gt[e]) : __expf(-gt[e])));
+        *reinterpret_cast<float4*>(out + c * 8) = make_float4(r[0], r[1], r[2], r[3]);
+        *reinterpret_cast<float4*>(out + c * 8 + 4) = make_float4(r[4], r[5], r[6], r[7]);
     }
 }
 
@@ -196,10 +239,16 @@ __global__ void head_gather_kernel(HeadGatherArgs a) {
 
 // ------------------------------------------------------------ launchers -----
 int launch_reg_attention(const RegAttnArgs& a, int nz, cudaStream_t st) {
-    const int wpb = 8;
-    dim3 grid((unsigned)(((long long)a.B * a.H + wpb - 1) / wpb), nz);
-    if (a.S <= 9) reg_attention_kernel<9><<<grid, wpb * 32, 0, st>>>(a);
-    else reg_attention_kernel<17><<<grid, wpb * 32, 0, st>>>(a);
+    const int wpb = 4, gpw = 32 / a.S;
+    const long long warps = ((long long)a.B * a.H + gpw - 1) / gpw;
+    dim3 grid((unsigned)((warps + wpb - 1) / wpb), nz);
+    if (a.proj_bf16) {
+        if (a.S <= 9) reg_attention_kernel<9, __nv_bfloat16><<<grid, wpb * 32, 0, st>>>(a);
+        else reg_attention_kernel<17, __nv_bfloat16><<<grid, wpb * 32, 0, st>>>(a);
+    } else {
+        if (a.S <= 9) reg_attention_kernel<9, float><<<grid, wpb * 32, 0, st>>>(a);
+        else reg_attention_kernel<17, float><<<grid, wpb * 32, 0, st>>>(a);
+    }
     CHROMO_CHECK_LAUNCH("reg_attention");
     return CHROMO_OK;
 }
@@ -319,11 +368,13 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     const bool train = w.training;
     const long long RS = w.res_stride;
     const bool bf16 = (flags & CHROMO_F_BF16) != 0;
+    const bool proj_bf16 = bf16 && !train && T >= 64;      // q|k|v|gate handed to the attention kernel in BF16
     __nv_bfloat16* packed = bf16 ? reinterpret_cast<__nv_bfloat16*>(ws + w.bf_params) : nullptr;
     // Dense projection: tcgen05 BF16 engine when requested and the shape qualifies, FP32 SIMT otherwise.
     auto lin = [&](const GemmArgs& g, int nz) -> int {
         if (bf16 && g.M >= 64 && g.B >= P && g.B < P + L.total && umma_supported(g))
             return umma_launch(g, packed + (g.B - P), nz, st);
+        if (g.c_bf16) { set_error("internal: BF16 output requested on the FP32 path"); return CHROMO_EINVAL; }
         return gemm_launch(g, true, true, nz, st);
     };
     if (bf16 && !(flags & CHROMO_F_PACKED)) CHROMO_TRY(pack_all_weights(c, L, P, packed, ws, w, in, st));
@@ -493,13 +544,14 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.A = xin; g.lda = D; g.sA1 = RS;
             g.B = P + ra.att; g.ldb = D; g.sB1 = L.reg_stride;
             g.C = ws + w.r_proj + so; g.ldc = 4 * dmr; g.sC1 = RS;
+            if (proj_bf16) { g.c_bf16 = 1; g.sC1 = 2 * RS; }
             g.M = T; g.N = 4 * dmr; g.K = D;
             CHROMO_TRY(lin(g, NR));
         }
         {
             RegAttnArgs a;
             a.B = B; a.S = S; a.H = Hr;
-            a.proj = ws + w.r_proj + so; a.proj_zstride = RS;
+            a.proj = ws + w.r_proj + so; a.proj_zstride = proj_bf16 ? 2 * RS : RS; a.proj_bf16 = proj_bf16 ? 1 : 0;
             a.gamma_f = P + ra.gamma_f; a.gamma_zstride = L.reg_stride;
             a.freq = in->freq;
             for (int r = 0; r < NR; ++r) a.imask[r] = in->imask[r];

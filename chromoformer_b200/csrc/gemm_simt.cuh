@@ -37,6 +37,7 @@ struct GemmArgs {
     float alpha;
     int accumulate;                            // C += result
     int ksplit;                                // split-K factor; >1 => atomicAdd into C
+    int c_bf16;                                // tensor path only: C is BF16 (ldc, strides in elements)
 };
 
 static inline GemmArgs gemm_args() {

@@ -30,7 +30,8 @@ struct AttnRowsArgs {
 
 struct RegAttnArgs {
     int B, S, H;
-    const float* proj; long long proj_zstride;
+    const void* proj; long long proj_zstride;    // [T, 4*dm] FP32, or BF16 when proj_bf16 (stride in elements)
+    int proj_bf16;
     const float* gamma_f; long long gamma_zstride;
     const float* freq;
     const uint8_t* imask[CHROMO_MAX_RES];

@@ -149,16 +149,36 @@ int pack_weights(const float* src, __nv_bfloat16* dst, int N, int K, int NT, lon
 
 // ------------------------------------------------------------------ the GEMM kernel --
 constexpr int UM = 128;           // rows per CTA = UMMA M = TMEM lanes
-constexpr int UTHREADS = 128;
+constexpr int UTHREADS = 256;     // 8 warps: warp w reads TMEM lanes 32*(w%4).., column chunks (c/32)%2 == w/4
 constexpr size_t UMMA_SMEM_MAX = 225 * 1024;   // of the 227 KB a CTA may opt in to
+constexpr int STAGE_LD = 33;      // padded row of the per-warp 32x32 epilogue staging tile
 
 struct UmmaArgs {
     GemmArgs g;
     const __nv_bfloat16* Bp;      // packed weights (same z strides as g.B)
     int NT;                       // N tile (multiple of 16, <= 256, divides N)
     int tmem_cols;                // power of two >= max(32, NT)
-    int swap_lbo_sbo;             // debug: alternative descriptor convention
+    int direct_store;             // debug/tuning: skip the shared-memory transpose in the epilogue
 };
+
+// Write one 32x32 FP32 tile held as (lane = row, v[0..31] = columns) to C so that every store
+// instruction covers 4 rows x 128 contiguous bytes: transpose through a padded shared tile.
+__device__ __forceinline__ void store_tile_f32(float* stage, const float* v, float* C, const long long* crow4,
+                                               int ldc, int col0, int ncols, int lane, unsigned rowmask) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stage[lane * STAGE_LD + j] = v[j];
+    __syncwarp();
+    const int cq = (lane & 7) * 4;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3);
+        const float* sp = stage + r * STAGE_LD + cq;
+        const float4 o = make_float4(sp[0], sp[1], sp[2], sp[3]);
+        const long long cr = __shfl_sync(0xffffffffu, crow4[0], r);     // destination row of tile row r
+        if (((rowmask >> r) & 1u) && cq < ncols) *reinterpret_cast<float4*>(C + cr * ldc + col0 + cq) = o;
+    }
+    __syncwarp();
+}
 
 __global__ void __launch_bounds__(UTHREADS) umma_linear_kernel(const UmmaArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -166,15 +186,17 @@ __global__ void __launch_bounds__(UTHREADS) umma_linear_kernel(const UmmaArgs a)
     const int K = g.K, NT = a.NT;
     __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem);
     __nv_bfloat16* sB = reinterpret_cast<__nv_bfloat16*>(smem + (size_t)UM * K * 2);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)(UM + NT) * K * 2);
+    size_t ctl = (size_t)(UM + NT) * K * 2;                     // control block sits behind operands AND staging
+    if (ctl < (size_t)(UTHREADS / 32) * 32 * STAGE_LD * 4) ctl = (size_t)(UTHREADS / 32) * 32 * STAGE_LD * 4;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ctl);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    float* red = reinterpret_cast<float*>(bars + 4);            // [2][128][2] LayerNorm partial sums
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int m0 = blockIdx.y * UM, nt = blockIdx.x, n0 = nt * NT;
     const int z1 = blockIdx.z / g.zdiv, z2 = blockIdx.z % g.zdiv;
     const float* A = g.A + z1 * g.sA1 + z2 * g.sA2;
     const __nv_bfloat16* Bp = a.Bp + z1 * g.sB1 + z2 * g.sB2 + (long long)nt * NT * K;
-    float* C = g.C + z1 * g.sC1 + z2 * g.sC2;
 
     if (warp == 0) tmem_alloc(tmem_slot, a.tmem_cols);
     if (tid == 0) {
@@ -193,29 +215,44 @@ __global__ void __launch_bounds__(UTHREADS) umma_linear_kernel(const UmmaArgs a)
         tma_bulk_g2s(sB, Bp, bytes, &bars[0]);
     }
 
-    // activations: FP32 -> BF16 into the canonical layout.  A warp covers 8 rows x 32 columns
-    // per step (lane -> row lane/4, 8-column chunk lane%4): 128-byte coalesced global segments,
-    // conflict-free 16-byte shared stores.
+    // activations: FP32 -> BF16 into the canonical layout.  A warp covers 8 rows x 32 columns per
+    // unit (lane -> row lane/4, 8-column chunk lane%4): 128-byte coalesced global segments,
+    // conflict-free 16-byte shared stores.  Four units are loaded before any is converted so
+    // that eight 16-byte loads per thread are in flight.
     {
         const int KC = K / 8;
-        const int units = (UM / 8) * ((KC + 3) / 4);     // (row group, group of 4 chunks)
-        for (int u = warp; u < units; u += UTHREADS / 32) {
-            const int rg = u % (UM / 8), cg = u / (UM / 8);
-            const int r = rg * 8 + (lane >> 2), kc = cg * 4 + (lane & 3);
-            if (kc >= KC) continue;
-            const int m = m0 + r;
-            uint4 packed = make_uint4(0, 0, 0, 0);
-            if (m < g.M) {
-                const float* p = A + (long long)(m / g.a_div) * g.lda + kc * 8;
-                const float4 x0 = *reinterpret_cast<const float4*>(p);
-                const float4 x1 = *reinterpret_cast<const float4*>(p + 4);
-                __nv_bfloat162 b0 = __floats2bfloat162_rn(x0.x, x0.y), b1 = __floats2bfloat162_rn(x0.z, x0.w);
-                __nv_bfloat162 b2 = __floats2bfloat162_rn(x1.x, x1.y), b3 = __floats2bfloat162_rn(x1.z, x1.w);
+        const int units = (UM / 8) * ((KC + 3) / 4);
+        constexpr int UNR = 4;
+        for (int u0 = warp; u0 < units; u0 += (UTHREADS / 32) * UNR) {
+            float4 x[UNR][2];
+            int r_[UNR], kc_[UNR];
+            bool ok_[UNR];
+#pragma unroll
+            for (int q = 0; q < UNR; ++q) {
+                const int u = u0 + q * (UTHREADS / 32);
+                const int rg = u % (UM / 8), cg = u / (UM / 8);
+                r_[q] = rg * 8 + (lane >> 2);
+                kc_[q] = cg * 4 + (lane & 3);
+                const int m = m0 + r_[q];
+                ok_[q] = u < units && kc_[q] < KC;
+                x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ok_[q] && m < g.M) {
+                    const float* p = A + (long long)(m / g.a_div) * g.lda + kc_[q] * 8;
+                    x[q][0] = __ldg(reinterpret_cast<const float4*>(p));
+                    x[q][1] = __ldg(reinterpret_cast<const float4*>(p + 4));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < UNR; ++q) {
+                if (!ok_[q]) continue;
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(x[q][0].x, x[q][0].y), b1 = __floats2bfloat162_rn(x[q][0].z, x[q][0].w);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(x[q][1].x, x[q][1].y), b3 = __floats2bfloat162_rn(x[q][1].z, x[q][1].w);
+                uint4 packed;
                 packed.x = *reinterpret_cast<uint32_t*>(&b0); packed.y = *reinterpret_cast<uint32_t*>(&b1);
                 packed.z = *reinterpret_cast<uint32_t*>(&b2); packed.w = *reinterpret_cast<uint32_t*>(&b3);
+                *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(sA) + ((size_t)(r_[q] >> 3) * KC + kc_[q]) * 128 +
+                                          (r_[q] & 7) * 16) = packed;
             }
-            *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(sA) + ((size_t)(r >> 3) * KC + kc) * 128 +
-                                      (r & 7) * 16) = packed;
         }
     }
     fence_async_smem();
@@ -225,8 +262,7 @@ __global__ void __launch_bounds__(UTHREADS) umma_linear_kernel(const UmmaArgs a)
         mbar_wait(&bars[0], 0);
         tc_fence_after();
         const uint32_t idesc = umma_idesc_bf16(UM, NT);
-        const uint32_t lbo = a.swap_lbo_sbo ? (uint32_t)K * 16 : 128u;
-        const uint32_t sbo = a.swap_lbo_sbo ? 128u : (uint32_t)K * 16;
+        const uint32_t lbo = 128u, sbo = (uint32_t)K * 16;
         const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
         for (int k = 0; k < K / 16; ++k) {
             const uint64_t ad = umma_smem_desc(a0 + k * 256, lbo, sbo);
@@ -238,84 +274,134 @@ __global__ void __launch_bounds__(UTHREADS) umma_linear_kernel(const UmmaArgs a)
     __syncwarp();
     mbar_wait(&bars[1], 0);
     tc_fence_after();
+    // all MMAs have completed: the operand tiles are dead, reuse them as epilogue staging
+    float* stage = reinterpret_cast<float*>(smem) + warp * (32 * STAGE_LD);
 
     // ------------------------------------------------------------------ epilogue ----
-    const int m = m0 + warp * 32 + lane;                 // this thread's row = its TMEM lane
-    const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+    const int lq = warp & 3, ch = warp >> 2;
+    const int m = m0 + lq * 32 + lane;                   // this thread's row = its TMEM lane
+    const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16);
     const bool ok = m < g.M;
+    const unsigned rowmask = __ballot_sync(0xffffffffu, ok);
     const long long crow = ok ? (long long)(m / g.c_div) * g.c_mul + (m % g.c_div) + g.c_add : 0;
     const float* bias = g.bias ? g.bias + z1 * g.sBias1 + z2 * g.sBias2 : nullptr;
     float v[32];
     if (g.epi == EPI_BIAS_RES_LN) {
-        // N == NT == 128: the thread owns the whole row.  Pass 1: statistics, pass 2: write.
+        // N == NT == 128.  The two warps sharing a lane quarter each own two 32-column chunks of the
+        // row: partial sums meet in shared memory, then each normalises and writes its chunks.
+        float* C = g.C + z1 * g.sC1 + z2 * g.sC2;
         const float* res = g.res + z1 * g.sRes1 + (ok ? (long long)(m / g.res_div) * g.ldres : 0);
         const float* gamma = g.gamma + z1 * g.sLn1;
         const float* beta = g.beta + z1 * g.sLn1;
         float* pre = (g.pre && ok) ? g.pre + z1 * g.sPre1 + (long long)m * g.N : nullptr;
+        float keep[2][32];
         float sum = 0.f, sq = 0.f;
-        for (int c = 0; c < 128; c += 32) {
-            tmem_ld32(trow + c, v);
-            if (ok) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 r4 = *reinterpret_cast<const float4*>(res + c + j);
-                    const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + c + j) : make_float4(0, 0, 0, 0);
-                    const float t0 = v[j] + b4.x + r4.x, t1 = v[j + 1] + b4.y + r4.y;
-                    const float t2 = v[j + 2] + b4.z + r4.z, t3 = v[j + 3] + b4.w + r4.w;
-                    sum += (t0 + t1) + (t2 + t3);
-                    sq += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
-                    if (pre) *reinterpret_cast<float4*>(pre + c + j) = make_float4(t0, t1, t2, t3);
-                }
+        for (int ci = 0; ci < 2; ++ci) {
+            const int c = (2 * ci + ch) * 32;
+            tmem_ld32(trow + c, v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 r4 = make_float4(0, 0, 0, 0);
+                if (ok) r4 = *reinterpret_cast<const float4*>(res + c + j);
+                const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + c + j) : make_float4(0, 0, 0, 0);
+                const float t0 = v[j] + b4.x + r4.x, t1 = v[j + 1] + b4.y + r4.y;
+                const float t2 = v[j + 2] + b4.z + r4.z, t3 = v[j + 3] + b4.w + r4.w;
+                keep[ci][j] = t0; keep[ci][j + 1] = t1; keep[ci][j + 2] = t2; keep[ci][j + 3] = t3;
+                sum += (t0 + t1) + (t2 + t3);
+                sq += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
+                if (pre) *reinterpret_cast<float4*>(pre + c + j) = make_float4(t0, t1, t2, t3);
             }
         }
+        red[(ch * 128 + lq * 32 + lane) * 2] = sum;
+        red[(ch * 128 + lq * 32 + lane) * 2 + 1] = sq;
+        __syncthreads();
+        sum += red[((1 - ch) * 128 + lq * 32 + lane) * 2];
+        sq += red[((1 - ch) * 128 + lq * 32 + lane) * 2 + 1];
         const float mean = sum * (1.f / 128.f);
         const float var = fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f);
         const float rstd = rsqrtf(var + 1e-5f);
-        for (int c = 0; c < 128; c += 32) {
-            tmem_ld32(trow + c, v);
-            if (ok) {
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const float4 r4 = *reinterpret_cast<const float4*>(res + c + j);
-                    const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + c + j) : make_float4(0, 0, 0, 0);
-                    const float4 ga = *reinterpret_cast<const float4*>(gamma + c + j);
-                    const float4 be = *reinterpret_cast<const float4*>(beta + c + j);
-                    float4 o;
-                    o.x = (v[j] + b4.x + r4.x - mean) * rstd * ga.x + be.x;
-                    o.y = (v[j + 1] + b4.y + r4.y - mean) * rstd * ga.y + be.y;
-                    o.z = (v[j + 2] + b4.z + r4.z - mean) * rstd * ga.z + be.z;
-                    o.w = (v[j + 3] + b4.w + r4.w - mean) * rstd * ga.w + be.w;
-                    *reinterpret_cast<float4*>(C + crow * g.ldc + c + j) = o;
-                }
-            }
-        }
-    } else {
-        for (int c = 0; c < NT; c += 32) {
-            tmem_ld32(trow + c, v);          // columns beyond NT (NT % 32 != 0) are ignored below
-            if (!ok) continue;
-            float* out = C + crow * g.ldc + n0 + c;
+        for (int ci = 0; ci < 2; ++ci) {
+            const int c = (2 * ci + ch) * 32;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
-                if (c + j >= NT) break;
-                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                if (g.epi != EPI_PLAIN && bias) {
-                    const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + c + j);
-                    o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+                const float4 ga = *reinterpret_cast<const float4*>(gamma + c + j);
+                const float4 be = *reinterpret_cast<const float4*>(beta + c + j);
+                v[j] = (keep[ci][j] - mean) * rstd * ga.x + be.x;
+                v[j + 1] = (keep[ci][j + 1] - mean) * rstd * ga.y + be.y;
+                v[j + 2] = (keep[ci][j + 2] - mean) * rstd * ga.z + be.z;
+                v[j + 3] = (keep[ci][j + 3] - mean) * rstd * ga.w + be.w;
+            }
+            store_tile_f32(stage, v, C, &crow, g.ldc, c, 32, lane, rowmask);
+        }
+    } else {
+        for (int c = ch * 32; c < NT; c += 64) {
+            tmem_ld32(trow + c, v);          // columns beyond NT (NT % 32 != 0) are dropped below
+            const int ncols = min(32, NT - c);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                if (j < ncols) {
+                    if (g.epi != EPI_PLAIN && bias) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + c + j);
+                        v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+                    }
+                    if (g.epi == EPI_BIAS_RELU) {
+                        v[j] = fmaxf(v[j], 0.f); v[j + 1] = fmaxf(v[j + 1], 0.f);
+                        v[j + 2] = fmaxf(v[j + 2], 0.f); v[j + 3] = fmaxf(v[j + 3], 0.f);
+                    }
                 }
-                if (g.epi == EPI_BIAS_RELU) {
-                    o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f);
+            }
+            if (g.c_bf16) {
+                // BF16 output: the thread's 32 columns are 64 contiguous bytes
+                if (ok) {
+                    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(g.C) + z1 * g.sC1 + z2 * g.sC2 +
+                                         crow * g.ldc + n0 + c;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (j < ncols) {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                            *reinterpret_cast<uint4*>(out + j) = pk;
+                        }
+                    }
                 }
-                if (g.accumulate) {
-                    const float4 old = *reinterpret_cast<const float4*>(out + j);
-                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+            } else {
+                float* C = g.C + z1 * g.sC1 + z2 * g.sC2;
+                if (g.accumulate || a.direct_store) {
+                    if (ok) {
+                        float* out = C + crow * g.ldc + n0 + c;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (j < ncols) {
+                                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                                if (g.accumulate) {
+                                    const float4 old = *reinterpret_cast<const float4*>(out + j);
+                                    o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
+                                }
+                                *reinterpret_cast<float4*>(out + j) = o;
+                            }
+                        }
+                    }
+                } else {
+                    store_tile_f32(stage, v, C, &crow, g.ldc, n0 + c, ncols, lane, rowmask);
                 }
-                *reinterpret_cast<float4*>(out + j) = o;
             }
         }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
+}
+
+static size_t umma_smem_bytes(int nt, int K) {
+    size_t operands = (size_t)(UM + nt) * K * 2;
+    const size_t staging = (size_t)(UTHREADS / 32) * 32 * STAGE_LD * 4;      // reuses the operand area
+    if (operands < staging) operands = staging;
+    return operands + 32 + 2 * 128 * 2 * 4;                                   // barriers, TMEM slot, LN partials
 }
 
 static int choose_nt(int N) {
@@ -332,25 +418,26 @@ bool umma_supported(const GemmArgs& g) {
     if (g.K % 16 != 0 || g.K < 16 || g.ksplit != 1) return false;
     const int nt = choose_nt(g.N);
     if (nt == 0) return false;
-    if ((size_t)(UM + nt) * g.K * 2 + 64 > UMMA_SMEM_MAX) return false;
+    if (umma_smem_bytes(nt, g.K) > UMMA_SMEM_MAX) return false;
     if (g.lda % 4 != 0 || g.ldc % 4 != 0) return false;
     if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.C) & 15)) return false;
-    if (g.epi == EPI_BIAS_RES_LN && (g.N != 128 || g.accumulate)) return false;
+    if (g.epi == EPI_BIAS_RES_LN && (g.N != 128 || g.accumulate || g.c_bf16)) return false;
+    if (g.c_bf16 && (g.accumulate || g.N % 8 != 0)) return false;
     return true;
 }
 
 int umma_launch(const GemmArgs& g, const __nv_bfloat16* Bp, int nz, cudaStream_t st) {
-    static int swap = -1;
-    if (swap < 0) {
-        const char* e = getenv("CHROMO_UMMA_SWAP");
-        swap = (e && e[0] == '1') ? 1 : 0;
+    static int direct = -1;
+    if (direct < 0) {
+        const char* e = getenv("CHROMO_UMMA_DIRECT_STORE");
+        direct = (e && e[0] == '1') ? 1 : 0;
     }
     UmmaArgs a;
     a.g = g; a.Bp = Bp; a.NT = choose_nt(g.N);
     a.tmem_cols = 32;
     while (a.tmem_cols < a.NT) a.tmem_cols *= 2;
-    a.swap_lbo_sbo = swap;
-    const size_t smem = (size_t)(UM + a.NT) * g.K * 2 + 64;
+    a.direct_store = direct;
+    const size_t smem = umma_smem_bytes(a.NT, g.K);
     static size_t configured = 0;
     if (smem > configured) {
         cudaError_t e = cudaFuncSetAttribute(umma_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX);
