@@ -152,7 +152,7 @@ def main():
     ap.add_argument("--mode", choices=["infer", "train"], default="infer")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--chunk", type=int, default=4096)
-    ap.add_argument("--precision", choices=["fp32", "bf16"], default="fp32")
+    ap.add_argument("--precision", choices=["fp32", "bf16"], default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     args = ap.parse_args()
@@ -236,13 +236,19 @@ def main():
     st = torch.cuda.current_stream().cuda_stream
     flags = _lib.F_BF16 if args.precision == "bf16" else 0
 
+    if args.precision == "bf16":
+        wpk = torch.empty(3, 1024, 128, dtype=torch.bfloat16, device=dev)
+        _lib.check(lib.chromo_pack_linear_weight(wgt.data_ptr(), wpk.data_ptr(), 1024, 128, 3, 1024 * 128, st), "pack")
+        wgt = wpk
+
     def one_linear():
         _lib.check(lib.chromo_linear(x.data_ptr(), wgt.data_ptr(), None, y.data_ptr(), T, 1024, 128, 0, 3,
                                      T * 128, 1024 * 128, 0, T * 1024, flags, st), "chromo_linear")
     ms_k = timed(one_linear, 20, 5)
     flops_k = 2.0 * 3 * T * 1024 * 128
     ach = flops_k / (ms_k * 1e-3) / 1e12
-    roofline = {"bound": "tensor", "kernel": "gemm_simt_kernel<64,64> as launched for regulation.*.self_att.att "
+    kname = "umma_linear_kernel (tcgen05, BF16 operands, FP32 out)" if args.precision == "bf16" else "gemm_simt_kernel<64,64> (FP32 CUDA cores)"
+    roofline = {"bound": "tensor", "kernel": f"{kname} as launched for regulation.*.self_att.att "
                                              f"(M={T}, N=1024, K=128, 3 resolutions)",
                 "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
                 "traffic": None, "peak_source": peaks["source"] + " burst (kernel timed alone)",

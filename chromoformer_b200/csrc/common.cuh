@@ -90,6 +90,10 @@ struct WsLayout {
     int64_t h_z, h_h1;
     // BF16 tensor path: packed parameter mirror + packed position tables (float offsets)
     int64_t bf_params, bf_pe[CHROMO_MAX_RES], bf_pet[CHROMO_MAX_RES];
+    // inference-time folded attention weights (FP32 scratch + packed BF16 mirror, element offsets equal):
+    //   M = [W_k[h]^T W_q[h]]_h  ([H*D, D]),  N = [W_o[:,h] W_v[h]]_h  ([D, H*D]);  slot 0 = embed, 1.. = pairwise layers
+    int64_t fold_f32, fold_bf, fold_stride, fold_total;
+    int64_t fold_slot[CHROMO_MAX_LAYERS + 1];
     // backward scratch (training only)
     int64_t g_base;
     int64_t total;

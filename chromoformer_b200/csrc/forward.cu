@@ -265,7 +265,7 @@ int launch_attn_rows(const AttnRowsArgs& a, cudaStream_t st) {
 int single_query_attention(const SqaArgs& s, cudaStream_t st) {
     const int dh = s.dm / s.H, D = s.D;
     // QK[(row,h), :] = W_k[h]^T Q[row, h]                                  (NN GEMM per head)
-    {
+    if (!s.folded) {
         GemmArgs g = gemm_args();
         g.A = s.q; g.lda = s.dm; g.sA2 = dh;
         g.B = s.w_k; g.ldb = D; g.sB2 = (long long)dh * D;
@@ -303,7 +303,7 @@ int single_query_attention(const SqaArgs& s, cudaStream_t st) {
         else CHROMO_TRY(gemm_launch(g, true, false, 1, st));
     }
     // Av[row, h*dh + e] = W_v[h*dh + e, :] . Cbar[(row,h), :]               (NT GEMM per head)
-    {
+    if (!s.folded) {
         GemmArgs g = gemm_args();
         g.A = s.cbar; g.lda = s.H * D; g.sA2 = D;
         g.B = s.w_v; g.ldb = D; g.sB2 = (long long)dh * D;
@@ -349,6 +349,43 @@ static int pack_all_weights(const chromo_config_t* c, const ParamLayout& L, cons
         CHROMO_TRY(pk(f.l2w, D, c->reg_d_ff, L.reg_stride, NR));
     }
     CHROMO_TRY(pk(L.fc0w, c->d_head, NR * D, 0, 1));
+    if (!w.training) {
+        // Folded single-query attention weights (exact re-association, inference only):
+        //   QK[(row,h), :] = (W_k[h]^T W_q[h]) x_row        -> one [H*D, D] linear replaces Q and the QK fold
+        //   out            = sum_h (W_o[:,h] W_v[h]) cbar_h -> one [D, H*D] linear replaces W_v and the out-projection
+        float* F32 = ws + w.fold_f32;
+        __nv_bfloat16* FB = reinterpret_cast<__nv_bfloat16*>(ws + w.fold_bf);
+        auto fold = [&](int slot, int H, int dm, int64_t wq, int64_t wk, int64_t wv, int64_t wo, long long pz) -> int {
+            const int dh = dm / H;
+            const int64_t oM = w.fold_slot[slot], oN = oM + (int64_t)H * D * D;
+            {   // M[h][d, e] = sum_c W_k[h*dh + c, d] W_q[h*dh + c, e]
+                GemmArgs g = gemm_args();
+                g.A = P + wk; g.lda = D; g.sA1 = pz; g.sA2 = (long long)dh * D;
+                g.B = P + wq; g.ldb = D; g.sB1 = pz; g.sB2 = (long long)dh * D;
+                g.C = F32 + oM; g.ldc = D; g.sC1 = w.fold_stride; g.sC2 = (long long)D * D;
+                g.M = D; g.N = D; g.K = dh; g.zdiv = H;
+                CHROMO_TRY(gemm_launch(g, false, false, NR * H, st));
+            }
+            {   // N[o, h*D + d] = sum_c W_o[o, h*dh + c] W_v[h*dh + c, d]
+                GemmArgs g = gemm_args();
+                g.A = P + wo; g.lda = dm; g.sA1 = pz; g.sA2 = dh;
+                g.B = P + wv; g.ldb = D; g.sB1 = pz; g.sB2 = (long long)dh * D;
+                g.C = F32 + oN; g.ldc = H * D; g.sC1 = w.fold_stride; g.sC2 = D;
+                g.M = D; g.N = D; g.K = dh; g.zdiv = H;
+                CHROMO_TRY(gemm_launch(g, true, false, NR * H, st));
+            }
+            CHROMO_TRY(pack_weights(F32 + oM, FB + oM, H * D, D, umma_tile_n(H * D), w.fold_stride, NR, false, D, st));
+            CHROMO_TRY(pack_weights(F32 + oN, FB + oN, D, H * D, umma_tile_n(D), w.fold_stride, NR, false, H * D, st));
+            return CHROMO_OK;
+        };
+        const int dme = c->embed_d_model, dmp = c->pw_d_model;
+        CHROMO_TRY(fold(0, c->embed_heads, dme, ea.att, ea.att + (int64_t)dme * D, ea.att + (int64_t)2 * dme * D, ea.ffw,
+                        L.embed_stride));
+        for (int l = 0; l < c->pw_layers; ++l) {
+            const AttnOff& a = L.pw[0].att[l];
+            CHROMO_TRY(fold(1 + l, c->pw_heads, dmp, a.p_att, a.c_att, a.c_att + (int64_t)dmp * D, a.ffw, L.pw_stride));
+        }
+    }
     for (int r = 0; r < NR; ++r) {
         const int n = c->n_bins[r];
         if (n % 16 != 0) continue;
@@ -368,12 +405,15 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     const bool train = w.training;
     const long long RS = w.res_stride;
     const bool bf16 = (flags & CHROMO_F_BF16) != 0;
-    const bool proj_bf16 = bf16 && !train && T >= 64;      // q|k|v|gate handed to the attention kernel in BF16
+    const bool proj_bf16 = bf16 && !train && T >= 64;
+    const bool fold = bf16 && !train;           // folded single-query attention weights (see pack_all_weights)      // q|k|v|gate handed to the attention kernel in BF16
     __nv_bfloat16* packed = bf16 ? reinterpret_cast<__nv_bfloat16*>(ws + w.bf_params) : nullptr;
     // Dense projection: tcgen05 BF16 engine when requested and the shape qualifies, FP32 SIMT otherwise.
     auto lin = [&](const GemmArgs& g, int nz) -> int {
         if (bf16 && g.M >= 64 && g.B >= P && g.B < P + L.total && umma_supported(g))
             return umma_launch(g, packed + (g.B - P), nz, st);
+        if (fold && g.B >= ws + w.fold_f32 && g.B < ws + w.fold_f32 + w.fold_total && umma_supported(g))
+            return umma_launch(g, reinterpret_cast<const __nv_bfloat16*>(ws + w.fold_bf) + (g.B - (ws + w.fold_f32)), nz, st);
         if (g.c_bf16) { set_error("internal: BF16 output requested on the FP32 path"); return CHROMO_EINVAL; }
         return gemm_launch(g, true, true, nz, st);
     };
@@ -393,7 +433,15 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     const AttnOff& ea = L.embed[0].att[0];
     const FfnOff& ef = L.embed[0].ffn[0];
     const int dme = c->embed_d_model;
-    {   // Q = Hc W_q^T
+    const int He = c->embed_heads;
+    if (fold) {   // QK = Hc M^T  (M = [W_k[h]^T W_q[h]]_h)
+        GemmArgs g = gemm_args();
+        g.A = ws + w.e_hc; g.lda = D; g.sA1 = RS;
+        g.B = ws + w.fold_f32 + w.fold_slot[0]; g.ldb = D; g.sB1 = w.fold_stride;
+        g.C = ws + w.e_qk; g.ldc = He * D; g.sC1 = RS;
+        g.M = B; g.N = He * D; g.K = D;
+        CHROMO_TRY(lin(g, NR));
+    } else {      // Q = Hc W_q^T
         GemmArgs g = gemm_args();
         g.A = ws + w.e_hc; g.lda = D; g.sA1 = RS;
         g.B = P + ea.att; g.ldb = D; g.sB1 = L.embed_stride;
@@ -414,7 +462,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         s.pe_pk = bf16 ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pe[r]) : nullptr;
         s.pet_pk = bf16 ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pet[r]) : nullptr;
         s.qk = ws + r * RS + w.e_qk; s.P = ws + w.e_p[r]; s.xbar = ws + r * RS + w.e_xbar;
-        s.cbar = ws + r * RS + w.e_cbar; s.av = ws + r * RS + w.e_av;
+        s.cbar = ws + r * RS + w.e_cbar; s.av = ws + r * RS + w.e_av; s.folded = fold;
         CHROMO_TRY(single_query_attention(s, st));
     }
     {   // U = LN(Hc + Av W_o^T + b_o)                            modules.py:29-30
@@ -423,6 +471,10 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         g.B = P + ea.ffw; g.ldb = dme; g.sB1 = L.embed_stride;
         g.C = ws + w.e_u; g.ldc = D; g.sC1 = RS;
         g.M = B; g.N = D; g.K = dme;
+        if (fold) {   // ... = LN(Hc + Cbar N^T + b_o),  N = [W_o[:,h] W_v[h]]_h
+            g.A = ws + w.e_cbar; g.lda = He * D; g.K = He * D;
+            g.B = ws + w.fold_f32 + w.fold_slot[0] + (int64_t)He * D * D; g.ldb = He * D; g.sB1 = w.fold_stride;
+        }
         g.epi = EPI_BIAS_RES_LN; g.bias = P + ea.ffb; g.sBias1 = L.embed_stride;
         g.res = ws + w.e_hc; g.ldres = D; g.sRes1 = RS;
         g.gamma = P + ea.lnw; g.beta = P + ea.lnb; g.sLn1 = L.embed_stride;
@@ -468,7 +520,14 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         const float* pin = l == 0 ? ws + w.p_pp : ws + w.p_out + (long long)w.pslot(l - 1) * w.p_slot;
         const int pin_div = l == 0 ? I : 1;
         const bool last = l == c->pw_layers - 1;
-        {   // Q = P_l W_q^T                                       modules.py:159
+        if (fold) {   // QK = P_l M^T
+            GemmArgs g = gemm_args();
+            g.A = pin; g.lda = D; g.sA1 = RS; g.a_div = pin_div;
+            g.B = ws + w.fold_f32 + w.fold_slot[1 + l]; g.ldb = D; g.sB1 = w.fold_stride;
+            g.C = ws + w.p_qk + so; g.ldc = Hp * D; g.sC1 = RS;
+            g.M = R; g.N = Hp * D; g.K = D;
+            CHROMO_TRY(lin(g, NR));
+        } else {      // Q = P_l W_q^T                             modules.py:159
             GemmArgs g = gemm_args();
             g.A = pin; g.lda = D; g.sA1 = RS; g.a_div = pin_div;
             g.B = P + pa.p_att; g.ldb = D; g.sB1 = L.pw_stride;
@@ -492,7 +551,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             s.qk = ws + r * RS + w.p_qk + so;
             s.P = ws + w.p_p[r] + (long long)w.pslot(l) * w.p_p_slot[r];
             s.xbar = ws + r * RS + w.p_xbar + so;
-            s.cbar = ws + r * RS + w.p_cbar + so; s.av = ws + r * RS + w.p_av + so;
+            s.cbar = ws + r * RS + w.p_cbar + so; s.av = ws + r * RS + w.p_av + so; s.folded = fold;
             CHROMO_TRY(single_query_attention(s, st));
         }
         {   // U = LN(P_l + Av W_o^T + b_o)                        modules.py:150-152
@@ -501,6 +560,10 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.B = P + pa.ffw; g.ldb = dmp; g.sB1 = L.pw_stride;
             g.C = ws + w.p_u + so; g.ldc = D; g.sC1 = RS;
             g.M = R; g.N = D; g.K = dmp;
+            if (fold) {
+                g.A = ws + w.p_cbar + so; g.lda = Hp * D; g.K = Hp * D;
+                g.B = ws + w.fold_f32 + w.fold_slot[1 + l] + (int64_t)Hp * D * D; g.ldb = Hp * D; g.sB1 = w.fold_stride;
+            }
             g.epi = EPI_BIAS_RES_LN; g.bias = P + pa.ffb; g.sBias1 = L.pw_stride;
             g.res = pin; g.ldres = D; g.res_div = pin_div; g.sRes1 = RS;
             g.gamma = P + pa.lnw; g.beta = P + pa.lnb; g.sLn1 = L.pw_stride;

@@ -79,6 +79,7 @@ struct SqaArgs {
     const float* x;                 // [rows, n, F]
     const uint8_t* mask; long long mask_stride, mask_row_offset;
     float* qk; float* P; float* xbar; float* cbar; float* av;
+    bool folded = false;                    // caller supplies qk and consumes cbar (folded weights)
     const __nv_bfloat16* pe_pk = nullptr;   // BF16 tensor path: PE packed as a [n,D] weight
     const __nv_bfloat16* pet_pk = nullptr;  //                   PE^T packed as a [D,n] weight
 };

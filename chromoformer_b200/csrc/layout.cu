@@ -188,7 +188,29 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
     int64_t cur = 0;
     auto take = [&](int64_t n) { int64_t o = cur; cur = align4(cur + n); return o; };
     const int He = c->embed_heads, Hp = c->pw_heads, Hr = c->reg_heads;
+    // Batch-independent part first, so that packed weights survive a change of batch size
+    // (CHROMO_F_PACKED).
+    if (flags & CHROMO_F_BF16) {
+        // BF16 mirror of the flat parameters in UMMA tile order (same element offsets) and
+        // the packed position tables (PE [n,D] as a weight, and its transpose).
+        w.bf_params = take((get_layout(c).total + 1) / 2 + 8);
+        for (int r = 0; r < c->n_res; ++r) {
+            const int64_t n16 = (c->n_bins[r] + 15) / 16 * 16;
+            w.bf_pe[r] = take((n16 * D + 1) / 2 + 8);
+            w.bf_pet[r] = take((n16 * D + 1) / 2 + 8);
+        }
+        if (!w.training) {
+            int64_t off = 0;
+            w.fold_slot[0] = off; off += (int64_t)2 * He * D * D;
+            for (int l = 0; l < c->pw_layers; ++l) { w.fold_slot[1 + l] = off; off += (int64_t)2 * Hp * D * D; }
+            w.fold_stride = off;
+            w.fold_total = off * c->n_res;
+            w.fold_f32 = take(w.fold_total);
+            w.fold_bf = take((w.fold_total + 1) / 2 + 8);
+        }
+    }
     // ---- per-resolution block
+    const int64_t res_base = cur;
     w.e_hc = take((int64_t)B * D);
     w.e_q = take((int64_t)B * c->embed_d_model);
     w.e_qk = take((int64_t)B * He * D);
@@ -232,8 +254,8 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
         w.r_slot = cur - s0;
         cur = s0 + w.r_slot * w.rslots;
     }
-    w.res_stride = cur;
-    cur = w.res_stride * c->n_res;
+    w.res_stride = cur - res_base;
+    cur = res_base + w.res_stride * c->n_res;
     // ---- resolution-dependent buffers
     for (int r = 0; r < c->n_res; ++r) {
         w.e_p[r] = take((int64_t)B * He * c->n_bins[r]);
@@ -242,16 +264,6 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
     }
     w.h_z = take((int64_t)B * c->n_res * D);
     w.h_h1 = take((int64_t)B * c->d_head);
-    if (flags & CHROMO_F_BF16) {
-        // BF16 mirror of the flat parameters in UMMA tile order (same element offsets) and
-        // the packed position tables (PE [n,D] as a weight, and its transpose).
-        w.bf_params = take((get_layout(c).total + 1) / 2 + 8);
-        for (int r = 0; r < c->n_res; ++r) {
-            const int64_t n16 = (c->n_bins[r] + 15) / 16 * 16;
-            w.bf_pe[r] = take((n16 * D + 1) / 2 + 8);
-            w.bf_pet[r] = take((n16 * D + 1) / 2 + 8);
-        }
-    }
     w.g_base = cur;
     if (w.training) {
         // backward scratch: generous bound, carved up in backward.cu

@@ -252,6 +252,8 @@ class _ChromoformerCore(nn.Module):
         object.__setattr__(self, "_flat_grad", None)
         object.__setattr__(self, "_anchor", None)
         object.__setattr__(self, "_table", None)
+        object.__setattr__(self, "_packed_key", None)
+        object.__setattr__(self, "_param_epoch", 0)
         self._rebuild_flat()
 
     def _lib_name(self, name):
@@ -294,12 +296,19 @@ class _ChromoformerCore(nn.Module):
         object.__setattr__(self, "_active", [p for (_, p, off, _) in slots if off < active])
         object.__setattr__(self, "_anchor", torch.zeros(1, device=dev, requires_grad=True))
         self._ws_cache.clear()
+        self.mark_parameters_changed()
 
     def _apply(self, fn, recurse=True):
         out = super()._apply(fn, recurse)
         if getattr(self, "_flat", None) is not None:
             self._rebuild_flat()
         return out
+
+    def mark_parameters_changed(self):
+        """Call after updating parameters through raw pointers (the fused optimiser does): cached
+        BF16 weight packs are rebuilt on the next forward.  In-place torch ops are tracked automatically."""
+        object.__setattr__(self, "_param_epoch", self._param_epoch + 1)
+        object.__setattr__(self, "_packed_key", None)
 
     def _flat_is_current(self):
         slots = self._slots
@@ -362,11 +371,21 @@ class _ChromoformerCore(nn.Module):
             self._rebuild_flat()
         training = bool(flags & _lib.F_TRAINING)
         ws = self._workspace(io.cfg, io.batch, flags, cached=not training)
+        packed_key = None
+        if (flags & _lib.F_BF16) and not training:
+            # the packed BF16 weights live at the (batch-independent) front of the cached workspace:
+            # reuse them while neither the buffer nor the parameters changed
+            packed_key = (ws.data_ptr(), self._flat._version, self._param_epoch,
+                          tuple(io.cfg.n_bins[r] for r in range(io.cfg.n_res)))
+            if packed_key == self._packed_key:
+                flags |= _lib.F_PACKED
         logits = torch.empty(io.batch, int(self._cfg.n_out), dtype=torch.float32, device=self._flat.device)
         stream = torch.cuda.current_stream(self._flat.device).cuda_stream
         _lib.check(lib.chromo_forward(ctypes.byref(io.cfg), self._flat.data_ptr(), ctypes.byref(io.struct),
                                       logits.data_ptr(), ws.data_ptr(), ws.numel(), flags, stream),
                    "chromo_forward")
+        if packed_key is not None:
+            object.__setattr__(self, "_packed_key", packed_key)
         return logits, ws
 
     def _launch_backward(self, io, ws, dlogits):

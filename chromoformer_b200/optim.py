@@ -69,5 +69,6 @@ class FusedAdamW(torch.optim.Optimizer):
                                     model.n_active, float(group["lr"]), float(group["betas"][0]),
                                     float(group["betas"][1]), float(group["eps"]), float(group["weight_decay"]),
                                     self._step, float(self.grad_scale), stream), "chromo_adamw")
+        model.mark_parameters_changed()
         self._publish_state()
         return loss

@@ -75,6 +75,7 @@ class TrainStep:
         _lib.check(lib.chromo_adamw(flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                     model.n_active, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,
                                     self.step_count, scale, stream), "chromo_adamw")
+        model.mark_parameters_changed()
         self.logits = logits
         return self.loss
 

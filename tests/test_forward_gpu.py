@@ -182,3 +182,24 @@ def test_bf16_tensor_path_tolerance(stress):
     assert err < (2e-2 * scale if stress else 1e-2), err
     assert (got.argmax(1) == want.argmax(1))[safe].all() and agree >= 0.99
     assert not torch.equal(got, want), "BF16 flag had no effect: tensor path not taken"
+
+
+def test_bf16_packed_weight_cache_is_invalidated():
+    """The packed BF16 weights are reused across chunks/batch sizes and rebuilt when parameters change."""
+    from chromoformer_b200.engine import InferenceEngine
+    batch = synthetic.make_batch(700, ragged=True, seed=4)
+    a_model = _mk(seed=1).cuda().eval(); a_model.precision = "bf16"
+    b_model = _mk(seed=2).cuda().eval(); b_model.precision = "bf16"
+    dev = InferenceEngine(a_model, chunk=256).to_device(batch)
+    a1 = InferenceEngine(a_model, chunk=256).predict_device(dev).cpu()       # 256, 256, 188: packs once
+    a2 = InferenceEngine(a_model, chunk=700).predict_device(dev).cpu()
+    assert torch.equal(a1, a2)
+    b1 = InferenceEngine(b_model, chunk=700).predict_device(dev).cpu()
+    assert not torch.equal(a1, b1)
+    a_model.load_state_dict(b_model.state_dict())                            # in-place copy_ -> version bump
+    a3 = InferenceEngine(a_model, chunk=256).predict_device(dev).cpu()
+    assert torch.equal(a3, b1)
+    with torch.no_grad():
+        a_model.fc_head[2].bias.add_(1.0)
+    a4 = InferenceEngine(a_model, chunk=256).predict_device(dev).cpu()
+    assert torch.allclose(a4, b1 + 1.0, atol=1e-5)
