@@ -94,6 +94,8 @@ struct WsLayout {
     //   M = [W_k[h]^T W_q[h]]_h  ([H*D, D]),  N = [W_o[:,h] W_v[h]]_h  ([D, H*D]);  slot 0 = embed, 1.. = pairwise layers
     int64_t fold_f32, fold_bf, fold_stride, fold_total;
     int64_t fold_slot[CHROMO_MAX_LAYERS + 1];
+    int64_t reg_stream;     // packed weight stream of the fused Regulation layers (float offset; 0 = unused)
+    int reg_fused;          // 1 when the fused Regulation-layer kernel applies to this configuration
     // backward scratch (training only)
     int64_t g_base;
     int64_t total;

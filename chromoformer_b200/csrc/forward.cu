@@ -13,11 +13,13 @@
 //
 // Everything is FP32 here; the tcgen05 BF16 engine (umma_gemm.cu) replaces the
 // large projections when CHROMO_F_BF16 is set.
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "kernels.cuh"
+#include "reg_fused.cuh"
 #include "umma_gemm.cuh"
 
 namespace chromo {
@@ -349,6 +351,16 @@ static int pack_all_weights(const chromo_config_t* c, const ParamLayout& L, cons
         CHROMO_TRY(pk(f.l2w, D, c->reg_d_ff, L.reg_stride, NR));
     }
     CHROMO_TRY(pk(L.fc0w, c->d_head, NR * D, 0, 1));
+    if (w.reg_fused) {
+        RegStreamArgs a;
+        a.params = P; a.p_z = L.reg_stride; a.n_layers = c->reg_layers;
+        for (int l = 0; l < c->reg_layers; ++l) {
+            a.att[l] = L.reg[0].att[l].att; a.ffw[l] = L.reg[0].att[l].ffw;
+            a.l1w[l] = L.reg[0].ffn[l].l1w; a.l2w[l] = L.reg[0].ffn[l].l2w;
+        }
+        a.stream = reinterpret_cast<__nv_bfloat16*>(ws + w.reg_stream);
+        CHROMO_TRY(pack_reg_stream(a, NR, st));
+    }
     if (!w.training) {
         // Folded single-query attention weights (exact re-association, inference only):
         //   QK[(row,h), :] = (W_k[h]^T W_q[h]) x_row        -> one [H*D, D] linear replaces Q and the QK fold
@@ -602,6 +614,20 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         const FfnOff& rf = L.reg[0].ffn[l];
         const long long so = (long long)w.rslot(l) * w.r_slot;
         const float* xin = l == 0 ? ws + w.r_xin : ws + w.r_out + (long long)w.rslot(l - 1) * w.r_slot;
+        if (w.reg_fused && !getenv("CHROMO_NO_REG_FUSED")) {
+            // whole layer in one launch (reg_fused.cu)
+            RegFusedArgs a;
+            a.B = B; a.S = S; a.G = 128 / S; a.n_tiles = (B + a.G - 1) / a.G;
+            a.x = xin; a.x_z = RS; a.y = ws + w.r_out + so; a.y_z = RS;
+            a.wstream = reinterpret_cast<const __nv_bfloat16*>(ws + w.reg_stream) + (long long)l * reg_stream_elems_per_layer();
+            a.w_z = (long long)c->reg_layers * reg_stream_elems_per_layer();
+            a.gamma_f = P + ra.gamma_f; a.bo = P + ra.ffb; a.ln1w = P + ra.lnw; a.ln1b = P + ra.lnb;
+            a.b1 = P + rf.l1b; a.b2 = P + rf.l2b; a.ln2w = P + rf.lnw; a.ln2b = P + rf.lnb; a.p_z = L.reg_stride;
+            a.freq = in->freq;
+            for (int r = 0; r < NR; ++r) a.imask[r] = in->imask[r];
+            CHROMO_TRY(launch_reg_layer_fused(a, NR, st));
+            continue;
+        }
         {   // proj = X W_att^T  (q|k|v|gate)                       modules.py:38
             GemmArgs g = gemm_args();
             g.A = xin; g.lda = D; g.sA1 = RS;

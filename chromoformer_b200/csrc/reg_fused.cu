@@ -1,0 +1,473 @@
+// One Regulation-transformer layer (modules.py:28-30,37-88,100-101 with gate=True) as ONE kernel.
+//
+// A CTA owns a tile of G genes (G*S <= 128 token rows) for the whole layer; activations never
+// leave the SM between the fused projection and the layer output:
+//
+//   X (FP32, HBM) -> BF16 A-operand in shared memory
+//   for each pair of heads t = 0..3:
+//       [q|k] and [v|gate] = X W^T          2 x (8 tcgen05.mma 128x128x16) -> TMEM (double buffered)
+//       k, v  TMEM -> shared (BF16);  one thread per (token, head): scores vs the gene's S keys,
+//       gamma*freq bias, mask(-1e9), softmax, P.V, sigmoid gate -> BF16 into the out-proj A-operand
+//   out-proj (K = 256, two chunks) -> TMEM -> + bias + residual X -> LayerNorm -> U (registers + BF16 operand)
+//   FFN-1 (N = 256, two chunks)    -> TMEM -> + bias, ReLU -> BF16 operand
+//   FFN-2 (K = 256, two chunks)    -> TMEM -> + bias + U -> LayerNorm -> Y (FP32, HBM, coalesced)
+//
+// The 14 weight chunks of a layer ([128 x 128] BF16 each, 448 KB, pre-packed in consumption
+// order by pack_reg_stream) are streamed through a 3-deep ring of 32 KB stages by 1-D TMA bulk
+// copies; a dedicated driver warp issues the copies and all tcgen05.mma, eight compute warps do
+// the TMEM epilogues and the attention.  mbarriers carry every hand-off.
+#include "common.cuh"
+#include "kernels.cuh"
+#include "reg_fused.cuh"
+#include "umma_ptx.cuh"
+
+namespace chromo {
+
+namespace {
+
+constexpr int RF_THREADS = 288;            // 8 compute warps + 1 driver warp
+constexpr int RF_NSTAGE = 3;
+constexpr int RF_CHUNK_ELEMS = 128 * 128;
+constexpr uint32_t RF_CHUNK_BYTES = RF_CHUNK_ELEMS * 2;
+constexpr int RF_NCHUNK = 14;
+
+// shared-memory map (bytes)
+constexpr uint32_t OFF_XB = 0;                              // [128 x 128] BF16 operand (X, later U)
+constexpr uint32_t OFF_ATT = 32768;                         // [128 x 256] BF16 operand (att, later F, later store staging)
+constexpr uint32_t OFF_STAGE = OFF_ATT + 65536;             // 3 x 32 KB weight ring
+constexpr uint32_t OFF_K = OFF_STAGE + RF_NSTAGE * RF_CHUNK_BYTES;   // [128 x 64] BF16, 16-byte chunks XOR-swizzled by row
+constexpr uint32_t OFF_V = OFF_K + 16384;
+constexpr uint32_t OFF_CTL = OFF_V + 16384;                 // mbarriers + TMEM slot
+constexpr uint32_t RF_SMEM = OFF_CTL + 256;
+
+enum { B_FULL0 = 0, B_FREE0 = 3, B_ACCQ0 = 6, B_ACCQFREE0 = 8, B_XREADY = 10, B_ATTREADY, B_UREADY, B_FREADY,
+       B_ACCO, B_ACCF1, B_ACCF2, B_COUNT };
+
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar);
+}
+__device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* v) {
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        v[2 * k] = __uint_as_float(w[k] << 16);
+        v[2 * k + 1] = __uint_as_float(w[k] & 0xffff0000u);
+    }
+}
+// byte offset of the 16-byte chunk holding columns [8*kc, 8*kc+8) of `row` in a K-major operand of K columns
+__device__ __forceinline__ uint32_t op_chunk(int row, int kc, int K) {
+    return (uint32_t)(row >> 3) * (uint32_t)(K * 16) + (uint32_t)kc * 128u + (uint32_t)(row & 7) * 16u;
+}
+
+}  // namespace
+
+template <int SMAX>
+__global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const RegFusedArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_CTL);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int z = blockIdx.y, tile = blockIdx.x;
+    const int S = a.S, G = a.G;
+    const long long row0 = (long long)tile * G * S;            // first token row of this tile
+    const int rows_valid = min((long long)G * S, (long long)a.B * S - row0);
+
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        for (int i = 0; i < RF_NSTAGE; ++i) { mbar_init(&bars[B_FULL0 + i], 1); mbar_init(&bars[B_FREE0 + i], 1); }
+        mbar_init(&bars[B_ACCQ0], 1); mbar_init(&bars[B_ACCQ0 + 1], 1);
+        mbar_init(&bars[B_ACCQFREE0], 8); mbar_init(&bars[B_ACCQFREE0 + 1], 8);
+        mbar_init(&bars[B_XREADY], 8); mbar_init(&bars[B_ATTREADY], 8);
+        mbar_init(&bars[B_UREADY], 8); mbar_init(&bars[B_FREADY], 8);
+        mbar_init(&bars[B_ACCO], 1); mbar_init(&bars[B_ACCF1], 1); mbar_init(&bars[B_ACCF2], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 8) {
+        // ===================================================== driver: TMA + tcgen05.mma ====
+        if (lane == 0) {
+            const __nv_bfloat16* wsrc = a.wstream + z * a.w_z;
+            const uint32_t idesc = umma_idesc_bf16(128, 128);
+            const uint32_t s_xb = smem_u32(smem + OFF_XB), s_att = smem_u32(smem + OFF_ATT);
+            auto issue_load = [&](int c) {
+                const int st = c % RF_NSTAGE;
+                if (c >= RF_NSTAGE) mbar_wait(&bars[B_FREE0 + st], ((c / RF_NSTAGE) - 1) & 1);
+                mbar_expect_tx(&bars[B_FULL0 + st], RF_CHUNK_BYTES);
+                tma_bulk_g2s(smem + OFF_STAGE + st * RF_CHUNK_BYTES, wsrc + (long long)c * RF_CHUNK_ELEMS, RF_CHUNK_BYTES,
+                             &bars[B_FULL0 + st]);
+            };
+            auto consume = [&](int c, uint32_t a_addr, uint32_t a_sbo, uint32_t col, bool accumulate) {
+                if (c + 2 < RF_NCHUNK) issue_load(c + 2);
+                const int st = c % RF_NSTAGE;
+                mbar_wait(&bars[B_FULL0 + st], (c / RF_NSTAGE) & 1);
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(smem + OFF_STAGE + st * RF_CHUNK_BYTES);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(tmem + col, umma_smem_desc(a_addr + k * 256, 128, a_sbo),
+                              umma_smem_desc(b_addr + k * 256, 128, 2048), idesc, (accumulate || k > 0) ? 1u : 0u);
+                umma_commit(&bars[B_FREE0 + st]);
+            };
+            issue_load(0);
+            issue_load(1);
+            mbar_wait(&bars[B_XREADY], 0);
+            for (int t = 0; t < 4; ++t) {
+                const int buf = t & 1;
+                if (t >= 2) mbar_wait(&bars[B_ACCQFREE0 + buf], 0);
+                consume(2 * t, s_xb, 2048, 256 * buf, false);          // [q | k] of heads 2t, 2t+1
+                consume(2 * t + 1, s_xb, 2048, 256 * buf + 128, false); // [v | gate]
+                umma_commit(&bars[B_ACCQ0 + buf]);
+            }
+            mbar_wait(&bars[B_ATTREADY], 0);
+            consume(8, s_att, 4096, 0, false);                          // out-projection, K halves
+            consume(9, s_att + 2048, 4096, 0, true);
+            umma_commit(&bars[B_ACCO]);
+            mbar_wait(&bars[B_UREADY], 0);
+            consume(10, s_xb, 2048, 256, false);                        // FFN-1, N halves
+            consume(11, s_xb, 2048, 384, false);
+            umma_commit(&bars[B_ACCF1]);
+            mbar_wait(&bars[B_FREADY], 0);
+            consume(12, s_att, 4096, 0, false);                         // FFN-2, K halves
+            consume(13, s_att + 2048, 4096, 0, true);
+            umma_commit(&bars[B_ACCF2]);
+        }
+    } else {
+        // ===================================================== compute warps =================
+        const int lq = warp & 3, ch = warp >> 2;
+        const int row = lq * 32 + lane;                      // tile row == TMEM lane
+        const bool valid = row < rows_valid;
+        const long long grow = row0 + row;
+        const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
+        const float* X = a.x + z * a.x_z;
+        float v[32];
+
+        // ---- phase 0: X -> BF16 operand
+        {
+            for (int u0 = warp; u0 < 64; u0 += 32) {
+                float4 x[4][2];
+                int r_[4], kc_[4];
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const int u = u0 + q * 8;
+                    r_[q] = (u & 15) * 8 + (lane >> 2);
+                    kc_[q] = (u >> 4) * 4 + (lane & 3);
+                    x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (r_[q] < rows_valid) {
+                        const float* p = X + (row0 + r_[q]) * 128 + kc_[q] * 8;
+                        x[q][0] = __ldg(reinterpret_cast<const float4*>(p));
+                        x[q][1] = __ldg(reinterpret_cast<const float4*>(p + 4));
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    uint4 pk;
+                    pk.x = pack2(x[q][0].x, x[q][0].y); pk.y = pack2(x[q][0].z, x[q][0].w);
+                    pk.z = pack2(x[q][1].x, x[q][1].y); pk.w = pack2(x[q][1].z, x[q][1].w);
+                    *reinterpret_cast<uint4*>(smem + OFF_XB + op_chunk(r_[q], kc_[q], 128)) = pk;
+                }
+            }
+            fence_async_smem();
+            warp_arrive(&bars[B_XREADY], lane);
+        }
+
+        // ---- phase 1: per pair of heads: k, v -> shared; attention; att -> BF16 operand
+        const int gl = row / S, qi = row % S;                 // gene within tile, query token
+        const long long gene = (long long)tile * G + gl;
+        const float* freq = a.freq + (valid ? (gene * S + qi) * S : 0);
+        const uint8_t* mask = a.imask[z] + (valid ? (gene * S + qi) * S : 0);
+        const float scale = 0.17677669529663687f;            // 1/sqrt(32)
+        for (int t = 0; t < 4; ++t) {
+            const int buf = t & 1;
+            const uint32_t qb = trow + 256 * buf;
+            mbar_wait(&bars[B_ACCQ0 + buf], (t >> 1) & 1);
+            tc_fence_after();
+            compute_barrier();                                // previous pair's readers are done with sK / sV
+            {   // ch 0 copies k (cols 64..127), ch 1 copies v (cols 128..191)
+                uint8_t* dst = smem + (ch == 0 ? OFF_K : OFF_V) + row * 128;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    tmem_ld32(qb + 64 + 64 * ch + 32 * half, v);
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint4 pk;
+                        pk.x = pack2(v[8 * c], v[8 * c + 1]); pk.y = pack2(v[8 * c + 2], v[8 * c + 3]);
+                        pk.z = pack2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack2(v[8 * c + 6], v[8 * c + 7]);
+                        *reinterpret_cast<uint4*>(dst + (((half * 4 + c) ^ (row & 7)) << 4)) = pk;
+                    }
+                }
+            }
+            compute_barrier();
+            // one thread per (token row, head 2t + ch)
+            const int head = 2 * t + ch;
+            float q[32];
+            tmem_ld32(qb + 32 * ch, q);
+            const float gamma = a.gamma_f[z * a.p_z + head];
+            float s[SMAX];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < SMAX; ++j) {
+                s[j] = -INFINITY;
+                if (j < S) {
+                    const int kr = gl * S + j;
+                    const uint8_t* kp = smem + OFF_K + (kr & 127) * 128;
+                    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float kv[8];
+                        unpack8(*reinterpret_cast<const uint4*>(kp + (((4 * ch + c) ^ (kr & 7)) << 4)), kv);
+#pragma unroll
+                        for (int e = 0; e < 8; e += 2) {
+                            d0 = fmaf(q[8 * c + e], kv[e], d0);
+                            d1 = fmaf(q[8 * c + e + 1], kv[e + 1], d1);
+                        }
+                    }
+                    float sc = (d0 + d1) * scale;
+                    if (valid) {
+                        sc += gamma * freq[j];
+                        if (mask[j]) sc = -1e9f;
+                    }
+                    s[j] = sc;
+                    mx = fmaxf(mx, sc);
+                }
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < SMAX; ++j)
+                if (j < S) { s[j] = __expf(s[j] - mx); sum += s[j]; }
+            const float inv = 1.f / sum;
+            float o[32];
+#pragma unroll
+            for (int d = 0; d < 32; ++d) o[d] = 0.f;
+#pragma unroll
+            for (int j = 0; j < SMAX; ++j) {
+                if (j < S) {
+                    const float p = s[j] * inv;
+                    const int kr = gl * S + j;
+                    const uint8_t* vp = smem + OFF_V + (kr & 127) * 128;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        float vv[8];
+                        unpack8(*reinterpret_cast<const uint4*>(vp + (((4 * ch + c) ^ (kr & 7)) << 4)), vv);
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[8 * c + e] = fmaf(p, vv[e], o[8 * c + e]);
+                    }
+                }
+            }
+            tmem_ld32(qb + 192 + 32 * ch, v);                 // gate
+            tc_fence_before();
+            warp_arrive(&bars[B_ACCQFREE0 + buf], lane);      // this TMEM half may be overwritten
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float r[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) r[e] = valid ? o[8 * c + e] / (1.f + __expf(-v[8 * c + e])) : 0.f;
+                uint4 pk;
+                pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
+                *reinterpret_cast<uint4*>(smem + OFF_ATT + op_chunk(row, 8 * t + 4 * ch + c, 256)) = pk;
+            }
+        }
+        fence_async_smem();
+        warp_arrive(&bars[B_ATTREADY], lane);
+
+        // ---- phase 2: out-projection epilogue: + bias + residual, LayerNorm -> U
+        float* red = reinterpret_cast<float*>(smem + OFF_K);  // [2][2][128][2] partial sums (k, v are dead)
+        float u_keep[2][32];
+        {
+            mbar_wait(&bars[B_ACCO], 0);
+            tc_fence_after();
+            const float* bo = a.bo + z * a.p_z;
+            float sum = 0.f, sq = 0.f;
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci) {
+                const int c = (2 * ci + ch) * 32;
+                tmem_ld32(trow + c, v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 r4 = make_float4(0, 0, 0, 0);
+                    if (valid) r4 = *reinterpret_cast<const float4*>(X + grow * 128 + c + j);
+                    const float4 b4 = *reinterpret_cast<const float4*>(bo + c + j);
+                    const float t0 = v[j] + b4.x + r4.x, t1 = v[j + 1] + b4.y + r4.y;
+                    const float t2 = v[j + 2] + b4.z + r4.z, t3 = v[j + 3] + b4.w + r4.w;
+                    u_keep[ci][j] = t0; u_keep[ci][j + 1] = t1; u_keep[ci][j + 2] = t2; u_keep[ci][j + 3] = t3;
+                    sum += (t0 + t1) + (t2 + t3);
+                    sq += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
+                }
+            }
+            tc_fence_before();
+            red[(ch * 128 + row) * 2] = sum;
+            red[(ch * 128 + row) * 2 + 1] = sq;
+            compute_barrier();
+            sum += red[((1 - ch) * 128 + row) * 2];
+            sq += red[((1 - ch) * 128 + row) * 2 + 1];
+            const float mean = sum * (1.f / 128.f);
+            const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
+            const float* lw = a.ln1w + z * a.p_z;
+            const float* lb = a.ln1b + z * a.p_z;
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci) {
+                const int c = (2 * ci + ch) * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float r[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) {
+                        r[e] = (u_keep[ci][j + e] - mean) * rstd * lw[c + j + e] + lb[c + j + e];
+                        u_keep[ci][j + e] = r[e];
+                    }
+                    uint4 pk;
+                    pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
+                    *reinterpret_cast<uint4*>(smem + OFF_XB + op_chunk(row, (c + j) >> 3, 128)) = pk;
+                }
+            }
+            fence_async_smem();
+            warp_arrive(&bars[B_UREADY], lane);
+        }
+
+        // ---- phase 3: FFN-1 epilogue: + bias, ReLU -> BF16 operand (over the dead att tile)
+        {
+            mbar_wait(&bars[B_ACCF1], 0);
+            tc_fence_after();
+            const float* b1 = a.b1 + z * a.p_z;
+#pragma unroll
+            for (int ci = 0; ci < 4; ++ci) {
+                const int c = (2 * ci + ch) * 32;
+                tmem_ld32(trow + 256 + c, v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float r[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) r[e] = fmaxf(v[j + e] + b1[c + j + e], 0.f);
+                    uint4 pk;
+                    pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
+                    *reinterpret_cast<uint4*>(smem + OFF_ATT + op_chunk(row, (c + j) >> 3, 256)) = pk;
+                }
+            }
+            tc_fence_before();
+            fence_async_smem();
+            warp_arrive(&bars[B_FREADY], lane);
+        }
+
+        // ---- phase 4: FFN-2 epilogue: + bias + U, LayerNorm -> Y (coalesced through shared)
+        {
+            mbar_wait(&bars[B_ACCF2], 0);
+            tc_fence_after();
+            const float* b2 = a.b2 + z * a.p_z;
+            float* red2 = red + 512;
+            float sum = 0.f, sq = 0.f;
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci) {
+                const int c = (2 * ci + ch) * 32;
+                tmem_ld32(trow + c, v);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const float t0 = v[j] + b2[c + j] + u_keep[ci][j];
+                    u_keep[ci][j] = t0;
+                    sum += t0;
+                    sq += t0 * t0;
+                }
+            }
+            tc_fence_before();
+            red2[(ch * 128 + row) * 2] = sum;
+            red2[(ch * 128 + row) * 2 + 1] = sq;
+            compute_barrier();
+            sum += red2[((1 - ch) * 128 + row) * 2];
+            sq += red2[((1 - ch) * 128 + row) * 2 + 1];
+            const float mean = sum * (1.f / 128.f);
+            const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
+            const float* lw = a.ln2w + z * a.p_z;
+            const float* lb = a.ln2b + z * a.p_z;
+            float* Y = a.y + z * a.y_z;
+            float* stage = reinterpret_cast<float*>(smem + OFF_ATT) + warp * (32 * 33);   // FFN-2 MMAs are complete
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci) {
+                const int c = (2 * ci + ch) * 32;
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    stage[lane * 33 + j] = (u_keep[ci][j] - mean) * rstd * lw[c + j] + lb[c + j];
+                __syncwarp();
+                const int cq = (lane & 7) * 4;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + (lane >> 3);
+                    const float* sp = stage + r * 33 + cq;
+                    const int trw = lq * 32 + r;
+                    if (trw < rows_valid)
+                        *reinterpret_cast<float4*>(Y + (row0 + trw) * 128 + c + cq) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                }
+                __syncwarp();
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------- weight stream ----
+// 14 chunks of [128 rows x 128 k] BF16 per (resolution, layer) in UMMA tile order, in the order
+// the kernel consumes them (see the header comment).
+__global__ void pack_reg_stream_kernel(RegStreamArgs a) {
+    const int z = blockIdx.z, l = blockIdx.y;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;        // (chunk, row, kc)
+    if (i >= RF_NCHUNK * 128 * 16) return;
+    const int c = i / (128 * 16), n = (i / 16) % 128, kc = i % 16;
+    const float* P = a.params + z * a.p_z;
+    const float* src;
+    if (c < 8) {                 // fused projection [1024, 128]: q rows 0.., k 256.., v 512.., gate 768..
+        const int t = c >> 1, base = (c & 1) ? 512 : 0;
+        const int r = base + (n < 64 ? 64 * t + n : 256 + 64 * t + (n - 64));
+        src = P + a.att[l] + (long long)r * 128 + kc * 8;
+    } else if (c < 10) {         // out-projection [128, 256], K halves
+        src = P + a.ffw[l] + (long long)n * 256 + (c - 8) * 128 + kc * 8;
+    } else if (c < 12) {         // FFN-1 [256, 128], N halves
+        src = P + a.l1w[l] + (long long)((c - 10) * 128 + n) * 128 + kc * 8;
+    } else {                     // FFN-2 [128, 256], K halves
+        src = P + a.l2w[l] + (long long)n * 256 + (c - 12) * 128 + kc * 8;
+    }
+    const float4 x0 = *reinterpret_cast<const float4*>(src), x1 = *reinterpret_cast<const float4*>(src + 4);
+    uint4 pk;
+    pk.x = pack2(x0.x, x0.y); pk.y = pack2(x0.z, x0.w); pk.z = pack2(x1.x, x1.y); pk.w = pack2(x1.z, x1.w);
+    __nv_bfloat16* dst = a.stream + ((long long)(z * a.n_layers + l) * RF_NCHUNK + c) * RF_CHUNK_ELEMS +
+                         ((n >> 3) * 16 + kc) * 64 + (n & 7) * 8;
+    *reinterpret_cast<uint4*>(dst) = pk;
+}
+
+long long reg_stream_elems_per_layer() { return (long long)RF_NCHUNK * RF_CHUNK_ELEMS; }
+
+int pack_reg_stream(const RegStreamArgs& a, int n_res, cudaStream_t st) {
+    dim3 grid((RF_NCHUNK * 128 * 16 + 255) / 256, a.n_layers, n_res);
+    pack_reg_stream_kernel<<<grid, 256, 0, st>>>(a);
+    CHROMO_CHECK_LAUNCH("pack_reg_stream");
+    return CHROMO_OK;
+}
+
+int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e1 = cudaFuncSetAttribute(reg_layer_fused_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaError_t e2 = cudaFuncSetAttribute(reg_layer_fused_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("reg_fused smem attribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return CHROMO_ECUDA; }
+        configured = true;
+    }
+    dim3 grid(a.n_tiles, n_res);
+    if (a.S <= 9) reg_layer_fused_kernel<9><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
+    else reg_layer_fused_kernel<17><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
+    CHROMO_CHECK_LAUNCH("reg_layer_fused");
+    return CHROMO_OK;
+}
+
+}  // namespace chromo

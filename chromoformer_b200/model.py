@@ -375,7 +375,8 @@ class _ChromoformerCore(nn.Module):
         if (flags & _lib.F_BF16) and not training:
             # the packed BF16 weights live at the (batch-independent) front of the cached workspace:
             # reuse them while neither the buffer nor the parameters changed
-            packed_key = (ws.data_ptr(), self._flat._version, self._param_epoch,
+            # (p.data = view keeps each parameter's own version counter, so sum them)
+            packed_key = (ws.data_ptr(), sum(p._version for (_, p, _, _) in self._slots), self._param_epoch,
                           tuple(io.cfg.n_bins[r] for r in range(io.cfg.n_res)))
             if packed_key == self._packed_key:
                 flags |= _lib.F_PACKED

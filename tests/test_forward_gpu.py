@@ -203,3 +203,19 @@ def test_bf16_packed_weight_cache_is_invalidated():
         a_model.fc_head[2].bias.add_(1.0)
     a4 = InferenceEngine(a_model, chunk=256).predict_device(dev).cpu()
     assert torch.allclose(a4, b1 + 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("n,i_max", [(3, 8), (14, 8), (15, 8), (200, 16), (1, 8)])
+def test_bf16_fused_regulation_tile_edges(n, i_max):
+    """Partial / single / multiple 128-row tiles of the fused Regulation-layer kernel, 9 and 17 tokens."""
+    model = _mk(seed=5)
+    batch = synthetic.make_batch(n, i_max=i_max, ragged=True, seed=30 + n, stress=True)
+    model.cuda().eval()
+    args = synthetic.forward_args(batch, "cuda")
+    with torch.no_grad():
+        model.precision = "fp32"
+        want = model(*args).cpu()
+        model.precision = "bf16"
+        got = model(*args).cpu()
+    assert torch.isfinite(got).all()
+    assert (got - want).abs().max().item() < 1e-2
