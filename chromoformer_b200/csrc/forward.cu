@@ -124,6 +124,105 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(AttnRowsArgs a) {
     }
 }
 
+// Register-resident variant: one warp per REGION, all heads; the region's features are read from
+// HBM once (not once per head and pass) and scores never round-trip through memory.  NJ = ceil(n/32).
+template <int NJ, int H>
+__global__ void __launch_bounds__(128) attn_rows_reg_kernel(AttnRowsArgs a) {
+    const int region = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (region >= a.rows / H) return;
+    const int n = a.n, F = a.F, D = a.D;
+    const float* x = a.x + (long long)(region / a.x_div) * n * F;
+    const uint8_t* mk = a.mask + (long long)region * a.mask_stride + a.mask_row_offset;
+    float xr[NJ][8];
+    bool msk[NJ];
+#pragma unroll
+    for (int jj = 0; jj < NJ; ++jj) {
+        const int j = lane + 32 * jj;
+        msk[jj] = true;
+#pragma unroll
+        for (int f = 0; f < 8; ++f) xr[jj][f] = 0.f;
+        if (j < n) {
+            msk[jj] = mk[j] != 0;
+#pragma unroll
+            for (int f = 0; f < 8; ++f)
+                if (f < F) xr[jj][f] = x[(long long)j * F + f];
+        }
+    }
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const long long rowi = (long long)region * H + h;
+        const float* qk = a.qk + rowi * D;
+        float* P = a.P + rowi * n;
+        float u[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) u[f] = 0.f;
+        for (int d = lane; d < D; d += 32) {
+            const float q = qk[d];
+            const float* w = a.w_in + (long long)d * F;
+#pragma unroll
+            for (int f = 0; f < 8; ++f)
+                if (f < F) u[f] = fmaf(w[f], q, u[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) u[f] += __shfl_xor_sync(0xffffffffu, u[f], o);
+        float s[NJ];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+            const int j = lane + 32 * jj;
+            s[jj] = -INFINITY;
+            if (j < n) {
+                float t = P[j];
+#pragma unroll
+                for (int f = 0; f < 8; ++f) t = fmaf(u[f], xr[jj][f], t);
+                t *= a.scale;
+                if (msk[jj]) t = -1e9f;
+                s[jj] = t;
+                mx = fmaxf(mx, t);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+            s[jj] = (lane + 32 * jj < n) ? expf(s[jj] - mx) : 0.f;
+            sum += s[jj];
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.f / sum;
+        float xb[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) xb[f] = 0.f;
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+            const int j = lane + 32 * jj;
+            const float p = s[jj] * inv;
+            if (j < n) P[j] = p;
+#pragma unroll
+            for (int f = 0; f < 8; ++f) xb[f] = fmaf(p, xr[jj][f], xb[f]);
+        }
+#pragma unroll
+        for (int f = 0; f < 8; ++f)
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) xb[f] += __shfl_xor_sync(0xffffffffu, xb[f], o);
+        if (lane < 8) a.xbar[rowi * 8 + lane] = lane < F ? xb[lane] : 0.f;
+        float* cb = a.cbar + rowi * D;
+        for (int d = lane; d < D; d += 32) {
+            const float* w = a.w_in + (long long)d * F;
+            float acc = 0.f;
+#pragma unroll
+            for (int f = 0; f < 8; ++f)
+                if (f < F) acc = fmaf(w[f], xb[f], acc);
+            cb[d] = acc;
+        }
+    }
+}
+
 // Regulation self-attention (modules.py:37-46,58-82): one THREAD per (gene, head, query token).
 // The S threads of a (gene, head) group sit in adjacent lanes, so their K/V loads hit the same
 // addresses (one transaction, broadcast) and nothing is reduced across lanes:
@@ -257,6 +356,14 @@ int launch_reg_attention(const RegAttnArgs& a, int nz, cudaStream_t st) {
 
 int launch_attn_rows(const AttnRowsArgs& a, cudaStream_t st) {
     const int wpb = 8;
+    if (a.H == 2 && a.n <= 416) {
+        const int regions = a.rows / 2, blocks = (regions + 3) / 4;
+        if (a.n <= 32) attn_rows_reg_kernel<1, 2><<<blocks, 128, 0, st>>>(a);
+        else if (a.n <= 96) attn_rows_reg_kernel<3, 2><<<blocks, 128, 0, st>>>(a);
+        else attn_rows_reg_kernel<13, 2><<<blocks, 128, 0, st>>>(a);
+        CHROMO_CHECK_LAUNCH("attn_rows_reg");
+        return CHROMO_OK;
+    }
     attn_rows_kernel<<<(a.rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(a);
     CHROMO_CHECK_LAUNCH("attn_rows");
     return CHROMO_OK;
