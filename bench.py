@@ -260,6 +260,31 @@ def main():
                                   "achieved_gbs": (126000 + 4500 + 1296) * genes_per_s / world / 1e9,
                                   "hbm_peak_gbs": peaks["hbm_gbs"]}}
 
+    # ---------------- input path kernel (data.py:68-113 on the device): HBM-bound byte work -------
+    import numpy as np
+    n_reg, L = 4096, 40000                                  # 2.29 GB of FP16 depth: larger than L2
+    raw = (torch.rand(n_reg * 7 * L // 2, device=dev) * 3).to(torch.float16)
+    raw = torch.cat([raw, raw])[: n_reg * 7 * L]
+    table = np.zeros(n_reg, dtype=[("offset", "<i8"), ("length", "<i4"), ("start", "<i4"), ("width", "<i4"), ("flip", "<i4")])
+    table["offset"] = np.arange(n_reg, dtype=np.int64) * 7 * L
+    table["length"], table["width"], table["flip"] = L, L, np.arange(n_reg) % 2
+    tab = torch.from_numpy(table.view(np.uint8).reshape(-1)).to(dev)
+    feats = [torch.empty(n_reg, n, 7, device=dev) for n in (20, 80, 400)]
+    spans = torch.empty(3, n_reg, 2, dtype=torch.int32, device=dev)
+    ptrs = (ctypes.c_void_p * 3)(*[f.data_ptr() for f in feats])
+    bins_c, nb_c = (ctypes.c_int32 * 3)(2000, 500, 100), (ctypes.c_int32 * 3)(20, 80, 400)
+
+    def one_bin():
+        _lib.check(lib.chromo_bin_regions(raw.data_ptr(), tab.data_ptr(), n_reg, 7, 3, bins_c, nb_c, ptrs,
+                                          spans.data_ptr(), st), "chromo_bin_regions")
+    ms_b = timed(one_bin, 10, 3)
+    bytes_b = n_reg * 7 * L * 2 + n_reg * 500 * 7 * 4
+    input_path = {"kernel": "bin_regions_kernel", "bound": "hbm", "regions": n_reg, "bp_per_region": L,
+                  "algorithmic_bytes": bytes_b, "ms_per_launch": ms_b, "achieved": bytes_b / (ms_b * 1e-3) / 1e9,
+                  "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bytes_b / (ms_b * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                  "regions_per_s": n_reg / (ms_b * 1e-3)}
+    del raw, feats
+
     # ---------------- training step (configs[2]): fwd + bwd + AdamW, DP all-reduce ----------
     train = None
     if not args.no_train:
@@ -294,7 +319,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": workload_config(args), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-                "roofline": roofline, "cpu_baseline": cpu, "train": train}
+                "roofline": roofline, "input_path": input_path, "cpu_baseline": cpu, "train": train}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -111,7 +111,6 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                              &bars[B_FULL0 + st]);
             };
             auto consume = [&](int c, uint32_t a_addr, uint32_t a_sbo, uint32_t col, bool accumulate) {
-                if (c + 2 < RF_NCHUNK) issue_load(c + 2);
                 const int st = c % RF_NSTAGE;
                 mbar_wait(&bars[B_FULL0 + st], (c / RF_NSTAGE) & 1);
                 tc_fence_after();
@@ -121,9 +120,12 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                     umma_bf16(tmem + col, umma_smem_desc(a_addr + k * 256, 128, a_sbo),
                               umma_smem_desc(b_addr + k * 256, 128, 2048), idesc, (accumulate || k > 0) ? 1u : 0u);
                 umma_commit(&bars[B_FREE0 + st]);
+                // refill the ring behind the MMAs just queued (waits for chunk c-1 only)
+                if (c + 2 < RF_NCHUNK && c >= 1) issue_load(c + 2);
             };
             issue_load(0);
             issue_load(1);
+            issue_load(2);
             mbar_wait(&bars[B_XREADY], 0);
             for (int t = 0; t < 4; ++t) {
                 const int buf = t & 1;
@@ -190,6 +192,16 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         const float* freq = a.freq + (valid ? (gene * S + qi) * S : 0);
         const uint8_t* mask = a.imask[z] + (valid ? (gene * S + qi) * S : 0);
         const float scale = 0.17677669529663687f;            // 1/sqrt(32)
+        float fr[SMAX];
+        unsigned mbits = 0;
+#pragma unroll
+        for (int j = 0; j < SMAX; ++j) {
+            fr[j] = 0.f;
+            if (j < S && valid) {
+                fr[j] = freq[j];
+                if (mask[j]) mbits |= 1u << j;
+            }
+        }
         for (int t = 0; t < 4; ++t) {
             const int buf = t & 1;
             const uint32_t qb = trow + 256 * buf;
@@ -235,11 +247,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                             d1 = fmaf(q[8 * c + e + 1], kv[e + 1], d1);
                         }
                     }
-                    float sc = (d0 + d1) * scale;
-                    if (valid) {
-                        sc += gamma * freq[j];
-                        if (mask[j]) sc = -1e9f;
-                    }
+                    float sc = fmaf(gamma, fr[j], (d0 + d1) * scale);
+                    if ((mbits >> j) & 1u) sc = -1e9f;
                     s[j] = sc;
                     mx = fmaxf(mx, sc);
                 }
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             for (int c = 0; c < 4; ++c) {
                 float r[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) r[e] = valid ? o[8 * c + e] / (1.f + __expf(-v[8 * c + e])) : 0.f;
+                for (int e = 0; e < 8; ++e) r[e] = valid ? __fdividef(o[8 * c + e], 1.f + __expf(-v[8 * c + e])) : 0.f;
                 uint4 pk;
                 pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
                 *reinterpret_cast<uint4*>(smem + OFF_ATT + op_chunk(row, 8 * t + 4 * ch + c, 256)) = pk;
@@ -283,13 +292,25 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         fence_async_smem();
         warp_arrive(&bars[B_ATTREADY], lane);
 
+        // small FP32 vectors of the layer -> shared (the v tile is dead): bo, ln1w, ln1b, b2, ln2w, ln2b, b1[256]
+        float* prm = reinterpret_cast<float*>(smem + OFF_V);
+        compute_barrier();                                    // every warp is done reading v
+        {
+            const float* srcs[6] = {a.bo, a.ln1w, a.ln1b, a.b2, a.ln2w, a.ln2b};
+            const int ct = warp * 32 + lane;                  // 0..255
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                if (ct < 128) prm[k * 128 + ct] = srcs[k][z * a.p_z + ct];
+            prm[768 + ct] = a.b1[z * a.p_z + ct];
+        }
+        compute_barrier();
         // ---- phase 2: out-projection epilogue: + bias + residual, LayerNorm -> U
         float* red = reinterpret_cast<float*>(smem + OFF_K);  // [2][2][128][2] partial sums (k, v are dead)
         float u_keep[2][32];
         {
             mbar_wait(&bars[B_ACCO], 0);
             tc_fence_after();
-            const float* bo = a.bo + z * a.p_z;
+            const float* bo = prm;
             float sum = 0.f, sq = 0.f;
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci) {
@@ -315,8 +336,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             sq += red[((1 - ch) * 128 + row) * 2 + 1];
             const float mean = sum * (1.f / 128.f);
             const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
-            const float* lw = a.ln1w + z * a.p_z;
-            const float* lb = a.ln1b + z * a.p_z;
+            const float* lw = prm + 128;
+            const float* lb = prm + 256;
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci) {
                 const int c = (2 * ci + ch) * 32;
@@ -341,7 +362,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         {
             mbar_wait(&bars[B_ACCF1], 0);
             tc_fence_after();
-            const float* b1 = a.b1 + z * a.p_z;
+            const float* b1 = prm + 768;
 #pragma unroll
             for (int ci = 0; ci < 4; ++ci) {
                 const int c = (2 * ci + ch) * 32;
@@ -365,7 +386,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         {
             mbar_wait(&bars[B_ACCF2], 0);
             tc_fence_after();
-            const float* b2 = a.b2 + z * a.p_z;
+            const float* b2 = prm + 384;
             float* red2 = red + 512;
             float sum = 0.f, sq = 0.f;
 #pragma unroll
@@ -388,8 +409,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             sq += red2[((1 - ch) * 128 + row) * 2 + 1];
             const float mean = sum * (1.f / 128.f);
             const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
-            const float* lw = a.ln2w + z * a.p_z;
-            const float* lb = a.ln2b + z * a.p_z;
+            const float* lw = prm + 512;
+            const float* lb = prm + 640;
             float* Y = a.y + z * a.y_z;
             float* stage = reinterpret_cast<float*>(smem + OFF_ATT) + warp * (32 * 33);   // FFN-2 MMAs are complete
 #pragma unroll
