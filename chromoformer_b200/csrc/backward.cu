@@ -289,9 +289,15 @@ struct Ctx {
     int NR;
 };
 
-inline int ksplit_for(int K) {
-    int s = (K + 255) / 256;
-    return s < 1 ? 1 : (s > 16 ? 16 : s);
+// Split-K factor: the training batch is small (bsz 64 => a few hundred rows), so most gradient
+// GEMMs would otherwise run on a handful of CTAs; split the reduction until ~2 waves of CTAs exist.
+inline int ksplit_for(int K, int M = 4096, int N = 4096, int nz = 1) {
+    const long long ctas = (long long)((M + 63) / 64) * ((N + 63) / 64) * nz;
+    long long want = (2 * 148 + ctas - 1) / ctas;
+    const int by_k = (K + 31) / 32;
+    if (want > by_k) want = by_k;
+    if (want > 32) want = 32;
+    return want < 1 ? 1 : (int)want;
 }
 
 // dX (=|+=) dY W        dY [M,N] (ld ldy), W [N,K] row-major, dX [M,K] (ld lddx)
@@ -302,6 +308,7 @@ int bwd_data(const Ctx& c, const float* dY, int ldy, long long dy_z, const float
     g.B = W; g.ldb = K; g.sB1 = w_z;
     g.C = dX; g.ldc = lddx; g.sC1 = dx_z;
     g.M = M; g.N = K; g.K = N; g.accumulate = accumulate ? 1 : 0;
+    if (accumulate) g.ksplit = ksplit_for(N, M, K, nz);      // atomics are fine on an accumulating output
     return gemm_launch(g, true, false, nz, c.st);
 }
 
@@ -313,14 +320,14 @@ int bwd_weight(const Ctx& c, const float* dY, int ldy, long long dy_z, const flo
     g.B = X; g.ldb = ldx; g.b_div = x_div; g.sB1 = x_z;
     g.C = dW; g.ldc = lddw; g.sC1 = dw_z;
     g.M = N; g.N = K; g.K = M;
-    g.ksplit = ksplit_for(M);
+    g.ksplit = ksplit_for(M, N, K, nz);
     g.accumulate = 1;
     return gemm_launch(g, false, false, nz, c.st);
 }
 
 int bwd_bias(const Ctx& c, const float* dY, int ld, long long dy_z, float* db, long long db_z, int M, int N,
              int nz) {
-    const int rpb = 64;
+    const int rpb = 16;
     dim3 grid((N + 127) / 128, (M + rpb - 1) / rpb, nz);
     colsum_kernel<<<grid, 128, 0, c.st>>>(dY, M, N, ld, dy_z, db, db_z, rpb);
     CHROMO_CHECK_LAUNCH("colsum");
@@ -383,7 +390,7 @@ int sqa_bwd(const Ctx& c, const SqaBwd& s) {
         g.A = s.dAv; g.lda = s.dm; g.sA2 = dh;
         g.B = s.cbar; g.ldb = s.H * D; g.sB2 = D;
         g.C = s.g_wv; g.ldc = D; g.sC2 = (long long)dh * D;
-        g.M = dh; g.N = D; g.K = s.rows; g.zdiv = s.H; g.accumulate = 1; g.ksplit = ksplit_for(s.rows);
+        g.M = dh; g.N = D; g.K = s.rows; g.zdiv = s.H; g.accumulate = 1; g.ksplit = ksplit_for(s.rows, dh, D, s.H);
         CHROMO_TRY(gemm_launch(g, false, false, s.H, c.st));
     }
     {   // dP (PE part) = dCbar PE^T
@@ -423,7 +430,7 @@ int sqa_bwd(const Ctx& c, const SqaBwd& s) {
         g.A = s.q; g.lda = s.dm; g.sA2 = dh;
         g.B = s.dQK; g.ldb = s.H * D; g.sB2 = D;
         g.C = s.g_wk; g.ldc = D; g.sC2 = (long long)dh * D;
-        g.M = dh; g.N = D; g.K = s.rows; g.zdiv = s.H; g.accumulate = 1; g.ksplit = ksplit_for(s.rows);
+        g.M = dh; g.N = D; g.K = s.rows; g.zdiv = s.H; g.accumulate = 1; g.ksplit = ksplit_for(s.rows, dh, D, s.H);
         CHROMO_TRY(gemm_launch(g, false, false, s.H, c.st));
     }
     return CHROMO_OK;

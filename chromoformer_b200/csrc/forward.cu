@@ -134,6 +134,20 @@ __global__ void __launch_bounds__(128) attn_rows_reg_kernel(AttnRowsArgs a) {
     const int n = a.n, F = a.F, D = a.D;
     const float* x = a.x + (long long)(region / a.x_div) * n * F;
     const uint8_t* mk = a.mask + (long long)region * a.mask_stride + a.mask_row_offset;
+    // stage the region's [n, F] feature block through shared memory: coalesced 16-byte global loads,
+    // then stride-F (odd => conflict-free) shared reads into registers
+    extern __shared__ __align__(16) float xs_all[];
+    float* xs = xs_all + (threadIdx.x >> 5) * (NJ * 32 * 8);
+    {
+        const int total = n * F;                           // multiple of 4 for the supported shapes
+        const float4* src = reinterpret_cast<const float4*>(x);
+        if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
+            for (int i = lane; i < total / 4; i += 32) reinterpret_cast<float4*>(xs)[i] = __ldg(src + i);
+        } else {
+            for (int i = lane; i < total; i += 32) xs[i] = x[i];
+        }
+        __syncwarp();
+    }
     float xr[NJ][8];
     bool msk[NJ];
 #pragma unroll
@@ -146,7 +160,7 @@ __global__ void __launch_bounds__(128) attn_rows_reg_kernel(AttnRowsArgs a) {
             msk[jj] = mk[j] != 0;
 #pragma unroll
             for (int f = 0; f < 8; ++f)
-                if (f < F) xr[jj][f] = x[(long long)j * F + f];
+                if (f < F) xr[jj][f] = xs[j * F + f];
         }
     }
 #pragma unroll
@@ -356,11 +370,16 @@ int launch_reg_attention(const RegAttnArgs& a, int nz, cudaStream_t st) {
 
 int launch_attn_rows(const AttnRowsArgs& a, cudaStream_t st) {
     const int wpb = 8;
-    if (a.H == 2 && a.n <= 416) {
+    if (a.H == 2 && a.n > 96 && a.n <= 416) {
+        // long rows: one warp per region, features staged once, scores in registers
         const int regions = a.rows / 2, blocks = (regions + 3) / 4;
-        if (a.n <= 32) attn_rows_reg_kernel<1, 2><<<blocks, 128, 0, st>>>(a);
-        else if (a.n <= 96) attn_rows_reg_kernel<3, 2><<<blocks, 128, 0, st>>>(a);
-        else attn_rows_reg_kernel<13, 2><<<blocks, 128, 0, st>>>(a);
+        const size_t smem = (size_t)4 * 13 * 32 * 8 * sizeof(float);
+        static bool configured = false;
+        if (!configured) {
+            cudaFuncSetAttribute(attn_rows_reg_kernel<13, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            configured = true;
+        }
+        attn_rows_reg_kernel<13, 2><<<blocks, 128, smem, st>>>(a);
         CHROMO_CHECK_LAUNCH("attn_rows_reg");
         return CHROMO_OK;
     }

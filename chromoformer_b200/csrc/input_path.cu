@@ -6,6 +6,7 @@
 // all resolutions, where the reference re-loads the .npy per bin size,
 // data.py:104) and each warp then reduces whole bins out of shared memory.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -135,6 +136,82 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_regions_kernel(BinArgs a) {
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Fast path (bin sizes that are multiples of the finest one, e.g. 100 | 500 | 2000): one THREAD per
+// finest bin reads its bp straight from HBM with 8-byte loads (a warp covers a contiguous
+// 32*bin0*2-byte span, every sector is consumed completely), coarser bins are sums of finest-bin
+// sums exchanged through shared memory.  Nothing is staged, each byte is read exactly once.
+//   grid = (chunks, F, regions), block = BT threads = one chunk of BT finest bins.
+struct BinFastArgs {
+    BinArgs b;
+    int bt;                 // threads per block = finest bins per chunk (multiple of every ratio)
+    int ratio[BIN_MAX_RES]; // bin[r] / bin0
+    int fine;               // index of the finest resolution
+};
+
+__global__ void __launch_bounds__(256) bin_regions_fast_kernel(BinFastArgs fa) {
+    __shared__ float sums[256];
+    const BinArgs& a = fa.b;
+    const int chunk = blockIdx.x, f = blockIdx.y, reg = blockIdx.z;
+    const chromo_region_t rg = a.regions[reg];
+    const int W = rg.width, bin0 = a.bin[fa.fine];
+    const __half* row = a.raw + rg.offset + (long long)f * rg.length + rg.start;
+    const int t = threadIdx.x;
+    const int fb = chunk * fa.bt + t;                       // finest-bin index within the region
+    const int s0 = fb * bin0, e0 = min(s0 + bin0, W);
+    float acc = 0.f;
+    if (s0 < W) {
+        const __half* p = row + s0;
+        int i = 0;
+        const int len = e0 - s0;
+        if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
+            const uint2* p8 = reinterpret_cast<const uint2*>(p);
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 5
+            for (; i + 4 <= len; i += 4) {
+                const uint2 u = __ldg(p8 + (i >> 2));
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+                const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+                a0 += lo.x; a1 += lo.y; a2 += hi.x; a3 += hi.y;
+            }
+            acc = (a0 + a1) + (a2 + a3);
+        }
+        for (; i < len; ++i) acc += __half2float(p[i]);
+    }
+    sums[t] = acc;
+    __syncthreads();
+    for (int r = 0; r < a.n_res; ++r) {
+        const int ratio = fa.ratio[r], bs = a.bin[r], n = a.nb[r];
+        int nbins = (W + bs - 1) / bs;
+        if (nbins > n) nbins = n;
+        const int lp = (n - nbins + 1) / 2, rp = (n - nbins) / 2;
+        const int per_chunk = fa.bt / ratio;
+        float* out = a.feats[r] + (long long)reg * n * a.F + f;
+        if (t < per_chunk) {
+            const int gb = chunk * per_chunk + t;
+            if (gb < nbins) {
+                float sacc = 0.f;
+                for (int k = 0; k < ratio; ++k) sacc += sums[t * ratio + k];
+                const int s = gb * bs, e = min(s + bs, W);
+                int pos = lp + gb;
+                if (rg.flip) pos = n - 1 - pos;
+                out[(long long)pos * a.F] = logf(sacc / (float)(e - s) + 1.f);
+            }
+        }
+        // zero padding + spans: the first chunk of each row owns them
+        if (chunk == 0) {
+            const int first = rg.flip ? rp : lp;
+            for (int p = t; p < n; p += blockDim.x)
+                if (p < first || p >= first + nbins) out[(long long)p * a.F] = 0.f;
+            if (f == 0 && t == 0) {
+                a.spans[((long long)r * a.n_regions + reg) * 2 + 0] = first;
+                a.spans[((long long)r * a.n_regions + reg) * 2 + 1] = nbins;
+            }
+        }
+    }
+}
+
 }  // namespace chromo
 
 using namespace chromo;
@@ -152,6 +229,38 @@ extern "C" int chromo_bin_regions(const uint16_t* raw, const chromo_region_t* re
     for (int r = 0; r < n_res; ++r) {
         if (bin_sizes[r] < 1 || n_bins[r] < 1 || !feats[r]) { set_error("bin_regions: bad resolution %d", r); return CHROMO_EINVAL; }
         a.bin[r] = bin_sizes[r]; a.nb[r] = n_bins[r]; a.feats[r] = feats[r];
+    }
+    // fast path: every bin size is a multiple of the finest one and a chunk of <= 256 finest bins
+    // can be cut on a boundary of all of them
+    {
+        BinFastArgs fa;
+        fa.b = a;
+        int fine = 0;
+        for (int r = 1; r < n_res; ++r) if (a.bin[r] < a.bin[fine]) fine = r;
+        long long max_width = 0;      // longer regions are truncated to n_bins anyway (data.py requires L <= w_max)
+        for (int r = 0; r < n_res; ++r) max_width = max_width > (long long)a.nb[r] * a.bin[r] ? max_width : (long long)a.nb[r] * a.bin[r];
+        bool ok = max_width > 0 && !getenv("CHROMO_BIN_GENERIC");
+        long long l = 1;
+        for (int r = 0; r < n_res && ok; ++r) {
+            if (a.bin[r] % a.bin[fine] != 0) { ok = false; break; }
+            fa.ratio[r] = a.bin[r] / a.bin[fine];
+            long long x = l, y = fa.ratio[r];
+            while (y) { long long t = x % y; x = y; y = t; }
+            l = l / x * fa.ratio[r];
+            if (l > 256) ok = false;
+        }
+        if (ok) {
+            fa.fine = fine;
+            fa.bt = (int)(256 / l * l);
+            const long long fine_bins = ((long long)max_width + a.bin[fine] - 1) / a.bin[fine];
+            const int chunks = (int)((fine_bins + fa.bt - 1) / fa.bt);
+            if (chunks >= 1 && chunks <= 65535 && n_feats <= 65535) {
+                dim3 grid(chunks, n_feats, n_regions);
+                bin_regions_fast_kernel<<<grid, fa.bt, 0, (cudaStream_t)stream>>>(fa);
+                CHROMO_CHECK_LAUNCH("bin_regions_fast");
+                return CHROMO_OK;
+            }
+        }
     }
     dim3 grid(n_feats, n_regions);
     bin_regions_kernel<<<grid, BIN_THREADS, 0, (cudaStream_t)stream>>>(a);
