@@ -526,7 +526,7 @@ static int pack_all_weights(const chromo_config_t* c, const ParamLayout& L, cons
     }
     for (int r = 0; r < NR; ++r) {
         const int n = c->n_bins[r];
-        if (n % 16 != 0) continue;
+        if (n % 16 != 0 || !in->pos_enc[r]) continue;
         CHROMO_TRY(pack_weights(in->pos_enc[r], reinterpret_cast<__nv_bfloat16*>(ws + w.bf_pe[r]), n, D,
                                 umma_tile_n(n), 0, 1, false, D, st));
         CHROMO_TRY(pack_weights(in->pos_enc[r], reinterpret_cast<__nv_bfloat16*>(ws + w.bf_pet[r]), D, n,
@@ -535,8 +535,10 @@ static int pack_all_weights(const chromo_config_t* c, const ParamLayout& L, cons
     return CHROMO_OK;
 }
 
+struct RegOnly { int layer; const float* x; float* y; long long xy_stride; };
+
 static int forward_impl(const chromo_config_t* c, const float* P, const chromo_batch_t* in, float* logits,
-                        float* ws, const WsLayout& w, int flags, cudaStream_t st) {
+                        float* ws, const WsLayout& w, int flags, cudaStream_t st, const RegOnly* only = nullptr) {
     const ParamLayout& L = get_layout(c);
     const int B = w.B, I = w.I, S = w.S, R = w.R, T = w.T, D = w.D, F = c->n_feats;
     const int NR = c->n_res;
@@ -557,6 +559,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     };
     if (bf16 && !(flags & CHROMO_F_PACKED)) CHROMO_TRY(pack_all_weights(c, L, P, packed, ws, w, in, st));
 
+    if (!only) {
     // ---------------- Embedding transformer, centre query (net.py:31-59) ----
     {
         CentreEmbedArgs a;
@@ -733,18 +736,23 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         }
     }
 
+    }   // !only
     // ---------------- Regulation transformer (net.py:152-153) ---------------
     const int dmr = c->reg_d_model, Hr = c->reg_heads;
     for (int l = 0; l < c->reg_layers; ++l) {
+        if (only && l != only->layer) continue;
         const AttnOff& ra = L.reg[0].att[l];
         const FfnOff& rf = L.reg[0].ffn[l];
         const long long so = (long long)w.rslot(l) * w.r_slot;
         const float* xin = l == 0 ? ws + w.r_xin : ws + w.r_out + (long long)w.rslot(l - 1) * w.r_slot;
+        float* xout = ws + w.r_out + so;
+        long long x_z = RS, y_z = RS;
+        if (only) { xin = only->x; xout = only->y; x_z = y_z = only->xy_stride; }
         if (w.reg_fused && !getenv("CHROMO_NO_REG_FUSED")) {
             // whole layer in one launch (reg_fused.cu)
             RegFusedArgs a;
             a.B = B; a.S = S; a.G = 128 / S; a.n_tiles = (B + a.G - 1) / a.G;
-            a.x = xin; a.x_z = RS; a.y = ws + w.r_out + so; a.y_z = RS;
+            a.x = xin; a.x_z = x_z; a.y = xout; a.y_z = y_z;
             a.wstream = reinterpret_cast<const __nv_bfloat16*>(ws + w.reg_stream) + (long long)l * reg_stream_elems_per_layer();
             a.w_z = (long long)c->reg_layers * reg_stream_elems_per_layer();
             a.gamma_f = P + ra.gamma_f; a.bo = P + ra.ffb; a.ln1w = P + ra.lnw; a.ln1b = P + ra.lnb;
@@ -756,7 +764,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         }
         {   // proj = X W_att^T  (q|k|v|gate)                       modules.py:38
             GemmArgs g = gemm_args();
-            g.A = xin; g.lda = D; g.sA1 = RS;
+            g.A = xin; g.lda = D; g.sA1 = x_z;
             g.B = P + ra.att; g.ldb = D; g.sB1 = L.reg_stride;
             g.C = ws + w.r_proj + so; g.ldc = 4 * dmr; g.sC1 = RS;
             if (proj_bf16) { g.c_bf16 = 1; g.sC1 = 2 * RS; }
@@ -781,7 +789,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.C = ws + w.r_u + so; g.ldc = D; g.sC1 = RS;
             g.M = T; g.N = D; g.K = dmr;
             g.epi = EPI_BIAS_RES_LN; g.bias = P + ra.ffb; g.sBias1 = L.reg_stride;
-            g.res = xin; g.ldres = D; g.sRes1 = RS;
+            g.res = xin; g.ldres = D; g.sRes1 = x_z;
             g.gamma = P + ra.lnw; g.beta = P + ra.lnb; g.sLn1 = L.reg_stride;
             if (train) { g.pre = ws + w.r_preU + so; g.sPre1 = RS; }
             CHROMO_TRY(lin(g, NR));
@@ -799,7 +807,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             GemmArgs g = gemm_args();
             g.A = ws + w.r_f + so; g.lda = c->reg_d_ff; g.sA1 = RS;
             g.B = P + rf.l2w; g.ldb = c->reg_d_ff; g.sB1 = L.reg_stride;
-            g.C = ws + w.r_out + so; g.ldc = D; g.sC1 = RS;
+            g.C = xout; g.ldc = D; g.sC1 = y_z;
             g.M = T; g.N = D; g.K = c->reg_d_ff;
             g.epi = EPI_BIAS_RES_LN; g.bias = P + rf.l2b; g.sBias1 = L.reg_stride;
             g.res = ws + w.r_u + so; g.ldres = D; g.sRes1 = RS;
@@ -809,6 +817,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         }
     }
 
+    if (only) return CHROMO_OK;
     // ---------------- head (net.py:377-380) ---------------------------------
     {
         HeadGatherArgs a;
@@ -864,6 +873,27 @@ extern "C" int chromo_forward(const chromo_config_t* cfg, const float* params, c
         return CHROMO_ENOMEM;
     }
     return forward_impl(cfg, params, in, logits, workspace, w, flags, (cudaStream_t)stream);
+}
+
+extern "C" int chromo_regulation_layer(const chromo_config_t* cfg, const float* params, int32_t layer, const float* x,
+                                       float* y, int64_t xy_stride, const uint8_t* const* imask, const float* freq,
+                                       int32_t batch, float* workspace, int64_t workspace_floats, int32_t flags,
+                                       void* stream) {
+    CHROMO_TRY(validate_config(cfg));
+    if (!params || !x || !y || !imask || !freq || !workspace || batch < 1) { set_error("chromo_regulation_layer: bad argument"); return CHROMO_EINVAL; }
+    if (layer < 0 || layer >= cfg->reg_layers) { set_error("chromo_regulation_layer: no such layer"); return CHROMO_EINVAL; }
+    if (flags & CHROMO_F_TRAINING) { set_error("chromo_regulation_layer: inference only"); return CHROMO_EINVAL; }
+    WsLayout w = make_ws_layout(cfg, batch, flags);
+    if (workspace_floats < w.total) { set_error("workspace too small"); return CHROMO_ENOMEM; }
+    chromo_batch_t in;
+    memset(&in, 0, sizeof(in));
+    in.batch = batch; in.freq = freq;
+    for (int r = 0; r < cfg->n_res; ++r) {
+        if (!imask[r]) { set_error("chromo_regulation_layer: null interaction mask"); return CHROMO_EINVAL; }
+        in.imask[r] = imask[r];
+    }
+    RegOnly only{layer, x, y, xy_stride};
+    return forward_impl(cfg, params, &in, nullptr, workspace, w, flags | CHROMO_F_REGONLY, (cudaStream_t)stream, &only);
 }
 
 extern "C" int chromo_linear(const float* x, const float* w, const float* bias, float* y, int32_t m, int32_t n,

@@ -38,6 +38,7 @@ extern "C" {
 #define CHROMO_F_TRAINING 1   /* keep every activation the backward needs   */
 #define CHROMO_F_BF16 2       /* dense projections on tcgen05 (BF16 operands,
                                  FP32 accumulate); default is strict FP32   */
+#define CHROMO_F_REGONLY 8    /* internal */
 #define CHROMO_F_PACKED 4     /* with CHROMO_F_BF16: the workspace already holds
                                  the packed BF16 weights of THESE parameters
                                  (left there by a previous call) - skip packing */
@@ -100,6 +101,15 @@ int64_t chromo_workspace_floats(const chromo_config_t* cfg, int32_t batch, int32
 int chromo_forward(const chromo_config_t* cfg, const float* params, const chromo_batch_t* in,
                    float* logits /* [B,n_out] */, float* workspace, int64_t workspace_floats,
                    int32_t flags, void* stream);
+
+/* ---- one Regulation-transformer layer: AttentionBlock with gate (modules.py:104-111 as used by
+ * net.py:152-153), for every resolution at once: y[r] = layer(x[r]), x/y = [n_res][B*(i_max+1), d_emb] FP32
+ * with `xy_stride` floats between resolutions.  With CHROMO_F_BF16 and the default geometry this is ONE
+ * fused tcgen05 kernel per call (reg_fused.cu); otherwise the FP32 kernels.  Inference only.          */
+int chromo_regulation_layer(const chromo_config_t* cfg, const float* params, int32_t layer, const float* x,
+                            float* y, int64_t xy_stride, const uint8_t* const* imask /* n_res x [B,S,S] */,
+                            const float* freq /* [B,S,S] */, int32_t batch, float* workspace,
+                            int64_t workspace_floats, int32_t flags, void* stream);
 
 /* ---- one dense layer: nn.Linear (+ReLU) as at modules.py:38,100,159-160, net.py:326-330 --
  * y[z] = act(x[z] W[z]^T + b[z]) for z < batches; x [m,k], W [n,k], y [m,n] row-major.
