@@ -226,35 +226,60 @@ def main():
     h2d = batch_nbytes(pinned)
     ms_e2e = timed(lambda: eng.predict_host(pinned), max(2, args.steps // 2), 3)
     e2e = {"value": world * N_GENES / (ms_e2e * 1e-3), "unit": "genes/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": N_GENES * 2 * 4, "ms_per_step": ms_e2e}
+           "d2h_bytes_per_step": N_GENES * 2 * 4, "ms_per_step": ms_e2e,
+           "h2d_gbs": world * h2d / (ms_e2e * 1e-3) / 1e9, "bound": "PCIe host->device copy of the FP32 features"}
 
-    # ---------------- dominant kernel alone: Regulation fused projection -------------------
-    T = args.chunk * 9
-    x = torch.randn(3, T, 128, device=dev)
-    wgt = torch.randn(3, 1024, 128, device=dev)
-    y = torch.empty(3, T, 1024, device=dev)
+    # ---------------- dominant kernel alone ----------------------------------------------------
+    # BF16: the fused Regulation layer (reg_layer_fused_kernel, 1/3 of the step); FP32: the batched projection GEMM.
     st = torch.cuda.current_stream().cuda_stream
     flags = _lib.F_BF16 if args.precision == "bf16" else 0
-
+    Bk = args.chunk
+    T = Bk * 9
     if args.precision == "bf16":
-        wpk = torch.empty(3, 1024, 128, dtype=torch.bfloat16, device=dev)
-        _lib.check(lib.chromo_pack_linear_weight(wgt.data_ptr(), wpk.data_ptr(), 1024, 128, 3, 1024 * 128, st), "pack")
-        wgt = wpk
+        cfgk = _lib.Config.from_buffer_copy(model._cfg)
+        xk = torch.randn(3, T, 128, device=dev)
+        yk = torch.empty_like(xk)
+        nws = _lib.check(lib.chromo_workspace_floats(ctypes.byref(cfgk), Bk, flags), "ws")
+        wsk = torch.empty(nws, device=dev)
+        imk = [resident["interaction_masks"][b][:Bk].contiguous() for b in BINS]
+        imp = (ctypes.c_void_p * 3)(*[m.data_ptr() for m in imk])
+        fqk = resident["interaction_freq"][:Bk].contiguous()
+        state = {"flags": flags}
 
-    def one_linear():
-        _lib.check(lib.chromo_linear(x.data_ptr(), wgt.data_ptr(), None, y.data_ptr(), T, 1024, 128, 0, 3,
-                                     T * 128, 1024 * 128, 0, T * 1024, flags, st), "chromo_linear")
-    ms_k = timed(one_linear, 20, 5)
-    flops_k = 2.0 * 3 * T * 1024 * 128
+        def one_kernel():
+            _lib.check(lib.chromo_regulation_layer(ctypes.byref(cfgk), model.flat_params.data_ptr(), 2, xk.data_ptr(),
+                                                   yk.data_ptr(), T * 128, imp, fqk.data_ptr(), Bk, wsk.data_ptr(), nws,
+                                                   state["flags"], st), "chromo_regulation_layer")
+        one_kernel()                                   # packs the weight stream once
+        state["flags"] = flags | _lib.F_PACKED
+        ms_k = timed(one_kernel, 20, 5)
+        flops_k = 3.0 * T * 2 * (4 * 256 * 128 + 256 * 128 + 2 * 128 * 256 + 8 * 9 * 32 * 2)
+        bytes_k = 2.0 * 3 * T * 128 * 4 + 3 * 14 * 32768
+        kname = (f"reg_layer_fused_kernel<9>: one Regulation layer, 3 resolutions x {T} tokens "
+                 "(proj + attention + out-proj/LN + FFN/LN, tcgen05 + TMA weight stream)")
+        traffic = {"bytes": 71.8e6, "source": "ncu --set full, profiles/r01_regfused_ncu.md (dram read 60.5 MB + write 11.3 MB)"}
+    else:
+        x = torch.randn(3, T, 128, device=dev)
+        wgt = torch.randn(3, 1024, 128, device=dev)
+        y = torch.empty(3, T, 1024, device=dev)
+
+        def one_kernel():
+            _lib.check(lib.chromo_linear(x.data_ptr(), wgt.data_ptr(), None, y.data_ptr(), T, 1024, 128, 0, 3,
+                                         T * 128, 1024 * 128, 0, T * 1024, flags, st), "chromo_linear")
+        ms_k = timed(one_kernel, 20, 5)
+        flops_k = 2.0 * 3 * T * 1024 * 128
+        bytes_k = 3.0 * T * (128 + 1024) * 4
+        kname = f"gemm_simt_kernel<64,64> (FP32 CUDA cores) as launched for regulation.*.self_att.att (M={T}, N=1024, K=128, x3)"
+        traffic = None
     ach = flops_k / (ms_k * 1e-3) / 1e12
-    kname = "umma_linear_kernel (tcgen05, BF16 operands, FP32 out)" if args.precision == "bf16" else "gemm_simt_kernel<64,64> (FP32 CUDA cores)"
-    roofline = {"bound": "tensor", "kernel": f"{kname} as launched for regulation.*.self_att.att "
-                                             f"(M={T}, N=1024, K=128, 3 resolutions)",
-                "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-                "traffic": None, "peak_source": peaks["source"] + " burst (kernel timed alone)",
-                "ms_per_launch": ms_k,
-                "whole_forward": {"executed_flops_per_gene": executed_flops_per_gene(),
-                                  "achieved_tflops": executed_flops_per_gene() * genes_per_s / world / 1e12,
+    fpg = executed_flops_per_gene()
+    roofline = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                "frac": ach / peaks["bf16_tflops"], "traffic": traffic,
+                "peak_source": peaks["source"] + " burst (kernel timed alone)", "ms_per_launch": ms_k,
+                "algorithmic_flops_per_launch": flops_k, "algorithmic_bytes_per_launch": bytes_k,
+                "hbm_frac": bytes_k / (ms_k * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                "whole_forward": {"executed_flops_per_gene": fpg,
+                                  "achieved_tflops": fpg * genes_per_s / world / 1e12,
                                   "reference_equivalent_tflops": REF_FLOPS_PER_GENE * genes_per_s / world / 1e12,
                                   "algorithmic_bytes_per_gene": 126000 + 4500 + 324 * 4,
                                   "achieved_gbs": (126000 + 4500 + 1296) * genes_per_s / world / 1e9,
