@@ -219,3 +219,25 @@ def test_bf16_fused_regulation_tile_edges(n, i_max):
         got = model(*args).cpu()
     assert torch.isfinite(got).all()
     assert (got - want).abs().max().item() < 1e-2
+
+
+def test_ensemble_sweep_units_and_sharding():
+    """configs[4] in miniature: 3 checkpoints x 700 genes, cut into units and dealt to 2 'ranks'."""
+    from chromoformer_b200.engine import InferenceEngine
+    from chromoformer_b200.sweep import EnsembleSweep
+    batch = synthetic.make_batch(700, ragged=True, seed=12)
+    model = _mk(seed=0).cuda().eval()
+    sweep = EnsembleSweep(model, chunk=256)
+    sds = []
+    for seed in (11, 12, 13):
+        sds.append({k: v.clone() for k, v in _mk(seed=seed).state_dict().items()})
+        sweep.add_state_dict(sds[-1])
+    dev = sweep.engine.to_device(batch)
+    parts = [sweep.run(dev, rank=r, world=2) for r in range(2)]
+    assert sum(len(u) for u, _ in parts) == 3 * 3
+    full = EnsembleSweep.assemble(3, 700, 2, parts)
+    for i, sd in enumerate(sds):
+        ref_model = _mk(seed=99)
+        ref_model.load_state_dict(sd)
+        want = InferenceEngine(ref_model.cuda().eval(), chunk=700).predict_device(dev).cpu()
+        assert torch.equal(full[i], want)
