@@ -142,7 +142,12 @@ __global__ void __launch_bounds__(128) attn_rows_reg_kernel(AttnRowsArgs a) {
         const int total = n * F;                           // multiple of 4 for the supported shapes
         const float4* src = reinterpret_cast<const float4*>(x);
         if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-            for (int i = lane; i < total / 4; i += 32) reinterpret_cast<float4*>(xs)[i] = __ldg(src + i);
+            // cp.async: all 16-byte copies of the block in flight at once, no register staging
+            const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(xs));
+            for (int i = lane; i < total / 4; i += 32)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(src + i) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
         } else {
             for (int i = lane; i < total; i += 32) xs[i] = x[i];
         }
