@@ -218,6 +218,9 @@ __global__ void __launch_bounds__(256) reg_attention_bwd_kernel(RegAttnBwdArgs a
 //   out: dS[j] = gradient wrt the pre-scale score, dU8 = sum_j dS_j x_j,
 //        dQK_init = W_in dU  (the PE part is added by a GEMM)
 __global__ void __launch_bounds__(256) attn_rows_bwd_kernel(AttnRowsBwdArgs a) {
+    __shared__ float w_s[128 * 8];
+    for (int i = threadIdx.x; i < a.D * a.F; i += blockDim.x) w_s[i] = a.w_in[i];
+    __syncthreads();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= a.rows) return;
@@ -233,7 +236,7 @@ __global__ void __launch_bounds__(256) attn_rows_bwd_kernel(AttnRowsBwdArgs a) {
     for (int f = 0; f < 8; ++f) dxb[f] = 0.f;
     for (int d = lane; d < D; d += 32) {
         const float c = dcb[d];
-        const float* w = a.w_in + (long long)d * F;
+        const float* w = w_s + d * F;
 #pragma unroll
         for (int f = 0; f < 8; ++f)
             if (f < F) dxb[f] = fmaf(w[f], c, dxb[f]);
@@ -272,7 +275,7 @@ __global__ void __launch_bounds__(256) attn_rows_bwd_kernel(AttnRowsBwdArgs a) {
     if (lane < 8) a.dU8[(long long)warp * 8 + lane] = lane < F ? du[lane] : 0.f;
     float* dqk = a.dqk + (long long)warp * D;
     for (int d = lane; d < D; d += 32) {
-        const float* w = a.w_in + (long long)d * F;
+        const float* w = w_s + d * F;
         float s = 0.f;
 #pragma unroll
         for (int f = 0; f < 8; ++f)

@@ -95,6 +95,8 @@ struct WsLayout {
     int64_t fold_f32, fold_bf, fold_stride, fold_total;
     int64_t fold_slot[CHROMO_MAX_LAYERS + 1];
     int64_t reg_stream;     // packed weight stream of the fused Regulation layers (float offset; 0 = unused)
+    int64_t tail_stream;    // packed weight streams of the fused Embedding/Pairwise tails (float offset)
+    int tail_fused;         // 1 when the fused row-tail kernel applies
     int reg_fused;          // 1 when the fused Regulation-layer kernel applies to this configuration
     // backward scratch (training only)
     int64_t g_base;

@@ -45,6 +45,10 @@ __global__ void centre_embed_kernel(CentreEmbedArgs a) {
 //   xbar = sum_j p_j x_j;   cbar_init = W_in xbar   (the PE part is added by a GEMM)
 // modules.py:58-61,71-77 / 170-189 restricted to the centre query.
 __global__ void __launch_bounds__(256) attn_rows_kernel(AttnRowsArgs a) {
+    // W_in [D, F] is read by every row with a stride-F pattern: stage it once per block (coalesced)
+    __shared__ float w_s[128 * 8];
+    for (int i = threadIdx.x; i < a.D * a.F; i += blockDim.x) w_s[i] = a.w_in[i];
+    __syncthreads();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= a.rows) return;
@@ -61,7 +65,7 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(AttnRowsArgs a) {
     for (int f = 0; f < 8; ++f) u[f] = 0.f;
     for (int d = lane; d < D; d += 32) {
         const float q = qk[d];
-        const float* w = a.w_in + (long long)d * F;
+        const float* w = w_s + d * F;
 #pragma unroll
         for (int f = 0; f < 8; ++f)
             if (f < F) u[f] = fmaf(w[f], q, u[f]);
@@ -115,7 +119,7 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(AttnRowsArgs a) {
     if (lane < 8) a.xbar[(long long)warp * 8 + lane] = lane < F ? xb[lane] : 0.f;
     float* cb = a.cbar + (long long)warp * D;
     for (int d = lane; d < D; d += 32) {
-        const float* w = a.w_in + (long long)d * F;
+        const float* w = w_s + d * F;
         float s = 0.f;
 #pragma unroll
         for (int f = 0; f < 8; ++f)
@@ -128,6 +132,9 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(AttnRowsArgs a) {
 // HBM once (not once per head and pass) and scores never round-trip through memory.  NJ = ceil(n/32).
 template <int NJ, int H>
 __global__ void __launch_bounds__(128) attn_rows_reg_kernel(AttnRowsArgs a) {
+    __shared__ float w_s[128 * 8];
+    for (int i = threadIdx.x; i < a.D * a.F; i += blockDim.x) w_s[i] = a.w_in[i];
+    __syncthreads();
     const int region = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (region >= a.rows / H) return;
@@ -178,7 +185,7 @@ __global__ void __launch_bounds__(128) attn_rows_reg_kernel(AttnRowsArgs a) {
         for (int f = 0; f < 8; ++f) u[f] = 0.f;
         for (int d = lane; d < D; d += 32) {
             const float q = qk[d];
-            const float* w = a.w_in + (long long)d * F;
+            const float* w = w_s + d * F;
 #pragma unroll
             for (int f = 0; f < 8; ++f)
                 if (f < F) u[f] = fmaf(w[f], q, u[f]);
@@ -232,7 +239,7 @@ __global__ void __launch_bounds__(128) attn_rows_reg_kernel(AttnRowsArgs a) {
         if (lane < 8) a.xbar[rowi * 8 + lane] = lane < F ? xb[lane] : 0.f;
         float* cb = a.cbar + rowi * D;
         for (int d = lane; d < D; d += 32) {
-            const float* w = a.w_in + (long long)d * F;
+            const float* w = w_s + d * F;
             float acc = 0.f;
 #pragma unroll
             for (int f = 0; f < 8; ++f)
@@ -528,6 +535,20 @@ static int pack_all_weights(const chromo_config_t* c, const ParamLayout& L, cons
             const AttnOff& a = L.pw[0].att[l];
             CHROMO_TRY(fold(1 + l, c->pw_heads, dmp, a.p_att, a.c_att, a.c_att + (int64_t)dmp * D, a.ffw, L.pw_stride));
         }
+        if (w.tail_fused) {
+            __nv_bfloat16* TS = reinterpret_cast<__nv_bfloat16*>(ws + w.tail_stream);
+            const long long tz = (long long)(1 + c->pw_layers) * TAIL_SLOT_ELEMS;
+            for (int slot = 0; slot <= c->pw_layers; ++slot) {
+                TailStreamArgs t;
+                const int H = slot == 0 ? c->embed_heads : c->pw_heads;
+                t.nfold = F32 + w.fold_slot[slot] + (int64_t)H * D * D; t.nfold_z = w.fold_stride;
+                t.params = P;
+                if (slot == 0) { t.p_z = L.embed_stride; t.l1w = L.embed[0].ffn[0].l1w; t.l2w = L.embed[0].ffn[0].l2w; t.dff = c->embed_d_ff; }
+                else { t.p_z = L.pw_stride; t.l1w = L.pw[0].ffn[slot - 1].l1w; t.l2w = L.pw[0].ffn[slot - 1].l2w; t.dff = c->pw_d_ff; }
+                t.stream = TS + slot * TAIL_SLOT_ELEMS; t.stream_z = tz;
+                CHROMO_TRY(pack_tail_stream(t, NR, st));
+            }
+        }
     }
     for (int r = 0; r < NR; ++r) {
         const int n = c->n_bins[r];
@@ -611,6 +632,19 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         s.cbar = ws + r * RS + w.e_cbar; s.av = ws + r * RS + w.e_av; s.folded = fold;
         CHROMO_TRY(single_query_attention(s, st));
     }
+    const bool tail = fold && w.tail_fused && !getenv("CHROMO_NO_TAIL_FUSED");
+    const long long tail_z = (long long)(1 + c->pw_layers) * TAIL_SLOT_ELEMS;
+    if (tail) {   // out-projection + LN + FFN + LN in one launch (row_tail_fused.cu) -> X_in[b, 0, :]
+        RowTailArgs t;
+        t.M = B; t.dff = c->embed_d_ff;
+        t.a = ws + w.e_cbar; t.lda = He * D; t.a_z = RS;
+        t.res = ws + w.e_hc; t.res_div = 1; t.res_z = RS;
+        t.y = ws + w.r_xin; t.y_z = RS; t.c_div = 1; t.c_mul = S; t.c_add = 0;
+        t.wstream = reinterpret_cast<const __nv_bfloat16*>(ws + w.tail_stream); t.w_z = tail_z;
+        t.bo = P + ea.ffb; t.ln1w = P + ea.lnw; t.ln1b = P + ea.lnb; t.b1 = P + ef.l1b; t.b2 = P + ef.l2b;
+        t.ln2w = P + ef.lnw; t.ln2b = P + ef.lnb; t.p_z = L.embed_stride;
+        CHROMO_TRY(launch_row_tail_fused(t, NR, st));
+    } else {
     {   // U = LN(Hc + Av W_o^T + b_o)                            modules.py:29-30
         GemmArgs g = gemm_args();
         g.A = ws + w.e_av; g.lda = dme; g.sA1 = RS;
@@ -648,6 +682,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         if (train) { g.pre = ws + w.e_preY; g.sPre1 = RS; }
         CHROMO_TRY(lin(g, NR));
     }
+    }   // !tail
 
     // ---------------- Pairwise Interaction transformer (net.py:105-139) -----
     const int dmp = c->pw_d_model, Hp = c->pw_heads;
@@ -699,6 +734,20 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             s.xbar = ws + r * RS + w.p_xbar + so;
             s.cbar = ws + r * RS + w.p_cbar + so; s.av = ws + r * RS + w.p_av + so; s.folded = fold;
             CHROMO_TRY(single_query_attention(s, st));
+        }
+        if (tail) {
+            RowTailArgs t;
+            t.M = R; t.dff = c->pw_d_ff;
+            t.a = ws + w.p_cbar + so; t.lda = Hp * D; t.a_z = RS;
+            t.res = pin; t.res_div = pin_div; t.res_z = RS;
+            if (last) { t.y = ws + w.r_xin; t.c_div = I; t.c_mul = S; t.c_add = 1; }
+            else { t.y = ws + w.p_out + so; t.c_div = 1; t.c_mul = 1; t.c_add = 0; }
+            t.y_z = RS;
+            t.wstream = reinterpret_cast<const __nv_bfloat16*>(ws + w.tail_stream) + (1 + l) * TAIL_SLOT_ELEMS; t.w_z = tail_z;
+            t.bo = P + pa.ffb; t.ln1w = P + pa.lnw; t.ln1b = P + pa.lnb; t.b1 = P + pf.l1b; t.b2 = P + pf.l2b;
+            t.ln2w = P + pf.lnw; t.ln2b = P + pf.lnb; t.p_z = L.pw_stride;
+            CHROMO_TRY(launch_row_tail_fused(t, NR, st));
+            continue;
         }
         {   // U = LN(P_l + Av W_o^T + b_o)                        modules.py:150-152
             GemmArgs g = gemm_args();

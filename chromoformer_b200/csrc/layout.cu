@@ -207,6 +207,11 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
             w.fold_total = off * c->n_res;
             w.fold_f32 = take(w.fold_total);
             w.fold_bf = take((w.fold_total + 1) / 2 + 8);
+            if (He * D == 256 && Hp * D == 256 && (c->embed_d_ff == 128 || c->embed_d_ff == 256) &&
+                (c->pw_d_ff == 128 || c->pw_d_ff == 256)) {
+                w.tail_fused = 1;
+                w.tail_stream = take(((int64_t)c->n_res * (1 + c->pw_layers) * 6 * 128 * 128 + 1) / 2 + 8);
+            }
             // fused Regulation layer: default geometry only (8 heads x 32, d_ff 256), <= 17 tokens per gene
             if (c->reg_heads == 8 && c->reg_d_model == 256 && c->reg_d_ff == 256 && D == 128 && S <= 17) {
                 w.reg_fused = 1;

@@ -24,6 +24,26 @@ struct RegStreamArgs {
     __nv_bfloat16* stream;                  // [res][layer][14][128*128]
 };
 
+// ---- fused tail of an Embedding / Pairwise layer (row_tail_fused.cu)
+struct RowTailArgs {
+    int M, dff;                             // rows, FFN width (128 or 256)
+    const float* a; int lda; long long a_z; // Cbar [M, 256] FP32
+    const float* res; int res_div; long long res_z;   // residual rows [M / res_div, 128]
+    float* y; long long y_z; int c_div, c_mul, c_add; // output rows (remapped as in GemmArgs), 128 wide
+    const __nv_bfloat16* wstream; long long w_z;
+    const float* bo; const float* ln1w; const float* ln1b; const float* b1; const float* b2;
+    const float* ln2w; const float* ln2b; long long p_z;
+};
+struct TailStreamArgs {
+    const float* nfold; long long nfold_z;  // folded out-projection N [128, 256] FP32
+    const float* params; long long p_z; long long l1w, l2w;
+    int dff;
+    __nv_bfloat16* stream; long long stream_z;
+};
+constexpr long long TAIL_SLOT_ELEMS = 6LL * 128 * 128;
+int pack_tail_stream(const TailStreamArgs& a, int n_res, cudaStream_t st);
+int launch_row_tail_fused(const RowTailArgs& a, int n_res, cudaStream_t st);
+
 long long reg_stream_elems_per_layer();
 int pack_reg_stream(const RegStreamArgs& a, int n_res, cudaStream_t st);
 int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st);

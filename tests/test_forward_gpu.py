@@ -241,3 +241,21 @@ def test_ensemble_sweep_units_and_sharding():
         ref_model.load_state_dict(sd)
         want = InferenceEngine(ref_model.cuda().eval(), chunk=700).predict_device(dev).cpu()
         assert torch.equal(full[i], want)
+
+
+def test_demo_goldens_through_bf16_tensor_path():
+    """config[0] on the tcgen05 path: logits within 1e-2 of the reference, AUROC / AP equal to 3 decimals."""
+    from sklearn import metrics
+    g = golden("demo_logits.npz")
+    model = _mk().cuda().eval()
+    model.precision = "bf16"
+    batch = demo_batch(0, 100)
+    with torch.no_grad():
+        got = model(*synthetic.forward_args(batch, "cuda")).cpu().numpy()
+    assert np.abs(got - g["logits"]).max() < 1e-2
+    pred = 1.0 / (1.0 + np.exp(-got[:, 1].astype(np.float64)))
+    labels = batch["labels"].numpy()
+    ref_pred = g["random_prediction"]
+    assert ((pred > 0.5) == (ref_pred > 0.5)).mean() >= 0.99
+    assert abs(metrics.roc_auc_score(labels, pred) - 0.5720594138900041) < 1e-3
+    assert abs(metrics.average_precision_score(labels, pred) - 0.5902055587970536) < 1e-3
