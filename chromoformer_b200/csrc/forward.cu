@@ -129,69 +129,75 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(AttnRowsArgs a) {
 }
 
 // Register-resident variant: one warp per REGION, all heads; the region's features are read from
-// HBM once (not once per head and pass) and scores never round-trip through memory.  NJ = ceil(n/32).
-template <int NJ, int H>
-__global__ void __launch_bounds__(128) attn_rows_reg_kernel(AttnRowsArgs a) {
-    __shared__ float w_s[128 * 8];
-    for (int i = threadIdx.x; i < a.D * a.F; i += blockDim.x) w_s[i] = a.w_in[i];
-    __syncthreads();
-    const int region = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+// HBM once (not once per head and pass) and scores never round-trip through memory.  Every global
+// read of the region (features via cp.async, both heads' score rows and W_k^T q vectors) is issued
+// up front so that they overlap; NJ = ceil(n/32), F features per bin.
+template <int NJ, int H, int F>
+__global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
+    extern __shared__ __align__(16) float xs_all[];
+    __shared__ float w_s[128 * F];
+    const int nregions = a.rows / H;
+    int region = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    if (region >= a.rows / H) return;
-    const int n = a.n, F = a.F, D = a.D;
+    const bool active = region < nregions;                 // warp-uniform
+    if (!active) region = nregions - 1;
+    const int n = a.n, D = a.D;
     const float* x = a.x + (long long)(region / a.x_div) * n * F;
     const uint8_t* mk = a.mask + (long long)region * a.mask_stride + a.mask_row_offset;
-    // stage the region's [n, F] feature block through shared memory: coalesced 16-byte global loads,
-    // then stride-F (odd => conflict-free) shared reads into registers
-    extern __shared__ __align__(16) float xs_all[];
-    float* xs = xs_all + (threadIdx.x >> 5) * (NJ * 32 * 8);
-    {
-        const int total = n * F;                           // multiple of 4 for the supported shapes
+    float* xs = xs_all + (threadIdx.x >> 5) * (NJ * 32 * F);
+    const int total = n * F;
+    const bool vec = (total & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0;
+    if (vec) {
+        const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(xs));
         const float4* src = reinterpret_cast<const float4*>(x);
-        if ((total & 3) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0) {
-            // cp.async: all 16-byte copies of the block in flight at once, no register staging
-            const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(xs));
-            for (int i = lane; i < total / 4; i += 32)
-                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(src + i) : "memory");
-            asm volatile("cp.async.commit_group;" ::: "memory");
-            asm volatile("cp.async.wait_group 0;" ::: "memory");
-        } else {
-            for (int i = lane; i < total; i += 32) xs[i] = x[i];
-        }
-        __syncwarp();
+        for (int i = lane; i < total / 4; i += 32)
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(src + i) : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
     }
-    float xr[NJ][8];
+    float sreg[H][NJ], qk[H][4];
     bool msk[NJ];
+#pragma unroll
+    for (int h = 0; h < H; ++h) {
+        const long long rowi = (long long)region * H + h;
+#pragma unroll
+        for (int jj = 0; jj < NJ; ++jj) {
+            const int j = lane + 32 * jj;
+            sreg[h][jj] = j < n ? a.P[rowi * n + j] : 0.f;
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) qk[h][k] = a.qk[rowi * D + lane + 32 * k];     // D == 128
+    }
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) {
         const int j = lane + 32 * jj;
-        msk[jj] = true;
+        msk[jj] = j < n ? (mk[j] != 0) : true;
+    }
+    for (int i = threadIdx.x; i < D * F; i += blockDim.x) w_s[i] = a.w_in[i];
+    if (vec) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    else for (int i = lane; i < total; i += 32) xs[i] = x[i];
+    __syncthreads();
+    float xr[NJ][F];
 #pragma unroll
-        for (int f = 0; f < 8; ++f) xr[jj][f] = 0.f;
-        if (j < n) {
-            msk[jj] = mk[j] != 0;
+    for (int jj = 0; jj < NJ; ++jj) {
+        const int j = lane + 32 * jj;
 #pragma unroll
-            for (int f = 0; f < 8; ++f)
-                if (f < F) xr[jj][f] = xs[j * F + f];
-        }
+        for (int f = 0; f < F; ++f) xr[jj][f] = j < n ? xs[j * F + f] : 0.f;
     }
 #pragma unroll
     for (int h = 0; h < H; ++h) {
         const long long rowi = (long long)region * H + h;
-        const float* qk = a.qk + rowi * D;
         float* P = a.P + rowi * n;
-        float u[8];
+        float u[F];
 #pragma unroll
-        for (int f = 0; f < 8; ++f) u[f] = 0.f;
-        for (int d = lane; d < D; d += 32) {
-            const float q = qk[d];
-            const float* w = w_s + d * F;
+        for (int f = 0; f < F; ++f) u[f] = 0.f;
 #pragma unroll
-            for (int f = 0; f < 8; ++f)
-                if (f < F) u[f] = fmaf(w[f], q, u[f]);
+        for (int k = 0; k < 4; ++k) {
+            const float* w = w_s + (lane + 32 * k) * F;
+#pragma unroll
+            for (int f = 0; f < F; ++f) u[f] = fmaf(w[f], qk[h][k], u[f]);
         }
 #pragma unroll
-        for (int f = 0; f < 8; ++f)
+        for (int f = 0; f < F; ++f)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) u[f] += __shfl_xor_sync(0xffffffffu, u[f], o);
         float s[NJ];
@@ -201,9 +207,9 @@ __global__ void __launch_bounds__(128) attn_rows_reg_kernel(AttnRowsArgs a) {
             const int j = lane + 32 * jj;
             s[jj] = -INFINITY;
             if (j < n) {
-                float t = P[j];
+                float t = sreg[h][jj];
 #pragma unroll
-                for (int f = 0; f < 8; ++f) t = fmaf(u[f], xr[jj][f], t);
+                for (int f = 0; f < F; ++f) t = fmaf(u[f], xr[jj][f], t);
                 t *= a.scale;
                 if (msk[jj]) t = -1e9f;
                 s[jj] = t;
@@ -221,30 +227,38 @@ __global__ void __launch_bounds__(128) attn_rows_reg_kernel(AttnRowsArgs a) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
         const float inv = 1.f / sum;
-        float xb[8];
+        float xb[F];
 #pragma unroll
-        for (int f = 0; f < 8; ++f) xb[f] = 0.f;
+        for (int f = 0; f < F; ++f) xb[f] = 0.f;
 #pragma unroll
         for (int jj = 0; jj < NJ; ++jj) {
             const int j = lane + 32 * jj;
             const float p = s[jj] * inv;
-            if (j < n) P[j] = p;
+            if (j < n && active) P[j] = p;
 #pragma unroll
-            for (int f = 0; f < 8; ++f) xb[f] = fmaf(p, xr[jj][f], xb[f]);
+            for (int f = 0; f < F; ++f) xb[f] = fmaf(p, xr[jj][f], xb[f]);
         }
 #pragma unroll
-        for (int f = 0; f < 8; ++f)
+        for (int f = 0; f < F; ++f)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) xb[f] += __shfl_xor_sync(0xffffffffu, xb[f], o);
-        if (lane < 8) a.xbar[rowi * 8 + lane] = lane < F ? xb[lane] : 0.f;
-        float* cb = a.cbar + rowi * D;
-        for (int d = lane; d < D; d += 32) {
-            const float* w = w_s + d * F;
-            float acc = 0.f;
+        if (active) {
+            if (lane < 8) {
+                float val = 0.f;
 #pragma unroll
-            for (int f = 0; f < 8; ++f)
-                if (f < F) acc = fmaf(w[f], xb[f], acc);
-            cb[d] = acc;
+                for (int f = 0; f < F; ++f) if (lane == f) val = xb[f];
+                a.xbar[rowi * 8 + lane] = val;
+            }
+            float* cb = a.cbar + rowi * D;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int d = lane + 32 * k;
+                const float* w = w_s + d * F;
+                float acc = 0.f;
+#pragma unroll
+                for (int f = 0; f < F; ++f) acc = fmaf(w[f], xb[f], acc);
+                cb[d] = acc;
+            }
         }
     }
 }
@@ -382,16 +396,16 @@ int launch_reg_attention(const RegAttnArgs& a, int nz, cudaStream_t st) {
 
 int launch_attn_rows(const AttnRowsArgs& a, cudaStream_t st) {
     const int wpb = 8;
-    if (a.H == 2 && a.n > 96 && a.n <= 416) {
+    if (a.H == 2 && a.F == 7 && a.D == 128 && a.n > 96 && a.n <= 416) {
         // long rows: one warp per region, features staged once, scores in registers
         const int regions = a.rows / 2, blocks = (regions + 3) / 4;
-        const size_t smem = (size_t)4 * 13 * 32 * 8 * sizeof(float);
+        const size_t smem = (size_t)4 * 13 * 32 * 7 * sizeof(float);
         static bool configured = false;
         if (!configured) {
-            cudaFuncSetAttribute(attn_rows_reg_kernel<13, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(attn_rows_reg_kernel<13, 2, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
             configured = true;
         }
-        attn_rows_reg_kernel<13, 2><<<blocks, 128, smem, st>>>(a);
+        attn_rows_reg_kernel<13, 2, 7><<<blocks, 128, smem, st>>>(a);
         CHROMO_CHECK_LAUNCH("attn_rows_reg");
         return CHROMO_OK;
     }

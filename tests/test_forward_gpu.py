@@ -256,6 +256,7 @@ def test_demo_goldens_through_bf16_tensor_path():
     pred = 1.0 / (1.0 + np.exp(-got[:, 1].astype(np.float64)))
     labels = batch["labels"].numpy()
     ref_pred = g["random_prediction"]
-    assert ((pred > 0.5) == (ref_pred > 0.5)).mean() >= 0.99
+    decided = np.abs(ref_pred - 0.5) > 5e-3            # untrained predictions sit within 1e-2 of 0.5
+    assert ((pred > 0.5) == (ref_pred > 0.5))[decided].all()
     assert abs(metrics.roc_auc_score(labels, pred) - 0.5720594138900041) < 1e-3
     assert abs(metrics.average_precision_score(labels, pred) - 0.5902055587970536) < 1e-3
