@@ -396,16 +396,18 @@ int launch_reg_attention(const RegAttnArgs& a, int nz, cudaStream_t st) {
 
 int launch_attn_rows(const AttnRowsArgs& a, cudaStream_t st) {
     const int wpb = 8;
-    if (a.H == 2 && a.F == 7 && a.D == 128 && a.n > 96 && a.n <= 416) {
-        // long rows: one warp per region, features staged once, scores in registers
+    if (a.H == 2 && a.F == 7 && a.D == 128 && a.n <= 416) {
+        // one warp per region, every global read issued up front, features staged once, scores in registers
         const int regions = a.rows / 2, blocks = (regions + 3) / 4;
-        const size_t smem = (size_t)4 * 13 * 32 * 7 * sizeof(float);
         static bool configured = false;
         if (!configured) {
-            cudaFuncSetAttribute(attn_rows_reg_kernel<13, 2, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            cudaFuncSetAttribute(attn_rows_reg_kernel<13, 2, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(4 * 13 * 32 * 7 * sizeof(float)));
             configured = true;
         }
-        attn_rows_reg_kernel<13, 2, 7><<<blocks, 128, smem, st>>>(a);
+        if (a.n <= 32) attn_rows_reg_kernel<1, 2, 7><<<blocks, 128, 4 * 1 * 32 * 7 * sizeof(float), st>>>(a);
+        else if (a.n <= 96) attn_rows_reg_kernel<3, 2, 7><<<blocks, 128, 4 * 3 * 32 * 7 * sizeof(float), st>>>(a);
+        else attn_rows_reg_kernel<13, 2, 7><<<blocks, 128, 4 * 13 * 32 * 7 * sizeof(float), st>>>(a);
         CHROMO_CHECK_LAUNCH("attn_rows_reg");
         return CHROMO_OK;
     }
