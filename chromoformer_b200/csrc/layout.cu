@@ -212,8 +212,9 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
                 w.tail_fused = 1;
                 w.tail_stream = take(((int64_t)c->n_res * (1 + c->pw_layers) * 6 * 128 * 128 + 1) / 2 + 8);
             }
-            // fused Regulation layer: default geometry only (8 heads x 32, d_ff 256), <= 17 tokens per gene
-            if (c->reg_heads == 8 && c->reg_d_model == 256 && c->reg_d_ff == 256 && D == 128 && S <= 17) {
+            // fused Regulation layer: default geometry only (8 heads x 32, d_ff 256), i_max 8 or 16 (kernel is
+            // specialised on the exact token count)
+            if (c->reg_heads == 8 && c->reg_d_model == 256 && c->reg_d_ff == 256 && D == 128 && (S == 9 || S == 17)) {
                 w.reg_fused = 1;
                 w.reg_stream = take(((int64_t)c->n_res * c->reg_layers * 14 * 128 * 128 + 1) / 2 + 8);
             }

@@ -78,7 +78,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int z = blockIdx.y, tile = blockIdx.x;
-    const int S = a.S, G = a.G;
+    constexpr int S = SMAX;                                   // exact tokens per gene: no per-key predicates
+    const int G = a.G;
     const long long row0 = (long long)tile * G * S;            // first token row of this tile
     const int rows_valid = min((long long)G * S, (long long)a.B * S - row0);
 
@@ -485,8 +486,9 @@ int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st) {
         configured = true;
     }
     dim3 grid(a.n_tiles, n_res);
-    if (a.S <= 9) reg_layer_fused_kernel<9><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
-    else reg_layer_fused_kernel<17><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
+    if (a.S == 9) reg_layer_fused_kernel<9><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
+    else if (a.S == 17) reg_layer_fused_kernel<17><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
+    else { set_error("reg_layer_fused: tokens per gene must be 9 or 17"); return CHROMO_EINVAL; }
     CHROMO_CHECK_LAUNCH("reg_layer_fused");
     return CHROMO_OK;
 }
