@@ -132,10 +132,14 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(AttnRowsArgs a) {
 // HBM once (not once per head and pass) and scores never round-trip through memory.  Every global
 // read of the region (features via cp.async, both heads' score rows and W_k^T q vectors) is issued
 // up front so that they overlap; NJ = ceil(n/32), F features per bin.
-template <int NJ, int H, int F>
+// FUSE_PE (short rows, n <= 32): the two GEMMs against the position table (scores QK.PE^T and
+// sum_j p_j PE_j) are done here as well, from a padded copy of the table in shared memory, so the
+// whole single-query attention core of a region is this one kernel.
+template <int NJ, int H, int F, bool FUSE_PE>
 __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
     extern __shared__ __align__(16) float xs_all[];
     __shared__ float w_s[128 * F];
+    __shared__ float pe_s[FUSE_PE ? 32 * 129 : 1];
     const int nregions = a.rows / H;
     int region = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -162,7 +166,7 @@ __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
 #pragma unroll
         for (int jj = 0; jj < NJ; ++jj) {
             const int j = lane + 32 * jj;
-            sreg[h][jj] = j < n ? a.P[rowi * n + j] : 0.f;
+            sreg[h][jj] = (!FUSE_PE && j < n) ? a.P[rowi * n + j] : 0.f;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) qk[h][k] = a.qk[rowi * D + lane + 32 * k];     // D == 128
@@ -173,6 +177,8 @@ __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
         msk[jj] = j < n ? (mk[j] != 0) : true;
     }
     for (int i = threadIdx.x; i < D * F; i += blockDim.x) w_s[i] = a.w_in[i];
+    if (FUSE_PE)
+        for (int i = threadIdx.x; i < n * D; i += blockDim.x) pe_s[(i >> 7) * 129 + (i & 127)] = a.pe[i];
     if (vec) asm volatile("cp.async.wait_group 0;" ::: "memory");
     else for (int i = lane; i < total; i += 32) xs[i] = x[i];
     __syncthreads();
@@ -200,6 +206,19 @@ __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
         for (int f = 0; f < F; ++f)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) u[f] += __shfl_xor_sync(0xffffffffu, u[f], o);
+        if (FUSE_PE) {
+            // lane j: QK . PE_j over the 128 channels (QK values broadcast lane by lane)
+            const float* per = pe_s + min(lane, n - 1) * 129;
+            float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+#pragma unroll
+                for (int src = 0; src < 32; src += 2) {
+                    a0 = fmaf(__shfl_sync(0xffffffffu, qk[h][k], src), per[32 * k + src], a0);
+                    a1 = fmaf(__shfl_sync(0xffffffffu, qk[h][k], src + 1), per[32 * k + src + 1], a1);
+                }
+            sreg[h][0] = a0 + a1;
+        }
         float s[NJ];
         float mx = -INFINITY;
 #pragma unroll
@@ -242,6 +261,16 @@ __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
         for (int f = 0; f < F; ++f)
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) xb[f] += __shfl_xor_sync(0xffffffffu, xb[f], o);
+        float pacc[4] = {0.f, 0.f, 0.f, 0.f};
+        if (FUSE_PE) {
+            // channels lane + 32k: sum_j p_j PE_j (p_j broadcast from lane j)
+            const float pj = s[0] * inv;
+            for (int j = 0; j < n; ++j) {
+                const float p = __shfl_sync(0xffffffffu, pj, j);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) pacc[k] = fmaf(p, pe_s[j * 129 + lane + 32 * k], pacc[k]);
+            }
+        }
         if (active) {
             if (lane < 8) {
                 float val = 0.f;
@@ -254,7 +283,7 @@ __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
             for (int k = 0; k < 4; ++k) {
                 const int d = lane + 32 * k;
                 const float* w = w_s + d * F;
-                float acc = 0.f;
+                float acc = pacc[k];
 #pragma unroll
                 for (int f = 0; f < F; ++f) acc = fmaf(w[f], xb[f], acc);
                 cb[d] = acc;
@@ -401,13 +430,14 @@ int launch_attn_rows(const AttnRowsArgs& a, cudaStream_t st) {
         const int regions = a.rows / 2, blocks = (regions + 3) / 4;
         static bool configured = false;
         if (!configured) {
-            cudaFuncSetAttribute(attn_rows_reg_kernel<13, 2, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+            cudaFuncSetAttribute(attn_rows_reg_kernel<13, 2, 7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(4 * 13 * 32 * 7 * sizeof(float)));
             configured = true;
         }
-        if (a.n <= 32) attn_rows_reg_kernel<1, 2, 7><<<blocks, 128, 4 * 1 * 32 * 7 * sizeof(float), st>>>(a);
-        else if (a.n <= 96) attn_rows_reg_kernel<3, 2, 7><<<blocks, 128, 4 * 3 * 32 * 7 * sizeof(float), st>>>(a);
-        else attn_rows_reg_kernel<13, 2, 7><<<blocks, 128, 4 * 13 * 32 * 7 * sizeof(float), st>>>(a);
+        if (a.n <= 32 && a.pe) attn_rows_reg_kernel<1, 2, 7, true><<<blocks, 128, 4 * 1 * 32 * 7 * sizeof(float), st>>>(a);
+        else if (a.n <= 32) attn_rows_reg_kernel<1, 2, 7, false><<<blocks, 128, 4 * 1 * 32 * 7 * sizeof(float), st>>>(a);
+        else if (a.n <= 96) attn_rows_reg_kernel<3, 2, 7, false><<<blocks, 128, 4 * 3 * 32 * 7 * sizeof(float), st>>>(a);
+        else attn_rows_reg_kernel<13, 2, 7, false><<<blocks, 128, 4 * 13 * 32 * 7 * sizeof(float), st>>>(a);
         CHROMO_CHECK_LAUNCH("attn_rows_reg");
         return CHROMO_OK;
     }
@@ -429,8 +459,10 @@ int single_query_attention(const SqaArgs& s, cudaStream_t st) {
         g.M = s.rows; g.N = D; g.K = dh; g.zdiv = s.H;
         CHROMO_TRY(gemm_launch(g, true, false, s.H, st));
     }
+    // short rows: the rows kernel also does both position-table GEMMs (attn_rows_reg_kernel<.., FUSE_PE>)
+    const bool fuse_pe = s.H == 2 && s.F == 7 && D == 128 && s.n <= 32;
     // Spe[(row,h), j] = QK[(row,h), :] . PE[j, :]                          (NT GEMM vs the table)
-    {
+    if (!fuse_pe) {
         GemmArgs g = gemm_args();
         g.A = s.qk; g.lda = D;
         g.B = s.pe; g.ldb = D;
@@ -445,11 +477,11 @@ int single_query_attention(const SqaArgs& s, cudaStream_t st) {
         a.qk = s.qk; a.P = s.P; a.x = s.x; a.x_div = 1;
         a.mask = s.mask; a.mask_stride = s.mask_stride; a.mask_row_offset = s.mask_row_offset;
         a.w_in = s.w_in; a.scale = 1.f / sqrtf((float)dh);
-        a.xbar = s.xbar; a.cbar = s.cbar;
+        a.xbar = s.xbar; a.cbar = s.cbar; a.pe = fuse_pe ? s.pe : nullptr;
         CHROMO_TRY(launch_attn_rows(a, st));
     }
     // Cbar += P . PE                                                        (NN GEMM, K = n)
-    {
+    if (!fuse_pe) {
         GemmArgs g = gemm_args();
         g.A = s.P; g.lda = s.n;
         g.B = s.pe; g.ldb = D;

@@ -26,6 +26,7 @@ struct AttnRowsArgs {
     float scale;
     float* xbar;          // [rows, 8]
     float* cbar;          // [rows, D]  <- W_in xbar
+    const float* pe = nullptr;   // [n, D] position table: set => the kernel also does both PE GEMMs (n <= 32)
 };
 
 struct RegAttnArgs {

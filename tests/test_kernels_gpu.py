@@ -104,3 +104,49 @@ def test_input_path_ragged_lengths_vs_oracle():
             got = feats[r][i].cpu().numpy().T
             assert np.abs(got - want).max() < 3e-6, (i, b)
             assert tuple(spans[r][i].cpu().numpy()) == (lp, nb)
+
+
+def test_gene_batcher_matches_reference_items(tmp_path):
+    """§8(f1): GeneBatcher (raw .npy -> device batch with centre-row masks, binned on the GPU) reproduces
+    the reference DataLoader items of 4 demo genes and the model output on them."""
+    import pandas as pd
+    from chromoformer_b200 import ChromoformerClassifier, synthetic
+    from chromoformer_b200.data import ChromoformerDataset, GeneBatcher
+    raw = golden("raw_regions.npz")
+    rows = []
+    for gi, gene in enumerate(raw["genes"]):
+        tss = 100000 * (gi + 1)
+        np.save(tmp_path / f"chrT:{tss - 20000}-{tss + 20000}.npy", raw[f"g{gi}_promoter"])
+        names = []
+        ci = 0
+        while f"g{gi}_pcre{ci}" in raw.files:
+            a = raw[f"g{gi}_pcre{ci}"]
+            s0 = 10_000_000 * (gi + 1) + 100_000 * ci
+            names.append(f"chrT:{s0}-{s0 + a.shape[1]}")
+            np.save(tmp_path / f"{names[-1]}.npy", a)
+            ci += 1
+        rows.append(dict(gene_id=str(gene), expression=1.0, eid="E003", label=gi % 2, chrom="chrT", start=tss,
+                         end=tss + 1, strand=str(raw["strands"][gi]), split=1, neighbors=";".join(names),
+                         scores=";".join(str(float(s)) for s in raw[f"g{gi}_scores"])))
+    meta = tmp_path / "meta.csv"
+    pd.DataFrame(rows).to_csv(meta, index=False)
+    ds = ChromoformerDataset(str(meta), str(tmp_path), [r["gene_id"] for r in rows])
+    batch = GeneBatcher(ds, device="cuda").batch(list(range(len(rows))))
+    ref = [demo_batch(int(i), int(i) + 1) for i in raw["index"]]
+    for b in BINS:
+        n = 40000 // b
+        for gi in range(len(rows)):
+            assert (batch["promoter_feats"][b][gi].cpu() - ref[gi]["promoter_feats"][b][0]).abs().max().item() < 3e-6
+            assert (batch["pcre_feats"][b][gi].cpu() - ref[gi]["pcre_feats"][b][0]).abs().max().item() < 3e-6
+            assert torch.equal(batch["pcre_pad_masks"][b][gi].cpu(), ref[gi]["pcre_pad_masks"][b][0, :, 0, n // 2])
+            assert torch.equal(batch["promoter_pad_masks"][b][gi].cpu(), ref[gi]["promoter_pad_masks"][b][0, :, 0, n // 2])
+            assert torch.equal(batch["interaction_masks"][b][gi].cpu(), ref[gi]["interaction_masks"][b][0])
+    # host items of the same dataset and the device batch give the same logits
+    model = ChromoformerClassifier(seed=123).cuda().eval()
+    with torch.no_grad():
+        got = model(*[batch[k] for k in synthetic.FORWARD_KEYS]).cpu()
+        items = [ds[i] for i in range(len(rows))]
+        coll = {k: {b: torch.stack([it[k][b] for it in items]).cuda() for b in BINS} for k in synthetic.FORWARD_KEYS[:5]}
+        want = model(*[coll[k] for k in synthetic.FORWARD_KEYS[:5]],
+                     torch.stack([it["interaction_freq"] for it in items]).cuda()).cpu()
+    assert (got - want).abs().max().item() < 2e-5
