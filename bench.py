@@ -162,6 +162,11 @@ def main():
         run_reference_arm(args)
         return
 
+    # keep stdout clean for the ONE JSON line: NCCL prints its version banner to stdout at init
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
     from chromoformer_b200 import ChromoformerClassifier, ChromoformerRegressor, _lib, synthetic
@@ -345,7 +350,10 @@ def main():
                 "config": workload_config(args), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
                 "roofline": roofline, "input_path": input_path, "cpu_baseline": cpu, "train": train}
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     if world > 1:
         dist.destroy_process_group()
 
