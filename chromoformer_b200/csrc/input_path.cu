@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(BIN_THREADS) bin_regions_kernel(BinArgs a) {
 // finest bin reads its bp straight from HBM with 8-byte loads (a warp covers a contiguous
 // 32*bin0*2-byte span, every sector is consumed completely), coarser bins are sums of finest-bin
 // sums exchanged through shared memory.  Nothing is staged, each byte is read exactly once.
-//   grid = (chunks, F, regions), block = BT threads = one chunk of BT finest bins.
+//   grid = (chunks, regions), block = BT threads = one chunk of BT finest bins (all F rows in turn).
 struct BinFastArgs {
     BinArgs b;
     int bt;                 // threads per block = finest bins per chunk (multiple of every ratio)
@@ -151,60 +151,80 @@ struct BinFastArgs {
 };
 
 __global__ void __launch_bounds__(256) bin_regions_fast_kernel(BinFastArgs fa) {
-    __shared__ float sums[256];
+    // grid = (chunks, regions); the block walks the F feature rows of its span one after the other and
+    // writes the [bins x F] outputs of every resolution as contiguous runs (F-interleaved, coalesced).
+    __shared__ float sums[8][256];
+    extern __shared__ __align__(16) __half span_s[];
     const BinArgs& a = fa.b;
-    const int chunk = blockIdx.x, f = blockIdx.y, reg = blockIdx.z;
+    const int chunk = blockIdx.x, reg = blockIdx.y;
     const chromo_region_t rg = a.regions[reg];
-    const int W = rg.width, bin0 = a.bin[fa.fine];
-    const __half* row = a.raw + rg.offset + (long long)f * rg.length + rg.start;
+    const int W = rg.width, bin0 = a.bin[fa.fine], F = a.F;
     const int t = threadIdx.x;
-    const int fb = chunk * fa.bt + t;                       // finest-bin index within the region
+    const int fb = chunk * fa.bt + t;                          // finest-bin index within the region
     const int s0 = fb * bin0, e0 = min(s0 + bin0, W);
-    float acc = 0.f;
-    if (s0 < W) {
-        const __half* p = row + s0;
-        int i = 0;
-        const int len = e0 - s0;
-        if ((reinterpret_cast<uintptr_t>(p) & 7) == 0) {
-            const uint2* p8 = reinterpret_cast<const uint2*>(p);
-            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 5
-            for (; i + 4 <= len; i += 4) {
-                const uint2 u = __ldg(p8 + (i >> 2));
-                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-                const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-                a0 += lo.x; a1 += lo.y; a2 += hi.x; a3 += hi.y;
+    const int c0 = chunk * fa.bt * bin0;                       // first bp of the span
+    const int clen = min(fa.bt * bin0, W - c0);                // bp in the span (<= 0: only padding to write)
+    for (int f = 0; f < F; ++f) {
+        float acc = 0.f;
+        if (clen > 0) {
+            // stage the span of feature f: 16-byte cp.async copies (coalesced, all in flight), element-wise head/tail
+            const __half* src = a.raw + rg.offset + (long long)f * rg.length + rg.start + c0;
+            const int mis = (int)((reinterpret_cast<uintptr_t>(src) & 15) >> 1);
+            const int head = mis ? min(clen, 8 - mis) : 0;
+            const int nvec = (clen - head) / 8;
+            for (int i = t; i < head; i += blockDim.x) span_s[mis + i] = src[i];
+            const uint32_t dst = static_cast<uint32_t>(__cvta_generic_to_shared(span_s + mis + head));
+            const __half* body = src + head;
+            for (int i = t; i < nvec; i += blockDim.x)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + i * 16), "l"(body + i * 8) : "memory");
+            asm volatile("cp.async.commit_group;" ::: "memory");
+            for (int i = head + nvec * 8 + t; i < clen; i += blockDim.x) span_s[mis + i] = src[i];
+            asm volatile("cp.async.wait_group 0;" ::: "memory");
+            __syncthreads();
+            if (s0 < W) {
+                const __half* p = span_s + mis + (s0 - c0);
+                const int len = e0 - s0;
+                int i = 0;
+                if ((reinterpret_cast<uintptr_t>(p) & 3) == 0) {
+                    float a0 = 0.f, a1 = 0.f;
+                    for (; i + 2 <= len; i += 2) {
+                        const float2 v = __half22float2(*reinterpret_cast<const __half2*>(p + i));
+                        a0 += v.x; a1 += v.y;
+                    }
+                    acc = a0 + a1;
+                }
+                for (; i < len; ++i) acc += __half2float(p[i]);
             }
-            acc = (a0 + a1) + (a2 + a3);
         }
-        for (; i < len; ++i) acc += __half2float(p[i]);
+        sums[f][t] = acc;
+        __syncthreads();                                       // span_s is reused by the next feature
     }
-    sums[t] = acc;
-    __syncthreads();
     for (int r = 0; r < a.n_res; ++r) {
         const int ratio = fa.ratio[r], bs = a.bin[r], n = a.nb[r];
         int nbins = (W + bs - 1) / bs;
         if (nbins > n) nbins = n;
         const int lp = (n - nbins + 1) / 2, rp = (n - nbins) / 2;
         const int per_chunk = fa.bt / ratio;
-        float* out = a.feats[r] + (long long)reg * n * a.F + f;
-        if (t < per_chunk) {
-            const int gb = chunk * per_chunk + t;
+        float* out = a.feats[r] + (long long)reg * n * F;
+        for (int idx = t; idx < per_chunk * F; idx += blockDim.x) {
+            const int lb = idx / F, f = idx - lb * F;
+            const int gb = chunk * per_chunk + lb;
             if (gb < nbins) {
                 float sacc = 0.f;
-                for (int k = 0; k < ratio; ++k) sacc += sums[t * ratio + k];
+                for (int k = 0; k < ratio; ++k) sacc += sums[f][lb * ratio + k];
                 const int s = gb * bs, e = min(s + bs, W);
                 int pos = lp + gb;
                 if (rg.flip) pos = n - 1 - pos;
-                out[(long long)pos * a.F] = logf(sacc / (float)(e - s) + 1.f);
+                out[(long long)pos * F + f] = logf(sacc / (float)(e - s) + 1.f);
             }
         }
-        // zero padding + spans: the first chunk of each row owns them
-        if (chunk == 0) {
+        if (chunk == 0) {   // zero padding + spans
             const int first = rg.flip ? rp : lp;
-            for (int p = t; p < n; p += blockDim.x)
-                if (p < first || p >= first + nbins) out[(long long)p * a.F] = 0.f;
-            if (f == 0 && t == 0) {
+            for (int idx = t; idx < n * F; idx += blockDim.x) {
+                const int pp = idx / F;
+                if (pp < first || pp >= first + nbins) out[idx] = 0.f;
+            }
+            if (t == 0) {
                 a.spans[((long long)r * a.n_regions + reg) * 2 + 0] = first;
                 a.spans[((long long)r * a.n_regions + reg) * 2 + 1] = nbins;
             }
@@ -254,9 +274,15 @@ extern "C" int chromo_bin_regions(const uint16_t* raw, const chromo_region_t* re
             fa.bt = (int)(256 / l * l);
             const long long fine_bins = ((long long)max_width + a.bin[fine] - 1) / a.bin[fine];
             const int chunks = (int)((fine_bins + fa.bt - 1) / fa.bt);
-            if (chunks >= 1 && chunks <= 65535 && n_feats <= 65535) {
-                dim3 grid(chunks, n_feats, n_regions);
-                bin_regions_fast_kernel<<<grid, fa.bt, 0, (cudaStream_t)stream>>>(fa);
+            const size_t smem = ((size_t)fa.bt * a.bin[fine] + 16) * sizeof(__half);
+            if (chunks >= 1 && n_feats <= 8 && smem <= 200 * 1024) {
+                dim3 grid(chunks, n_regions);
+                static size_t configured = 0;
+                if (smem > configured) {
+                    cudaFuncSetAttribute(bin_regions_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                    configured = smem;
+                }
+                bin_regions_fast_kernel<<<grid, fa.bt, smem, (cudaStream_t)stream>>>(fa);
                 CHROMO_CHECK_LAUNCH("bin_regions_fast");
                 return CHROMO_OK;
             }
