@@ -309,11 +309,47 @@ def main():
                                           spans.data_ptr(), st), "chromo_bin_regions")
     ms_b = timed(one_bin, 10, 3)
     bytes_b = n_reg * 7 * L * 2 + n_reg * 500 * 7 * 4
-    input_path = {"kernel": "bin_regions_kernel", "bound": "hbm", "regions": n_reg, "bp_per_region": L,
+    input_path = {"kernel": "bin_regions_fast_kernel", "bound": "hbm", "regions": n_reg, "bp_per_region": L,
                   "algorithmic_bytes": bytes_b, "ms_per_launch": ms_b, "achieved": bytes_b / (ms_b * 1e-3) / 1e9,
                   "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": bytes_b / (ms_b * 1e-3) / 1e9 / peaks["hbm_gbs"],
                   "regions_per_s": n_reg / (ms_b * 1e-3)}
     del raw, feats
+
+    # ---------------- raw-depth path: FP16 depth in HBM -> binning kernel -> forward (no host work) ---------------
+    Bq = 1024
+    nreg = Bq * 9                                            # promoters first, then the 8 pCREs of every gene (40 kb each)
+    rawq = (torch.rand(nreg * 7 * L // 2, device=dev) * 3).to(torch.float16)
+    rawq = torch.cat([rawq, rawq])[: nreg * 7 * L]
+    tq = np.zeros(nreg, dtype=table.dtype)
+    tq["offset"] = np.arange(nreg, dtype=np.int64) * 7 * L
+    tq["length"], tq["width"] = L, L
+    tq["flip"][:Bq] = np.arange(Bq) % 2
+    tabq = torch.from_numpy(tq.view(np.uint8).reshape(-1)).to(dev)
+    fq = [torch.empty(nreg, n, 7, device=dev) for n in (20, 80, 400)]
+    sq = torch.empty(3, nreg, 2, dtype=torch.int32, device=dev)
+    pq = (ctypes.c_void_p * 3)(*[f.data_ptr() for f in fq])
+    imq = {b: resident["interaction_masks"][b][:Bq] for b in BINS}
+    frq = resident["interaction_freq"][:Bq]
+
+    def raw_step():
+        _lib.check(lib.chromo_bin_regions(rawq.data_ptr(), tabq.data_ptr(), nreg, 7, 3, bins_c, nb_c, pq, sq.data_ptr(), st),
+                   "chromo_bin_regions")
+        xp, xc, mp, mc = {}, {}, {}, {}
+        for r, (b, n) in enumerate(zip(BINS, (20, 80, 400))):
+            xp[b] = fq[r][:Bq].view(Bq, 1, n, 7)
+            xc[b] = fq[r][Bq:].view(Bq, 8, n, 7)
+            pos = torch.arange(n, device=dev).view(1, n)
+            sp = sq[r].long()
+            valid = (pos >= sp[:, :1]) & (pos < sp[:, :1] + sp[:, 1:2])          # centre-row masks from the valid spans
+            mp[b] = ~valid[:Bq].view(Bq, 1, n)
+            mc[b] = ~valid[Bq:].view(Bq, 8, n)
+        with torch.no_grad():
+            return model(xp, mp, xc, mc, imq, frq)
+    ms_r = timed(raw_step, 5, 3)
+    raw_path = {"what": "raw FP16 depth resident in HBM -> chromo_bin_regions -> forward, 1024 dense genes per step",
+                "value": world * Bq / (ms_r * 1e-3), "unit": "genes/s", "ms_per_step": ms_r,
+                "raw_bytes_per_gene": 9 * 7 * L * 2, "hbm_gbs": Bq * 9 * 7 * L * 2 / (ms_r * 1e-3) / 1e9}
+    del rawq, fq
 
     # ---------------- training step (configs[2]): fwd + bwd + AdamW, DP all-reduce ----------
     train = None
@@ -349,7 +385,8 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": workload_config(args), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-                "roofline": roofline, "input_path": input_path, "cpu_baseline": cpu, "train": train}
+                "roofline": roofline, "input_path": input_path, "raw_depth_path": raw_path, "cpu_baseline": cpu,
+                "train": train}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)
         print(json.dumps(line), flush=True)
