@@ -140,6 +140,7 @@ __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
     extern __shared__ __align__(16) float xs_all[];
     __shared__ float w_s[128 * F];
     __shared__ float pe_s[FUSE_PE ? 32 * 129 : 1];
+    __shared__ __align__(16) float qk_s[FUSE_PE ? 4 * 128 : 4];
     const int nregions = a.rows / H;
     int region = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
@@ -207,17 +208,24 @@ __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) u[f] += __shfl_xor_sync(0xffffffffu, u[f], o);
         if (FUSE_PE) {
-            // lane j: QK . PE_j over the 128 channels (QK values broadcast lane by lane)
+            // lane j: QK . PE_j over the 128 channels; QK of this (region, head) goes through shared memory
+            // (broadcast reads), four independent accumulators
+            float* qs = qk_s + (threadIdx.x >> 5) * 128;
+            __syncwarp();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) qs[lane + 32 * k] = qk[h][k];
+            __syncwarp();
             const float* per = pe_s + min(lane, n - 1) * 129;
-            float a0 = 0.f, a1 = 0.f;
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-#pragma unroll
-                for (int src = 0; src < 32; src += 2) {
-                    a0 = fmaf(__shfl_sync(0xffffffffu, qk[h][k], src), per[32 * k + src], a0);
-                    a1 = fmaf(__shfl_sync(0xffffffffu, qk[h][k], src + 1), per[32 * k + src + 1], a1);
-                }
-            sreg[h][0] = a0 + a1;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 8
+            for (int d = 0; d < 128; d += 4) {
+                const float4 q4 = *reinterpret_cast<const float4*>(qs + d);
+                a0 = fmaf(q4.x, per[d], a0);
+                a1 = fmaf(q4.y, per[d + 1], a1);
+                a2 = fmaf(q4.z, per[d + 2], a2);
+                a3 = fmaf(q4.w, per[d + 3], a3);
+            }
+            sreg[h][0] = (a0 + a1) + (a2 + a3);
         }
         float s[NJ];
         float mx = -INFINITY;
