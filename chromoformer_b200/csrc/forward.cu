@@ -142,11 +142,16 @@ __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
     __shared__ float pe_s[FUSE_PE ? 32 * 129 : 1];
     __shared__ __align__(16) float qk_s[FUSE_PE ? 4 * 128 : 4];
     const int nregions = a.rows / H;
-    int region = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
-    const bool active = region < nregions;                 // warp-uniform
-    if (!active) region = nregions - 1;
     const int n = a.n, D = a.D;
+    // block-wide tables once, then every warp walks its share of the regions
+    for (int i = threadIdx.x; i < D * F; i += blockDim.x) w_s[i] = a.w_in[i];
+    if (FUSE_PE)
+        for (int i = threadIdx.x; i < n * D; i += blockDim.x) pe_s[(i >> 7) * 129 + (i & 127)] = a.pe[i];
+    __syncthreads();
+    const int warps_total = (gridDim.x * blockDim.x) >> 5;
+    for (int region = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; region < nregions; region += warps_total) {
+    const bool active = true;
     const float* x = a.x + (long long)(region / a.x_div) * n * F;
     const uint8_t* mk = a.mask + (long long)region * a.mask_stride + a.mask_row_offset;
     float* xs = xs_all + (threadIdx.x >> 5) * (NJ * 32 * F);
@@ -177,12 +182,9 @@ __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
         const int j = lane + 32 * jj;
         msk[jj] = j < n ? (mk[j] != 0) : true;
     }
-    for (int i = threadIdx.x; i < D * F; i += blockDim.x) w_s[i] = a.w_in[i];
-    if (FUSE_PE)
-        for (int i = threadIdx.x; i < n * D; i += blockDim.x) pe_s[(i >> 7) * 129 + (i & 127)] = a.pe[i];
     if (vec) asm volatile("cp.async.wait_group 0;" ::: "memory");
     else for (int i = lane; i < total; i += 32) xs[i] = x[i];
-    __syncthreads();
+    __syncwarp();
     float xr[NJ][F];
 #pragma unroll
     for (int jj = 0; jj < NJ; ++jj) {
@@ -297,6 +299,8 @@ __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
                 cb[d] = acc;
             }
         }
+    }
+    __syncwarp();   // xs is re-filled by the next region
     }
 }
 
@@ -435,7 +439,9 @@ int launch_attn_rows(const AttnRowsArgs& a, cudaStream_t st) {
     const int wpb = 8;
     if (a.H == 2 && a.F == 7 && a.D == 128 && a.n <= 416) {
         // one warp per region, every global read issued up front, features staged once, scores in registers
-        const int regions = a.rows / 2, blocks = (regions + 3) / 4;
+        const int regions = a.rows / 2;
+        int blocks = (regions + 3) / 4;
+        if (blocks > 148 * 6) blocks = 148 * 6;      // persistent: <= 6 blocks per SM, warps loop over regions
         static bool configured = false;
         if (!configured) {
             cudaFuncSetAttribute(attn_rows_reg_kernel<13, 2, 7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
