@@ -441,7 +441,9 @@ int launch_attn_rows(const AttnRowsArgs& a, cudaStream_t st) {
         // one warp per region, every global read issued up front, features staged once, scores in registers
         const int regions = a.rows / 2;
         int blocks = (regions + 3) / 4;
-        if (blocks > 148 * 6) blocks = 148 * 6;      // persistent: <= 6 blocks per SM, warps loop over regions
+        // persistent (<= 6 blocks per SM, warps loop over regions) where the per-block table staging or the
+        // long rows make it pay; one region per warp otherwise
+        if ((a.n > 96 || a.n <= 32) && blocks > 148 * 6) blocks = 148 * 6;
         static bool configured = false;
         if (!configured) {
             cudaFuncSetAttribute(attn_rows_reg_kernel<13, 2, 7, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
