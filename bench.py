@@ -155,6 +155,7 @@ def main():
     ap.add_argument("--precision", choices=["fp32", "bf16"], default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -351,6 +352,29 @@ def main():
                 "raw_bytes_per_gene": 9 * 7 * L * 2, "hbm_gbs": Bq * 9 * 7 * L * 2 / (ms_r * 1e-3) / 1e9}
     del rawq, fq
 
+    # ---------------- ensemble sweep (configs[4]): 44 checkpoints x this rank's share of (checkpoint, chunk) units ----
+    sweep = None
+    if not args.no_sweep:
+        from chromoformer_b200.sweep import EnsembleSweep
+        es = EnsembleSweep(model, chunk=args.chunk)
+        base = model.flat_params.detach().clone()
+        gsw = torch.Generator(device=dev).manual_seed(1)
+        for ck in range(44):                                  # 44 distinct random-init "checkpoints" (no weights offline)
+            es.flats.append(base + 1e-3 * torch.randn(base.shape, generator=gsw, device=dev))
+        units = None
+
+        def sweep_step():
+            nonlocal units
+            units, _ = es.run(resident, rank=rank, world=world)
+        ms_s = timed(sweep_step, 2, 1)
+        evals = sum(g1 - g0 for (_, g0, g1) in units)
+        model.flat_params.copy_(base)
+        model.mark_parameters_changed()
+        sweep = {"what": "44 checkpoints x 18,955 genes, (checkpoint, gene-chunk) units sharded over ranks, no collective",
+                 "gene_evaluations_per_rank": evals, "ms": ms_s, "value": world * evals / (ms_s * 1e-3) if world == 1 else None,
+                 "per_rank_value": evals / (ms_s * 1e-3), "unit": "gene-evaluations/s",
+                 "full_sweep_seconds_on_this_many_gpus": 44 * N_GENES / (evals / (ms_s * 1e-3)) / world}
+
     # ---------------- training step (configs[2]): fwd + bwd + AdamW, DP all-reduce ----------
     train = None
     if not args.no_train:
@@ -385,7 +409,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": workload_config(args), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-                "roofline": roofline, "input_path": input_path, "raw_depth_path": raw_path, "cpu_baseline": cpu,
+                "roofline": roofline, "input_path": input_path, "raw_depth_path": raw_path, "ensemble_sweep": sweep, "cpu_baseline": cpu,
                 "train": train}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

@@ -236,3 +236,113 @@ class GeneBatcher:
         out["label"] = torch.stack(labels).to(dev)
         out["n_partners"] = kd
         return out
+
+
+class DeviceRegionStore:
+    """§8(f1) — the whole raw dataset resident in HBM.
+
+    Every region file a dataset references (promoters and pCREs; a region shared by several genes is stored
+    once) is packed ONCE into a single FP16 device buffer (18,955 genes x ~1 MB = ~19 GB for the full
+    sweep: a tenth of a B200's HBM).  A batch is then just a list of gene indices: the region table of the
+    batch is gathered on the device, `chromo_bin_regions` bins all resolutions, and pad masks are produced
+    as centre rows from the valid spans.  No host work, no H2D traffic per batch, no DataLoader."""
+
+    def __init__(self, dataset, device="cuda", genes=None):
+        self.ds, self.device = dataset, torch.device(device)
+        ds = dataset
+        genes = list(range(len(ds))) if genes is None else list(genes)
+        self.I, self.S = ds.i_max, ds.i_max + 1
+        paths, rows = {}, []
+        k = torch.zeros(len(genes), dtype=torch.long)
+        freq = torch.zeros(len(genes), self.S, self.S)
+        slot_region = torch.full((len(genes), self.S), -1, dtype=torch.long)      # region id per (gene, slot)
+        labels = []
+        for g, i in enumerate(genes):
+            gene = ds.target_genes[i]
+            regs = ds.gene_regions(gene)
+            if len(regs) - 1 > self.I:
+                raise ValueError(f"{gene}: more pCREs than i_max")
+            for j, (path, start, width, flip) in enumerate(regs):
+                key = (path, start, width, flip)
+                if key not in paths:
+                    paths[key] = len(rows)
+                    rows.append(key)
+                slot_region[g, j] = paths[key]
+            k[g] = len(regs) - 1
+            for j, s in enumerate(ds.ensg2scores[gene]):
+                freq[g, 0, j + 1] = s
+            labels.append(ds._label(gene))
+        arrays = [np.load(p) for (p, _, _, _) in rows]
+        F = arrays[0].shape[0]
+        total = sum(a.shape[1] for a in arrays) * F
+        total += (-total) % 8
+        host = torch.empty(total, dtype=torch.float16, pin_memory=torch.cuda.is_available())
+        table = np.zeros(len(rows) + 1, dtype=[("offset", "<i8"), ("length", "<i4"), ("start", "<i4"), ("width", "<i4"),
+                                               ("flip", "<i4")])
+        cur, hv = 0, host.numpy()
+        for r, (a, (_, start, width, flip)) in enumerate(zip(arrays, rows)):
+            L = int(a.shape[1])
+            start = max(0, int(start))
+            width = L - start if width is None else min(int(width), L - start)
+            hv[cur:cur + F * L] = a.astype(np.float16, copy=False).reshape(-1)
+            table[r] = (cur, L, start, width, 1 if flip else 0)
+            cur += F * L
+        table[len(rows)] = (0, 1, 0, 0, 0)                                       # dummy pCRE slot: zero width
+        self.F, self.n_regions = F, len(rows)
+        self.raw = host.to(self.device)
+        self.table = torch.from_numpy(table.view(np.uint8).reshape(len(rows) + 1, -1).copy()).to(self.device)
+        slot_region[slot_region < 0] = len(rows)
+        self.slot_region = slot_region.to(self.device)
+        self.k, self.freq = k.to(self.device), freq.to(self.device)
+        self.labels = torch.stack(labels).to(self.device)
+        self.nbytes = int(self.raw.numel() * 2)
+
+    def batch(self, indices):
+        """indices: gene positions within the store (list / LongTensor).  Returns the forward arguments."""
+        lib = _lib.load()
+        ds, dev, I, S = self.ds, self.device, self.I, self.S
+        idx = torch.as_tensor(indices, dtype=torch.long, device=dev)
+        B = idx.numel()
+        # region order: all promoters, then the I pCRE slots of every gene (dummies -> zero-width region)
+        sr = self.slot_region[idx]                                               # [B, S]
+        order = torch.cat([sr[:, 0], sr[:, 1:].reshape(-1)])
+        tab = self.table[order].contiguous()
+        n_reg = order.numel()
+        nb = [ds.w_max // b for b in ds.binsizes]
+        feats = [torch.empty(n_reg, n, self.F, dtype=torch.float32, device=dev) for n in nb]
+        spans = torch.empty(len(nb), n_reg, 2, dtype=torch.int32, device=dev)
+        ptrs = (ctypes.c_void_p * len(nb))(*[f.data_ptr() for f in feats])
+        bins_c = (ctypes.c_int32 * len(nb))(*[int(b) for b in ds.binsizes])
+        nb_c = (ctypes.c_int32 * len(nb))(*nb)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        for lo in range(0, n_reg, 65535):                                        # grid.y limit of the kernel
+            hi = min(n_reg, lo + 65535)
+            sub = (ctypes.c_void_p * len(nb))(*[f[lo:hi].data_ptr() for f in feats])
+            sp = spans[:, lo:hi].contiguous() if (lo, hi) != (0, n_reg) else spans
+            _lib.check(lib.chromo_bin_regions(self.raw.data_ptr(), tab[lo:hi].data_ptr(), hi - lo, self.F, len(nb),
+                                              bins_c, nb_c, sub, sp.data_ptr(), st), "chromo_bin_regions")
+            if sp is not spans:
+                spans[:, lo:hi] = sp
+        kd = self.k[idx]
+        ar = torch.arange(S, device=dev)
+        inside = (ar.view(1, S, 1) <= kd.view(B, 1, 1)) & (ar.view(1, 1, S) <= kd.view(B, 1, 1))
+        live = (torch.arange(I, device=dev).view(1, I) < kd.view(B, 1))          # real (non-dummy) pCRE slots
+        out = {"promoter_feats": {}, "promoter_pad_masks": {}, "pcre_feats": {}, "pcre_pad_masks": {},
+               "interaction_masks": {}}
+        for r, b in enumerate(ds.binsizes):
+            n = nb[r]
+            out["promoter_feats"][b] = feats[r][:B].view(B, 1, n, self.F)
+            out["pcre_feats"][b] = feats[r][B:].view(B, I, n, self.F)
+            pos = torch.arange(n, device=dev).view(1, n)
+            sp = spans[r].long()
+            valid = (pos >= sp[:, :1]) & (pos < sp[:, :1] + sp[:, 1:2])
+            vp = valid[:B]
+            centre_ok = vp[:, n // 2].view(B, 1, 1)
+            out["promoter_pad_masks"][b] = ~(vp.view(B, 1, n) & centre_ok)
+            vc = valid[B:].view(B, I, n) & live.view(B, I, 1)
+            out["pcre_pad_masks"][b] = ~(vc & centre_ok)
+            out["interaction_masks"][b] = (~inside).unsqueeze(1)
+        out["interaction_freq"] = self.freq[idx]
+        out["label"] = self.labels[idx]
+        out["n_partners"] = kd
+        return out

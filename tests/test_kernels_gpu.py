@@ -150,3 +150,19 @@ def test_gene_batcher_matches_reference_items(tmp_path):
         want = model(*[coll[k] for k in synthetic.FORWARD_KEYS[:5]],
                      torch.stack([it["interaction_freq"] for it in items]).cuda()).cpu()
     assert (got - want).abs().max().item() < 2e-5
+    # DeviceRegionStore: the raw dataset resident in HBM, batches by index (any order, repeats allowed)
+    from chromoformer_b200.data import DeviceRegionStore
+    store = DeviceRegionStore(ds, device="cuda")
+    order = [2, 0, 3, 1, 2]
+    sb = store.batch(order)
+    for key in synthetic.FORWARD_KEYS:
+        v = sb[key]
+        if isinstance(v, dict):
+            for b in BINS:
+                assert torch.equal(v[b], batch[key][b][order]), (key, b)
+        else:
+            assert torch.equal(v, batch[key][order])
+    assert torch.equal(sb["label"], batch["label"][order])
+    with torch.no_grad():
+        got2 = model(*[sb[k] for k in synthetic.FORWARD_KEYS]).cpu()
+    assert torch.equal(got2, got[order])
