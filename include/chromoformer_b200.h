@@ -123,6 +123,9 @@ int chromo_linear(const float* x, const float* w, const float* bias, float* y, i
 int chromo_pack_linear_weight(const float* w, uint16_t* packed, int32_t n, int32_t k, int32_t batches,
                               int64_t w_stride, void* stream);
 
+/* Test-only hardware-semantics probe (MN-major B operand, A operand in TMEM); see csrc/umma_probe.cu. */
+int chromo_debug_umma_probe(int32_t mode, const float* a, const float* b, float* d, int32_t n, int32_t k, void* stream);
+
 /* Number of kernel launches issued by this library since the last reset (process-wide). */
 int64_t chromo_launch_counter(int32_t reset);
 
