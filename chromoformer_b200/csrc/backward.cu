@@ -418,6 +418,7 @@ int sqa_bwd(const Ctx& c, const SqaBwd& s) {
         GemmArgs g = gemm_args();
         g.A = s.dS; g.lda = s.n; g.B = s.pe; g.ldb = D; g.C = s.dQK; g.ldc = D; g.accumulate = 1;
         g.M = RH; g.N = D; g.K = s.n;
+        g.ksplit = ksplit_for(s.n, RH, D, 1);       // K = n bins (up to 400) on a handful of CTAs otherwise
         CHROMO_TRY(gemm_launch(g, true, false, 1, c.st));
     }
     {   // dQ[r, h] = W_k[h] dQK[(r,h), :]
