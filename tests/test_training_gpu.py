@@ -69,10 +69,11 @@ def test_gradient_accumulation_and_zero_grad():
     model.zero_grad(set_to_none=True)
     run(b1); run(b2)                     # accumulate
     both = model.flat_grads.clone()
-    assert torch.allclose(both, g1 + g2, rtol=1e-4, atol=1e-7)
+    # split-K atomics: summation order varies run to run, so compare against the gradient scale
+    assert (both - (g1 + g2)).abs().max().item() < 1e-5 * (g1 + g2).abs().max().item()
     model.zero_grad(set_to_none=False)   # zero in place
     run(b1)
-    assert torch.allclose(model.flat_grads, g1, rtol=1e-4, atol=1e-7)
+    assert (model.flat_grads - g1).abs().max().item() < 1e-5 * g1.abs().max().item()
 
 
 @pytest.mark.parametrize("tag", ["reg", "clf"])
