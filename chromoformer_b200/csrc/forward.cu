@@ -55,7 +55,7 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(AttnRowsArgs a) {
     const int region = warp / a.H;
     const int n = a.n, F = a.F, D = a.D;
     const float* qk = a.qk + (long long)warp * D;
-    float* P = a.P + (long long)warp * n;
+    float* P = a.P + (long long)warp * (a.ldp ? a.ldp : n);
     const float* x = a.x + (long long)(region / a.x_div) * n * F;
     const uint8_t* mk = a.mask + (long long)region * a.mask_stride + a.mask_row_offset;
 
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
     __shared__ __align__(16) float qk_s[FUSE_PE ? 4 * 128 : 4];
     const int nregions = a.rows / H;
     const int lane = threadIdx.x & 31;
-    const int n = a.n, D = a.D;
+    const int n = a.n, D = a.D, ldp = a.ldp ? a.ldp : a.n;
     // block-wide tables once, then every warp walks its share of the regions
     for (int i = threadIdx.x; i < D * F; i += blockDim.x) w_s[i] = a.w_in[i];
     if (FUSE_PE)
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
 #pragma unroll
         for (int jj = 0; jj < NJ; ++jj) {
             const int j = lane + 32 * jj;
-            sreg[h][jj] = (!FUSE_PE && j < n) ? a.P[rowi * n + j] : 0.f;
+            sreg[h][jj] = (!FUSE_PE && j < n) ? a.P[rowi * ldp + j] : 0.f;
         }
 #pragma unroll
         for (int k = 0; k < 4; ++k) qk[h][k] = a.qk[rowi * D + lane + 32 * k];     // D == 128
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
 #pragma unroll
     for (int h = 0; h < H; ++h) {
         const long long rowi = (long long)region * H + h;
-        float* P = a.P + rowi * n;
+        float* P = a.P + rowi * ldp;
         float u[F];
 #pragma unroll
         for (int f = 0; f < F; ++f) u[f] = 0.f;
@@ -475,16 +475,21 @@ int single_query_attention(const SqaArgs& s, cudaStream_t st) {
         g.M = s.rows; g.N = D; g.K = dh; g.zdiv = s.H;
         CHROMO_TRY(gemm_launch(g, true, false, s.H, st));
     }
-    // short rows: the rows kernel also does both position-table GEMMs (attn_rows_reg_kernel<.., FUSE_PE>)
-    const bool fuse_pe = s.H == 2 && s.F == 7 && D == 128 && s.n <= 32;
+    // Short rows (n <= 32).  BF16 inference: pad the row to 32 bins (the packed position tables carry zero rows /
+    // columns there) so that both position-table GEMMs run on the tensor pipe; otherwise the rows kernel does
+    // them itself (attn_rows_reg_kernel<.., FUSE_PE>).
+    const bool pad32 = s.pe_pk && s.folded && s.n <= 32 && s.rows * s.H >= 64;
+    const int np = pad32 ? 32 : s.n;                       // row stride / GEMM extent of the P buffer
+    const bool fuse_pe = !pad32 && s.H == 2 && s.F == 7 && D == 128 && s.n <= 32;
     // Spe[(row,h), j] = QK[(row,h), :] . PE[j, :]                          (NT GEMM vs the table)
     if (!fuse_pe) {
         GemmArgs g = gemm_args();
         g.A = s.qk; g.lda = D;
         g.B = s.pe; g.ldb = D;
-        g.C = s.P; g.ldc = s.n;
-        g.M = s.rows * s.H; g.N = s.n; g.K = D;
-        if (s.pe_pk && g.M >= 64 && s.n % 16 == 0 && umma_supported(g)) CHROMO_TRY(umma_launch(g, s.pe_pk, 1, st));
+        g.C = s.P; g.ldc = np;
+        g.M = s.rows * s.H; g.N = np; g.K = D;
+        if (s.pe_pk && g.M >= 64 && np % 16 == 0 && umma_supported(g)) CHROMO_TRY(umma_launch(g, s.pe_pk, 1, st));
+        else if (pad32) { set_error("internal: padded short-row path needs the tensor engine"); return CHROMO_EINVAL; }
         else CHROMO_TRY(gemm_launch(g, true, true, 1, st));
     }
     {
@@ -493,17 +498,18 @@ int single_query_attention(const SqaArgs& s, cudaStream_t st) {
         a.qk = s.qk; a.P = s.P; a.x = s.x; a.x_div = 1;
         a.mask = s.mask; a.mask_stride = s.mask_stride; a.mask_row_offset = s.mask_row_offset;
         a.w_in = s.w_in; a.scale = 1.f / sqrtf((float)dh);
-        a.xbar = s.xbar; a.cbar = s.cbar; a.pe = fuse_pe ? s.pe : nullptr;
+        a.xbar = s.xbar; a.cbar = s.cbar; a.pe = fuse_pe ? s.pe : nullptr; a.ldp = np;
         CHROMO_TRY(launch_attn_rows(a, st));
     }
     // Cbar += P . PE                                                        (NN GEMM, K = n)
     if (!fuse_pe) {
         GemmArgs g = gemm_args();
-        g.A = s.P; g.lda = s.n;
+        g.A = s.P; g.lda = np;
         g.B = s.pe; g.ldb = D;
         g.C = s.cbar; g.ldc = D; g.accumulate = 1;
-        g.M = s.rows * s.H; g.N = D; g.K = s.n;
-        if (s.pet_pk && g.M >= 64 && s.n % 16 == 0 && umma_supported(g)) CHROMO_TRY(umma_launch(g, s.pet_pk, 1, st));
+        g.M = s.rows * s.H; g.N = D; g.K = np;
+        if (s.pet_pk && g.M >= 64 && np % 16 == 0 && umma_supported(g)) CHROMO_TRY(umma_launch(g, s.pet_pk, 1, st));
+        else if (pad32) { set_error("internal: padded short-row path needs the tensor engine"); return CHROMO_EINVAL; }
         else {
             // FP32 path: few rows (training batch) x long K => split the reduction over more CTAs
             const long long ctas = (long long)((g.M + 63) / 64) * ((g.N + 63) / 64);
@@ -621,11 +627,13 @@ static int pack_all_weights(const chromo_config_t* c, const ParamLayout& L, cons
     }
     for (int r = 0; r < NR; ++r) {
         const int n = c->n_bins[r];
-        if (n % 16 != 0 || !in->pos_enc[r]) continue;
-        CHROMO_TRY(pack_weights(in->pos_enc[r], reinterpret_cast<__nv_bfloat16*>(ws + w.bf_pe[r]), n, D,
-                                umma_tile_n(n), 0, 1, false, D, st));
-        CHROMO_TRY(pack_weights(in->pos_enc[r], reinterpret_cast<__nv_bfloat16*>(ws + w.bf_pet[r]), D, n,
-                                umma_tile_n(D), 0, 1, true, D, st));
+        if (!in->pos_enc[r]) continue;
+        const int np = n <= 32 ? 32 : n;                   // short rows are padded to 32 bins with zeros
+        if (np % 16 != 0) continue;
+        CHROMO_TRY(pack_weights(in->pos_enc[r], reinterpret_cast<__nv_bfloat16*>(ws + w.bf_pe[r]), np, D,
+                                umma_tile_n(np), 0, 1, false, D, st, n));
+        CHROMO_TRY(pack_weights(in->pos_enc[r], reinterpret_cast<__nv_bfloat16*>(ws + w.bf_pet[r]), D, np,
+                                umma_tile_n(D), 0, 1, true, D, st, n));
     }
     return CHROMO_OK;
 }

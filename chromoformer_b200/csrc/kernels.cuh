@@ -18,7 +18,8 @@ struct CentreEmbedArgs {
 struct AttnRowsArgs {
     int rows, H, n, F, D;
     const float* qk;      // [rows, D]
-    float* P;             // [rows, n]  in: PE part of the scores, out: probabilities
+    float* P;             // [rows, ldp]  in: PE part of the scores, out: probabilities (ldp >= n)
+    int ldp = 0;          // row stride of P (0 = n)
     const float* x;       // [regions / x_div, n, F]
     int x_div;
     const uint8_t* mask; long long mask_stride, mask_row_offset;

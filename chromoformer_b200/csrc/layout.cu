@@ -195,7 +195,7 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
         // the packed position tables (PE [n,D] as a weight, and its transpose).
         w.bf_params = take((get_layout(c).total + 1) / 2 + 8);
         for (int r = 0; r < c->n_res; ++r) {
-            const int64_t n16 = (c->n_bins[r] + 15) / 16 * 16;
+            const int64_t n16 = c->n_bins[r] <= 32 ? 32 : (c->n_bins[r] + 15) / 16 * 16;
             w.bf_pe[r] = take((n16 * D + 1) / 2 + 8);
             w.bf_pet[r] = take((n16 * D + 1) / 2 + 8);
         }
@@ -269,8 +269,10 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
     cur = res_base + w.res_stride * c->n_res;
     // ---- resolution-dependent buffers
     for (int r = 0; r < c->n_res; ++r) {
-        w.e_p[r] = take((int64_t)B * He * c->n_bins[r]);
-        w.p_p_slot[r] = align4((int64_t)R * Hp * c->n_bins[r]);
+        // rows may be padded to a multiple of 16 bins (tensor path for short rows, see single_query_attention)
+        const int64_t n16 = (c->n_bins[r] + 15) / 16 * 16;
+        w.e_p[r] = take((int64_t)B * He * n16);
+        w.p_p_slot[r] = align4((int64_t)R * Hp * n16);
         w.p_p[r] = take(w.p_p_slot[r] * w.pslots);
     }
     w.h_z = take((int64_t)B * c->n_res * D);

@@ -26,7 +26,7 @@ namespace chromo {
 // ------------------------------------------------------------------ weight packing --
 // src FP32 [N,K] row-major -> dst BF16, tiles of NT rows, each [NT/8][K/8][8][8].
 __global__ void pack_weights_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, int N, int K,
-                                    int NT, long long z_stride, int transposed, int ld_src) {
+                                    int NT, long long z_stride, int transposed, int ld_src, int valid) {
     const int z = blockIdx.y;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one 8-element K chunk
     const int KC = K / 8;
@@ -37,7 +37,9 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, __nv_bfloat16
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const int k = kc * 8 + j;
-        const float x = transposed ? s[(long long)k * ld_src + n] : s[(long long)n * ld_src + k];
+        // `valid` bounds the source extent along the padded dimension (K when transposed, N otherwise)
+        const bool in = transposed ? (k < valid) : (n < valid);
+        const float x = !in ? 0.f : (transposed ? s[(long long)k * ld_src + n] : s[(long long)n * ld_src + k]);
         v[j] = __float2bfloat16_rn(x);
     }
     const int t = n / NT, r = n % NT;
@@ -46,11 +48,12 @@ __global__ void pack_weights_kernel(const float* __restrict__ src, __nv_bfloat16
 }
 
 int pack_weights(const float* src, __nv_bfloat16* dst, int N, int K, int NT, long long z_stride, int nz,
-                 bool transposed, int ld_src, cudaStream_t st) {
+                 bool transposed, int ld_src, cudaStream_t st, int valid) {
+    if (valid < 0) valid = transposed ? K : N;
     if (K % 8 != 0 || N % NT != 0 || NT % 8 != 0) { set_error("pack_weights: bad shape"); return CHROMO_EINVAL; }
     const long long units = (long long)N * (K / 8);
     pack_weights_kernel<<<dim3((unsigned)((units + 255) / 256), nz), 256, 0, st>>>(src, dst, N, K, NT, z_stride,
-                                                                                    transposed ? 1 : 0, ld_src);
+                                                                                    transposed ? 1 : 0, ld_src, valid);
     CHROMO_CHECK_LAUNCH("pack_weights");
     return CHROMO_OK;
 }

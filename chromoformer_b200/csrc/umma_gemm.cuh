@@ -13,6 +13,6 @@ bool umma_supported(const GemmArgs& g);
 int umma_launch(const GemmArgs& g, const __nv_bfloat16* Bp, int nz, cudaStream_t st);
 // FP32 [N,K] (or its transpose when `transposed`: element (n,k) at src[k*ld_src + n]) -> packed BF16
 int pack_weights(const float* src, __nv_bfloat16* dst, int N, int K, int NT, long long z_stride, int nz,
-                 bool transposed, int ld_src, cudaStream_t st);
+                 bool transposed, int ld_src, cudaStream_t st, int valid = -1);
 
 }  // namespace chromo
