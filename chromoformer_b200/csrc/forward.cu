@@ -510,12 +510,7 @@ int single_query_attention(const SqaArgs& s, cudaStream_t st) {
         g.M = s.rows * s.H; g.N = D; g.K = np;
         if (s.pet_pk && g.M >= 64 && np % 16 == 0 && umma_supported(g)) CHROMO_TRY(umma_launch(g, s.pet_pk, 1, st));
         else if (pad32) { set_error("internal: padded short-row path needs the tensor engine"); return CHROMO_EINVAL; }
-        else {
-            // FP32 path: few rows (training batch) x long K => split the reduction over more CTAs
-            const long long ctas = (long long)((g.M + 63) / 64) * ((g.N + 63) / 64);
-            if (ctas < 148 && g.K >= 128) g.ksplit = (int)((296 + ctas - 1) / ctas) < g.K / 32 ? (int)((296 + ctas - 1) / ctas) : g.K / 32;
-            CHROMO_TRY(gemm_launch(g, true, false, 1, st));
-        }
+        else CHROMO_TRY(gemm_launch(g, true, false, 1, st));   // (no split-K here: the forward stays deterministic)
     }
     // Av[row, h*dh + e] = W_v[h*dh + e, :] . Cbar[(row,h), :]               (NT GEMM per head)
     if (!s.folded) {
