@@ -16,6 +16,8 @@
 // order by pack_reg_stream) are streamed through a 3-deep ring of 32 KB stages by 1-D TMA bulk
 // copies; a dedicated driver warp issues the copies and all tcgen05.mma, eight compute warps do
 // the TMEM epilogues and the attention.  mbarriers carry every hand-off.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "kernels.cuh"
 #include "reg_fused.cuh"
@@ -41,7 +43,7 @@ constexpr uint32_t OFF_CTL = OFF_V + 16384;                 // mbarriers + TMEM 
 constexpr uint32_t RF_SMEM = OFF_CTL + 256;
 
 enum { B_FULL0 = 0, B_FREE0 = 3, B_ACCQ0 = 6, B_ACCQFREE0 = 8, B_XREADY = 10, B_ATTREADY, B_UREADY, B_FREADY,
-       B_ACCO, B_ACCF1, B_ACCF2, B_COUNT };
+       B_ACCO, B_ACCF1, B_ACCF2, B_QKVR0, B_SR0 = B_QKVR0 + 2, B_PR0 = B_SR0 + 2, B_OR0 = B_PR0 + 2, B_COUNT = B_OR0 + 2 };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -69,9 +71,75 @@ __device__ __forceinline__ uint32_t op_chunk(int row, int kc, int K) {
     return (uint32_t)(row >> 3) * (uint32_t)(K * 16) + (uint32_t)kc * 128u + (uint32_t)(row & 7) * 16u;
 }
 
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        :
+        : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        :
+        : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+          "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]),
+          "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]),
+          "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// A operand in TMEM (lane = row, two BF16 per 32-bit column), B in shared memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+        :
+        : "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// P row of one (token, head) as packed BF16 pairs for the 64-key window that starts at the warp's first
+// gene (rounded down to an even key): entry m holds keys 2m, 2m+1 of the window; only the S keys of the
+// thread's own gene (candidate index c relative to the warp's first gene) are non-zero.
+template <int S, int NC, int PAR>
+__device__ __forceinline__ void build_p_window(const float* p, int c, uint32_t* W) {
+#pragma unroll
+    for (int m = 0; m < 32; ++m) {
+        float val[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+            constexpr int dummy = 0; (void)dummy;
+            const int o = 2 * m + e - PAR;                    // key offset from the warp's first gene
+            val[e] = 0.f;
+            if (o >= 0 && o / S < NC) {
+                if (c == o / S) val[e] = p[o % S];
+            }
+        }
+        W[m] = pack2(val[0], val[1]);
+    }
+}
+
 }  // namespace
 
-template <int SMAX>
+template <int SMAX, bool TC>
 __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const RegFusedArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_CTL);
@@ -91,6 +159,10 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         mbar_init(&bars[B_XREADY], 8); mbar_init(&bars[B_ATTREADY], 8);
         mbar_init(&bars[B_UREADY], 8); mbar_init(&bars[B_FREADY], 8);
         mbar_init(&bars[B_ACCO], 1); mbar_init(&bars[B_ACCF1], 1); mbar_init(&bars[B_ACCF2], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars[B_QKVR0 + i], 4); mbar_init(&bars[B_SR0 + i], 1);
+            mbar_init(&bars[B_PR0 + i], 4); mbar_init(&bars[B_OR0 + i], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -128,12 +200,43 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             issue_load(1);
             issue_load(2);
             mbar_wait(&bars[B_XREADY], 0);
+            if (!TC) {
             for (int t = 0; t < 4; ++t) {
                 const int buf = t & 1;
                 if (t >= 2) mbar_wait(&bars[B_ACCQFREE0 + buf], 0);
                 consume(2 * t, s_xb, 2048, 256 * buf, false);          // [q | k] of heads 2t, 2t+1
                 consume(2 * t + 1, s_xb, 2048, 256 * buf + 128, false); // [v | gate]
                 umma_commit(&bars[B_ACCQ0 + buf]);
+            }
+            } else {
+            // attention on the tensor pipe: TMEM [0,128) / [128,256) = S then P of the two heads in flight,
+            // [256,512) = projection pair (q0 q1 k0 k1 v0 v1 g0 g1, 32 columns each; O overwrites k)
+            const uint32_t idesc_s = umma_idesc_bf16(128, 128), idesc_o = umma_idesc_bf16(128, 32) | (1u << 16);
+            const uint32_t s_k = smem_u32(smem + OFF_K), s_v = smem_u32(smem + OFF_V);
+            for (int t = 0; t < 4; ++t) {
+                if (t > 0) mbar_wait(&bars[B_ACCQFREE0], (t - 1) & 1);
+                consume(2 * t, s_xb, 2048, 256, false);
+                consume(2 * t + 1, s_xb, 2048, 384, false);
+                umma_commit(&bars[B_ACCQ0]);
+                for (int i = 0; i < 2; ++i) {       // S = Q K^T: A = BF16 Q in TMEM, B = K (K-major, 128 keys x 32)
+                    mbar_wait(&bars[B_QKVR0 + i], t & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        umma_bf16_ts(tmem + 128 * i, tmem + 256 + 32 * i + 8 * k,
+                                     umma_smem_desc(s_k + i * 8192 + k * 256, 128, 512), idesc_s, k > 0 ? 1u : 0u);
+                    umma_commit(&bars[B_SR0 + i]);
+                }
+                for (int i = 0; i < 2; ++i) {       // O = P V: A = BF16 P in TMEM, B = V (MN-major, 32 dims x 128 keys)
+                    mbar_wait(&bars[B_PR0 + i], t & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        umma_bf16_ts(tmem + 256 + 64 + 32 * i, tmem + 128 * i + 8 * k,
+                                     umma_smem_desc(s_v + i * 8192 + k * 256, 128, 2048), idesc_o, k > 0 ? 1u : 0u);
+                    umma_commit(&bars[B_OR0 + i]);
+                }
+            }
             }
             mbar_wait(&bars[B_ATTREADY], 0);
             consume(8, s_att, 4096, 0, false);                          // out-projection, K halves
@@ -203,6 +306,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                 if (mask[j]) mbits |= 1u << j;
             }
         }
+        if (!TC) {
         for (int t = 0; t < 4; ++t) {
             const int buf = t & 1;
             const uint32_t qb = trow + 256 * buf;
@@ -289,6 +393,111 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                 pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
                 *reinterpret_cast<uint4*>(smem + OFF_ATT + op_chunk(row, 8 * t + 4 * ch + c, 256)) = pk;
             }
+        }
+        } else {
+        for (int t = 0; t < 4; ++t) {
+            // one thread per token row; warps 0-3 take head 2t, warps 4-7 head 2t+1
+            const uint32_t pb = trow + 256;
+            const int head = 2 * t + ch;
+            uint8_t* sk = smem + OFF_K + ch * 8192;
+            uint8_t* sv = smem + OFF_V + ch * 8192;
+            mbar_wait(&bars[B_ACCQ0], t & 1);
+            tc_fence_after();
+            {   // Q -> BF16, back into TMEM in place (A operand of S = Q K^T)
+                uint32_t qp[16];
+                tmem_ld32(pb + 32 * ch, v);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) qp[c] = pack2(v[2 * c], v[2 * c + 1]);
+                tmem_st16(pb + 32 * ch, qp);
+                // K -> shared, K-major [128 keys x 32]; V -> shared, MN-major [32 dims x 128 keys]
+                tmem_ld32(pb + 64 + 32 * ch, v);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4 pk;
+                    pk.x = pack2(v[8 * c], v[8 * c + 1]); pk.y = pack2(v[8 * c + 2], v[8 * c + 3]);
+                    pk.z = pack2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack2(v[8 * c + 6], v[8 * c + 7]);
+                    *reinterpret_cast<uint4*>(sk + op_chunk(row, c, 32)) = pk;
+                }
+                tmem_ld32(pb + 128 + 32 * ch, v);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4 pk;
+                    pk.x = pack2(v[8 * c], v[8 * c + 1]); pk.y = pack2(v[8 * c + 2], v[8 * c + 3]);
+                    pk.z = pack2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack2(v[8 * c + 6], v[8 * c + 7]);
+                    *reinterpret_cast<uint4*>(sv + c * 2048 + (row >> 3) * 128 + (row & 7) * 16) = pk;
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                fence_async_smem();
+                warp_arrive(&bars[B_QKVR0 + ch], lane);
+            }
+            // scores of this row against the S keys of its own gene: a window of the S tile that starts at the
+            // first gene touched by this warp (register indices stay compile-time, the column is warp-uniform)
+            constexpr int NC = (31 + S - 1) / S + 1;             // genes a 32-row warp can touch
+            constexpr int NW = NC * S;                            // window width in keys (<= 64)
+            const int g_lo = (32 * lq) / S;
+            const int cand = gl - g_lo;                           // 0 .. NC-1
+            const float gamma = a.gamma_f[z * a.p_z + head];
+            float w[64];
+            mbar_wait(&bars[B_SR0 + ch], t & 1);
+            tc_fence_after();
+            {
+                const uint32_t sc0 = trow + 128 * ch + S * g_lo;
+                tmem_ld32(sc0, w);
+                if (NW > 48) tmem_ld32(sc0 + 32, w + 32);
+                else tmem_ld16(sc0 + 32, w + 32);
+            }
+            float s[SMAX];
+            float mx = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < S; ++j) {
+                float sc = w[j];
+#pragma unroll
+                for (int c = 1; c < NC; ++c)
+                    if (cand == c) sc = w[c * S + j];
+                sc = fmaf(gamma, fr[j], sc * scale);
+                if ((mbits >> j) & 1u) sc = -1e9f;
+                s[j] = sc;
+                mx = fmaxf(mx, sc);
+            }
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < S; ++j) { s[j] = __expf(s[j] - mx); sum += s[j]; }
+            const float inv = 1.f / sum;
+#pragma unroll
+            for (int j = 0; j < S; ++j) s[j] *= inv;
+            {   // P (BF16 pairs) over the first 64 columns of the S tile: zeros, then this warp's window
+                uint32_t W[32];
+#pragma unroll
+                for (int m = 0; m < 32; ++m) W[m] = 0u;
+                tmem_st32(trow + 128 * ch, W);
+                tmem_st32(trow + 128 * ch + 32, W);
+                tmem_st_wait();
+                const int kb = S * g_lo;
+                if (kb & 1) build_p_window<S, NC, 1>(s, cand, W);
+                else build_p_window<S, NC, 0>(s, cand, W);
+                tmem_st32(trow + 128 * ch + (kb >> 1), W);
+                tmem_st_wait();
+                tc_fence_before();
+                warp_arrive(&bars[B_PR0 + ch], lane);
+            }
+            mbar_wait(&bars[B_OR0 + ch], t & 1);
+            tc_fence_after();
+            float o[32];
+            tmem_ld32(pb + 64 + 32 * ch, o);                      // O = P V (over the dead k columns)
+            tmem_ld32(pb + 192 + 32 * ch, v);                     // gate
+            tc_fence_before();
+            warp_arrive(&bars[B_ACCQFREE0], lane);                // the projection pair may be overwritten
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float r[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) r[e] = valid ? __fdividef(o[8 * c + e], 1.f + __expf(-v[8 * c + e])) : 0.f;
+                uint4 pk;
+                pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
+                *reinterpret_cast<uint4*>(smem + OFF_ATT + op_chunk(row, 8 * t + 4 * ch + c, 256)) = pk;
+            }
+        }
         }
         fence_async_smem();
         warp_arrive(&bars[B_ATTREADY], lane);
@@ -480,14 +689,20 @@ int pack_reg_stream(const RegStreamArgs& a, int n_res, cudaStream_t st) {
 int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e1 = cudaFuncSetAttribute(reg_layer_fused_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
-        cudaError_t e2 = cudaFuncSetAttribute(reg_layer_fused_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaError_t e1 = cudaFuncSetAttribute(reg_layer_fused_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaError_t e2 = cudaFuncSetAttribute(reg_layer_fused_kernel<17, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaFuncSetAttribute(reg_layer_fused_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaFuncSetAttribute(reg_layer_fused_kernel<17, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
         if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("reg_fused smem attribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return CHROMO_ECUDA; }
         configured = true;
     }
     dim3 grid(a.n_tiles, n_res);
-    if (a.S == 9) reg_layer_fused_kernel<9><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
-    else if (a.S == 17) reg_layer_fused_kernel<17><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
+    static int tc = -1;      // attention on the tensor pipe (block-diagonal Q K^T / P V); CHROMO_REG_TC=0 selects the CUDA-core variant
+    if (tc < 0) { const char* e = getenv("CHROMO_REG_TC"); tc = (e && e[0] == '0') ? 0 : 1; }
+    if (a.S == 9 && tc) reg_layer_fused_kernel<9, true><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
+    else if (a.S == 9) reg_layer_fused_kernel<9, false><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
+    else if (a.S == 17 && tc) reg_layer_fused_kernel<17, true><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
+    else if (a.S == 17) reg_layer_fused_kernel<17, false><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
     else { set_error("reg_layer_fused: tokens per gene must be 9 or 17"); return CHROMO_EINVAL; }
     CHROMO_CHECK_LAUNCH("reg_layer_fused");
     return CHROMO_OK;
