@@ -74,6 +74,8 @@ EXPORTS = {
                                           POINTER(c_void_p), c_void_p, c_int32, c_void_p, c_int64, c_int32, c_void_p]),
     "chromo_linear": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                 c_int64, c_int64, c_int64, c_int64, c_int32, c_void_p]),
+    "chromo_single_query_attention": (c_int32, [c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                                c_float, c_void_p, c_void_p, c_int64, c_void_p]),
     "chromo_pack_linear_weight": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p]),
     "chromo_launch_counter": (c_int64, [c_int32]),
     "chromo_debug_umma_probe": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),

@@ -20,6 +20,7 @@
 #include "gemm_simt.cuh"
 #include "kernels.cuh"
 #include "reg_fused.cuh"
+#include "sqa_fused.cuh"
 #include "umma_gemm.cuh"
 
 namespace chromo {
@@ -688,7 +689,32 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         g.M = B; g.N = dme; g.K = D;
         CHROMO_TRY(lin(g, NR));
     }
-    for (int r = 0; r < NR; ++r) {
+    // fused single-query attention core (sqa_fused.cu): all resolutions of a stage in one launch
+    auto sqa_fused = [&](int regions, int H, const float* const* x, const uint8_t* const* mask, const int64_t* mstride,
+                         const int64_t* moff, int64_t w_in, long long w_in_z, int dm, float* qk, float* cbar,
+                         bool* done) -> int {
+        *done = false;
+        if (!fold) return CHROMO_OK;
+        SqaFusedArgs f;
+        f.n_res = NR; f.regions = regions;
+        for (int r = 0; r < NR; ++r) {
+            f.n[r] = c->n_bins[r]; f.ns[r] = c->n_bins[r] <= 32 ? 32 : c->n_bins[r]; f.order[r] = r;
+            f.x[r] = x[r]; f.mask[r] = mask[r]; f.mask_stride[r] = mstride[r]; f.mask_row_offset[r] = moff[r];
+            f.pe_pk[r] = in->pos_enc[r] ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pe[r]) : nullptr;
+        }
+        for (int i = 1; i < NR; ++i)                       // long rows first
+            for (int j = i; j > 0 && f.n[f.order[j]] > f.n[f.order[j - 1]]; --j) std::swap(f.order[j], f.order[j - 1]);
+        f.qk = qk; f.qk_z = RS; f.cbar = cbar; f.cbar_z = RS;
+        f.w_in = P + w_in; f.w_in_z = w_in_z;
+        f.scale = 1.f / sqrtf((float)(dm / H));
+        if (!sqa_fused_supported(f, H, F, D)) return CHROMO_OK;
+        *done = true;
+        return launch_sqa_fused(f, st);
+    };
+    bool e_fused = false;
+    CHROMO_TRY(sqa_fused(B, c->embed_heads, in->x_p, in->mask_p, in->mask_p_stride, in->mask_p_row_offset,
+                         L.embed[0].lin_proj, L.embed_stride, dme, ws + w.e_qk, ws + w.e_cbar, &e_fused));
+    for (int r = 0; r < NR && !e_fused; ++r) {
         SqaArgs s;
         s.rows = B; s.H = c->embed_heads; s.dm = dme; s.D = D; s.n = c->n_bins[r]; s.F = F;
         s.q = ws + r * RS + w.e_q;
@@ -788,7 +814,10 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.M = R; g.N = dmp; g.K = D;
             CHROMO_TRY(lin(g, NR));
         }
-        for (int r = 0; r < NR; ++r) {
+        bool p_fused = false;
+        CHROMO_TRY(sqa_fused(R, Hp, in->x_pcre, in->mask_pcre, in->mask_pcre_stride, in->mask_pcre_row_offset,
+                             L.pw[0].lin_proj_pcre, L.pw_stride, dmp, ws + w.p_qk + so, ws + w.p_cbar + so, &p_fused));
+        for (int r = 0; r < NR && !p_fused; ++r) {
             SqaArgs s;
             s.rows = R; s.H = Hp; s.dm = dmp; s.D = D; s.n = c->n_bins[r]; s.F = F;
             s.q = ws + r * RS + w.p_q + so;
@@ -1038,6 +1067,33 @@ extern "C" int chromo_linear(const float* x, const float* w, const float* bias, 
         return umma_launch(g, reinterpret_cast<const __nv_bfloat16*>(w), batches, (cudaStream_t)stream);
     }
     return gemm_launch(g, true, true, batches, (cudaStream_t)stream);
+}
+
+extern "C" int chromo_single_query_attention(int32_t regions, int32_t n, const float* qk, const float* x,
+                                             const uint8_t* mask, const float* w_in, const float* pos_enc, float scale,
+                                             float* cbar, float* workspace, int64_t workspace_floats, void* stream) {
+    if (!qk || !x || !mask || !w_in || !pos_enc || !cbar || !workspace || regions < 1 || n < 4) {
+        set_error("chromo_single_query_attention: bad argument");
+        return CHROMO_EINVAL;
+    }
+    const int ns = n <= 32 ? 32 : (n + 15) / 16 * 16;
+    if (workspace_floats < (int64_t)ns * 64) { set_error("chromo_single_query_attention: workspace too small"); return CHROMO_EINVAL; }
+    cudaStream_t st = (cudaStream_t)stream;
+    __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(workspace);
+    SqaFusedArgs f;
+    f.n_res = 1; f.regions = regions;
+    f.n[0] = n; f.ns[0] = ns; f.order[0] = 0;
+    f.x[0] = x; f.mask[0] = mask; f.mask_stride[0] = n; f.mask_row_offset[0] = 0;
+    f.pe_pk[0] = pk;
+    f.qk = qk; f.qk_z = 0; f.cbar = cbar; f.cbar_z = 0;
+    f.w_in = w_in; f.w_in_z = 0;
+    f.scale = scale;
+    if (umma_tile_n(ns) == 0 || !sqa_fused_supported(f, 2, 7, 128)) {
+        set_error("chromo_single_query_attention: shape / alignment not supported by the fused kernel");
+        return CHROMO_EINVAL;
+    }
+    CHROMO_TRY(pack_weights(pos_enc, pk, ns, 128, umma_tile_n(ns), 0, 1, false, 128, st, n));
+    return launch_sqa_fused(f, st);
 }
 
 extern "C" int chromo_pack_linear_weight(const float* w, uint16_t* packed, int32_t n, int32_t k, int32_t batches,

@@ -697,7 +697,10 @@ int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st) {
         configured = true;
     }
     dim3 grid(a.n_tiles, n_res);
-    static int tc = -1;      // attention on the tensor pipe (block-diagonal Q K^T / P V); CHROMO_REG_TC=0 selects the CUDA-core variant
+    // Attention on the tensor pipe (block-diagonal Q K^T / P V with Q and P rounded to BF16, as in every flash-attention
+    // kernel) is the default: 14 % faster, max |logit error| 4.7e-3 vs 4.5e-3 for the CUDA-core attention on the demo set
+    // (profiles/r01_precision.md).  CHROMO_REG_TC=0 selects the CUDA-core variant (FP32 q and probabilities).
+    static int tc = -1;
     if (tc < 0) { const char* e = getenv("CHROMO_REG_TC"); tc = (e && e[0] == '0') ? 0 : 1; }
     if (a.S == 9 && tc) reg_layer_fused_kernel<9, true><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
     else if (a.S == 9) reg_layer_fused_kernel<9, false><<<grid, RF_THREADS, RF_SMEM, st>>>(a);

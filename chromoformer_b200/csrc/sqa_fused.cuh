@@ -1,0 +1,28 @@
+// Fused single-query attention core (BF16 inference path): scores against the position table, the rank-F feature
+// term, masked softmax and the probability-weighted sums in ONE kernel per stage, all resolutions in one launch.
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "common.cuh"
+
+namespace chromo {
+
+struct SqaFusedArgs {
+    int n_res, regions;                       // regions (gene or gene x pCRE slot) per resolution; 2 heads each
+    int n[CHROMO_MAX_RES];                    // bins per region
+    int ns[CHROMO_MAX_RES];                   // bins padded to the packed position table (multiple of 16, <= 400)
+    int order[CHROMO_MAX_RES];                // resolutions by descending n (long tiles first)
+    const float* qk; long long qk_z;          // [regions*2, 128]  W_k[h]^T q  per (region, head)
+    const float* x[CHROMO_MAX_RES];           // [regions, n, 7]
+    const uint8_t* mask[CHROMO_MAX_RES]; long long mask_stride[CHROMO_MAX_RES], mask_row_offset[CHROMO_MAX_RES];
+    const float* w_in; long long w_in_z;      // [128, 7]
+    const __nv_bfloat16* pe_pk[CHROMO_MAX_RES];   // position table, BF16, [ns/8][16][8][8] (pack_weights order)
+    float scale;
+    float* cbar; long long cbar_z;            // [regions*2, 128]  sum_j p_j (W_in x_j + PE_j)
+};
+
+bool sqa_fused_supported(const SqaFusedArgs& a, int H, int F, int D);
+int launch_sqa_fused(const SqaFusedArgs& a, cudaStream_t st);
+
+}  // namespace chromo

@@ -31,7 +31,9 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         : "memory");
 }
 
-// mode bit 0: B MN-major in shared memory (else K-major); mode bit 1: A in TMEM (else shared, K-major)
+// mode bit 0: B MN-major in shared memory (else K-major); mode bit 1: A in TMEM (else shared, K-major);
+// mode bit 2 (with bit 0): the MN-major B is stored with its k-blocks far apart and its n-blocks adjacent
+// (the bytes of a K-major [K, N] operand re-read as MN-major: LBO = N*16, SBO = 128)
 __global__ void __launch_bounds__(128) umma_probe_kernel(int mode, const float* A, const float* B, float* D, int N, int K) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __nv_bfloat16* sA = reinterpret_cast<__nv_bfloat16*>(smem);
@@ -43,7 +45,7 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(int mode, const float* 
     if (tid == 0) { mbar_init(bar, 1); asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
     tc_fence_before(); __syncthreads(); tc_fence_after();
     const uint32_t tmem = *slot;
-    const bool b_mn = mode & 1, a_tm = mode & 2;
+    const bool b_mn = mode & 1, a_tm = mode & 2, b_tr = (mode & 4) && b_mn;
     const int KC = K / 8;
     // A: shared K-major canonical, or TMEM (row = lane, two BF16 per 32-bit column, even k in the low half)
     if (!a_tm) {
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(int mode, const float* 
         const int k = i / N, n = i % N;
         const __nv_bfloat16 v = __float2bfloat16_rn(B[i]);
         if (!b_mn) sB[((n >> 3) * KC + (k >> 3)) * 64 + (n & 7) * 8 + (k & 7)] = v;          // K-major: LBO 128, SBO K*16
+        else if (b_tr) sB[((k >> 3) * (N / 8) + (n >> 3)) * 64 + (k & 7) * 8 + (n & 7)] = v;   // k-blocks N*16 B apart
         else sB[((n >> 3) * KC + (k >> 3)) * 64 + (k & 7) * 8 + (n & 7)] = v;                 // MN-major: 8(k) x 8(n) cores
     }
     fence_async_smem();
@@ -78,7 +81,8 @@ __global__ void __launch_bounds__(128) umma_probe_kernel(int mode, const float* 
         const uint32_t idesc = umma_idesc_bf16(128, N) | (b_mn ? (1u << 16) : 0u);
         for (int k = 0; k < K / 16; ++k) {
             // K-major: advance 2 core matrices (256 B) per MMA.  MN-major: k-blocks are LBO = 128 B apart, n-blocks SBO = K*16
-            const uint64_t bd = umma_smem_desc(smem_u32(sB) + k * 256, 128, (uint32_t)K * 16);
+            const uint64_t bd = b_tr ? umma_smem_desc(smem_u32(sB) + k * 2 * N * 16, (uint32_t)N * 16, 128)
+                                     : umma_smem_desc(smem_u32(sB) + k * 256, 128, (uint32_t)K * 16);
             if (!a_tm) umma_bf16(tmem, umma_smem_desc(smem_u32(sA) + k * 256, 128, (uint32_t)K * 16), bd, idesc, k > 0);
             else umma_bf16_ts(tmem, tmem + 256 + k * 8, bd, idesc, k > 0);
         }

@@ -111,6 +111,20 @@ int chromo_regulation_layer(const chromo_config_t* cfg, const float* params, int
                             const float* freq /* [B,S,S] */, int32_t batch, float* workspace,
                             int64_t workspace_floats, int32_t flags, void* stream);
 
+/* ---- single-query attention core of the Embedding / Pairwise Interaction transformers --------------
+ * For every (region, head) row: the attention of ONE query over the n bins of the region, with keys and
+ * values W_in x_j + PE_j (net.py:31-59 and 105-139 feed modules.py:16-30 / 150-170 this way; only the
+ * centre query is consumed downstream):
+ *   s_j = scale * qk[row] . (W_in x[region, j] + PE_j);  masked j -> -1e9;  p = softmax_j(s)
+ *   cbar[row] = sum_j p_j (W_in x[region, j] + PE_j)
+ * qk [regions*2, 128] (= W_k[h]^T q per head), x [regions, n, 7], mask [regions, n] bytes (non-zero = pad),
+ * w_in [128, 7], pos_enc [n, 128], cbar [regions*2, 128]; n % 4 == 0, n <= 400.  BF16 tensor path only
+ * (sqa_fused.cu): the kernel the BF16 forward runs per stage, exposed to be tested and timed alone.
+ * workspace: at least 64 * max(32, round_up(n, 16)) floats (the packed BF16 position table).          */
+int chromo_single_query_attention(int32_t regions, int32_t n, const float* qk, const float* x, const uint8_t* mask,
+                                  const float* w_in, const float* pos_enc, float scale, float* cbar,
+                                  float* workspace, int64_t workspace_floats, void* stream);
+
 /* ---- one dense layer: nn.Linear (+ReLU) as at modules.py:38,100,159-160, net.py:326-330 --
  * y[z] = act(x[z] W[z]^T + b[z]) for z < batches; x [m,k], W [n,k], y [m,n] row-major.
  * The same kernel the forward uses for every projection; exposed so that a single

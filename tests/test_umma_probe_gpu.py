@@ -7,10 +7,11 @@ from chromoformer_b200 import _lib
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 5, 7])
 @pytest.mark.parametrize("n,k", [(32, 128), (128, 32), (64, 64)])
 def test_umma_operand_forms(mode, n, k):
-    """mode bit 0: B MN-major in shared memory; bit 1: A in TMEM (tcgen05.st).  D = bf16(A) @ bf16(B)."""
+    """mode bit 0: B MN-major in shared memory; bit 1: A in TMEM (tcgen05.st); bit 2: MN-major B with
+    k-blocks N*16 B apart (the K-major bytes of B^T re-read as MN-major).  D = bf16(A) @ bf16(B)."""
     lib = _lib.load()
     g = torch.Generator().manual_seed(n * 1000 + k)
     A = torch.randn(128, k, generator=g).cuda()
