@@ -231,59 +231,71 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
             const int c_begin = half ? CA : 0, c_cnt = half ? CB : CA;
             const int nF = n * SQ_F;
 
-            // ring: chunk idx of this half (8 keys x 7 features per region, and the 8 mask bytes)
-            auto fetch = [&](int idx) {
+            // ring: chunk idx of this half (8 keys x 7 features per region, and the 8 mask bytes).  Copy plan: the 16
+            // threads ht/16*16.. move the fourteen 16-byte parts of ONE 224-byte chunk row (contiguous in HBM), regions
+            // ht/16 + 8k for k = 0..7; x_row_off(r0 + 8k) = x_row_off(r0) + 1792 k + 16 (k & 1) + 32 (k >> 1).
+            const int fr0 = ht >> 4, fpart = ht & 15;
+            const bool fact = fpart < 14;
+            const float* fsrc = X + (long long)(region0 + fr0) * nF + fpart * 4;
+            const long long fstep = 8LL * nF;
+            const uint32_t fdst = s_ring + half * SQ_HALF_X + x_row_off(fr0) + fpart * 16;
+            const int mreg = ht >> 1, modd = ht & 1;
+            const bool mvalid = 2 * mreg < rows_valid;
+            const uint8_t* msrc = MK + (long long)(region0 + (mvalid ? mreg : 0)) * mstride + modd * 4;
+            const uint32_t mdst = s_ring + SQ_STAGE_X + half * 512 + mreg * 8 + modd * 4;
+            auto fetch = [&](int idx, int stage) {
                 if (idx < c_cnt) {
                     const int cg = c_begin + idx;
-                    const uint32_t sb = s_ring + (idx % SQ_NSTAGE) * SQ_STAGE;
-                    const uint32_t dx = sb + half * SQ_HALF_X;
+                    const float* src = fsrc + cg * SQ_XROW;
+                    const uint32_t so = stage * SQ_STAGE;
+                    const bool full = cg * 8 + 8 <= n;         // (uniform) every key of the chunk exists
+                    const bool pok = fact && (full || cg * SQ_XROW + fpart * 4 + 3 < nF);
+                    if (fact) {
 #pragma unroll
-                    for (int k = 0; k < 7; ++k) {
-                        const int q = ht + 128 * k;
-                        const int reg = q / 14, part = q - reg * 14;
-                        const int foff = cg * SQ_XROW + part * 4;
-                        const bool ok = 2 * reg < rows_valid && foff + 3 < nF;
-                        const float* src = ok ? X + (long long)(region0 + reg) * nF + foff : X;
-                        cp_async16(dx + x_row_off(reg) + part * 16, src, ok);
+                        for (int k = 0; k < 8; ++k) {
+                            const bool ok = pok && 2 * (fr0 + 8 * k) < rows_valid;
+                            cp_async16(fdst + so + k * 1792 + 16 * (k & 1) + 32 * (k >> 1), ok ? src + k * fstep : X, ok);
+                        }
                     }
-                    {
-                        const int reg = ht >> 1, wd = ht & 1;
-                        const bool ok = 2 * reg < rows_valid && cg * 8 + wd * 4 < n;
-                        const uint8_t* src = ok ? MK + (long long)(region0 + reg) * mstride + cg * 8 + wd * 4 : MK;
-                        cp_async4(sb + SQ_STAGE_X + half * 512 + reg * 8 + wd * 4, src, ok);
-                    }
+                    const bool okm = mvalid && (full || cg * 8 + modd * 4 < n);
+                    cp_async4(mdst + so, okm ? msrc + cg * 8 : MK, okm);
                 }
                 cp_async_commit();
             };
-            fetch(0);
-            fetch(1);
+            fetch(0, 0);
+            fetch(1, 1);
 
             // ---- stage QK (FP32 -> BF16, canonical K-major) and u = W_in^T qk ----
             {
                 const float* Q = a.qk + res * a.qk_z + (long long)row0 * 128;
+                float4 lo[2][4], hi[2][4];                     // all 16 loads of the thread in flight at once
 #pragma unroll
                 for (int gq = 0; gq < 2; ++gq) {
                     const int r = warp * 16 + gq * 8 + (lane & 7);
                     const bool ok = r < rows_valid;
-                    float uacc[SQ_F];
-#pragma unroll
-                    for (int f = 0; f < SQ_F; ++f) uacc[f] = 0.f;
-                    float4 lo[4], hi[4];
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
                         const int kc = s * 4 + (lane >> 3);
                         const float4* src = reinterpret_cast<const float4*>(Q + (long long)r * 128 + kc * 8);
-                        lo[s] = ok ? src[0] : make_float4(0.f, 0.f, 0.f, 0.f);
-                        hi[s] = ok ? src[1] : make_float4(0.f, 0.f, 0.f, 0.f);
+                        lo[gq][s] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        hi[gq][s] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
+                }
+#pragma unroll
+                for (int gq = 0; gq < 2; ++gq) {
+                    const int r = warp * 16 + gq * 8 + (lane & 7);
+                    float uacc[SQ_F];
+#pragma unroll
+                    for (int f = 0; f < SQ_F; ++f) uacc[f] = 0.f;
 #pragma unroll
                     for (int s = 0; s < 4; ++s) {
                         const int kc = s * 4 + (lane >> 3);
+                        const float4 l4 = lo[gq][s], h4 = hi[gq][s];
                         uint4 pk;
-                        pk.x = pack2(lo[s].x, lo[s].y); pk.y = pack2(lo[s].z, lo[s].w);
-                        pk.z = pack2(hi[s].x, hi[s].y); pk.w = pack2(hi[s].z, hi[s].w);
+                        pk.x = pack2(l4.x, l4.y); pk.y = pack2(l4.z, l4.w);
+                        pk.z = pack2(h4.x, h4.y); pk.w = pack2(h4.z, h4.w);
                         *reinterpret_cast<uint4*>(smem + OFF_Q + (r >> 3) * 2048 + kc * 128 + (r & 7) * 16) = pk;
-                        const float qv[8] = {lo[s].x, lo[s].y, lo[s].z, lo[s].w, hi[s].x, hi[s].y, hi[s].z, hi[s].w};
+                        const float qv[8] = {l4.x, l4.y, l4.z, l4.w, h4.x, h4.y, h4.z, h4.w};
                         const float4* w4p = reinterpret_cast<const float4*>(w_s + kc * 8 * SQ_F);
                         float wv[8 * SQ_F];
 #pragma unroll
@@ -323,12 +335,15 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
             for (int f = 0; f < SQ_F; ++f) xb[f] = 0.f;
             const uint32_t pcol = trow + (half ? P_B_COL : 0);
             const uint32_t xro = x_row_off(rit);
+            int rs = 0, fs = 2;                               // ring stage being read / filled
             for (int idx = 0; idx < c_cnt; ++idx) {
                 cp_async_wait1();
                 named_barrier(2 + half, 128);
-                fetch(idx + 2);
+                fetch(idx + 2, fs);
                 const int cg = c_begin + idx;
-                const uint8_t* sb = smem + OFF_X + (idx % SQ_NSTAGE) * SQ_STAGE;
+                const uint8_t* sb = smem + OFF_X + rs * SQ_STAGE;
+                rs = rs == SQ_NSTAGE - 1 ? 0 : rs + 1;
+                fs = fs == SQ_NSTAGE - 1 ? 0 : fs + 1;
                 const float4* xs = reinterpret_cast<const float4*>(sb + half * SQ_HALF_X + xro);
                 const uint2 mk = *reinterpret_cast<const uint2*>(sb + SQ_STAGE_X + half * 512 + rit * 8);
                 float s[8];
@@ -348,10 +363,15 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
                     t *= scale2;
                     const uint32_t mb = ((i < 4 ? mk.x : mk.y) >> (8 * (i & 3))) & 0xffu;
                     if (mb) t = -1e9f;
-                    if (cg * 8 + i >= n) t = -INFINITY;
                     s[i] = t;
-                    cmx = fmaxf(cmx, t);
                 }
+                if (cg * 8 + 8 > n) {                          // (uniform) keys beyond n of a padded table
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (cg * 8 + i >= n) s[i] = -INFINITY;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) cmx = fmaxf(cmx, s[i]);
                 const bool ev = cmx > m + tau;              // (always on the first chunk that holds a key)
                 if (__any_sync(0xffffffffu, ev)) {
                     // move the reference maximum: rescale the running sums and the P chunks already in TMEM
