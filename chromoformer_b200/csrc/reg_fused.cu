@@ -53,6 +53,11 @@ __device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
     if (lane == 0) mbar_arrive(bar);
 }
 __device__ __forceinline__ void compute_barrier() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// the four warps that serve one of the two heads in flight
+__device__ __forceinline__ void group_barrier(int ch) {
+    if (ch) asm volatile("bar.sync 3, 128;" ::: "memory");
+    else asm volatile("bar.sync 2, 128;" ::: "memory");
+}
 
 // o * sigmoid(g) with sigmoid(g) = 0.5 + 0.5 tanh(g / 2): one MUFU (tanh.approx, abs. error 2^-11, well inside the
 // BF16 rounding of the result) instead of ex2 + rcp.  (Rows past the tile's last gene carry finite garbage that only
@@ -219,31 +224,12 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             } else {
             // attention on the tensor pipe: TMEM [0,128) / [128,256) = S then P of the two heads in flight,
             // [256,512) = projection pair (q0 q1 k0 k1 v0 v1 g0 g1, 32 columns each; O overwrites k)
-            const uint32_t idesc_s = umma_idesc_bf16(128, 128), idesc_o = umma_idesc_bf16(128, 32) | (1u << 16);
-            const uint32_t s_k = smem_u32(smem + OFF_K), s_v = smem_u32(smem + OFF_V);
+            // (the S = Q K^T and O = P V instructions are issued by the compute groups themselves)
             for (int t = 0; t < 4; ++t) {
                 if (t > 0) mbar_wait(&bars[B_ACCQFREE0], (t - 1) & 1);
                 consume(2 * t, s_xb, 2048, 256, false);
                 consume(2 * t + 1, s_xb, 2048, 384, false);
                 umma_commit(&bars[B_ACCQ0]);
-                for (int i = 0; i < 2; ++i) {       // S = Q K^T: A = BF16 Q in TMEM, B = K (K-major, 128 keys x 32)
-                    mbar_wait(&bars[B_QKVR0 + i], t & 1);
-                    tc_fence_after();
-#pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        umma_bf16_ts(tmem + 128 * i, tmem + 256 + 32 * i + 8 * k,
-                                     umma_smem_desc(s_k + i * 8192 + k * 256, 128, 512), idesc_s, k > 0 ? 1u : 0u);
-                    umma_commit(&bars[B_SR0 + i]);
-                }
-                for (int i = 0; i < 2; ++i) {       // O = P V: A = BF16 P in TMEM, B = V (MN-major, 32 dims x 128 keys)
-                    mbar_wait(&bars[B_PR0 + i], t & 1);
-                    tc_fence_after();
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma_bf16_ts(tmem + 256 + 64 + 32 * i, tmem + 128 * i + 8 * k,
-                                     umma_smem_desc(s_v + i * 8192 + k * 256, 128, 2048), idesc_o, k > 0 ? 1u : 0u);
-                    umma_commit(&bars[B_OR0 + i]);
-                }
             }
             }
             mbar_wait(&bars[B_ATTREADY], 0);
@@ -409,7 +395,6 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         for (int t = 0; t < 4; ++t) {
             // one thread per token row; warps 0-3 take head 2t, warps 4-7 head 2t+1
             const uint32_t pb = trow + 256;
-            const int head = 2 * t + ch;
             uint8_t* sk = smem + OFF_K + ch * 8192;
             uint8_t* sv = smem + OFF_V + ch * 8192;
             mbar_wait(&bars[B_ACCQ0], t & 1);
@@ -440,7 +425,20 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                 tmem_st_wait();
                 tc_fence_before();
                 fence_async_smem();
-                warp_arrive(&bars[B_QKVR0 + ch], lane);
+                // S = Q K^T is issued by this group itself (no round trip through the driver warp):
+                // A = BF16 Q in TMEM, B = K (K-major, 128 keys x 32)
+                group_barrier(ch);
+                if ((warp & 3) == 0 && lane == 0) {
+                    tc_fence_after();
+                    const uint32_t s_k = smem_u32(smem + OFF_K);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        umma_bf16_ts(tmem + 128 * ch, tmem + 256 + 32 * ch + 8 * k,
+                                     umma_smem_desc(s_k + ch * 8192 + k * 256, 128, 512), umma_idesc_bf16(128, 128),
+                                     k > 0 ? 1u : 0u);
+                    umma_commit(&bars[B_SR0 + ch]);
+                }
+                __syncwarp();
             }
             // scores of this row against the S keys of its own gene: a window of the S tile that starts at the
             // first gene touched by this warp (register indices stay compile-time, the column is warp-uniform)
@@ -490,7 +488,19 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                 tmem_st32(trow + 128 * ch + (kb >> 1), W);
                 tmem_st_wait();
                 tc_fence_before();
-                warp_arrive(&bars[B_PR0 + ch], lane);
+                // O = P V, issued by the group: A = BF16 P in TMEM, B = V (MN-major, 32 dims x 128 keys)
+                group_barrier(ch);
+                if ((warp & 3) == 0 && lane == 0) {
+                    tc_fence_after();
+                    const uint32_t s_v = smem_u32(smem + OFF_V);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        umma_bf16_ts(tmem + 256 + 64 + 32 * ch, tmem + 128 * ch + 8 * k,
+                                     umma_smem_desc(s_v + ch * 8192 + k * 256, 128, 2048),
+                                     umma_idesc_bf16(128, 32) | (1u << 16), k > 0 ? 1u : 0u);
+                    umma_commit(&bars[B_OR0 + ch]);
+                }
+                __syncwarp();
             }
             mbar_wait(&bars[B_OR0 + ch], t & 1);
             tc_fence_after();

@@ -27,7 +27,7 @@
 namespace chromo {
 namespace {
 
-constexpr int SQ_THREADS = 320;                 // 8 compute warps + driver warp + L2 prefetch warp
+constexpr int SQ_THREADS = 288;                 // 8 compute warps + 1 driver warp
 constexpr int SQ_NSTAGE = 3;
 constexpr int SQ_F = 7;
 constexpr int SQ_KC = 8;                        // keys per ring chunk
@@ -122,9 +122,6 @@ __device__ __forceinline__ void cp_async4(uint32_t dst, const void* src, bool va
     const int sz = valid ? 4 : 0;
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
 }
-__device__ __forceinline__ void l2_prefetch(const void* src, uint32_t bytes) {      // 16-byte aligned address and size
-    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
-}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -136,7 +133,6 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_CTL);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
-    int* prog = reinterpret_cast<int*>(tmem_slot + 1);     // quarter tiles entered, summed over the compute warps (pacing only)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     if (warp == 8) tmem_alloc(tmem_slot, 512);
@@ -147,7 +143,6 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
         mbar_init(&bars[B_P], 8);
         mbar_init(&bars[B_O], 1);
         mbar_init(&bars[B_EPI], 8);
-        *prog = 0;
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -201,53 +196,6 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
             }
         }
         __syncwarp();
-    } else if (warp == 9) {
-        // ===================================================== L2 prefetch warp ====================
-        // The ring moves 224-byte pieces of 64 region rows that lie 28*n bytes apart: as demand misses these are
-        // short, page-hopping DRAM accesses.  This warp asks L2 for the same bytes a quarter tile (about 1.4 KB per
-        // region and key half) at a time, two quarters ahead of the compute warps, so that the ring reads hit L2.
-        auto prefetch_quarter = [&](int Q) {
-            const int g = blockIdx.x + (Q >> 2) * gridDim.x, q = Q & 3;
-            if (g >= total) return;
-            const int res = a.order[g / tiles_per_res], tile = g % tiles_per_res;
-            const int n = a.n[res], ns = a.ns[res];
-            const int CA = first_half_chunks(ns), CB = (ns >> 3) - CA;
-            const int row0 = tile * 128;
-            const int rows_valid = min(128, rows_total - row0);
-            const long long rowb = (long long)n * SQ_F * 4;               // bytes per region row
-            const char* X = reinterpret_cast<const char*>(a.x[res]) + (long long)(row0 >> 1) * rowb;
-            if (q == 2 && lane < 4 && 32 * lane < rows_valid) {           // QK of this CTA's next tile, 16 KB per lane
-                const int g2 = g + gridDim.x;
-                if (g2 < total) {
-                    const int res2 = a.order[g2 / tiles_per_res], r2 = (g2 % tiles_per_res) * 128 + 32 * lane;
-                    const int left = rows_total - r2;
-                    if (left > 0)
-                        l2_prefetch(a.qk + res2 * a.qk_z + (long long)r2 * 128, (uint32_t)min(32, left) * 512u);
-                }
-            }
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                const int cb = h ? CA : 0, cn = h ? CB : CA;
-                const long long b0 = (long long)(cb + cn * q / 4) * (SQ_XROW * 4);
-                const long long b1 = min((long long)(cb + cn * (q + 1) / 4) * (SQ_XROW * 4), rowb);
-                if (b1 > b0) {
-#pragma unroll
-                    for (int rr = 0; rr < 2; ++rr) {
-                        const int reg = lane + 32 * rr;
-                        if (2 * reg < rows_valid) l2_prefetch(X + reg * rowb + b0, (uint32_t)(b1 - b0));
-                    }
-                }
-            }
-        };
-        prefetch_quarter(0);
-        prefetch_quarter(1);
-        const int n_tiles = (total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-        for (int Q = 0; Q < 4 * n_tiles; ++Q) {
-            // pacing only (a plain counter, not an mbarrier: nothing holds the compute warps back, so a phase
-            // parity could be lapped): wait until every compute warp has entered quarter Q
-            while (*reinterpret_cast<volatile int*>(prog) < 8 * (Q + 1)) __nanosleep(256);
-            prefetch_quarter(Q + 2);
-        }
     } else {
         // ===================================================== compute warps =======================
         const int half = warp >> 2, lq = warp & 3;
@@ -388,9 +336,7 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
             const uint32_t pcol = trow + (half ? P_B_COL : 0);
             const uint32_t xro = x_row_off(rit);
             int rs = 0, fs = 2;                               // ring stage being read / filled
-            int nq = 0;                                       // quarters of the tile announced to the prefetch warp
             for (int idx = 0; idx < c_cnt; ++idx) {
-                while (nq < 4 && idx >= c_cnt * nq / 4) { if (lane == 0) atomicAdd(prog, 1); ++nq; }
                 cp_async_wait1();
                 named_barrier(2 + half, 128);
                 fetch(idx + 2, fs);
@@ -459,7 +405,6 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
                 for (int i = 0; i < 4; ++i) pk[i] = pack2(s[2 * i], s[2 * i + 1]);
                 tmem_st4(pcol + 4 * idx, pk);
             }
-            while (nq < 4) { if (lane == 0) atomicAdd(prog, 1); ++nq; }
             cp_async_wait0();
             tmem_st_wait();
             tc_fence_before();
