@@ -43,7 +43,7 @@ constexpr uint32_t OFF_CTL = OFF_V + 16384;                 // mbarriers + TMEM 
 constexpr uint32_t RF_SMEM = OFF_CTL + 256;
 
 enum { B_FULL0 = 0, B_FREE0 = 3, B_ACCQ0 = 6, B_ACCQFREE0 = 8, B_XREADY = 10, B_ATTREADY, B_UREADY, B_FREADY,
-       B_ACCO, B_ACCF1, B_ACCF2, B_QKVR0, B_SR0 = B_QKVR0 + 2, B_PR0 = B_SR0 + 2, B_OR0 = B_PR0 + 2, B_COUNT = B_OR0 + 2 };
+       B_ACCO, B_ACCF1, B_ACCF2, B_QKVR0, B_SR0 = B_QKVR0 + 2, B_PR0 = B_SR0 + 2, B_OR0 = B_PR0 + 2, B_QKFREE = B_OR0 + 2, B_COUNT };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -176,6 +176,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             mbar_init(&bars[B_QKVR0 + i], 4); mbar_init(&bars[B_SR0 + i], 1);
             mbar_init(&bars[B_PR0 + i], 4); mbar_init(&bars[B_OR0 + i], 1);
         }
+        mbar_init(&bars[B_QKFREE], 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -222,13 +223,34 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                 umma_commit(&bars[B_ACCQ0 + buf]);
             }
             } else {
-            // attention on the tensor pipe: TMEM [0,128) / [128,256) = S then P of the two heads in flight,
-            // [256,512) = projection pair (q0 q1 k0 k1 v0 v1 g0 g1, 32 columns each; O overwrites k)
-            // (the S = Q K^T and O = P V instructions are issued by the compute groups themselves)
-            for (int t = 0; t < 4; ++t) {
-                if (t > 0) mbar_wait(&bars[B_ACCQFREE0], (t - 1) & 1);
-                consume(2 * t, s_xb, 2048, 256, false);
-                consume(2 * t + 1, s_xb, 2048, 384, false);
+            // attention on the tensor pipe: TMEM [0,128) / [128,256) = S, then P (first 64..77 columns) and O (last 32)
+            // of the two heads in flight; [256,512) = projection pair (q0 q1 k0 k1 v0 v1 g0 g1, 32 columns each).
+            // S = Q K^T and O = P V are issued by the compute groups themselves.  The projections of the NEXT pair
+            // overlap the attention of this one: [q|k] and v as soon as the S instructions are done with q / k and v
+            // sits in shared memory (B_QKFREE), the gates once this pair's gates have been read (B_ACCQFREE).
+            auto consume_half = [&](int c, int hf, uint32_t col, bool release) {
+                const int st = c % RF_NSTAGE;
+                mbar_wait(&bars[B_FULL0 + st], (c / RF_NSTAGE) & 1);
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(smem + OFF_STAGE + st * RF_CHUNK_BYTES) + hf * 16384;
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(tmem + col, umma_smem_desc(s_xb + k * 256, 128, 2048),
+                              umma_smem_desc(b_addr + k * 256, 128, 2048), umma_idesc_bf16(128, 64), k > 0 ? 1u : 0u);
+                if (release) {
+                    umma_commit(&bars[B_FREE0 + st]);
+                    if (c + 2 < RF_NCHUNK && c >= 1) issue_load(c + 2);
+                }
+            };
+            consume(0, s_xb, 2048, 256, false);
+            consume(1, s_xb, 2048, 384, false);
+            umma_commit(&bars[B_ACCQ0]);
+            for (int t = 0; t < 3; ++t) {
+                mbar_wait(&bars[B_QKFREE], t & 1);
+                consume(2 * t + 2, s_xb, 2048, 256, false);             // next [q | k]
+                consume_half(2 * t + 3, 0, 384, false);                 // next v
+                mbar_wait(&bars[B_ACCQFREE0], t & 1);
+                consume_half(2 * t + 3, 1, 448, true);                  // next gates
                 umma_commit(&bars[B_ACCQ0]);
             }
             }
@@ -257,28 +279,26 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
 
         // ---- phase 0: X -> BF16 operand
         {
-            for (int u0 = warp; u0 < 64; u0 += 32) {
-                float4 x[4][2];
-                int r_[4], kc_[4];
+            float4 x[8][2];                                   // all 16 loads of the thread in flight at once
+            int r_[8], kc_[8];
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const int u = u0 + q * 8;
-                    r_[q] = (u & 15) * 8 + (lane >> 2);
-                    kc_[q] = (u >> 4) * 4 + (lane & 3);
-                    x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (r_[q] < rows_valid) {
-                        const float* p = X + (row0 + r_[q]) * 128 + kc_[q] * 8;
-                        x[q][0] = __ldg(reinterpret_cast<const float4*>(p));
-                        x[q][1] = __ldg(reinterpret_cast<const float4*>(p + 4));
-                    }
+            for (int q = 0; q < 8; ++q) {
+                const int u = warp + (q >> 2) * 32 + (q & 3) * 8;
+                r_[q] = (u & 15) * 8 + (lane >> 2);
+                kc_[q] = (u >> 4) * 4 + (lane & 3);
+                x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r_[q] < rows_valid) {
+                    const float* p = X + (row0 + r_[q]) * 128 + kc_[q] * 8;
+                    x[q][0] = __ldg(reinterpret_cast<const float4*>(p));
+                    x[q][1] = __ldg(reinterpret_cast<const float4*>(p + 4));
                 }
+            }
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    uint4 pk;
-                    pk.x = pack2(x[q][0].x, x[q][0].y); pk.y = pack2(x[q][0].z, x[q][0].w);
-                    pk.z = pack2(x[q][1].x, x[q][1].y); pk.w = pack2(x[q][1].z, x[q][1].w);
-                    *reinterpret_cast<uint4*>(smem + OFF_XB + op_chunk(r_[q], kc_[q], 128)) = pk;
-                }
+            for (int q = 0; q < 8; ++q) {
+                uint4 pk;
+                pk.x = pack2(x[q][0].x, x[q][0].y); pk.y = pack2(x[q][0].z, x[q][0].w);
+                pk.z = pack2(x[q][1].x, x[q][1].y); pk.w = pack2(x[q][1].z, x[q][1].w);
+                *reinterpret_cast<uint4*>(smem + OFF_XB + op_chunk(r_[q], kc_[q], 128)) = pk;
             }
             fence_async_smem();
             warp_arrive(&bars[B_XREADY], lane);
@@ -450,6 +470,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             float w[64];
             mbar_wait(&bars[B_SR0 + ch], t & 1);
             tc_fence_after();
+            warp_arrive(&bars[B_QKFREE], lane);                   // q / k columns are dead, v is in shared memory
             {
                 const uint32_t sc0 = trow + 128 * ch + S * g_lo;
                 tmem_ld32(sc0, w);
@@ -495,7 +516,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                     const uint32_t s_v = smem_u32(smem + OFF_V);
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        umma_bf16_ts(tmem + 256 + 64 + 32 * ch, tmem + 128 * ch + 8 * k,
+                        umma_bf16_ts(tmem + 128 * ch + 96, tmem + 128 * ch + 8 * k,
                                      umma_smem_desc(s_v + ch * 8192 + k * 256, 128, 2048),
                                      umma_idesc_bf16(128, 32) | (1u << 16), k > 0 ? 1u : 0u);
                     umma_commit(&bars[B_OR0 + ch]);
@@ -505,7 +526,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             mbar_wait(&bars[B_OR0 + ch], t & 1);
             tc_fence_after();
             float o[32];
-            tmem_ld32(pb + 64 + 32 * ch, o);                      // O = P V (over the dead k columns)
+            tmem_ld32(trow + 128 * ch + 96, o);                   // O = P V (last 32 columns of the S tile)
             tmem_ld32(pb + 192 + 32 * ch, v);                     // gate
             tc_fence_before();
             warp_arrive(&bars[B_ACCQFREE0], lane);                // the projection pair may be overwritten
@@ -523,6 +544,19 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         fence_async_smem();
         warp_arrive(&bars[B_ATTREADY], lane);
 
+        // residual rows of phase 2 (FP32, from global / L2): issued now so that their latency hides behind the
+        // out-projection MMA; u_keep then carries U and is the residual of phase 4
+        float u_keep[2][32];
+#pragma unroll
+        for (int ci = 0; ci < 2; ++ci) {
+            const int c = (2 * ci + ch) * 32;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) r4 = __ldg(reinterpret_cast<const float4*>(X + grow * 128 + c + j));
+                u_keep[ci][j] = r4.x; u_keep[ci][j + 1] = r4.y; u_keep[ci][j + 2] = r4.z; u_keep[ci][j + 3] = r4.w;
+            }
+        }
         // small FP32 vectors of the layer -> shared (the v tile is dead): bo, ln1w, ln1b, b2, ln2w, ln2b, b1[256]
         float* prm = reinterpret_cast<float*>(smem + OFF_V);
         compute_barrier();                                    // every warp is done reading v
@@ -537,7 +571,6 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         compute_barrier();
         // ---- phase 2: out-projection epilogue: + bias + residual, LayerNorm -> U
         float* red = reinterpret_cast<float*>(smem + OFF_K);  // [2][2][128][2] partial sums (k, v are dead)
-        float u_keep[2][32];
         {
             mbar_wait(&bars[B_ACCO], 0);
             tc_fence_after();
@@ -549,11 +582,9 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                 tmem_ld32(trow + c, v);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    float4 r4 = make_float4(0, 0, 0, 0);
-                    if (valid) r4 = *reinterpret_cast<const float4*>(X + grow * 128 + c + j);
                     const float4 b4 = *reinterpret_cast<const float4*>(bo + c + j);
-                    const float t0 = v[j] + b4.x + r4.x, t1 = v[j + 1] + b4.y + r4.y;
-                    const float t2 = v[j + 2] + b4.z + r4.z, t3 = v[j + 3] + b4.w + r4.w;
+                    const float t0 = v[j] + b4.x + u_keep[ci][j], t1 = v[j + 1] + b4.y + u_keep[ci][j + 1];
+                    const float t2 = v[j + 2] + b4.z + u_keep[ci][j + 2], t3 = v[j + 3] + b4.w + u_keep[ci][j + 3];
                     u_keep[ci][j] = t0; u_keep[ci][j + 1] = t1; u_keep[ci][j + 2] = t2; u_keep[ci][j + 3] = t3;
                     sum += (t0 + t1) + (t2 + t3);
                     sq += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
