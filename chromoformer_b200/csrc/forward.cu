@@ -895,7 +895,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     // ---------------- Regulation transformer (net.py:152-153) ---------------
     const int dmr = c->reg_d_model, Hr = c->reg_heads;
     for (int l = 0; l < c->reg_layers; ++l) {
-        if (only && l != only->layer) continue;
+        if (only && only->layer >= 0 && l != only->layer) continue;
         const AttnOff& ra = L.reg[0].att[l];
         const FfnOff& rf = L.reg[0].ffn[l];
         const long long so = (long long)w.rslot(l) * w.r_slot;
@@ -904,10 +904,20 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         long long x_z = RS, y_z = RS;
         if (only) { xin = only->x; xout = only->y; x_z = y_z = only->xy_stride; }
         if (w.reg_fused && !getenv("CHROMO_NO_REG_FUSED")) {
-            // whole layer in one launch (reg_fused.cu)
+            // whole layer in one launch (reg_fused.cu); with the tensor-pipe attention ALL layers in one launch:
+            // a CTA keeps its 14 genes on chip from layer to layer (the tokens of a gene only attend to each other)
+            const bool all = (!only || only->layer < 0) && reg_fused_tensor_attention() && !getenv("CHROMO_REG_PER_LAYER");
+            if (all && l > 0) continue;
             RegFusedArgs a;
             a.B = B; a.S = S; a.G = 128 / S; a.n_tiles = (B + a.G - 1) / a.G;
             a.x = xin; a.x_z = x_z; a.y = xout; a.y_z = y_z;
+            a.n_layers = 1; a.y_mid = nullptr; a.y_mid_z = 0; a.y_l = 0; a.p_l = 0;
+            if (all) {
+                a.n_layers = c->reg_layers;
+                a.y_mid = ws + w.r_out; a.y_mid_z = RS; a.y_l = w.rslots > 1 ? w.r_slot : 0;
+                if (!only) a.y = ws + w.r_out + (long long)w.rslot(c->reg_layers - 1) * w.r_slot;
+                a.p_l = c->reg_layers > 1 ? L.reg[0].att[1].gamma_f - L.reg[0].att[0].gamma_f : 0;
+            }
             a.wstream = reinterpret_cast<const __nv_bfloat16*>(ws + w.reg_stream) + (long long)l * reg_stream_elems_per_layer();
             a.w_z = (long long)c->reg_layers * reg_stream_elems_per_layer();
             a.gamma_f = P + ra.gamma_f; a.bo = P + ra.ffb; a.ln1w = P + ra.lnw; a.ln1b = P + ra.lnb;
@@ -1036,7 +1046,7 @@ extern "C" int chromo_regulation_layer(const chromo_config_t* cfg, const float* 
                                        void* stream) {
     CHROMO_TRY(validate_config(cfg));
     if (!params || !x || !y || !imask || !freq || !workspace || batch < 1) { set_error("chromo_regulation_layer: bad argument"); return CHROMO_EINVAL; }
-    if (layer < 0 || layer >= cfg->reg_layers) { set_error("chromo_regulation_layer: no such layer"); return CHROMO_EINVAL; }
+    if (layer >= cfg->reg_layers) { set_error("chromo_regulation_layer: no such layer"); return CHROMO_EINVAL; }
     if (flags & CHROMO_F_TRAINING) { set_error("chromo_regulation_layer: inference only"); return CHROMO_EINVAL; }
     WsLayout w = make_ws_layout(cfg, batch, flags);
     if (workspace_floats < w.total) { set_error("workspace too small"); return CHROMO_ENOMEM; }
@@ -1046,6 +1056,11 @@ extern "C" int chromo_regulation_layer(const chromo_config_t* cfg, const float* 
     for (int r = 0; r < cfg->n_res; ++r) {
         if (!imask[r]) { set_error("chromo_regulation_layer: null interaction mask"); return CHROMO_EINVAL; }
         in.imask[r] = imask[r];
+    }
+    if (layer < 0 && !((flags & CHROMO_F_BF16) && w.reg_fused && reg_fused_tensor_attention() && !getenv("CHROMO_NO_REG_FUSED") &&
+                       !getenv("CHROMO_REG_PER_LAYER"))) {
+        set_error("chromo_regulation_layer: layer < 0 (all layers in one launch) needs the fused BF16 kernel");
+        return CHROMO_EINVAL;
     }
     RegOnly only{layer, x, y, xy_stride};
     return forward_impl(cfg, params, &in, nullptr, workspace, w, flags | CHROMO_F_REGONLY, (cudaStream_t)stream, &only);

@@ -188,6 +188,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         // ===================================================== driver: TMA + tcgen05.mma ====
         if (lane == 0) {
             const __nv_bfloat16* wsrc = a.wstream + z * a.w_z;
+            const int n_chunks = RF_NCHUNK * a.n_layers;   // the layers' chunks follow each other in the stream
             const uint32_t idesc = umma_idesc_bf16(128, 128);
             const uint32_t s_xb = smem_u32(smem + OFF_XB), s_att = smem_u32(smem + OFF_ATT);
             auto issue_load = [&](int c) {
@@ -208,18 +209,21 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                               umma_smem_desc(b_addr + k * 256, 128, 2048), idesc, (accumulate || k > 0) ? 1u : 0u);
                 umma_commit(&bars[B_FREE0 + st]);
                 // refill the ring behind the MMAs just queued (waits for chunk c-1 only)
-                if (c + 2 < RF_NCHUNK && c >= 1) issue_load(c + 2);
+                if (c + 2 < n_chunks && c >= 1) issue_load(c + 2);
             };
             issue_load(0);
             issue_load(1);
             issue_load(2);
-            mbar_wait(&bars[B_XREADY], 0);
+            for (int li = 0; li < a.n_layers; ++li) {
+            const int cb = li * RF_NCHUNK;
+            const uint32_t lp = li & 1;
+            mbar_wait(&bars[B_XREADY], lp);
             if (!TC) {
             for (int t = 0; t < 4; ++t) {
                 const int buf = t & 1;
                 if (t >= 2) mbar_wait(&bars[B_ACCQFREE0 + buf], 0);
-                consume(2 * t, s_xb, 2048, 256 * buf, false);          // [q | k] of heads 2t, 2t+1
-                consume(2 * t + 1, s_xb, 2048, 256 * buf + 128, false); // [v | gate]
+                consume(cb + 2 * t, s_xb, 2048, 256 * buf, false);          // [q | k] of heads 2t, 2t+1
+                consume(cb + 2 * t + 1, s_xb, 2048, 256 * buf + 128, false); // [v | gate]
                 umma_commit(&bars[B_ACCQ0 + buf]);
             }
             } else {
@@ -239,33 +243,34 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                               umma_smem_desc(b_addr + k * 256, 128, 2048), umma_idesc_bf16(128, 64), k > 0 ? 1u : 0u);
                 if (release) {
                     umma_commit(&bars[B_FREE0 + st]);
-                    if (c + 2 < RF_NCHUNK && c >= 1) issue_load(c + 2);
+                    if (c + 2 < n_chunks && c >= 1) issue_load(c + 2);
                 }
             };
-            consume(0, s_xb, 2048, 256, false);
-            consume(1, s_xb, 2048, 384, false);
+            consume(cb, s_xb, 2048, 256, false);
+            consume(cb + 1, s_xb, 2048, 384, false);
             umma_commit(&bars[B_ACCQ0]);
             for (int t = 0; t < 3; ++t) {
                 mbar_wait(&bars[B_QKFREE], t & 1);
-                consume(2 * t + 2, s_xb, 2048, 256, false);             // next [q | k]
-                consume_half(2 * t + 3, 0, 384, false);                 // next v
+                consume(cb + 2 * t + 2, s_xb, 2048, 256, false);        // next [q | k]
+                consume_half(cb + 2 * t + 3, 0, 384, false);            // next v
                 mbar_wait(&bars[B_ACCQFREE0], t & 1);
-                consume_half(2 * t + 3, 1, 448, true);                  // next gates
+                consume_half(cb + 2 * t + 3, 1, 448, true);             // next gates
                 umma_commit(&bars[B_ACCQ0]);
             }
             }
-            mbar_wait(&bars[B_ATTREADY], 0);
-            consume(8, s_att, 4096, 0, false);                          // out-projection, K halves
-            consume(9, s_att + 2048, 4096, 0, true);
+            mbar_wait(&bars[B_ATTREADY], lp);
+            consume(cb + 8, s_att, 4096, 0, false);                     // out-projection, K halves
+            consume(cb + 9, s_att + 2048, 4096, 0, true);
             umma_commit(&bars[B_ACCO]);
-            mbar_wait(&bars[B_UREADY], 0);
-            consume(10, s_xb, 2048, 256, false);                        // FFN-1, N halves
-            consume(11, s_xb, 2048, 384, false);
+            mbar_wait(&bars[B_UREADY], lp);
+            consume(cb + 10, s_xb, 2048, 256, false);                   // FFN-1, N halves
+            consume(cb + 11, s_xb, 2048, 384, false);
             umma_commit(&bars[B_ACCF1]);
-            mbar_wait(&bars[B_FREADY], 0);
-            consume(12, s_att, 4096, 0, false);                         // FFN-2, K halves
-            consume(13, s_att + 2048, 4096, 0, true);
+            mbar_wait(&bars[B_FREADY], lp);
+            consume(cb + 12, s_att, 4096, 0, false);                    // FFN-2, K halves
+            consume(cb + 13, s_att + 2048, 4096, 0, true);
             umma_commit(&bars[B_ACCF2]);
+            }   // layers
         }
     } else {
         // ===================================================== compute warps =================
@@ -277,7 +282,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         const float* X = a.x + z * a.x_z;
         float v[32];
 
-        // ---- phase 0: X -> BF16 operand
+        // ---- phase 0 (first layer only; later layers get their operand from phase 4): X -> BF16 operand
         {
             float4 x[8][2];                                   // all 16 loads of the thread in flight at once
             int r_[8], kc_[8];
@@ -320,9 +325,13 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                 if (mask[j]) mbits |= 1u << j;
             }
         }
+        for (int li = 0; li < a.n_layers; ++li) {
+        const uint32_t lp = li & 1;
+        const long long po = z * a.p_z + li * a.p_l;          // this (resolution, layer)'s parameters
+        const float* Xl = li == 0 ? X : a.y_mid + z * a.y_mid_z + ((li - 1) & 1) * a.y_l;   // the layer's input rows
         float gam[4];                                         // gamma_f of the four heads this thread serves (TC path)
 #pragma unroll
-        for (int t = 0; t < 4; ++t) gam[t] = a.gamma_f[z * a.p_z + 2 * t + ch];
+        for (int t = 0; t < 4; ++t) gam[t] = a.gamma_f[po + 2 * t + ch];
         if (!TC) {
         for (int t = 0; t < 4; ++t) {
             const int buf = t & 1;
@@ -349,7 +358,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             const int head = 2 * t + ch;
             float q[32];
             tmem_ld32(qb + 32 * ch, q);
-            const float gamma = a.gamma_f[z * a.p_z + head];
+            const float gamma = a.gamma_f[po + head];
             float s[SMAX];
             float mx = -INFINITY;
 #pragma unroll
@@ -553,7 +562,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) r4 = __ldg(reinterpret_cast<const float4*>(X + grow * 128 + c + j));
+                if (valid) r4 = __ldcg(reinterpret_cast<const float4*>(Xl + grow * 128 + c + j));   // (L2: written by this CTA)
                 u_keep[ci][j] = r4.x; u_keep[ci][j + 1] = r4.y; u_keep[ci][j + 2] = r4.z; u_keep[ci][j + 3] = r4.w;
             }
         }
@@ -565,14 +574,14 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             const int ct = warp * 32 + lane;                  // 0..255
 #pragma unroll
             for (int k = 0; k < 6; ++k)
-                if (ct < 128) prm[k * 128 + ct] = srcs[k][z * a.p_z + ct];
-            prm[768 + ct] = a.b1[z * a.p_z + ct];
+                if (ct < 128) prm[k * 128 + ct] = srcs[k][po + ct];
+            prm[768 + ct] = a.b1[po + ct];
         }
         compute_barrier();
         // ---- phase 2: out-projection epilogue: + bias + residual, LayerNorm -> U
         float* red = reinterpret_cast<float*>(smem + OFF_K);  // [2][2][128][2] partial sums (k, v are dead)
         {
-            mbar_wait(&bars[B_ACCO], 0);
+            mbar_wait(&bars[B_ACCO], lp);
             tc_fence_after();
             const float* bo = prm;
             float sum = 0.f, sq = 0.f;
@@ -622,7 +631,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
 
         // ---- phase 3: FFN-1 epilogue: + bias, ReLU -> BF16 operand (over the dead att tile)
         {
-            mbar_wait(&bars[B_ACCF1], 0);
+            mbar_wait(&bars[B_ACCF1], lp);
             tc_fence_after();
             const float* b1 = prm + 768;
 #pragma unroll
@@ -646,7 +655,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
 
         // ---- phase 4: FFN-2 epilogue: + bias + U, LayerNorm -> Y (coalesced through shared)
         {
-            mbar_wait(&bars[B_ACCF2], 0);
+            mbar_wait(&bars[B_ACCF2], lp);
             tc_fence_after();
             const float* b2 = prm + 384;
             float* red2 = red + 512;
@@ -673,14 +682,26 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
             const float* lw = prm + 512;
             const float* lb = prm + 640;
-            float* Y = a.y + z * a.y_z;
+            const bool more = li + 1 < a.n_layers;            // Y is also the next layer's operand (BF16, in place of X)
+            float* Y = more ? a.y_mid + z * a.y_mid_z + (li & 1) * a.y_l : a.y + z * a.y_z;
             float* stage = reinterpret_cast<float*>(smem + OFF_ATT) + warp * (32 * 33);   // FFN-2 MMAs are complete
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci) {
                 const int c = (2 * ci + ch) * 32;
 #pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    stage[lane * 33 + j] = (u_keep[ci][j] - mean) * rstd * lw[c + j] + lb[c + j];
+                for (int j = 0; j < 32; ++j) {
+                    u_keep[ci][j] = (u_keep[ci][j] - mean) * rstd * lw[c + j] + lb[c + j];
+                    stage[lane * 33 + j] = u_keep[ci][j];
+                }
+                if (more) {
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 pk;
+                        pk.x = pack2(u_keep[ci][j], u_keep[ci][j + 1]); pk.y = pack2(u_keep[ci][j + 2], u_keep[ci][j + 3]);
+                        pk.z = pack2(u_keep[ci][j + 4], u_keep[ci][j + 5]); pk.w = pack2(u_keep[ci][j + 6], u_keep[ci][j + 7]);
+                        *reinterpret_cast<uint4*>(smem + OFF_XB + op_chunk(row, (c + j) >> 3, 128)) = pk;
+                    }
+                }
                 __syncwarp();
                 const int cq = (lane & 7) * 4;
 #pragma unroll
@@ -693,7 +714,13 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                 }
                 __syncwarp();
             }
+            if (more) {
+                fence_async_smem();
+                compute_barrier();        // Y rows are visible to the CTA (residual of the next layer); prm / red are free
+                warp_arrive(&bars[B_XREADY], lane);
+            }
         }
+        }   // layers
     }
     tc_fence_before();
     __syncthreads();
@@ -738,6 +765,12 @@ int pack_reg_stream(const RegStreamArgs& a, int n_res, cudaStream_t st) {
     return CHROMO_OK;
 }
 
+bool reg_fused_tensor_attention() {
+    static int tc = -1;
+    if (tc < 0) { const char* e = getenv("CHROMO_REG_TC"); tc = (e && e[0] == '0') ? 0 : 1; }
+    return tc != 0;
+}
+
 int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
@@ -752,8 +785,8 @@ int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st) {
     // Attention on the tensor pipe (block-diagonal Q K^T / P V with Q and P rounded to BF16, as in every flash-attention
     // kernel) is the default: 14 % faster, max |logit error| 4.7e-3 vs 4.5e-3 for the CUDA-core attention on the demo set
     // (profiles/r01_precision.md).  CHROMO_REG_TC=0 selects the CUDA-core variant (FP32 q and probabilities).
-    static int tc = -1;
-    if (tc < 0) { const char* e = getenv("CHROMO_REG_TC"); tc = (e && e[0] == '0') ? 0 : 1; }
+    const int tc = reg_fused_tensor_attention() ? 1 : 0;
+    if (a.n_layers < 1 || (a.n_layers > 1 && !tc)) { set_error("reg_layer_fused: multi-layer launches need the tensor-pipe attention"); return CHROMO_EINVAL; }
     if (a.S == 9 && tc) reg_layer_fused_kernel<9, true><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
     else if (a.S == 9) reg_layer_fused_kernel<9, false><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
     else if (a.S == 17 && tc) reg_layer_fused_kernel<17, true><<<grid, RF_THREADS, RF_SMEM, st>>>(a);

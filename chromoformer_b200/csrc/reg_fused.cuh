@@ -9,8 +9,10 @@ namespace chromo {
 struct RegFusedArgs {
     int B, S, G, n_tiles;                   // genes, tokens per gene, genes per tile (G*S <= 128), tiles
     const float* x; long long x_z;          // layer input  [B*S, 128] FP32 (z = resolution stride)
-    float* y; long long y_z;                // layer output [B*S, 128] FP32
-    const __nv_bfloat16* wstream; long long w_z;   // this layer's 14 packed weight chunks
+    float* y; long long y_z;                // output of the LAST layer [B*S, 128] FP32
+    float* y_mid; long long y_mid_z, y_l;   // multi-layer launch: layer li < last writes y_mid + (li & 1) * y_l
+    int n_layers; long long p_l;            // layers run back to back by one launch, parameter stride between layers
+    const __nv_bfloat16* wstream; long long w_z;   // 14 packed weight chunks per layer, layers contiguous
     const float* gamma_f; const float* bo; const float* ln1w; const float* ln1b;
     const float* b1; const float* b2; const float* ln2w; const float* ln2b; long long p_z;
     const float* freq;                      // [B,S,S]
@@ -46,6 +48,7 @@ int launch_row_tail_fused(const RowTailArgs& a, int n_res, cudaStream_t st);
 
 long long reg_stream_elems_per_layer();
 int pack_reg_stream(const RegStreamArgs& a, int n_res, cudaStream_t st);
+bool reg_fused_tensor_attention();      // CHROMO_REG_TC != 0: attention on the tensor pipe; allows multi-layer launches
 int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st);
 
 }  // namespace chromo

@@ -105,7 +105,9 @@ int chromo_forward(const chromo_config_t* cfg, const float* params, const chromo
 /* ---- one Regulation-transformer layer: AttentionBlock with gate (modules.py:104-111 as used by
  * net.py:152-153), for every resolution at once: y[r] = layer(x[r]), x/y = [n_res][B*(i_max+1), d_emb] FP32
  * with `xy_stride` floats between resolutions.  With CHROMO_F_BF16 and the default geometry this is ONE
- * fused tcgen05 kernel per call (reg_fused.cu); otherwise the FP32 kernels.  Inference only.          */
+ * fused tcgen05 kernel per call (reg_fused.cu); otherwise the FP32 kernels.  Inference only.
+ * layer < 0 (fused BF16 kernel only): the whole Regulation transformer, y = layer_{L-1}(...layer_0(x)), in ONE
+ * launch, as the BF16 forward runs it (a CTA keeps its genes on chip from layer to layer).              */
 int chromo_regulation_layer(const chromo_config_t* cfg, const float* params, int32_t layer, const float* x,
                             float* y, int64_t xy_stride, const uint8_t* const* imask /* n_res x [B,S,S] */,
                             const float* freq /* [B,S,S] */, int32_t batch, float* workspace,
