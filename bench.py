@@ -28,6 +28,8 @@ KWS = ({"n_layers": 1, "n_heads": 2, "d_model": 128, "d_ff": 128},
        {"n_layers": 2, "n_heads": 2, "d_model": 128, "d_ff": 256},
        {"n_layers": 6, "n_heads": 8, "d_model": 256, "d_ff": 256})
 BINS = (2000, 500, 100)
+# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel (ncu --set full, profiles/)
+REG_TRAFFIC = {"bytes": 136.6e6, "source": "ncu --set full, profiles/r01_summary_final.md (dram read 68.2 MB + write 68.4 MB)"}
 REF_FLOPS_PER_GENE = 3862328832          # as-written forward, SURVEY §8d tier A
 
 
@@ -252,18 +254,43 @@ def main():
         fqk = resident["interaction_freq"][:Bk].contiguous()
         state = {"flags": flags}
 
-        def one_kernel():
-            _lib.check(lib.chromo_regulation_layer(ctypes.byref(cfgk), model.flat_params.data_ptr(), 2, xk.data_ptr(),
+        n_lay = int(cfgk.reg_layers)
+
+        def one_kernel():       # layer = -1: the whole Regulation transformer in one launch, as the forward runs it
+            _lib.check(lib.chromo_regulation_layer(ctypes.byref(cfgk), model.flat_params.data_ptr(), -1, xk.data_ptr(),
                                                    yk.data_ptr(), T * 128, imp, fqk.data_ptr(), Bk, wsk.data_ptr(), nws,
                                                    state["flags"], st), "chromo_regulation_layer")
         one_kernel()                                   # packs the weight stream once
         state["flags"] = flags | _lib.F_PACKED
         ms_k = timed(one_kernel, 20, 5)
-        flops_k = 3.0 * T * 2 * (4 * 256 * 128 + 256 * 128 + 2 * 128 * 256 + 8 * 9 * 32 * 2)
-        bytes_k = 2.0 * 3 * T * 128 * 4 + 3 * 14 * 32768
-        kname = (f"reg_layer_fused_kernel<9>: one Regulation layer, 3 resolutions x {T} tokens "
-                 "(proj + attention + out-proj/LN + FFN/LN, tcgen05 + TMA weight stream)")
-        traffic = {"bytes": 71.8e6, "source": "ncu --set full, profiles/r01_regfused_ncu.md (dram read 60.5 MB + write 11.3 MB)"}
+        flops_k = n_lay * 3.0 * T * 2 * (4 * 256 * 128 + 256 * 128 + 2 * 128 * 256 + 8 * 9 * 32 * 2)
+        bytes_k = 2.0 * 3 * T * 128 * 4 + n_lay * 3 * 14 * 32768
+        kname = (f"reg_layer_fused_kernel<9,true>: the {n_lay} Regulation layers in one launch, 3 resolutions x {T} tokens "
+                 "(per layer: proj + tensor-pipe attention + out-proj/LN + FFN/LN; tcgen05 + TMA weight stream)")
+        traffic = REG_TRAFFIC
+        # second kernel: the fused single-query attention core at n = 400 (HBM-bound: 11.2 KB of features per region)
+        nreg_s = Bk * 8
+        g = torch.Generator(device="cpu").manual_seed(1)
+        qk_s = torch.randn(nreg_s * 2, 128, device=dev) * 0.1
+        x_s = resident["pcre_feats"][100][:Bk].reshape(nreg_s, 400, 7).contiguous()
+        mk_s = torch.zeros(nreg_s, 400, dtype=torch.uint8, device=dev)
+        win_s = torch.randn(128, 7, device=dev) * 0.1
+        from chromoformer_b200.model import sinusoid_table
+        pe_s = sinusoid_table(400, 128).to(dev)
+        cb_s = torch.empty(nreg_s * 2, 128, device=dev)
+        ws_s = torch.empty(64 * 400, device=dev)
+
+        def one_sqa():
+            _lib.check(lib.chromo_single_query_attention(nreg_s, 400, qk_s.data_ptr(), x_s.data_ptr(), mk_s.data_ptr(),
+                                                         win_s.data_ptr(), pe_s.data_ptr(), 0.125, cb_s.data_ptr(),
+                                                         ws_s.data_ptr(), ws_s.numel(), st), "chromo_single_query_attention")
+        ms_s = timed(one_sqa, 20, 5)
+        bytes_s = nreg_s * (400 * 7 * 4 + 400 + 2 * 128 * 4 * 2)
+        sqa_line = {"kernel": "sqa_fused_kernel, n = 400 (scores + online softmax + both position-table GEMMs in TMEM)",
+                    "bound": "hbm", "regions": nreg_s, "ms_per_launch": ms_s, "algorithmic_bytes": bytes_s,
+                    "achieved": bytes_s / (ms_s * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                    "frac": bytes_s / (ms_s * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                    "tflops": nreg_s * 2 * 2.0 * (2 * 128 * 400) / (ms_s * 1e-3) / 1e12}
     else:
         x = torch.randn(3, T, 128, device=dev)
         wgt = torch.randn(3, 1024, 128, device=dev)
@@ -277,6 +304,7 @@ def main():
         bytes_k = 3.0 * T * (128 + 1024) * 4
         kname = f"gemm_simt_kernel<64,64> (FP32 CUDA cores) as launched for regulation.*.self_att.att (M={T}, N=1024, K=128, x3)"
         traffic = None
+        sqa_line = None
     ach = flops_k / (ms_k * 1e-3) / 1e12
     fpg = executed_flops_per_gene()
     roofline = {"bound": "tensor", "kernel": kname, "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
@@ -409,7 +437,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": workload_config(args), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
-                "roofline": roofline, "input_path": input_path, "raw_depth_path": raw_path, "ensemble_sweep": sweep, "cpu_baseline": cpu,
+                "roofline": roofline, "sqa_kernel": sqa_line, "input_path": input_path, "raw_depth_path": raw_path, "ensemble_sweep": sweep, "cpu_baseline": cpu,
                 "train": train}
         sys.stdout.flush()
         os.dup2(real_stdout, 1)

@@ -692,7 +692,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     // fused single-query attention core (sqa_fused.cu): all resolutions of a stage in one launch
     auto sqa_fused = [&](int regions, int H, const float* const* x, const uint8_t* const* mask, const int64_t* mstride,
                          const int64_t* moff, int64_t w_in, long long w_in_z, int dm, float* qk, float* cbar,
-                         bool* done) -> int {
+                         bool cbar_bf16, bool* done) -> int {
         *done = false;
         if (!fold) return CHROMO_OK;
         SqaFusedArgs f;
@@ -705,15 +705,18 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         for (int i = 1; i < NR; ++i)                       // long rows first
             for (int j = i; j > 0 && f.n[f.order[j]] > f.n[f.order[j - 1]]; --j) std::swap(f.order[j], f.order[j - 1]);
         f.qk = qk; f.qk_z = RS; f.cbar = cbar; f.cbar_z = RS;
+        if (cbar_bf16) f.cbar_bf16 = reinterpret_cast<__nv_bfloat16*>(cbar);   // same buffer, BF16 rows (the fused tail reads them)
         f.w_in = P + w_in; f.w_in_z = w_in_z;
         f.scale = 1.f / sqrtf((float)(dm / H));
         if (!sqa_fused_supported(f, H, F, D)) return CHROMO_OK;
         *done = true;
         return launch_sqa_fused(f, st);
     };
+    const bool tail = fold && w.tail_fused && !getenv("CHROMO_NO_TAIL_FUSED");
+    const bool cb16 = tail && !getenv("CHROMO_CBAR_FP32");     // Cbar handed from sqa_fused to the fused tail in BF16
     bool e_fused = false;
     CHROMO_TRY(sqa_fused(B, c->embed_heads, in->x_p, in->mask_p, in->mask_p_stride, in->mask_p_row_offset,
-                         L.embed[0].lin_proj, L.embed_stride, dme, ws + w.e_qk, ws + w.e_cbar, &e_fused));
+                         L.embed[0].lin_proj, L.embed_stride, dme, ws + w.e_qk, ws + w.e_cbar, cb16, &e_fused));
     for (int r = 0; r < NR && !e_fused; ++r) {
         SqaArgs s;
         s.rows = B; s.H = c->embed_heads; s.dm = dme; s.D = D; s.n = c->n_bins[r]; s.F = F;
@@ -730,12 +733,12 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         s.cbar = ws + r * RS + w.e_cbar; s.av = ws + r * RS + w.e_av; s.folded = fold;
         CHROMO_TRY(single_query_attention(s, st));
     }
-    const bool tail = fold && w.tail_fused && !getenv("CHROMO_NO_TAIL_FUSED");
     const long long tail_z = (long long)(1 + c->pw_layers) * TAIL_SLOT_ELEMS;
     if (tail) {   // out-projection + LN + FFN + LN in one launch (row_tail_fused.cu) -> X_in[b, 0, :]
         RowTailArgs t;
         t.M = B; t.dff = c->embed_d_ff;
         t.a = ws + w.e_cbar; t.lda = He * D; t.a_z = RS;
+        if (e_fused && cb16) t.a_bf16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.e_cbar);
         t.res = ws + w.e_hc; t.res_div = 1; t.res_z = RS;
         t.y = ws + w.r_xin; t.y_z = RS; t.c_div = 1; t.c_mul = S; t.c_add = 0;
         t.wstream = reinterpret_cast<const __nv_bfloat16*>(ws + w.tail_stream); t.w_z = tail_z;
@@ -816,7 +819,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         }
         bool p_fused = false;
         CHROMO_TRY(sqa_fused(R, Hp, in->x_pcre, in->mask_pcre, in->mask_pcre_stride, in->mask_pcre_row_offset,
-                             L.pw[0].lin_proj_pcre, L.pw_stride, dmp, ws + w.p_qk + so, ws + w.p_cbar + so, &p_fused));
+                             L.pw[0].lin_proj_pcre, L.pw_stride, dmp, ws + w.p_qk + so, ws + w.p_cbar + so, cb16, &p_fused));
         for (int r = 0; r < NR && !p_fused; ++r) {
             SqaArgs s;
             s.rows = R; s.H = Hp; s.dm = dmp; s.D = D; s.n = c->n_bins[r]; s.F = F;
@@ -840,6 +843,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             RowTailArgs t;
             t.M = R; t.dff = c->pw_d_ff;
             t.a = ws + w.p_cbar + so; t.lda = Hp * D; t.a_z = RS;
+            if (p_fused && cb16) t.a_bf16 = reinterpret_cast<const __nv_bfloat16*>(ws + w.p_cbar + so);
             t.res = pin; t.res_div = pin_div; t.res_z = RS;
             if (last) { t.y = ws + w.r_xin; t.c_div = I; t.c_mul = S; t.c_add = 1; }
             else { t.y = ws + w.p_out + so; t.c_div = 1; t.c_mul = 1; t.c_add = 0; }

@@ -30,6 +30,7 @@ struct RegStreamArgs {
 struct RowTailArgs {
     int M, dff;                             // rows, FFN width (128 or 256)
     const float* a; int lda; long long a_z; // Cbar [M, 256] FP32
+    const __nv_bfloat16* a_bf16 = nullptr;  // set: Cbar is BF16 at this address instead (lda in elements, resolution stride 2 * a_z elements)
     const float* res; int res_div; long long res_z;   // residual rows [M / res_div, 128]
     float* y; long long y_z; int c_div, c_mul, c_add; // output rows (remapped as in GemmArgs), 128 wide
     const __nv_bfloat16* wstream; long long w_z;

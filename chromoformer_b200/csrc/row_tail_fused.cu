@@ -123,6 +123,23 @@ __global__ void __launch_bounds__(RT_THREADS, 1) row_tail_fused_kernel(const Row
                 if (ct < 128) prm[k * 128 + ct] = srcs[k][z * a.p_z + ct];
             if (ct < a.dff) prm[768 + ct] = a.b1[z * a.p_z + ct];
             const float* A = a.a + z * a.a_z;
+            if (a.a_bf16) {                                     // BF16 rows: 16-byte chunks go straight into the operand
+                const __nv_bfloat16* Ab = a.a_bf16 + 2 * z * a.a_z;   // (same byte stride as the FP32 view)
+                uint4 xb[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int u = warp + (q >> 2) * 32 + (q & 3) * 8;
+                    const int r = (u & 15) * 8 + (lane >> 2), kc = (u >> 4) * 4 + (lane & 3);
+                    xb[q] = make_uint4(0u, 0u, 0u, 0u);
+                    if (r < rows_valid) xb[q] = __ldg(reinterpret_cast<const uint4*>(Ab + (long long)(m0 + r) * a.lda + kc * 8));
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const int u = warp + (q >> 2) * 32 + (q & 3) * 8;
+                    const int r = (u & 15) * 8 + (lane >> 2), kc = (u >> 4) * 4 + (lane & 3);
+                    *reinterpret_cast<uint4*>(smem + RT_OFF_A + t_chunk(r, kc, 256)) = xb[q];
+                }
+            } else
             for (int u0 = warp; u0 < 128; u0 += 32) {           // 16 row groups x 8 groups of four 8-column chunks
                 float4 x[4][2];
                 int r_[4], kc_[4];

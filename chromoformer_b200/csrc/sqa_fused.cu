@@ -467,6 +467,7 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
 #pragma unroll
                     for (int f = 0; f < SQ_F; ++f) w4[e][f] = w_s[(4 * lane + e) * SQ_F + f];
                 float* C = a.cbar + res * a.cbar_z + (long long)row0 * 128;
+                __nv_bfloat16* Cb = a.cbar_bf16 ? a.cbar_bf16 + 2 * res * a.cbar_z + (long long)row0 * 128 : nullptr;   // (same byte stride as the FP32 view)
 #pragma unroll 4
                 for (int i = 0; i < 16; ++i) {
                     const int r = 32 * lq + 16 * half + i;
@@ -482,7 +483,8 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
                             o.z = fmaf(w4[2][f], xr[f], o.z);
                             o.w = fmaf(w4[3][f], xr[f], o.w);
                         }
-                        *reinterpret_cast<float4*>(C + (long long)r * 128 + 4 * lane) = o;
+                        if (Cb) *reinterpret_cast<uint2*>(Cb + (long long)r * 128 + 4 * lane) = make_uint2(pack2(o.x, o.y), pack2(o.z, o.w));
+                        else *reinterpret_cast<float4*>(C + (long long)r * 128 + 4 * lane) = o;
                     }
                 }
             }
@@ -499,7 +501,8 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
 bool sqa_fused_supported(const SqaFusedArgs& a, int H, int F, int D) {
     if (H != 2 || F != SQ_F || D != 128 || a.n_res < 1 || a.regions < 1) return false;
     if (getenv("CHROMO_NO_SQA_FUSED")) return false;
-    if ((reinterpret_cast<uintptr_t>(a.qk) & 15) || (reinterpret_cast<uintptr_t>(a.cbar) & 15) || (a.qk_z & 3) || (a.cbar_z & 3))
+    if ((reinterpret_cast<uintptr_t>(a.qk) & 15) || (reinterpret_cast<uintptr_t>(a.cbar) & 15) || (a.qk_z & 3) || (a.cbar_z & 3) ||
+        (reinterpret_cast<uintptr_t>(a.cbar_bf16) & 15))
         return false;
     for (int r = 0; r < a.n_res; ++r) {
         if (a.n[r] < 4 || a.n[r] % 4 != 0 || a.ns[r] % 16 != 0 || a.ns[r] < a.n[r] || a.ns[r] > SQ_MAX_NS) return false;

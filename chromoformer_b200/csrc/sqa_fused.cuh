@@ -20,6 +20,7 @@ struct SqaFusedArgs {
     const __nv_bfloat16* pe_pk[CHROMO_MAX_RES];   // position table, BF16, [ns/8][16][8][8] (pack_weights order)
     float scale;
     float* cbar; long long cbar_z;            // [regions*2, 128]  sum_j p_j (W_in x_j + PE_j)
+    __nv_bfloat16* cbar_bf16 = nullptr;       // set: the result is written here in BF16 instead (dense rows; resolution stride 2 * cbar_z elements)
 };
 
 bool sqa_fused_supported(const SqaFusedArgs& a, int H, int F, int D);
