@@ -278,7 +278,7 @@ def main():
         from chromoformer_b200.model import sinusoid_table
         pe_s = sinusoid_table(400, 128).to(dev)
         cb_s = torch.empty(nreg_s * 2, 128, device=dev)
-        ws_s = torch.empty(64 * 400, device=dev)
+        ws_s = torch.empty(64 * 400 + 1024 + 8192 * ((nreg_s + 63) // 64), device=dev)
 
         def one_sqa():
             _lib.check(lib.chromo_single_query_attention(nreg_s, 400, qk_s.data_ptr(), x_s.data_ptr(), mk_s.data_ptr(),

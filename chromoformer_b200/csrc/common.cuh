@@ -90,6 +90,8 @@ struct WsLayout {
     int64_t h_z, h_h1;
     // BF16 tensor path: packed parameter mirror + packed position tables (float offsets)
     int64_t bf_params, bf_pe[CHROMO_MAX_RES], bf_pet[CHROMO_MAX_RES];
+    int64_t bf_win[2];                // W_in as the BF16 B operand of sqa_fused (embed, pairwise), 1024 floats per resolution
+    int64_t e_qkt, p_qkt;             // QK rows as BF16 operand tiles for sqa_fused (per-resolution block; p_qkt + slot * p_slot)
     // inference-time folded attention weights (FP32 scratch + packed BF16 mirror, element offsets equal):
     //   M = [W_k[h]^T W_q[h]]_h  ([H*D, D]),  N = [W_o[:,h] W_v[h]]_h  ([D, H*D]);  slot 0 = embed, 1.. = pairwise layers
     int64_t fold_f32, fold_bf, fold_stride, fold_total;

@@ -621,6 +621,8 @@ static int pack_all_weights(const chromo_config_t* c, const ParamLayout& L, cons
             }
         }
     }
+    CHROMO_TRY(sqa_pack_w_in(P + L.embed[0].lin_proj, L.embed_stride, reinterpret_cast<__nv_bfloat16*>(ws + w.bf_win[0]), 2048, NR, st));
+    CHROMO_TRY(sqa_pack_w_in(P + L.pw[0].lin_proj_pcre, L.pw_stride, reinterpret_cast<__nv_bfloat16*>(ws + w.bf_win[1]), 2048, NR, st));
     for (int r = 0; r < NR; ++r) {
         const int n = c->n_bins[r];
         if (!in->pos_enc[r]) continue;
@@ -674,25 +676,10 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     const FfnOff& ef = L.embed[0].ffn[0];
     const int dme = c->embed_d_model;
     const int He = c->embed_heads;
-    if (fold) {   // QK = Hc M^T  (M = [W_k[h]^T W_q[h]]_h)
-        GemmArgs g = gemm_args();
-        g.A = ws + w.e_hc; g.lda = D; g.sA1 = RS;
-        g.B = ws + w.fold_f32 + w.fold_slot[0]; g.ldb = D; g.sB1 = w.fold_stride;
-        g.C = ws + w.e_qk; g.ldc = He * D; g.sC1 = RS;
-        g.M = B; g.N = He * D; g.K = D;
-        CHROMO_TRY(lin(g, NR));
-    } else {      // Q = Hc W_q^T
-        GemmArgs g = gemm_args();
-        g.A = ws + w.e_hc; g.lda = D; g.sA1 = RS;
-        g.B = P + ea.att; g.ldb = D; g.sB1 = L.embed_stride;
-        g.C = ws + w.e_q; g.ldc = dme; g.sC1 = RS;
-        g.M = B; g.N = dme; g.K = D;
-        CHROMO_TRY(lin(g, NR));
-    }
     // fused single-query attention core (sqa_fused.cu): all resolutions of a stage in one launch
     auto sqa_fused = [&](int regions, int H, const float* const* x, const uint8_t* const* mask, const int64_t* mstride,
-                         const int64_t* moff, int64_t w_in, long long w_in_z, int dm, float* qk, float* cbar,
-                         bool cbar_bf16, bool* done) -> int {
+                         const int64_t* moff, int64_t w_in, long long w_in_z, int stage, int dm, float* qk, float* qkt,
+                         float* cbar, bool cbar_bf16, bool probe, bool have_tiles, bool* done) -> int {
         *done = false;
         if (!fold) return CHROMO_OK;
         SqaFusedArgs f;
@@ -704,19 +691,54 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         }
         for (int i = 1; i < NR; ++i)                       // long rows first
             for (int j = i; j > 0 && f.n[f.order[j]] > f.n[f.order[j - 1]]; --j) std::swap(f.order[j], f.order[j - 1]);
-        f.qk = qk; f.qk_z = RS; f.cbar = cbar; f.cbar_z = RS;
+        f.qk_tiles = reinterpret_cast<const __nv_bfloat16*>(qkt); f.qk_tz = 2 * RS;
+        f.w_in_pk = reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_win[stage]); f.w_in_pk_z = 2048;
+        f.cbar = cbar; f.cbar_z = RS;
         if (cbar_bf16) f.cbar_bf16 = reinterpret_cast<__nv_bfloat16*>(cbar);   // same buffer, BF16 rows (the fused tail reads them)
         f.w_in = P + w_in; f.w_in_z = w_in_z;
         f.scale = 1.f / sqrtf((float)(dm / H));
         if (!sqa_fused_supported(f, H, F, D)) return CHROMO_OK;
         *done = true;
+        if (probe) return CHROMO_OK;
+        // QK rows -> BF16 operand tiles, unless the query GEMM's epilogue has written them already
+        if (!have_tiles) CHROMO_TRY(sqa_pack_qk(qk, RS, reinterpret_cast<__nv_bfloat16*>(qkt), 2 * RS, regions * H, NR, st));
         return launch_sqa_fused(f, st);
     };
     const bool tail = fold && w.tail_fused && !getenv("CHROMO_NO_TAIL_FUSED");
     const bool cb16 = tail && !getenv("CHROMO_CBAR_FP32");     // Cbar handed from sqa_fused to the fused tail in BF16
-    bool e_fused = false;
+    // the query GEMM of a stage: straight into the operand tiles of sqa_fused when that kernel will run and the tensor
+    // GEMM takes the shape, FP32 rows otherwise
+    auto qk_gemm = [&](const GemmArgs& g, float* qkt, bool sqa_ok, bool* tiles) -> int {
+        *tiles = false;
+        if (sqa_ok && !getenv("CHROMO_QK_FP32")) {
+            GemmArgs t = g;
+            t.c_sqa_tiles = 1; t.C = qkt; t.sC1 = 2 * RS;
+            if (umma_supported(t)) { *tiles = true; return lin(t, NR); }
+        }
+        return lin(g, NR);
+    };
+    bool e_fused = false, e_tiles = false;
     CHROMO_TRY(sqa_fused(B, c->embed_heads, in->x_p, in->mask_p, in->mask_p_stride, in->mask_p_row_offset,
-                         L.embed[0].lin_proj, L.embed_stride, dme, ws + w.e_qk, ws + w.e_cbar, cb16, &e_fused));
+                         L.embed[0].lin_proj, L.embed_stride, 0, dme, ws + w.e_qk, ws + w.e_qkt, ws + w.e_cbar, cb16, true, false,
+                         &e_fused));
+    if (fold) {   // QK = Hc M^T  (M = [W_k[h]^T W_q[h]]_h)
+        GemmArgs g = gemm_args();
+        g.A = ws + w.e_hc; g.lda = D; g.sA1 = RS;
+        g.B = ws + w.fold_f32 + w.fold_slot[0]; g.ldb = D; g.sB1 = w.fold_stride;
+        g.C = ws + w.e_qk; g.ldc = He * D; g.sC1 = RS;
+        g.M = B; g.N = He * D; g.K = D;
+        CHROMO_TRY(qk_gemm(g, ws + w.e_qkt, e_fused, &e_tiles));
+    } else {      // Q = Hc W_q^T
+        GemmArgs g = gemm_args();
+        g.A = ws + w.e_hc; g.lda = D; g.sA1 = RS;
+        g.B = P + ea.att; g.ldb = D; g.sB1 = L.embed_stride;
+        g.C = ws + w.e_q; g.ldc = dme; g.sC1 = RS;
+        g.M = B; g.N = dme; g.K = D;
+        CHROMO_TRY(lin(g, NR));
+    }
+    CHROMO_TRY(sqa_fused(B, c->embed_heads, in->x_p, in->mask_p, in->mask_p_stride, in->mask_p_row_offset,
+                         L.embed[0].lin_proj, L.embed_stride, 0, dme, ws + w.e_qk, ws + w.e_qkt, ws + w.e_cbar, cb16, false, e_tiles,
+                         &e_fused));
     for (int r = 0; r < NR && !e_fused; ++r) {
         SqaArgs s;
         s.rows = B; s.H = c->embed_heads; s.dm = dme; s.D = D; s.n = c->n_bins[r]; s.F = F;
@@ -802,13 +824,17 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         const float* pin = l == 0 ? ws + w.p_pp : ws + w.p_out + (long long)w.pslot(l - 1) * w.p_slot;
         const int pin_div = l == 0 ? I : 1;
         const bool last = l == c->pw_layers - 1;
+        bool p_fused = false, p_tiles = false;
+        CHROMO_TRY(sqa_fused(R, Hp, in->x_pcre, in->mask_pcre, in->mask_pcre_stride, in->mask_pcre_row_offset,
+                             L.pw[0].lin_proj_pcre, L.pw_stride, 1, dmp, ws + w.p_qk + so, ws + w.p_qkt + so, ws + w.p_cbar + so,
+                             cb16, true, false, &p_fused));
         if (fold) {   // QK = P_l M^T
             GemmArgs g = gemm_args();
             g.A = pin; g.lda = D; g.sA1 = RS; g.a_div = pin_div;
             g.B = ws + w.fold_f32 + w.fold_slot[1 + l]; g.ldb = D; g.sB1 = w.fold_stride;
             g.C = ws + w.p_qk + so; g.ldc = Hp * D; g.sC1 = RS;
             g.M = R; g.N = Hp * D; g.K = D;
-            CHROMO_TRY(lin(g, NR));
+            CHROMO_TRY(qk_gemm(g, ws + w.p_qkt + so, p_fused, &p_tiles));
         } else {      // Q = P_l W_q^T                             modules.py:159
             GemmArgs g = gemm_args();
             g.A = pin; g.lda = D; g.sA1 = RS; g.a_div = pin_div;
@@ -817,9 +843,9 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.M = R; g.N = dmp; g.K = D;
             CHROMO_TRY(lin(g, NR));
         }
-        bool p_fused = false;
         CHROMO_TRY(sqa_fused(R, Hp, in->x_pcre, in->mask_pcre, in->mask_pcre_stride, in->mask_pcre_row_offset,
-                             L.pw[0].lin_proj_pcre, L.pw_stride, dmp, ws + w.p_qk + so, ws + w.p_cbar + so, cb16, &p_fused));
+                             L.pw[0].lin_proj_pcre, L.pw_stride, 1, dmp, ws + w.p_qk + so, ws + w.p_qkt + so, ws + w.p_cbar + so,
+                             cb16, false, p_tiles, &p_fused));
         for (int r = 0; r < NR && !p_fused; ++r) {
             SqaArgs s;
             s.rows = R; s.H = Hp; s.dm = dmp; s.D = D; s.n = c->n_bins[r]; s.F = F;
@@ -1096,22 +1122,27 @@ extern "C" int chromo_single_query_attention(int32_t regions, int32_t n, const f
         return CHROMO_EINVAL;
     }
     const int ns = n <= 32 ? 32 : (n + 15) / 16 * 16;
-    if (workspace_floats < (int64_t)ns * 64) { set_error("chromo_single_query_attention: workspace too small"); return CHROMO_EINVAL; }
+    const int64_t tiles = ((int64_t)regions * 2 + 127) / 128;
+    if (workspace_floats < (int64_t)ns * 64 + 1024 + tiles * 8192) { set_error("chromo_single_query_attention: workspace too small"); return CHROMO_EINVAL; }
     cudaStream_t st = (cudaStream_t)stream;
     __nv_bfloat16* pk = reinterpret_cast<__nv_bfloat16*>(workspace);
+    __nv_bfloat16* wpk = reinterpret_cast<__nv_bfloat16*>(workspace + (int64_t)ns * 64);
+    __nv_bfloat16* qkt = reinterpret_cast<__nv_bfloat16*>(workspace + (int64_t)ns * 64 + 1024);
     SqaFusedArgs f;
     f.n_res = 1; f.regions = regions;
     f.n[0] = n; f.ns[0] = ns; f.order[0] = 0;
     f.x[0] = x; f.mask[0] = mask; f.mask_stride[0] = n; f.mask_row_offset[0] = 0;
     f.pe_pk[0] = pk;
-    f.qk = qk; f.qk_z = 0; f.cbar = cbar; f.cbar_z = 0;
-    f.w_in = w_in; f.w_in_z = 0;
+    f.qk_tiles = qkt; f.qk_tz = 0; f.cbar = cbar; f.cbar_z = 0;
+    f.w_in = w_in; f.w_in_z = 0; f.w_in_pk = wpk; f.w_in_pk_z = 0;
     f.scale = scale;
-    if (umma_tile_n(ns) == 0 || !sqa_fused_supported(f, 2, 7, 128)) {
+    if (umma_tile_n(ns) == 0 || (reinterpret_cast<uintptr_t>(qk) & 15) || !sqa_fused_supported(f, 2, 7, 128)) {
         set_error("chromo_single_query_attention: shape / alignment not supported by the fused kernel");
         return CHROMO_EINVAL;
     }
     CHROMO_TRY(pack_weights(pos_enc, pk, ns, 128, umma_tile_n(ns), 0, 1, false, 128, st, n));
+    CHROMO_TRY(sqa_pack_w_in(w_in, 0, wpk, 0, 1, st));
+    CHROMO_TRY(sqa_pack_qk(qk, 0, qkt, 0, regions * 2, 1, st));
     return launch_sqa_fused(f, st);
 }
 

@@ -38,6 +38,9 @@ struct GemmArgs {
     int accumulate;                            // C += result
     int ksplit;                                // split-K factor; >1 => atomicAdd into C
     int c_bf16;                                // tensor path only: C is BF16 (ldc, strides in elements)
+    int c_sqa_tiles;                           // tensor path only: C [M, 256] = QK of (region m, head n / 128) written as the
+                                               //   BF16 operand tiles of sqa_fused (row 2m + head, 128-row tiles in the
+                                               //   canonical K-major layout); sC1 in BF16 elements
 };
 
 static inline GemmArgs gemm_args() {

@@ -199,6 +199,8 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
             w.bf_pe[r] = take((n16 * D + 1) / 2 + 8);
             w.bf_pet[r] = take((n16 * D + 1) / 2 + 8);
         }
+        w.bf_win[0] = take((int64_t)c->n_res * 1024);
+        w.bf_win[1] = take((int64_t)c->n_res * 1024);
         if (!w.training) {
             int64_t off = 0;
             w.fold_slot[0] = off; off += (int64_t)2 * He * D * D;
@@ -225,6 +227,7 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
     w.e_hc = take((int64_t)B * D);
     w.e_q = take((int64_t)B * c->embed_d_model);
     w.e_qk = take((int64_t)B * He * D);
+    w.e_qkt = take((int64_t)((B * He + 127) / 128) * 8192);
     w.e_cbar = take((int64_t)B * He * D);
     w.e_xbar = take((int64_t)B * He * 8);
     w.e_av = take((int64_t)B * c->embed_d_model);
@@ -237,6 +240,7 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
         int64_t s0 = cur;
         w.p_q = take((int64_t)R * c->pw_d_model) - s0;
         w.p_qk = take((int64_t)R * Hp * D) - s0;
+        w.p_qkt = take((int64_t)((R * Hp + 127) / 128) * 8192) - s0;
         w.p_cbar = take((int64_t)R * Hp * D) - s0;
         w.p_xbar = take((int64_t)R * Hp * 8) - s0;
         w.p_av = take((int64_t)R * c->pw_d_model) - s0;
@@ -247,7 +251,7 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
         w.p_out = take((int64_t)R * D) - s0;
         w.p_slot = cur - s0;
         // make offsets absolute for slot 0
-        w.p_q += s0; w.p_qk += s0; w.p_cbar += s0; w.p_xbar += s0; w.p_av += s0;
+        w.p_q += s0; w.p_qk += s0; w.p_qkt += s0; w.p_cbar += s0; w.p_xbar += s0; w.p_av += s0;
         w.p_preU += s0; w.p_u += s0; w.p_f += s0; w.p_preY += s0; w.p_out += s0;
         cur = s0 + w.p_slot * w.pslots;
     }

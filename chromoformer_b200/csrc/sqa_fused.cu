@@ -6,8 +6,9 @@
 //   S = QK PE^T  [128 rows x n]   and   O = P PE  [128 rows x 128]
 // and this kernel keeps S, P and O in tensor memory, so that neither the scores nor the probabilities (2 x 105 MB per
 // stage at n = 400) ever reach HBM.  One persistent CTA per SM walks 128-row tiles (64 regions x 2 heads):
-//   compute warps  stage QK (FP32 -> BF16 canonical K-major tile) and u = W_in^T qk (FP32, 7 per row)
-//   driver warp    MMA 1: S = QK PE^T (B = table, K-major)                                       -> TMEM [0, ns)
+//   driver warp    QK tile (BF16, already in the canonical K-major operand layout: written that way by the query
+//                  GEMM's epilogue, or by sqa_pack_qk) -> shared memory with ONE TMA bulk copy, a tile ahead
+//   driver warp    MMA 1: S = QK PE^T (B = table, K-major) -> TMEM [0, ns);  u = QK W_in (N = 16) -> TMEM [400, 416)
 //   compute warps  thread = (row, key half), ONE pass over the keys with an online softmax:
 //                    s_j = (S_j + u.x_j) scale (base 2), mask;  p_j = 2^(s_j - m);  sum, sum p_j x_j;  P (BF16) -> TMEM
 //                  m is the running reference maximum of the thread; it is only moved when a chunk exceeds it by
@@ -18,7 +19,7 @@
 //   compute warps  cbar = (O_A 2^(mA-m) + O_B 2^(mB-m)) / sum + W_in xbar, transposed through shared memory,
 //                  512-byte row stores
 // Tensor-memory map (512 columns): scores [0, ns); P of the first key half in place [0, 4*CA), P of the second half
-// [416, 416 + 4*CB); O_A [256, 384) and O_B [128, 256) once the scores are dead.
+// [416, 416 + 4*CB); u [400, 407); O_A [256, 384) and O_B [128, 256) once the scores are dead.
 #include <stdlib.h>
 
 #include "sqa_fused.cuh"
@@ -37,17 +38,16 @@ constexpr uint32_t SQ_STAGE_X = 2 * SQ_HALF_X;
 constexpr uint32_t SQ_STAGE = SQ_STAGE_X + 2 * 64 * 8;      // + 8 mask bytes per region and half
 constexpr int SQ_MAX_NS = 400;
 constexpr uint32_t OFF_PE = 0;                               // position table, up to 400 x 128 BF16
-constexpr uint32_t OFF_Q = OFF_PE + SQ_MAX_NS * 256;         // [128 x 128] BF16 QK tile; later the row exchange area
-constexpr uint32_t OFF_X = OFF_Q + 32768;                    // ring; later the store staging (4 x 32 x 132 floats)
-constexpr uint32_t OFF_U = OFF_X + SQ_NSTAGE * SQ_STAGE;     // u[128][7]
-constexpr uint32_t OFF_W = OFF_U + 128 * SQ_F * 4;              // W_in [128][7] FP32 of the current resolution
-constexpr uint32_t OFF_CTL = OFF_W + 128 * SQ_F * 4;
+constexpr uint32_t OFF_Q = OFF_PE + SQ_MAX_NS * 256;         // [128 x 128] BF16 QK tile (TMA destination)
+constexpr uint32_t OFF_X = OFF_Q + 32768;                    // ring; after the pass: store staging + row exchange area
+constexpr uint32_t OFF_WB = OFF_X + SQ_NSTAGE * SQ_STAGE;    // W_in as a BF16 operand [16 x 128] (rows 7.. are zero)
+constexpr uint32_t OFF_CTL = OFF_WB + 4096;
 constexpr uint32_t SQ_SMEM = OFF_CTL + 128;
+constexpr uint32_t SQ_XCH = 4 * 32 * 132 * 4;                // exchange area inside the ring, behind the store staging
 static_assert(SQ_SMEM <= 227 * 1024, "shared memory budget");
-static_assert(4 * 32 * 132 * 4 <= SQ_NSTAGE * SQ_STAGE, "store staging fits in the ring");
-// exchange area inside OFF_Q (valid between MMA 1 and the next tile)
 constexpr uint32_t QX_MAX = 0, QX_SUM = 1024, QX_XB = 2048, QX_XBAR = 2048 + 8192;
-constexpr int P_B_COL = 416, OA_COL = 256, OB_COL = 128;
+static_assert(SQ_XCH + QX_XBAR + 4096 <= SQ_NSTAGE * SQ_STAGE, "store staging + exchange area fit in the ring");
+constexpr int P_B_COL = 416, OA_COL = 256, OB_COL = 128, U_COL = 400;
 constexpr float SQ_TAU = 16.f;                  // the reference maximum moves when a chunk exceeds it by 2^16
 constexpr float SQ_MINIT = -3.0e38f;
 
@@ -57,7 +57,7 @@ __device__ __forceinline__ uint32_t x_row_off(int r) {
     return (uint32_t)r * (SQ_XROW * 4) + 16u * (uint32_t)(((r >> 2) & 1) + ((r >> 3) & 1)) + 32u * (uint32_t)(r >> 4);
 }
 
-enum { B_PE = 0, B_QREADY, B_S, B_P, B_O, B_EPI, B_COUNT };
+enum { B_PE = 0, B_QFULL, B_S, B_P, B_O, B_EPI, B_COUNT };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
     if (warp == 8) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
         mbar_init(&bars[B_PE], 1);
-        mbar_init(&bars[B_QREADY], 8);
+        mbar_init(&bars[B_QFULL], 1);
         mbar_init(&bars[B_S], 1);
         mbar_init(&bars[B_P], 8);
         mbar_init(&bars[B_O], 1);
@@ -165,13 +165,19 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
                 const int CA = first_half_chunks(ns), CB = (ns >> 3) - CA;
                 if (res != cur) {
                     if (it > 0) mbar_wait(&bars[B_O], (it - 1) & 1);               // MMA 2 of the last tile is done with the table
-                    mbar_expect_tx(&bars[B_PE], (uint32_t)ns * 256u);
+                    mbar_expect_tx(&bars[B_PE], (uint32_t)ns * 256u + 4096u);
                     tma_bulk_g2s(smem + OFF_PE, a.pe_pk[res], (uint32_t)ns * 256u, &bars[B_PE]);
+                    tma_bulk_g2s(smem + OFF_WB, a.w_in_pk + res * a.w_in_pk_z, 4096u, &bars[B_PE]);
                     mbar_wait(&bars[B_PE], pe_par);
                     pe_par ^= 1;
                     cur = res;
                 }
-                mbar_wait(&bars[B_QREADY], it & 1);
+                if (it == 0) {                                                     // (later tiles are fetched a tile ahead)
+                    mbar_expect_tx(&bars[B_QFULL], 32768u);
+                    tma_bulk_g2s(smem + OFF_Q, a.qk_tiles + res * a.qk_tz + (long long)(g % tiles_per_res) * 16384, 32768u,
+                                 &bars[B_QFULL]);
+                }
+                mbar_wait(&bars[B_QFULL], it & 1);
                 if (it > 0) mbar_wait(&bars[B_EPI], (it - 1) & 1);                 // O of the last tile has been read
                 tc_fence_after();
                 for (int n0 = 0; n0 < ns; n0 += 256) {                             // S = QK PE^T, N in parts of <= 256
@@ -182,7 +188,22 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
                         umma_bf16(tmem + n0, umma_smem_desc(s_q + k * 256, 128, 2048),
                                   umma_smem_desc(s_pe + (n0 >> 3) * 2048 + k * 256, 128, 2048), idesc, k > 0 ? 1u : 0u);
                 }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)                                         // u = QK W_in (columns 7.. are zero)
+                    umma_bf16(tmem + U_COL, umma_smem_desc(s_q + k * 256, 128, 2048),
+                              umma_smem_desc(smem_u32(smem + OFF_WB) + k * 256, 128, 2048), umma_idesc_bf16(128, 16),
+                              k > 0 ? 1u : 0u);
                 umma_commit(&bars[B_S]);
+                {   // the QK tile of this CTA's next tile, as soon as MMA 1 no longer reads the buffer
+                    const int g2 = g + gridDim.x;
+                    if (g2 < total) {
+                        mbar_wait(&bars[B_S], it & 1);
+                        const int res2 = a.order[g2 / tiles_per_res];
+                        mbar_expect_tx(&bars[B_QFULL], 32768u);
+                        tma_bulk_g2s(smem + OFF_Q, a.qk_tiles + res2 * a.qk_tz + (long long)(g2 % tiles_per_res) * 16384,
+                                     32768u, &bars[B_QFULL]);
+                    }
+                }
                 mbar_wait(&bars[B_P], it & 1);
                 tc_fence_after();
                 // O = P PE: key blocks of the table are 2048 B apart (LBO), channel blocks 128 B (SBO)
@@ -204,14 +225,12 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
         const int ht = tid & 127;                            // thread within the key half
         const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
         const uint32_t s_ring = smem_u32(smem + OFF_X);
-        float* u_s = reinterpret_cast<float*>(smem + OFF_U);
-        float* red_max = reinterpret_cast<float*>(smem + OFF_Q + QX_MAX);
-        float* red_sum = reinterpret_cast<float*>(smem + OFF_Q + QX_SUM);
-        float* red_xb = reinterpret_cast<float*>(smem + OFF_Q + QX_XB);
-        float* xbar_s = reinterpret_cast<float*>(smem + OFF_Q + QX_XBAR);
+        float* red_max = reinterpret_cast<float*>(smem + OFF_X + SQ_XCH + QX_MAX);
+        float* red_sum = reinterpret_cast<float*>(smem + OFF_X + SQ_XCH + QX_SUM);
+        float* red_xb = reinterpret_cast<float*>(smem + OFF_X + SQ_XCH + QX_XB);
+        float* xbar_s = reinterpret_cast<float*>(smem + OFF_X + SQ_XCH + QX_XBAR);
         const float scale2 = a.scale * 1.4426950408889634f;  // softmax in base 2
-        const float* w_s = reinterpret_cast<const float*>(smem + OFF_W);
-        int it = 0, cur = -1;
+        int it = 0;
         for (int g = blockIdx.x; g < total; g += gridDim.x, ++it) {
             const int res = a.order[g / tiles_per_res], tile = g % tiles_per_res;
             const int n = a.n[res], ns = a.ns[res];
@@ -222,12 +241,7 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
             const float* X = a.x[res];
             const uint8_t* MK = a.mask[res] + a.mask_row_offset[res];
             const long long mstride = a.mask_stride[res];
-            if (res != cur) {                                 // (the previous tile ended with a compute barrier)
-                const float4* W = reinterpret_cast<const float4*>(a.w_in + res * a.w_in_z);
-                if (tid < 128 * SQ_F / 4) reinterpret_cast<float4*>(smem + OFF_W)[tid] = W[tid];
-                cur = res;
-                compute_barrier();
-            }
+            const float* W = a.w_in + res * a.w_in_z;
             const int c_begin = half ? CA : 0, c_cnt = half ? CB : CA;
             const int nF = n * SQ_F;
 
@@ -265,69 +279,15 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
             fetch(0, 0);
             fetch(1, 1);
 
-            // ---- stage QK (FP32 -> BF16, canonical K-major) and u = W_in^T qk ----
-            {
-                const float* Q = a.qk + res * a.qk_z + (long long)row0 * 128;
-                float4 lo[2][4], hi[2][4];                     // all 16 loads of the thread in flight at once
-#pragma unroll
-                for (int gq = 0; gq < 2; ++gq) {
-                    const int r = warp * 16 + gq * 8 + (lane & 7);
-                    const bool ok = r < rows_valid;
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        const int kc = s * 4 + (lane >> 3);
-                        const float4* src = reinterpret_cast<const float4*>(Q + (long long)r * 128 + kc * 8);
-                        lo[gq][s] = ok ? __ldg(src) : make_float4(0.f, 0.f, 0.f, 0.f);
-                        hi[gq][s] = ok ? __ldg(src + 1) : make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-#pragma unroll
-                for (int gq = 0; gq < 2; ++gq) {
-                    const int r = warp * 16 + gq * 8 + (lane & 7);
-                    float uacc[SQ_F];
-#pragma unroll
-                    for (int f = 0; f < SQ_F; ++f) uacc[f] = 0.f;
-#pragma unroll
-                    for (int s = 0; s < 4; ++s) {
-                        const int kc = s * 4 + (lane >> 3);
-                        const float4 l4 = lo[gq][s], h4 = hi[gq][s];
-                        uint4 pk;
-                        pk.x = pack2(l4.x, l4.y); pk.y = pack2(l4.z, l4.w);
-                        pk.z = pack2(h4.x, h4.y); pk.w = pack2(h4.z, h4.w);
-                        *reinterpret_cast<uint4*>(smem + OFF_Q + (r >> 3) * 2048 + kc * 128 + (r & 7) * 16) = pk;
-                        const float qv[8] = {l4.x, l4.y, l4.z, l4.w, h4.x, h4.y, h4.z, h4.w};
-                        const float4* w4p = reinterpret_cast<const float4*>(w_s + kc * 8 * SQ_F);
-                        float wv[8 * SQ_F];
-#pragma unroll
-                        for (int q = 0; q < 14; ++q) {
-                            const float4 t = w4p[q];
-                            wv[4 * q] = t.x; wv[4 * q + 1] = t.y; wv[4 * q + 2] = t.z; wv[4 * q + 3] = t.w;
-                        }
-#pragma unroll
-                        for (int e = 0; e < 8; ++e)
-#pragma unroll
-                            for (int f = 0; f < SQ_F; ++f) uacc[f] = fmaf(wv[e * SQ_F + f], qv[e], uacc[f]);
-                    }
-#pragma unroll
-                    for (int f = 0; f < SQ_F; ++f) {
-                        uacc[f] += __shfl_xor_sync(0xffffffffu, uacc[f], 8);
-                        uacc[f] += __shfl_xor_sync(0xffffffffu, uacc[f], 16);
-                    }
-                    if (lane < 8) {
-#pragma unroll
-                        for (int f = 0; f < SQ_F; ++f) u_s[r * SQ_F + f] = uacc[f];
-                    }
-                }
-            }
-            fence_async_smem();
-            compute_barrier();                                // u_s complete for every row
-            warp_arrive(&bars[B_QREADY], lane);
-
-            float u[SQ_F];
-#pragma unroll
-            for (int f = 0; f < SQ_F; ++f) u[f] = u_s[row * SQ_F + f];
             mbar_wait(&bars[B_S], it & 1);
             tc_fence_after();
+            float u[SQ_F];                                    // u = W_in^T qk of this row (MMA of the driver, columns 400..406)
+            {
+                float uu[8];
+                tmem_ld8(trow + U_COL, uu);
+#pragma unroll
+                for (int f = 0; f < SQ_F; ++f) u[f] = uu[f];
+            }
 
             // ---- one pass over the keys: scores, online softmax, P (BF16 pairs) -> TMEM ----
             float m = SQ_MINIT, sum = 0.f, xb[SQ_F];
@@ -410,7 +370,8 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
             tc_fence_before();
             warp_arrive(&bars[B_P], lane);
 
-            // ---- exchange the halves: common maximum, 1 / sum, xbar per row ----
+            // ---- exchange the halves: common maximum, 1 / sum, xbar per row (in the ring, once every warp has left it) ----
+            compute_barrier();
             red_max[half * 128 + row] = m;
             red_sum[half * 128 + row] = sum;
             {
@@ -465,7 +426,7 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
 #pragma unroll
                 for (int e = 0; e < 4; ++e)
 #pragma unroll
-                    for (int f = 0; f < SQ_F; ++f) w4[e][f] = w_s[(4 * lane + e) * SQ_F + f];
+                    for (int f = 0; f < SQ_F; ++f) w4[e][f] = __ldg(W + (4 * lane + e) * SQ_F + f);
                 float* C = a.cbar + res * a.cbar_z + (long long)row0 * 128;
                 __nv_bfloat16* Cb = a.cbar_bf16 ? a.cbar_bf16 + 2 * res * a.cbar_z + (long long)row0 * 128 : nullptr;   // (same byte stride as the FP32 view)
 #pragma unroll 4
@@ -496,19 +457,63 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
     if (warp == 8) tmem_dealloc(tmem, 512);
 }
 
+
+// ---- operand preparation -------------------------------------------------------------------------------------
+// QK rows [rows, 128] FP32 -> BF16 tiles of 128 rows in the canonical K-major layout ([16 row groups][16 k chunks][8][8]);
+// rows past the end of the last tile are zero.  (The query GEMM of the forward writes this layout itself.)
+__global__ void sqa_pack_qk_kernel(const float* __restrict__ qk, long long qk_z, __nv_bfloat16* __restrict__ tiles,
+                                   long long tz, int rows, int tiles_per_res) {
+    const int z = blockIdx.y;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;      // one 8-column chunk of one row
+    if (i >= (long long)tiles_per_res * 128 * 16) return;
+    const int row = (int)(i >> 4), kc = (int)(i & 15);
+    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+    if (row < rows) {
+        const float4* src = reinterpret_cast<const float4*>(qk + z * qk_z + (long long)row * 128 + kc * 8);
+        const float4 lo = src[0], hi = src[1];
+        pk.x = pack2(lo.x, lo.y); pk.y = pack2(lo.z, lo.w); pk.z = pack2(hi.x, hi.y); pk.w = pack2(hi.z, hi.w);
+    }
+    const int r = row & 127;
+    *reinterpret_cast<uint4*>(tiles + z * tz + (long long)(row >> 7) * 16384 + (r >> 3) * 1024 + kc * 64 + (r & 7) * 8) = pk;
+}
+// W_in [128, 7] FP32 -> B operand of u = QK W_in: [16 rows (feature, 7.. zero)][128 (channel)] BF16, canonical K-major
+__global__ void sqa_pack_w_in_kernel(const float* __restrict__ w_in, long long w_z, __nv_bfloat16* __restrict__ out,
+                                     long long out_z) {
+    const int z = blockIdx.x, t = threadIdx.x;                                  // 256 threads: (feature row n, k chunk)
+    const int n = t >> 4, kc = t & 15;
+    __nv_bfloat16 v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = __float2bfloat16_rn(n < SQ_F ? w_in[z * w_z + (kc * 8 + j) * SQ_F + n] : 0.f);
+    *reinterpret_cast<uint4*>(out + z * out_z + ((n >> 3) * 16 + kc) * 64 + (n & 7) * 8) = *reinterpret_cast<const uint4*>(v);
+}
+
 }  // namespace
+
+int sqa_pack_qk(const float* qk, long long qk_z, __nv_bfloat16* tiles, long long tz, int rows, int n_res, cudaStream_t st) {
+    const int tpr = (rows + 127) / 128;
+    const long long units = (long long)tpr * 128 * 16;
+    sqa_pack_qk_kernel<<<dim3((unsigned)((units + 255) / 256), n_res), 256, 0, st>>>(qk, qk_z, tiles, tz, rows, tpr);
+    CHROMO_CHECK_LAUNCH("sqa_pack_qk");
+    return CHROMO_OK;
+}
+int sqa_pack_w_in(const float* w_in, long long w_z, __nv_bfloat16* out, long long out_z, int n_res, cudaStream_t st) {
+    sqa_pack_w_in_kernel<<<n_res, 256, 0, st>>>(w_in, w_z, out, out_z);
+    CHROMO_CHECK_LAUNCH("sqa_pack_w_in");
+    return CHROMO_OK;
+}
 
 bool sqa_fused_supported(const SqaFusedArgs& a, int H, int F, int D) {
     if (H != 2 || F != SQ_F || D != 128 || a.n_res < 1 || a.regions < 1) return false;
     if (getenv("CHROMO_NO_SQA_FUSED")) return false;
-    if ((reinterpret_cast<uintptr_t>(a.qk) & 15) || (reinterpret_cast<uintptr_t>(a.cbar) & 15) || (a.qk_z & 3) || (a.cbar_z & 3) ||
-        (reinterpret_cast<uintptr_t>(a.cbar_bf16) & 15))
+    if (!a.qk_tiles || !a.w_in_pk || (reinterpret_cast<uintptr_t>(a.qk_tiles) & 15) || (a.qk_tz & 7) ||
+        (reinterpret_cast<uintptr_t>(a.w_in_pk) & 15) || (a.w_in_pk_z & 7))
         return false;
+    if ((reinterpret_cast<uintptr_t>(a.cbar) & 15) || (a.cbar_z & 3) || (reinterpret_cast<uintptr_t>(a.cbar_bf16) & 15)) return false;
     for (int r = 0; r < a.n_res; ++r) {
         if (a.n[r] < 4 || a.n[r] % 4 != 0 || a.ns[r] % 16 != 0 || a.ns[r] < a.n[r] || a.ns[r] > SQ_MAX_NS) return false;
         if (!a.pe_pk[r] || (reinterpret_cast<uintptr_t>(a.pe_pk[r]) & 15)) return false;
         if (reinterpret_cast<uintptr_t>(a.x[r]) & 15) return false;
-        if ((reinterpret_cast<uintptr_t>(a.w_in) & 15) || (a.w_in_z & 3)) return false;
+        if (!a.w_in) return false;
         if ((reinterpret_cast<uintptr_t>(a.mask[r]) & 3) || (a.mask_stride[r] & 3) || (a.mask_row_offset[r] & 3)) return false;
     }
     return true;

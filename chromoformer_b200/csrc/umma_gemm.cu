@@ -263,7 +263,27 @@ __global__ void __launch_bounds__(UTHREADS) umma_linear_kernel(const UmmaArgs a)
                     }
                 }
             }
-            if (g.c_bf16) {
+            if (g.c_sqa_tiles) {
+                // QK operand tiles of sqa_fused: row 2m + head of the 128-row tiles, 16-byte chunks of 8 channels
+                if (ok) {
+                    const int head = (n0 + c) >> 7, kc0 = ((n0 + c) & 127) >> 3;
+                    const long long R = 2LL * m + head;
+                    const int r = (int)(R & 127);
+                    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(g.C) + z1 * g.sC1 + z2 * g.sC2 + (R >> 7) * 16384 +
+                                         (r >> 3) * 1024 + (r & 7) * 8;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        if (j < ncols) {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                            uint4 pk;
+                            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                            *reinterpret_cast<uint4*>(out + (kc0 + (j >> 3)) * 64) = pk;
+                        }
+                    }
+                }
+            } else if (g.c_bf16) {
                 // BF16 output: the thread's 32 columns are 64 contiguous bytes
                 if (ok) {
                     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(g.C) + z1 * g.sC1 + z2 * g.sC2 +
@@ -334,6 +354,9 @@ bool umma_supported(const GemmArgs& g) {
     if ((reinterpret_cast<uintptr_t>(g.A) & 15) || (reinterpret_cast<uintptr_t>(g.C) & 15)) return false;
     if (g.epi == EPI_BIAS_RES_LN && (g.N != 128 || g.accumulate || g.c_bf16)) return false;
     if (g.c_bf16 && (g.accumulate || g.N % 8 != 0)) return false;
+    if (g.c_sqa_tiles && (g.N != 256 || g.accumulate || g.epi != EPI_PLAIN || g.c_div != 1 || g.c_mul != 1 || g.c_add != 0 ||
+                          g.zdiv != 1))
+        return false;
     return true;
 }
 

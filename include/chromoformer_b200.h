@@ -122,7 +122,8 @@ int chromo_regulation_layer(const chromo_config_t* cfg, const float* params, int
  * qk [regions*2, 128] (= W_k[h]^T q per head), x [regions, n, 7], mask [regions, n] bytes (non-zero = pad),
  * w_in [128, 7], pos_enc [n, 128], cbar [regions*2, 128]; n % 4 == 0, n <= 400.  BF16 tensor path only
  * (sqa_fused.cu): the kernel the BF16 forward runs per stage, exposed to be tested and timed alone.
- * workspace: at least 64 * max(32, round_up(n, 16)) floats (the packed BF16 position table).          */
+ * workspace: at least 64 * max(32, round_up(n, 16)) + 1024 + 8192 * ceil(regions / 64) floats (the position table,
+ * W_in and the qk rows as BF16 tensor-core operands).                                                */
 int chromo_single_query_attention(int32_t regions, int32_t n, const float* qk, const float* x, const uint8_t* mask,
                                   const float* w_in, const float* pos_enc, float scale, float* cbar,
                                   float* workspace, int64_t workspace_floats, void* stream);

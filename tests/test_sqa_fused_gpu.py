@@ -1,7 +1,8 @@
 """The fused single-query attention kernel (sqa_fused.cu) alone, through chromo_single_query_attention.
 
-Reference: float64 torch with the two operands the tensor pipe sees in BF16 (qk and the position table) rounded the
-same way; what remains is the BF16 rounding of the probabilities (2^-9 relative) and FP32 accumulation order."""
+Reference: float64 torch with the operands the tensor pipe sees in BF16 (qk, the position table and W_in in the score
+term) rounded the same way; what remains is the BF16 rounding of the probabilities (2^-9 relative) and FP32
+accumulation order."""
 import math
 
 import pytest
@@ -17,7 +18,7 @@ def _reference(qk, x, mask, w_in, pe, scale):
     """modules.py:16-30 for one query: keys = values = W_in x_j + PE_j."""
     regions, n, _ = x.shape
     qk_b, pe_b = qk.bfloat16().double(), pe.bfloat16().double()
-    u = qk.double() @ w_in.double()                                         # [rows, 7]   (FP32 path in the kernel)
+    u = qk_b @ w_in.bfloat16().double()                                     # [rows, 7]   (a tensor-core GEMM in the kernel)
     s = qk_b @ pe_b.t() + torch.einsum("rf,rjf->rj", u, x.double().repeat_interleave(2, 0))
     s = s * scale
     s = s.masked_fill(mask.bool().repeat_interleave(2, 0), -1e9)
@@ -30,7 +31,7 @@ def _run(qk, x, mask, w_in, pe, scale, tau=None, monkeypatch=None):
     lib = _lib.load()
     regions, n, _ = x.shape
     ns = 32 if n <= 32 else (n + 15) // 16 * 16
-    ws = torch.empty(64 * ns, device="cuda")
+    ws = torch.empty(64 * ns + 1024 + 8192 * ((regions + 63) // 64), device="cuda")
     out = torch.full((regions * 2, 128), float("nan"), device="cuda")
     dev = [t.cuda().contiguous() for t in (qk, x, mask.to(torch.uint8), w_in, pe)]
     if tau is not None:
