@@ -6,6 +6,8 @@
 #include <map>
 #include <mutex>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace chromo {
@@ -265,7 +267,11 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
         w.r_u = take((int64_t)T * D);
         w.r_f = take((int64_t)T * c->reg_d_ff);
         w.r_preY = take((int64_t)T * D);
-        w.r_out = take((int64_t)T * D);
+        {   // (the fused multi-layer kernel parks whole 128-row tiles of floor(128 / S) genes here between layers)
+            const int64_t G = 128 / S > 0 ? 128 / S : 1;
+            const int64_t tiles = (B + G - 1) / G;
+            w.r_out = take(std::max((int64_t)T * D, tiles * 128 * D));
+        }
         w.r_slot = cur - s0;
         cur = s0 + w.r_slot * w.rslots;
     }

@@ -328,7 +328,6 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         for (int li = 0; li < a.n_layers; ++li) {
         const uint32_t lp = li & 1;
         const long long po = z * a.p_z + li * a.p_l;          // this (resolution, layer)'s parameters
-        const float* Xl = li == 0 ? X : a.y_mid + z * a.y_mid_z + ((li - 1) & 1) * a.y_l;   // the layer's input rows
         float gam[4];                                         // gamma_f of the four heads this thread serves (TC path)
 #pragma unroll
         for (int t = 0; t < 4; ++t) gam[t] = a.gamma_f[po + 2 * t + ch];
@@ -553,18 +552,32 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         fence_async_smem();
         warp_arrive(&bars[B_ATTREADY], lane);
 
-        // residual rows of phase 2 (FP32, from global / L2): issued now so that their latency hides behind the
-        // out-projection MMA; u_keep then carries U and is the residual of phase 4
+        // residual rows of phase 2 (FP32): issued now so that their latency hides behind the out-projection MMA; u_keep
+        // then carries U and is the residual of phase 4.  First layer: the caller's row-major X.  Later layers: what THIS
+        // thread parked in the scratch slot at the end of the previous layer, in a lane-major order (float4 index
+        // ((ch*2 + ci)*8 + j/4)*128 + row inside the tile's 64 KB block) so that every warp access is 512 contiguous bytes.
         float u_keep[2][32];
+        if (li == 0) {
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
-            const int c = (2 * ci + ch) * 32;
+            for (int ci = 0; ci < 2; ++ci) {
+                const int c = (2 * ci + ch) * 32;
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (valid) r4 = __ldcg(reinterpret_cast<const float4*>(Xl + grow * 128 + c + j));   // (L2: written by this CTA)
-                u_keep[ci][j] = r4.x; u_keep[ci][j + 1] = r4.y; u_keep[ci][j + 2] = r4.z; u_keep[ci][j + 3] = r4.w;
+                for (int j = 0; j < 32; j += 4) {
+                    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) r4 = __ldg(reinterpret_cast<const float4*>(X + grow * 128 + c + j));
+                    u_keep[ci][j] = r4.x; u_keep[ci][j + 1] = r4.y; u_keep[ci][j + 2] = r4.z; u_keep[ci][j + 3] = r4.w;
+                }
             }
+        } else {
+            const float4* park = reinterpret_cast<const float4*>(a.y_mid + z * a.y_mid_z + ((li - 1) & 1) * a.y_l) +
+                                 (long long)tile * 4096 + row;
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci)
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 r4 = __ldcg(park + ((ch * 2 + ci) * 8 + (j >> 2)) * 128);
+                    u_keep[ci][j] = r4.x; u_keep[ci][j + 1] = r4.y; u_keep[ci][j + 2] = r4.z; u_keep[ci][j + 3] = r4.w;
+                }
         }
         // small FP32 vectors of the layer -> shared (the v tile is dead): bo, ln1w, ln1b, b2, ln2w, ln2b, b1[256]
         float* prm = reinterpret_cast<float*>(smem + OFF_V);
@@ -682,18 +695,16 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
             const float* lw = prm + 512;
             const float* lb = prm + 640;
-            const bool more = li + 1 < a.n_layers;            // Y is also the next layer's operand (BF16, in place of X)
-            float* Y = more ? a.y_mid + z * a.y_mid_z + (li & 1) * a.y_l : a.y + z * a.y_z;
-            float* stage = reinterpret_cast<float*>(smem + OFF_ATT) + warp * (32 * 33);   // FFN-2 MMAs are complete
+            const bool more = li + 1 < a.n_layers;
+            if (more) {
+                // Y is the next layer's operand (BF16, over X in shared memory) and residual (FP32, parked in the scratch
+                // slot by the thread that will read it back, lane-major)
+                float4* park = reinterpret_cast<float4*>(a.y_mid + z * a.y_mid_z + (li & 1) * a.y_l) + (long long)tile * 4096 + row;
 #pragma unroll
-            for (int ci = 0; ci < 2; ++ci) {
-                const int c = (2 * ci + ch) * 32;
+                for (int ci = 0; ci < 2; ++ci) {
+                    const int c = (2 * ci + ch) * 32;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    u_keep[ci][j] = (u_keep[ci][j] - mean) * rstd * lw[c + j] + lb[c + j];
-                    stage[lane * 33 + j] = u_keep[ci][j];
-                }
-                if (more) {
+                    for (int j = 0; j < 32; ++j) u_keep[ci][j] = (u_keep[ci][j] - mean) * rstd * lw[c + j] + lb[c + j];
 #pragma unroll
                     for (int j = 0; j < 32; j += 8) {
                         uint4 pk;
@@ -701,23 +712,36 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                         pk.z = pack2(u_keep[ci][j + 4], u_keep[ci][j + 5]); pk.w = pack2(u_keep[ci][j + 6], u_keep[ci][j + 7]);
                         *reinterpret_cast<uint4*>(smem + OFF_XB + op_chunk(row, (c + j) >> 3, 128)) = pk;
                     }
-                }
-                __syncwarp();
-                const int cq = (lane & 7) * 4;
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int r = it * 4 + (lane >> 3);
-                    const float* sp = stage + r * 33 + cq;
-                    const int trw = lq * 32 + r;
-                    if (trw < rows_valid)
-                        *reinterpret_cast<float4*>(Y + (row0 + trw) * 128 + c + cq) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                    for (int j = 0; j < 32; j += 4)
+                        __stcg(park + ((ch * 2 + ci) * 8 + (j >> 2)) * 128,
+                               make_float4(u_keep[ci][j], u_keep[ci][j + 1], u_keep[ci][j + 2], u_keep[ci][j + 3]));
                 }
-                __syncwarp();
-            }
-            if (more) {
                 fence_async_smem();
-                compute_barrier();        // Y rows are visible to the CTA (residual of the next layer); prm / red are free
+                compute_barrier();        // prm / red are free for the next layer's k, v
                 warp_arrive(&bars[B_XREADY], lane);
+            } else {
+                // last layer: Y row-major to the caller, coalesced through a shared-memory transpose
+                float* Y = a.y + z * a.y_z;
+                float* stage = reinterpret_cast<float*>(smem + OFF_ATT) + warp * (32 * 33);   // FFN-2 MMAs are complete
+#pragma unroll
+                for (int ci = 0; ci < 2; ++ci) {
+                    const int c = (2 * ci + ch) * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        stage[lane * 33 + j] = (u_keep[ci][j] - mean) * rstd * lw[c + j] + lb[c + j];
+                    __syncwarp();
+                    const int cq = (lane & 7) * 4;
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        const int r = it * 4 + (lane >> 3);
+                        const float* sp = stage + r * 33 + cq;
+                        const int trw = lq * 32 + r;
+                        if (trw < rows_valid)
+                            *reinterpret_cast<float4*>(Y + (row0 + trw) * 128 + c + cq) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                    }
+                    __syncwarp();
+                }
             }
         }
         }   // layers

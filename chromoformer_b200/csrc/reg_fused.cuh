@@ -10,7 +10,8 @@ struct RegFusedArgs {
     int B, S, G, n_tiles;                   // genes, tokens per gene, genes per tile (G*S <= 128), tiles
     const float* x; long long x_z;          // layer input  [B*S, 128] FP32 (z = resolution stride)
     float* y; long long y_z;                // output of the LAST layer [B*S, 128] FP32
-    float* y_mid; long long y_mid_z, y_l;   // multi-layer launch: layer li < last writes y_mid + (li & 1) * y_l
+    float* y_mid; long long y_mid_z, y_l;   // multi-layer launch: scratch slots y_mid + (li & 1) * y_l, n_tiles * 16384 floats
+                                            //   each, where a CTA parks the FP32 residual rows of its tile between layers
     int n_layers; long long p_l;            // layers run back to back by one launch, parameter stride between layers
     const __nv_bfloat16* wstream; long long w_z;   // 14 packed weight chunks per layer, layers contiguous
     const float* gamma_f; const float* bo; const float* ln1w; const float* ln1b;
