@@ -62,6 +62,11 @@ __device__ __forceinline__ void group_barrier(int ch) {
 // o * sigmoid(g) with sigmoid(g) = 0.5 + 0.5 tanh(g / 2): one MUFU (tanh.approx, abs. error 2^-11, well inside the
 // BF16 rounding of the result) instead of ex2 + rcp.  (Rows past the tile's last gene carry finite garbage that only
 // reaches their own, never stored, output rows.)
+__device__ __forceinline__ float gate_factor(float g) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * g));
+    return fmaf(0.5f, t, 0.5f);
+}
 __device__ __forceinline__ float gated(float o, float g) {
     float t;
     asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * g));
@@ -230,31 +235,15 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             // attention on the tensor pipe: TMEM [0,128) / [128,256) = S, then P (first 64..77 columns) and O (last 32)
             // of the two heads in flight; [256,512) = projection pair (q0 q1 k0 k1 v0 v1 g0 g1, 32 columns each).
             // S = Q K^T and O = P V are issued by the compute groups themselves.  The projections of the NEXT pair
-            // overlap the attention of this one: [q|k] and v as soon as the S instructions are done with q / k and v
-            // sits in shared memory (B_QKFREE), the gates once this pair's gates have been read (B_ACCQFREE).
-            auto consume_half = [&](int c, int hf, uint32_t col, bool release) {
-                const int st = c % RF_NSTAGE;
-                mbar_wait(&bars[B_FULL0 + st], (c / RF_NSTAGE) & 1);
-                tc_fence_after();
-                const uint32_t b_addr = smem_u32(smem + OFF_STAGE + st * RF_CHUNK_BYTES) + hf * 16384;
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    umma_bf16(tmem + col, umma_smem_desc(s_xb + k * 256, 128, 2048),
-                              umma_smem_desc(b_addr + k * 256, 128, 2048), umma_idesc_bf16(128, 64), k > 0 ? 1u : 0u);
-                if (release) {
-                    umma_commit(&bars[B_FREE0 + st]);
-                    if (c + 2 < n_chunks && c >= 1) issue_load(c + 2);
-                }
-            };
+            // overlap the attention of this one: they are issued as soon as the S instructions are done with q / k, v sits in
+            // shared memory and the gates in registers (B_QKFREE).
             consume(cb, s_xb, 2048, 256, false);
             consume(cb + 1, s_xb, 2048, 384, false);
             umma_commit(&bars[B_ACCQ0]);
             for (int t = 0; t < 3; ++t) {
                 mbar_wait(&bars[B_QKFREE], t & 1);
                 consume(cb + 2 * t + 2, s_xb, 2048, 256, false);        // next [q | k]
-                consume_half(cb + 2 * t + 3, 0, 384, false);            // next v
-                mbar_wait(&bars[B_ACCQFREE0], t & 1);
-                consume_half(cb + 2 * t + 3, 1, 448, true);             // next gates
+                consume(cb + 2 * t + 3, s_xb, 2048, 384, false);        // next [v | gate]
                 umma_commit(&bars[B_ACCQ0]);
             }
             }
@@ -423,6 +412,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         for (int t = 0; t < 4; ++t) {
             // one thread per token row; warps 0-3 take head 2t, warps 4-7 head 2t+1
             const uint32_t pb = trow + 256;
+            uint32_t gsig[16];
             uint8_t* sk = smem + OFF_K + ch * 8192;
             uint8_t* sv = smem + OFF_V + ch * 8192;
             mbar_wait(&bars[B_ACCQ0], t & 1);
@@ -450,6 +440,11 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                     pk.z = pack2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack2(v[8 * c + 6], v[8 * c + 7]);
                     *reinterpret_cast<uint4*>(sv + c * 2048 + (row >> 3) * 128 + (row & 7) * 16) = pk;
                 }
+                // gate -> sigmoid(g) as BF16 pairs in registers: with q, k, v consumed too, every projection column of this
+                // pair is dead once S = Q K^T has run, so the driver can issue the whole next pair behind it
+                tmem_ld32(pb + 192 + 32 * ch, v);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) gsig[c] = pack2(gate_factor(v[2 * c]), gate_factor(v[2 * c + 1]));
                 tmem_st_wait();
                 tc_fence_before();
                 fence_async_smem();
@@ -535,14 +530,16 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             tc_fence_after();
             float o[32];
             tmem_ld32(trow + 128 * ch + 96, o);                   // O = P V (last 32 columns of the S tile)
-            tmem_ld32(pb + 192 + 32 * ch, v);                     // gate
             tc_fence_before();
-            warp_arrive(&bars[B_ACCQFREE0], lane);                // the projection pair may be overwritten
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 float r[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) r[e] = gated(o[8 * c + e], v[8 * c + e]);
+                for (int e = 0; e < 8; e += 2) {
+                    const uint32_t gp = gsig[4 * c + (e >> 1)];
+                    r[e] = o[8 * c + e] * __uint_as_float(gp << 16);
+                    r[e + 1] = o[8 * c + e + 1] * __uint_as_float(gp & 0xffff0000u);
+                }
                 uint4 pk;
                 pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
                 *reinterpret_cast<uint4*>(smem + OFF_ATT + op_chunk(row, 8 * t + 4 * ch + c, 256)) = pk;

@@ -171,9 +171,20 @@ __global__ void __launch_bounds__(RT_THREADS, 1) row_tail_fused_kernel(const Row
         // ---- phase 1: out-projection epilogue: + bias + residual, LayerNorm -> U
         float u_keep[2][32];
         {
+            // residual rows first: their (row-strided) loads overlap the out-projection MMA
+            const float* res = a.res + z * a.res_z + (valid ? (long long)(m / a.res_div) * 128 : 0);
+#pragma unroll
+            for (int ci = 0; ci < 2; ++ci) {
+                const int c = (2 * ci + ch) * 32;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (valid) r4 = __ldg(reinterpret_cast<const float4*>(res + c + j));
+                    u_keep[ci][j] = r4.x; u_keep[ci][j + 1] = r4.y; u_keep[ci][j + 2] = r4.z; u_keep[ci][j + 3] = r4.w;
+                }
+            }
             mbar_wait(&bars[T_ACCO], 0);
             tc_fence_after();
-            const float* res = a.res + z * a.res_z + (valid ? (long long)(m / a.res_div) * 128 : 0);
             float sum = 0.f, sq = 0.f;
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci) {
@@ -181,11 +192,9 @@ __global__ void __launch_bounds__(RT_THREADS, 1) row_tail_fused_kernel(const Row
                 tmem_ld32(trow + c, v);
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    float4 r4 = make_float4(0, 0, 0, 0);
-                    if (valid) r4 = *reinterpret_cast<const float4*>(res + c + j);
                     const float4 b4 = *reinterpret_cast<const float4*>(prm + c + j);
-                    const float t0 = v[j] + b4.x + r4.x, t1 = v[j + 1] + b4.y + r4.y;
-                    const float t2 = v[j + 2] + b4.z + r4.z, t3 = v[j + 3] + b4.w + r4.w;
+                    const float t0 = v[j] + b4.x + u_keep[ci][j], t1 = v[j + 1] + b4.y + u_keep[ci][j + 1];
+                    const float t2 = v[j + 2] + b4.z + u_keep[ci][j + 2], t3 = v[j + 3] + b4.w + u_keep[ci][j + 3];
                     u_keep[ci][j] = t0; u_keep[ci][j + 1] = t1; u_keep[ci][j + 2] = t2; u_keep[ci][j + 3] = t3;
                     sum += (t0 + t1) + (t2 + t3);
                     sq += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
