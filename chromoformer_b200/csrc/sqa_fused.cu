@@ -19,7 +19,7 @@
 //   compute warps  cbar = (O_A 2^(mA-m) + O_B 2^(mB-m)) / sum + W_in xbar, transposed through shared memory,
 //                  512-byte row stores
 // Tensor-memory map (512 columns): scores [0, ns); P of the first key half in place [0, 4*CA), P of the second half
-// [416, 416 + 4*CB); u [400, 407); O_A [256, 384) and O_B [128, 256) once the scores are dead.
+// [416, 416 + 4*CB); u [400, 407); O_B [256, 384) and O_A [128, 256) once the scores under them are dead.
 #include <stdlib.h>
 
 #include "sqa_fused.cuh"
@@ -47,7 +47,9 @@ constexpr uint32_t SQ_XCH = 4 * 32 * 132 * 4;                // exchange area in
 static_assert(SQ_SMEM <= 227 * 1024, "shared memory budget");
 constexpr uint32_t QX_MAX = 0, QX_SUM = 1024, QX_XB = 2048, QX_XBAR = 2048 + 8192;
 static_assert(SQ_XCH + QX_XBAR + 4096 <= SQ_NSTAGE * SQ_STAGE, "store staging + exchange area fit in the ring");
-constexpr int P_B_COL = 416, OA_COL = 256, OB_COL = 128, U_COL = 400;
+// O_B is issued while the first key half may still be reading its scores, so it must land on columns of the SECOND
+// half's (finished) scores: [256, 384) holds keys 256..383 at ns = 400.  O_A follows once everybody is through.
+constexpr int P_B_COL = 416, OA_COL = 128, OB_COL = 256, U_COL = 400;
 constexpr float SQ_TAU = 16.f;                  // the reference maximum moves when a chunk exceeds it by 2^16
 constexpr float SQ_MINIT = -3.0e38f;
 
@@ -57,7 +59,7 @@ __device__ __forceinline__ uint32_t x_row_off(int r) {
     return (uint32_t)r * (SQ_XROW * 4) + 16u * (uint32_t)(((r >> 2) & 1) + ((r >> 3) & 1)) + 32u * (uint32_t)(r >> 4);
 }
 
-enum { B_PE = 0, B_QFULL, B_S, B_P, B_O, B_EPI, B_COUNT };
+enum { B_PE = 0, B_QFULL, B_S, B_PA, B_PB, B_O, B_EPI, B_COUNT };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -88,6 +90,19 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float* v) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+// the same load in two halves: issue early, complete (with the registers tied to the wait) just before the first use
+__device__ __forceinline__ void tmem_ld8_issue(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld8_wait(uint32_t* r) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7])
+                 :
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_ld4(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
@@ -140,7 +155,8 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
         mbar_init(&bars[B_PE], 1);
         mbar_init(&bars[B_QFULL], 1);
         mbar_init(&bars[B_S], 1);
-        mbar_init(&bars[B_P], 8);
+        mbar_init(&bars[B_PA], 4);
+        mbar_init(&bars[B_PB], 4);
         mbar_init(&bars[B_O], 1);
         mbar_init(&bars[B_EPI], 8);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -204,15 +220,20 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
                                      32768u, &bars[B_QFULL]);
                     }
                 }
-                mbar_wait(&bars[B_P], it & 1);
+                // O = P PE per key half, as soon as that half's warps are through (the second half has fewer chunks and
+                // finishes first): key blocks of the table are 2048 B apart (LBO), channel blocks 128 B (SBO)
+                if (CB > 0) {
+                    mbar_wait(&bars[B_PB], it & 1);
+                    tc_fence_after();
+                    for (int k = 0; k < CB / 2; ++k)
+                        umma_bf16_ts(tmem + OB_COL, tmem + P_B_COL + 8 * k,
+                                     umma_smem_desc(s_pe + (CA / 2 + k) * 4096, 2048, 128), idesc_o, k > 0 ? 1u : 0u);
+                }
+                mbar_wait(&bars[B_PA], it & 1);
                 tc_fence_after();
-                // O = P PE: key blocks of the table are 2048 B apart (LBO), channel blocks 128 B (SBO)
                 for (int k = 0; k < CA / 2; ++k)
                     umma_bf16_ts(tmem + OA_COL, tmem + 8 * k, umma_smem_desc(s_pe + k * 4096, 2048, 128), idesc_o,
                                  k > 0 ? 1u : 0u);
-                for (int k = 0; k < CB / 2; ++k)
-                    umma_bf16_ts(tmem + OB_COL, tmem + P_B_COL + 8 * k,
-                                 umma_smem_desc(s_pe + (CA / 2 + k) * 4096, 2048, 128), idesc_o, k > 0 ? 1u : 0u);
                 umma_commit(&bars[B_O]);
             }
         }
@@ -297,23 +318,27 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
             const uint32_t xro = x_row_off(rit);
             int rs = 0, fs = 2;                               // ring stage being read / filled
             for (int idx = 0; idx < c_cnt; ++idx) {
+                const int cg = c_begin + idx;
+                uint32_t sraw[8];
+                tmem_ld8_issue(trow + 8 * cg, sraw);           // the scores of the chunk travel while the ring is awaited
                 cp_async_wait1();
                 named_barrier(2 + half, 128);
                 fetch(idx + 2, fs);
-                const int cg = c_begin + idx;
                 const uint8_t* sb = smem + OFF_X + rs * SQ_STAGE;
                 rs = rs == SQ_NSTAGE - 1 ? 0 : rs + 1;
                 fs = fs == SQ_NSTAGE - 1 ? 0 : fs + 1;
                 const float4* xs = reinterpret_cast<const float4*>(sb + half * SQ_HALF_X + xro);
                 const uint2 mk = *reinterpret_cast<const uint2*>(sb + SQ_STAGE_X + half * 512 + rit * 8);
-                float s[8];
-                tmem_ld8(trow + 8 * cg, s);
                 float xv[SQ_XROW];
 #pragma unroll
                 for (int q = 0; q < 14; ++q) {
                     const float4 t = xs[q];
                     xv[4 * q] = t.x; xv[4 * q + 1] = t.y; xv[4 * q + 2] = t.z; xv[4 * q + 3] = t.w;
                 }
+                float s[8];
+                tmem_ld8_wait(sraw);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) s[i] = __uint_as_float(sraw[i]);
                 float cmx = -INFINITY;
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -368,7 +393,7 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
             cp_async_wait0();
             tmem_st_wait();
             tc_fence_before();
-            warp_arrive(&bars[B_P], lane);
+            warp_arrive(&bars[half ? B_PB : B_PA], lane);
 
             // ---- exchange the halves: common maximum, 1 / sum, xbar per row (in the ring, once every warp has left it) ----
             compute_barrier();
