@@ -29,7 +29,7 @@ KWS = ({"n_layers": 1, "n_heads": 2, "d_model": 128, "d_ff": 128},
        {"n_layers": 6, "n_heads": 8, "d_model": 256, "d_ff": 256})
 BINS = (2000, 500, 100)
 # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel (ncu --set full, profiles/)
-REG_TRAFFIC = {"bytes": 136.6e6, "source": "ncu --set full, profiles/r01_summary_final.md (dram read 68.2 MB + write 68.4 MB)"}
+REG_TRAFFIC = {"bytes": 137.2e6, "source": "ncu --set full, profiles/r01_summary_final.md (dram read 68.2 MB + write 69.1 MB)"}
 REF_FLOPS_PER_GENE = 3862328832          # as-written forward, SURVEY §8d tier A
 
 

@@ -18,8 +18,15 @@ from .synthetic import FORWARD_KEYS
 
 
 class TrainStep:
+    """``use_graph``: after two eager steps with a given batch geometry the forward + loss + backward chain of that
+    geometry (about 330 small launches at batch 64) is captured in a CUDA graph and replayed; every step then costs one
+    graph launch, the copies of the new batch into the graph's input buffers, the (eager) all-reduce and one AdamW
+    launch.  Other geometries (a short last batch) keep running eagerly."""
+
+    GRAPH_AFTER = 2
+
     def __init__(self, model, lr=3e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, regression=False,
-                 process_group=None, distributed=None):
+                 process_group=None, distributed=None, use_graph=True):
         self.model = model
         self.lr, self.betas, self.eps, self.wd = lr, betas, eps, weight_decay
         self.regression = regression
@@ -37,39 +44,109 @@ class TrainStep:
         self.step_count = 0
         self.flags = _lib.F_TRAINING | model._precision_flag()
         self._ws = None
+        self.use_graph = use_graph
+        self._seen = {}          # geometry -> eager steps so far
+        self._graphs = {}        # geometry -> captured chain
+        self.graph_replays = 0
+
+    # ---- forward + loss + backward into self.grad (everything a CUDA graph may hold) -------------------------
+    def _chain(self, io, target, logits, dlogits):
+        lib = _lib.load()
+        model = self.model
+        flat = model.flat_params
+        stream = torch.cuda.current_stream(flat.device).cuda_stream
+        ws = self._ws
+        cfg = ctypes.byref(io.cfg)
+        n_out = int(io.cfg.n_out)
+        _lib.check(lib.chromo_forward(cfg, flat.data_ptr(), ctypes.byref(io.struct), logits.data_ptr(),
+                                      ws.data_ptr(), ws.numel(), self.flags, stream), "chromo_forward")
+        if self.regression:
+            _lib.check(lib.chromo_mse_loss(logits.data_ptr(), target.data_ptr(), io.batch * n_out, 1.0,
+                                           self.loss.data_ptr(), dlogits.data_ptr(), stream), "chromo_mse_loss")
+        else:
+            _lib.check(lib.chromo_ce_loss(logits.data_ptr(), target.data_ptr(), io.batch, n_out, 1.0,
+                                          self.loss.data_ptr(), dlogits.data_ptr(), stream), "chromo_ce_loss")
+        self.grad[:model.n_active].zero_()
+        _lib.check(lib.chromo_backward(cfg, flat.data_ptr(), ctypes.byref(io.struct), dlogits.data_ptr(),
+                                       self.grad.data_ptr(), ws.data_ptr(), ws.numel(), self.flags, stream),
+                   "chromo_backward")
+
+    def _io(self, batch):
+        model = self.model
+        return _BatchIO(model, *[[batch[k][b] for b in model.binsizes] if isinstance(batch[k], dict) else batch[k]
+                                 for k in FORWARD_KEYS])
+
+    def _target(self, target):
+        return target.to(torch.float32 if self.regression else torch.int64).contiguous()
+
+    @staticmethod
+    def _geometry(batch, target):
+        key = [tuple(target.shape)]
+        for k in FORWARD_KEYS:
+            v = batch[k]
+            key += [(b, tuple(t.shape), t.dtype) for b, t in v.items()] if isinstance(v, dict) else [(tuple(v.shape), v.dtype)]
+        return tuple(key)
+
+    def _capture(self, key, batch, target):
+        """Static copies of the batch, one eager run on them, then the same chain under graph capture."""
+        dev = self.model.flat_params.device
+        static = {k: ({b: t.detach().clone().contiguous() for b, t in batch[k].items()} if isinstance(batch[k], dict)
+                      else batch[k].detach().clone().contiguous()) for k in FORWARD_KEYS}
+        tgt = self._target(target).clone()
+        io = self._io(static)
+        logits = torch.empty(io.batch, int(io.cfg.n_out), dtype=torch.float32, device=dev)
+        dlogits = torch.empty_like(logits)
+        graph = torch.cuda.CUDAGraph()
+        try:
+            torch.cuda.synchronize(dev)
+            with torch.cuda.graph(graph):
+                self._chain(io, tgt, logits, dlogits)
+        except Exception:                      # a driver / toolkit that cannot capture this chain: stay eager
+            self.use_graph = False
+            torch.cuda.synchronize(dev)
+            return None
+        ent = {"graph": graph, "static": static, "target": tgt, "io": io, "logits": logits, "dlogits": dlogits}
+        self._graphs[key] = ent
+        return ent
 
     def __call__(self, batch, target):
         """batch: dict with the six forward arguments on the model's device; target: labels.
         Returns the (device) loss tensor of this rank's micro-batch; no host sync."""
         lib = _lib.load()
         model = self.model
-        io = _BatchIO(model, *[[batch[k][b] for b in model.binsizes] if isinstance(batch[k], dict) else batch[k]
-                               for k in FORWARD_KEYS])
         flat = model.flat_params
         dev = flat.device
-        stream = torch.cuda.current_stream(dev).cuda_stream
-        need = _lib.check(lib.chromo_workspace_floats(ctypes.byref(io.cfg), io.batch, self.flags), "workspace")
-        if self._ws is None or self._ws.numel() < need:
-            self._ws = torch.empty(need, dtype=torch.float32, device=dev)
-        ws = self._ws
-        n_out = int(io.cfg.n_out)
-        logits = torch.empty(io.batch, n_out, dtype=torch.float32, device=dev)
-        dlogits = torch.empty_like(logits)
-        cfg = ctypes.byref(io.cfg)
-        _lib.check(lib.chromo_forward(cfg, flat.data_ptr(), ctypes.byref(io.struct), logits.data_ptr(),
-                                      ws.data_ptr(), ws.numel(), self.flags, stream), "chromo_forward")
-        if self.regression:
-            t = target.to(torch.float32).contiguous()
-            _lib.check(lib.chromo_mse_loss(logits.data_ptr(), t.data_ptr(), io.batch * n_out, 1.0,
-                                           self.loss.data_ptr(), dlogits.data_ptr(), stream), "chromo_mse_loss")
+        key = self._geometry(batch, target) if self.use_graph else None
+        ent = self._graphs.get(key) if self.use_graph else None
+        if ent is None:
+            io = self._io(batch)
+            need = _lib.check(lib.chromo_workspace_floats(ctypes.byref(io.cfg), io.batch, self.flags), "workspace")
+            if self._ws is None or self._ws.numel() < need:
+                if self._graphs:               # captured chains point into the old workspace
+                    self._graphs.clear()
+                    self._seen.clear()
+                self._ws = torch.empty(need, dtype=torch.float32, device=dev)
+            seen = self._seen.get(key, 0) if self.use_graph else 0
+            if self.use_graph and seen >= self.GRAPH_AFTER:
+                ent = self._capture(key, batch, target)
+        if ent is not None:
+            for k in FORWARD_KEYS:
+                if isinstance(batch[k], dict):
+                    for b, t in batch[k].items():
+                        ent["static"][k][b].copy_(t, non_blocking=True)
+                else:
+                    ent["static"][k].copy_(batch[k], non_blocking=True)
+            ent["target"].copy_(target, non_blocking=True)
+            ent["graph"].replay()
+            self.graph_replays += 1
+            logits = ent["logits"]
         else:
-            t = target.to(torch.int64).contiguous()
-            _lib.check(lib.chromo_ce_loss(logits.data_ptr(), t.data_ptr(), io.batch, n_out, 1.0,
-                                          self.loss.data_ptr(), dlogits.data_ptr(), stream), "chromo_ce_loss")
-        self.grad[:model.n_active].zero_()
-        _lib.check(lib.chromo_backward(cfg, flat.data_ptr(), ctypes.byref(io.struct), dlogits.data_ptr(),
-                                       self.grad.data_ptr(), ws.data_ptr(), ws.numel(), self.flags, stream),
-                   "chromo_backward")
+            if self.use_graph:
+                self._seen[key] = self._seen.get(key, 0) + 1
+            logits = torch.empty(io.batch, int(io.cfg.n_out), dtype=torch.float32, device=dev)
+            dlogits = torch.empty_like(logits)
+            self._chain(io, self._target(target), logits, dlogits)
+        stream = torch.cuda.current_stream(dev).cuda_stream
         scale = allreduce_gradients(self.grad, model.n_active, self.group) if self.world > 1 else 1.0
         self.step_count += 1
         _lib.check(lib.chromo_adamw(flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),

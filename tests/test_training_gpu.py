@@ -152,3 +152,38 @@ def test_stock_torch_adamw_and_steplr_run_unchanged():
     fresh = _mk(ChromoformerClassifier, seed=42)
     tail = slice(fresh.n_active, None)
     assert torch.equal(finals[1][tail].cpu(), fresh.flat_params[tail])
+
+
+@pytest.mark.parametrize("regression", [True, False])
+def test_fused_train_step_graph_replay_matches_eager(regression):
+    """trainer.TrainStep: the CUDA-graph replay of forward + loss + backward (from the third step of a batch geometry
+    on) walks the same parameters as the eager chain, also when batches of another geometry come in between."""
+    from chromoformer_b200.trainer import TrainStep
+    cls = ChromoformerRegressor if regression else ChromoformerClassifier
+    batches = [synthetic.make_batch(24, ragged=True, seed=60 + i) for i in range(6)]
+    odd = synthetic.make_batch(7, ragged=True, seed=99)                      # a short last batch: stays eager
+
+    def to_dev(b):
+        return {k: ({bb: t.cuda() for bb, t in v.items()} if isinstance(v, dict) else v.cuda()) for k, v in b.items()}
+
+    def run(use_graph):
+        model = _mk(cls, seed=11).cuda().train()
+        step = TrainStep(model, lr=1e-3, regression=regression, use_graph=use_graph)
+        losses = []
+        for i, b in enumerate(batches):
+            d = to_dev(b)
+            tgt = d["labels_reg"].view(-1, 1) if regression else d["labels_clf"]
+            losses.append(step(d, tgt).item())
+            if i == 3:
+                d7 = to_dev(odd)
+                losses.append(step(d7, d7["labels_reg"].view(-1, 1) if regression else d7["labels_clf"]).item())
+        return model.flat_params.detach().cpu().clone(), losses, step
+
+    p_e, l_e, _ = run(False)
+    p_g, l_g, step = run(True)
+    assert step.graph_replays == 4 and step.use_graph                       # steps 3..6 of the 24-gene geometry
+    assert np.allclose(l_e, l_g, rtol=1e-5, atol=1e-6), (l_e, l_g)
+    # Parameters: the backward sums with atomics, so two runs differ in the last bits of the gradients, and AdamW turns
+    # a noise-level gradient into a +-lr step whatever its size: compare in the bulk, not in the maximum.
+    diff = (p_e - p_g).abs()
+    assert diff.mean().item() < 1e-6 and torch.quantile(diff[:: 7], 0.999).item() < 1e-4, (diff.mean(), diff.max())
