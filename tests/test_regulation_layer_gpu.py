@@ -57,3 +57,35 @@ def test_regulation_layer_vs_oracle(B, S, layer):
     # BF16 operands on unit-variance activations: a few 1e-2 absolute after two LayerNorms
     assert (got16 - want).abs().max().item() < 6e-2
     assert (got16 - want).abs().mean().item() < 5e-3
+
+
+@pytest.mark.parametrize("B,S", [(33, 9), (150, 9), (20, 17)])
+def test_all_layers_in_one_launch(B, S):
+    """layer = -1: the six layers in ONE launch of the fused kernel (operand tile resident in shared memory, residual
+    rows parked in scratch between layers) against the FP32 kernels layer by layer and against six single-layer
+    launches of the same fused kernel."""
+    model = ChromoformerClassifier(7, 128, 128, dict(KWS[0]), dict(KWS[1]), dict(KWS[2]), seed=78).cuda()
+    g = torch.Generator().manual_seed(B + S)
+    x = torch.randn(3, B * S, 128, generator=g).cuda()
+    freq = torch.zeros(B, S, S); freq[:, 0, 1:] = 1.5 + 1.5 * torch.rand(B, S - 1, generator=g)
+    k = torch.randint(0, S, (B,), generator=g)
+    idx = torch.arange(S)
+    inside = (idx.view(1, S, 1) <= k.view(B, 1, 1)) & (idx.view(1, 1, S) <= k.view(B, 1, 1))
+    md = [(~inside).clone().cuda().contiguous() for _ in range(3)]
+    fd = freq.cuda()
+    want, step = x, x
+    for layer in range(6):
+        want = _layer(model, layer, want, md, fd, 0)
+        step = _layer(model, layer, step, md, fd, _lib.F_BF16)
+    got = _layer(model, -1, x, md, fd, _lib.F_BF16)
+    assert torch.isfinite(got).all()
+    assert (got - step).abs().max().item() < 1e-5          # same arithmetic, layer by layer or in one launch
+    assert (got - want).abs().max().item() < 1.5e-1 and (got - want).abs().mean().item() < 1e-2
+    # FP32 kernels have no all-layer form
+    lib = _lib.load()
+    cfg = _lib.Config.from_buffer_copy(model._cfg); cfg.i_max = S - 1
+    ptrs = (ctypes.c_void_p * 3)(*[m.data_ptr() for m in md])
+    ws = torch.empty(1 << 20, device="cuda")
+    rc = lib.chromo_regulation_layer(ctypes.byref(cfg), model.flat_params.data_ptr(), -1, x.data_ptr(), x.data_ptr(),
+                                     x.shape[1] * 128, ptrs, fd.data_ptr(), B, ws.data_ptr(), 1 << 40, 0, None)
+    assert rc != 0
