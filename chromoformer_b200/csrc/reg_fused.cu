@@ -409,71 +409,77 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             }
         }
         } else {
-        for (int t = 0; t < 4; ++t) {
-            // one thread per token row; warps 0-3 take head 2t, warps 4-7 head 2t+1
-            const uint32_t pb = trow + 256;
-            uint32_t gsig[16];
-            uint8_t* sk = smem + OFF_K + ch * 8192;
-            uint8_t* sv = smem + OFF_V + ch * 8192;
+        // one thread per token row; warps 0-3 take head 2t, warps 4-7 head 2t+1.  The steps of consecutive head pairs
+        // are interleaved so that the two MMA round trips of a pair hide behind CUDA-core work of the next one:
+        //   ... softmax(t), issue O(t) | q, k of pair t+1 | wait O(t), gate, att | issue S(t+1) | v, gates of t+1 | ...
+        const uint32_t pb = trow + 256;
+        uint32_t gsig[16];
+        uint8_t* sk = smem + OFF_K + ch * 8192;
+        uint8_t* sv = smem + OFF_V + ch * 8192;
+        auto stage_qk = [&](int t) {        // Q -> BF16 back into TMEM in place (A operand of S = Q K^T); K -> shared, K-major
             mbar_wait(&bars[B_ACCQ0], t & 1);
             tc_fence_after();
-            {   // Q -> BF16, back into TMEM in place (A operand of S = Q K^T)
-                uint32_t qp[16];
-                tmem_ld32(pb + 32 * ch, v);
+            uint32_t qp[16];
+            tmem_ld32(pb + 32 * ch, v);
 #pragma unroll
-                for (int c = 0; c < 16; ++c) qp[c] = pack2(v[2 * c], v[2 * c + 1]);
-                tmem_st16(pb + 32 * ch, qp);
-                // K -> shared, K-major [128 keys x 32]; V -> shared, MN-major [32 dims x 128 keys]
-                tmem_ld32(pb + 64 + 32 * ch, v);
+            for (int c = 0; c < 16; ++c) qp[c] = pack2(v[2 * c], v[2 * c + 1]);
+            tmem_st16(pb + 32 * ch, qp);
+            tmem_ld32(pb + 64 + 32 * ch, v);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint4 pk;
-                    pk.x = pack2(v[8 * c], v[8 * c + 1]); pk.y = pack2(v[8 * c + 2], v[8 * c + 3]);
-                    pk.z = pack2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack2(v[8 * c + 6], v[8 * c + 7]);
-                    *reinterpret_cast<uint4*>(sk + op_chunk(row, c, 32)) = pk;
-                }
-                tmem_ld32(pb + 128 + 32 * ch, v);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint4 pk;
-                    pk.x = pack2(v[8 * c], v[8 * c + 1]); pk.y = pack2(v[8 * c + 2], v[8 * c + 3]);
-                    pk.z = pack2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack2(v[8 * c + 6], v[8 * c + 7]);
-                    *reinterpret_cast<uint4*>(sv + c * 2048 + (row >> 3) * 128 + (row & 7) * 16) = pk;
-                }
-                // gate -> sigmoid(g) as BF16 pairs in registers: with q, k, v consumed too, every projection column of this
-                // pair is dead once S = Q K^T has run, so the driver can issue the whole next pair behind it
-                tmem_ld32(pb + 192 + 32 * ch, v);
-#pragma unroll
-                for (int c = 0; c < 16; ++c) gsig[c] = pack2(gate_factor(v[2 * c]), gate_factor(v[2 * c + 1]));
-                tmem_st_wait();
-                tc_fence_before();
-                fence_async_smem();
-                // S = Q K^T is issued by this group itself (no round trip through the driver warp):
-                // A = BF16 Q in TMEM, B = K (K-major, 128 keys x 32)
-                group_barrier(ch);
-                if ((warp & 3) == 0 && lane == 0) {
-                    tc_fence_after();
-                    const uint32_t s_k = smem_u32(smem + OFF_K);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        umma_bf16_ts(tmem + 128 * ch, tmem + 256 + 32 * ch + 8 * k,
-                                     umma_smem_desc(s_k + ch * 8192 + k * 256, 128, 512), umma_idesc_bf16(128, 128),
-                                     k > 0 ? 1u : 0u);
-                    umma_commit(&bars[B_SR0 + ch]);
-                }
-                __syncwarp();
+            for (int c = 0; c < 4; ++c) {
+                uint4 pk;
+                pk.x = pack2(v[8 * c], v[8 * c + 1]); pk.y = pack2(v[8 * c + 2], v[8 * c + 3]);
+                pk.z = pack2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack2(v[8 * c + 6], v[8 * c + 7]);
+                *reinterpret_cast<uint4*>(sk + op_chunk(row, c, 32)) = pk;
             }
-            // scores of this row against the S keys of its own gene: a window of the S tile that starts at the
-            // first gene touched by this warp (register indices stay compile-time, the column is warp-uniform)
-            constexpr int NC = (31 + S - 1) / S + 1;             // genes a 32-row warp can touch
-            constexpr int NW = NC * S;                            // window width in keys (<= 64)
+        };
+        auto issue_s = [&]() {              // S = Q K^T, issued by the group itself: A = BF16 Q in TMEM, B = K in shared memory
+            tmem_st_wait();
+            tc_fence_before();
+            fence_async_smem();
+            group_barrier(ch);
+            if ((warp & 3) == 0 && lane == 0) {
+                tc_fence_after();
+                const uint32_t s_k = smem_u32(smem + OFF_K);
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    umma_bf16_ts(tmem + 128 * ch, tmem + 256 + 32 * ch + 8 * k,
+                                 umma_smem_desc(s_k + ch * 8192 + k * 256, 128, 512), umma_idesc_bf16(128, 128),
+                                 k > 0 ? 1u : 0u);
+                umma_commit(&bars[B_SR0 + ch]);
+            }
+            __syncwarp();
+        };
+        auto stage_vg = [&]() {             // V -> shared, MN-major [32 dims x 128 keys]; gate -> sigmoid(g) as BF16 pairs
+            tmem_ld32(pb + 128 + 32 * ch, v);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 pk;
+                pk.x = pack2(v[8 * c], v[8 * c + 1]); pk.y = pack2(v[8 * c + 2], v[8 * c + 3]);
+                pk.z = pack2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack2(v[8 * c + 6], v[8 * c + 7]);
+                *reinterpret_cast<uint4*>(sv + c * 2048 + (row >> 3) * 128 + (row & 7) * 16) = pk;
+            }
+            tmem_ld32(pb + 192 + 32 * ch, v);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) gsig[c] = pack2(gate_factor(v[2 * c]), gate_factor(v[2 * c + 1]));
+            tc_fence_before();
+            fence_async_smem();             // (V must be visible to the tensor pipe before the barrier in front of O = P V)
+        };
+        stage_qk(0);
+        issue_s();
+        stage_vg();
+        // scores of a row against the S keys of its own gene: a window of the S tile that starts at the first gene touched
+        // by this warp (register indices stay compile-time, the column is warp-uniform)
+        constexpr int NC = (31 + S - 1) / S + 1;             // genes a 32-row warp can touch
+        constexpr int NW = NC * S;                            // window width in keys (<= 64)
+        for (int t = 0; t < 4; ++t) {
             const int g_lo = (32 * lq) / S;
             const int cand = gl - g_lo;                           // 0 .. NC-1
             const float gamma = t == 0 ? gam[0] : t == 1 ? gam[1] : t == 2 ? gam[2] : gam[3];
             float w[64];
             mbar_wait(&bars[B_SR0 + ch], t & 1);
             tc_fence_after();
-            warp_arrive(&bars[B_QKFREE], lane);                   // q / k columns are dead, v is in shared memory
+            warp_arrive(&bars[B_QKFREE], lane);                   // q / k columns are dead, v sits in shared memory, the gates in registers
             {
                 const uint32_t sc0 = trow + 128 * ch + S * g_lo;
                 tmem_ld32(sc0, w);
@@ -526,6 +532,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                 }
                 __syncwarp();
             }
+            if (t < 3) stage_qk(t + 1);                             // (while O = P V runs)
             mbar_wait(&bars[B_OR0 + ch], t & 1);
             tc_fence_after();
             float o[32];
@@ -543,6 +550,10 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                 uint4 pk;
                 pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
                 *reinterpret_cast<uint4*>(smem + OFF_ATT + op_chunk(row, 8 * t + 4 * ch + c, 256)) = pk;
+            }
+            if (t < 3) {
+                issue_s();
+                stage_vg();                                         // (while S = Q K^T runs)
             }
         }
         }
