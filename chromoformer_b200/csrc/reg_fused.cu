@@ -43,7 +43,7 @@ constexpr uint32_t OFF_CTL = OFF_V + 16384;                 // mbarriers + TMEM 
 constexpr uint32_t RF_SMEM = OFF_CTL + 256;
 
 enum { B_FULL0 = 0, B_FREE0 = 3, B_ACCQ0 = 6, B_ACCQFREE0 = 8, B_XREADY = 10, B_ATTREADY, B_UREADY, B_FREADY,
-       B_ACCO, B_ACCF1, B_ACCF2, B_QKVR0, B_SR0 = B_QKVR0 + 2, B_PR0 = B_SR0 + 2, B_OR0 = B_PR0 + 2, B_QKFREE = B_OR0 + 2, B_COUNT };
+       B_ACCO, B_ACCF1, B_ACCF2, B_QKVR0, B_SR0 = B_QKVR0 + 2, B_PR0 = B_SR0 + 2, B_OR0 = B_PR0 + 2, B_QKFREE = B_OR0 + 2, B_ACCVG, B_COUNT };
 
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -182,6 +182,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             mbar_init(&bars[B_PR0 + i], 4); mbar_init(&bars[B_OR0 + i], 1);
         }
         mbar_init(&bars[B_QKFREE], 8);
+        mbar_init(&bars[B_ACCVG], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
@@ -237,14 +238,17 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             // S = Q K^T and O = P V are issued by the compute groups themselves.  The projections of the NEXT pair
             // overlap the attention of this one: they are issued as soon as the S instructions are done with q / k, v sits in
             // shared memory and the gates in registers (B_QKFREE).
+            // ([q | k] and [v | gate] are committed separately: the compute warps repack q, k first)
             consume(cb, s_xb, 2048, 256, false);
-            consume(cb + 1, s_xb, 2048, 384, false);
             umma_commit(&bars[B_ACCQ0]);
+            consume(cb + 1, s_xb, 2048, 384, false);
+            umma_commit(&bars[B_ACCVG]);
             for (int t = 0; t < 3; ++t) {
                 mbar_wait(&bars[B_QKFREE], t & 1);
                 consume(cb + 2 * t + 2, s_xb, 2048, 256, false);        // next [q | k]
-                consume(cb + 2 * t + 3, s_xb, 2048, 384, false);        // next [v | gate]
                 umma_commit(&bars[B_ACCQ0]);
+                consume(cb + 2 * t + 3, s_xb, 2048, 384, false);        // next [v | gate]
+                umma_commit(&bars[B_ACCVG]);
             }
             }
             mbar_wait(&bars[B_ATTREADY], lp);
@@ -450,7 +454,9 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             }
             __syncwarp();
         };
-        auto stage_vg = [&]() {             // V -> shared, MN-major [32 dims x 128 keys]; gate -> sigmoid(g) as BF16 pairs
+        auto stage_vg = [&](int t) {        // V -> shared, MN-major [32 dims x 128 keys]; gate -> sigmoid(g) as BF16 pairs
+            mbar_wait(&bars[B_ACCVG], t & 1);
+            tc_fence_after();
             tmem_ld32(pb + 128 + 32 * ch, v);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
@@ -467,7 +473,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         };
         stage_qk(0);
         issue_s();
-        stage_vg();
+        stage_vg(0);
         // scores of a row against the S keys of its own gene: a window of the S tile that starts at the first gene touched
         // by this warp (register indices stay compile-time, the column is warp-uniform)
         constexpr int NC = (31 + S - 1) / S + 1;             // genes a 32-row warp can touch
@@ -553,7 +559,7 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             }
             if (t < 3) {
                 issue_s();
-                stage_vg();                                         // (while S = Q K^T runs)
+                stage_vg(t + 1);                                    // (while S = Q K^T runs)
             }
         }
         }
