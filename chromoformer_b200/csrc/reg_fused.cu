@@ -712,8 +712,9 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             const bool more = li + 1 < a.n_layers;
             if (more) {
                 // Y is the next layer's operand (BF16, over X in shared memory) and residual (FP32, parked in the scratch
-                // slot by the thread that will read it back, lane-major)
-                float4* park = reinterpret_cast<float4*>(a.y_mid + z * a.y_mid_z + (li & 1) * a.y_l) + (long long)tile * 4096 + row;
+                // slot by the thread that will read it back, lane-major).  Operand first: the driver starts the next
+                // layer's projections on B_XREADY while the rows are being parked.  (No CTA barrier is needed for prm / red:
+                // nobody gets past the next B_ACCQ0 before every warp has arrived here.)
 #pragma unroll
                 for (int ci = 0; ci < 2; ++ci) {
                     const int c = (2 * ci + ch) * 32;
@@ -726,14 +727,16 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                         pk.z = pack2(u_keep[ci][j + 4], u_keep[ci][j + 5]); pk.w = pack2(u_keep[ci][j + 6], u_keep[ci][j + 7]);
                         *reinterpret_cast<uint4*>(smem + OFF_XB + op_chunk(row, (c + j) >> 3, 128)) = pk;
                     }
+                }
+                fence_async_smem();
+                warp_arrive(&bars[B_XREADY], lane);
+                float4* park = reinterpret_cast<float4*>(a.y_mid + z * a.y_mid_z + (li & 1) * a.y_l) + (long long)tile * 4096 + row;
+#pragma unroll
+                for (int ci = 0; ci < 2; ++ci)
 #pragma unroll
                     for (int j = 0; j < 32; j += 4)
                         __stcg(park + ((ch * 2 + ci) * 8 + (j >> 2)) * 128,
                                make_float4(u_keep[ci][j], u_keep[ci][j + 1], u_keep[ci][j + 2], u_keep[ci][j + 3]));
-                }
-                fence_async_smem();
-                compute_barrier();        // prm / red are free for the next layer's k, v
-                warp_arrive(&bars[B_XREADY], lane);
             } else {
                 // last layer: Y row-major to the caller, coalesced through a shared-memory transpose
                 float* Y = a.y + z * a.y_z;
