@@ -60,8 +60,9 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region.  Samples are placed in time by nvidia-smi's
+    own `timestamp` field (the reader thread can be starved of the GIL while the main thread launches kernels)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
@@ -70,21 +71,33 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
             self.proc = None
 
+    @staticmethod
+    def _epoch(stamp):
+        # "2026/10/17 12:34:56.789" in local time
+        try:
+            head, _, ms = stamp.partition(".")
+            return time.mktime(time.strptime(head, "%Y/%m/%d %H:%M:%S")) + (float("0." + ms) if ms else 0.0)
+        except ValueError:
+            return None
+
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+            f = [x.strip() for x in line.split(",")]
+            ts = self._epoch(f[0]) if f else None
+            self.rows.append((ts if ts is not None else time.time(), f[1:]))
 
     def window(self, t0, t1):
-        """Samples that arrived in [t0, t1] (+ one sampling period of slack at the end)."""
+        """Samples taken in [t0, t1]."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
-        rows = [r for ts, r in list(self.rows) if t0 <= ts <= t1 + 0.1]
+        time.sleep(0.12)                      # let the reader thread drain what nvidia-smi has already written
+        rows = [r for ts, r in list(self.rows) if t0 <= ts <= t1]
         sm = sorted(int(r[0]) for r in rows if r and r[0].isdigit())
         mx = [int(r[1]) for r in rows if len(r) > 1 and r[1].isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -243,8 +256,8 @@ def main():
                 eng.predict_device(resident, out)
                 torch.cuda.synchronize()
             clocks = sampler.window(te, time.time())
-            clocks["note"] = ("timed region (%.0f ms) shorter than the sampling period; sampled over 0.6 s of the same step "
-                              "run directly behind it" % ((t1 - t0) * 1e3))
+            clocks["note"] = ("no nvidia-smi sample fell inside the timed region (%.0f ms); sampled over 0.6 s of the same "
+                              "step run directly behind it" % ((t1 - t0) * 1e3))
         sampler.stop()
     genes_per_s = world * N_GENES / (ms * 1e-3)
 
