@@ -166,7 +166,7 @@ def workload_config(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--mode", choices=["infer", "train"], default="infer")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
