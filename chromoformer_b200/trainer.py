@@ -47,6 +47,7 @@ class TrainStep:
         self.use_graph = use_graph
         self._seen = {}          # geometry -> eager steps so far
         self._graphs = {}        # geometry -> captured chain
+        self._flat_ptr = flat.data_ptr()
         self.graph_replays = 0
 
     # ---- forward + loss + backward into self.grad (everything a CUDA graph may hold) -------------------------
@@ -105,6 +106,7 @@ class TrainStep:
             self.use_graph = False
             torch.cuda.synchronize(dev)
             return None
+        self._flat_ptr = self.model.flat_params.data_ptr()
         ent = {"graph": graph, "static": static, "target": tgt, "io": io, "logits": logits, "dlogits": dlogits}
         self._graphs[key] = ent
         return ent
@@ -117,6 +119,9 @@ class TrainStep:
         flat = model.flat_params
         dev = flat.device
         key = self._geometry(batch, target) if self.use_graph else None
+        if self._graphs and self._flat_ptr != flat.data_ptr():      # the model's buffer moved: captured chains are stale
+            self._graphs.clear()
+            self._seen.clear()
         ent = self._graphs.get(key) if self.use_graph else None
         if ent is None:
             io = self._io(batch)
