@@ -424,16 +424,16 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             mbar_wait(&bars[B_ACCQ0], t & 1);
             tc_fence_after();
             uint32_t qp[16];
-            tmem_ld32(pb + 32 * ch, v);
+            float v2[32];
+            tmem_ld32_pair(pb + 32 * ch, v, pb + 64 + 32 * ch, v2);    // q and k of this head, both loads in flight
 #pragma unroll
             for (int c = 0; c < 16; ++c) qp[c] = pack2(v[2 * c], v[2 * c + 1]);
             tmem_st16(pb + 32 * ch, qp);
-            tmem_ld32(pb + 64 + 32 * ch, v);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint4 pk;
-                pk.x = pack2(v[8 * c], v[8 * c + 1]); pk.y = pack2(v[8 * c + 2], v[8 * c + 3]);
-                pk.z = pack2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack2(v[8 * c + 6], v[8 * c + 7]);
+                pk.x = pack2(v2[8 * c], v2[8 * c + 1]); pk.y = pack2(v2[8 * c + 2], v2[8 * c + 3]);
+                pk.z = pack2(v2[8 * c + 4], v2[8 * c + 5]); pk.w = pack2(v2[8 * c + 6], v2[8 * c + 7]);
                 *reinterpret_cast<uint4*>(sk + op_chunk(row, c, 32)) = pk;
             }
         };
@@ -457,7 +457,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         auto stage_vg = [&](int t) {        // V -> shared, MN-major [32 dims x 128 keys]; gate -> sigmoid(g) as BF16 pairs
             mbar_wait(&bars[B_ACCVG], t & 1);
             tc_fence_after();
-            tmem_ld32(pb + 128 + 32 * ch, v);
+            float v2[32];
+            tmem_ld32_pair(pb + 128 + 32 * ch, v, pb + 192 + 32 * ch, v2);   // v and gate of this head
 #pragma unroll
             for (int c = 0; c < 4; ++c) {
                 uint4 pk;
@@ -465,9 +466,8 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                 pk.z = pack2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack2(v[8 * c + 6], v[8 * c + 7]);
                 *reinterpret_cast<uint4*>(sv + c * 2048 + (row >> 3) * 128 + (row & 7) * 16) = pk;
             }
-            tmem_ld32(pb + 192 + 32 * ch, v);
 #pragma unroll
-            for (int c = 0; c < 16; ++c) gsig[c] = pack2(gate_factor(v[2 * c]), gate_factor(v[2 * c + 1]));
+            for (int c = 0; c < 16; ++c) gsig[c] = pack2(gate_factor(v2[2 * c]), gate_factor(v2[2 * c + 1]));
             tc_fence_before();
             fence_async_smem();             // (V must be visible to the tensor pipe before the barrier in front of O = P V)
         };
