@@ -115,44 +115,142 @@ def make_model(cls, seed=123):
 
 
 # ------------------------------------------------------------------------------- CPU arm
-def cpu_oracle_genes_per_s(n_sample, iters, threads):
-    """Reference algorithm as written (oracle port) on the host cores, bounded sample."""
+REF_DIR = os.path.join(ROOT, "baseline", "_ref")        # `pip install --target baseline/_ref /root/reference`
+
+
+def _load_by_path(name, path):
+    """Import one source file WITHOUT importing its package (the reference arm must not load this repo's package)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(name, path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _reference_modules():
+    """The UNMODIFIED reference package from baseline/_ref, on the CPU: `.cuda()` (hard-coded in net.py:52,129) is
+    patched to the identity.  Returns (package, kind)."""
     import torch
-    from chromoformer_b200 import ChromoformerClassifier, synthetic
-    from oracle import chromoformer_oracle as oracle
-    torch.set_num_threads(threads)
-    model = make_model(ChromoformerClassifier)
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    batch = synthetic.make_batch(n_sample, ragged=False, full_masks=True, seed=0)
-    args = synthetic.forward_args(batch)
-    with torch.no_grad():
-        oracle.chromoformer_forward(sd, *args)                    # warm-up
-        t0 = time.perf_counter()
-        for _ in range(iters):
-            oracle.chromoformer_forward(sd, *args)
-        dt = time.perf_counter() - t0
-    return n_sample * iters / dt, dt / iters
+    if not os.path.isdir(os.path.join(REF_DIR, "chromoformer")):
+        return None, "port"
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    torch.nn.Module.cuda = lambda self, *a, **k: self
+    sys.path.insert(0, REF_DIR)
+    for name in [m for m in sys.modules if m == "chromoformer" or m.startswith("chromoformer.")]:
+        del sys.modules[name]
+    import chromoformer
+    assert os.path.abspath(chromoformer.__file__).startswith(REF_DIR), chromoformer.__file__
+    return chromoformer, "reference"
 
 
 def run_reference_arm(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
+    """`--impl reference`: the reference's own CPU implementation of the path (its PyTorch-eager modules, FP32, all
+    host threads) on this arm's workload, in bounded samples: one step = one forward of 64 dense synthetic genes
+    (train.py / run_demo.py batch sizes are 64 / 32).  Nothing of this repo's package or .so is loaded here."""
+    if int(os.environ.get("RANK", "0")) != 0:
         return
+    import torch
     threads = os.cpu_count() or 1
-    n_sample = 32
-    # W warm-ups + K steps of a bounded sample, capped to stay within a few minutes
-    _, per = cpu_oracle_genes_per_s(n_sample, 1, threads)
-    iters = max(1, min(args.steps, int(60.0 / max(per, 1e-3))))
-    gps, per = cpu_oracle_genes_per_s(n_sample, iters, threads)
+    torch.set_num_threads(threads)
+    ref, kind = _reference_modules()
+    syn = _load_by_path("chromo_synthetic_standalone", os.path.join(ROOT, "chromoformer_b200", "synthetic.py"))
+    n_sample = args.ref_batch
+    batch = syn.make_batch(n_sample, ragged=False, full_masks=True, seed=0)
+    fargs = syn.forward_args(batch)
+    if kind == "reference":
+        model = ref.ChromoformerClassifier(7, 128, 128, dict(KWS[0]), dict(KWS[1]), dict(KWS[2]), seed=123).eval()
+        fwd = lambda: model(*fargs)
+        what = "unmodified reference modules (baseline/_ref/chromoformer, PyTorch eager, CPU FP32)"
+    else:       # reference package not staged: the oracle port of the same algorithm
+        oracle = _load_by_path("chromo_oracle_standalone", os.path.join(ROOT, "oracle", "chromoformer_oracle.py"))
+        sd = oracle.init_state_dict(regression=False, seed=123)
+        fwd = lambda: oracle.chromoformer_forward(sd, *fargs)
+        what = "oracle port of the as-written forward (oracle/chromoformer_oracle.py, torch CPU FP32)"
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        fwd()                                                     # first call also sizes the run
+        first = time.perf_counter() - t0
+        budget = 150.0                                            # the whole arm stays within a few minutes
+        warmup = max(0, min(args.warmup, int(0.25 * budget / first)) - 1)
+        steps = max(1, min(args.steps, int(0.75 * budget / first)))
+        for _ in range(warmup):
+            fwd()
+        times = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            fwd()
+            times.append(time.perf_counter() - t0)
+    per = sum(times) / len(times)
+    gps = n_sample / per
+    extra = {}
+    if not args.no_train and kind == "reference":
+        extra["train"] = _reference_train_step(ref, syn, threads)
+        extra["getitem"] = _reference_getitem(ref)
     line = {"impl": "reference", "metric": "genes/sec inference", "value": gps, "unit": "genes/s",
-            "n_gpus": args.gpus, "steps": iters, "warmup": 1, "ms_per_step": per * 1e3,
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup + 1, "steps_requested": args.steps,
+            "warmup_requested": args.warmup, "ms_per_step": per * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp32", "data": "synthetic",
             "config": workload_config(args),
-            "cpu_baseline": {"value": gps, "unit": "genes/s", "cores": threads, "kind": "port",
-                             "sample": f"{n_sample} dense synthetic genes x {iters} passes of the as-written forward "
-                                       "(oracle/chromoformer_oracle.py, torch CPU FP32)"},
-            "e2e": {"value": gps, "unit": "genes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+            "cpu_baseline": {"value": gps, "unit": "genes/s", "cores": threads, "kind": kind,
+                             "sample": f"{n_sample} dense synthetic genes per step x {steps} steps (median "
+                                       f"{sorted(times)[len(times) // 2] * 1e3:.0f} ms): {what}",
+                             "parallel_info": torch.__config__.parallel_info().split("\n")[1:3]},
+            "e2e": {"value": gps, "unit": "genes/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, **extra}
     print(json.dumps(line), flush=True)
+
+
+def _reference_train_step(ref, syn, threads):
+    """ChromoformerRegressor fwd + MSELoss + backward + torch.optim.AdamW.step, bsz 64, CPU FP32."""
+    import torch
+    model = ref.ChromoformerRegressor(7, 128, 128, dict(KWS[0]), dict(KWS[1]), dict(KWS[2]), seed=123).train()
+    opt = torch.optim.AdamW(model.parameters(), lr=3e-5)
+    crit = torch.nn.MSELoss()
+    b = syn.make_batch(64, ragged=False, full_masks=True, seed=100)
+    fargs, target = syn.forward_args(b), b["labels_reg"].view(-1, 1)
+    times = []
+    for it in range(3):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = crit(model(*fargs), target)
+        loss.backward()
+        opt.step()
+        times.append(time.perf_counter() - t0)
+    per = min(times[1:])
+    return {"metric": "train samples/sec", "value": 64 / per, "unit": "samples/s", "ms_per_step": per * 1e3, "cores": threads,
+            "kind": "reference", "sample": "Chromoformer-reg bsz 64, 1 warm-up + best of 2 steps, unmodified reference + "
+                                           "torch.optim.AdamW, CPU FP32"}
+
+
+def _reference_getitem(ref):
+    """the reference's ChromoformerDataset.__getitem__, one process, on the staged demo genes."""
+    demo = os.path.join(REF_DIR, "demo")
+    meta = os.path.join(demo, "demo_meta_head.csv")
+    if not os.path.exists(meta):
+        return None
+    import pandas as pd
+    genes = pd.read_csv(meta).gene_id.tolist()
+    ds = ref.ChromoformerDataset(meta, os.path.join(demo, "demo_data"), genes, 7, 8, [2000, 500, 100], 40000, 40000)
+    ds[0]
+    t0 = time.perf_counter()
+    for i in range(len(genes)):
+        ds[i]
+    per = (time.perf_counter() - t0) / len(genes)
+    return {"metric": "ChromoformerDataset.__getitem__", "value": 1.0 / per, "unit": "genes/s/process", "ms_per_gene": per * 1e3,
+            "kind": "reference", "sample": f"{len(genes)} staged demo genes, one process (data.py:115-212)"}
+
+
+def cpu_baseline_subprocess(steps=3, warmup=1, train=True):
+    """The b200 arm's `cpu_baseline`: the reference arm above in its OWN process (so that neither this repo's .so nor its
+    `chromoformer` shim is anywhere near the timed reference code)."""
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", str(warmup)]
+    if not train:
+        cmd.append("--no-train")
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    try:
+        out = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env).stdout.strip().splitlines()
+        return json.loads(out[-1])
+    except Exception as e:                                        # noqa: BLE001
+        return {"error": repr(e)}
 
 
 def workload_config(args):
@@ -175,6 +273,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--ref-batch", type=int, default=64, help="genes per step of the CPU reference arm")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -456,12 +555,13 @@ def main():
     # ---------------- CPU baseline (rank 0, N = 1 only) -------------------------------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        gps, per = cpu_oracle_genes_per_s(32, 1, threads)
-        iters = max(1, min(8, int(15.0 / max(per, 1e-3))))
-        gps, per = cpu_oracle_genes_per_s(32, iters, threads)
-        cpu = {"value": gps, "unit": "genes/s", "cores": threads, "kind": "port",
-               "sample": f"32 dense synthetic genes x {iters} passes of the as-written forward (oracle port, torch CPU FP32)"}
+        ref_line = cpu_baseline_subprocess(steps=4, warmup=1, train=not args.no_train)
+        cpu = ref_line.get("cpu_baseline") or ref_line
+        if train is not None and isinstance(ref_line.get("train"), dict):
+            train["cpu_baseline"] = ref_line["train"]
+        cpu_getitem = ref_line.get("getitem")
+        if cpu_getitem:
+            cpu["getitem"] = cpu_getitem
 
     if rank == 0:
         line = {"metric": "genes/sec inference", "value": genes_per_s, "unit": "genes/s", "n_gpus": world,

@@ -116,7 +116,8 @@ class ChromoformerDataset(Dataset):
                 xp, lp = xp[:, ::-1], rp
             mp = torch.ones(1, 1, n, n, dtype=torch.bool)
             mp[0, 0, lp:lp + nbp, lp:lp + nbp] = False
-            xc = np.zeros((self.i_max, n, self.n_feats), dtype=np.float32)
+            # feature count from the data, not from `n_feats`: run_demo_regression.py:79-81 passes i_max in that slot
+            xc = np.zeros((self.i_max, n, raws[0].shape[0]), dtype=np.float32)
             mc = torch.ones(self.i_max, 1, n, n, dtype=torch.bool)
             for j in range(k):
                 c, lc, nbc, _ = _centre_pad(_bin_log_mean(raws[1 + j], b), n)

@@ -58,7 +58,7 @@ class InferenceEngine:
             out = torch.empty(n, int(self.model._cfg.n_out), dtype=torch.float32, device=self.device)
         for lo in range(0, n, self.chunk):
             hi = min(n, lo + self.chunk)
-            out[lo:hi] = self.model(*_args(_slice(batch, lo, hi)))
+            out[lo:hi] = self.model.forward_batch(_slice(batch, lo, hi))
         return out
 
     def _staging(self, batch):
@@ -108,7 +108,7 @@ class InferenceEngine:
             if i + 1 < len(bounds):
                 upload(i + 1)
             main.wait_event(copied[i])
-            out[lo:hi] = self.model(*_args(_slice(sets[i % 2], 0, hi - lo)))
+            out[lo:hi] = self.model.forward_batch(_slice(sets[i % 2], 0, hi - lo))
             freed[i].record(main)
         host = torch.empty(out.shape, dtype=out.dtype, pin_memory=True)
         host.copy_(out, non_blocking=True)

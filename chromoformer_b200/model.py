@@ -15,6 +15,8 @@ the C ABI, forward and backward.  There is no PyTorch fallback.
 """
 import ctypes
 import math
+import os
+import re
 
 import numpy as np
 import torch
@@ -91,6 +93,34 @@ class _Stack(nn.Module):
         self.layers = nn.ModuleList(layers)
 
 
+def _default_precision():
+    p = os.environ.get("CHROMO_PRECISION", "fp32").strip().lower()
+    if p not in ("fp32", "bf16"):
+        raise ValueError(f"CHROMO_PRECISION must be 'fp32' or 'bf16', got {p!r}")
+    return p
+
+
+# Legacy checkpoint key generations (misc/convert_weight.py:19-88), oldest first.  Each rule rewrites one
+# generation's spelling into the dict layout of net.py:273-330; `canonical_key` applies them in that order.
+_LEGACY_RULES = (
+    (re.compile(r"lin_proj_c(?=\.)"), "lin_proj_pcre"),
+    (re.compile(r"^transformer(\d+)\."), r"regulation.\1.transformer."),
+    (re.compile(r"^embed(\d+)_a\."), r"embed.\1."),
+    (re.compile(r"^embed(\d+)_b\."), r"pairwise_interaction.\1."),
+    (re.compile(r"^embed(\d+)\."), r"embed.\1."),
+    (re.compile(r"^pw_int(\d+)\."), r"pairwise_interaction.\1."),
+    (re.compile(r"^reg(\d+)\."), r"regulation.\1."),
+)
+
+
+def canonical_key(key):
+    """Any generation of checkpoint key -> the dict-layout key (`embed.2000.…`, `pairwise_interaction.2000.…`,
+    `regulation.2000.…`); keys already in that layout come back unchanged."""
+    for pat, rep in _LEGACY_RULES:
+        key = pat.sub(rep, key)
+    return key
+
+
 def _standalone_error(name):
     raise NotImplementedError(
         f"{name} is a parameter container here: the sm_100a kernels evaluate the whole "
@@ -144,7 +174,12 @@ class RegulationTransformer(nn.Module):
 # autograd bridge
 # --------------------------------------------------------------------------------------
 class _ChromoFunction(torch.autograd.Function):
-    """loss.backward() support for the unchanged training loop (train.py:182-196)."""
+    """loss.backward() support for the unchanged training loop (train.py:182-196).
+
+    Limits (by design: the backward kernels write straight into the flat gradient buffer): parameter gradients
+    arrive as a side effect on ``p.grad`` (``torch.autograd.grad(loss, params)`` sees only the zero anchor), there is
+    no gradient with respect to the input features, and a forward's activations are released by its first
+    backward (no ``retain_graph``)."""
 
     @staticmethod
     def forward(ctx, anchor, model, io):
@@ -155,6 +190,9 @@ class _ChromoFunction(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dlogits):
         model, io, ws = ctx.model, ctx.io, ctx.ws
+        if ws is None:
+            raise RuntimeError("chromoformer_b200: this forward's activations were released by its first backward "
+                               "(retain_graph is not supported: run the forward again)")
         model._launch_backward(io, ws, dlogits.contiguous())
         ctx.ws = None
         return None, None, None
@@ -229,8 +267,10 @@ class _BatchIO:
 class _ChromoformerCore(nn.Module):
     """Shared machinery: flat parameter buffer, C config, launchers."""
 
-    #: "fp32" = strict FP32 on the CUDA cores, "bf16" = tcgen05 BF16 operands / FP32 accumulate
-    precision = "fp32"
+    #: "fp32" = strict FP32 on the CUDA cores, "bf16" = tcgen05 BF16 operands / FP32 accumulate.  The class default
+    #: comes from the environment (CHROMO_PRECISION=bf16) so that callers that cannot be edited - the reference's
+    #: demo/run_demo.py, `python -m chromoformer.train` - reach the tensor path without a code change.
+    precision = _default_precision()
 
     # ---- construction ----------------------------------------------------------------
     def _finalise(self, n_feats, d_emb, d_head, n_out, embed_kws, pw_kws, reg_kws, binsizes, i_max, w_max):
@@ -311,13 +351,8 @@ class _ChromoformerCore(nn.Module):
         object.__setattr__(self, "_packed_key", None)
 
     def _flat_is_current(self):
-        slots = self._slots
         base = self._flat.data_ptr()
-        for i in (0, len(slots) // 2, len(slots) - 1):
-            _, p, off, _ = slots[i]
-            if p.data_ptr() != base + 4 * off:
-                return False
-        return True
+        return all(p.data_ptr() == base + 4 * off for (_, p, off, _) in self._slots)
 
     # ---- flat views used by the optimiser / data-parallel wrapper ----------------------
     @property
@@ -377,7 +412,7 @@ class _ChromoformerCore(nn.Module):
             # reuse them while neither the buffer nor the parameters changed
             # (p.data = view keeps each parameter's own version counter, so sum them)
             packed_key = (ws.data_ptr(), sum(p._version for (_, p, _, _) in self._slots), self._param_epoch,
-                          tuple(io.cfg.n_bins[r] for r in range(io.cfg.n_res)))
+                          int(io.cfg.i_max), tuple(io.cfg.n_bins[r] for r in range(io.cfg.n_res)))
             if packed_key == self._packed_key:
                 flags |= _lib.F_PACKED
         logits = torch.empty(io.batch, int(self._cfg.n_out), dtype=torch.float32, device=self._flat.device)
@@ -421,6 +456,30 @@ class _ChromoformerCore(nn.Module):
                 if off < self._n_active and p.requires_grad:
                     g = target[off:off + numel].view(p.shape)
                     p.grad = g.clone() if p.grad is None else p.grad + g
+
+    # ---- checkpoints: every key generation of the reference loads into every class (misc/convert_weight.py) ----
+    def _own_key(self, canon):
+        """dict-layout key -> this class's own state_dict key."""
+        return canon
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        mapped = {self._own_key(canonical_key(k)): v for k, v in state_dict.items()}
+        out = super().load_state_dict(mapped, strict=strict, assign=assign)
+        if not self._flat_is_current():          # assign=True rebinds the parameters: re-home them in the flat buffer
+            self._rebuild_flat()
+        else:
+            self.mark_parameters_changed()
+        return out
+
+    def forward_batch(self, batch):
+        """Forward from a dict of the six arguments keyed like the reference's collated items (dicts by int bin size):
+        the one calling convention `InferenceEngine` / `EnsembleSweep` use for the flat and the dict API alike."""
+        def pick(d, b):
+            return d[b] if b in d else d[str(b)]
+        bs = self.binsizes
+        return self._run([pick(batch["promoter_feats"], b) for b in bs], [pick(batch["promoter_pad_masks"], b) for b in bs],
+                         [pick(batch["pcre_feats"], b) for b in bs], [pick(batch["pcre_pad_masks"], b) for b in bs],
+                         [pick(batch["interaction_masks"], b) for b in bs], batch["interaction_freq"])
 
     def _run(self, x_p, mask_p, x_pcre, mask_pcre, imask, freq):
         io = _BatchIO(self, x_p, mask_p, x_pcre, mask_pcre, imask, freq)
@@ -523,6 +582,13 @@ class Chromoformer(_ChromoformerCore):
             list(self._BINS), i_max, w_max)
 
     _PREFIX = {"embed": "embed", "pw_int": "pairwise_interaction", "reg": "regulation"}
+
+    def _own_key(self, canon):
+        for short, full in self._PREFIX.items():
+            if canon.startswith(full + "."):
+                res, rest = canon[len(full) + 1:].split(".", 1)
+                return f"{short}{res}.{rest}"
+        return canon
 
     def _lib_name(self, name):
         head, rest = name.split(".", 1)

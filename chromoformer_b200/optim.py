@@ -25,12 +25,39 @@ class FusedAdamW(torch.optim.Optimizer):
         self._step = 0
         self.grad_scale = grad_scale
 
-    def _ensure_state(self):
+    def _ensure_state(self, keep_state=False):
         flat = self._model.flat_params
         if self._m is None or self._m.device != flat.device or self._m.numel() != flat.numel():
             self._m = torch.zeros_like(flat)
             self._v = torch.zeros_like(flat)
-            self.state.clear()
+            if not keep_state:
+                self.state.clear()
+
+    def load_state_dict(self, state_dict):
+        """Resume (the `optimizer` entry of train.py:322-343 checkpoints, written by this class or by stock
+        torch.optim.AdamW): the loaded per-parameter moments are copied into the flat buffers the kernel updates and
+        the state entries are re-pointed at views of those buffers; the step count is restored."""
+        super().load_state_dict(state_dict)
+        self._m = self._v = None
+        self._ensure_state(keep_state=True)
+        steps = []
+        for (_, p, off, numel) in self._model._slots:
+            st = self.state.get(p)
+            if not st or "exp_avg" not in st:
+                continue
+            if off >= self._model.n_active:
+                raise _lib.ChromoLibError("FusedAdamW.load_state_dict: optimiser state for a tensor that never "
+                                          "receives a gradient")
+            m_view = self._m[off:off + numel].view(p.shape)
+            v_view = self._v[off:off + numel].view(p.shape)
+            m_view.copy_(st["exp_avg"])
+            v_view.copy_(st["exp_avg_sq"])
+            st["exp_avg"], st["exp_avg_sq"] = m_view, v_view
+            steps.append(int(float(st["step"])))
+        if steps and min(steps) != max(steps):
+            raise _lib.ChromoLibError("FusedAdamW.load_state_dict: per-parameter step counts differ "
+                                      f"({min(steps)}..{max(steps)}); the fused kernel keeps one step for all tensors")
+        self._step = steps[0] if steps else 0
 
     def _publish_state(self):
         """Expose the flat moments through the stock per-parameter state layout."""

@@ -51,7 +51,7 @@ class EnsembleSweep:
             if ck != active:
                 self._activate(ck)
                 active = ck
-            out.append(self.model(*[_slice(batch, g0, g1)[k] for k in _KEYS]))
+            out.append(self.model.forward_batch(_slice(batch, g0, g1)))
         return mine, out
 
     @staticmethod

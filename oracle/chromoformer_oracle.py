@@ -156,6 +156,64 @@ def chromoformer_forward(sd, promoter_feats, promoter_pad_masks, pcre_feats, pcr
     return h @ sd["fc_head.2.weight"].t() + sd["fc_head.2.bias"]
 
 
+def init_state_dict(regression=False, seed=42, n_feats=7, d_emb=128, d_head=128, binsizes=(2000, 500, 100),
+                    embed=(1, 2, 128), pairwise=(2, 2, 128, 256), regulation=(6, 8, 256, 256)):
+    """Initial weights of `ChromoformerClassifier(seed)` / `ChromoformerRegressor(seed)` in the dict layout: the same
+    sequence of nn.Linear / nn.LayerNorm constructor calls after torch.manual_seed(seed) as net.py:301-330 (regressor:
+    net.py:413-428 builds the 2-logit head first, then the 1-output head) with modules.py:16-25,94-96,135-146 inside.
+    Tuples are (n_layers, n_heads, [d_model,] d_ff)."""
+    import torch.nn as nn
+    torch.manual_seed(seed)
+    sd = {}
+
+    def put(prefix, module):
+        for k, v in module.state_dict().items():
+            sd[prefix + k] = v.detach().clone()
+
+    def self_att(pre, heads, d_model, gate):
+        sd[pre + "gamma_f"] = torch.ones(heads)
+        put(pre + "w_bias.", nn.Linear(2, heads, bias=False))
+        put(pre + "att.", nn.Linear(d_emb, (4 if gate else 3) * d_model, bias=False))
+        put(pre + "ff.", nn.Linear(d_model, d_emb))
+        put(pre + "ln.", nn.LayerNorm(d_emb))
+
+    def ffn(pre, d_ff):
+        put(pre + "l1.", nn.Linear(d_emb, d_ff))
+        put(pre + "l2.", nn.Linear(d_ff, d_emb))
+        put(pre + "ln.", nn.LayerNorm(d_emb))
+
+    for b in binsizes:
+        pre = f"embed.{b}."
+        put(pre + "lin_proj.", nn.Linear(n_feats, d_emb, bias=False))
+        for l in range(embed[0]):
+            self_att(f"{pre}transformer.layers.{l}.self_att.", embed[1], d_emb, gate=False)
+            ffn(f"{pre}transformer.layers.{l}.ff.", embed[2])
+    for b in binsizes:
+        pre = f"pairwise_interaction.{b}."
+        put(pre + "ln.", nn.LayerNorm(d_emb))
+        put(pre + "lin_proj_p.", nn.Linear(d_emb, d_emb, bias=False))
+        put(pre + "lin_proj_pcre.", nn.Linear(n_feats, d_emb, bias=False))
+        for l in range(pairwise[0]):
+            ap = f"{pre}transformer.layers.{l}.self_att."
+            sd[ap + "gamma_f"] = torch.ones(pairwise[1])
+            put(ap + "p_att.", nn.Linear(d_emb, pairwise[2], bias=False))
+            put(ap + "c_att.", nn.Linear(d_emb, 2 * pairwise[2], bias=False))
+            put(ap + "ff.", nn.Linear(pairwise[2], d_emb))
+            put(ap + "ln.", nn.LayerNorm(d_emb))
+            ffn(f"{pre}transformer.layers.{l}.ff.", pairwise[3])
+    for b in binsizes:
+        pre = f"regulation.{b}."
+        for l in range(regulation[0]):
+            self_att(f"{pre}transformer.layers.{l}.self_att.", regulation[1], regulation[2], gate=True)
+            ffn(f"{pre}transformer.layers.{l}.ff.", regulation[3])
+    heads = [(nn.Linear(d_emb * 3, d_head), nn.Linear(d_head, 2))]
+    if regression:
+        heads.append((nn.Linear(d_emb * 3, d_head), nn.Linear(d_head, 1)))
+    put("fc_head.0.", heads[-1][0])
+    put("fc_head.2.", heads[-1][1])
+    return sd
+
+
 def legacy_to_dict_layout(sd):
     """Key renaming of misc/convert_weight.py:19-88 (embed2000 -> embed.2000 ...)."""
     out = {}

@@ -187,3 +187,53 @@ def test_fused_train_step_graph_replay_matches_eager(regression):
     # a noise-level gradient into a +-lr step whatever its size: compare in the bulk, not in the maximum.
     diff = (p_e - p_g).abs()
     assert diff.mean().item() < 1e-6 and torch.quantile(diff[:: 7], 0.999).item() < 1e-4, (diff.mean(), diff.max())
+
+
+def test_fused_adamw_resume_matches_stock_adamw():
+    """a FusedAdamW restored from a checkpoint (its own or stock AdamW's `optimizer` entry, train.py:322-343)
+    must continue with the saved moments and step count, and keep publishing live views of them."""
+    batches = [synthetic.make_batch(4, ragged=True, seed=40 + i) for i in range(4)]
+
+    def run(model, opt, b):
+        opt.zero_grad()
+        out = model(*synthetic.forward_args(b, "cuda"))
+        torch.nn.functional.mse_loss(out, b["labels_reg"].view(-1, 1).cuda()).backward()
+        opt.step()
+
+    # uninterrupted stock AdamW run: 4 steps
+    ref = _mk(ChromoformerRegressor, seed=5).cuda().train()
+    ref_opt = torch.optim.AdamW(ref.parameters(), lr=1e-3)
+    for b in batches:
+        run(ref, ref_opt, b)
+    # fused: 2 steps, checkpoint, fresh model + optimiser, restore, 2 more steps
+    a = _mk(ChromoformerRegressor, seed=5).cuda().train()
+    a_opt = FusedAdamW(a, lr=1e-3)
+    for b in batches[:2]:
+        run(a, a_opt, b)
+    ckpt = {"net": {k: v.clone() for k, v in a.state_dict().items()}, "optimizer": a_opt.state_dict()}
+    assert len(ckpt["optimizer"]["state"]) == 334
+    b_model = _mk(ChromoformerRegressor, seed=77).cuda().train()
+    b_model.load_state_dict(ckpt["net"])
+    b_opt = FusedAdamW(b_model, lr=1e-3)
+    b_opt.load_state_dict(ckpt["optimizer"])
+    assert b_opt._step == 2
+    for b in batches[2:]:
+        run(b_model, b_opt, b)
+    for (n1, p1), (_, p2) in zip(ref.named_parameters(), b_model.named_parameters()):
+        assert (p1 - p2).abs().max().item() < 2e-6, n1
+    # the published state is the live flat buffers (not stale loaded tensors) and carries the step
+    sd = b_opt.state_dict()
+    assert float(sd["state"][0]["step"]) == 4.0
+    p0 = next(iter(b_model.parameters()))
+    assert b_opt.state[p0]["exp_avg"].data_ptr() >= b_opt._m.data_ptr()
+    assert b_opt.state[p0]["exp_avg"].data_ptr() < b_opt._m.data_ptr() + 4 * b_opt._m.numel()
+    # a stock-AdamW checkpoint restores into the fused optimiser as well
+    c_model = _mk(ChromoformerRegressor, seed=78).cuda().train()
+    c_model.load_state_dict(ref.state_dict())
+    c_opt = FusedAdamW(c_model, lr=1e-3)
+    c_opt.load_state_dict(ref_opt.state_dict())
+    assert c_opt._step == 4
+    run(ref, ref_opt, batches[0])
+    run(c_model, c_opt, batches[0])
+    for (n1, p1), (_, p2) in zip(ref.named_parameters(), c_model.named_parameters()):
+        assert (p1 - p2).abs().max().item() < 2e-6, n1

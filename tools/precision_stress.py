@@ -1,0 +1,82 @@
+"""BF16 tensor path vs strict FP32 (CUDA) and vs the CPU oracle, untrained / stress-scaled / briefly trained weights:
+max-abs logit error, logit range and predicted-label agreement on >= 10k synthetic genes.  Prints a markdown table and
+writes the same numbers as JSON (committed under profiles/).  Needs a GPU.
+
+    python tools/precision_stress.py [out.json]
+"""
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch  # noqa: E402
+
+from chromoformer_b200 import ChromoformerClassifier, synthetic  # noqa: E402
+from chromoformer_b200.engine import InferenceEngine  # noqa: E402
+from chromoformer_b200.trainer import TrainStep  # noqa: E402
+from oracle import chromoformer_oracle as oracle  # noqa: E402
+
+N = 10240
+
+
+def measure(name, model, batch, n_oracle=64):
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    model.eval()
+    eng = InferenceEngine(model, chunk=4096)
+    dev = eng.to_device(batch)
+    model.precision = "fp32"
+    want = eng.predict_device(dev).cpu()
+    model.precision = "bf16"
+    got = eng.predict_device(dev).cpu()
+    part = synthetic.expand_full_masks(synthetic.slice_batch(batch, 0, n_oracle))
+    with torch.no_grad():
+        ora = oracle.chromoformer_forward(sd, *synthetic.forward_args(part))
+    margin = (want[:, 1] - want[:, 0]).abs()
+    err = (got - want).abs().max().item()
+    same = got.argmax(1) == want.argmax(1)
+    return {"weights": name, "genes": int(want.size(0)), "logit_range": [want.min().item(), want.max().item()],
+            "bf16_vs_fp32_cuda_max_abs": err, "bf16_vs_oracle_max_abs_%d_genes" % n_oracle: (got[:n_oracle] - ora).abs().max().item(),
+            "fp32_cuda_vs_oracle_max_abs": (want[:n_oracle] - ora).abs().max().item(),
+            "label_agreement": same.float().mean().item(),
+            "label_agreement_margin_gt_1e-2": same[margin > 1e-2].float().mean().item(),
+            "genes_with_margin_le_1e-2": int((margin <= 1e-2).sum()),
+            "median_abs_margin": margin.median().item()}
+
+
+def main():
+    rows = []
+    m = ChromoformerClassifier(seed=123).cuda()
+    rows.append(measure("untrained (seed 123), ragged genes", m, synthetic.make_batch(N, ragged=True, seed=17)))
+    rows.append(measure("untrained (seed 123), dense genes (the bench workload)", m, synthetic.make_batch(N, ragged=False, seed=0)))
+    m = ChromoformerClassifier(seed=123)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if p.dim() == 2:
+                p.mul_(8.0 if name == "fc_head.2.weight" else 2.0)
+    m.cuda()
+    rows.append(measure("stress-scaled (2-D weights x2, last layer x8), stress features", m,
+                        synthetic.make_batch(N, ragged=True, seed=17, stress=True)))
+    # briefly trained: 200 AdamW steps on a learnable synthetic rule (label = mean promoter signal above median)
+    m = ChromoformerClassifier(seed=123).cuda().train()
+    tb = synthetic.make_batch(4096, ragged=True, seed=5)
+    sig = tb["promoter_feats"][100].mean(dim=(1, 2, 3))
+    labels = (sig > sig.median()).long().cuda()
+    dev = {k: ({b: t.cuda() for b, t in v.items()} if isinstance(v, dict) else v.cuda()) for k, v in tb.items()}
+    step = TrainStep(m, regression=False, lr=3e-4, use_graph=False)
+    for it in range(200):
+        lo = (it * 64) % 4096
+        step(synthetic.slice_batch(dev, lo, lo + 64), labels[lo:lo + 64])
+    rows.append(measure("trained 200 steps (synthetic rule), ragged genes", m, synthetic.make_batch(N, ragged=True, seed=18)))
+    keys = list(rows[0].keys())
+    print("| " + " | ".join(keys) + " |")
+    print("|" + "---|" * len(keys))
+    for r in rows:
+        print("| " + " | ".join(("%.3e" % v if isinstance(v, float) else str(v)) for v in r.values()) + " |")
+    if len(sys.argv) > 1:
+        json.dump(rows, open(sys.argv[1], "w"), indent=1)
+
+
+if __name__ == "__main__":
+    main()
