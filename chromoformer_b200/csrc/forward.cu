@@ -659,6 +659,9 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         return gemm_launch(g, true, true, nz, st);
     };
     if (bf16 && !(flags & CHROMO_F_PACKED)) CHROMO_TRY(pack_all_weights(c, L, P, packed, ws, w, in, st));
+    // precision diagnostics (tools/precision_stress.py): keep one stage's contractions on the FP32 CUDA-core GEMM
+    const bool reg_fp32 = getenv("CHROMO_REG_FP32") != nullptr, head_fp32 = getenv("CHROMO_HEAD_FP32") != nullptr;
+    auto lin_fp32 = [&](const GemmArgs& g, int nz) -> int { return gemm_launch(g, true, true, nz, st); };
 
     if (!only) {
     // ---------------- Embedding transformer, centre query (net.py:31-59) ----
@@ -924,6 +927,8 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     }   // !only
     // ---------------- Regulation transformer (net.py:152-153) ---------------
     const int dmr = c->reg_d_model, Hr = c->reg_heads;
+    const bool pb16 = proj_bf16 && !reg_fp32;
+    auto rlin = [&](const GemmArgs& g, int nz) -> int { return reg_fp32 ? lin_fp32(g, nz) : lin(g, nz); };
     for (int l = 0; l < c->reg_layers; ++l) {
         if (only && only->layer >= 0 && l != only->layer) continue;
         const AttnOff& ra = L.reg[0].att[l];
@@ -933,7 +938,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         float* xout = ws + w.r_out + so;
         long long x_z = RS, y_z = RS;
         if (only) { xin = only->x; xout = only->y; x_z = y_z = only->xy_stride; }
-        if (w.reg_fused && !getenv("CHROMO_NO_REG_FUSED")) {
+        if (w.reg_fused && !reg_fp32 && !getenv("CHROMO_NO_REG_FUSED")) {
             // whole layer in one launch (reg_fused.cu); with the tensor-pipe attention ALL layers in one launch:
             // a CTA keeps its 14 genes on chip from layer to layer (the tokens of a gene only attend to each other)
             const bool all = (!only || only->layer < 0) && reg_fused_tensor_attention() && !getenv("CHROMO_REG_PER_LAYER");
@@ -962,14 +967,14 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.A = xin; g.lda = D; g.sA1 = x_z;
             g.B = P + ra.att; g.ldb = D; g.sB1 = L.reg_stride;
             g.C = ws + w.r_proj + so; g.ldc = 4 * dmr; g.sC1 = RS;
-            if (proj_bf16) { g.c_bf16 = 1; g.sC1 = 2 * RS; }
+            if (pb16) { g.c_bf16 = 1; g.sC1 = 2 * RS; }
             g.M = T; g.N = 4 * dmr; g.K = D;
-            CHROMO_TRY(lin(g, NR));
+            CHROMO_TRY(rlin(g, NR));
         }
         {
             RegAttnArgs a;
             a.B = B; a.S = S; a.H = Hr;
-            a.proj = ws + w.r_proj + so; a.proj_zstride = proj_bf16 ? 2 * RS : RS; a.proj_bf16 = proj_bf16 ? 1 : 0;
+            a.proj = ws + w.r_proj + so; a.proj_zstride = pb16 ? 2 * RS : RS; a.proj_bf16 = pb16 ? 1 : 0;
             a.gamma_f = P + ra.gamma_f; a.gamma_zstride = L.reg_stride;
             a.freq = in->freq;
             for (int r = 0; r < NR; ++r) a.imask[r] = in->imask[r];
@@ -987,7 +992,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.res = xin; g.ldres = D; g.sRes1 = x_z;
             g.gamma = P + ra.lnw; g.beta = P + ra.lnb; g.sLn1 = L.reg_stride;
             if (train) { g.pre = ws + w.r_preU + so; g.sPre1 = RS; }
-            CHROMO_TRY(lin(g, NR));
+            CHROMO_TRY(rlin(g, NR));
         }
         {
             GemmArgs g = gemm_args();
@@ -996,7 +1001,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.C = ws + w.r_f + so; g.ldc = c->reg_d_ff; g.sC1 = RS;
             g.M = T; g.N = c->reg_d_ff; g.K = D;
             g.epi = EPI_BIAS_RELU; g.bias = P + rf.l1b; g.sBias1 = L.reg_stride;
-            CHROMO_TRY(lin(g, NR));
+            CHROMO_TRY(rlin(g, NR));
         }
         {
             GemmArgs g = gemm_args();
@@ -1008,7 +1013,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.res = ws + w.r_u + so; g.ldres = D; g.sRes1 = RS;
             g.gamma = P + rf.lnw; g.beta = P + rf.lnb; g.sLn1 = L.reg_stride;
             if (train) { g.pre = ws + w.r_preY + so; g.sPre1 = RS; }
-            CHROMO_TRY(lin(g, NR));
+            CHROMO_TRY(rlin(g, NR));
         }
     }
 
@@ -1029,7 +1034,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         g.C = ws + w.h_h1; g.ldc = c->d_head;
         g.M = B; g.N = c->d_head; g.K = NR * D;
         g.epi = EPI_BIAS_RELU; g.bias = P + L.fc0b;
-        CHROMO_TRY(lin(g, 1));
+        CHROMO_TRY(head_fp32 ? lin_fp32(g, 1) : lin(g, 1));
     }
     {
         GemmArgs g = gemm_args();
@@ -1038,7 +1043,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         g.C = logits; g.ldc = c->n_out;
         g.M = B; g.N = c->n_out; g.K = c->d_head;
         g.epi = EPI_BIAS; g.bias = P + L.fc2b;
-        CHROMO_TRY(lin(g, 1));
+        CHROMO_TRY(head_fp32 ? lin_fp32(g, 1) : lin(g, 1));
     }
     (void)flags;
     return CHROMO_OK;

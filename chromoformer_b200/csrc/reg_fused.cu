@@ -157,8 +157,8 @@ __device__ __forceinline__ void build_p_window(const float* p, int c, uint32_t* 
 
 }  // namespace
 
-template <int SMAX, bool TC>
-__global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const RegFusedArgs a) {
+template <int SMAX>
+__global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_cc_kernel(const RegFusedArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_CTL);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
@@ -224,32 +224,12 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
             const int cb = li * RF_NCHUNK;
             const uint32_t lp = li & 1;
             mbar_wait(&bars[B_XREADY], lp);
-            if (!TC) {
             for (int t = 0; t < 4; ++t) {
                 const int buf = t & 1;
                 if (t >= 2) mbar_wait(&bars[B_ACCQFREE0 + buf], 0);
                 consume(cb + 2 * t, s_xb, 2048, 256 * buf, false);          // [q | k] of heads 2t, 2t+1
                 consume(cb + 2 * t + 1, s_xb, 2048, 256 * buf + 128, false); // [v | gate]
                 umma_commit(&bars[B_ACCQ0 + buf]);
-            }
-            } else {
-            // attention on the tensor pipe: TMEM [0,128) / [128,256) = S, then P (first 64..77 columns) and O (last 32)
-            // of the two heads in flight; [256,512) = projection pair (q0 q1 k0 k1 v0 v1 g0 g1, 32 columns each).
-            // S = Q K^T and O = P V are issued by the compute groups themselves.  The projections of the NEXT pair
-            // overlap the attention of this one: they are issued as soon as the S instructions are done with q / k, v sits in
-            // shared memory and the gates in registers (B_QKFREE).
-            // ([q | k] and [v | gate] are committed separately: the compute warps repack q, k first)
-            consume(cb, s_xb, 2048, 256, false);
-            umma_commit(&bars[B_ACCQ0]);
-            consume(cb + 1, s_xb, 2048, 384, false);
-            umma_commit(&bars[B_ACCVG]);
-            for (int t = 0; t < 3; ++t) {
-                mbar_wait(&bars[B_QKFREE], t & 1);
-                consume(cb + 2 * t + 2, s_xb, 2048, 256, false);        // next [q | k]
-                umma_commit(&bars[B_ACCQ0]);
-                consume(cb + 2 * t + 3, s_xb, 2048, 384, false);        // next [v | gate]
-                umma_commit(&bars[B_ACCVG]);
-            }
             }
             mbar_wait(&bars[B_ATTREADY], lp);
             consume(cb + 8, s_att, 4096, 0, false);                     // out-projection, K halves
@@ -321,10 +301,6 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
         for (int li = 0; li < a.n_layers; ++li) {
         const uint32_t lp = li & 1;
         const long long po = z * a.p_z + li * a.p_l;          // this (resolution, layer)'s parameters
-        float gam[4];                                         // gamma_f of the four heads this thread serves (TC path)
-#pragma unroll
-        for (int t = 0; t < 4; ++t) gam[t] = a.gamma_f[po + 2 * t + ch];
-        if (!TC) {
         for (int t = 0; t < 4; ++t) {
             const int buf = t & 1;
             const uint32_t qb = trow + 256 * buf;
@@ -411,157 +387,6 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
                 pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
                 *reinterpret_cast<uint4*>(smem + OFF_ATT + op_chunk(row, 8 * t + 4 * ch + c, 256)) = pk;
             }
-        }
-        } else {
-        // one thread per token row; warps 0-3 take head 2t, warps 4-7 head 2t+1.  The steps of consecutive head pairs
-        // are interleaved so that the two MMA round trips of a pair hide behind CUDA-core work of the next one:
-        //   ... softmax(t), issue O(t) | q, k of pair t+1 | wait O(t), gate, att | issue S(t+1) | v, gates of t+1 | ...
-        const uint32_t pb = trow + 256;
-        uint32_t gsig[16];
-        uint8_t* sk = smem + OFF_K + ch * 8192;
-        uint8_t* sv = smem + OFF_V + ch * 8192;
-        auto stage_qk = [&](int t) {        // Q -> BF16 back into TMEM in place (A operand of S = Q K^T); K -> shared, K-major
-            mbar_wait(&bars[B_ACCQ0], t & 1);
-            tc_fence_after();
-            uint32_t qp[16];
-            float v2[32];
-            tmem_ld32_pair(pb + 32 * ch, v, pb + 64 + 32 * ch, v2);    // q and k of this head, both loads in flight
-#pragma unroll
-            for (int c = 0; c < 16; ++c) qp[c] = pack2(v[2 * c], v[2 * c + 1]);
-            tmem_st16(pb + 32 * ch, qp);
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint4 pk;
-                pk.x = pack2(v2[8 * c], v2[8 * c + 1]); pk.y = pack2(v2[8 * c + 2], v2[8 * c + 3]);
-                pk.z = pack2(v2[8 * c + 4], v2[8 * c + 5]); pk.w = pack2(v2[8 * c + 6], v2[8 * c + 7]);
-                *reinterpret_cast<uint4*>(sk + op_chunk(row, c, 32)) = pk;
-            }
-        };
-        auto issue_s = [&]() {              // S = Q K^T, issued by the group itself: A = BF16 Q in TMEM, B = K in shared memory
-            tmem_st_wait();
-            tc_fence_before();
-            fence_async_smem();
-            group_barrier(ch);
-            if ((warp & 3) == 0 && lane == 0) {
-                tc_fence_after();
-                const uint32_t s_k = smem_u32(smem + OFF_K);
-#pragma unroll
-                for (int k = 0; k < 2; ++k)
-                    umma_bf16_ts(tmem + 128 * ch, tmem + 256 + 32 * ch + 8 * k,
-                                 umma_smem_desc(s_k + ch * 8192 + k * 256, 128, 512), umma_idesc_bf16(128, 128),
-                                 k > 0 ? 1u : 0u);
-                umma_commit(&bars[B_SR0 + ch]);
-            }
-            __syncwarp();
-        };
-        auto stage_vg = [&](int t) {        // V -> shared, MN-major [32 dims x 128 keys]; gate -> sigmoid(g) as BF16 pairs
-            mbar_wait(&bars[B_ACCVG], t & 1);
-            tc_fence_after();
-            float v2[32];
-            tmem_ld32_pair(pb + 128 + 32 * ch, v, pb + 192 + 32 * ch, v2);   // v and gate of this head
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint4 pk;
-                pk.x = pack2(v[8 * c], v[8 * c + 1]); pk.y = pack2(v[8 * c + 2], v[8 * c + 3]);
-                pk.z = pack2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack2(v[8 * c + 6], v[8 * c + 7]);
-                *reinterpret_cast<uint4*>(sv + c * 2048 + (row >> 3) * 128 + (row & 7) * 16) = pk;
-            }
-#pragma unroll
-            for (int c = 0; c < 16; ++c) gsig[c] = pack2(gate_factor(v2[2 * c]), gate_factor(v2[2 * c + 1]));
-            tc_fence_before();
-            fence_async_smem();             // (V must be visible to the tensor pipe before the barrier in front of O = P V)
-        };
-        stage_qk(0);
-        issue_s();
-        stage_vg(0);
-        // scores of a row against the S keys of its own gene: a window of the S tile that starts at the first gene touched
-        // by this warp (register indices stay compile-time, the column is warp-uniform)
-        constexpr int NC = (31 + S - 1) / S + 1;             // genes a 32-row warp can touch
-        constexpr int NW = NC * S;                            // window width in keys (<= 64)
-        for (int t = 0; t < 4; ++t) {
-            const int g_lo = (32 * lq) / S;
-            const int cand = gl - g_lo;                           // 0 .. NC-1
-            const float gamma = t == 0 ? gam[0] : t == 1 ? gam[1] : t == 2 ? gam[2] : gam[3];
-            float w[64];
-            mbar_wait(&bars[B_SR0 + ch], t & 1);
-            tc_fence_after();
-            warp_arrive(&bars[B_QKFREE], lane);                   // q / k columns are dead, v sits in shared memory, the gates in registers
-            {
-                const uint32_t sc0 = trow + 128 * ch + S * g_lo;
-                tmem_ld32(sc0, w);
-                if (NW > 48) tmem_ld32(sc0 + 32, w + 32);
-                else tmem_ld16(sc0 + 32, w + 32);
-            }
-            float s[SMAX];
-            float mx = -INFINITY;
-#pragma unroll
-            for (int j = 0; j < S; ++j) {
-                float sc = w[j];
-#pragma unroll
-                for (int c = 1; c < NC; ++c)
-                    if (cand == c) sc = w[c * S + j];
-                sc = fmaf(gamma, fr[j], sc * scale);
-                if ((mbits >> j) & 1u) sc = -1e9f;
-                s[j] = sc;
-                mx = fmaxf(mx, sc);
-            }
-            float sum = 0.f;
-#pragma unroll
-            for (int j = 0; j < S; ++j) { s[j] = __expf(s[j] - mx); sum += s[j]; }
-            const float inv = 1.f / sum;
-#pragma unroll
-            for (int j = 0; j < S; ++j) s[j] *= inv;
-            {   // P (BF16 pairs) over the first 64 columns of the S tile: zeros, then this warp's window
-                uint32_t W[32];
-#pragma unroll
-                for (int m = 0; m < 32; ++m) W[m] = 0u;
-                tmem_st32(trow + 128 * ch, W);
-                tmem_st32(trow + 128 * ch + 32, W);
-                tmem_st_wait();
-                const int kb = S * g_lo;
-                if (kb & 1) build_p_window<S, NC, 1>(s, cand, W);
-                else build_p_window<S, NC, 0>(s, cand, W);
-                tmem_st32(trow + 128 * ch + (kb >> 1), W);
-                tmem_st_wait();
-                tc_fence_before();
-                // O = P V, issued by the group: A = BF16 P in TMEM, B = V (MN-major, 32 dims x 128 keys)
-                group_barrier(ch);
-                if ((warp & 3) == 0 && lane == 0) {
-                    tc_fence_after();
-                    const uint32_t s_v = smem_u32(smem + OFF_V);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k)
-                        umma_bf16_ts(tmem + 128 * ch + 96, tmem + 128 * ch + 8 * k,
-                                     umma_smem_desc(s_v + ch * 8192 + k * 256, 128, 2048),
-                                     umma_idesc_bf16(128, 32) | (1u << 16), k > 0 ? 1u : 0u);
-                    umma_commit(&bars[B_OR0 + ch]);
-                }
-                __syncwarp();
-            }
-            if (t < 3) stage_qk(t + 1);                             // (while O = P V runs)
-            mbar_wait(&bars[B_OR0 + ch], t & 1);
-            tc_fence_after();
-            float o[32];
-            tmem_ld32(trow + 128 * ch + 96, o);                   // O = P V (last 32 columns of the S tile)
-            tc_fence_before();
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                float r[8];
-#pragma unroll
-                for (int e = 0; e < 8; e += 2) {
-                    const uint32_t gp = gsig[4 * c + (e >> 1)];
-                    r[e] = o[8 * c + e] * __uint_as_float(gp << 16);
-                    r[e + 1] = o[8 * c + e + 1] * __uint_as_float(gp & 0xffff0000u);
-                }
-                uint4 pk;
-                pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
-                *reinterpret_cast<uint4*>(smem + OFF_ATT + op_chunk(row, 8 * t + 4 * ch + c, 256)) = pk;
-            }
-            if (t < 3) {
-                issue_s();
-                stage_vg(t + 1);                                    // (while S = Q K^T runs)
-            }
-        }
         }
         fence_async_smem();
         warp_arrive(&bars[B_ATTREADY], lane);
@@ -768,6 +593,542 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_fused_kernel(const Re
     if (warp == 0) tmem_dealloc(tmem, 512);
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tensor-pipe attention variant (the default): 16 compute warps + 1 driver warp.
+//
+// TMEM lane quarter lq = warp & 3 (hardware rule); role = warp >> 2:
+//   role 0, 1  "score" warps of the two heads in flight (ch = role & 1): q -> BF16 A operand in TMEM, k -> shared,
+//              issue S = Q K^T, softmax on the gene's own S keys, P -> BF16 A operand in TMEM, issue O = P V;
+//   role 2, 3  "value" warps of the same two heads: v -> shared (MN-major), sigmoid(gate) kept in registers,
+//              O -> gate -> BF16 out-projection operand.
+// The two kinds of warps work on the SAME rows a head pair apart from each other in time: while the value warps gate
+// O(t), the score warps already repack q / k of pair t+1 — a software pipeline over the four head pairs of a layer.
+// In the epilogue phases (out-projection + LayerNorm, FFN-1, FFN-2 + LayerNorm) role = column quarter: every row is
+// served by four threads, 32 columns each (64 of the 256 FFN-1 columns), and FFN-1 / FFN-2 are chained per half of the
+// hidden width, so that one half's bias + ReLU epilogue runs under the other half's MMAs.
+constexpr int RF2_THREADS = 544;
+enum { C_FULL0 = 0, C_FREE0 = 3, C_XREADY = 6, C_ATTREADY, C_UREADY, C_FREADY0, C_FREADY1, C_ACCQ, C_ACCVG, C_ACCO, C_ACCF1A,
+       C_ACCF1B, C_ACCF2, C_QKFREE, C_VGFREE, C_SR0, C_OR0 = C_SR0 + 2, C_VR0 = C_OR0 + 2, C_OFREE0 = C_VR0 + 2,
+       C_COUNT = C_OFREE0 + 2 };
+static_assert(C_COUNT * 8 + 8 <= 256, "control block");
+
+__device__ __forceinline__ void all_compute_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+
+template <int SMAX>
+__global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const RegFusedArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_CTL);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C_COUNT);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int z = blockIdx.y, tile = blockIdx.x;
+    constexpr int S = SMAX;                                   // exact tokens per gene: no per-key predicates
+    const int G = a.G;
+    const long long row0 = (long long)tile * G * S;            // first token row of this tile
+    const int rows_valid = min((long long)G * S, (long long)a.B * S - row0);
+
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (tid == 0) {
+        for (int i = 0; i < RF_NSTAGE; ++i) { mbar_init(&bars[C_FULL0 + i], 1); mbar_init(&bars[C_FREE0 + i], 1); }
+        mbar_init(&bars[C_XREADY], 16); mbar_init(&bars[C_ATTREADY], 8); mbar_init(&bars[C_UREADY], 16);
+        mbar_init(&bars[C_FREADY0], 8); mbar_init(&bars[C_FREADY1], 8);
+        mbar_init(&bars[C_ACCQ], 1); mbar_init(&bars[C_ACCVG], 1); mbar_init(&bars[C_ACCO], 1);
+        mbar_init(&bars[C_ACCF1A], 1); mbar_init(&bars[C_ACCF1B], 1); mbar_init(&bars[C_ACCF2], 1);
+        mbar_init(&bars[C_QKFREE], 8); mbar_init(&bars[C_VGFREE], 8);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars[C_SR0 + i], 1); mbar_init(&bars[C_OR0 + i], 1);
+            mbar_init(&bars[C_VR0 + i], 4); mbar_init(&bars[C_OFREE0 + i], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 16) {
+        // ===================================================== driver: TMA + the dense tcgen05.mma ====
+        if (lane == 0) {
+            const __nv_bfloat16* wsrc = a.wstream + z * a.w_z;
+            const int n_chunks = RF_NCHUNK * a.n_layers;   // the layers' chunks follow each other in the stream
+            const uint32_t idesc = umma_idesc_bf16(128, 128);
+            const uint32_t s_xb = smem_u32(smem + OFF_XB), s_att = smem_u32(smem + OFF_ATT);
+            auto issue_load = [&](int c) {
+                const int st = c % RF_NSTAGE;
+                if (c >= RF_NSTAGE) mbar_wait(&bars[C_FREE0 + st], ((c / RF_NSTAGE) - 1) & 1);
+                mbar_expect_tx(&bars[C_FULL0 + st], RF_CHUNK_BYTES);
+                tma_bulk_g2s(smem + OFF_STAGE + st * RF_CHUNK_BYTES, wsrc + (long long)c * RF_CHUNK_ELEMS, RF_CHUNK_BYTES,
+                             &bars[C_FULL0 + st]);
+            };
+            auto consume = [&](int c, uint32_t a_addr, uint32_t a_sbo, uint32_t col, bool accumulate) {
+                const int st = c % RF_NSTAGE;
+                mbar_wait(&bars[C_FULL0 + st], (c / RF_NSTAGE) & 1);
+                tc_fence_after();
+                const uint32_t b_addr = smem_u32(smem + OFF_STAGE + st * RF_CHUNK_BYTES);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(tmem + col, umma_smem_desc(a_addr + k * 256, 128, a_sbo),
+                              umma_smem_desc(b_addr + k * 256, 128, 2048), idesc, (accumulate || k > 0) ? 1u : 0u);
+                umma_commit(&bars[C_FREE0 + st]);
+                // refill the ring behind the MMAs just queued (waits for chunk c-1 only)
+                if (c + 2 < n_chunks && c >= 1) issue_load(c + 2);
+            };
+            issue_load(0);
+            issue_load(1);
+            issue_load(2);
+            for (int li = 0; li < a.n_layers; ++li) {
+                const int cb = li * RF_NCHUNK;
+                const uint32_t lp = li & 1;
+                mbar_wait(&bars[C_XREADY], lp);
+                // TMEM [0,128) / [128,256): S, then P (first 64..77 columns) and O (last 32) of the two heads in flight;
+                // [256,512): projection pair (q0 q1 k0 k1 v0 v1 g0 g1, 32 columns each).  [q | k] and [v | gate] of the
+                // next pair are projected as soon as their readers are done with the columns.
+                consume(cb, s_xb, 2048, 256, false);
+                umma_commit(&bars[C_ACCQ]);
+                consume(cb + 1, s_xb, 2048, 384, false);
+                umma_commit(&bars[C_ACCVG]);
+                for (int t = 0; t < 3; ++t) {
+                    mbar_wait(&bars[C_QKFREE], t & 1);
+                    consume(cb + 2 * t + 2, s_xb, 2048, 256, false);        // next [q | k]
+                    umma_commit(&bars[C_ACCQ]);
+                    mbar_wait(&bars[C_VGFREE], t & 1);
+                    consume(cb + 2 * t + 3, s_xb, 2048, 384, false);        // next [v | gate]
+                    umma_commit(&bars[C_ACCVG]);
+                }
+                mbar_wait(&bars[C_ATTREADY], lp);
+                consume(cb + 8, s_att, 4096, 0, false);                     // out-projection, K halves
+                consume(cb + 9, s_att + 2048, 4096, 0, true);
+                umma_commit(&bars[C_ACCO]);
+                mbar_wait(&bars[C_UREADY], lp);
+                consume(cb + 10, s_xb, 2048, 256, false);                   // FFN-1, hidden half A
+                umma_commit(&bars[C_ACCF1A]);
+                consume(cb + 11, s_xb, 2048, 384, false);                   // FFN-1, hidden half B
+                umma_commit(&bars[C_ACCF1B]);
+                mbar_wait(&bars[C_FREADY0], lp);
+                consume(cb + 12, s_att, 4096, 0, false);                    // FFN-2 over hidden half A
+                mbar_wait(&bars[C_FREADY1], lp);
+                consume(cb + 13, s_att + 2048, 4096, 0, true);              // ... + half B
+                umma_commit(&bars[C_ACCF2]);
+            }   // layers
+        }
+    } else {
+        // ===================================================== compute warps =================
+        const int lq = warp & 3, role = warp >> 2;
+        const int ch = role & 1;                             // head of the pair (attention)
+        const bool score_warp = role < 2;
+        const int cq = role;                                 // column quarter (epilogues)
+        const int row = lq * 32 + lane;                      // tile row == TMEM lane
+        const bool valid = row < rows_valid;
+        const long long grow = row0 + row;
+        const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
+        const float* X = a.x + z * a.x_z;
+        float v[32];
+
+        // ---- phase 0 (first layer only; later layers get their operand from phase 4): X -> BF16 operand
+        {
+            float4 x[4][2];                                   // all 8 loads of the thread in flight at once
+            int r_[4], kc_[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int u = warp + q * 16;                  // 64 (8-row group, 4-chunk group) items
+                r_[q] = (u & 15) * 8 + (lane >> 2);
+                kc_[q] = (u >> 4) * 4 + (lane & 3);
+                x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (r_[q] < rows_valid) {
+                    const float* p = X + (row0 + r_[q]) * 128 + kc_[q] * 8;
+                    x[q][0] = __ldg(reinterpret_cast<const float4*>(p));
+                    x[q][1] = __ldg(reinterpret_cast<const float4*>(p + 4));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 pk;
+                pk.x = pack2(x[q][0].x, x[q][0].y); pk.y = pack2(x[q][0].z, x[q][0].w);
+                pk.z = pack2(x[q][1].x, x[q][1].y); pk.w = pack2(x[q][1].z, x[q][1].w);
+                *reinterpret_cast<uint4*>(smem + OFF_XB + op_chunk(r_[q], kc_[q], 128)) = pk;
+            }
+            fence_async_smem();
+            warp_arrive(&bars[C_XREADY], lane);
+        }
+
+        const int gl = row / S, qi = row % S;                 // gene within tile, query token
+        const long long gene = (long long)tile * G + gl;
+        const float scale = 0.17677669529663687f;            // 1/sqrt(32)
+        float fr[SMAX];
+        unsigned mbits = 0;
+        if (score_warp) {
+            const float* freq = a.freq + (valid ? (gene * S + qi) * S : 0);
+            const uint8_t* mask = a.imask[z] + (valid ? (gene * S + qi) * S : 0);
+#pragma unroll
+            for (int j = 0; j < SMAX; ++j) {
+                fr[j] = 0.f;
+                if (valid) {
+                    fr[j] = freq[j];
+                    if (mask[j]) mbits |= 1u << j;
+                }
+            }
+        }
+        uint8_t* sk = smem + OFF_K + ch * 8192;
+        uint8_t* sv = smem + OFF_V + ch * 8192;
+        const uint32_t pb = trow + 256;
+        const bool elected = lq == 0 && lane == 0;            // issues this head's S / O instructions
+
+        for (int li = 0; li < a.n_layers; ++li) {
+        const uint32_t lp = li & 1;
+        const long long po = z * a.p_z + li * a.p_l;          // this (resolution, layer)'s parameters
+
+        // ---- phase 1: attention, four head pairs
+        if (score_warp) {
+            float gam[4];
+#pragma unroll
+            for (int t = 0; t < 4; ++t) gam[t] = a.gamma_f[po + 2 * t + ch];
+            auto stage_qk = [&](int t) {    // Q -> BF16 back into TMEM in place (A operand of S = Q K^T); K -> shared, K-major
+                mbar_wait(&bars[C_ACCQ], t & 1);
+                tc_fence_after();
+                uint32_t qp[16];
+                float v2[32];
+                tmem_ld32_pair(pb + 32 * ch, v, pb + 64 + 32 * ch, v2);    // q and k of this head, both loads in flight
+#pragma unroll
+                for (int c = 0; c < 16; ++c) qp[c] = pack2(v[2 * c], v[2 * c + 1]);
+                tmem_st16(pb + 32 * ch, qp);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4 pk;
+                    pk.x = pack2(v2[8 * c], v2[8 * c + 1]); pk.y = pack2(v2[8 * c + 2], v2[8 * c + 3]);
+                    pk.z = pack2(v2[8 * c + 4], v2[8 * c + 5]); pk.w = pack2(v2[8 * c + 6], v2[8 * c + 7]);
+                    *reinterpret_cast<uint4*>(sk + op_chunk(row, c, 32)) = pk;
+                }
+            };
+            auto issue_s = [&](int t) {     // S = Q K^T: A = BF16 Q in TMEM, B = K in shared memory
+                tmem_st_wait();
+                tc_fence_before();
+                fence_async_smem();
+                group_barrier(ch);
+                if (elected) {
+                    if (t > 0) mbar_wait(&bars[C_OFREE0 + ch], (t - 1) & 1);    // O(t-1) has been read out of this tile
+                    tc_fence_after();
+                    const uint32_t s_k = smem_u32(smem + OFF_K);
+#pragma unroll
+                    for (int k = 0; k < 2; ++k)
+                        umma_bf16_ts(tmem + 128 * ch, tmem + 256 + 32 * ch + 8 * k,
+                                     umma_smem_desc(s_k + ch * 8192 + k * 256, 128, 512), umma_idesc_bf16(128, 128),
+                                     k > 0 ? 1u : 0u);
+                    umma_commit(&bars[C_SR0 + ch]);
+                }
+                __syncwarp();
+            };
+            stage_qk(0);
+            issue_s(0);
+            // scores of a row against the S keys of its own gene: a window of the S tile that starts at the first gene touched
+            // by this warp (register indices stay compile-time, the column is warp-uniform)
+            constexpr int NC = (31 + S - 1) / S + 1;             // genes a 32-row warp can touch
+            constexpr int NW = NC * S;                            // window width in keys (<= 64)
+            const int g_lo = (32 * lq) / S;
+            const int cand = gl - g_lo;                           // 0 .. NC-1
+#pragma unroll 1
+            for (int t = 0; t < 4; ++t) {
+                const float gamma = t == 0 ? gam[0] : t == 1 ? gam[1] : t == 2 ? gam[2] : gam[3];
+                float w[64];
+                mbar_wait(&bars[C_SR0 + ch], t & 1);
+                tc_fence_after();
+                warp_arrive(&bars[C_QKFREE], lane);               // q / k columns are dead: the next [q | k] may be projected
+                {
+                    const uint32_t sc0 = trow + 128 * ch + S * g_lo;
+                    if (NW > 48) tmem_ld32_pair(sc0, w, sc0 + 32, w + 32);
+                    else { tmem_ld32(sc0, w); tmem_ld16(sc0 + 32, w + 32); }
+                }
+                float s[SMAX];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    float sc = w[j];
+#pragma unroll
+                    for (int c = 1; c < NC; ++c)
+                        if (cand == c) sc = w[c * S + j];
+                    sc = fmaf(gamma, fr[j], sc * scale);
+                    if ((mbits >> j) & 1u) sc = -1e9f;
+                    s[j] = sc;
+                    mx = fmaxf(mx, sc);
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < S; ++j) { s[j] = __expf(s[j] - mx); sum += s[j]; }
+                const float inv = 1.f / sum;
+#pragma unroll
+                for (int j = 0; j < S; ++j) s[j] *= inv;
+                {   // P (BF16 pairs) over the first 64 columns of the S tile: zeros, then this warp's window
+                    uint32_t W[32];
+#pragma unroll
+                    for (int m = 0; m < 32; ++m) W[m] = 0u;
+                    tmem_st32(trow + 128 * ch, W);
+                    tmem_st32(trow + 128 * ch + 32, W);
+                    tmem_st_wait();
+                    const int kb = S * g_lo;
+                    if (kb & 1) build_p_window<S, NC, 1>(s, cand, W);
+                    else build_p_window<S, NC, 0>(s, cand, W);
+                    tmem_st32(trow + 128 * ch + (kb >> 1), W);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    // O = P V: A = BF16 P in TMEM, B = V (MN-major, 32 dims x 128 keys) staged by the value warps
+                    group_barrier(ch);
+                    if (elected) {
+                        mbar_wait(&bars[C_VR0 + ch], t & 1);
+                        tc_fence_after();
+                        const uint32_t s_v = smem_u32(smem + OFF_V);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k)
+                            umma_bf16_ts(tmem + 128 * ch + 96, tmem + 128 * ch + 8 * k,
+                                         umma_smem_desc(s_v + ch * 8192 + k * 256, 128, 2048),
+                                         umma_idesc_bf16(128, 32) | (1u << 16), k > 0 ? 1u : 0u);
+                        umma_commit(&bars[C_OR0 + ch]);
+                    }
+                    __syncwarp();
+                }
+                if (t < 3) {
+                    stage_qk(t + 1);                                // (while O = P V runs and the value warps gate it)
+                    issue_s(t + 1);
+                }
+            }
+        } else {
+            uint32_t vp[16], gsig[16];
+            auto load_vg = [&](int t) {     // v -> BF16 pairs (for the MN-major B operand of O = P V); sigmoid(gate) as BF16 pairs
+                mbar_wait(&bars[C_ACCVG], t & 1);
+                tc_fence_after();
+                float v2[32];
+                tmem_ld32_pair(pb + 128 + 32 * ch, v, pb + 192 + 32 * ch, v2);   // v and gate of this head
+                tc_fence_before();
+                warp_arrive(&bars[C_VGFREE], lane);               // the next [v | gate] may be projected
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    vp[c] = pack2(v[2 * c], v[2 * c + 1]);
+                    gsig[c] = pack2(gate_factor(v2[2 * c]), gate_factor(v2[2 * c + 1]));
+                }
+            };
+            auto store_v = [&]() {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    *reinterpret_cast<uint4*>(sv + c * 2048 + (row >> 3) * 128 + (row & 7) * 16) =
+                        make_uint4(vp[4 * c], vp[4 * c + 1], vp[4 * c + 2], vp[4 * c + 3]);
+                fence_async_smem();             // (V must be visible to the tensor pipe before O = P V is issued)
+                warp_arrive(&bars[C_VR0 + ch], lane);
+            };
+            load_vg(0);
+            store_v();
+#pragma unroll 1
+            for (int t = 0; t < 4; ++t) {
+                uint32_t gcur[16];
+#pragma unroll
+                for (int c = 0; c < 16; ++c) gcur[c] = gsig[c];
+                if (t < 3) load_vg(t + 1);                          // v, gates of the next pair wait in registers
+                mbar_wait(&bars[C_OR0 + ch], t & 1);
+                tc_fence_after();
+                float o[32];
+                tmem_ld32(trow + 128 * ch + 96, o);               // O = P V (last 32 columns of the S tile)
+                tc_fence_before();
+                warp_arrive(&bars[C_OFREE0 + ch], lane);          // the tile may take the next S
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float r[8];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        const uint32_t gp = gcur[4 * c + (e >> 1)];
+                        r[e] = o[8 * c + e] * __uint_as_float(gp << 16);
+                        r[e + 1] = o[8 * c + e + 1] * __uint_as_float(gp & 0xffff0000u);
+                    }
+                    uint4 pk;
+                    pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
+                    *reinterpret_cast<uint4*>(smem + OFF_ATT + op_chunk(row, 8 * t + 4 * ch + c, 256)) = pk;
+                }
+                if (t < 3) store_v();                               // O(t) is complete: V(t) may be overwritten
+            }
+            fence_async_smem();
+            warp_arrive(&bars[C_ATTREADY], lane);
+        }
+
+        // residual rows of phase 2 (FP32), 32 columns per thread: issued now so that their latency hides behind the
+        // out-projection MMA; u_keep then carries U and is the residual of phase 4.  First layer: the caller's row-major X.
+        // Later layers: what THIS thread parked in the scratch slot at the end of the previous layer, in a lane-major order
+        // (float4 index (cq*8 + j/4)*128 + row inside the tile's 64 KB block): every warp access is 512 contiguous bytes.
+        float u_keep[32];
+        if (li == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                float4 r4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (valid) r4 = __ldg(reinterpret_cast<const float4*>(X + grow * 128 + 32 * cq + j));
+                u_keep[j] = r4.x; u_keep[j + 1] = r4.y; u_keep[j + 2] = r4.z; u_keep[j + 3] = r4.w;
+            }
+        } else {
+            const float4* park = reinterpret_cast<const float4*>(a.y_mid + z * a.y_mid_z + ((li - 1) & 1) * a.y_l) +
+                                 (long long)tile * 4096 + row;
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 r4 = __ldcg(park + (cq * 8 + (j >> 2)) * 128);
+                u_keep[j] = r4.x; u_keep[j + 1] = r4.y; u_keep[j + 2] = r4.z; u_keep[j + 3] = r4.w;
+            }
+        }
+        // small FP32 vectors of the layer -> shared (k, v are dead once every value warp has passed its last O):
+        // bo, ln1w, ln1b, b2, ln2w, ln2b, b1[256]
+        float* prm = reinterpret_cast<float*>(smem + OFF_V);
+        all_compute_barrier();
+        {
+            const float* srcs[6] = {a.bo, a.ln1w, a.ln1b, a.b2, a.ln2w, a.ln2b};
+            const int ct = warp * 32 + lane;                  // 0..511
+#pragma unroll
+            for (int k = 0; k < 6; ++k)
+                if ((ct >> 7) == (k >> 1)) prm[k * 128 + (ct & 127)] = srcs[k][po + (ct & 127)];
+            if (ct >= 256) prm[768 + ct - 256] = a.b1[po + ct - 256];
+        }
+        all_compute_barrier();
+        // ---- phase 2: out-projection epilogue: + bias + residual, LayerNorm -> U
+        float* red = reinterpret_cast<float*>(smem + OFF_K);  // [4][128][2] partial sums (k is dead)
+        const int c0 = 32 * cq;
+        {
+            mbar_wait(&bars[C_ACCO], lp);
+            tc_fence_after();
+            const float* bo = prm;
+            float sum = 0.f, sq = 0.f;
+            tmem_ld32(trow + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(bo + c0 + j);
+                const float t0 = v[j] + b4.x + u_keep[j], t1 = v[j + 1] + b4.y + u_keep[j + 1];
+                const float t2 = v[j + 2] + b4.z + u_keep[j + 2], t3 = v[j + 3] + b4.w + u_keep[j + 3];
+                u_keep[j] = t0; u_keep[j + 1] = t1; u_keep[j + 2] = t2; u_keep[j + 3] = t3;
+                sum += (t0 + t1) + (t2 + t3);
+                sq += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
+            }
+            tc_fence_before();
+            *reinterpret_cast<float2*>(red + (cq * 128 + row) * 2) = make_float2(sum, sq);
+            all_compute_barrier();
+            sum = 0.f; sq = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 p2 = *reinterpret_cast<const float2*>(red + (k * 128 + row) * 2);
+                sum += p2.x; sq += p2.y;
+            }
+            const float mean = sum * (1.f / 128.f);
+            const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
+            const float* lw = prm + 128;
+            const float* lb = prm + 256;
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+                float r[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    r[e] = (u_keep[j + e] - mean) * rstd * lw[c0 + j + e] + lb[c0 + j + e];
+                    u_keep[j + e] = r[e];
+                }
+                uint4 pk;
+                pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
+                *reinterpret_cast<uint4*>(smem + OFF_XB + op_chunk(row, (c0 + j) >> 3, 128)) = pk;
+            }
+            fence_async_smem();
+            warp_arrive(&bars[C_UREADY], lane);
+        }
+
+        // ---- phase 3: FFN-1 epilogue: + bias, ReLU -> BF16 operand (over the dead att tile); 64 hidden columns per thread,
+        //      the two halves of the hidden width are committed (and handed to FFN-2) separately
+        {
+            mbar_wait(&bars[cq < 2 ? C_ACCF1A : C_ACCF1B], lp);
+            tc_fence_after();
+            const float* b1 = prm + 768;
+            const int h0 = 64 * cq;
+            float v2[32];
+            tmem_ld32_pair(trow + 256 + h0, v, trow + 256 + h0 + 32, v2);
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const float* vv = half ? v2 : v;
+                const int c = h0 + 32 * half;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    float r[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) r[e] = fmaxf(vv[j + e] + b1[c + j + e], 0.f);
+                    uint4 pk;
+                    pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
+                    *reinterpret_cast<uint4*>(smem + OFF_ATT + op_chunk(row, (c + j) >> 3, 256)) = pk;
+                }
+            }
+            tc_fence_before();
+            fence_async_smem();
+            warp_arrive(&bars[cq < 2 ? C_FREADY0 : C_FREADY1], lane);
+        }
+
+        // ---- phase 4: FFN-2 epilogue: + bias + U, LayerNorm -> Y (coalesced through shared)
+        {
+            mbar_wait(&bars[C_ACCF2], lp);
+            tc_fence_after();
+            const float* b2 = prm + 384;
+            float* red2 = red + 1024;
+            float sum = 0.f, sq = 0.f;
+            tmem_ld32(trow + c0, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+                const float t0 = v[j] + b2[c0 + j] + u_keep[j];
+                u_keep[j] = t0;
+                sum += t0;
+                sq += t0 * t0;
+            }
+            tc_fence_before();
+            *reinterpret_cast<float2*>(red2 + (cq * 128 + row) * 2) = make_float2(sum, sq);
+            all_compute_barrier();
+            sum = 0.f; sq = 0.f;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float2 p2 = *reinterpret_cast<const float2*>(red2 + (k * 128 + row) * 2);
+                sum += p2.x; sq += p2.y;
+            }
+            const float mean = sum * (1.f / 128.f);
+            const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
+            const float* lw = prm + 512;
+            const float* lb = prm + 640;
+            const bool more = li + 1 < a.n_layers;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) u_keep[j] = (u_keep[j] - mean) * rstd * lw[c0 + j] + lb[c0 + j];
+            if (more) {
+                // Y is the next layer's operand (BF16, over X in shared memory) and residual (FP32, parked in the scratch
+                // slot by the thread that will read it back, lane-major).  Operand first: the driver starts the next
+                // layer's projections on C_XREADY while the rows are being parked.  (No CTA barrier is needed for prm / red:
+                // nobody gets past the next all_compute_barrier before every warp has arrived there.)
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint4 pk;
+                    pk.x = pack2(u_keep[j], u_keep[j + 1]); pk.y = pack2(u_keep[j + 2], u_keep[j + 3]);
+                    pk.z = pack2(u_keep[j + 4], u_keep[j + 5]); pk.w = pack2(u_keep[j + 6], u_keep[j + 7]);
+                    *reinterpret_cast<uint4*>(smem + OFF_XB + op_chunk(row, (c0 + j) >> 3, 128)) = pk;
+                }
+                fence_async_smem();
+                warp_arrive(&bars[C_XREADY], lane);
+                float4* park = reinterpret_cast<float4*>(a.y_mid + z * a.y_mid_z + (li & 1) * a.y_l) + (long long)tile * 4096 + row;
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    __stcg(park + (cq * 8 + (j >> 2)) * 128, make_float4(u_keep[j], u_keep[j + 1], u_keep[j + 2], u_keep[j + 3]));
+            } else {
+                // last layer: Y row-major to the caller, coalesced through a shared-memory transpose.  16 warps x 4224 B
+                // run from the att tile into the (by now idle) weight ring: every MMA of the launch is complete.
+                float* Y = a.y + z * a.y_z;
+                float* stage = reinterpret_cast<float*>(smem + OFF_ATT) + warp * (32 * 33);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) stage[lane * 33 + j] = u_keep[j];
+                __syncwarp();
+                const int cc = (lane & 7) * 4;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + (lane >> 3);
+                    const float* sp = stage + r * 33 + cc;
+                    const int trw = lq * 32 + r;
+                    if (trw < rows_valid)
+                        *reinterpret_cast<float4*>(Y + (row0 + trw) * 128 + c0 + cc) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                }
+            }
+        }
+        }   // layers
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 512);
+}
+
 // ---------------------------------------------------------------- weight stream ----
 // 14 chunks of [128 rows x 128 k] BF16 per (resolution, layer) in UMMA tile order, in the order
 // the kernel consumes them (see the header comment).
@@ -815,23 +1176,24 @@ bool reg_fused_tensor_attention() {
 int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e1 = cudaFuncSetAttribute(reg_layer_fused_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
-        cudaError_t e2 = cudaFuncSetAttribute(reg_layer_fused_kernel<17, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
-        cudaFuncSetAttribute(reg_layer_fused_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
-        cudaFuncSetAttribute(reg_layer_fused_kernel<17, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
-        if (e1 != cudaSuccess || e2 != cudaSuccess) { set_error("reg_fused smem attribute: %s", cudaGetErrorString(e1 != cudaSuccess ? e1 : e2)); return CHROMO_ECUDA; }
+        cudaError_t e1 = cudaFuncSetAttribute(reg_layer_cc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaError_t e2 = cudaFuncSetAttribute(reg_layer_cc_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaError_t e3 = cudaFuncSetAttribute(reg_layer_fused_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaError_t e4 = cudaFuncSetAttribute(reg_layer_fused_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        for (cudaError_t e : {e1, e2, e3, e4})
+            if (e != cudaSuccess) { set_error("reg_fused smem attribute: %s", cudaGetErrorString(e)); return CHROMO_ECUDA; }
         configured = true;
     }
     dim3 grid(a.n_tiles, n_res);
     // Attention on the tensor pipe (block-diagonal Q K^T / P V with Q and P rounded to BF16, as in every flash-attention
-    // kernel) is the default: 14 % faster, max |logit error| 4.7e-3 vs 4.5e-3 for the CUDA-core attention on the demo set
-    // (profiles/r01_precision.md).  CHROMO_REG_TC=0 selects the CUDA-core variant (FP32 q and probabilities).
+    // kernel) is the default (profiles/r01_precision.md).  CHROMO_REG_TC=0 selects the CUDA-core variant (FP32 q and
+    // probabilities, one layer per launch).
     const int tc = reg_fused_tensor_attention() ? 1 : 0;
     if (a.n_layers < 1 || (a.n_layers > 1 && !tc)) { set_error("reg_layer_fused: multi-layer launches need the tensor-pipe attention"); return CHROMO_EINVAL; }
-    if (a.S == 9 && tc) reg_layer_fused_kernel<9, true><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
-    else if (a.S == 9) reg_layer_fused_kernel<9, false><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
-    else if (a.S == 17 && tc) reg_layer_fused_kernel<17, true><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
-    else if (a.S == 17) reg_layer_fused_kernel<17, false><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
+    if (a.S == 9 && tc) reg_layer_fused_kernel<9><<<grid, RF2_THREADS, RF_SMEM, st>>>(a);
+    else if (a.S == 9) reg_layer_cc_kernel<9><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
+    else if (a.S == 17 && tc) reg_layer_fused_kernel<17><<<grid, RF2_THREADS, RF_SMEM, st>>>(a);
+    else if (a.S == 17) reg_layer_cc_kernel<17><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
     else { set_error("reg_layer_fused: tokens per gene must be 9 or 17"); return CHROMO_EINVAL; }
     CHROMO_CHECK_LAUNCH("reg_layer_fused");
     return CHROMO_OK;

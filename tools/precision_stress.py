@@ -45,7 +45,20 @@ def measure(name, model, batch, n_oracle=64):
             "median_abs_margin": margin.median().item()}
 
 
+def stress_model():
+    m = ChromoformerClassifier(seed=123)
+    with torch.no_grad():
+        for name, p in m.named_parameters():
+            if p.dim() == 2:
+                p.mul_(8.0 if name == "fc_head.2.weight" else 2.0)
+    return m.cuda()
+
+
 def main():
+    child = os.environ.get("CHROMO_PRECISION_CHILD")
+    if child is not None:
+        print(json.dumps(measure(child, stress_model(), synthetic.make_batch(N, ragged=True, seed=17, stress=True))))
+        return
     rows = []
     m = ChromoformerClassifier(seed=123).cuda()
     rows.append(measure("untrained (seed 123), ragged genes", m, synthetic.make_batch(N, ragged=True, seed=17)))
@@ -69,11 +82,25 @@ def main():
         lo = (it * 64) % 4096
         step(synthetic.slice_batch(dev, lo, lo + 64), labels[lo:lo + 64])
     rows.append(measure("trained 200 steps (synthetic rule), ragged genes", m, synthetic.make_batch(N, ragged=True, seed=18)))
+    # where does the stress-weight error come from?  One stage at a time kept on the FP32 CUDA-core GEMMs
+    if os.environ.get("CHROMO_PRECISION_CHILD") is None:
+        import subprocess
+        for tag, env in (("stress, head GEMMs in FP32 (CHROMO_HEAD_FP32)", {"CHROMO_HEAD_FP32": "1"}),
+                         ("stress, Regulation stack in FP32 (CHROMO_REG_FP32)", {"CHROMO_REG_FP32": "1"}),
+                         ("stress, Regulation + head in FP32", {"CHROMO_REG_FP32": "1", "CHROMO_HEAD_FP32": "1"}),
+                         ("stress, Regulation attention on CUDA cores (CHROMO_REG_TC=0)", {"CHROMO_REG_TC": "0"}),
+                         ("stress, unfused single-query attention (CHROMO_NO_SQA_FUSED)", {"CHROMO_NO_SQA_FUSED": "1"})):
+            e = dict(os.environ, CHROMO_PRECISION_CHILD=tag, **env)
+            out = subprocess.run([sys.executable, os.path.abspath(__file__)], env=e, capture_output=True, text=True)
+            try:
+                rows.append(json.loads(out.stdout.strip().splitlines()[-1]))
+            except Exception:                                   # noqa: BLE001
+                rows.append({"weights": tag, "error": out.stderr[-300:]})
     keys = list(rows[0].keys())
     print("| " + " | ".join(keys) + " |")
     print("|" + "---|" * len(keys))
     for r in rows:
-        print("| " + " | ".join(("%.3e" % v if isinstance(v, float) else str(v)) for v in r.values()) + " |")
+        print("| " + " | ".join(("%.3e" % r[k] if isinstance(r.get(k), float) else str(r.get(k))) for k in keys) + " |")
     if len(sys.argv) > 1:
         json.dump(rows, open(sys.argv[1], "w"), indent=1)
 
