@@ -78,6 +78,7 @@ EXPORTS = {
                                                 c_float, c_void_p, c_void_p, c_int64, c_void_p]),
     "chromo_pack_linear_weight": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p]),
     "chromo_launch_counter": (c_int64, [c_int32]),
+    "chromo_debug_trace": (c_int32, [c_void_p]),
     "chromo_debug_umma_probe": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "chromo_backward": (c_int32, [POINTER(Config), c_void_p, POINTER(Batch), c_void_p, c_void_p, c_void_p,
                                   c_int64, c_int32, c_void_p]),
@@ -85,6 +86,8 @@ EXPORTS = {
     "chromo_ce_loss": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
     "chromo_adamw": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                c_float, c_float, c_int32, c_float, c_void_p]),
+    "chromo_unpack_wire": (c_int32, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int32,
+                                     POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "chromo_bin_regions": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(c_int32),
                                      POINTER(c_int32), POINTER(c_void_p), c_void_p, c_void_p]),
 }

@@ -293,3 +293,77 @@ extern "C" int chromo_bin_regions(const uint16_t* raw, const chromo_region_t* re
     CHROMO_CHECK_LAUNCH("bin_regions");
     return CHROMO_OK;
 }
+
+// ------------------------------------------------------------------ FP16 feature wire ----
+// Host -> device transport of a gene batch at half the bytes of the reference's (run_demo.py:100-105 ships FP32
+// features + n x n boolean masks): features travel as FP16 (the raw depth is FP16 on disk; ln(mean + 1) <= 11 fits
+// with 2^-11 relative rounding), pad masks as (first valid bin, count) spans.  One launch widens every feature tensor
+// back to the FP32 layout the forward consumes and expands the spans to centre-row masks.
+namespace chromo {
+
+constexpr int WIRE_MAX = 8;
+struct WireArgs {
+    int n_seg, n_sets;
+    const __half* src[WIRE_MAX]; float* dst[WIRE_MAX]; long long count[WIRE_MAX];
+    const int* spans[WIRE_MAX]; uint8_t* mask[WIRE_MAX]; int rows[WIRE_MAX]; int n[WIRE_MAX];
+};
+
+__global__ void __launch_bounds__(256) unpack_wire_kernel(const WireArgs a) {
+    const int seg = blockIdx.y;
+    const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x, nthr = (long long)gridDim.x * blockDim.x;
+    if (seg < a.n_seg) {
+        const __half* src = a.src[seg];
+        float* dst = a.dst[seg];
+        const long long n8 = a.count[seg] >> 3;
+        for (long long i = tid; i < n8; i += nthr) {
+            const uint4 h = __ldg(reinterpret_cast<const uint4*>(src) + i);
+            const __half2* h2 = reinterpret_cast<const __half2*>(&h);
+            const float2 f0 = __half22float2(h2[0]), f1 = __half22float2(h2[1]);
+            const float2 f2 = __half22float2(h2[2]), f3 = __half22float2(h2[3]);
+            float4* o = reinterpret_cast<float4*>(dst) + 2 * i;
+            o[0] = make_float4(f0.x, f0.y, f1.x, f1.y);
+            o[1] = make_float4(f2.x, f2.y, f3.x, f3.y);
+        }
+        for (long long i = (n8 << 3) + tid; i < a.count[seg]; i += nthr) dst[i] = __half2float(src[i]);
+    } else {
+        const int set = seg - a.n_seg;
+        const int n = a.n[set];
+        const long long total = (long long)a.rows[set] * n;
+        for (long long i = tid; i < total; i += nthr) {
+            const int row = (int)(i / n), p = (int)(i - (long long)row * n);
+            const int lo = a.spans[set][2 * row], cnt = a.spans[set][2 * row + 1];
+            a.mask[set][i] = (p >= lo && p < lo + cnt) ? 0 : 1;
+        }
+    }
+}
+
+}  // namespace chromo
+
+extern "C" int chromo_unpack_wire(int32_t n_seg, const uint16_t* const* src, float* const* dst, const int64_t* counts,
+                                  int32_t n_sets, const int32_t* const* spans, uint8_t* const* masks,
+                                  const int32_t* rows, const int32_t* n_bins, void* stream) {
+    using namespace chromo;
+    if (n_seg < 0 || n_seg > WIRE_MAX || n_sets < 0 || n_sets > WIRE_MAX) { set_error("unpack_wire: at most %d segments / span sets", WIRE_MAX); return CHROMO_EINVAL; }
+    if (n_seg + n_sets == 0) return CHROMO_OK;
+    WireArgs a;
+    a.n_seg = n_seg; a.n_sets = n_sets;
+    long long most = 0;
+    for (int i = 0; i < n_seg; ++i) {
+        if (!src[i] || !dst[i] || counts[i] < 0) { set_error("unpack_wire: bad segment %d", i); return CHROMO_EINVAL; }
+        if ((reinterpret_cast<uintptr_t>(src[i]) | reinterpret_cast<uintptr_t>(dst[i])) & 15) { set_error("unpack_wire: segment %d is not 16-byte aligned", i); return CHROMO_EINVAL; }
+        a.src[i] = reinterpret_cast<const __half*>(src[i]); a.dst[i] = dst[i]; a.count[i] = counts[i];
+        most = counts[i] / 8 > most ? counts[i] / 8 : most;
+    }
+    for (int i = 0; i < n_sets; ++i) {
+        if (!spans[i] || !masks[i] || rows[i] < 0 || n_bins[i] < 1) { set_error("unpack_wire: bad span set %d", i); return CHROMO_EINVAL; }
+        a.spans[i] = spans[i]; a.mask[i] = masks[i]; a.rows[i] = rows[i]; a.n[i] = n_bins[i];
+        const long long t = (long long)rows[i] * n_bins[i];
+        most = t > most ? t : most;
+    }
+    long long blocks = (most + 255) / 256;
+    if (blocks > 148 * 8) blocks = 148 * 8;           // grid-stride: 8 CTAs per SM cover the widest segment
+    if (blocks < 1) blocks = 1;
+    unpack_wire_kernel<<<dim3((unsigned)blocks, n_seg + n_sets), 256, 0, (cudaStream_t)stream>>>(a);
+    CHROMO_CHECK_LAUNCH("unpack_wire");
+    return CHROMO_OK;
+}

@@ -613,6 +613,14 @@ enum { C_FULL0 = 0, C_FREE0 = 3, C_XREADY = 6, C_ATTREADY, C_UREADY, C_FREADY0, 
        C_COUNT = C_OFREE0 + 2 };
 static_assert(C_COUNT * 8 + 8 <= 256, "control block");
 
+// timeline hook: four traced threads of CTA (0,0) (driver, one score warp, one value warp, warp 0 in the epilogues) append
+// (event id << 48 | clock64) to their own 512-entry lane of a.trace
+struct Tracer {
+    long long* p; int n;
+    __device__ __forceinline__ void operator()(int id) {
+        if (p && n < 512) { p[n++] = ((long long)id << 48) | (clock64() & 0xFFFFFFFFFFFFll); }
+    }
+};
 __device__ __forceinline__ void all_compute_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 template <int SMAX>
@@ -676,39 +684,54 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             issue_load(0);
             issue_load(1);
             issue_load(2);
+            Tracer tr{(a.trace && tile == 0 && z == 0) ? a.trace : nullptr, 0};
             for (int li = 0; li < a.n_layers; ++li) {
                 const int cb = li * RF_NCHUNK;
                 const uint32_t lp = li & 1;
                 mbar_wait(&bars[C_XREADY], lp);
+                tr(1);
                 // TMEM [0,128) / [128,256): S, then P (first 64..77 columns) and O (last 32) of the two heads in flight;
                 // [256,512): projection pair (q0 q1 k0 k1 v0 v1 g0 g1, 32 columns each).  [q | k] and [v | gate] of the
                 // next pair are projected as soon as their readers are done with the columns.
                 consume(cb, s_xb, 2048, 256, false);
                 umma_commit(&bars[C_ACCQ]);
+                tr(2);
                 consume(cb + 1, s_xb, 2048, 384, false);
                 umma_commit(&bars[C_ACCVG]);
+                tr(3);
                 for (int t = 0; t < 3; ++t) {
                     mbar_wait(&bars[C_QKFREE], t & 1);
+                    tr(4);
                     consume(cb + 2 * t + 2, s_xb, 2048, 256, false);        // next [q | k]
                     umma_commit(&bars[C_ACCQ]);
+                    tr(2);
                     mbar_wait(&bars[C_VGFREE], t & 1);
+                    tr(5);
                     consume(cb + 2 * t + 3, s_xb, 2048, 384, false);        // next [v | gate]
                     umma_commit(&bars[C_ACCVG]);
+                    tr(3);
                 }
                 mbar_wait(&bars[C_ATTREADY], lp);
+                tr(6);
                 consume(cb + 8, s_att, 4096, 0, false);                     // out-projection, K halves
                 consume(cb + 9, s_att + 2048, 4096, 0, true);
                 umma_commit(&bars[C_ACCO]);
+                tr(7);
                 mbar_wait(&bars[C_UREADY], lp);
+                tr(8);
                 consume(cb + 10, s_xb, 2048, 256, false);                   // FFN-1, hidden half A
                 umma_commit(&bars[C_ACCF1A]);
                 consume(cb + 11, s_xb, 2048, 384, false);                   // FFN-1, hidden half B
                 umma_commit(&bars[C_ACCF1B]);
+                tr(9);
                 mbar_wait(&bars[C_FREADY0], lp);
+                tr(10);
                 consume(cb + 12, s_att, 4096, 0, false);                    // FFN-2 over hidden half A
                 mbar_wait(&bars[C_FREADY1], lp);
+                tr(11);
                 consume(cb + 13, s_att + 2048, 4096, 0, true);              // ... + half B
                 umma_commit(&bars[C_ACCF2]);
+                tr(12);
             }   // layers
         }
     } else {
@@ -772,6 +795,8 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
         uint8_t* sv = smem + OFF_V + ch * 8192;
         const uint32_t pb = trow + 256;
         const bool elected = lq == 0 && lane == 0;            // issues this head's S / O instructions
+        // traced threads: warp 0 lane 0 (score warp, lane 1 of the buffer), warp 8 lane 0 (value warp, lane 2)
+        Tracer tr{(a.trace && tile == 0 && z == 0 && lane == 0 && (warp == 0 || warp == 8)) ? a.trace + (warp == 0 ? 512 : 1024) : nullptr, 0};
 
         for (int li = 0; li < a.n_layers; ++li) {
         const uint32_t lp = li & 1;
@@ -784,6 +809,7 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             for (int t = 0; t < 4; ++t) gam[t] = a.gamma_f[po + 2 * t + ch];
             auto stage_qk = [&](int t) {    // Q -> BF16 back into TMEM in place (A operand of S = Q K^T); K -> shared, K-major
                 mbar_wait(&bars[C_ACCQ], t & 1);
+                tr(20);
                 tc_fence_after();
                 uint32_t qp[16];
                 float v2[32];
@@ -803,9 +829,12 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                 tmem_st_wait();
                 tc_fence_before();
                 fence_async_smem();
+                tr(21);
                 group_barrier(ch);
+                tr(22);
                 if (elected) {
                     if (t > 0) mbar_wait(&bars[C_OFREE0 + ch], (t - 1) & 1);    // O(t-1) has been read out of this tile
+                    tr(23);
                     tc_fence_after();
                     const uint32_t s_k = smem_u32(smem + OFF_K);
 #pragma unroll
@@ -830,6 +859,7 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                 const float gamma = t == 0 ? gam[0] : t == 1 ? gam[1] : t == 2 ? gam[2] : gam[3];
                 float w[64];
                 mbar_wait(&bars[C_SR0 + ch], t & 1);
+                tr(24);
                 tc_fence_after();
                 warp_arrive(&bars[C_QKFREE], lane);               // q / k columns are dead: the next [q | k] may be projected
                 {
@@ -869,10 +899,12 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                     tmem_st32(trow + 128 * ch + (kb >> 1), W);
                     tmem_st_wait();
                     tc_fence_before();
+                    tr(25);
                     // O = P V: A = BF16 P in TMEM, B = V (MN-major, 32 dims x 128 keys) staged by the value warps
                     group_barrier(ch);
                     if (elected) {
                         mbar_wait(&bars[C_VR0 + ch], t & 1);
+                        tr(26);
                         tc_fence_after();
                         const uint32_t s_v = smem_u32(smem + OFF_V);
 #pragma unroll
@@ -893,6 +925,7 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             uint32_t vp[16], gsig[16];
             auto load_vg = [&](int t) {     // v -> BF16 pairs (for the MN-major B operand of O = P V); sigmoid(gate) as BF16 pairs
                 mbar_wait(&bars[C_ACCVG], t & 1);
+                tr(30);
                 tc_fence_after();
                 float v2[32];
                 tmem_ld32_pair(pb + 128 + 32 * ch, v, pb + 192 + 32 * ch, v2);   // v and gate of this head
@@ -911,16 +944,15 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                         make_uint4(vp[4 * c], vp[4 * c + 1], vp[4 * c + 2], vp[4 * c + 3]);
                 fence_async_smem();             // (V must be visible to the tensor pipe before O = P V is issued)
                 warp_arrive(&bars[C_VR0 + ch], lane);
+                tr(31);
             };
             load_vg(0);
             store_v();
 #pragma unroll 1
             for (int t = 0; t < 4; ++t) {
-                uint32_t gcur[16];
-#pragma unroll
-                for (int c = 0; c < 16; ++c) gcur[c] = gsig[c];
-                if (t < 3) load_vg(t + 1);                          // v, gates of the next pair wait in registers
+                // O(t) first: the score warps cannot start S(t+1) in this tile before O(t) has been read out of it
                 mbar_wait(&bars[C_OR0 + ch], t & 1);
+                tr(32);
                 tc_fence_after();
                 float o[32];
                 tmem_ld32(trow + 128 * ch + 96, o);               // O = P V (last 32 columns of the S tile)
@@ -931,7 +963,7 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                     float r[8];
 #pragma unroll
                     for (int e = 0; e < 8; e += 2) {
-                        const uint32_t gp = gcur[4 * c + (e >> 1)];
+                        const uint32_t gp = gsig[4 * c + (e >> 1)];
                         r[e] = o[8 * c + e] * __uint_as_float(gp << 16);
                         r[e + 1] = o[8 * c + e + 1] * __uint_as_float(gp & 0xffff0000u);
                     }
@@ -939,7 +971,11 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                     pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
                     *reinterpret_cast<uint4*>(smem + OFF_ATT + op_chunk(row, 8 * t + 4 * ch + c, 256)) = pk;
                 }
-                if (t < 3) store_v();                               // O(t) is complete: V(t) may be overwritten
+                tr(33);
+                if (t < 3) {                                        // O(t) is complete: V(t) may be overwritten
+                    load_vg(t + 1);
+                    store_v();
+                }
             }
             fence_async_smem();
             warp_arrive(&bars[C_ATTREADY], lane);
@@ -969,7 +1005,9 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
         // small FP32 vectors of the layer -> shared (k, v are dead once every value warp has passed its last O):
         // bo, ln1w, ln1b, b2, ln2w, ln2b, b1[256]
         float* prm = reinterpret_cast<float*>(smem + OFF_V);
+        tr(40);
         all_compute_barrier();
+        tr(41);
         {
             const float* srcs[6] = {a.bo, a.ln1w, a.ln1b, a.b2, a.ln2w, a.ln2b};
             const int ct = warp * 32 + lane;                  // 0..511
@@ -983,7 +1021,9 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
         float* red = reinterpret_cast<float*>(smem + OFF_K);  // [4][128][2] partial sums (k is dead)
         const int c0 = 32 * cq;
         {
+            tr(42);
             mbar_wait(&bars[C_ACCO], lp);
+            tr(43);
             tc_fence_after();
             const float* bo = prm;
             float sum = 0.f, sq = 0.f;
@@ -1024,12 +1064,14 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             }
             fence_async_smem();
             warp_arrive(&bars[C_UREADY], lane);
+            tr(44);
         }
 
         // ---- phase 3: FFN-1 epilogue: + bias, ReLU -> BF16 operand (over the dead att tile); 64 hidden columns per thread,
         //      the two halves of the hidden width are committed (and handed to FFN-2) separately
         {
             mbar_wait(&bars[cq < 2 ? C_ACCF1A : C_ACCF1B], lp);
+            tr(45);
             tc_fence_after();
             const float* b1 = prm + 768;
             const int h0 = 64 * cq;
@@ -1052,11 +1094,13 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             tc_fence_before();
             fence_async_smem();
             warp_arrive(&bars[cq < 2 ? C_FREADY0 : C_FREADY1], lane);
+            tr(46);
         }
 
         // ---- phase 4: FFN-2 epilogue: + bias + U, LayerNorm -> Y (coalesced through shared)
         {
             mbar_wait(&bars[C_ACCF2], lp);
+            tr(47);
             tc_fence_after();
             const float* b2 = prm + 384;
             float* red2 = red + 1024;
@@ -1099,6 +1143,7 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                 }
                 fence_async_smem();
                 warp_arrive(&bars[C_XREADY], lane);
+                tr(48);
                 float4* park = reinterpret_cast<float4*>(a.y_mid + z * a.y_mid_z + (li & 1) * a.y_l) + (long long)tile * 4096 + row;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
@@ -1167,6 +1212,9 @@ int pack_reg_stream(const RegStreamArgs& a, int n_res, cudaStream_t st) {
     return CHROMO_OK;
 }
 
+static long long* g_trace = nullptr;
+void reg_fused_set_trace(long long* buf) { g_trace = buf; }
+
 bool reg_fused_tensor_attention() {
     static int tc = -1;
     if (tc < 0) { const char* e = getenv("CHROMO_REG_TC"); tc = (e && e[0] == '0') ? 0 : 1; }
@@ -1185,14 +1233,16 @@ int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st) {
         configured = true;
     }
     dim3 grid(a.n_tiles, n_res);
+    RegFusedArgs at = a;
+    at.trace = g_trace;
     // Attention on the tensor pipe (block-diagonal Q K^T / P V with Q and P rounded to BF16, as in every flash-attention
     // kernel) is the default (profiles/r01_precision.md).  CHROMO_REG_TC=0 selects the CUDA-core variant (FP32 q and
     // probabilities, one layer per launch).
     const int tc = reg_fused_tensor_attention() ? 1 : 0;
     if (a.n_layers < 1 || (a.n_layers > 1 && !tc)) { set_error("reg_layer_fused: multi-layer launches need the tensor-pipe attention"); return CHROMO_EINVAL; }
-    if (a.S == 9 && tc) reg_layer_fused_kernel<9><<<grid, RF2_THREADS, RF_SMEM, st>>>(a);
+    if (a.S == 9 && tc) reg_layer_fused_kernel<9><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
     else if (a.S == 9) reg_layer_cc_kernel<9><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
-    else if (a.S == 17 && tc) reg_layer_fused_kernel<17><<<grid, RF2_THREADS, RF_SMEM, st>>>(a);
+    else if (a.S == 17 && tc) reg_layer_fused_kernel<17><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
     else if (a.S == 17) reg_layer_cc_kernel<17><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
     else { set_error("reg_layer_fused: tokens per gene must be 9 or 17"); return CHROMO_EINVAL; }
     CHROMO_CHECK_LAUNCH("reg_layer_fused");

@@ -18,6 +18,7 @@ struct RegFusedArgs {
     const float* b1; const float* b2; const float* ln2w; const float* ln2b; long long p_z;
     const float* freq;                      // [B,S,S]
     const uint8_t* imask[CHROMO_MAX_RES];   // [B,S,S] per resolution
+    long long* trace = nullptr;             // profiling hook (chromo_debug_trace): CTA (0,0) logs (event << 48 | clock64) here
 };
 
 struct RegStreamArgs {
@@ -50,6 +51,7 @@ int launch_row_tail_fused(const RowTailArgs& a, int n_res, cudaStream_t st);
 
 long long reg_stream_elems_per_layer();
 int pack_reg_stream(const RegStreamArgs& a, int n_res, cudaStream_t st);
+void reg_fused_set_trace(long long* buf);
 bool reg_fused_tensor_attention();      // CHROMO_REG_TC != 0: attention on the tensor pipe; allows multi-layer launches
 int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st);
 

@@ -143,6 +143,11 @@ int chromo_pack_linear_weight(const float* w, uint16_t* packed, int32_t n, int32
 /* Test-only hardware-semantics probe (MN-major B operand, A operand in TMEM); see csrc/umma_probe.cu. */
 int chromo_debug_umma_probe(int32_t mode, const float* a, const float* b, float* d, int32_t n, int32_t k, void* stream);
 
+/* Profiling hook: while `buf` (device memory, 1536 int64, zero-filled by the caller) is set, CTA (0,0) of every fused
+ * Regulation launch logs (event id << 48 | clock64) for its driver thread ([0,512)), one score warp ([512,1024)) and one
+ * value warp ([1024,1536)); NULL switches it off.  tools/reg_timeline.py prints the timeline. */
+int chromo_debug_trace(int64_t* buf);
+
 /* Number of kernel launches issued by this library since the last reset (process-wide). */
 int64_t chromo_launch_counter(int32_t reset);
 
@@ -183,6 +188,19 @@ int chromo_bin_regions(const uint16_t* raw /* fp16 bits */, const chromo_region_
                        const int32_t* bin_sizes, const int32_t* n_bins,
                        float* const* feats /* n_res device ptrs */, int32_t* spans /* [n_res,regions,2] */,
                        void* stream);
+
+/* ---- host -> device transport: run_demo.py:100-105 / train.py:172-177 -------
+ * The reference ships every tensor of a batch with `.cuda()`: FP32 features and
+ * n x n boolean masks, 1.63 MB per gene.  The wire format of this library is
+ * FP16 features (the raw depth is FP16 on disk; ln(mean+1) rounds at 2^-11) and
+ * (first valid bin, count) spans instead of pad masks: 64 kB per gene.  This
+ * call widens n_seg feature tensors to the FP32 layout chromo_forward consumes
+ * and expands n_sets span arrays ([rows,2] int32) to centre-row pad masks
+ * ([rows,n_bins] bytes, 1 = padded), all in one launch.  Pointer ARRAYS are
+ * host memory; what they point at is device memory, 16-byte aligned.          */
+int chromo_unpack_wire(int32_t n_seg, const uint16_t* const* src /* fp16 bits */, float* const* dst,
+                       const int64_t* counts, int32_t n_sets, const int32_t* const* spans,
+                       uint8_t* const* masks, const int32_t* rows, const int32_t* n_bins, void* stream);
 
 #ifdef __cplusplus
 }
