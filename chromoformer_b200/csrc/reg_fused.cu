@@ -136,22 +136,33 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
 
 // P row of one (token, head) as packed BF16 pairs for the 64-key window that starts at the warp's first
 // gene (rounded down to an even key): entry m holds keys 2m, 2m+1 of the window; only the S keys of the
-// thread's own gene (candidate index c relative to the warp's first gene) are non-zero.
+// thread's own gene (candidate index c relative to the warp's first gene) are non-zero.  The S probabilities are
+// packed once in both alignments (gene starting on an even / odd key of the window); a candidate then only decides
+// WHICH run of packed registers receives them: one select per (candidate, packed register).
 template <int S, int NC, int PAR>
 __device__ __forceinline__ void build_p_window(const float* p, int c, uint32_t* W) {
+    constexpr int NE = (S + 1) / 2, NO = S / 2 + 1;
+    uint32_t ev[NE], od[NO];
 #pragma unroll
-    for (int m = 0; m < 32; ++m) {
-        float val[2];
+    for (int i = 0; i < NE; ++i) ev[i] = pack2(p[2 * i], 2 * i + 1 < S ? p[2 * i + 1] : 0.f);
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-            constexpr int dummy = 0; (void)dummy;
-            const int o = 2 * m + e - PAR;                    // key offset from the warp's first gene
-            val[e] = 0.f;
-            if (o >= 0 && o / S < NC) {
-                if (c == o / S) val[e] = p[o % S];
-            }
+    for (int i = 0; i < NO; ++i) od[i] = pack2(i > 0 ? p[2 * i - 1] : 0.f, 2 * i < S ? p[2 * i] : 0.f);
+#pragma unroll
+    for (int m = 0; m < 32; ++m) W[m] = 0u;
+#pragma unroll
+    for (int cc = 0; cc < NC; ++cc) {
+        constexpr int dummy = 0; (void)dummy;
+        const int base = cc * S + PAR;                        // first key of candidate cc's gene inside the window
+        const bool mine = c == cc;
+        if (base % 2 == 0) {
+#pragma unroll
+            for (int i = 0; i < NE; ++i)
+                if (base / 2 + i < 32) W[base / 2 + i] = mine ? ev[i] : W[base / 2 + i];
+        } else {
+#pragma unroll
+            for (int i = 0; i < NO; ++i)
+                if (base / 2 + i < 32) W[base / 2 + i] = mine ? od[i] : W[base / 2 + i];
         }
-        W[m] = pack2(val[0], val[1]);
     }
 }
 
@@ -209,10 +220,12 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_cc_kernel(const RegFu
                 mbar_wait(&bars[B_FULL0 + st], (c / RF_NSTAGE) & 1);
                 tc_fence_after();
                 const uint32_t b_addr = smem_u32(smem + OFF_STAGE + st * RF_CHUNK_BYTES);
+                // descriptors once per chunk, then plain adds (+256 B = +16 in the address field): building them per MMA
+                // costs the issuing thread ~120 cycles per instruction against the 64-cycle MMA (tools/bench_micro/mma_rate.cu)
+                const uint64_t ad = umma_smem_desc(a_addr, 128, a_sbo), bd = umma_smem_desc(b_addr, 128, 2048);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    umma_bf16(tmem + col, umma_smem_desc(a_addr + k * 256, 128, a_sbo),
-                              umma_smem_desc(b_addr + k * 256, 128, 2048), idesc, (accumulate || k > 0) ? 1u : 0u);
+                    umma_bf16(tmem + col, ad + 16 * k, bd + 16 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
                 umma_commit(&bars[B_FREE0 + st]);
                 // refill the ring behind the MMAs just queued (waits for chunk c-1 only)
                 if (c + 2 < n_chunks && c >= 1) issue_load(c + 2);
@@ -607,13 +620,13 @@ __global__ void __launch_bounds__(RF_THREADS, 1) reg_layer_cc_kernel(const RegFu
 // In the epilogue phases (out-projection + LayerNorm, FFN-1, FFN-2 + LayerNorm) role = column quarter: every row is
 // served by four threads, 32 columns each (64 of the 256 FFN-1 columns), and FFN-1 / FFN-2 are chained per half of the
 // hidden width, so that one half's bias + ReLU epilogue runs under the other half's MMAs.
-constexpr int RF2_THREADS = 544;
+constexpr int RF2_THREADS = 640;            // 16 compute warps + dense-MMA issuer + weight loader + 2 attention issuers
 enum { C_FULL0 = 0, C_FREE0 = 3, C_XREADY = 6, C_ATTREADY, C_UREADY, C_FREADY0, C_FREADY1, C_ACCQ, C_ACCVG, C_ACCO, C_ACCF1A,
-       C_ACCF1B, C_ACCF2, C_QKFREE, C_VGFREE, C_SR0, C_OR0 = C_SR0 + 2, C_VR0 = C_OR0 + 2, C_OFREE0 = C_VR0 + 2,
-       C_COUNT = C_OFREE0 + 2 };
+       C_ACCF1B, C_ACCF2, C_OFREE, C_SR0, C_OR0 = C_SR0 + 2, C_QKS0 = C_OR0 + 2, C_PST0 = C_QKS0 + 2,
+       C_VR0 = C_PST0 + 2, C_COUNT = C_VR0 + 2 };
 static_assert(C_COUNT * 8 + 8 <= 256, "control block");
 
-// timeline hook: four traced threads of CTA (0,0) (driver, one score warp, one value warp, warp 0 in the epilogues) append
+// timeline hook: traced threads of CTA (0,0) (dense issuer, one score warp, one value warp) append
 // (event id << 48 | clock64) to their own 512-entry lane of a.trace
 struct Tracer {
     long long* p; int n;
@@ -622,6 +635,8 @@ struct Tracer {
     }
 };
 __device__ __forceinline__ void all_compute_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
+// the four warps that share a TMEM lane quarter (the four column quarters of the same 32 rows)
+__device__ __forceinline__ void quarter_barrier(int lq) { asm volatile("bar.sync %0, 128;" ::"r"(4 + lq) : "memory"); }
 
 template <int SMAX>
 __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const RegFusedArgs a) {
@@ -642,10 +657,10 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
         mbar_init(&bars[C_FREADY0], 8); mbar_init(&bars[C_FREADY1], 8);
         mbar_init(&bars[C_ACCQ], 1); mbar_init(&bars[C_ACCVG], 1); mbar_init(&bars[C_ACCO], 1);
         mbar_init(&bars[C_ACCF1A], 1); mbar_init(&bars[C_ACCF1B], 1); mbar_init(&bars[C_ACCF2], 1);
-        mbar_init(&bars[C_QKFREE], 8); mbar_init(&bars[C_VGFREE], 8);
+        mbar_init(&bars[C_OFREE], 8);
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bars[C_SR0 + i], 1); mbar_init(&bars[C_OR0 + i], 1);
-            mbar_init(&bars[C_VR0 + i], 4); mbar_init(&bars[C_OFREE0 + i], 4);
+            mbar_init(&bars[C_QKS0 + i], 4); mbar_init(&bars[C_PST0 + i], 4); mbar_init(&bars[C_VR0 + i], 4);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -654,82 +669,113 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
 
-    if (warp == 16) {
-        // ===================================================== driver: TMA + the dense tcgen05.mma ====
+    if (warp == 17) {
+        // ===================================================== loader: weight stream through the 3-stage ring ====
         if (lane == 0) {
             const __nv_bfloat16* wsrc = a.wstream + z * a.w_z;
             const int n_chunks = RF_NCHUNK * a.n_layers;   // the layers' chunks follow each other in the stream
-            const uint32_t idesc = umma_idesc_bf16(128, 128);
-            const uint32_t s_xb = smem_u32(smem + OFF_XB), s_att = smem_u32(smem + OFF_ATT);
-            auto issue_load = [&](int c) {
+            for (int c = 0; c < n_chunks; ++c) {
                 const int st = c % RF_NSTAGE;
                 if (c >= RF_NSTAGE) mbar_wait(&bars[C_FREE0 + st], ((c / RF_NSTAGE) - 1) & 1);
                 mbar_expect_tx(&bars[C_FULL0 + st], RF_CHUNK_BYTES);
                 tma_bulk_g2s(smem + OFF_STAGE + st * RF_CHUNK_BYTES, wsrc + (long long)c * RF_CHUNK_ELEMS, RF_CHUNK_BYTES,
                              &bars[C_FULL0 + st]);
-            };
-            auto consume = [&](int c, uint32_t a_addr, uint32_t a_sbo, uint32_t col, bool accumulate) {
+            }
+        }
+    } else if (warp >= 18) {
+        // ===================================================== attention issuers: S = Q K^T and O = P V of one head each ====
+        // The order per head is fixed - S(0), O(0), S(1), O(1), ... (S(t+1) overwrites the tile P(t) sits in, so it has to
+        // follow O(t) in the in-order tensor pipe) - so a dedicated thread per head simply blocks on the hand-offs in that
+        // order; nothing else competes for its instruction slots.
+        if (lane == 0) {
+            const int ch = warp - 18;
+            const uint64_t k_d = umma_smem_desc(smem_u32(smem + OFF_K) + ch * 8192, 128, 512);
+            const uint64_t v_d = umma_smem_desc(smem_u32(smem + OFF_V) + ch * 8192, 128, 2048);
+            const uint32_t idesc_s = umma_idesc_bf16(128, 128), idesc_o = umma_idesc_bf16(128, 32) | (1u << 16);   // O: B MN-major
+            const int n_steps = 4 * a.n_layers;
+            for (int i = 0; i < n_steps; ++i) {
+                const uint32_t par = i & 1;
+                mbar_wait(&bars[C_QKS0 + ch], par);                        // q (TMEM, BF16) and k (shared) of this pair staged
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 2; ++k)
+                    umma_bf16_ts(tmem + 128 * ch, tmem + 256 + 32 * ch + 8 * k, k_d + 16 * k, idesc_s, k > 0 ? 1u : 0u);
+                umma_commit(&bars[C_SR0 + ch]);
+                mbar_wait(&bars[C_PST0 + ch], par);                        // P stored by the score warps
+                mbar_wait(&bars[C_VR0 + ch], par);                         // V staged by the value warps
+                tc_fence_after();
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16_ts(tmem + 384 + 32 * ch, tmem + 128 * ch + 8 * k, v_d + 16 * k, idesc_o, k > 0 ? 1u : 0u);
+                umma_commit(&bars[C_OR0 + ch]);
+            }
+        }
+    } else if (warp == 16) {
+        // ===================================================== dense issuer: projections, out-projection, FFN ====
+        if (lane == 0) {
+            const uint32_t idesc = umma_idesc_bf16(128, 128);
+            const uint32_t s_xb = smem_u32(smem + OFF_XB), s_att = smem_u32(smem + OFF_ATT);
+            const uint64_t xd = umma_smem_desc(s_xb, 128, 2048), attd = umma_smem_desc(s_att, 128, 4096);
+            const uint64_t stage_d = umma_smem_desc(smem_u32(smem + OFF_STAGE), 128, 2048);   // + st * 2048 per ring stage
+            Tracer tr{(a.trace && tile == 0 && z == 0) ? a.trace : nullptr, 0};
+            auto consume = [&](int c, uint64_t ad, uint32_t col, bool accumulate) {
                 const int st = c % RF_NSTAGE;
                 mbar_wait(&bars[C_FULL0 + st], (c / RF_NSTAGE) & 1);
                 tc_fence_after();
-                const uint32_t b_addr = smem_u32(smem + OFF_STAGE + st * RF_CHUNK_BYTES);
+                // descriptors by plain adds (+256 B = +16 in the address field): building them per MMA costs the issuing
+                // thread ~120 cycles per instruction against the 64-cycle MMA (tools/bench_micro/mma_rate.cu)
+                const uint64_t bd = stage_d + 2048 * st;
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    umma_bf16(tmem + col, umma_smem_desc(a_addr + k * 256, 128, a_sbo),
-                              umma_smem_desc(b_addr + k * 256, 128, 2048), idesc, (accumulate || k > 0) ? 1u : 0u);
-                umma_commit(&bars[C_FREE0 + st]);
-                // refill the ring behind the MMAs just queued (waits for chunk c-1 only)
-                if (c + 2 < n_chunks && c >= 1) issue_load(c + 2);
+                    umma_bf16(tmem + col, ad + 16 * k, bd + 16 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
+                umma_commit(&bars[C_FREE0 + st]);                           // (the loader warp refills the stage)
             };
-            issue_load(0);
-            issue_load(1);
-            issue_load(2);
-            Tracer tr{(a.trace && tile == 0 && z == 0) ? a.trace : nullptr, 0};
             for (int li = 0; li < a.n_layers; ++li) {
                 const int cb = li * RF_NCHUNK;
                 const uint32_t lp = li & 1;
                 mbar_wait(&bars[C_XREADY], lp);
                 tr(1);
-                // TMEM [0,128) / [128,256): S, then P (first 64..77 columns) and O (last 32) of the two heads in flight;
-                // [256,512): projection pair (q0 q1 k0 k1 v0 v1 g0 g1, 32 columns each).  [q | k] and [v | gate] of the
-                // next pair are projected as soon as their readers are done with the columns.
-                consume(cb, s_xb, 2048, 256, false);
+                // TMEM [0,128) / [128,256): S, then P (first 64..77 columns) of the two heads in flight; [256,512): projection
+                // pair (q0 q1 k0 k1 v0 v1 g0 g1, 32 columns each); O = P V of a head lands in the (by then dead) v columns of
+                // that head, so the S tile is free for the next pair's scores as soon as O has been ISSUED (the tensor pipe
+                // runs in order).  The next [q | k] goes out when S is done with q / k (the issuer watches the S commit barriers
+                // itself), the next [v | gate] when O has been read out of the v columns.
+                consume(cb, xd, 256, false);
                 umma_commit(&bars[C_ACCQ]);
                 tr(2);
-                consume(cb + 1, s_xb, 2048, 384, false);
+                consume(cb + 1, xd, 384, false);
                 umma_commit(&bars[C_ACCVG]);
                 tr(3);
                 for (int t = 0; t < 3; ++t) {
-                    mbar_wait(&bars[C_QKFREE], t & 1);
+                    mbar_wait(&bars[C_SR0], t & 1);                         // S(t) of both heads complete: q / k columns are dead
+                    mbar_wait(&bars[C_SR0 + 1], t & 1);
                     tr(4);
-                    consume(cb + 2 * t + 2, s_xb, 2048, 256, false);        // next [q | k]
+                    consume(cb + 2 * t + 2, xd, 256, false);                // next [q | k]
                     umma_commit(&bars[C_ACCQ]);
                     tr(2);
-                    mbar_wait(&bars[C_VGFREE], t & 1);
+                    mbar_wait(&bars[C_OFREE], t & 1);
                     tr(5);
-                    consume(cb + 2 * t + 3, s_xb, 2048, 384, false);        // next [v | gate]
+                    consume(cb + 2 * t + 3, xd, 384, false);                // next [v | gate]
                     umma_commit(&bars[C_ACCVG]);
                     tr(3);
                 }
                 mbar_wait(&bars[C_ATTREADY], lp);
                 tr(6);
-                consume(cb + 8, s_att, 4096, 0, false);                     // out-projection, K halves
-                consume(cb + 9, s_att + 2048, 4096, 0, true);
+                consume(cb + 8, attd, 0, false);                            // out-projection, K halves
+                consume(cb + 9, attd + 128, 0, true);
                 umma_commit(&bars[C_ACCO]);
                 tr(7);
                 mbar_wait(&bars[C_UREADY], lp);
                 tr(8);
-                consume(cb + 10, s_xb, 2048, 256, false);                   // FFN-1, hidden half A
+                consume(cb + 10, xd, 256, false);                           // FFN-1, hidden half A
                 umma_commit(&bars[C_ACCF1A]);
-                consume(cb + 11, s_xb, 2048, 384, false);                   // FFN-1, hidden half B
+                consume(cb + 11, xd, 384, false);                           // FFN-1, hidden half B
                 umma_commit(&bars[C_ACCF1B]);
                 tr(9);
                 mbar_wait(&bars[C_FREADY0], lp);
-                tr(10);
-                consume(cb + 12, s_att, 4096, 0, false);                    // FFN-2 over hidden half A
+                consume(cb + 12, attd, 0, false);                           // FFN-2 over hidden half A
                 mbar_wait(&bars[C_FREADY1], lp);
-                tr(11);
-                consume(cb + 13, s_att + 2048, 4096, 0, true);              // ... + half B
+                consume(cb + 13, attd + 128, 0, true);                      // ... + half B
                 umma_commit(&bars[C_ACCF2]);
                 tr(12);
             }   // layers
@@ -794,7 +840,6 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
         uint8_t* sk = smem + OFF_K + ch * 8192;
         uint8_t* sv = smem + OFF_V + ch * 8192;
         const uint32_t pb = trow + 256;
-        const bool elected = lq == 0 && lane == 0;            // issues this head's S / O instructions
         // traced threads: warp 0 lane 0 (score warp, lane 1 of the buffer), warp 8 lane 0 (value warp, lane 2)
         Tracer tr{(a.trace && tile == 0 && z == 0 && lane == 0 && (warp == 0 || warp == 8)) ? a.trace + (warp == 0 ? 512 : 1024) : nullptr, 0};
 
@@ -802,54 +847,14 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
         const uint32_t lp = li & 1;
         const long long po = z * a.p_z + li * a.p_l;          // this (resolution, layer)'s parameters
 
-        // ---- phase 1: attention, four head pairs
+        // ---- phase 1: attention, four head pairs.  Score warps: scores of a row against the S keys of its own gene ->
+        // softmax -> P; value warps: operand staging (q, k, v), sigmoid(gate), O -> gated out-projection operand.
         if (score_warp) {
             float gam[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) gam[t] = a.gamma_f[po + 2 * t + ch];
-            auto stage_qk = [&](int t) {    // Q -> BF16 back into TMEM in place (A operand of S = Q K^T); K -> shared, K-major
-                mbar_wait(&bars[C_ACCQ], t & 1);
-                tr(20);
-                tc_fence_after();
-                uint32_t qp[16];
-                float v2[32];
-                tmem_ld32_pair(pb + 32 * ch, v, pb + 64 + 32 * ch, v2);    // q and k of this head, both loads in flight
-#pragma unroll
-                for (int c = 0; c < 16; ++c) qp[c] = pack2(v[2 * c], v[2 * c + 1]);
-                tmem_st16(pb + 32 * ch, qp);
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint4 pk;
-                    pk.x = pack2(v2[8 * c], v2[8 * c + 1]); pk.y = pack2(v2[8 * c + 2], v2[8 * c + 3]);
-                    pk.z = pack2(v2[8 * c + 4], v2[8 * c + 5]); pk.w = pack2(v2[8 * c + 6], v2[8 * c + 7]);
-                    *reinterpret_cast<uint4*>(sk + op_chunk(row, c, 32)) = pk;
-                }
-            };
-            auto issue_s = [&](int t) {     // S = Q K^T: A = BF16 Q in TMEM, B = K in shared memory
-                tmem_st_wait();
-                tc_fence_before();
-                fence_async_smem();
-                tr(21);
-                group_barrier(ch);
-                tr(22);
-                if (elected) {
-                    if (t > 0) mbar_wait(&bars[C_OFREE0 + ch], (t - 1) & 1);    // O(t-1) has been read out of this tile
-                    tr(23);
-                    tc_fence_after();
-                    const uint32_t s_k = smem_u32(smem + OFF_K);
-#pragma unroll
-                    for (int k = 0; k < 2; ++k)
-                        umma_bf16_ts(tmem + 128 * ch, tmem + 256 + 32 * ch + 8 * k,
-                                     umma_smem_desc(s_k + ch * 8192 + k * 256, 128, 512), umma_idesc_bf16(128, 128),
-                                     k > 0 ? 1u : 0u);
-                    umma_commit(&bars[C_SR0 + ch]);
-                }
-                __syncwarp();
-            };
-            stage_qk(0);
-            issue_s(0);
-            // scores of a row against the S keys of its own gene: a window of the S tile that starts at the first gene touched
-            // by this warp (register indices stay compile-time, the column is warp-uniform)
+            // a window of the S tile that starts at the first gene touched by this warp (register indices stay
+            // compile-time, the column is warp-uniform)
             constexpr int NC = (31 + S - 1) / S + 1;             // genes a 32-row warp can touch
             constexpr int NW = NC * S;                            // window width in keys (<= 64)
             const int g_lo = (32 * lq) / S;
@@ -861,11 +866,18 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                 mbar_wait(&bars[C_SR0 + ch], t & 1);
                 tr(24);
                 tc_fence_after();
-                warp_arrive(&bars[C_QKFREE], lane);               // q / k columns are dead: the next [q | k] may be projected
                 {
                     const uint32_t sc0 = trow + 128 * ch + S * g_lo;
                     if (NW > 48) tmem_ld32_pair(sc0, w, sc0 + 32, w + 32);
                     else { tmem_ld32(sc0, w); tmem_ld16(sc0 + 32, w + 32); }
+                }
+                tc_fence_before();
+                {   // zeros over the P columns of the tile while the scores are being reduced
+                    uint32_t Z[32];
+#pragma unroll
+                    for (int m = 0; m < 32; ++m) Z[m] = 0u;
+                    tmem_st32(trow + 128 * ch, Z);
+                    tmem_st32(trow + 128 * ch + 32, Z);
                 }
                 float s[SMAX];
                 float mx = -INFINITY;
@@ -886,96 +898,92 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                 const float inv = 1.f / sum;
 #pragma unroll
                 for (int j = 0; j < S; ++j) s[j] *= inv;
-                {   // P (BF16 pairs) over the first 64 columns of the S tile: zeros, then this warp's window
+                {   // P (BF16 pairs) over the first 64 columns of the S tile: this warp's window over the zeros
                     uint32_t W[32];
-#pragma unroll
-                    for (int m = 0; m < 32; ++m) W[m] = 0u;
-                    tmem_st32(trow + 128 * ch, W);
-                    tmem_st32(trow + 128 * ch + 32, W);
-                    tmem_st_wait();
                     const int kb = S * g_lo;
                     if (kb & 1) build_p_window<S, NC, 1>(s, cand, W);
                     else build_p_window<S, NC, 0>(s, cand, W);
+                    tmem_st_wait();                                 // (the zeros have landed)
                     tmem_st32(trow + 128 * ch + (kb >> 1), W);
                     tmem_st_wait();
                     tc_fence_before();
+                    warp_arrive(&bars[C_PST0 + ch], lane);          // P(t) of this warp's rows is in place
                     tr(25);
-                    // O = P V: A = BF16 P in TMEM, B = V (MN-major, 32 dims x 128 keys) staged by the value warps
-                    group_barrier(ch);
-                    if (elected) {
-                        mbar_wait(&bars[C_VR0 + ch], t & 1);
-                        tr(26);
-                        tc_fence_after();
-                        const uint32_t s_v = smem_u32(smem + OFF_V);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k)
-                            umma_bf16_ts(tmem + 128 * ch + 96, tmem + 128 * ch + 8 * k,
-                                         umma_smem_desc(s_v + ch * 8192 + k * 256, 128, 2048),
-                                         umma_idesc_bf16(128, 32) | (1u << 16), k > 0 ? 1u : 0u);
-                        umma_commit(&bars[C_OR0 + ch]);
-                    }
-                    __syncwarp();
-                }
-                if (t < 3) {
-                    stage_qk(t + 1);                                // (while O = P V runs and the value warps gate it)
-                    issue_s(t + 1);
                 }
             }
         } else {
-            uint32_t vp[16], gsig[16];
-            auto load_vg = [&](int t) {     // v -> BF16 pairs (for the MN-major B operand of O = P V); sigmoid(gate) as BF16 pairs
+            uint32_t gsig[16];
+            auto stage_qk = [&](int t) {    // Q -> BF16 back into TMEM in place (A operand of S = Q K^T); K -> shared, K-major
+                mbar_wait(&bars[C_ACCQ], t & 1);
+                tr(20);
+                tc_fence_after();
+                uint32_t qp[16];
+                float v2[32];
+                tmem_ld32_pair(pb + 32 * ch, v, pb + 64 + 32 * ch, v2);    // q and k of this head, both loads in flight
+#pragma unroll
+                for (int c = 0; c < 16; ++c) qp[c] = pack2(v[2 * c], v[2 * c + 1]);
+                tmem_st16(pb + 32 * ch, qp);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    uint4 pk;
+                    pk.x = pack2(v2[8 * c], v2[8 * c + 1]); pk.y = pack2(v2[8 * c + 2], v2[8 * c + 3]);
+                    pk.z = pack2(v2[8 * c + 4], v2[8 * c + 5]); pk.w = pack2(v2[8 * c + 6], v2[8 * c + 7]);
+                    *reinterpret_cast<uint4*>(sk + op_chunk(row, c, 32)) = pk;
+                }
+                tmem_st_wait();
+                tc_fence_before();
+                fence_async_smem();
+                warp_arrive(&bars[C_QKS0 + ch], lane);
+                tr(21);
+            };
+            auto stage_vg = [&](int t) {    // v -> shared, MN-major (B operand of O = P V); sigmoid(gate) kept as BF16 pairs
                 mbar_wait(&bars[C_ACCVG], t & 1);
                 tr(30);
                 tc_fence_after();
                 float v2[32];
                 tmem_ld32_pair(pb + 128 + 32 * ch, v, pb + 192 + 32 * ch, v2);   // v and gate of this head
                 tc_fence_before();
-                warp_arrive(&bars[C_VGFREE], lane);               // the next [v | gate] may be projected
 #pragma unroll
-                for (int c = 0; c < 16; ++c) {
-                    vp[c] = pack2(v[2 * c], v[2 * c + 1]);
-                    gsig[c] = pack2(gate_factor(v2[2 * c]), gate_factor(v2[2 * c + 1]));
+                for (int c = 0; c < 4; ++c) {
+                    uint4 pk;
+                    pk.x = pack2(v[8 * c], v[8 * c + 1]); pk.y = pack2(v[8 * c + 2], v[8 * c + 3]);
+                    pk.z = pack2(v[8 * c + 4], v[8 * c + 5]); pk.w = pack2(v[8 * c + 6], v[8 * c + 7]);
+                    *reinterpret_cast<uint4*>(sv + c * 2048 + (row >> 3) * 128 + (row & 7) * 16) = pk;
                 }
-            };
-            auto store_v = [&]() {
-#pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    *reinterpret_cast<uint4*>(sv + c * 2048 + (row >> 3) * 128 + (row & 7) * 16) =
-                        make_uint4(vp[4 * c], vp[4 * c + 1], vp[4 * c + 2], vp[4 * c + 3]);
                 fence_async_smem();             // (V must be visible to the tensor pipe before O = P V is issued)
                 warp_arrive(&bars[C_VR0 + ch], lane);
                 tr(31);
+#pragma unroll
+                for (int c = 0; c < 16; ++c) gsig[c] = pack2(gate_factor(v2[2 * c]), gate_factor(v2[2 * c + 1]));
             };
-            load_vg(0);
-            store_v();
+            stage_qk(0);
+            stage_vg(0);
 #pragma unroll 1
             for (int t = 0; t < 4; ++t) {
-                // O(t) first: the score warps cannot start S(t+1) in this tile before O(t) has been read out of it
+                if (t < 3) stage_qk(t + 1);                         // (S(t) is complete once [q | k](t+1) has been projected)
                 mbar_wait(&bars[C_OR0 + ch], t & 1);
                 tr(32);
                 tc_fence_after();
                 float o[32];
-                tmem_ld32(trow + 128 * ch + 96, o);               // O = P V (last 32 columns of the S tile)
+                tmem_ld32(pb + 128 + 32 * ch, o);                 // O = P V (in this head's v columns)
                 tc_fence_before();
-                warp_arrive(&bars[C_OFREE0 + ch], lane);          // the tile may take the next S
+                warp_arrive(&bars[C_OFREE], lane);                // the v columns may take the next [v | gate]
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     float r[8];
 #pragma unroll
                     for (int e = 0; e < 8; e += 2) {
                         const uint32_t gp = gsig[4 * c + (e >> 1)];
-                        r[e] = o[8 * c + e] * __uint_as_float(gp << 16);
-                        r[e + 1] = o[8 * c + e + 1] * __uint_as_float(gp & 0xffff0000u);
+                        const float2 g2 = make_float2(__uint_as_float(gp << 16), __uint_as_float(gp & 0xffff0000u));
+                        const float2 r2 = __fmul2_rn(make_float2(o[8 * c + e], o[8 * c + e + 1]), g2);
+                        r[e] = r2.x; r[e + 1] = r2.y;
                     }
                     uint4 pk;
                     pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
                     *reinterpret_cast<uint4*>(smem + OFF_ATT + op_chunk(row, 8 * t + 4 * ch + c, 256)) = pk;
                 }
                 tr(33);
-                if (t < 3) {                                        // O(t) is complete: V(t) may be overwritten
-                    load_vg(t + 1);
-                    store_v();
-                }
+                if (t < 3) stage_vg(t + 1);                         // O(t) is complete: V(t) may be overwritten
             }
             fence_async_smem();
             warp_arrive(&bars[C_ATTREADY], lane);
@@ -1005,16 +1013,19 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
         // small FP32 vectors of the layer -> shared (k, v are dead once every value warp has passed its last O):
         // bo, ln1w, ln1b, b2, ln2w, ln2b, b1[256]
         float* prm = reinterpret_cast<float*>(smem + OFF_V);
-        tr(40);
-        all_compute_barrier();
-        tr(41);
-        {
+        {   // (global loads before the barrier, so that their latency hides behind it)
             const float* srcs[6] = {a.bo, a.ln1w, a.ln1b, a.b2, a.ln2w, a.ln2b};
             const int ct = warp * 32 + lane;                  // 0..511
+            float pv[3] = {0.f, 0.f, 0.f};
 #pragma unroll
             for (int k = 0; k < 6; ++k)
-                if ((ct >> 7) == (k >> 1)) prm[k * 128 + (ct & 127)] = srcs[k][po + (ct & 127)];
-            if (ct >= 256) prm[768 + ct - 256] = a.b1[po + ct - 256];
+                if ((ct >> 7) == (k >> 1)) pv[k & 1] = __ldg(srcs[k] + po + (ct & 127));
+            if (ct >= 256) pv[2] = __ldg(a.b1 + po + ct - 256);
+            tr(40);
+            all_compute_barrier();
+            tr(41);
+            if (ct < 384) { prm[(2 * (ct >> 7)) * 128 + (ct & 127)] = pv[0]; prm[(2 * (ct >> 7) + 1) * 128 + (ct & 127)] = pv[1]; }
+            if (ct >= 256) prm[768 + ct - 256] = pv[2];
         }
         all_compute_barrier();
         // ---- phase 2: out-projection epilogue: + bias + residual, LayerNorm -> U
@@ -1028,18 +1039,25 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             const float* bo = prm;
             float sum = 0.f, sq = 0.f;
             tmem_ld32(trow + c0, v);
+            tr(50);
+            float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);      // packed FP32x2 math (sm_100)
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 const float4 b4 = *reinterpret_cast<const float4*>(bo + c0 + j);
-                const float t0 = v[j] + b4.x + u_keep[j], t1 = v[j + 1] + b4.y + u_keep[j + 1];
-                const float t2 = v[j + 2] + b4.z + u_keep[j + 2], t3 = v[j + 3] + b4.w + u_keep[j + 3];
-                u_keep[j] = t0; u_keep[j + 1] = t1; u_keep[j + 2] = t2; u_keep[j + 3] = t3;
-                sum += (t0 + t1) + (t2 + t3);
-                sq += (t0 * t0 + t1 * t1) + (t2 * t2 + t3 * t3);
+                const float2 ta = __fadd2_rn(__fadd2_rn(make_float2(v[j], v[j + 1]), make_float2(b4.x, b4.y)),
+                                             make_float2(u_keep[j], u_keep[j + 1]));
+                const float2 tb = __fadd2_rn(__fadd2_rn(make_float2(v[j + 2], v[j + 3]), make_float2(b4.z, b4.w)),
+                                             make_float2(u_keep[j + 2], u_keep[j + 3]));
+                u_keep[j] = ta.x; u_keep[j + 1] = ta.y; u_keep[j + 2] = tb.x; u_keep[j + 3] = tb.y;
+                sum2 = __fadd2_rn(sum2, __fadd2_rn(ta, tb));
+                sq2 = __ffma2_rn(ta, ta, __ffma2_rn(tb, tb, sq2));
             }
+            sum = sum2.x + sum2.y; sq = sq2.x + sq2.y;
             tc_fence_before();
             *reinterpret_cast<float2*>(red + (cq * 128 + row) * 2) = make_float2(sum, sq);
-            all_compute_barrier();
+            tr(51);
+            quarter_barrier(lq);
+            tr(52);
             sum = 0.f; sq = 0.f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -1050,18 +1068,26 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             const float rstd = rsqrtf(fmaxf(sq * (1.f / 128.f) - mean * mean, 0.f) + 1e-5f);
             const float* lw = prm + 128;
             const float* lb = prm + 256;
+            const float2 nm2 = make_float2(-mean, -mean), rs2 = make_float2(rstd, rstd);
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
                 float r[8];
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    r[e] = (u_keep[j + e] - mean) * rstd * lw[c0 + j + e] + lb[c0 + j + e];
-                    u_keep[j + e] = r[e];
+                for (int e = 0; e < 8; e += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(lw + c0 + j + e);
+                    const float4 b4 = *reinterpret_cast<const float4*>(lb + c0 + j + e);
+                    const float2 ra = __ffma2_rn(__fadd2_rn(make_float2(u_keep[j + e], u_keep[j + e + 1]), nm2),
+                                                 __fmul2_rn(rs2, make_float2(w4.x, w4.y)), make_float2(b4.x, b4.y));
+                    const float2 rb = __ffma2_rn(__fadd2_rn(make_float2(u_keep[j + e + 2], u_keep[j + e + 3]), nm2),
+                                                 __fmul2_rn(rs2, make_float2(w4.z, w4.w)), make_float2(b4.z, b4.w));
+                    r[e] = ra.x; r[e + 1] = ra.y; r[e + 2] = rb.x; r[e + 3] = rb.y;
+                    u_keep[j + e] = ra.x; u_keep[j + e + 1] = ra.y; u_keep[j + e + 2] = rb.x; u_keep[j + e + 3] = rb.y;
                 }
                 uint4 pk;
                 pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
                 *reinterpret_cast<uint4*>(smem + OFF_XB + op_chunk(row, (c0 + j) >> 3, 128)) = pk;
             }
+            tr(53);
             fence_async_smem();
             warp_arrive(&bars[C_UREADY], lane);
             tr(44);
@@ -1085,7 +1111,12 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                 for (int j = 0; j < 32; j += 8) {
                     float r[8];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) r[e] = fmaxf(vv[j + e] + b1[c + j + e], 0.f);
+                    for (int e = 0; e < 8; e += 4) {
+                        const float4 b4 = *reinterpret_cast<const float4*>(b1 + c + j + e);
+                        const float2 ra = __fadd2_rn(make_float2(vv[j + e], vv[j + e + 1]), make_float2(b4.x, b4.y));
+                        const float2 rb = __fadd2_rn(make_float2(vv[j + e + 2], vv[j + e + 3]), make_float2(b4.z, b4.w));
+                        r[e] = fmaxf(ra.x, 0.f); r[e + 1] = fmaxf(ra.y, 0.f); r[e + 2] = fmaxf(rb.x, 0.f); r[e + 3] = fmaxf(rb.y, 0.f);
+                    }
                     uint4 pk;
                     pk.x = pack2(r[0], r[1]); pk.y = pack2(r[2], r[3]); pk.z = pack2(r[4], r[5]); pk.w = pack2(r[6], r[7]);
                     *reinterpret_cast<uint4*>(smem + OFF_ATT + op_chunk(row, (c + j) >> 3, 256)) = pk;
@@ -1106,16 +1137,22 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             float* red2 = red + 1024;
             float sum = 0.f, sq = 0.f;
             tmem_ld32(trow + c0, v);
+            float2 sum2 = make_float2(0.f, 0.f), sq2 = make_float2(0.f, 0.f);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-                const float t0 = v[j] + b2[c0 + j] + u_keep[j];
-                u_keep[j] = t0;
-                sum += t0;
-                sq += t0 * t0;
+            for (int j = 0; j < 32; j += 4) {
+                const float4 b4 = *reinterpret_cast<const float4*>(b2 + c0 + j);
+                const float2 ta = __fadd2_rn(__fadd2_rn(make_float2(v[j], v[j + 1]), make_float2(b4.x, b4.y)),
+                                             make_float2(u_keep[j], u_keep[j + 1]));
+                const float2 tb = __fadd2_rn(__fadd2_rn(make_float2(v[j + 2], v[j + 3]), make_float2(b4.z, b4.w)),
+                                             make_float2(u_keep[j + 2], u_keep[j + 3]));
+                u_keep[j] = ta.x; u_keep[j + 1] = ta.y; u_keep[j + 2] = tb.x; u_keep[j + 3] = tb.y;
+                sum2 = __fadd2_rn(sum2, __fadd2_rn(ta, tb));
+                sq2 = __ffma2_rn(ta, ta, __ffma2_rn(tb, tb, sq2));
             }
+            sum = sum2.x + sum2.y; sq = sq2.x + sq2.y;
             tc_fence_before();
             *reinterpret_cast<float2*>(red2 + (cq * 128 + row) * 2) = make_float2(sum, sq);
-            all_compute_barrier();
+            quarter_barrier(lq);
             sum = 0.f; sq = 0.f;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -1127,8 +1164,19 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             const float* lw = prm + 512;
             const float* lb = prm + 640;
             const bool more = li + 1 < a.n_layers;
+            {
+                const float2 nm2 = make_float2(-mean, -mean), rs2 = make_float2(rstd, rstd);
 #pragma unroll
-            for (int j = 0; j < 32; ++j) u_keep[j] = (u_keep[j] - mean) * rstd * lw[c0 + j] + lb[c0 + j];
+                for (int j = 0; j < 32; j += 4) {
+                    const float4 w4 = *reinterpret_cast<const float4*>(lw + c0 + j);
+                    const float4 b4 = *reinterpret_cast<const float4*>(lb + c0 + j);
+                    const float2 ra = __ffma2_rn(__fadd2_rn(make_float2(u_keep[j], u_keep[j + 1]), nm2),
+                                                 __fmul2_rn(rs2, make_float2(w4.x, w4.y)), make_float2(b4.x, b4.y));
+                    const float2 rb = __ffma2_rn(__fadd2_rn(make_float2(u_keep[j + 2], u_keep[j + 3]), nm2),
+                                                 __fmul2_rn(rs2, make_float2(w4.z, w4.w)), make_float2(b4.z, b4.w));
+                    u_keep[j] = ra.x; u_keep[j + 1] = ra.y; u_keep[j + 2] = rb.x; u_keep[j + 3] = rb.y;
+                }
+            }
             if (more) {
                 // Y is the next layer's operand (BF16, over X in shared memory) and residual (FP32, parked in the scratch
                 // slot by the thread that will read it back, lane-major).  Operand first: the driver starts the next

@@ -85,10 +85,10 @@ __global__ void __launch_bounds__(RT_THREADS, 1) row_tail_fused_kernel(const Row
                 mbar_wait(&bars[T_FULL0 + st], (c / RT_NSTAGE) & 1);
                 tc_fence_after();
                 const uint32_t b_addr = smem_u32(smem + RT_OFF_STAGE + st * RT_CHUNK_BYTES);
+                const uint64_t ad = umma_smem_desc(a_addr, 128, a_sbo), bd = umma_smem_desc(b_addr, 128, 2048);   // (see reg_fused.cu)
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    umma_bf16(tmem + col, umma_smem_desc(a_addr + k * 256, 128, a_sbo),
-                              umma_smem_desc(b_addr + k * 256, 128, 2048), idesc, (accumulate || k > 0) ? 1u : 0u);
+                    umma_bf16(tmem + col, ad + 16 * k, bd + 16 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
                 umma_commit(&bars[T_FREE0 + st]);
                 if (c + 2 < nchunk && c >= 1) issue_load(c + 2);
             };

@@ -196,19 +196,20 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
                 mbar_wait(&bars[B_QFULL], it & 1);
                 if (it > 0) mbar_wait(&bars[B_EPI], (it - 1) & 1);                 // O of the last tile has been read
                 tc_fence_after();
+                // descriptors once, then adds in the address field (+256 B = +16): see reg_fused.cu / tools/bench_micro
+                const uint64_t qd = umma_smem_desc(s_q, 128, 2048);
                 for (int n0 = 0; n0 < ns; n0 += 256) {                             // S = QK PE^T, N in parts of <= 256
                     const int np = min(256, ns - n0);
                     const uint32_t idesc = umma_idesc_bf16(128, np);
+                    const uint64_t pd = umma_smem_desc(s_pe + (n0 >> 3) * 2048, 128, 2048);
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
-                        umma_bf16(tmem + n0, umma_smem_desc(s_q + k * 256, 128, 2048),
-                                  umma_smem_desc(s_pe + (n0 >> 3) * 2048 + k * 256, 128, 2048), idesc, k > 0 ? 1u : 0u);
+                        umma_bf16(tmem + n0, qd + 16 * k, pd + 16 * k, idesc, k > 0 ? 1u : 0u);
                 }
+                const uint64_t wd = umma_smem_desc(smem_u32(smem + OFF_WB), 128, 2048);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)                                         // u = QK W_in (columns 7.. are zero)
-                    umma_bf16(tmem + U_COL, umma_smem_desc(s_q + k * 256, 128, 2048),
-                              umma_smem_desc(smem_u32(smem + OFF_WB) + k * 256, 128, 2048), umma_idesc_bf16(128, 16),
-                              k > 0 ? 1u : 0u);
+                    umma_bf16(tmem + U_COL, qd + 16 * k, wd + 16 * k, umma_idesc_bf16(128, 16), k > 0 ? 1u : 0u);
                 umma_commit(&bars[B_S]);
                 {   // the QK tile of this CTA's next tile, as soon as MMA 1 no longer reads the buffer
                     const int g2 = g + gridDim.x;
@@ -225,15 +226,15 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
                 if (CB > 0) {
                     mbar_wait(&bars[B_PB], it & 1);
                     tc_fence_after();
+                    const uint64_t ob = umma_smem_desc(s_pe + (CA / 2) * 4096, 2048, 128);
                     for (int k = 0; k < CB / 2; ++k)
-                        umma_bf16_ts(tmem + OB_COL, tmem + P_B_COL + 8 * k,
-                                     umma_smem_desc(s_pe + (CA / 2 + k) * 4096, 2048, 128), idesc_o, k > 0 ? 1u : 0u);
+                        umma_bf16_ts(tmem + OB_COL, tmem + P_B_COL + 8 * k, ob + 256 * k, idesc_o, k > 0 ? 1u : 0u);
                 }
                 mbar_wait(&bars[B_PA], it & 1);
                 tc_fence_after();
+                const uint64_t oa = umma_smem_desc(s_pe, 2048, 128);
                 for (int k = 0; k < CA / 2; ++k)
-                    umma_bf16_ts(tmem + OA_COL, tmem + 8 * k, umma_smem_desc(s_pe + k * 4096, 2048, 128), idesc_o,
-                                 k > 0 ? 1u : 0u);
+                    umma_bf16_ts(tmem + OA_COL, tmem + 8 * k, oa + 256 * k, idesc_o, k > 0 ? 1u : 0u);
                 umma_commit(&bars[B_O]);
             }
         }

@@ -175,11 +175,8 @@ __global__ void __launch_bounds__(UTHREADS) umma_linear_kernel(const UmmaArgs a)
         const uint32_t idesc = umma_idesc_bf16(UM, NT);
         const uint32_t lbo = 128u, sbo = (uint32_t)K * 16;
         const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-        for (int k = 0; k < K / 16; ++k) {
-            const uint64_t ad = umma_smem_desc(a0 + k * 256, lbo, sbo);
-            const uint64_t bd = umma_smem_desc(b0 + k * 256, lbo, sbo);
-            umma_bf16(tmem_base, ad, bd, idesc, k > 0 ? 1u : 0u);
-        }
+        const uint64_t ad = umma_smem_desc(a0, lbo, sbo), bd = umma_smem_desc(b0, lbo, sbo);   // then +256 B = +16 per k step
+        for (int k = 0; k < K / 16; ++k) umma_bf16(tmem_base, ad + 16 * k, bd + 16 * k, idesc, k > 0 ? 1u : 0u);
         umma_commit(&bars[1]);
     }
     __syncwarp();

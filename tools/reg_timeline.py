@@ -13,8 +13,10 @@ from chromoformer_b200 import ChromoformerClassifier, _lib, synthetic  # noqa: E
 
 NAMES = {1: "D x ready", 2: "D [q|k] issued", 3: "D [v|g] issued", 4: "D qkfree seen", 5: "D vgfree seen", 6: "D att ready",
          7: "D out-proj issued", 8: "D u ready", 9: "D ffn1 issued", 10: "D f ready A", 11: "D f ready B", 12: "D ffn2 issued",
+         13: "D   chunk in smem", 14: "D   mmas queued", 15: "D   prev chunk done, refill issued",
          20: "S accq seen", 21: "S q,k staged", 22: "S group barrier", 23: "S ofree seen", 24: "S sr seen", 25: "S P stored",
          26: "S vr seen (O issue)", 30: "V accvg seen", 31: "V v stored", 32: "V or seen", 33: "V att stored",
+         50: "E   acc loaded", 51: "E   partial sums stored", 52: "E   quarter barrier", 53: "E   U packed + stored",
          40: "E attention done", 41: "E barrier", 42: "E prm loaded", 43: "E acco seen", 44: "E u ready", 45: "E accf1 seen",
          46: "E f ready", 47: "E accf2 seen", 48: "E x ready"}
 
@@ -43,6 +45,7 @@ def main():
                                                T * 128, imp, fq.data_ptr(), B, ws.data_ptr(), nws, fl, st), "reg")
     run(flags)
     run(flags | _lib.F_PACKED)
+    only = set(int(x) for x in sys.argv[3].split(',')) if len(sys.argv) > 3 else None
     buf = torch.zeros(1536, dtype=torch.int64, device=dev)
     lib.chromo_debug_trace(ctypes.c_void_p(buf.data_ptr()))
     run(flags | _lib.F_PACKED)
@@ -62,7 +65,7 @@ def main():
     hi = starts[layer + 1] if layer + 1 < len(starts) else ev[-1][0] + 1
     prev = lo
     for t, e in ev:
-        if lo <= t < hi:
+        if lo <= t < hi and (only is None or e in only):
             print(f"{t - lo:7d}  (+{t - prev:5d})  {NAMES.get(e, e)}")
             prev = t
 
