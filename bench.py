@@ -28,8 +28,22 @@ KWS = ({"n_layers": 1, "n_heads": 2, "d_model": 128, "d_ff": 128},
        {"n_layers": 2, "n_heads": 2, "d_model": 128, "d_ff": 256},
        {"n_layers": 6, "n_heads": 8, "d_model": 256, "d_ff": 256})
 BINS = (2000, 500, 100)
-# dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel (ncu --set full, profiles/)
-REG_TRAFFIC = {"bytes": 137.2e6, "source": "ncu --set full, profiles/r01_summary_final.md (dram read 68.2 MB + write 69.1 MB)"}
+
+
+def ncu_traffic(kernel="reg_layer_fused_kernel"):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed export of the
+    `ncu --set full` capture (profiles/r02_ncu_metrics.json, written by tools/ncu_extract.py); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")
+    try:
+        d = json.load(open(path))[kernel]
+        unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        rd = d["dram__bytes_read.sum"] * unit[d["dram__bytes_read.sum#unit"]]
+        wr = d["dram__bytes_write.sum"] * unit[d["dram__bytes_write.sum#unit"]]
+        return {"bytes": rd + wr, "read": rd, "write": wr, "source": "profiles/r02_ncu_metrics.json (" + d.get("report", "?") + ")",
+                "tensor_pipe_active_pct": max([v for k, v in d.items() if k.startswith("sm__pipe_tensor") and
+                                               k.endswith("pct_of_peak_sustained_active") and isinstance(v, float)] or [None])}
+    except (OSError, KeyError, ValueError):
+        return None
 REF_FLOPS_PER_GENE = 3862328832          # as-written forward, SURVEY §8d tier A
 
 
@@ -270,6 +284,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--chunk", type=int, default=4096)
     ap.add_argument("--precision", choices=["fp32", "bf16"], default="bf16")
+    ap.add_argument("--train-precision", choices=["fp32", "bf16"], default="fp32")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")
@@ -289,7 +304,8 @@ def main():
     import torch
     import torch.distributed as dist
     from chromoformer_b200 import ChromoformerClassifier, ChromoformerRegressor, _lib, synthetic
-    from chromoformer_b200.engine import InferenceEngine, batch_nbytes, pin_batch
+    from chromoformer_b200.engine import InferenceEngine, batch_nbytes, pack_wire, pin_batch, wire_nbytes
+    from chromoformer_b200.parallel import bind_to_gpu_numa
     from chromoformer_b200.trainer import TrainStep
 
     rank = int(os.environ.get("RANK", "0"))
@@ -297,6 +313,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_note = bind_to_gpu_numa(local)          # before any pinned allocation
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -343,6 +360,13 @@ def main():
     launches_per_step = int(lib.chromo_launch_counter(1))
     t0 = time.time()
     ms = timed(lambda: eng.predict_device(resident, out), args.steps, args.warmup)
+    # `value` is EXACTLY --steps sweeps (the driver's contract); a short region (20 steps = 0.13 s) is followed by a second,
+    # >= 0.6 s region of the same step so that the clock samples and a sustained figure exist regardless of --steps
+    sustained = None
+    if ms * args.steps < 600.0:
+        n2 = int(600.0 / ms) + 1
+        ms2 = timed(lambda: eng.predict_device(resident, out), n2, 0)
+        sustained = {"steps": n2, "ms_per_step": ms2, "value": world * N_GENES / (ms2 * 1e-3), "unit": "genes/s"}
     t1 = time.time()
     clocks = None
     if rank == 0:
@@ -360,13 +384,66 @@ def main():
         sampler.stop()
     genes_per_s = world * N_GENES / (ms * 1e-3)
 
+    # ---------------- configs[3]: ragged genes (0..8 pCREs, demo-like lengths), same sweep size ----------------
+    del resident
+    rag_host = synthetic.make_batch(N_GENES, ragged=True, seed=1000 + rank)
+    rag = eng.to_device(rag_host)
+    ms_rag = timed(lambda: eng.predict_device(rag, out), max(5, args.steps // 4), 3)
+    ragged = {"what": "same sweep over ragged genes (pCRE count ~ demo histogram, valid 100-bp bins mean ~63 of 400)",
+              "value": world * N_GENES / (ms_rag * 1e-3), "unit": "genes/s", "ms_per_step": ms_rag}
+    del rag, rag_host
+    resident = eng.to_device(host)
+
     # ---------------- inference: end-to-end through the host API ---------------------------
-    pinned = pin_batch(host)
-    h2d = batch_nbytes(pinned)
-    ms_e2e = timed(lambda: eng.predict_host(pinned), max(2, args.steps // 2), 3)
+    # headline `e2e`: the FP16 / span wire format (engine.pack_wire -> predict_wire): pinned host buffers, H2D of every
+    # chunk + chromo_unpack_wire + forward + D2H of the logits, all inside the timed region.  Variants for context:
+    # the FP32 compact layout (round 1's e2e), the reference's own collation (FP32 + n x n masks, 1.63 MB per gene, on a
+    # 1024-gene sample) and raw .npy files through GeneBatcher (the staged demo genes).
+    wire = pack_wire(host)
+    h2d = wire_nbytes(wire)
+    e2e_steps = max(2, args.steps // 2)
+    ms_e2e = timed(lambda: eng.predict_wire(wire), e2e_steps, 3)
     e2e = {"value": world * N_GENES / (ms_e2e * 1e-3), "unit": "genes/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": N_GENES * 2 * 4, "ms_per_step": ms_e2e,
-           "h2d_gbs": world * h2d / (ms_e2e * 1e-3) / 1e9, "bound": "PCIe host->device copy of the FP32 features"}
+           "d2h_bytes_per_step": N_GENES * 2 * 4, "ms_per_step": ms_e2e, "api": "InferenceEngine.predict_wire(pack_wire(batch))",
+           "format": "FP16 features + (first valid bin, count) spans; FP32 / n x n masks rebuilt on the device",
+           "h2d_bytes_per_gene": h2d / N_GENES, "h2d_gbs": world * h2d / (ms_e2e * 1e-3) / 1e9,
+           "bound": "PCIe host->device copy", "numa": numa_note, "variants": {}}
+    pinned = pin_batch(host)
+    ms_v = timed(lambda: eng.predict_host(pinned), max(2, e2e_steps // 2), 2)
+    e2e["variants"]["fp32_compact"] = {"value": world * N_GENES / (ms_v * 1e-3), "unit": "genes/s", "h2d_bytes_per_gene": batch_nbytes(pinned) / N_GENES,
+                                       "what": "FP32 features + centre-row masks (round 1's e2e)"}
+    del pinned
+    n_full = 1024
+    full = pin_batch(synthetic.expand_full_masks(synthetic.slice_batch(host, 0, n_full)))
+    eng_full = InferenceEngine(model, chunk=256)
+    ms_v = timed(lambda: eng_full.predict_host(full), 3, 1)
+    e2e["variants"]["reference_collated"] = {"value": world * n_full / (ms_v * 1e-3), "unit": "genes/s",
+                                             "h2d_bytes_per_gene": batch_nbytes(full) / n_full,
+                                             "what": "the reference DataLoader's own collation (FP32 + [B,8,1,n,n] boolean masks), "
+                                                     f"{n_full}-gene sample in chunks of 256"}
+    del full, eng_full
+    demo_dir = os.path.join(ROOT, "baseline", "_ref", "demo")
+    if os.path.exists(os.path.join(demo_dir, "demo_meta_head.csv")) and rank == 0:
+        import pandas as pd
+        from chromoformer_b200.data import ChromoformerDataset, GeneBatcher
+        meta = os.path.join(demo_dir, "demo_meta_head.csv")
+        genes = pd.read_csv(meta).gene_id.tolist()
+        ds = ChromoformerDataset(meta, os.path.join(demo_dir, "demo_data"), genes)
+        gb = GeneBatcher(ds, device=dev, cache=False)
+
+        def raw_npy():
+            b = gb.batch(list(range(len(genes))))
+            with torch.no_grad():
+                return model.forward_batch(b).cpu()
+        raw_npy()
+        t0 = time.perf_counter()
+        for _ in range(3):
+            raw_npy()
+        dt = (time.perf_counter() - t0) / 3
+        e2e["variants"]["raw_npy_genebatcher"] = {"value": len(genes) / dt, "unit": "genes/s", "genes": len(genes),
+                                                  "what": "np.load of the staged demo regions (page cache) -> pinned FP16 -> device binning "
+                                                          "kernel -> forward -> host, one process, no DataLoader (reference __getitem__: "
+                                                          "see cpu_baseline.getitem)"}
 
     # ---------------- dominant kernel alone ----------------------------------------------------
     # BF16: the fused Regulation layer (reg_layer_fused_kernel, 1/3 of the step); FP32: the batched projection GEMM.
@@ -396,9 +473,9 @@ def main():
         ms_k = timed(one_kernel, 20, 5)
         flops_k = n_lay * 3.0 * T * 2 * (4 * 256 * 128 + 256 * 128 + 2 * 128 * 256 + 8 * 9 * 32 * 2)
         bytes_k = 2.0 * 3 * T * 128 * 4 + n_lay * 3 * 14 * 32768
-        kname = (f"reg_layer_fused_kernel<9,true>: the {n_lay} Regulation layers in one launch, 3 resolutions x {T} tokens "
+        kname = (f"reg_layer_fused_kernel<9>: the {n_lay} Regulation layers in one launch, 3 resolutions x {T} tokens "
                  "(per layer: proj + tensor-pipe attention + out-proj/LN + FFN/LN; tcgen05 + TMA weight stream)")
-        traffic = REG_TRAFFIC
+        traffic = ncu_traffic()
         # second kernel: the fused single-query attention core at n = 400 (HBM-bound: 11.2 KB of features per region)
         nreg_s = Bk * 8
         g = torch.Generator(device="cpu").manual_seed(1)
@@ -538,7 +615,7 @@ def main():
     train = None
     if not args.no_train:
         reg = make_model(ChromoformerRegressor).cuda().train()
-        reg.precision = args.precision
+        reg.precision = args.train_precision      # the precision the gradient-parity tests cover (tests/test_training_gpu.py)
         tb = synthetic.make_batch(64, ragged=False, seed=100 + rank)
         tdev = {k: ({b: t.to(dev) for b, t in v.items()} if isinstance(v, dict) else v.to(dev)) for k, v in tb.items()}
         target = tdev["labels_reg"].view(-1, 1)
@@ -549,6 +626,7 @@ def main():
         ms_t = timed(lambda: step(tdev, target), 20, 5)
         train = {"metric": "train samples/sec", "value": world * 64 / (ms_t * 1e-3), "unit": "samples/s",
                  "ms_per_step": ms_t, "per_gpu_batch": 64, "model": "Chromoformer-reg", "gpu_launches": train_launches,
+                 "dtype": args.train_precision,
                  "collective": "nccl all_reduce of %d fp32 grads" % reg.n_active if world > 1 else "none (1 GPU)",
                  "loss": float(step.loss.item())}
 
@@ -569,6 +647,7 @@ def main():
                 "scaling": "weak", "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
                 "config": workload_config(args), "clocks": clocks, "e2e": e2e,
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+                "sustained": sustained, "ragged": ragged,
                 "roofline": roofline, "sqa_kernel": sqa_line, "input_path": input_path, "raw_depth_path": raw_path, "ensemble_sweep": sweep, "cpu_baseline": cpu,
                 "train": train}
         sys.stdout.flush()

@@ -30,6 +30,28 @@ def init_distributed(backend=None):
     return rank, local, world
 
 
+def bind_to_gpu_numa(local_rank):
+    """Pin this process to the CPUs NVML reports as local to its GPU BEFORE it allocates pinned host buffers, so that
+    the staging memory of every rank sits on the NUMA node (and behind the PCIe root) of that rank's GPU instead of
+    wherever the launcher happened to start the process.  Returns a short description for the bench line."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(local_rank))
+        n_cpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (n_cpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (int(word) >> b) & 1 and 64 * w + b < n_cpu]
+        if not cpus:
+            return "nvml reported no local CPUs"
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return "local CPUs outside this process's cpuset"
+        os.sched_setaffinity(0, allowed)
+        return f"{len(allowed)} CPUs local to GPU {local_rank} ({allowed[0]}..{allowed[-1]})"
+    except Exception as e:                                          # noqa: BLE001 - best effort, never fatal
+        return f"unavailable ({type(e).__name__})"
+
+
 def shard_range(n_items, rank, world):
     """Contiguous, balanced [lo, hi) slice of `n_items` units for `rank` (sizes differ by <= 1)."""
     base, rem = divmod(n_items, world)
