@@ -3,7 +3,10 @@ optimiser/scheduler settings and checkpoint layout as the reference script (trai
 52-68, 79-103, 156-158, 322-343), running on the sm_100a kernels.
 
 Differences that do not change results: the fused AdamW (one launch) replaces
-torch.optim.AdamW, anomaly detection is off, and wandb is imported only with --use-wandb.
+torch.optim.AdamW, anomaly detection is off, wandb is imported only with --use-wandb, and the
+metrics of train.py:198-251,286-320 (sklearn / scipy on out.cpu()) are evaluated on the device
+(`chromoformer_b200.metrics.DeviceMetrics`: logits never leave the GPU; one small host read per
+log line instead of one per step).
 """
 import argparse
 import os
@@ -13,6 +16,7 @@ import torch
 import yaml
 
 from chromoformer_b200.data import ChromoformerDataset
+from chromoformer_b200.metrics import DeviceMetrics
 from chromoformer_b200.model import ChromoformerClassifier, ChromoformerRegressor
 from chromoformer_b200.optim import FusedAdamW
 
@@ -43,17 +47,6 @@ def to_device(batch, device):
 def call_model(model, d):
     return model(d["promoter_feats"], d["promoter_pad_masks"], d["pcre_feats"], d["pcre_pad_masks"],
                  d["interaction_masks"], d["interaction_freq"])
-
-
-def metrics_of(out, label, regression):
-    from scipy import stats
-    from sklearn import metrics
-    if regression:
-        pred, lab = out.flatten().numpy(), label.flatten().numpy()
-        return {"r2": metrics.r2_score(lab, pred) * 100, "r": stats.pearsonr(lab, pred)[0] * 100}
-    score, pred, lab = out.softmax(dim=1)[:, 1].numpy(), out.argmax(dim=1).numpy(), label.numpy()
-    return {"acc": metrics.accuracy_score(lab, pred) * 100, "auc": metrics.roc_auc_score(lab, score) * 100,
-            "ap": metrics.average_precision_score(lab, score) * 100}
 
 
 def main(argv=None):
@@ -103,7 +96,8 @@ def main(argv=None):
     val_loss = val_key = None
     for epoch in range(1, cfg["num_epoch"]):
         model.train()
-        running, outs, labels = 0.0, [], []
+        running = torch.zeros((), device=device)
+        log = DeviceMetrics(args.regression, capacity=10 * cfg["bsz"], device=device)
         for i, d in enumerate(train_loader, 1):
             d = to_device(d, device)
             if args.regression:
@@ -113,33 +107,36 @@ def main(argv=None):
             loss = criterion(out, d["label"])
             loss.backward()
             optimizer.step()
-            running += loss.item()
-            outs.append(out.detach().cpu()); labels.append(d["label"].cpu())
+            running += loss.detach()
+            log.update(out, d["label"])
             if i % 10 == 0:
-                m = metrics_of(torch.cat(outs), torch.cat(labels), args.regression)
+                m = log.compute()
+                m.pop("mse", None)
                 text = ", ".join(f"{k}={v:.4f}" for k, v in m.items())
-                print(f"E{epoch} [{i}/{len(train_loader)}] {running / 10.0:.4f}, lr={optimizer.param_groups[0]['lr']}, {text}")
+                mean_loss = running.item() / 10.0
+                print(f"E{epoch} [{i}/{len(train_loader)}] {mean_loss:.4f}, lr={optimizer.param_groups[0]['lr']}, {text}")
                 if wandb:
-                    wandb.log({"train/loss": running / 10.0, **{f"train/{k}": v for k, v in m.items()}})
-                running, outs, labels = 0.0, [], []
+                    wandb.log({"train/loss": mean_loss, **{f"train/{k}": v for k, v in m.items()}})
+                running.zero_()
+                log.reset()
 
         model.eval()
-        outs, labels = [], []
+        val = DeviceMetrics(args.regression, capacity=len(val_genes), device=device)
         with torch.no_grad():
             for d in val_loader:
                 d = to_device(d, device)
-                outs.append(call_model(model, d).cpu()); labels.append(d["label"].cpu())
-        val_out, val_label = torch.cat(outs), torch.cat(labels)
-        val_loss = criterion(val_out, val_label.view(-1, 1) if args.regression else val_label)
-        m = metrics_of(val_out, val_label, args.regression)
+                val.update(call_model(model, d), d["label"])
+        val_out, val_label = val.logits, val.labels
+        val_loss = criterion(val_out, val_label.view(-1, 1) if args.regression else val_label).cpu()
+        m = val.compute()
+        m.pop("mse", None)
         print(f"Validation loss={val_loss:.4f}, " + ", ".join(f"{k}={v:.4f}" for k, v in m.items()))
         if wandb:
             wandb.log({"val/loss": val_loss, "val/epoch": epoch, **{f"val/{k}": v for k, v in m.items()}})
         val_key = ("last_val_r2", m["r2"]) if args.regression else ("last_val_auc", m["auc"])
-        score = val_out.flatten().numpy() if args.regression else val_out.softmax(dim=1)[:, 1].numpy()
         torch.save({"net": model.state_dict(), "optimizer": optimizer.state_dict(), "epoch": epoch,
-                    "last_val_loss": val_loss, val_key[0]: val_key[1], "val_score": score,
-                    "val_label": val_label.numpy()}, args.output)
+                    "last_val_loss": val_loss, val_key[0]: val_key[1], "val_score": val.score.cpu().numpy(),
+                    "val_label": val_label.cpu().numpy()}, args.output)
         scheduler.step()
     if wandb and val_key:
         wandb.summary.update({"last_val_loss": val_loss, val_key[0]: val_key[1]})

@@ -82,8 +82,12 @@ EXPORTS = {
     "chromo_debug_umma_probe": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "chromo_backward": (c_int32, [POINTER(Config), c_void_p, POINTER(Batch), c_void_p, c_void_p, c_void_p,
                                   c_int64, c_int32, c_void_p]),
+    "chromo_matmul": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32,
+                                c_int32, c_int32, c_int32, c_void_p]),
     "chromo_mse_loss": (c_int32, [c_void_p, c_void_p, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
     "chromo_ce_loss": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p]),
+    "chromo_clf_metrics": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "chromo_reg_metrics": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "chromo_adamw": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float,
                                c_float, c_float, c_int32, c_float, c_void_p]),
     "chromo_unpack_wire": (c_int32, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int32,

@@ -7,11 +7,13 @@
 //     y = LN(x + f(x)):   g <- LN'(g);  (weight grads of f);  g <- g + f'(g)
 // Every dense contraction reuses the batched GEMM (data grads: NN form, weight
 // grads: A^T form with split-K atomics).
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "kernels.cuh"
+#include "umma_train.cuh"
 
 namespace chromo {
 
@@ -290,6 +292,7 @@ namespace {
 struct Ctx {
     cudaStream_t st;
     int NR;
+    bool tc = false;        // CHROMO_F_BF16: contractions on the tensor pipe (umma_train.cu) where the shape qualifies
 };
 
 // Split-K factor: the training batch is small (bsz 64 => a few hundred rows), so most gradient
@@ -306,6 +309,15 @@ inline int ksplit_for(int K, int M = 4096, int N = 4096, int nz = 1) {
 // dX (=|+=) dY W        dY [M,N] (ld ldy), W [N,K] row-major, dX [M,K] (ld lddx)
 int bwd_data(const Ctx& c, const float* dY, int ldy, long long dy_z, const float* W, long long w_z, float* dX,
              int lddx, long long dx_z, int M, int N, int K, bool accumulate, int nz) {
+    if (c.tc && M >= 64) {      // dX = dY W: A = dY rows (K-major), B = W rows [n, k] (MN-major: k contiguous)
+        TGemmArgs t;
+        t.A = dY; t.lda = ldy; t.a_z = dy_z; t.a_t = 0; t.a_div = 1;
+        t.B = W; t.ldb = K; t.b_z = w_z; t.b_t = 1; t.b_div = 1;
+        t.C = dX; t.ldc = lddx; t.c_z = dx_z; t.M = M; t.N = K; t.Kc = N; t.NT = 0;
+        t.atomic = accumulate ? 1 : 0;
+        t.ksplit = accumulate ? (N + 255) / 256 : 1;
+        if (tgemm_supported(t)) return tgemm_launch(t, nz, c.st);
+    }
     GemmArgs g = gemm_args();
     g.A = dY; g.lda = ldy; g.sA1 = dy_z;
     g.B = W; g.ldb = K; g.sB1 = w_z;
@@ -318,6 +330,15 @@ int bwd_data(const Ctx& c, const float* dY, int ldy, long long dy_z, const float
 // dW += dY^T X          dY [M,N], X [M/x_div rows broadcast, K] (ld ldx), dW [N,K] row-major
 int bwd_weight(const Ctx& c, const float* dY, int ldy, long long dy_z, const float* X, int ldx, int x_div,
                long long x_z, float* dW, int lddw, long long dw_z, int M, int N, int K, int nz) {
+    if (c.tc && M >= 64 && N >= 16) {   // dW += dY^T X: both operands MN-major (rows = tokens = the contraction)
+        TGemmArgs t;
+        t.A = dY; t.lda = ldy; t.a_z = dy_z; t.a_t = 1; t.a_div = 1;
+        t.B = X; t.ldb = ldx; t.b_z = x_z; t.b_t = 1; t.b_div = x_div;
+        t.C = dW; t.ldc = lddw; t.c_z = dw_z; t.M = N; t.N = K; t.Kc = M; t.NT = 0;
+        t.atomic = 1;
+        t.ksplit = (M + 127) / 128;                 // one 128-token chunk per CTA
+        if (tgemm_supported(t)) return tgemm_launch(t, nz, c.st);
+    }
     GemmArgs g = gemm_args();
     g.A = dY; g.lda = ldy; g.sA1 = dy_z;
     g.B = X; g.ldb = ldx; g.b_div = x_div; g.sB1 = x_z;
@@ -443,14 +464,14 @@ int sqa_bwd(const Ctx& c, const SqaBwd& s) {
 }  // namespace
 
 static int backward_impl(const chromo_config_t* c, const float* P, const chromo_batch_t* in, const float* dlogits,
-                         float* G, float* ws, const WsLayout& w, cudaStream_t st) {
+                         float* G, float* ws, const WsLayout& w, cudaStream_t st, bool tc) {
     const ParamLayout& L = get_layout(c);
     const int B = w.B, I = w.I, S = w.S, R = w.R, T = w.T, D = w.D, F = c->n_feats, NR = c->n_res;
     const long long RS = w.res_stride;
     const int dme = c->embed_d_model, He = c->embed_heads, dffe = c->embed_d_ff;
     const int dmp = c->pw_d_model, Hp = c->pw_heads, dffp = c->pw_d_ff;
     const int dmr = c->reg_d_model, Hr = c->reg_heads, dffr = c->reg_d_ff;
-    Ctx cx{st, NR};
+    Ctx cx{st, NR, tc};
 
     // ---- gradient scratch ---------------------------------------------------
     int64_t cur = w.g_base;
@@ -477,7 +498,7 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
 
     // ---- head (net.py:377-380) ------------------------------------------------
     {
-        Ctx c1{st, 1};
+        Ctx c1{st, 1, tc};
         const int dh = c->d_head, no = c->n_out;
         CHROMO_TRY(bwd_weight(c1, dlogits, no, 0, ws + w.h_h1, dh, 1, 0, G + L.fc2w, dh, 0, B, no, dh, 1));
         CHROMO_TRY(bwd_bias(c1, dlogits, no, 0, G + L.fc2b, 0, B, no, 1));
@@ -611,7 +632,7 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
         // gE = dHc;  Hc = W_lp x_c + PE_c  ->  dW_lp += dHc^T x_p[:, c, :]
         for (int r = 0; r < NR; ++r) {
             const int n = c->n_bins[r];
-            Ctx c1{st, 1};
+            Ctx c1{st, 1, tc};
             CHROMO_TRY(bwd_weight(c1, gE + r * GS, D, 0, in->x_p[r] + (long long)(n / 2) * F, n * F, 1, 0,
                                   G + L.embed[r].lin_proj, F, 0, B, D, F, 1));
         }
@@ -635,5 +656,6 @@ extern "C" int chromo_backward(const chromo_config_t* cfg, const float* params, 
         set_error("workspace too small: need %lld floats, got %lld", (long long)w.total, (long long)workspace_floats);
         return CHROMO_ENOMEM;
     }
-    return backward_impl(cfg, params, in, dlogits, grads, workspace, w, (cudaStream_t)stream);
+    return backward_impl(cfg, params, in, dlogits, grads, workspace, w, (cudaStream_t)stream,
+                         (flags & CHROMO_F_BF16) != 0 && !getenv("CHROMO_BWD_FP32"));
 }

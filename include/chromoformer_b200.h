@@ -158,6 +158,16 @@ int chromo_backward(const chromo_config_t* cfg, const float* params, const chrom
                     const float* dlogits /* [B,n_out] */, float* grads, float* workspace,
                     int64_t workspace_floats, int32_t flags, void* stream);
 
+/* ---- the contraction of the training step on the tensor pipe (train.py:195: autograd of nn.Linear) --------
+ * C[M,N] (=|+=) opA . opB^T with BF16 operands converted on the fly and FP32 accumulation (tcgen05 / TMEM):
+ *   a_transposed = 0: A is [M,K] (ld lda); 1: A is [K,M]        b_transposed = 0: B is [N,K] (ld ldb); 1: B is [K,N]
+ * data gradient  dX = dY W   : chromo_matmul(dY, ., 0, W, ., 1, dX, ...)    (W [N_out, K_in] as stored by nn.Linear)
+ * weight gradient dW += dY^T X: chromo_matmul(dY, ., 1, X, ., 1, dW, ..., accumulate = 1, ksplit = token chunks)
+ * chromo_backward routes every qualifying contraction through this kernel when CHROMO_F_BF16 is set.  N % 16 == 0,
+ * leading dimensions % 4 == 0, 16-byte aligned pointers; ksplit > 1 needs accumulate (FP32 atomics).            */
+int chromo_matmul(const float* A, int64_t lda, int32_t a_transposed, const float* B, int64_t ldb, int32_t b_transposed,
+                  float* C, int64_t ldc, int32_t M, int32_t N, int32_t K, int32_t accumulate, int32_t ksplit, void* stream);
+
 /* ---- losses: train.py:156,193 (mean reduction); write loss[0] and dlogits -- */
 int chromo_mse_loss(const float* logits, const float* target, int32_t count, float grad_scale,
                     float* loss, float* dlogits, void* stream);
@@ -170,6 +180,18 @@ int chromo_ce_loss(const float* logits, const int64_t* labels, int32_t batch, in
 int chromo_adamw(float* params, const float* grads, float* exp_avg, float* exp_avg_sq,
                  int64_t count, float lr, float beta1, float beta2, float eps,
                  float weight_decay, int32_t step, float grad_scale, void* stream);
+
+/* ---- validation metrics on the device: train.py:198-251 (training log) and 286-320 (validation) --------------
+ * Replaces out.cpu() + sklearn.metrics.{accuracy_score, roc_auc_score, average_precision_score} / r2_score +
+ * scipy.stats.pearsonr.  Rank statistics are exact pair counts (ties as sklearn treats them), sums in FP64.
+ * chromo_clf_metrics: logits [n, n_out] (n_out >= 2), labels int64 [n]; writes score[n] = softmax(logits)[:, 1]
+ *   (the `val_score` the checkpoint keeps, train.py:322-343) and out[4] = {accuracy, AUROC, average precision,
+ *   #positives}; `scratch` = 32 bytes of device memory.
+ * chromo_reg_metrics: pred, labels FP32 [n]; out[3] = {r2_score(labels, pred), pearsonr, MSE}.
+ * Fractions, not percent.  Asynchronous on `stream`; nothing is copied to the host.                              */
+int chromo_clf_metrics(const float* logits, const int64_t* labels, int32_t n, int32_t n_out, float* score,
+                       double* out, void* scratch, void* stream);
+int chromo_reg_metrics(const float* pred, const float* labels, int32_t n, double* out, void* stream);
 
 /* ---- input path: data.py:68-113 -------------------------------------------
  * Bins raw per-bp depth (FP16 [F,L] per region, regions concatenated in one

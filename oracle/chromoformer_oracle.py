@@ -228,6 +228,27 @@ def legacy_to_dict_layout(sd):
 
 
 # ----------------------------------------------------------------------------- training
+class bf16_operands:
+    """Context manager: every `@` contraction of the restatement (the nn.Linear call sites, modules.py:38,48,100-101,
+    159-160; the attention products use torch.matmul and stay FP32) sees its two operands rounded to BF16, with a
+    straight-through gradient - the arithmetic contract of `precision = "bf16"` (BF16 operands, FP32 accumulation).  A
+    yardstick for how far BF16 training gradients may sit from FP32 ones: the rounding itself, not a kernel's fault."""
+
+    def __enter__(self):
+        self._orig = torch.Tensor.__matmul__
+        orig = self._orig
+
+        def rnd(x):
+            return x + (x.to(torch.bfloat16).to(x.dtype) - x).detach()
+
+        torch.Tensor.__matmul__ = lambda a, b: orig(rnd(a), rnd(b))
+        return self
+
+    def __exit__(self, *exc):
+        torch.Tensor.__matmul__ = self._orig
+        return False
+
+
 def loss_fn(logits, target, regression):
     """train.py:156,193: MSELoss / CrossEntropyLoss with mean reduction."""
     if regression:
