@@ -13,17 +13,17 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "kernels.cuh"
-#include "umma_train.cuh"
+#include "train_gemm.cuh"
 
 namespace chromo {
 
 // ------------------------------------------------------------------ kernels --
 
-// LayerNorm backward, in place on g (dy -> dz); one warp per row of 128.
+// LayerNorm backward (dy -> dz, `gout` may alias `gin`); one warp per row of 128.
 struct LnBwdArgs {
     int M;
     const float* pre; long long pre_z;
-    float* g; long long g_z;
+    const float* gin; float* g; long long g_z;
     const float* gamma; float* dgamma; float* dbeta; long long p_z;
 };
 __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
@@ -32,12 +32,13 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
     const int z = blockIdx.y;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float* pre = a.pre + z * a.pre_z;
+    const float* gin = a.gin + z * a.g_z;
     float* g = a.g + z * a.g_z;
     const float4 ga = *reinterpret_cast<const float4*>(a.gamma + z * a.p_z + lane * 4);
     float dg[4] = {0, 0, 0, 0}, db[4] = {0, 0, 0, 0};
     for (int m = blockIdx.x * 8 + warp; m < a.M; m += gridDim.x * 8) {
         const float4 zv = *reinterpret_cast<const float4*>(pre + (long long)m * 128 + lane * 4);
-        float4 dy = *reinterpret_cast<float4*>(g + (long long)m * 128 + lane * 4);
+        float4 dy = *reinterpret_cast<const float4*>(gin + (long long)m * 128 + lane * 4);
         float s = zv.x + zv.y + zv.z + zv.w;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
@@ -75,13 +76,6 @@ __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
         atomicAdd(a.dgamma + z * a.p_z + threadIdx.x, x);
         atomicAdd(a.dbeta + z * a.p_z + threadIdx.x, y);
     }
-}
-
-// g *= (f > 0)
-__global__ void relu_bwd_kernel(float* g, const float* f, long long count, long long g_z, long long f_z) {
-    const int z = blockIdx.y;
-    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < count && !(f[z * f_z + i] > 0.f)) g[z * g_z + i] = 0.f;
 }
 
 // out[n] += sum_m dY[m, n]      (bias gradients)
@@ -289,10 +283,14 @@ __global__ void __launch_bounds__(256) attn_rows_bwd_kernel(AttnRowsBwdArgs a) {
 // ------------------------------------------------------------ host helpers ---
 namespace {
 
+// Every gradient tensor of the pass has a buffer of its own (nothing is updated in place), so the weight / bias
+// gradients can be taken from them at any later point: on the tensor path they are queued (`q`) and run as ONE
+// persistent launch at the end of the pass; the strict FP32 path launches them where they arise.
 struct Ctx {
     cudaStream_t st;
     int NR;
-    bool tc = false;        // CHROMO_F_BF16: contractions on the tensor pipe (umma_train.cu) where the shape qualifies
+    bool tc = false;            // CHROMO_F_BF16: contractions on the tensor pipe (train_gemm.cu)
+    WgradQueue* q = nullptr;    // tc: the deferred weight / bias gradients
 };
 
 // Split-K factor: the training batch is small (bsz 64 => a few hundred rows), so most gradient
@@ -306,38 +304,36 @@ inline int ksplit_for(int K, int M = 4096, int N = 4096, int nz = 1) {
     return want < 1 ? 1 : (int)want;
 }
 
-// dX (=|+=) dY W        dY [M,N] (ld ldy), W [N,K] row-major, dX [M,K] (ld lddx)
+// dX = [res +] mask( dY W )     dY [M,N] (ld ldy), W [N,K] row-major, dX [M,K] (ld lddx); res [M,K] (ld lddx, same batch
+// stride as dX) is the gradient arriving over the residual connection, mask [M,K] (ld K) the ReLU output of the forward
+struct DataEpi { const float* res = nullptr; const float* mask = nullptr; long long mask_z = 0; };
 int bwd_data(const Ctx& c, const float* dY, int ldy, long long dy_z, const float* W, long long w_z, float* dX,
-             int lddx, long long dx_z, int M, int N, int K, bool accumulate, int nz) {
-    if (c.tc && M >= 64) {      // dX = dY W: A = dY rows (K-major), B = W rows [n, k] (MN-major: k contiguous)
-        TGemmArgs t;
-        t.A = dY; t.lda = ldy; t.a_z = dy_z; t.a_t = 0; t.a_div = 1;
-        t.B = W; t.ldb = K; t.b_z = w_z; t.b_t = 1; t.b_div = 1;
-        t.C = dX; t.ldc = lddx; t.c_z = dx_z; t.M = M; t.N = K; t.Kc = N; t.NT = 0;
-        t.atomic = accumulate ? 1 : 0;
-        t.ksplit = accumulate ? (N + 255) / 256 : 1;
-        if (tgemm_supported(t)) return tgemm_launch(t, nz, c.st);
+             int lddx, long long dx_z, int M, int N, int K, const DataEpi& e, int nz) {
+    if (c.tc && K % 16 == 0) {      // A = dY rows (K-major), B = W rows [n, k] (MN-major: k contiguous)
+        TcGemm t = tc_gemm_args();
+        t.A = dY; t.lda = ldy; t.a_z = dy_z;
+        t.B = W; t.ldb = K; t.b_z = w_z; t.b_t = 1;
+        t.C = dX; t.ldc = lddx; t.c_z = dx_z; t.M = M; t.N = K; t.Kc = N;
+        if (e.res) { t.epi |= TC_RES; t.res = e.res; t.ldres = lddx; t.res_z = dx_z; }
+        if (e.mask) { t.epi |= TC_MASK; t.mask = e.mask; t.ldmask = K; t.mask_z = e.mask_z; }
+        if (tc_gemm_supported(t)) return tc_gemm_launch(t, nz, c.st);
     }
     GemmArgs g = gemm_args();
     g.A = dY; g.lda = ldy; g.sA1 = dy_z;
     g.B = W; g.ldb = K; g.sB1 = w_z;
     g.C = dX; g.ldc = lddx; g.sC1 = dx_z;
-    g.M = M; g.N = K; g.K = N; g.accumulate = accumulate ? 1 : 0;
-    if (accumulate) g.ksplit = ksplit_for(N, M, K, nz);      // atomics are fine on an accumulating output
+    g.M = M; g.N = K; g.K = N;
+    if (e.res) { g.res_plain = 1; g.res = e.res; g.ldres = lddx; g.sRes1 = dx_z; }
+    if (e.mask) { g.mask = e.mask; g.ldmask = K; g.sMask1 = e.mask_z; }
     return gemm_launch(g, true, false, nz, c.st);
 }
 
 // dW += dY^T X          dY [M,N], X [M/x_div rows broadcast, K] (ld ldx), dW [N,K] row-major
 int bwd_weight(const Ctx& c, const float* dY, int ldy, long long dy_z, const float* X, int ldx, int x_div,
                long long x_z, float* dW, int lddw, long long dw_z, int M, int N, int K, int nz) {
-    if (c.tc && M >= 64 && N >= 16) {   // dW += dY^T X: both operands MN-major (rows = tokens = the contraction)
-        TGemmArgs t;
-        t.A = dY; t.lda = ldy; t.a_z = dy_z; t.a_t = 1; t.a_div = 1;
-        t.B = X; t.ldb = ldx; t.b_z = x_z; t.b_t = 1; t.b_div = x_div;
-        t.C = dW; t.ldc = lddw; t.c_z = dw_z; t.M = N; t.N = K; t.Kc = M; t.NT = 0;
-        t.atomic = 1;
-        t.ksplit = (M + 127) / 128;                 // one 128-token chunk per CTA
-        if (tgemm_supported(t)) return tgemm_launch(t, nz, c.st);
+    if (c.q) {      // both operands MN-major (rows = tokens = the contraction); runs at the end of the pass
+        c.q->add_weight(dY, ldy, dy_z, X, ldx, x_div, x_z, dW, lddw, dw_z, M, N, K, nz);
+        return CHROMO_OK;
     }
     GemmArgs g = gemm_args();
     g.A = dY; g.lda = ldy; g.sA1 = dy_z;
@@ -351,6 +347,10 @@ int bwd_weight(const Ctx& c, const float* dY, int ldy, long long dy_z, const flo
 
 int bwd_bias(const Ctx& c, const float* dY, int ld, long long dy_z, float* db, long long db_z, int M, int N,
              int nz) {
+    if (c.q) {
+        c.q->add_bias(dY, ld, dy_z, db, db_z, M, N, nz);
+        return CHROMO_OK;
+    }
     const int rpb = 16;
     dim3 grid((N + 127) / 128, (M + rpb - 1) / rpb, nz);
     colsum_kernel<<<grid, 128, 0, c.st>>>(dY, M, N, ld, dy_z, db, db_z, rpb);
@@ -358,9 +358,9 @@ int bwd_bias(const Ctx& c, const float* dY, int ld, long long dy_z, float* db, l
     return CHROMO_OK;
 }
 
-int ln_bwd(const Ctx& c, const float* pre, long long pre_z, float* g, long long g_z, const float* gamma,
-           float* dgamma, float* dbeta, long long p_z, int M, int nz) {
-    LnBwdArgs a{M, pre, pre_z, g, g_z, gamma, dgamma, dbeta, p_z};
+int ln_bwd(const Ctx& c, const float* pre, long long pre_z, const float* gin, float* gout, long long g_z,
+           const float* gamma, float* dgamma, float* dbeta, long long p_z, int M, int nz) {
+    LnBwdArgs a{M, pre, pre_z, gin, gout, g_z, gamma, dgamma, dbeta, p_z};
     int blocks = (M + 7) / 8;
     if (blocks > 296) blocks = 296;
     ln_bwd_kernel<<<dim3(blocks, nz), 256, 0, c.st>>>(a);
@@ -368,24 +368,21 @@ int ln_bwd(const Ctx& c, const float* pre, long long pre_z, float* g, long long 
     return CHROMO_OK;
 }
 
-int relu_bwd(const Ctx& c, float* g, long long g_z, const float* f, long long f_z, long long count, int nz) {
-    relu_bwd_kernel<<<dim3((unsigned)((count + 255) / 256), nz), 256, 0, c.st>>>(g, f, count, g_z, f_z);
-    CHROMO_CHECK_LAUNCH("relu_bwd");
-    return CHROMO_OK;
-}
-
-// Backward of  y = LN(u + W2 relu(W1 u + b1) + b2)  in place on g [M,128].
+// Backward of  y = LN(u + W2 relu(W1 u + b1) + b2):  gin = dy [M,128]  ->  gA = LN'(gin), dF = relu'(gA W2),
+// gout = gA + dF W1 (= du).  gA and dF stay untouched afterwards (weight gradients).
 int ffn_bwd(const Ctx& c, const float* P, float* G, const FfnOff& f, long long p_z, int dff, const float* u,
-            const float* fact, const float* preY, long long act_z, float* g, float* dF, long long g_z, int M) {
+            const float* fact, const float* preY, long long act_z, const float* gin, float* gA, float* dF, float* gout,
+            long long g_z, int M) {
     const int D = 128, nz = c.NR;
-    CHROMO_TRY(ln_bwd(c, preY, act_z, g, g_z, P + f.lnw, G + f.lnw, G + f.lnb, p_z, M, nz));
-    CHROMO_TRY(bwd_weight(c, g, D, g_z, fact, dff, 1, act_z, G + f.l2w, dff, p_z, M, D, dff, nz));
-    CHROMO_TRY(bwd_bias(c, g, D, g_z, G + f.l2b, p_z, M, D, nz));
-    CHROMO_TRY(bwd_data(c, g, D, g_z, P + f.l2w, p_z, dF, dff, g_z, M, D, dff, false, nz));
-    CHROMO_TRY(relu_bwd(c, dF, g_z, fact, act_z, (long long)M * dff, nz));
+    CHROMO_TRY(ln_bwd(c, preY, act_z, gin, gA, g_z, P + f.lnw, G + f.lnw, G + f.lnb, p_z, M, nz));
+    CHROMO_TRY(bwd_weight(c, gA, D, g_z, fact, dff, 1, act_z, G + f.l2w, dff, p_z, M, D, dff, nz));
+    CHROMO_TRY(bwd_bias(c, gA, D, g_z, G + f.l2b, p_z, M, D, nz));
+    DataEpi relu; relu.mask = fact; relu.mask_z = act_z;
+    CHROMO_TRY(bwd_data(c, gA, D, g_z, P + f.l2w, p_z, dF, dff, g_z, M, D, dff, relu, nz));
     CHROMO_TRY(bwd_weight(c, dF, dff, g_z, u, D, 1, act_z, G + f.l1w, D, p_z, M, dff, D, nz));
     CHROMO_TRY(bwd_bias(c, dF, dff, g_z, G + f.l1b, p_z, M, dff, nz));
-    CHROMO_TRY(bwd_data(c, dF, dff, g_z, P + f.l1w, p_z, g, D, g_z, M, dff, D, true, nz));
+    DataEpi resid; resid.res = gA;
+    CHROMO_TRY(bwd_data(c, dF, dff, g_z, P + f.l1w, p_z, gout, D, g_z, M, dff, D, resid, nz));
     return CHROMO_OK;
 }
 
@@ -401,6 +398,7 @@ struct SqaBwd {
 
 int sqa_bwd(const Ctx& c, const SqaBwd& s) {
     const int dh = s.dm / s.H, D = s.D, RH = s.rows * s.H;
+    Ctx c1 = c; c1.NR = 1;
     {   // dCbar[(r,h), :] = dAv[r, h] W_v[h]
         GemmArgs g = gemm_args();
         g.A = s.dAv; g.lda = s.dm; g.sA2 = dh;
@@ -409,14 +407,10 @@ int sqa_bwd(const Ctx& c, const SqaBwd& s) {
         g.M = s.rows; g.N = D; g.K = dh; g.zdiv = s.H;
         CHROMO_TRY(gemm_launch(g, true, false, s.H, c.st));
     }
-    {   // dW_v[h] += dAv[:, h]^T Cbar[(:,h), :]
-        GemmArgs g = gemm_args();
-        g.A = s.dAv; g.lda = s.dm; g.sA2 = dh;
-        g.B = s.cbar; g.ldb = s.H * D; g.sB2 = D;
-        g.C = s.g_wv; g.ldc = D; g.sC2 = (long long)dh * D;
-        g.M = dh; g.N = D; g.K = s.rows; g.zdiv = s.H; g.accumulate = 1; g.ksplit = ksplit_for(s.rows, dh, D, s.H);
-        CHROMO_TRY(gemm_launch(g, false, false, s.H, c.st));
-    }
+    // dW_v[h] += dAv[:, h]^T Cbar[(:,h), :]
+    for (int h = 0; h < s.H; ++h)
+        CHROMO_TRY(bwd_weight(c1, s.dAv + h * dh, s.dm, 0, s.cbar + (long long)h * D, s.H * D, 1, 0,
+                              s.g_wv + (long long)h * dh * D, D, 0, s.rows, dh, D, 1));
     {   // dP (PE part) = dCbar PE^T
         GemmArgs g = gemm_args();
         g.A = s.dCbar; g.lda = D; g.B = s.pe; g.ldb = D; g.C = s.dS; g.ldc = s.n;
@@ -433,8 +427,8 @@ int sqa_bwd(const Ctx& c, const SqaBwd& s) {
         CHROMO_CHECK_LAUNCH("attn_rows_bwd");
     }
     // dW_in += dCbar^T xbar + QK^T dU
-    CHROMO_TRY(bwd_weight(c, s.dCbar, D, 0, s.xbar, 8, 1, 0, s.g_win, s.F, 0, RH, D, s.F, 1));
-    CHROMO_TRY(bwd_weight(c, s.qk, D, 0, s.dU8, 8, 1, 0, s.g_win, s.F, 0, RH, D, s.F, 1));
+    CHROMO_TRY(bwd_weight(c1, s.dCbar, D, 0, s.xbar, 8, 1, 0, s.g_win, s.F, 0, RH, D, s.F, 1));
+    CHROMO_TRY(bwd_weight(c1, s.qk, D, 0, s.dU8, 8, 1, 0, s.g_win, s.F, 0, RH, D, s.F, 1));
     {   // dQK += dS PE
         GemmArgs g = gemm_args();
         g.A = s.dS; g.lda = s.n; g.B = s.pe; g.ldb = D; g.C = s.dQK; g.ldc = D; g.accumulate = 1;
@@ -450,14 +444,10 @@ int sqa_bwd(const Ctx& c, const SqaBwd& s) {
         g.M = s.rows; g.N = dh; g.K = D; g.zdiv = s.H;
         CHROMO_TRY(gemm_launch(g, true, true, s.H, c.st));
     }
-    {   // dW_k[h] += Q[:, h]^T dQK[(:,h), :]
-        GemmArgs g = gemm_args();
-        g.A = s.q; g.lda = s.dm; g.sA2 = dh;
-        g.B = s.dQK; g.ldb = s.H * D; g.sB2 = D;
-        g.C = s.g_wk; g.ldc = D; g.sC2 = (long long)dh * D;
-        g.M = dh; g.N = D; g.K = s.rows; g.zdiv = s.H; g.accumulate = 1; g.ksplit = ksplit_for(s.rows, dh, D, s.H);
-        CHROMO_TRY(gemm_launch(g, false, false, s.H, c.st));
-    }
+    // dW_k[h] += Q[:, h]^T dQK[(:,h), :]
+    for (int h = 0; h < s.H; ++h)
+        CHROMO_TRY(bwd_weight(c1, s.q + h * dh, s.dm, 0, s.dQK + (long long)h * D, s.H * D, 1, 0,
+                              s.g_wk + (long long)h * dh * D, D, 0, s.rows, dh, D, 1));
     return CHROMO_OK;
 }
 
@@ -471,21 +461,32 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
     const int dme = c->embed_d_model, He = c->embed_heads, dffe = c->embed_d_ff;
     const int dmp = c->pw_d_model, Hp = c->pw_heads, dffp = c->pw_d_ff;
     const int dmr = c->reg_d_model, Hr = c->reg_heads, dffr = c->reg_d_ff;
-    Ctx cx{st, NR, tc};
+    WgradQueue queue;
+    Ctx cx{st, NR, tc, tc ? &queue : nullptr};
+    Ctx c1 = cx; c1.NR = 1;
 
-    // ---- gradient scratch ---------------------------------------------------
+    // ---- gradient scratch: one buffer per gradient tensor and layer (see Ctx) -------------------------------------
     int64_t cur = w.g_base;
     auto take = [&](int64_t n) { int64_t o = cur; cur = align4(cur + n); return o; };
     const int64_t blk0 = cur;
-    const int64_t o_gR = take((int64_t)T * D), o_dFr = take((int64_t)T * dffr), o_dAtt = take((int64_t)T * dmr),
-                  o_dProj = take((int64_t)T * 4 * dmr);
-    const int64_t o_gP = take((int64_t)R * D), o_dFp = take((int64_t)R * dffp), o_dAvp = take((int64_t)R * dmp),
-                  o_dQp = take((int64_t)R * dmp), o_dCbP = take((int64_t)R * Hp * D),
-                  o_dQKp = take((int64_t)R * Hp * D), o_dU8p = take((int64_t)R * Hp * 8),
-                  o_dPP = take((int64_t)B * D);
-    const int64_t o_gE = take((int64_t)B * D), o_dFe = take((int64_t)B * dffe), o_dAve = take((int64_t)B * dme),
-                  o_dQe = take((int64_t)B * dme), o_dCbE = take((int64_t)B * He * D),
-                  o_dQKe = take((int64_t)B * He * D), o_dU8e = take((int64_t)B * He * 8);
+    int64_t o_gAr[CHROMO_MAX_LAYERS], o_dFr[CHROMO_MAX_LAYERS], o_gCr[CHROMO_MAX_LAYERS], o_dProj[CHROMO_MAX_LAYERS];
+    for (int l = 0; l < c->reg_layers; ++l) {
+        o_gAr[l] = take((int64_t)T * D); o_dFr[l] = take((int64_t)T * dffr);
+        o_gCr[l] = take((int64_t)T * D); o_dProj[l] = take((int64_t)T * 4 * dmr);
+    }
+    const int64_t o_tR0 = take((int64_t)T * D), o_tR1 = take((int64_t)T * D), o_dAtt = take((int64_t)T * dmr);
+    int64_t o_gAp[CHROMO_MAX_LAYERS], o_dFp[CHROMO_MAX_LAYERS], o_gCp[CHROMO_MAX_LAYERS], o_dAvp[CHROMO_MAX_LAYERS],
+        o_dQp[CHROMO_MAX_LAYERS], o_dCbP[CHROMO_MAX_LAYERS], o_dQKp[CHROMO_MAX_LAYERS], o_dU8p[CHROMO_MAX_LAYERS];
+    for (int l = 0; l < c->pw_layers; ++l) {
+        o_gAp[l] = take((int64_t)R * D); o_dFp[l] = take((int64_t)R * dffp); o_gCp[l] = take((int64_t)R * D);
+        o_dAvp[l] = take((int64_t)R * dmp); o_dQp[l] = take((int64_t)R * dmp); o_dCbP[l] = take((int64_t)R * Hp * D);
+        o_dQKp[l] = take((int64_t)R * Hp * D); o_dU8p[l] = take((int64_t)R * Hp * 8);
+    }
+    const int64_t o_tP0 = take((int64_t)R * D), o_tP1 = take((int64_t)R * D), o_dPP = take((int64_t)B * D);
+    const int64_t o_gAe = take((int64_t)B * D), o_dFe = take((int64_t)B * dffe), o_gCe = take((int64_t)B * D),
+                  o_dAve = take((int64_t)B * dme), o_dQe = take((int64_t)B * dme), o_dCbE = take((int64_t)B * He * D),
+                  o_dQKe = take((int64_t)B * He * D), o_dU8e = take((int64_t)B * He * 8),
+                  o_tE0 = take((int64_t)B * D), o_tE1 = take((int64_t)B * D), o_dHc = take((int64_t)B * D);
     const long long GS = cur - blk0;
     cur = blk0 + GS * NR;
     int64_t o_dSp[CHROMO_MAX_RES], o_dSe[CHROMO_MAX_RES];
@@ -498,40 +499,41 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
 
     // ---- head (net.py:377-380) ------------------------------------------------
     {
-        Ctx c1{st, 1, tc};
         const int dh = c->d_head, no = c->n_out;
         CHROMO_TRY(bwd_weight(c1, dlogits, no, 0, ws + w.h_h1, dh, 1, 0, G + L.fc2w, dh, 0, B, no, dh, 1));
         CHROMO_TRY(bwd_bias(c1, dlogits, no, 0, G + L.fc2b, 0, B, no, 1));
-        CHROMO_TRY(bwd_data(c1, dlogits, no, 0, P + L.fc2w, 0, ws + o_dh1, dh, 0, B, no, dh, false, 1));
-        CHROMO_TRY(relu_bwd(c1, ws + o_dh1, 0, ws + w.h_h1, 0, (long long)B * dh, 1));
+        DataEpi relu; relu.mask = ws + w.h_h1;
+        CHROMO_TRY(bwd_data(c1, dlogits, no, 0, P + L.fc2w, 0, ws + o_dh1, dh, 0, B, no, dh, relu, 1));
         CHROMO_TRY(bwd_weight(c1, ws + o_dh1, dh, 0, ws + w.h_z, NR * D, 1, 0, G + L.fc0w, NR * D, 0, B, dh, NR * D, 1));
         CHROMO_TRY(bwd_bias(c1, ws + o_dh1, dh, 0, G + L.fc0b, 0, B, dh, 1));
-        CHROMO_TRY(bwd_data(c1, ws + o_dh1, dh, 0, P + L.fc0w, 0, ws + o_dz, NR * D, 0, B, dh, NR * D, false, 1));
+        CHROMO_TRY(bwd_data(c1, ws + o_dh1, dh, 0, P + L.fc0w, 0, ws + o_dz, NR * D, 0, B, dh, NR * D, DataEpi(), 1));
         head_scatter_kernel<<<dim3((unsigned)(((long long)T * D + 255) / 256), NR), 256, 0, st>>>(
-            ws + o_gR, GS, ws + o_dz, B, S, D, NR);
+            ws + o_tR0, GS, ws + o_dz, B, S, D, NR);
         CHROMO_CHECK_LAUNCH("head_scatter");
     }
 
     // ---- Regulation transformer ------------------------------------------------
-    float* gR = ws + o_gR;
+    float* gcur = ws + o_tR0;           // gradient arriving at the layer's output
+    float* gnext = ws + o_tR1;
     for (int l = c->reg_layers - 1; l >= 0; --l) {
         const AttnOff& ra = L.reg[0].att[l];
         const FfnOff& rf = L.reg[0].ffn[l];
         const long long so = (long long)w.rslot(l) * w.r_slot;
         const float* xin = l == 0 ? ws + w.r_xin : ws + w.r_out + (long long)w.rslot(l - 1) * w.r_slot;
+        float* gA = ws + o_gAr[l]; float* dF = ws + o_dFr[l]; float* gC = ws + o_gCr[l]; float* dProj = ws + o_dProj[l];
         CHROMO_TRY(ffn_bwd(cx, P, G, rf, L.reg_stride, dffr, ws + w.r_u + so, ws + w.r_f + so, ws + w.r_preY + so, RS,
-                           gR, ws + o_dFr, GS, T));
-        CHROMO_TRY(ln_bwd(cx, ws + w.r_preU + so, RS, gR, GS, P + ra.lnw, G + ra.lnw, G + ra.lnb, L.reg_stride, T, NR));
-        CHROMO_TRY(bwd_weight(cx, gR, D, GS, ws + w.r_att + so, dmr, 1, RS, G + ra.ffw, dmr, L.reg_stride, T, D, dmr, NR));
-        CHROMO_TRY(bwd_bias(cx, gR, D, GS, G + ra.ffb, L.reg_stride, T, D, NR));
-        CHROMO_TRY(bwd_data(cx, gR, D, GS, P + ra.ffw, L.reg_stride, ws + o_dAtt, dmr, GS, T, D, dmr, false, NR));
+                           gcur, gA, dF, gnext, GS, T));
+        CHROMO_TRY(ln_bwd(cx, ws + w.r_preU + so, RS, gnext, gC, GS, P + ra.lnw, G + ra.lnw, G + ra.lnb, L.reg_stride, T, NR));
+        CHROMO_TRY(bwd_weight(cx, gC, D, GS, ws + w.r_att + so, dmr, 1, RS, G + ra.ffw, dmr, L.reg_stride, T, D, dmr, NR));
+        CHROMO_TRY(bwd_bias(cx, gC, D, GS, G + ra.ffb, L.reg_stride, T, D, NR));
+        CHROMO_TRY(bwd_data(cx, gC, D, GS, P + ra.ffw, L.reg_stride, ws + o_dAtt, dmr, GS, T, D, dmr, DataEpi(), NR));
         {
             RegAttnBwdArgs a;
             a.B = B; a.S = S; a.H = Hr;
             a.proj = ws + w.r_proj + so; a.proj_z = RS;
             a.prob = ws + w.r_prob + so; a.prob_z = RS;
             a.dout = ws + o_dAtt; a.dout_z = GS;
-            a.dproj = ws + o_dProj; a.dproj_z = GS;
+            a.dproj = dProj; a.dproj_z = GS;
             a.freq = in->freq;
             for (int r = 0; r < NR; ++r) a.imask[r] = in->imask[r];
             a.dgamma_f = G + ra.gamma_f; a.dgamma_z = L.reg_stride;
@@ -540,16 +542,19 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
             else reg_attention_bwd_kernel<17><<<grid, 256, 0, st>>>(a);
             CHROMO_CHECK_LAUNCH("reg_attention_bwd");
         }
-        CHROMO_TRY(bwd_weight(cx, ws + o_dProj, 4 * dmr, GS, xin, D, 1, RS, G + ra.att, D, L.reg_stride, T, 4 * dmr, D, NR));
-        CHROMO_TRY(bwd_data(cx, ws + o_dProj, 4 * dmr, GS, P + ra.att, L.reg_stride, gR, D, GS, T, 4 * dmr, D, true, NR));
+        CHROMO_TRY(bwd_weight(cx, dProj, 4 * dmr, GS, xin, D, 1, RS, G + ra.att, D, L.reg_stride, T, 4 * dmr, D, NR));
+        DataEpi resid; resid.res = gC;
+        CHROMO_TRY(bwd_data(cx, dProj, 4 * dmr, GS, P + ra.att, L.reg_stride, gcur, D, GS, T, 4 * dmr, D, resid, NR));
+        // gcur = dX of this layer = the gradient arriving at the output of layer l-1; gnext is free again
     }
-    // gR is now dX_in (without the residual of net.py:378)
+    float* gR = gcur;                   // dX_in (without the residual of net.py:378)
     head_residual_kernel<<<dim3((B * D + 255) / 256, NR), 256, 0, st>>>(gR, GS, ws + o_dz, B, S, D, NR);
     CHROMO_CHECK_LAUNCH("head_residual");
 
     // ---- Pairwise Interaction transformer ---------------------------------------
-    float* gP = ws + o_gP;
-    gather_rows_kernel<<<dim3((unsigned)(((long long)R * 32 + 255) / 256), NR), 256, 0, st>>>(gP, GS, gR, GS, R, I, S, 1);
+    float* pcur = ws + o_tP0;
+    float* pnext = ws + o_tP1;
+    gather_rows_kernel<<<dim3((unsigned)(((long long)R * 32 + 255) / 256), NR), 256, 0, st>>>(pcur, GS, gR, GS, R, I, S, 1);
     CHROMO_CHECK_LAUNCH("gather_pairwise");
     for (int l = c->pw_layers - 1; l >= 0; --l) {
         const AttnOff& pa = L.pw[0].att[l];
@@ -557,12 +562,13 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
         const long long so = (long long)w.pslot(l) * w.p_slot;
         const float* pin = l == 0 ? ws + w.p_pp : ws + w.p_out + (long long)w.pslot(l - 1) * w.p_slot;
         const int pin_div = l == 0 ? I : 1;
+        float* gA = ws + o_gAp[l]; float* dF = ws + o_dFp[l]; float* gC = ws + o_gCp[l];
         CHROMO_TRY(ffn_bwd(cx, P, G, pf, L.pw_stride, dffp, ws + w.p_u + so, ws + w.p_f + so, ws + w.p_preY + so, RS,
-                           gP, ws + o_dFp, GS, R));
-        CHROMO_TRY(ln_bwd(cx, ws + w.p_preU + so, RS, gP, GS, P + pa.lnw, G + pa.lnw, G + pa.lnb, L.pw_stride, R, NR));
-        CHROMO_TRY(bwd_weight(cx, gP, D, GS, ws + w.p_av + so, dmp, 1, RS, G + pa.ffw, dmp, L.pw_stride, R, D, dmp, NR));
-        CHROMO_TRY(bwd_bias(cx, gP, D, GS, G + pa.ffb, L.pw_stride, R, D, NR));
-        CHROMO_TRY(bwd_data(cx, gP, D, GS, P + pa.ffw, L.pw_stride, ws + o_dAvp, dmp, GS, R, D, dmp, false, NR));
+                           pcur, gA, dF, pnext, GS, R));
+        CHROMO_TRY(ln_bwd(cx, ws + w.p_preU + so, RS, pnext, gC, GS, P + pa.lnw, G + pa.lnw, G + pa.lnb, L.pw_stride, R, NR));
+        CHROMO_TRY(bwd_weight(cx, gC, D, GS, ws + w.p_av + so, dmp, 1, RS, G + pa.ffw, dmp, L.pw_stride, R, D, dmp, NR));
+        CHROMO_TRY(bwd_bias(cx, gC, D, GS, G + pa.ffb, L.pw_stride, R, D, NR));
+        CHROMO_TRY(bwd_data(cx, gC, D, GS, P + pa.ffw, L.pw_stride, ws + o_dAvp[l], dmp, GS, R, D, dmp, DataEpi(), NR));
         for (int r = 0; r < NR; ++r) {
             SqaBwd s;
             s.rows = R; s.H = Hp; s.dm = dmp; s.D = D; s.n = c->n_bins[r]; s.F = F;
@@ -575,16 +581,17 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
             s.mask = in->mask_pcre[r]; s.mask_stride = in->mask_pcre_stride[r];
             s.mask_row_offset = in->mask_pcre_row_offset[r];
             s.g_wk = G + catt; s.g_wv = G + catt + (long long)dmp * D; s.g_win = G + L.pw[r].lin_proj_pcre;
-            s.dAv = ws + r * GS + o_dAvp; s.dQ = ws + r * GS + o_dQp;
-            s.dCbar = ws + r * GS + o_dCbP; s.dQK = ws + r * GS + o_dQKp; s.dU8 = ws + r * GS + o_dU8p;
+            s.dAv = ws + r * GS + o_dAvp[l]; s.dQ = ws + r * GS + o_dQp[l];
+            s.dCbar = ws + r * GS + o_dCbP[l]; s.dQK = ws + r * GS + o_dQKp[l]; s.dU8 = ws + r * GS + o_dU8p[l];
             s.dS = ws + o_dSp[r];
             CHROMO_TRY(sqa_bwd(cx, s));
         }
-        CHROMO_TRY(bwd_weight(cx, ws + o_dQp, dmp, GS, pin, D, pin_div, RS, G + pa.p_att, D, L.pw_stride, R, dmp, D, NR));
-        CHROMO_TRY(bwd_data(cx, ws + o_dQp, dmp, GS, P + pa.p_att, L.pw_stride, gP, D, GS, R, dmp, D, true, NR));
+        CHROMO_TRY(bwd_weight(cx, ws + o_dQp[l], dmp, GS, pin, D, pin_div, RS, G + pa.p_att, D, L.pw_stride, R, dmp, D, NR));
+        DataEpi resid; resid.res = gC;
+        CHROMO_TRY(bwd_data(cx, ws + o_dQp[l], dmp, GS, P + pa.p_att, L.pw_stride, pcur, D, GS, R, dmp, D, resid, NR));
     }
-    // gP = dP_0 per (gene, slot); P_0 = PP[gene] for every slot (net.py:114-118)
-    slot_sum_kernel<<<dim3((unsigned)(((long long)B * 32 + 255) / 256), NR), 256, 0, st>>>(ws + o_dPP, GS, gP, GS, B, I);
+    // pcur = dP_0 per (gene, slot); P_0 = PP[gene] for every slot (net.py:114-118)
+    slot_sum_kernel<<<dim3((unsigned)(((long long)B * 32 + 255) / 256), NR), 256, 0, st>>>(ws + o_dPP, GS, pcur, GS, B, I);
     CHROMO_CHECK_LAUNCH("slot_sum");
     CHROMO_TRY(bwd_weight(cx, ws + o_dPP, D, GS, ws + w.r_xin, S * D, 1, RS, G + L.pw[0].lin_proj_p, D, L.pw_stride, B, D, D, NR));
     {   // dX_in[b, 0, :] += dPP W_lpp
@@ -597,18 +604,20 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
     }
 
     // ---- Embedding transformer ----------------------------------------------------
-    float* gE = ws + o_gE;
-    gather_rows_kernel<<<dim3((unsigned)(((long long)B * 32 + 255) / 256), NR), 256, 0, st>>>(gE, GS, gR, GS, B, 1, S, 0);
+    float* ecur = ws + o_tE0;
+    float* enext = ws + o_tE1;
+    gather_rows_kernel<<<dim3((unsigned)(((long long)B * 32 + 255) / 256), NR), 256, 0, st>>>(ecur, GS, gR, GS, B, 1, S, 0);
     CHROMO_CHECK_LAUNCH("gather_embed");
     {
         const AttnOff& ea = L.embed[0].att[0];
         const FfnOff& ef = L.embed[0].ffn[0];
-        CHROMO_TRY(ffn_bwd(cx, P, G, ef, L.embed_stride, dffe, ws + w.e_u, ws + w.e_f, ws + w.e_preY, RS, gE,
-                           ws + o_dFe, GS, B));
-        CHROMO_TRY(ln_bwd(cx, ws + w.e_preU, RS, gE, GS, P + ea.lnw, G + ea.lnw, G + ea.lnb, L.embed_stride, B, NR));
-        CHROMO_TRY(bwd_weight(cx, gE, D, GS, ws + w.e_av, dme, 1, RS, G + ea.ffw, dme, L.embed_stride, B, D, dme, NR));
-        CHROMO_TRY(bwd_bias(cx, gE, D, GS, G + ea.ffb, L.embed_stride, B, D, NR));
-        CHROMO_TRY(bwd_data(cx, gE, D, GS, P + ea.ffw, L.embed_stride, ws + o_dAve, dme, GS, B, D, dme, false, NR));
+        float* gA = ws + o_gAe; float* dF = ws + o_dFe; float* gC = ws + o_gCe; float* dHc = ws + o_dHc;
+        CHROMO_TRY(ffn_bwd(cx, P, G, ef, L.embed_stride, dffe, ws + w.e_u, ws + w.e_f, ws + w.e_preY, RS, ecur, gA, dF,
+                           enext, GS, B));
+        CHROMO_TRY(ln_bwd(cx, ws + w.e_preU, RS, enext, gC, GS, P + ea.lnw, G + ea.lnw, G + ea.lnb, L.embed_stride, B, NR));
+        CHROMO_TRY(bwd_weight(cx, gC, D, GS, ws + w.e_av, dme, 1, RS, G + ea.ffw, dme, L.embed_stride, B, D, dme, NR));
+        CHROMO_TRY(bwd_bias(cx, gC, D, GS, G + ea.ffb, L.embed_stride, B, D, NR));
+        CHROMO_TRY(bwd_data(cx, gC, D, GS, P + ea.ffw, L.embed_stride, ws + o_dAve, dme, GS, B, D, dme, DataEpi(), NR));
         for (int r = 0; r < NR; ++r) {
             SqaBwd s;
             s.rows = B; s.H = He; s.dm = dme; s.D = D; s.n = c->n_bins[r]; s.F = F;
@@ -628,16 +637,16 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
         }
         // W_q is rows [0, dme) of att.weight
         CHROMO_TRY(bwd_weight(cx, ws + o_dQe, dme, GS, ws + w.e_hc, D, 1, RS, G + ea.att, D, L.embed_stride, B, dme, D, NR));
-        CHROMO_TRY(bwd_data(cx, ws + o_dQe, dme, GS, P + ea.att, L.embed_stride, gE, D, GS, B, dme, D, true, NR));
-        // gE = dHc;  Hc = W_lp x_c + PE_c  ->  dW_lp += dHc^T x_p[:, c, :]
+        DataEpi resid; resid.res = gC;
+        CHROMO_TRY(bwd_data(cx, ws + o_dQe, dme, GS, P + ea.att, L.embed_stride, dHc, D, GS, B, dme, D, resid, NR));
+        // Hc = W_lp x_c + PE_c  ->  dW_lp += dHc^T x_p[:, c, :]
         for (int r = 0; r < NR; ++r) {
             const int n = c->n_bins[r];
-            Ctx c1{st, 1, tc};
-            CHROMO_TRY(bwd_weight(c1, gE + r * GS, D, 0, in->x_p[r] + (long long)(n / 2) * F, n * F, 1, 0,
+            CHROMO_TRY(bwd_weight(c1, dHc + r * GS, D, 0, in->x_p[r] + (long long)(n / 2) * F, n * F, 1, 0,
                                   G + L.embed[r].lin_proj, F, 0, B, D, F, 1));
         }
     }
-    return CHROMO_OK;
+    return tc ? queue.flush(st) : CHROMO_OK;
 }
 
 }  // namespace chromo

@@ -21,6 +21,7 @@
 #include "kernels.cuh"
 #include "reg_fused.cuh"
 #include "sqa_fused.cuh"
+#include "train_gemm.cuh"
 #include "umma_gemm.cuh"
 
 namespace chromo {
@@ -636,6 +637,26 @@ static int pack_all_weights(const chromo_config_t* c, const ParamLayout& L, cons
     return CHROMO_OK;
 }
 
+// GemmArgs of an nn.Linear call site (A [M,K], W [N,K], both K-contiguous) -> the training tensor-core GEMM
+static bool tc_from_gemm(const GemmArgs& g, TcGemm& t) {
+    if (g.zdiv != 1 || g.ksplit != 1 || g.alpha != 1.f || g.accumulate || g.c_bf16 || g.c_sqa_tiles || g.res_plain || g.mask)
+        return false;
+    t = tc_gemm_args();
+    t.A = g.A; t.lda = g.lda; t.a_z = g.sA1; t.a_div = g.a_div;
+    t.B = g.B; t.ldb = g.ldb; t.b_z = g.sB1; t.b_t = 0;
+    t.C = g.C; t.ldc = g.ldc; t.c_z = g.sC1; t.c_div = g.c_div; t.c_mul = g.c_mul; t.c_add = g.c_add;
+    t.M = g.M; t.N = g.N; t.Kc = g.K;
+    if (g.epi != EPI_PLAIN && g.bias) { t.epi |= TC_BIAS; t.bias = g.bias; t.bias_z = g.sBias1; }
+    if (g.epi == EPI_BIAS_RELU) t.epi |= TC_RELU;
+    if (g.epi == EPI_BIAS_RES_LN) {
+        t.epi |= TC_RES | TC_LN;
+        t.res = g.res; t.ldres = g.ldres; t.res_z = g.sRes1; t.res_div = g.res_div;
+        t.gamma = g.gamma; t.beta = g.beta; t.ln_z = g.sLn1;
+        t.pre = g.pre; t.pre_z = g.sPre1;
+    }
+    return true;
+}
+
 struct RegOnly { int layer; const float* x; float* y; long long xy_stride; };
 
 static int forward_impl(const chromo_config_t* c, const float* P, const chromo_batch_t* in, float* logits,
@@ -651,6 +672,12 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     __nv_bfloat16* packed = bf16 ? reinterpret_cast<__nv_bfloat16*>(ws + w.bf_params) : nullptr;
     // Dense projection: tcgen05 BF16 engine when requested and the shape qualifies, FP32 SIMT otherwise.
     auto lin = [&](const GemmArgs& g, int nz) -> int {
+        if (bf16 && train) {
+            // training: parameters change every step, so nothing is packed: FP32 weights are converted while staged
+            TcGemm t;
+            if (tc_from_gemm(g, t) && tc_gemm_supported(t)) return tc_gemm_launch(t, nz, st);
+            return gemm_launch(g, true, true, nz, st);
+        }
         if (bf16 && g.M >= 64 && g.B >= P && g.B < P + L.total && umma_supported(g))
             return umma_launch(g, packed + (g.B - P), nz, st);
         if (fold && g.B >= ws + w.fold_f32 && g.B < ws + w.fold_f32 + w.fold_total && umma_supported(g))
@@ -658,7 +685,8 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         if (g.c_bf16) { set_error("internal: BF16 output requested on the FP32 path"); return CHROMO_EINVAL; }
         return gemm_launch(g, true, true, nz, st);
     };
-    if (bf16 && !(flags & CHROMO_F_PACKED)) CHROMO_TRY(pack_all_weights(c, L, P, packed, ws, w, in, st));
+    if (bf16 && !train && !(flags & CHROMO_F_PACKED)) CHROMO_TRY(pack_all_weights(c, L, P, packed, ws, w, in, st));
+    const bool pe_packed = bf16 && !train;      // the packed position tables exist
     // precision diagnostics (tools/precision_stress.py): keep one stage's contractions on the FP32 CUDA-core GEMM
     const bool reg_fp32 = getenv("CHROMO_REG_FP32") != nullptr, head_fp32 = getenv("CHROMO_HEAD_FP32") != nullptr;
     auto lin_fp32 = [&](const GemmArgs& g, int nz) -> int { return gemm_launch(g, true, true, nz, st); };
@@ -752,8 +780,8 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         s.pe = in->pos_enc[r];
         s.x = in->x_p[r];
         s.mask = in->mask_p[r]; s.mask_stride = in->mask_p_stride[r]; s.mask_row_offset = in->mask_p_row_offset[r];
-        s.pe_pk = bf16 ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pe[r]) : nullptr;
-        s.pet_pk = bf16 ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pet[r]) : nullptr;
+        s.pe_pk = pe_packed ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pe[r]) : nullptr;
+        s.pet_pk = pe_packed ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pet[r]) : nullptr;
         s.qk = ws + r * RS + w.e_qk; s.P = ws + w.e_p[r]; s.xbar = ws + r * RS + w.e_xbar;
         s.cbar = ws + r * RS + w.e_cbar; s.av = ws + r * RS + w.e_av; s.folded = fold;
         CHROMO_TRY(single_query_attention(s, st));
@@ -860,8 +888,8 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             s.x = in->x_pcre[r];
             s.mask = in->mask_pcre[r]; s.mask_stride = in->mask_pcre_stride[r];
             s.mask_row_offset = in->mask_pcre_row_offset[r];
-            s.pe_pk = bf16 ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pe[r]) : nullptr;
-            s.pet_pk = bf16 ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pet[r]) : nullptr;
+            s.pe_pk = pe_packed ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pe[r]) : nullptr;
+            s.pet_pk = pe_packed ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pet[r]) : nullptr;
             s.qk = ws + r * RS + w.p_qk + so;
             s.P = ws + w.p_p[r] + (long long)w.pslot(l) * w.p_p_slot[r];
             s.xbar = ws + r * RS + w.p_xbar + so;

@@ -38,6 +38,8 @@ struct GemmArgs {
     int accumulate;                            // C += result
     int ksplit;                                // split-K factor; >1 => atomicAdd into C
     int c_bf16;                                // tensor path only: C is BF16 (ldc, strides in elements)
+    int res_plain;                             // plain epilogues: C = acc (+ bias) + res[m / res_div, n]  (not with split-K)
+    const float* mask; int ldmask; long long sMask1;   // zero where mask[m, n] <= 0 (ReLU backward; not with split-K)
     int c_sqa_tiles;                           // tensor path only: C [M, 256] = QK of (region m, head n / 128) written as the
                                                //   BF16 operand tiles of sqa_fused (row 2m + head, 128-row tiles in the
                                                //   canonical K-major layout); sC1 in BF16 elements
@@ -204,7 +206,9 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_simt_kernel(const GemmArgs 
                 if (n >= g.N) continue;
                 float v = g.alpha * acc[i][j];
                 if (g.epi != EPI_PLAIN && bias) v += bias[n];
+                if (g.res_plain) v += g.res[z1 * g.sRes1 + (long long)(m / g.res_div) * g.ldres + n];
                 if (g.epi == EPI_BIAS_RELU) v = fmaxf(v, 0.f);
+                if (g.mask && !(g.mask[z1 * g.sMask1 + (long long)m * g.ldmask + n] > 0.f)) v = 0.f;
                 float* c = C + crow * g.ldc + n;
                 if (g.ksplit > 1) atomicAdd(c, v);
                 else if (g.accumulate) *c += v;

@@ -290,10 +290,13 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
     w.h_h1 = take((int64_t)B * c->d_head);
     w.g_base = cur;
     if (w.training) {
-        // backward scratch: generous bound, carved up in backward.cu
-        int64_t per_res = (int64_t)T * (4 * c->reg_d_model + c->reg_d_model + c->reg_d_ff + 4 * D) +
-                          (int64_t)R * (2 * Hp * D + 2 * c->pw_d_model + c->pw_d_ff + 6 * D + Hp * 8) +
-                          (int64_t)B * (2 * He * D + 2 * c->embed_d_model + c->embed_d_ff + 8 * D + He * 8);
+        // backward scratch, carved up in backward.cu: every gradient tensor of every layer has its own buffer (the
+        // weight gradients are taken from them in one launch at the end of the pass)
+        int64_t per_res = (int64_t)c->reg_layers * T * (4 * c->reg_d_model + c->reg_d_ff + 2 * D) +
+                          (int64_t)T * (c->reg_d_model + 2 * D) +
+                          (int64_t)c->pw_layers * R * (2 * Hp * D + 2 * c->pw_d_model + c->pw_d_ff + 2 * D + Hp * 8) +
+                          (int64_t)R * 2 * D + (int64_t)B * D +
+                          (int64_t)B * (2 * He * D + 2 * c->embed_d_model + c->embed_d_ff + 5 * D + He * 8) + 4096;
         int64_t nmax = 0;
         for (int r = 0; r < c->n_res; ++r) nmax = nmax > c->n_bins[r] ? nmax : c->n_bins[r];
         int64_t probs = (int64_t)R * Hp * nmax + (int64_t)B * He * nmax;
