@@ -284,7 +284,7 @@ def main():
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
     ap.add_argument("--chunk", type=int, default=4096)
     ap.add_argument("--precision", choices=["fp32", "bf16"], default="bf16")
-    ap.add_argument("--train-precision", choices=["fp32", "bf16"], default="fp32")
+    ap.add_argument("--train-precision", choices=["fp32", "bf16"], default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-train", action="store_true")
     ap.add_argument("--no-sweep", action="store_true")

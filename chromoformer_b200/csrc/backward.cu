@@ -11,9 +11,8 @@
 #include <string.h>
 
 #include "common.cuh"
-#include "gemm_simt.cuh"
+#include "gemm_dispatch.cuh"
 #include "kernels.cuh"
-#include "train_gemm.cuh"
 
 namespace chromo {
 
@@ -323,6 +322,19 @@ int bwd_data(const Ctx& c, const float* dY, int ldy, long long dy_z, const float
     g.B = W; g.ldb = K; g.sB1 = w_z;
     g.C = dX; g.ldc = lddx; g.sC1 = dx_z;
     g.M = M; g.N = K; g.K = N;
+    if (e.res && !e.mask && lddx == K) {
+        // strict FP32 path: dX <- res (one strided copy), then dX += dY W with the contraction split over CTAs (atomics):
+        // the batch of a training step is a few hundred rows, a handful of CTAs otherwise
+        if (cudaMemcpy2DAsync(dX, (size_t)(nz > 1 ? dx_z : (long long)M * K) * sizeof(float), e.res,
+                              (size_t)(nz > 1 ? dx_z : (long long)M * K) * sizeof(float), (size_t)M * K * sizeof(float), nz,
+                              cudaMemcpyDeviceToDevice, c.st) != cudaSuccess) {
+            set_error("bwd_data: residual copy failed");
+            return CHROMO_ECUDA;
+        }
+        g.accumulate = 1;
+        g.ksplit = ksplit_for(N, M, K, nz);
+        return gemm_launch(g, true, false, nz, c.st);
+    }
     if (e.res) { g.res_plain = 1; g.res = e.res; g.ldres = lddx; g.sRes1 = dx_z; }
     if (e.mask) { g.mask = e.mask; g.ldmask = K; g.sMask1 = e.mask_z; }
     return gemm_launch(g, true, false, nz, c.st);
@@ -405,17 +417,26 @@ int sqa_bwd(const Ctx& c, const SqaBwd& s) {
         g.B = s.w_v; g.ldb = D; g.sB2 = (long long)dh * D;
         g.C = s.dCbar; g.ldc = s.H * D; g.sC2 = D;
         g.M = s.rows; g.N = D; g.K = dh; g.zdiv = s.H;
-        CHROMO_TRY(gemm_launch(g, true, false, s.H, c.st));
+        CHROMO_TRY(gemm_auto(g, true, false, s.H, c.st, c.tc));
     }
     // dW_v[h] += dAv[:, h]^T Cbar[(:,h), :]
-    for (int h = 0; h < s.H; ++h)
-        CHROMO_TRY(bwd_weight(c1, s.dAv + h * dh, s.dm, 0, s.cbar + (long long)h * D, s.H * D, 1, 0,
-                              s.g_wv + (long long)h * dh * D, D, 0, s.rows, dh, D, 1));
+    if (c.q) {
+        for (int h = 0; h < s.H; ++h)
+            CHROMO_TRY(bwd_weight(c1, s.dAv + h * dh, s.dm, 0, s.cbar + (long long)h * D, s.H * D, 1, 0,
+                                  s.g_wv + (long long)h * dh * D, D, 0, s.rows, dh, D, 1));
+    } else {
+        GemmArgs g = gemm_args();
+        g.A = s.dAv; g.lda = s.dm; g.sA2 = dh;
+        g.B = s.cbar; g.ldb = s.H * D; g.sB2 = D;
+        g.C = s.g_wv; g.ldc = D; g.sC2 = (long long)dh * D;
+        g.M = dh; g.N = D; g.K = s.rows; g.zdiv = s.H; g.accumulate = 1; g.ksplit = ksplit_for(s.rows, dh, D, s.H);
+        CHROMO_TRY(gemm_launch(g, false, false, s.H, c.st));
+    }
     {   // dP (PE part) = dCbar PE^T
         GemmArgs g = gemm_args();
         g.A = s.dCbar; g.lda = D; g.B = s.pe; g.ldb = D; g.C = s.dS; g.ldc = s.n;
         g.M = RH; g.N = s.n; g.K = D;
-        CHROMO_TRY(gemm_launch(g, true, true, 1, c.st));
+        CHROMO_TRY(gemm_auto(g, true, true, 1, c.st, c.tc));
     }
     {
         AttnRowsBwdArgs a;
@@ -434,7 +455,7 @@ int sqa_bwd(const Ctx& c, const SqaBwd& s) {
         g.A = s.dS; g.lda = s.n; g.B = s.pe; g.ldb = D; g.C = s.dQK; g.ldc = D; g.accumulate = 1;
         g.M = RH; g.N = D; g.K = s.n;
         g.ksplit = ksplit_for(s.n, RH, D, 1);       // K = n bins (up to 400) on a handful of CTAs otherwise
-        CHROMO_TRY(gemm_launch(g, true, false, 1, c.st));
+        CHROMO_TRY(gemm_auto(g, true, false, 1, c.st, c.tc));
     }
     {   // dQ[r, h] = W_k[h] dQK[(r,h), :]
         GemmArgs g = gemm_args();
@@ -442,12 +463,21 @@ int sqa_bwd(const Ctx& c, const SqaBwd& s) {
         g.B = s.w_k; g.ldb = D; g.sB2 = (long long)dh * D;
         g.C = s.dQ; g.ldc = s.dm; g.sC2 = dh;
         g.M = s.rows; g.N = dh; g.K = D; g.zdiv = s.H;
-        CHROMO_TRY(gemm_launch(g, true, true, s.H, c.st));
+        CHROMO_TRY(gemm_auto(g, true, true, s.H, c.st, c.tc));
     }
     // dW_k[h] += Q[:, h]^T dQK[(:,h), :]
-    for (int h = 0; h < s.H; ++h)
-        CHROMO_TRY(bwd_weight(c1, s.q + h * dh, s.dm, 0, s.dQK + (long long)h * D, s.H * D, 1, 0,
-                              s.g_wk + (long long)h * dh * D, D, 0, s.rows, dh, D, 1));
+    if (c.q) {
+        for (int h = 0; h < s.H; ++h)
+            CHROMO_TRY(bwd_weight(c1, s.q + h * dh, s.dm, 0, s.dQK + (long long)h * D, s.H * D, 1, 0,
+                                  s.g_wk + (long long)h * dh * D, D, 0, s.rows, dh, D, 1));
+    } else {
+        GemmArgs g = gemm_args();
+        g.A = s.q; g.lda = s.dm; g.sA2 = dh;
+        g.B = s.dQK; g.ldb = s.H * D; g.sB2 = D;
+        g.C = s.g_wk; g.ldc = D; g.sC2 = (long long)dh * D;
+        g.M = dh; g.N = D; g.K = s.rows; g.zdiv = s.H; g.accumulate = 1; g.ksplit = ksplit_for(s.rows, dh, D, s.H);
+        CHROMO_TRY(gemm_launch(g, false, false, s.H, c.st));
+    }
     return CHROMO_OK;
 }
 
@@ -600,7 +630,7 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
         g.B = P + L.pw[0].lin_proj_p; g.ldb = D; g.sB1 = L.pw_stride;
         g.C = gR; g.ldc = D; g.sC1 = GS; g.c_div = 1; g.c_mul = S; g.c_add = 0; g.accumulate = 1;
         g.M = B; g.N = D; g.K = D;
-        CHROMO_TRY(gemm_launch(g, true, false, NR, st));
+        CHROMO_TRY(gemm_auto(g, true, false, NR, st, tc));
     }
 
     // ---- Embedding transformer ----------------------------------------------------

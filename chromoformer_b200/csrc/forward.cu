@@ -21,7 +21,7 @@
 #include "kernels.cuh"
 #include "reg_fused.cuh"
 #include "sqa_fused.cuh"
-#include "train_gemm.cuh"
+#include "gemm_dispatch.cuh"
 #include "umma_gemm.cuh"
 
 namespace chromo {
@@ -475,7 +475,7 @@ int single_query_attention(const SqaArgs& s, cudaStream_t st) {
         g.B = s.w_k; g.ldb = D; g.sB2 = (long long)dh * D;
         g.C = s.qk; g.ldc = s.H * D; g.sC2 = D;
         g.M = s.rows; g.N = D; g.K = dh; g.zdiv = s.H;
-        CHROMO_TRY(gemm_launch(g, true, false, s.H, st));
+        CHROMO_TRY(gemm_auto(g, true, false, s.H, st, s.tc));
     }
     // Short rows (n <= 32).  BF16 inference: pad the row to 32 bins (the packed position tables carry zero rows /
     // columns there) so that both position-table GEMMs run on the tensor pipe; otherwise the rows kernel does
@@ -492,7 +492,7 @@ int single_query_attention(const SqaArgs& s, cudaStream_t st) {
         g.M = s.rows * s.H; g.N = np; g.K = D;
         if (s.pe_pk && g.M >= 64 && np % 16 == 0 && umma_supported(g)) CHROMO_TRY(umma_launch(g, s.pe_pk, 1, st));
         else if (pad32) { set_error("internal: padded short-row path needs the tensor engine"); return CHROMO_EINVAL; }
-        else CHROMO_TRY(gemm_launch(g, true, true, 1, st));
+        else CHROMO_TRY(gemm_auto(g, true, true, 1, st, s.tc));
     }
     {
         AttnRowsArgs a;
@@ -512,7 +512,7 @@ int single_query_attention(const SqaArgs& s, cudaStream_t st) {
         g.M = s.rows * s.H; g.N = D; g.K = np;
         if (s.pet_pk && g.M >= 64 && np % 16 == 0 && umma_supported(g)) CHROMO_TRY(umma_launch(g, s.pet_pk, 1, st));
         else if (pad32) { set_error("internal: padded short-row path needs the tensor engine"); return CHROMO_EINVAL; }
-        else CHROMO_TRY(gemm_launch(g, true, false, 1, st));   // (no split-K here: the forward stays deterministic)
+        else CHROMO_TRY(gemm_auto(g, true, false, 1, st, s.tc));   // (no split-K here: the forward stays deterministic)
     }
     // Av[row, h*dh + e] = W_v[h*dh + e, :] . Cbar[(row,h), :]               (NT GEMM per head)
     if (!s.folded) {
@@ -521,7 +521,7 @@ int single_query_attention(const SqaArgs& s, cudaStream_t st) {
         g.B = s.w_v; g.ldb = D; g.sB2 = (long long)dh * D;
         g.C = s.av; g.ldc = s.dm; g.sC2 = dh;
         g.M = s.rows; g.N = dh; g.K = D; g.zdiv = s.H;
-        CHROMO_TRY(gemm_launch(g, true, true, s.H, st));
+        CHROMO_TRY(gemm_auto(g, true, true, s.H, st, s.tc));
     }
     return CHROMO_OK;
 }
@@ -637,26 +637,6 @@ static int pack_all_weights(const chromo_config_t* c, const ParamLayout& L, cons
     return CHROMO_OK;
 }
 
-// GemmArgs of an nn.Linear call site (A [M,K], W [N,K], both K-contiguous) -> the training tensor-core GEMM
-static bool tc_from_gemm(const GemmArgs& g, TcGemm& t) {
-    if (g.zdiv != 1 || g.ksplit != 1 || g.alpha != 1.f || g.accumulate || g.c_bf16 || g.c_sqa_tiles || g.res_plain || g.mask)
-        return false;
-    t = tc_gemm_args();
-    t.A = g.A; t.lda = g.lda; t.a_z = g.sA1; t.a_div = g.a_div;
-    t.B = g.B; t.ldb = g.ldb; t.b_z = g.sB1; t.b_t = 0;
-    t.C = g.C; t.ldc = g.ldc; t.c_z = g.sC1; t.c_div = g.c_div; t.c_mul = g.c_mul; t.c_add = g.c_add;
-    t.M = g.M; t.N = g.N; t.Kc = g.K;
-    if (g.epi != EPI_PLAIN && g.bias) { t.epi |= TC_BIAS; t.bias = g.bias; t.bias_z = g.sBias1; }
-    if (g.epi == EPI_BIAS_RELU) t.epi |= TC_RELU;
-    if (g.epi == EPI_BIAS_RES_LN) {
-        t.epi |= TC_RES | TC_LN;
-        t.res = g.res; t.ldres = g.ldres; t.res_z = g.sRes1; t.res_div = g.res_div;
-        t.gamma = g.gamma; t.beta = g.beta; t.ln_z = g.sLn1;
-        t.pre = g.pre; t.pre_z = g.sPre1;
-    }
-    return true;
-}
-
 struct RegOnly { int layer; const float* x; float* y; long long xy_stride; };
 
 static int forward_impl(const chromo_config_t* c, const float* P, const chromo_batch_t* in, float* logits,
@@ -674,9 +654,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     auto lin = [&](const GemmArgs& g, int nz) -> int {
         if (bf16 && train) {
             // training: parameters change every step, so nothing is packed: FP32 weights are converted while staged
-            TcGemm t;
-            if (tc_from_gemm(g, t) && tc_gemm_supported(t)) return tc_gemm_launch(t, nz, st);
-            return gemm_launch(g, true, true, nz, st);
+            return gemm_auto(g, true, true, nz, st, true);
         }
         if (bf16 && g.M >= 64 && g.B >= P && g.B < P + L.total && umma_supported(g))
             return umma_launch(g, packed + (g.B - P), nz, st);
@@ -783,7 +761,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         s.pe_pk = pe_packed ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pe[r]) : nullptr;
         s.pet_pk = pe_packed ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pet[r]) : nullptr;
         s.qk = ws + r * RS + w.e_qk; s.P = ws + w.e_p[r]; s.xbar = ws + r * RS + w.e_xbar;
-        s.cbar = ws + r * RS + w.e_cbar; s.av = ws + r * RS + w.e_av; s.folded = fold;
+        s.cbar = ws + r * RS + w.e_cbar; s.av = ws + r * RS + w.e_av; s.folded = fold; s.tc = bf16 && train;
         CHROMO_TRY(single_query_attention(s, st));
     }
     const long long tail_z = (long long)(1 + c->pw_layers) * TAIL_SLOT_ELEMS;
@@ -893,7 +871,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             s.qk = ws + r * RS + w.p_qk + so;
             s.P = ws + w.p_p[r] + (long long)w.pslot(l) * w.p_p_slot[r];
             s.xbar = ws + r * RS + w.p_xbar + so;
-            s.cbar = ws + r * RS + w.p_cbar + so; s.av = ws + r * RS + w.p_av + so; s.folded = fold;
+            s.cbar = ws + r * RS + w.p_cbar + so; s.av = ws + r * RS + w.p_av + so; s.folded = fold; s.tc = bf16 && train;
             CHROMO_TRY(single_query_attention(s, st));
         }
         if (tail) {

@@ -82,6 +82,7 @@ struct SqaArgs {
     const uint8_t* mask; long long mask_stride, mask_row_offset;
     float* qk; float* P; float* xbar; float* cbar; float* av;
     bool folded = false;                    // caller supplies qk and consumes cbar (folded weights)
+    bool tc = false;                        // BF16 training: the four contractions on the staged tcgen05 GEMM
     const __nv_bfloat16* pe_pk = nullptr;   // BF16 tensor path: PE packed as a [n,D] weight
     const __nv_bfloat16* pet_pk = nullptr;  //                   PE^T packed as a [D,n] weight
 };

@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "reg_fused.cuh"
+#include "train_gemm.cuh"
 
 namespace chromo {
 long long launch_counter(bool reset);
@@ -314,7 +315,11 @@ using namespace chromo;
 extern "C" {
 
 int chromo_abi_version(void) { return CHROMO_ABI_VERSION; }
-int chromo_debug_trace(int64_t* buf) { chromo::reg_fused_set_trace(reinterpret_cast<long long*>(buf)); return CHROMO_OK; }
+int chromo_debug_trace(int64_t* buf) {
+    chromo::reg_fused_set_trace(reinterpret_cast<long long*>(buf));
+    chromo::tc_gemm_set_trace(reinterpret_cast<long long*>(buf));
+    return CHROMO_OK;
+}
 int64_t chromo_launch_counter(int32_t reset) { return chromo::launch_counter(reset != 0); }
 const char* chromo_last_error(void) { return g_err; }
 

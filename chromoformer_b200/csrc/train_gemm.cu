@@ -16,6 +16,7 @@
 // Epilogues (tcgen05.ld, thread = accumulator row): bias, residual add, pre-LayerNorm stash + LayerNorm, ReLU, ReLU
 // mask of the backward pass; rows leave through a shared-memory transpose as 128-byte segments.
 #include <algorithm>
+#include <stdlib.h>
 #include <string.h>
 #include <unordered_map>
 #include <cuda_bf16.h>
@@ -26,15 +27,27 @@
 
 namespace chromo {
 
+static long long* g_tg_trace = nullptr;        // chromo_debug_trace: phase clocks of CTA 0 of every tc_gemm launch ([2048..))
+void tc_gemm_set_trace(long long* buf) { g_tg_trace = buf; }
+
 namespace {
 
-constexpr int TG_THREADS = 256;
+constexpr int TG_THREADS = 512;                // 16 warps: the staging and the epilogue of a tile are latency chains per warp
 constexpr int TG_WARPS = TG_THREADS / 32;
 constexpr int TG_KCH = 128;                    // contraction elements per chunk
 constexpr uint32_t TG_A_BYTES = 128 * TG_KCH * 2;
 constexpr int TG_UNR = 8;                      // 32-byte runs per thread in flight
 constexpr int STAGE_LD = 33;                   // padded row of the per-warp 32 x 32 epilogue staging tile
 
+// round half up on the integer pipe (tuning experiment: F2FP is a low-rate instruction)
+__device__ __forceinline__ uint32_t pack2_int(float lo, float hi) {
+    return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
+}
+__device__ __forceinline__ uint4 pack8_int(const float4& a, const float4& b) {
+    uint4 pk;
+    pk.x = pack2_int(a.x, a.y); pk.y = pack2_int(a.z, a.w); pk.z = pack2_int(b.x, b.y); pk.w = pack2_int(b.z, b.w);
+    return pk;
+}
 __device__ __forceinline__ uint4 pack8(const float4& a, const float4& b) {
     __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
     __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
@@ -63,9 +76,9 @@ __device__ __forceinline__ void load8(const float* __restrict__ p, int n, bool v
 //   mn_major == 1: memory is [kc, mn] (mn contiguous)  -> ((mn/8)*16 + kc/8)*128 + (kc%8)*16 + (mn%8)*2
 // Out-of-range elements are zeros.  `div` broadcasts memory ROWS (row index / div).  `vec`: 16-byte loads are legal
 // (aligned base, leading dimension a multiple of 4 floats).
-__device__ __forceinline__ void stage_operand(uint8_t* dst, const float* __restrict__ src, long long ld, int mn_major, int div,
-                                              int rows, int mn0, int mn_lim, int kc0, int kc_lim, bool vec, int warp,
-                                              int lane) {
+__device__ __noinline__ void stage_operand_generic(uint8_t* dst, const float* __restrict__ src, long long ld, int mn_major,
+                                                   int div, int rows, int mn0, int mn_lim, int kc0, int kc_lim, bool vec,
+                                                   int warp, int lane) {
     const int rg_n = (rows + 31) >> 5;
     const int units = mn_major ? (TG_KCH / 8) * rg_n : (rows >> 3) * 4;
     for (int u0 = warp; u0 < units; u0 += TG_WARPS * TG_UNR) {
@@ -96,16 +109,84 @@ __device__ __forceinline__ void stage_operand(uint8_t* dst, const float* __restr
     }
 }
 
+// The same staging when no row is broadcast (div == 1) and the tile's 32-column groups divide the 16 warps: the runs of
+// a thread then differ by constant strides in memory and in the tile, so that a chunk costs each thread two compares,
+// two 16-byte loads, four conversions and one 16-byte store per run - all loads ahead of the first conversion.
+__device__ __forceinline__ void stage_operand(uint8_t* dst, const float* __restrict__ src, long long ld, int mn_major, int div,
+                                              int rows, int mn0, int mn_lim, int kc0, int kc_lim, bool vec, int warp,
+                                              int lane, int dbg = 0) {
+    const int rg_n = (rows + 31) >> 5;
+    if (div != 1 || (mn_major && (TG_WARPS % rg_n) != 0)) {
+        stage_operand_generic(dst, src, ld, mn_major, div, rows, mn0, mn_lim, kc0, kc_lim, vec, warp, lane);
+        return;
+    }
+    const float* p; long long pstride; uint32_t off, ostride; int idx, istride, ilim, nq, nvalid;
+    if (!mn_major) {
+        const int units = (rows >> 3) * 4;
+        const int r0 = (warp >> 2) * 8 + (lane >> 2), c8 = (warp & 3) * 4 + (lane & 3);
+        nq = warp < units ? (units - warp + TG_WARPS - 1) / TG_WARPS : 0;
+        p = src + (long long)(mn0 + r0) * ld + kc0 + c8 * 8; pstride = (long long)(TG_WARPS / 4) * 8 * ld;
+        off = (uint32_t)(((r0 >> 3) * 16 + c8) * 128 + (r0 & 7) * 16); ostride = (TG_WARPS / 4) * 2048;
+        idx = mn0 + r0; istride = (TG_WARPS / 4) * 8; ilim = mn_lim;
+        nvalid = kc_lim - (kc0 + c8 * 8);
+    } else {
+        const int per = TG_WARPS / rg_n;                      // k groups advanced per step
+        const int kq = warp / rg_n, r8 = (warp % rg_n) * 4 + (lane & 3), k = kq * 8 + (lane >> 2);
+        nq = (r8 * 8 < rows && kq < TG_KCH / 8) ? (TG_KCH / 8 - kq + per - 1) / per : 0;
+        p = src + (long long)(kc0 + k) * ld + mn0 + r8 * 8; pstride = (long long)per * 8 * ld;
+        off = (uint32_t)((r8 * 16 + (k >> 3)) * 128 + (k & 7) * 16); ostride = per * 128;
+        idx = kc0 + k; istride = per * 8; ilim = kc_lim;
+        nvalid = mn_lim - (mn0 + r8 * 8);
+    }
+    nvalid = nvalid < 0 ? 0 : (nvalid > 8 ? 8 : nvalid);
+    if (dbg & 1) ilim = 0;
+    if (dbg & 2) nq = 0;
+    const bool full = vec && nvalid == 8;
+    for (int q0 = 0; q0 < nq; q0 += TG_UNR) {
+        float4 x[TG_UNR][2];
+        if (full) {
+#pragma unroll
+            for (int j = 0; j < TG_UNR; ++j) {
+                const int q = q0 + j;
+                x[j][0] = x[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < nq && idx + q * istride < ilim) {
+                    const float* pp = p + q * pstride;
+                    x[j][0] = __ldg(reinterpret_cast<const float4*>(pp));
+                    x[j][1] = __ldg(reinterpret_cast<const float4*>(pp + 4));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < TG_UNR; ++j) {
+                const int q = q0 + j;
+                x[j][0] = x[j][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < nq && idx + q * istride < ilim && nvalid > 0) load8(p + q * pstride, nvalid, false, x[j][0], x[j][1]);
+            }
+        }
+        if (dbg & 4) {
+#pragma unroll
+            for (int j = 0; j < TG_UNR; ++j)
+                if (q0 + j < nq) *reinterpret_cast<uint4*>(dst + off + (uint32_t)(q0 + j) * ostride) = pack8_int(x[j][0], x[j][1]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < TG_UNR; ++j)
+                if (q0 + j < nq) *reinterpret_cast<uint4*>(dst + off + (uint32_t)(q0 + j) * ostride) = pack8(x[j][0], x[j][1]);
+        }
+    }
+}
+
 struct Operands {
     const float* A; long long lda; int a_t, a_div, a_vec, m0, m_lim;
     const float* B; long long ldb; int b_t, b_div, b_vec, n0, n_lim;
     int Kc, NT;
+    int dbg = 0;                // tuning experiments (CHROMO_TG_DBG): 1 = no loads, 2 = no conversion / stores
 };
 
 // The contraction of one output tile into TMEM columns [0, NT).  `g` counts the chunks this CTA has pushed through the
 // two stages so far (mbarrier parities carry over from tile to tile), `tiles` the tiles it has finished.
 __device__ __forceinline__ void contract_tile(const Operands& o, uint8_t* smem, uint32_t stage_bytes, uint64_t* bars,
-                                              uint32_t tmem, uint32_t& g, uint32_t tiles, int tid, int warp, int lane) {
+                                              uint32_t tmem, uint32_t& g, uint32_t tiles, int tid, int warp, int lane,
+                                              long long* trace = nullptr) {
     const int chunks = (o.Kc + TG_KCH - 1) / TG_KCH;
     const uint32_t idesc = umma_idesc_bf16(128, o.NT) | (o.a_t ? (1u << 15) : 0u) | (o.b_t ? (1u << 16) : 0u);
     for (int ci = 0; ci < chunks; ++ci, ++g) {
@@ -114,10 +195,13 @@ __device__ __forceinline__ void contract_tile(const Operands& o, uint8_t* smem, 
         uint8_t* sB = sA + TG_A_BYTES;
         if (g >= 2) mbar_wait(&bars[st], ((g >> 1) - 1) & 1);           // the MMAs of chunk g-2 have left this stage
         const int kc0 = ci * TG_KCH;
-        stage_operand(sA, o.A, o.lda, o.a_t, o.a_div, 128, o.m0, o.m_lim, kc0, o.Kc, o.a_vec, warp, lane);
-        stage_operand(sB, o.B, o.ldb, o.b_t, o.b_div, o.NT, o.n0, o.n_lim, kc0, o.Kc, o.b_vec, warp, lane);
+        stage_operand(sA, o.A, o.lda, o.a_t, o.a_div, 128, o.m0, o.m_lim, kc0, o.Kc, o.a_vec, warp, lane, o.dbg);
+        if (ci == 0 && trace && tid == 0) trace[2] = clock64();
+        stage_operand(sB, o.B, o.ldb, o.b_t, o.b_div, o.NT, o.n0, o.n_lim, kc0, o.Kc, o.b_vec, warp, lane, o.dbg);
+        if (ci == 0 && trace && tid == 0) trace[3] = clock64();
         fence_async_smem();
         __syncthreads();
+        if (ci == 0 && trace && tid == 0) trace[4] = clock64();
         if (tid == 0) {
             tc_fence_after();
             const int ksteps = (min(TG_KCH, o.Kc - kc0) + 15) / 16;
@@ -127,6 +211,7 @@ __device__ __forceinline__ void contract_tile(const Operands& o, uint8_t* smem, 
             if (ci == chunks - 1) umma_commit(&bars[2]);
         }
     }
+    if (trace && tid == 0) trace[5] = clock64();
     mbar_wait(&bars[2], tiles & 1);
     tc_fence_after();
 }
@@ -150,15 +235,60 @@ __device__ __forceinline__ void store_tile_f32(float* stage, const float* v, flo
     __syncwarp();
 }
 
-__global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a) {
+// The reverse: a 32 x 32 tile of a row-major matrix (row of tile row r at element offset `rowoff` of lane r) into
+// (lane = row, v[0..31] = columns) through the same padded shared tile: 4 rows x 128 contiguous bytes per load.
+__device__ __forceinline__ void load_tile_f32(float* stage, float* v, const float* src, long long rowoff, int col0, int ncols,
+                                              int lane, unsigned rowmask) {
+    const int cq = (lane & 7) * 4;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3);
+        const long long ro = __shfl_sync(0xffffffffu, rowoff, r);
+        float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (((rowmask >> r) & 1u) && cq < ncols) x = *reinterpret_cast<const float4*>(src + ro + col0 + cq);
+        float* sp = stage + r * STAGE_LD + cq;
+        sp[0] = x.x; sp[1] = x.y; sp[2] = x.z; sp[3] = x.w;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = stage[lane * STAGE_LD + j];
+    __syncwarp();
+}
+
+// C tile (32 consecutive rows from `C`, leading dimension ldc) += (lane = row, v = columns), coalesced
+__device__ __forceinline__ void add_tile_f32(float* stage, const float* v, float* C, long long ldc, int ncols, int nrows,
+                                             int lane) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) stage[lane * STAGE_LD + j] = v[j];
+    __syncwarp();
+    const int cq = (lane & 7) * 4;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3);
+        if (r < nrows && cq < ncols) {
+            const float* sp = stage + r * STAGE_LD + cq;
+            float4* out = reinterpret_cast<float4*>(C + (long long)r * ldc + cq);
+            float4 x = *out;
+            x.x += sp[0]; x.y += sp[1]; x.z += sp[2]; x.w += sp[3];
+            *out = x;
+        }
+    }
+    __syncwarp();
+}
+
+#define TG_MARK(i) do { if (trace && tid == 0) trace[i] = clock64(); } while (0)
+
+__global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a, long long* trace_buf, int dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    long long* trace = (trace_buf && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? trace_buf : nullptr;
     const int NT = a.NT;
     const uint32_t stage_bytes = TG_A_BYTES + (uint32_t)NT * TG_KCH * 2;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);      // [0,1] stage free, [2] tile done
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
-    float* red = reinterpret_cast<float*>(bars + 4);                            // [2][128][2] LayerNorm partial sums
+    float* red = reinterpret_cast<float*>(bars + 4);                            // [4][128][2] LayerNorm partial sums
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n0 = blockIdx.x * NT, m0 = blockIdx.y * 128, z = blockIdx.z;
+    TG_MARK(0);
     int tmem_cols = 32;
     while (tmem_cols < NT) tmem_cols *= 2;
 
@@ -171,15 +301,17 @@ __global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    TG_MARK(1);
 
     Operands o;
     o.A = a.A + z * a.a_z; o.lda = a.lda; o.a_t = a.a_t; o.a_div = a.a_div; o.m0 = m0; o.m_lim = a.M;
     o.B = a.B + z * a.b_z; o.ldb = a.ldb; o.b_t = a.b_t; o.b_div = a.b_div; o.n0 = n0; o.n_lim = a.N;
     o.a_vec = ((reinterpret_cast<uintptr_t>(o.A) & 15) == 0 && (a.lda & 3) == 0) ? 1 : 0;
     o.b_vec = ((reinterpret_cast<uintptr_t>(o.B) & 15) == 0 && (a.ldb & 3) == 0) ? 1 : 0;
-    o.Kc = a.Kc; o.NT = NT;
+    o.Kc = a.Kc; o.NT = NT; o.dbg = dbg;
     uint32_t g = 0;
-    contract_tile(o, smem, stage_bytes, bars, tmem, g, 0, tid, warp, lane);
+    contract_tile(o, smem, stage_bytes, bars, tmem, g, 0, tid, warp, lane, trace);
+    TG_MARK(6);
 
     // ------------------------------------------------------------------ epilogue ----
     // all MMAs have completed: the operand stages are dead, reuse them as the transpose staging of the stores
@@ -192,63 +324,60 @@ __global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a) {
     const long long crow = ok ? (long long)(m / a.c_div) * a.c_mul + (m % a.c_div) + a.c_add : 0;
     float* C = a.C + z * a.c_z;
     const float* bias = (a.epi & TC_BIAS) ? a.bias + z * a.bias_z : nullptr;
-    const float* res = (a.epi & TC_RES) ? a.res + z * a.res_z + (ok ? (long long)(m / a.res_div) * a.ldres : 0) : nullptr;
-    float v[32];
+    const float* res = (a.epi & TC_RES) ? a.res + z * a.res_z : nullptr;
+    const long long res_off = ok ? (long long)(m / a.res_div) * a.ldres : 0;
+    float v[32], t[32];
     if (a.epi & TC_LN) {
-        // N == NT == 128.  The two warps sharing a lane quarter each own two 32-column chunks of the row: partial sums
-        // meet in shared memory, then each normalises and writes its chunks.
+        // N == NT == 128.  The four warps sharing a lane quarter each own one 32-column chunk of the row: partial sums
+        // meet in shared memory, then each normalises and writes its chunk.
         const float* gamma = a.gamma + z * a.ln_z;
         const float* beta = a.beta + z * a.ln_z;
-        float* pre = (a.pre && ok) ? a.pre + z * a.pre_z + (long long)m * a.N : nullptr;
-        float keep[2][32];
+        const int c = ch * 32, rr = lq * 32 + lane;
         float sum = 0.f, sq = 0.f;
+        tmem_ld32(trow + c, v);
+        if (res) {
+            load_tile_f32(stage, t, res, res_off, c, 32, lane, rowmask);
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
-            const int c = (2 * ci + ch) * 32;
-            tmem_ld32(trow + c, v);
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                float4 r4 = make_float4(0, 0, 0, 0);
-                if (res && ok) r4 = *reinterpret_cast<const float4*>(res + c + j);
-                const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + c + j) : make_float4(0, 0, 0, 0);
-                const float t0 = v[j] + b4.x + r4.x, t1 = v[j + 1] + b4.y + r4.y;
-                const float t2 = v[j + 2] + b4.z + r4.z, t3 = v[j + 3] + b4.w + r4.w;
-                keep[ci][j] = t0; keep[ci][j + 1] = t1; keep[ci][j + 2] = t2; keep[ci][j + 3] = t3;
-                sum += (t0 + t1) + (t2 + t3);
-                if (pre) *reinterpret_cast<float4*>(pre + c + j) = make_float4(t0, t1, t2, t3);
-            }
+            for (int j = 0; j < 32; ++j) v[j] += t[j];
         }
-        red[(ch * 128 + lq * 32 + lane) * 2] = sum;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 b4 = bias ? *reinterpret_cast<const float4*>(bias + c + j) : make_float4(0, 0, 0, 0);
+            v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+            sum += (v[j] + v[j + 1]) + (v[j + 2] + v[j + 3]);
+        }
+        if (a.pre) store_tile_f32(stage, v, a.pre + z * a.pre_z, ok ? (long long)m : 0, a.N, c, 32, lane, rowmask);
+        red[(ch * 128 + rr) * 2] = sum;
         __syncthreads();
-        sum += red[((1 - ch) * 128 + lq * 32 + lane) * 2];
+        sum = (red[rr * 2] + red[(128 + rr) * 2]) + (red[(256 + rr) * 2] + red[(384 + rr) * 2]);
         const float mean = sum * (1.f / 128.f);
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci)
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { const float d = keep[ci][j] - mean; sq = fmaf(d, d, sq); }
-        red[(ch * 128 + lq * 32 + lane) * 2 + 1] = sq;
+        for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; sq = fmaf(d, d, sq); }
+        red[(ch * 128 + rr) * 2 + 1] = sq;
         __syncthreads();
-        sq += red[((1 - ch) * 128 + lq * 32 + lane) * 2 + 1];
+        sq = (red[rr * 2 + 1] + red[(128 + rr) * 2 + 1]) + (red[(256 + rr) * 2 + 1] + red[(384 + rr) * 2 + 1]);
         const float rstd = rsqrtf(sq * (1.f / 128.f) + 1e-5f);
 #pragma unroll
-        for (int ci = 0; ci < 2; ++ci) {
-            const int c = (2 * ci + ch) * 32;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-                const float4 ga = *reinterpret_cast<const float4*>(gamma + c + j);
-                const float4 be = *reinterpret_cast<const float4*>(beta + c + j);
-                v[j] = (keep[ci][j] - mean) * rstd * ga.x + be.x;
-                v[j + 1] = (keep[ci][j + 1] - mean) * rstd * ga.y + be.y;
-                v[j + 2] = (keep[ci][j + 2] - mean) * rstd * ga.z + be.z;
-                v[j + 3] = (keep[ci][j + 3] - mean) * rstd * ga.w + be.w;
-            }
-            store_tile_f32(stage, v, C, crow, a.ldc, c, 32, lane, rowmask);
+        for (int j = 0; j < 32; j += 4) {
+            const float4 ga = *reinterpret_cast<const float4*>(gamma + c + j);
+            const float4 be = *reinterpret_cast<const float4*>(beta + c + j);
+            v[j] = (v[j] - mean) * rstd * ga.x + be.x;
+            v[j + 1] = (v[j + 1] - mean) * rstd * ga.y + be.y;
+            v[j + 2] = (v[j + 2] - mean) * rstd * ga.z + be.z;
+            v[j + 3] = (v[j + 3] - mean) * rstd * ga.w + be.w;
         }
+        store_tile_f32(stage, v, C, crow, a.ldc, c, 32, lane, rowmask);
     } else {
-        const float* mask = (a.epi & TC_MASK) ? a.mask + z * a.mask_z + (ok ? (long long)m * a.ldmask : 0) : nullptr;
-        for (int c = ch * 32; c < NT; c += 64) {
+        const float* mask = (a.epi & TC_MASK) ? a.mask + z * a.mask_z : nullptr;
+        const long long mask_off = ok ? (long long)m * a.ldmask : 0;
+        for (int c = ch * 32; c < NT; c += 128) {
             tmem_ld32(trow + c, v);          // columns beyond NT (NT % 32 != 0) are dropped below
             const int ncols = min(32, NT - c);
+            if (res) {
+                load_tile_f32(stage, t, res, res_off, n0 + c, ncols, lane, rowmask);
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] += t[j];
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 if (j < ncols) {
@@ -256,29 +385,35 @@ __global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a) {
                         const float4 b4 = *reinterpret_cast<const float4*>(bias + n0 + c + j);
                         v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
                     }
-                    if (res && ok) {
-                        const float4 r4 = *reinterpret_cast<const float4*>(res + n0 + c + j);
-                        v[j] += r4.x; v[j + 1] += r4.y; v[j + 2] += r4.z; v[j + 3] += r4.w;
-                    }
                     if (a.epi & TC_RELU) {
                         v[j] = fmaxf(v[j], 0.f); v[j + 1] = fmaxf(v[j + 1], 0.f);
                         v[j + 2] = fmaxf(v[j + 2], 0.f); v[j + 3] = fmaxf(v[j + 3], 0.f);
                     }
-                    if (mask && ok) {
-                        const float4 k4 = *reinterpret_cast<const float4*>(mask + n0 + c + j);
-                        if (!(k4.x > 0.f)) v[j] = 0.f;
-                        if (!(k4.y > 0.f)) v[j + 1] = 0.f;
-                        if (!(k4.z > 0.f)) v[j + 2] = 0.f;
-                        if (!(k4.w > 0.f)) v[j + 3] = 0.f;
-                    }
                 }
             }
-            store_tile_f32(stage, v, C, crow, a.ldc, n0 + c, ncols, lane, rowmask);
+            if (mask) {
+                load_tile_f32(stage, t, mask, mask_off, n0 + c, ncols, lane, rowmask);
+#pragma unroll
+                for (int j = 0; j < 32; ++j)
+                    if (!(t[j] > 0.f)) v[j] = 0.f;
+            }
+            if (dbg & 8) {
+                if (ok) {
+                    float* out = C + crow * a.ldc + n0 + c;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4)
+                        if (j < ncols) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+            } else {
+                store_tile_f32(stage, v, C, crow, a.ldc, n0 + c, ncols, lane, rowmask);
+            }
         }
     }
+    TG_MARK(7);
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, tmem_cols);
+    TG_MARK(8);
 }
 
 // ------------------------------------------------------------------ deferred weight / bias gradients ----
@@ -292,8 +427,10 @@ struct WgTable {
 static_assert(sizeof(WgItem) == 48, "WgItem layout");
 static_assert(sizeof(WgTable) <= 32000, "kernel parameter space");
 
-__global__ void __launch_bounds__(TG_THREADS) wgrad_grouped_kernel(const __grid_constant__ WgTable tbl) {
+__global__ void __launch_bounds__(TG_THREADS) wgrad_grouped_kernel(const __grid_constant__ WgTable tbl, long long* trace_buf) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    long long* trace = (trace_buf && blockIdx.x == 0) ? trace_buf : nullptr;
+    int tr_i = 0;
     constexpr uint32_t stage_bytes = TG_A_BYTES + (uint32_t)WG_NT_MAX * TG_KCH * 2;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
@@ -312,8 +449,10 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_grouped_kernel(const __grid_
     const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
     uint32_t g = 0, tiles = 0;
 
+    if (trace && threadIdx.x == 0) trace[tr_i++] = clock64();
     for (int it = blockIdx.x; it < tbl.n; it += gridDim.x) {
         const WgItem& w = tbl.items[it];
+        if (trace && threadIdx.x == 0 && tr_i < 60) { trace[tr_i++] = ((long long)w.tokens << 48) | ((long long)w.n_cols << 36) | (clock64() & 0xfffffffffLL); }
         if (w.kind & 1) {
             // db[n] += sum_t dY[t, n]: one column per thread, four rows in flight
             if (tid < w.n_cols) {
@@ -338,27 +477,25 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_grouped_kernel(const __grid_
         o.Kc = w.tokens; o.NT = (w.n_cols + 15) & ~15;
         contract_tile(o, smem, stage_bytes, bars, tmem, g, tiles, tid, warp, lane);
         ++tiles;
-        // dW tile += accumulator (this CTA owns the tile for the whole launch: plain read-modify-write)
+        if (trace && threadIdx.x == 0 && tr_i < 60) trace[tr_i++] = clock64() & 0xfffffffffLL;
+        // dW tile += accumulator (this CTA owns the tile for the whole launch: plain read-modify-write, through a
+        // shared-memory transpose so that every access covers 4 rows x 128 contiguous bytes)
         const int row = lq * 32 + lane;
         const bool vec = (reinterpret_cast<uintptr_t>(w.C) & 15) == 0 && (w.ldc & 3) == 0 && (w.n_cols & 3) == 0;
+        float* wstage = reinterpret_cast<float*>(smem) + warp * (32 * STAGE_LD);     // (all MMAs of the tile have completed)
         float v[32];
-        for (int c = ch * 32; c < o.NT; c += 64) {
+        for (int c = ch * 32; c < o.NT; c += 128) {
             tmem_ld32(trow + c, v);
-            if (row < w.m_rows) {
+            const int ncols = min(32, w.n_cols - c);
+            if (vec && !(w.kind & 2)) {
+                if (lq * 32 < w.m_rows && ncols > 0)
+                    add_tile_f32(wstage, v, w.C + (long long)(lq * 32) * w.ldc + c, w.ldc, ncols, w.m_rows - lq * 32, lane);
+            } else if (row < w.m_rows) {
                 float* out = w.C + (long long)row * w.ldc + c;
-                const int ncols = min(32, w.n_cols - c);
                 if (w.kind & 2) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (j < ncols) atomicAdd(out + j, v[j]);
-                } else if (vec) {
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        if (j < ncols) {
-                            float4 x = *reinterpret_cast<float4*>(out + j);
-                            x.x += v[j]; x.y += v[j + 1]; x.z += v[j + 2]; x.w += v[j + 3];
-                            *reinterpret_cast<float4*>(out + j) = x;
-                        }
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
@@ -366,8 +503,11 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_grouped_kernel(const __grid_
                 }
             }
         }
+        __syncthreads();              // the staging area goes back to the operands of the next tile
         tc_fence_before();            // the next tile's first MMA overwrites these columns: order it behind the loads
+        if (trace && threadIdx.x == 0 && tr_i < 60) trace[tr_i++] = clock64() & 0xfffffffffLL;
     }
+    if (trace && threadIdx.x == 0) { trace[tr_i++] = clock64() & 0xfffffffffLL; trace[63] = tr_i; }
     tc_fence_before();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tmem, WG_NT_MAX);
@@ -388,7 +528,7 @@ int choose_nt(int N, int M, int nz, bool ln) {
     return 0;
 }
 
-size_t gemm_smem(int NT) { return 2 * ((size_t)TG_A_BYTES + (size_t)NT * TG_KCH * 2) + 64 + 2 * 128 * 2 * 4; }
+size_t gemm_smem(int NT) { return 2 * ((size_t)TG_A_BYTES + (size_t)NT * TG_KCH * 2) + 64 + 4 * 128 * 2 * 4; }
 
 }  // namespace
 
@@ -423,7 +563,8 @@ int tc_gemm_launch(const TcGemm& in, int nz, cudaStream_t st) {
         configured = gemm_smem(256);
     }
     dim3 grid(a.N / a.NT, (a.M + 127) / 128, nz);
-    tc_gemm_kernel<<<grid, TG_THREADS, smem, st>>>(a);
+    const char* dbg = getenv("CHROMO_TG_DBG");
+    tc_gemm_kernel<<<grid, TG_THREADS, smem, st>>>(a, g_tg_trace ? g_tg_trace + 2048 : nullptr, dbg ? atoi(dbg) : 0);
     CHROMO_CHECK_LAUNCH("tc_gemm");
     return CHROMO_OK;
 }
@@ -493,7 +634,7 @@ int WgradQueue::flush(cudaStream_t st) {
         tbl.n = (int)wave.size();
         std::copy(wave.begin(), wave.end(), tbl.items);
         const int grid = std::min(tbl.n, sms);
-        wgrad_grouped_kernel<<<grid, TG_THREADS, smem, st>>>(tbl);
+        wgrad_grouped_kernel<<<grid, TG_THREADS, smem, st>>>(tbl, g_tg_trace ? g_tg_trace + 3072 : nullptr);
         CHROMO_CHECK_LAUNCH("wgrad_grouped");
     }
     return CHROMO_OK;

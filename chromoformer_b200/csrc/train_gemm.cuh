@@ -27,6 +27,7 @@ struct TcGemm {
 TcGemm tc_gemm_args();
 bool tc_gemm_supported(const TcGemm& g);
 int tc_gemm_launch(const TcGemm& g, int nz, cudaStream_t st);
+void tc_gemm_set_trace(long long* buf);      // chromo_debug_trace: phase clocks of CTA 0 at buf[2048..2056]
 
 // Deferred weight / bias gradients: every  dW += dY^T X  and  db += colsum(dY)  of a backward pass is queued here and
 // executed by ONE persistent launch at the end (their operands stay alive until then: backward.cu keeps each layer's
