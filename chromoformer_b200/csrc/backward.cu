@@ -577,6 +577,13 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
         CHROMO_TRY(bwd_data(cx, dProj, 4 * dmr, GS, P + ra.att, L.reg_stride, gcur, D, GS, T, 4 * dmr, D, resid, NR));
         // gcur = dX of this layer = the gradient arriving at the output of layer l-1; gnext is free again
     }
+    // The Regulation transformer's weight gradients (two thirds of the queue) start now, on a side stream and on two
+    // thirds of the SMs, under the Pairwise / Embedding backward; the rest follows at the end.
+    cudaStream_t wst = st;
+    if (tc && !getenv("CHROMO_WGRAD_AT_END")) {
+        CHROMO_TRY(aux_fork(st, &wst));
+        if (wst != st) CHROMO_TRY(queue.flush(wst, 96));
+    }
     float* gR = gcur;                   // dX_in (without the residual of net.py:378)
     head_residual_kernel<<<dim3((B * D + 255) / 256, NR), 256, 0, st>>>(gR, GS, ws + o_dz, B, S, D, NR);
     CHROMO_CHECK_LAUNCH("head_residual");
@@ -599,6 +606,8 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
         CHROMO_TRY(bwd_weight(cx, gC, D, GS, ws + w.p_av + so, dmp, 1, RS, G + pa.ffw, dmp, L.pw_stride, R, D, dmp, NR));
         CHROMO_TRY(bwd_bias(cx, gC, D, GS, G + pa.ffb, L.pw_stride, R, D, NR));
         CHROMO_TRY(bwd_data(cx, gC, D, GS, P + pa.ffw, L.pw_stride, ws + o_dAvp[l], dmp, GS, R, D, dmp, DataEpi(), NR));
+        ResStreams prs;
+        CHROMO_TRY(res_fork(st, NR, prs));
         for (int r = 0; r < NR; ++r) {
             SqaBwd s;
             s.rows = R; s.H = Hp; s.dm = dmp; s.D = D; s.n = c->n_bins[r]; s.F = F;
@@ -614,8 +623,10 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
             s.dAv = ws + r * GS + o_dAvp[l]; s.dQ = ws + r * GS + o_dQp[l];
             s.dCbar = ws + r * GS + o_dCbP[l]; s.dQK = ws + r * GS + o_dQKp[l]; s.dU8 = ws + r * GS + o_dU8p[l];
             s.dS = ws + o_dSp[r];
-            CHROMO_TRY(sqa_bwd(cx, s));
+            Ctx cr = cx; cr.st = prs.s[r];
+            CHROMO_TRY(sqa_bwd(cr, s));
         }
+        CHROMO_TRY(res_join(prs));
         CHROMO_TRY(bwd_weight(cx, ws + o_dQp[l], dmp, GS, pin, D, pin_div, RS, G + pa.p_att, D, L.pw_stride, R, dmp, D, NR));
         DataEpi resid; resid.res = gC;
         CHROMO_TRY(bwd_data(cx, ws + o_dQp[l], dmp, GS, P + pa.p_att, L.pw_stride, pcur, D, GS, R, dmp, D, resid, NR));
@@ -633,6 +644,12 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
         CHROMO_TRY(gemm_auto(g, true, false, NR, st, tc));
     }
 
+    if (wst != st) {     // the Pairwise weight gradients follow on the side stream (its operands are final: order them behind st)
+        cudaStream_t again = st;
+        CHROMO_TRY(aux_fork(st, &again));
+        CHROMO_TRY(queue.flush(again, 64));
+    }
+
     // ---- Embedding transformer ----------------------------------------------------
     float* ecur = ws + o_tE0;
     float* enext = ws + o_tE1;
@@ -648,6 +665,8 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
         CHROMO_TRY(bwd_weight(cx, gC, D, GS, ws + w.e_av, dme, 1, RS, G + ea.ffw, dme, L.embed_stride, B, D, dme, NR));
         CHROMO_TRY(bwd_bias(cx, gC, D, GS, G + ea.ffb, L.embed_stride, B, D, NR));
         CHROMO_TRY(bwd_data(cx, gC, D, GS, P + ea.ffw, L.embed_stride, ws + o_dAve, dme, GS, B, D, dme, DataEpi(), NR));
+        ResStreams ers;
+        CHROMO_TRY(res_fork(st, NR, ers));
         for (int r = 0; r < NR; ++r) {
             SqaBwd s;
             s.rows = B; s.H = He; s.dm = dme; s.D = D; s.n = c->n_bins[r]; s.F = F;
@@ -663,8 +682,10 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
             s.dAv = ws + r * GS + o_dAve; s.dQ = ws + r * GS + o_dQe;
             s.dCbar = ws + r * GS + o_dCbE; s.dQK = ws + r * GS + o_dQKe; s.dU8 = ws + r * GS + o_dU8e;
             s.dS = ws + o_dSe[r];
-            CHROMO_TRY(sqa_bwd(cx, s));
+            Ctx cr = cx; cr.st = ers.s[r];
+            CHROMO_TRY(sqa_bwd(cr, s));
         }
+        CHROMO_TRY(res_join(ers));
         // W_q is rows [0, dme) of att.weight
         CHROMO_TRY(bwd_weight(cx, ws + o_dQe, dme, GS, ws + w.e_hc, D, 1, RS, G + ea.att, D, L.embed_stride, B, dme, D, NR));
         DataEpi resid; resid.res = gC;
@@ -676,7 +697,8 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
                                   G + L.embed[r].lin_proj, F, 0, B, D, F, 1));
         }
     }
-    return tc ? queue.flush(st) : CHROMO_OK;
+    if (tc) CHROMO_TRY(queue.flush(st));
+    return aux_join(st, wst);
 }
 
 }  // namespace chromo

@@ -111,4 +111,19 @@ WsLayout make_ws_layout(const chromo_config_t* cfg, int batch, int flags);
 
 static inline int64_t align4(int64_t x) { return (x + 3) & ~int64_t(3); }
 
+// --------------------------------------------------- per-resolution branches --
+// The 2000 / 500 / 100-bp chains of a stage are independent wherever their shapes differ (the single-query attention
+// over n bins): between res_fork and res_join resolution r runs on `s[r]` (s[0] is the caller's stream, the others are
+// library-owned side streams ordered behind it by an event), so the chains overlap on the device - also inside a captured
+// CUDA graph, where the events become plain dependency edges.
+struct ResStreams {
+    cudaStream_t s[CHROMO_MAX_RES];
+    int n;
+};
+int res_fork(cudaStream_t st, int n, ResStreams& rs);
+int res_join(const ResStreams& rs);
+// One more side stream, independent of the per-resolution ones (the early weight-gradient launch of backward.cu)
+int aux_fork(cudaStream_t st, cudaStream_t* aux);     // *aux == st when side streams are off
+int aux_join(cudaStream_t st, cudaStream_t aux);
+
 }  // namespace chromo

@@ -748,6 +748,8 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     CHROMO_TRY(sqa_fused(B, c->embed_heads, in->x_p, in->mask_p, in->mask_p_stride, in->mask_p_row_offset,
                          L.embed[0].lin_proj, L.embed_stride, 0, dme, ws + w.e_qk, ws + w.e_qkt, ws + w.e_cbar, cb16, false, e_tiles,
                          &e_fused));
+    ResStreams ers;
+    if (!e_fused) CHROMO_TRY(res_fork(st, NR, ers));
     for (int r = 0; r < NR && !e_fused; ++r) {
         SqaArgs s;
         s.rows = B; s.H = c->embed_heads; s.dm = dme; s.D = D; s.n = c->n_bins[r]; s.F = F;
@@ -762,8 +764,9 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         s.pet_pk = pe_packed ? reinterpret_cast<const __nv_bfloat16*>(ws + w.bf_pet[r]) : nullptr;
         s.qk = ws + r * RS + w.e_qk; s.P = ws + w.e_p[r]; s.xbar = ws + r * RS + w.e_xbar;
         s.cbar = ws + r * RS + w.e_cbar; s.av = ws + r * RS + w.e_av; s.folded = fold; s.tc = bf16 && train;
-        CHROMO_TRY(single_query_attention(s, st));
+        CHROMO_TRY(single_query_attention(s, ers.s[r]));
     }
+    if (!e_fused) CHROMO_TRY(res_join(ers));
     const long long tail_z = (long long)(1 + c->pw_layers) * TAIL_SLOT_ELEMS;
     if (tail) {   // out-projection + LN + FFN + LN in one launch (row_tail_fused.cu) -> X_in[b, 0, :]
         RowTailArgs t;
@@ -855,6 +858,8 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         CHROMO_TRY(sqa_fused(R, Hp, in->x_pcre, in->mask_pcre, in->mask_pcre_stride, in->mask_pcre_row_offset,
                              L.pw[0].lin_proj_pcre, L.pw_stride, 1, dmp, ws + w.p_qk + so, ws + w.p_qkt + so, ws + w.p_cbar + so,
                              cb16, false, p_tiles, &p_fused));
+        ResStreams prs;
+        if (!p_fused) CHROMO_TRY(res_fork(st, NR, prs));
         for (int r = 0; r < NR && !p_fused; ++r) {
             SqaArgs s;
             s.rows = R; s.H = Hp; s.dm = dmp; s.D = D; s.n = c->n_bins[r]; s.F = F;
@@ -872,8 +877,9 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             s.P = ws + w.p_p[r] + (long long)w.pslot(l) * w.p_p_slot[r];
             s.xbar = ws + r * RS + w.p_xbar + so;
             s.cbar = ws + r * RS + w.p_cbar + so; s.av = ws + r * RS + w.p_av + so; s.folded = fold; s.tc = bf16 && train;
-            CHROMO_TRY(single_query_attention(s, st));
+            CHROMO_TRY(single_query_attention(s, prs.s[r]));
         }
+        if (!p_fused) CHROMO_TRY(res_join(prs));
         if (tail) {
             RowTailArgs t;
             t.M = R; t.dff = c->pw_d_ff;

@@ -1,5 +1,6 @@
 // Flat parameter layout + workspace layout + error plumbing (host only).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -306,6 +307,94 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
     }
     w.total = cur;
     return w;
+}
+
+namespace {
+struct SideStreams {
+    int device = -1;
+    cudaStream_t s[CHROMO_MAX_RES] = {};
+    cudaEvent_t fork = nullptr, join[CHROMO_MAX_RES] = {};
+};
+SideStreams g_side[16];
+}  // namespace
+
+static SideStreams* side_streams() {
+    static const bool off = getenv("CHROMO_NO_RES_STREAMS") != nullptr;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (off || dev < 0 || dev >= 16) return nullptr;
+    SideStreams& g = g_side[dev];
+    if (g.device != dev) {
+        for (int r = 1; r < CHROMO_MAX_RES; ++r) {
+            if (cudaStreamCreateWithFlags(&g.s[r], cudaStreamNonBlocking) != cudaSuccess ||
+                cudaEventCreateWithFlags(&g.join[r], cudaEventDisableTiming) != cudaSuccess) {
+                set_error("cannot create the side streams");
+                return nullptr;
+            }
+        }
+        if (cudaEventCreateWithFlags(&g.fork, cudaEventDisableTiming) != cudaSuccess) {
+            set_error("cannot create the fork event");
+            return nullptr;
+        }
+        g.device = dev;
+    }
+    return &g;
+}
+
+int res_fork(cudaStream_t st, int n, ResStreams& rs) {
+    rs.n = n;
+    rs.s[0] = st;
+    SideStreams* g = n >= 2 && n < CHROMO_MAX_RES ? side_streams() : nullptr;     // (the last side stream is aux_fork's)
+    if (!g) {
+        for (int r = 1; r < n; ++r) rs.s[r] = st;
+        rs.n = 1;                                   // nothing to join
+        return CHROMO_OK;
+    }
+    if (cudaEventRecord(g->fork, st) != cudaSuccess) { set_error("res_fork: event record failed"); return CHROMO_ECUDA; }
+    for (int r = 1; r < n; ++r) {
+        rs.s[r] = g->s[r];
+        if (cudaStreamWaitEvent(g->s[r], g->fork, 0) != cudaSuccess) { set_error("res_fork: stream wait failed"); return CHROMO_ECUDA; }
+    }
+    return CHROMO_OK;
+}
+
+int aux_fork(cudaStream_t st, cudaStream_t* aux) {
+    *aux = st;
+    SideStreams* g = side_streams();
+    if (!g) return CHROMO_OK;
+    if (cudaEventRecord(g->fork, st) != cudaSuccess || cudaStreamWaitEvent(g->s[CHROMO_MAX_RES - 1], g->fork, 0) != cudaSuccess) {
+        set_error("aux_fork: event record / wait failed");
+        return CHROMO_ECUDA;
+    }
+    *aux = g->s[CHROMO_MAX_RES - 1];
+    return CHROMO_OK;
+}
+
+int aux_join(cudaStream_t st, cudaStream_t aux) {
+    if (aux == st) return CHROMO_OK;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SideStreams& g = g_side[dev];
+    if (cudaEventRecord(g.join[CHROMO_MAX_RES - 1], aux) != cudaSuccess ||
+        cudaStreamWaitEvent(st, g.join[CHROMO_MAX_RES - 1], 0) != cudaSuccess) {
+        set_error("aux_join: event record / wait failed");
+        return CHROMO_ECUDA;
+    }
+    return CHROMO_OK;
+}
+
+int res_join(const ResStreams& rs) {
+    if (rs.n < 2) return CHROMO_OK;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    SideStreams& g = g_side[dev];
+    for (int r = 1; r < rs.n; ++r) {
+        if (cudaEventRecord(g.join[r], rs.s[r]) != cudaSuccess || cudaStreamWaitEvent(rs.s[0], g.join[r], 0) != cudaSuccess) {
+            set_error("res_join: event record / wait failed");
+            return CHROMO_ECUDA;
+        }
+    }
+    return CHROMO_OK;
 }
 
 }  // namespace chromo

@@ -594,7 +594,7 @@ void WgradQueue::add_bias(const float* dY, int ld, long long dy_z, float* db, lo
         }
 }
 
-int WgradQueue::flush(cudaStream_t st) {
+int WgradQueue::flush(cudaStream_t st, int max_ctas) {
     if (items_.empty()) return CHROMO_OK;
     // A CTA owns its output tile for the whole launch (plain read-modify-write).  Tiles are either disjoint or
     // identical; the few tensors that receive several products (dW_in: three) take theirs with FP32 atomics instead.
@@ -633,7 +633,7 @@ int WgradQueue::flush(cudaStream_t st) {
         WgTable tbl;
         tbl.n = (int)wave.size();
         std::copy(wave.begin(), wave.end(), tbl.items);
-        const int grid = std::min(tbl.n, sms);
+        const int grid = std::min(tbl.n, max_ctas > 0 ? std::min(max_ctas, sms) : sms);
         wgrad_grouped_kernel<<<grid, TG_THREADS, smem, st>>>(tbl, g_tg_trace ? g_tg_trace + 3072 : nullptr);
         CHROMO_CHECK_LAUNCH("wgrad_grouped");
     }

@@ -46,7 +46,7 @@ public:
     void add_weight(const float* dY, int ldy, long long dy_z, const float* X, int ldx, int x_div, long long x_z, float* dW,
                     int lddw, long long dw_z, int tokens, int N, int K, int nz);
     void add_bias(const float* dY, int ld, long long dy_z, float* db, long long db_z, int tokens, int N, int nz);
-    int flush(cudaStream_t st);             // one launch (per 640 items)
+    int flush(cudaStream_t st, int max_ctas = 0);   // one launch (per 640 items); max_ctas > 0 leaves SMs to other streams
     size_t size() const { return items_.size(); }
 private:
     std::vector<WgItem> items_;
