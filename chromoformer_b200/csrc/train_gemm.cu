@@ -178,7 +178,8 @@ __device__ __forceinline__ void stage_operand(uint8_t* dst, const float* __restr
 struct Operands {
     const float* A; long long lda; int a_t, a_div, a_vec, m0, m_lim;
     const float* B; long long ldb; int b_t, b_div, b_vec, n0, n_lim;
-    int Kc, NT;
+    int Kc, NT;                 // contraction range [k_begin, Kc)
+    int k_begin = 0;
     int dbg = 0;                // tuning experiments (CHROMO_TG_DBG): 1 = no loads, 2 = no conversion / stores
 };
 
@@ -187,14 +188,14 @@ struct Operands {
 __device__ __forceinline__ void contract_tile(const Operands& o, uint8_t* smem, uint32_t stage_bytes, uint64_t* bars,
                                               uint32_t tmem, uint32_t& g, uint32_t tiles, int tid, int warp, int lane,
                                               long long* trace = nullptr) {
-    const int chunks = (o.Kc + TG_KCH - 1) / TG_KCH;
+    const int chunks = (o.Kc - o.k_begin + TG_KCH - 1) / TG_KCH;
     const uint32_t idesc = umma_idesc_bf16(128, o.NT) | (o.a_t ? (1u << 15) : 0u) | (o.b_t ? (1u << 16) : 0u);
     for (int ci = 0; ci < chunks; ++ci, ++g) {
         const uint32_t st = g & 1;
         uint8_t* sA = smem + st * stage_bytes;
         uint8_t* sB = sA + TG_A_BYTES;
         if (g >= 2) mbar_wait(&bars[st], ((g >> 1) - 1) & 1);           // the MMAs of chunk g-2 have left this stage
-        const int kc0 = ci * TG_KCH;
+        const int kc0 = o.k_begin + ci * TG_KCH;
         stage_operand(sA, o.A, o.lda, o.a_t, o.a_div, 128, o.m0, o.m_lim, kc0, o.Kc, o.a_vec, warp, lane, o.dbg);
         if (ci == 0 && trace && tid == 0) trace[2] = clock64();
         stage_operand(sB, o.B, o.ldb, o.b_t, o.b_div, o.NT, o.n0, o.n_lim, kc0, o.Kc, o.b_vec, warp, lane, o.dbg);
@@ -287,7 +288,7 @@ __global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a, lon
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
     float* red = reinterpret_cast<float*>(bars + 4);                            // [4][128][2] LayerNorm partial sums
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n0 = blockIdx.x * NT, m0 = blockIdx.y * 128, z = blockIdx.z;
+    const int n0 = blockIdx.x * NT, m0 = blockIdx.y * 128, z = blockIdx.z / a.ksplit, split = blockIdx.z % a.ksplit;
     TG_MARK(0);
     int tmem_cols = 32;
     while (tmem_cols < NT) tmem_cols *= 2;
@@ -309,6 +310,12 @@ __global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a, lon
     o.a_vec = ((reinterpret_cast<uintptr_t>(o.A) & 15) == 0 && (a.lda & 3) == 0) ? 1 : 0;
     o.b_vec = ((reinterpret_cast<uintptr_t>(o.B) & 15) == 0 && (a.ldb & 3) == 0) ? 1 : 0;
     o.Kc = a.Kc; o.NT = NT; o.dbg = dbg;
+    if (a.ksplit > 1) {
+        const int per = ((a.Kc + TG_KCH - 1) / TG_KCH + a.ksplit - 1) / a.ksplit * TG_KCH;
+        o.k_begin = split * per;
+        o.Kc = min(a.Kc, o.k_begin + per);
+                                                        // (the launcher never makes an empty split)
+    }
     uint32_t g = 0;
     contract_tile(o, smem, stage_bytes, bars, tmem, g, 0, tid, warp, lane, trace);
     TG_MARK(6);
@@ -324,7 +331,7 @@ __global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a, lon
     const long long crow = ok ? (long long)(m / a.c_div) * a.c_mul + (m % a.c_div) + a.c_add : 0;
     float* C = a.C + z * a.c_z;
     const float* bias = (a.epi & TC_BIAS) ? a.bias + z * a.bias_z : nullptr;
-    const float* res = (a.epi & TC_RES) ? a.res + z * a.res_z : nullptr;
+    const float* res = ((a.epi & TC_RES) && split == 0) ? a.res + z * a.res_z : nullptr;
     const long long res_off = ok ? (long long)(m / a.res_div) * a.ldres : 0;
     float v[32], t[32];
     if (a.epi & TC_LN) {
@@ -397,7 +404,14 @@ __global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a, lon
                 for (int j = 0; j < 32; ++j)
                     if (!(t[j] > 0.f)) v[j] = 0.f;
             }
-            if (dbg & 8) {
+            if (a.ksplit > 1) {             // partial tile: FP32 atomics into the zeroed output
+                if (ok) {
+                    float* out = C + crow * a.ldc + n0 + c;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (j < ncols) atomicAdd(out + j, v[j]);
+                }
+            } else if (dbg & 8) {
                 if (ok) {
                     float* out = C + crow * a.ldc + n0 + c;
 #pragma unroll
@@ -562,7 +576,29 @@ int tc_gemm_launch(const TcGemm& in, int nz, cudaStream_t st) {
         if (e != cudaSuccess) { set_error("tc_gemm smem attribute: %s", cudaGetErrorString(e)); return CHROMO_ECUDA; }
         configured = gemm_smem(256);
     }
-    dim3 grid(a.N / a.NT, (a.M + 127) / 128, nz);
+    // a long contraction on a handful of row tiles (the data gradient of the fused q|k|v|gate projection, K = 1024; the
+    // position-table products over n = 400 bins): split it over CTAs until every SM has one.  Partial tiles are added
+    // with FP32 atomics: to the output itself when the call accumulates in place, to a zeroed output otherwise.
+    a.ksplit = 1;
+    const int chunks = (a.Kc + TG_KCH - 1) / TG_KCH;
+    if (chunks >= 4 && (a.epi & ~TC_RES) == 0 && a.c_div == 1 && a.c_mul == 1 && a.c_add == 0 && !getenv("CHROMO_TG_NO_KSPLIT")) {
+        const bool in_place = (a.epi & TC_RES) && a.res == a.C && a.ldres == a.ldc && a.res_z == a.c_z && a.res_div == 1;
+        const int ctas = (a.N / a.NT) * ((a.M + 127) / 128) * nz;
+        int ks = 1;
+        while (ks * 2 <= chunks / 2 && ctas * ks * 2 <= 160) ks *= 2;
+        const int per = (chunks + ks - 1) / ks;
+        if (ks > 1 && per * (ks - 1) < chunks && (in_place || a.ldc == a.N)) {
+            if (in_place) {
+                a.epi &= ~TC_RES;
+            } else if (cudaMemset2DAsync(a.C, (size_t)(nz > 1 ? a.c_z : (long long)a.M * a.N) * sizeof(float), 0,
+                                         (size_t)a.M * a.N * sizeof(float), nz, st) != cudaSuccess) {
+                set_error("tc_gemm: cannot zero the split-K output");
+                return CHROMO_ECUDA;
+            }
+            a.ksplit = ks;
+        }
+    }
+    dim3 grid(a.N / a.NT, (a.M + 127) / 128, nz * a.ksplit);
     const char* dbg = getenv("CHROMO_TG_DBG");
     tc_gemm_kernel<<<grid, TG_THREADS, smem, st>>>(a, g_tg_trace ? g_tg_trace + 2048 : nullptr, dbg ? atoi(dbg) : 0);
     CHROMO_CHECK_LAUNCH("tc_gemm");

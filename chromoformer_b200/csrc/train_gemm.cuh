@@ -22,7 +22,8 @@ struct TcGemm {
     const float* gamma; const float* beta; long long ln_z; //          (N == 128)
                                                            //   ReLU
     const float* mask; long long ldmask, mask_z;           //   zero where mask[m, n] <= 0   (ReLU backward)
-    int NT;                                                // filled in by tc_gemm_launch
+    int NT, ksplit;                                        // filled in by tc_gemm_launch (ksplit > 1: contraction split over CTAs,
+                                                           //   partial tiles added to a zeroed C with FP32 atomics)
 };
 TcGemm tc_gemm_args();
 bool tc_gemm_supported(const TcGemm& g);
