@@ -26,6 +26,7 @@ struct LnBwdArgs {
     const float* gamma; float* dgamma; float* dbeta; long long p_z;
 };
 __global__ void __launch_bounds__(256) ln_bwd_kernel(LnBwdArgs a) {
+    CHROMO_PDL_ENTER();
     __shared__ float s_dg[8][128];
     __shared__ float s_db[8][128];
     const int z = blockIdx.y;
@@ -93,6 +94,7 @@ __global__ void __launch_bounds__(256) colsum_kernel(const float* dY, int M, int
 // dst[m, :] (=|+=) src[(m / div) * mul + m % div + add, :]   (128-wide rows)
 __global__ void gather_rows_kernel(float* dst, long long dst_z, const float* src, long long src_z, int M, int div,
                                    int mul, int add) {
+    CHROMO_PDL_ENTER();
     const int z = blockIdx.y;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // float4 index
     if (i >= (long long)M * 32) return;
@@ -103,6 +105,7 @@ __global__ void gather_rows_kernel(float* dst, long long dst_z, const float* src
 
 // dst[b, :] = sum_i src[b * I + i, :]
 __global__ void slot_sum_kernel(float* dst, long long dst_z, const float* src, long long src_z, int B, int I) {
+    CHROMO_PDL_ENTER();
     const int z = blockIdx.y;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * 32) return;
@@ -118,6 +121,7 @@ __global__ void slot_sum_kernel(float* dst, long long dst_z, const float* src, l
 
 // Head fan-out: g_reg[b*S + 0, :] = dz[b, r*D:(r+1)*D], other rows 0          (net.py:377)
 __global__ void head_scatter_kernel(float* g, long long g_z, const float* dz, int B, int S, int D, int n_res) {
+    CHROMO_PDL_ENTER();
     const int z = blockIdx.y;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (long long)B * S * D) return;
@@ -128,6 +132,7 @@ __global__ void head_scatter_kernel(float* g, long long g_z, const float* dz, in
 }
 // g[b*S + 0, :] += dz[b, r*D:(r+1)*D]                                        (residual, net.py:378)
 __global__ void head_residual_kernel(float* g, long long g_z, const float* dz, int B, int S, int D, int n_res) {
+    CHROMO_PDL_ENTER();
     const int z = blockIdx.y;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B * D) return;
@@ -138,6 +143,7 @@ __global__ void head_residual_kernel(float* g, long long g_z, const float* dz, i
 // Backward of reg_attention_kernel.  One warp per (gene, head), lane = channel.
 template <int SMAX>
 __global__ void __launch_bounds__(256) reg_attention_bwd_kernel(RegAttnBwdArgs a) {
+    CHROMO_PDL_ENTER();
     const int warp_in_block = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long gw = (long long)blockIdx.x * (blockDim.x >> 5) + warp_in_block;
     const int z = blockIdx.y;
@@ -213,6 +219,7 @@ __global__ void __launch_bounds__(256) reg_attention_bwd_kernel(RegAttnBwdArgs a
 //   out: dS[j] = gradient wrt the pre-scale score, dU8 = sum_j dS_j x_j,
 //        dQK_init = W_in dU  (the PE part is added by a GEMM)
 __global__ void __launch_bounds__(256) attn_rows_bwd_kernel(AttnRowsBwdArgs a) {
+    CHROMO_PDL_ENTER();
     __shared__ float w_s[128 * 8];
     for (int i = threadIdx.x; i < a.D * a.F; i += blockDim.x) w_s[i] = a.w_in[i];
     __syncthreads();
@@ -375,7 +382,7 @@ int ln_bwd(const Ctx& c, const float* pre, long long pre_z, const float* gin, fl
     LnBwdArgs a{M, pre, pre_z, gin, gout, g_z, gamma, dgamma, dbeta, p_z};
     int blocks = (M + 7) / 8;
     if (blocks > 296) blocks = 296;
-    ln_bwd_kernel<<<dim3(blocks, nz), 256, 0, c.st>>>(a);
+    launch_pdl(ln_bwd_kernel, dim3(dim3(blocks, nz)), dim3(256), 0, c.st, a);
     CHROMO_CHECK_LAUNCH("ln_bwd");
     return CHROMO_OK;
 }
@@ -444,7 +451,7 @@ int sqa_bwd(const Ctx& c, const SqaBwd& s) {
         a.P = s.P; a.dS = s.dS; a.dcbar = s.dCbar; a.x = s.x;
         a.mask = s.mask; a.mask_stride = s.mask_stride; a.mask_row_offset = s.mask_row_offset;
         a.w_in = s.w_in; a.scale = 1.f / sqrtf((float)dh); a.dU8 = s.dU8; a.dqk = s.dQK;
-        attn_rows_bwd_kernel<<<(RH + 7) / 8, 256, 0, c.st>>>(a);
+        launch_pdl(attn_rows_bwd_kernel, dim3((RH + 7) / 8), dim3(256), 0, c.st, a);
         CHROMO_CHECK_LAUNCH("attn_rows_bwd");
     }
     // dW_in += dCbar^T xbar + QK^T dU
@@ -537,7 +544,7 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
         CHROMO_TRY(bwd_weight(c1, ws + o_dh1, dh, 0, ws + w.h_z, NR * D, 1, 0, G + L.fc0w, NR * D, 0, B, dh, NR * D, 1));
         CHROMO_TRY(bwd_bias(c1, ws + o_dh1, dh, 0, G + L.fc0b, 0, B, dh, 1));
         CHROMO_TRY(bwd_data(c1, ws + o_dh1, dh, 0, P + L.fc0w, 0, ws + o_dz, NR * D, 0, B, dh, NR * D, DataEpi(), 1));
-        head_scatter_kernel<<<dim3((unsigned)(((long long)T * D + 255) / 256), NR), 256, 0, st>>>(
+        launch_pdl(head_scatter_kernel, dim3(dim3((unsigned)(((long long)T * D + 255) / 256), NR)), dim3(256), 0, st, 
             ws + o_tR0, GS, ws + o_dz, B, S, D, NR);
         CHROMO_CHECK_LAUNCH("head_scatter");
     }
@@ -568,8 +575,8 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
             for (int r = 0; r < NR; ++r) a.imask[r] = in->imask[r];
             a.dgamma_f = G + ra.gamma_f; a.dgamma_z = L.reg_stride;
             dim3 grid((unsigned)(((long long)B * Hr + 7) / 8), NR);
-            if (S <= 9) reg_attention_bwd_kernel<9><<<grid, 256, 0, st>>>(a);
-            else reg_attention_bwd_kernel<17><<<grid, 256, 0, st>>>(a);
+            if (S <= 9) launch_pdl(reg_attention_bwd_kernel<9>, dim3(grid), dim3(256), 0, st, a);
+            else launch_pdl(reg_attention_bwd_kernel<17>, dim3(grid), dim3(256), 0, st, a);
             CHROMO_CHECK_LAUNCH("reg_attention_bwd");
         }
         CHROMO_TRY(bwd_weight(cx, dProj, 4 * dmr, GS, xin, D, 1, RS, G + ra.att, D, L.reg_stride, T, 4 * dmr, D, NR));
@@ -585,13 +592,13 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
         if (wst != st) CHROMO_TRY(queue.flush(wst, 96));
     }
     float* gR = gcur;                   // dX_in (without the residual of net.py:378)
-    head_residual_kernel<<<dim3((B * D + 255) / 256, NR), 256, 0, st>>>(gR, GS, ws + o_dz, B, S, D, NR);
+    launch_pdl(head_residual_kernel, dim3(dim3((B * D + 255) / 256, NR)), dim3(256), 0, st, gR, GS, ws + o_dz, B, S, D, NR);
     CHROMO_CHECK_LAUNCH("head_residual");
 
     // ---- Pairwise Interaction transformer ---------------------------------------
     float* pcur = ws + o_tP0;
     float* pnext = ws + o_tP1;
-    gather_rows_kernel<<<dim3((unsigned)(((long long)R * 32 + 255) / 256), NR), 256, 0, st>>>(pcur, GS, gR, GS, R, I, S, 1);
+    launch_pdl(gather_rows_kernel, dim3(dim3((unsigned)(((long long)R * 32 + 255) / 256), NR)), dim3(256), 0, st, pcur, GS, gR, GS, R, I, S, 1);
     CHROMO_CHECK_LAUNCH("gather_pairwise");
     for (int l = c->pw_layers - 1; l >= 0; --l) {
         const AttnOff& pa = L.pw[0].att[l];
@@ -632,7 +639,7 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
         CHROMO_TRY(bwd_data(cx, ws + o_dQp[l], dmp, GS, P + pa.p_att, L.pw_stride, pcur, D, GS, R, dmp, D, resid, NR));
     }
     // pcur = dP_0 per (gene, slot); P_0 = PP[gene] for every slot (net.py:114-118)
-    slot_sum_kernel<<<dim3((unsigned)(((long long)B * 32 + 255) / 256), NR), 256, 0, st>>>(ws + o_dPP, GS, pcur, GS, B, I);
+    launch_pdl(slot_sum_kernel, dim3(dim3((unsigned)(((long long)B * 32 + 255) / 256), NR)), dim3(256), 0, st, ws + o_dPP, GS, pcur, GS, B, I);
     CHROMO_CHECK_LAUNCH("slot_sum");
     CHROMO_TRY(bwd_weight(cx, ws + o_dPP, D, GS, ws + w.r_xin, S * D, 1, RS, G + L.pw[0].lin_proj_p, D, L.pw_stride, B, D, D, NR));
     {   // dX_in[b, 0, :] += dPP W_lpp
@@ -653,7 +660,7 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
     // ---- Embedding transformer ----------------------------------------------------
     float* ecur = ws + o_tE0;
     float* enext = ws + o_tE1;
-    gather_rows_kernel<<<dim3((unsigned)(((long long)B * 32 + 255) / 256), NR), 256, 0, st>>>(ecur, GS, gR, GS, B, 1, S, 0);
+    launch_pdl(gather_rows_kernel, dim3(dim3((unsigned)(((long long)B * 32 + 255) / 256), NR)), dim3(256), 0, st, ecur, GS, gR, GS, B, 1, S, 0);
     CHROMO_CHECK_LAUNCH("gather_embed");
     {
         const AttnOff& ea = L.embed[0].att[0];

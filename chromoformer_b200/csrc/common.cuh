@@ -28,6 +28,28 @@ void count_launch();
         if (rc__ != CHROMO_OK) return rc__;                                    \
     } while (0)
 
+// --------------------------------------------------- programmatic dependent launch --
+// The training step is a chain of ~200 small dependent kernels.  A kernel launched through launch_pdl may be scheduled
+// while the kernel in front of it is still running (its launch latency, and for the staged GEMM its TMEM / barrier set-up
+// and the staging of the parameter operand, disappear behind that kernel's tail); CHROMO_PDL_ENTER() at the top of the
+// kernel blocks until everything in front has completed and its memory is visible, then lets the NEXT kernel start.
+#define CHROMO_PDL_ENTER()                                                     \
+    do {                                                                       \
+        asm volatile("griddepcontrol.wait;" ::: "memory");                     \
+        asm volatile("griddepcontrol.launch_dependents;");                     \
+    } while (0)
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+static inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);        // (errors surface in CHROMO_CHECK_LAUNCH)
+}
+
 // --------------------------------------------------- parameter layout -------
 // Offsets (in floats) into the flat parameter / gradient buffers.
 struct AttnOff {      // MultiHeadAttention (modules.py:8-26) / PairwiseMultiHeadAttention (modules.py:127-148)

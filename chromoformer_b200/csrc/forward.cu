@@ -30,6 +30,7 @@ namespace chromo {
 
 // Hc[b,:] = W_lp x_p[b,c,:] + PE[c,:]        (net.py:42,47-53 at the centre bin)
 __global__ void centre_embed_kernel(CentreEmbedArgs a) {
+    CHROMO_PDL_ENTER();
     const int r = blockIdx.y;
     const int n = a.n[r], c = n / 2, D = a.D, F = a.F;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -47,6 +48,7 @@ __global__ void centre_embed_kernel(CentreEmbedArgs a) {
 //   xbar = sum_j p_j x_j;   cbar_init = W_in xbar   (the PE part is added by a GEMM)
 // modules.py:58-61,71-77 / 170-189 restricted to the centre query.
 __global__ void __launch_bounds__(256) attn_rows_kernel(AttnRowsArgs a) {
+    CHROMO_PDL_ENTER();
     // W_in [D, F] is read by every row with a stride-F pattern: stage it once per block (coalesced)
     __shared__ float w_s[128 * 8];
     for (int i = threadIdx.x; i < a.D * a.F; i += blockDim.x) w_s[i] = a.w_in[i];
@@ -139,6 +141,7 @@ __global__ void __launch_bounds__(256) attn_rows_kernel(AttnRowsArgs a) {
 // whole single-query attention core of a region is this one kernel.
 template <int NJ, int H, int F, bool FUSE_PE>
 __global__ void __launch_bounds__(128, 3) attn_rows_reg_kernel(AttnRowsArgs a) {
+    CHROMO_PDL_ENTER();
     extern __shared__ __align__(16) float xs_all[];
     __shared__ float w_s[128 * F];
     __shared__ float pe_s[FUSE_PE ? 32 * 129 : 1];
@@ -333,6 +336,7 @@ template <> struct ProjLoad<__nv_bfloat16> {
 
 template <int SMAX, typename PT>
 __global__ void __launch_bounds__(128) reg_attention_kernel(RegAttnArgs a) {
+    CHROMO_PDL_ENTER();
     const int S = a.S, H = a.H, dm = 32 * H;
     const int gpw = 32 / S;                                   // (gene, head) groups per warp
     const int lane = threadIdx.x & 31;
@@ -413,6 +417,7 @@ __global__ void __launch_bounds__(128) reg_attention_kernel(RegAttnArgs a) {
 
 // z[b, r*D + d] = X_out_r[b, 0, d] + X_in_r[b, 0, d]           (net.py:377-378)
 __global__ void head_gather_kernel(HeadGatherArgs a) {
+    CHROMO_PDL_ENTER();
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
     const int W = a.n_res * a.D;
     if (idx >= a.B * W) return;
@@ -427,11 +432,11 @@ int launch_reg_attention(const RegAttnArgs& a, int nz, cudaStream_t st) {
     const long long warps = ((long long)a.B * a.H + gpw - 1) / gpw;
     dim3 grid((unsigned)((warps + wpb - 1) / wpb), nz);
     if (a.proj_bf16) {
-        if (a.S <= 9) reg_attention_kernel<9, __nv_bfloat16><<<grid, wpb * 32, 0, st>>>(a);
-        else reg_attention_kernel<17, __nv_bfloat16><<<grid, wpb * 32, 0, st>>>(a);
+        if (a.S <= 9) launch_pdl(reg_attention_kernel<9, __nv_bfloat16>, dim3(grid), dim3(wpb * 32), 0, st, a);
+        else launch_pdl(reg_attention_kernel<17, __nv_bfloat16>, dim3(grid), dim3(wpb * 32), 0, st, a);
     } else {
-        if (a.S <= 9) reg_attention_kernel<9, float><<<grid, wpb * 32, 0, st>>>(a);
-        else reg_attention_kernel<17, float><<<grid, wpb * 32, 0, st>>>(a);
+        if (a.S <= 9) launch_pdl(reg_attention_kernel<9, float>, dim3(grid), dim3(wpb * 32), 0, st, a);
+        else launch_pdl(reg_attention_kernel<17, float>, dim3(grid), dim3(wpb * 32), 0, st, a);
     }
     CHROMO_CHECK_LAUNCH("reg_attention");
     return CHROMO_OK;
@@ -452,14 +457,14 @@ int launch_attn_rows(const AttnRowsArgs& a, cudaStream_t st) {
                                  (int)(4 * 13 * 32 * 7 * sizeof(float)));
             configured = true;
         }
-        if (a.n <= 32 && a.pe) attn_rows_reg_kernel<1, 2, 7, true><<<blocks, 128, 4 * 1 * 32 * 7 * sizeof(float), st>>>(a);
-        else if (a.n <= 32) attn_rows_reg_kernel<1, 2, 7, false><<<blocks, 128, 4 * 1 * 32 * 7 * sizeof(float), st>>>(a);
-        else if (a.n <= 96) attn_rows_reg_kernel<3, 2, 7, false><<<blocks, 128, 4 * 3 * 32 * 7 * sizeof(float), st>>>(a);
-        else attn_rows_reg_kernel<13, 2, 7, false><<<blocks, 128, 4 * 13 * 32 * 7 * sizeof(float), st>>>(a);
+        if (a.n <= 32 && a.pe) launch_pdl(attn_rows_reg_kernel<1, 2, 7, true>, dim3(blocks), dim3(128), 4 * 1 * 32 * 7 * sizeof(float), st, a);
+        else if (a.n <= 32) launch_pdl(attn_rows_reg_kernel<1, 2, 7, false>, dim3(blocks), dim3(128), 4 * 1 * 32 * 7 * sizeof(float), st, a);
+        else if (a.n <= 96) launch_pdl(attn_rows_reg_kernel<3, 2, 7, false>, dim3(blocks), dim3(128), 4 * 3 * 32 * 7 * sizeof(float), st, a);
+        else launch_pdl(attn_rows_reg_kernel<13, 2, 7, false>, dim3(blocks), dim3(128), 4 * 13 * 32 * 7 * sizeof(float), st, a);
         CHROMO_CHECK_LAUNCH("attn_rows_reg");
         return CHROMO_OK;
     }
-    attn_rows_kernel<<<(a.rows + wpb - 1) / wpb, wpb * 32, 0, st>>>(a);
+    launch_pdl(attn_rows_kernel, dim3((a.rows + wpb - 1) / wpb), dim3(wpb * 32), 0, st, a);
     CHROMO_CHECK_LAUNCH("attn_rows");
     return CHROMO_OK;
 }
@@ -678,7 +683,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         a.w = P + L.embed[0].lin_proj; a.w_stride = L.embed_stride;
         a.out = ws + w.e_hc; a.out_stride = RS;
         dim3 grid((B * D + 255) / 256, NR);
-        centre_embed_kernel<<<grid, 256, 0, st>>>(a);
+        launch_pdl(centre_embed_kernel, dim3(grid), dim3(256), 0, st, a);
         CHROMO_CHECK_LAUNCH("centre_embed");
     }
     const AttnOff& ea = L.embed[0].att[0];
@@ -1036,7 +1041,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         a.B = B; a.S = S; a.D = D; a.n_res = NR;
         a.xout = ws + w.r_out + (long long)w.rslot(c->reg_layers - 1) * w.r_slot;
         a.xin = ws + w.r_xin; a.zstride = RS; a.z = ws + w.h_z;
-        head_gather_kernel<<<(B * NR * D + 255) / 256, 256, 0, st>>>(a);
+        launch_pdl(head_gather_kernel, dim3((B * NR * D + 255) / 256), dim3(256), 0, st, a);
         CHROMO_CHECK_LAUNCH("head_gather");
     }
     {

@@ -109,6 +109,7 @@ __device__ __forceinline__ void gemm_load_tile(float (*S)[BD + GEMM_PAD], const 
 // four complete rows).
 template <int BM, int BN, bool A_KC, bool B_KC, bool LN>
 __global__ void __launch_bounds__(GEMM_THREADS) gemm_simt_kernel(const GemmArgs g) {
+    CHROMO_PDL_ENTER();
     static_assert((BM / 4) * (BN / 4) == GEMM_THREADS, "tile/thread mismatch");
     __shared__ __align__(16) float As[GEMM_BK][BM + GEMM_PAD];
     __shared__ __align__(16) float Bs[GEMM_BK][BN + GEMM_PAD];
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(GEMM_THREADS) gemm_simt_kernel(const GemmArgs 
 template <bool A_KC, bool B_KC>
 static inline int gemm_launch_plain(const GemmArgs& g, int nz, cudaStream_t st) {
     dim3 grid((g.N + 63) / 64, (g.M + 63) / 64, nz * g.ksplit);
-    gemm_simt_kernel<64, 64, A_KC, B_KC, false><<<grid, GEMM_THREADS, 0, st>>>(g);
+    launch_pdl(gemm_simt_kernel<64, 64, A_KC, B_KC, false>, dim3(grid), dim3(GEMM_THREADS), 0, st, g);
     CHROMO_CHECK_LAUNCH("gemm_simt");
     return CHROMO_OK;
 }
@@ -235,7 +236,7 @@ static inline int gemm_launch(const GemmArgs& g, bool a_kc, bool b_kc, int nz, c
             return CHROMO_EINVAL;
         }
         dim3 grid(1, (g.M + 31) / 32, nz);
-        gemm_simt_kernel<32, 128, true, true, true><<<grid, GEMM_THREADS, 0, st>>>(g);
+        launch_pdl(gemm_simt_kernel<32, 128, true, true, true>, dim3(grid), dim3(GEMM_THREADS), 0, st, g);
         CHROMO_CHECK_LAUNCH("gemm_simt_ln");
         return CHROMO_OK;
     }

@@ -309,6 +309,11 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
     return w;
 }
 
+bool pdl_enabled() {
+    static const bool on = getenv("CHROMO_NO_PDL") == nullptr;
+    return on;
+}
+
 namespace {
 struct SideStreams {
     int device = -1;

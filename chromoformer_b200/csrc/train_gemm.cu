@@ -180,6 +180,7 @@ struct Operands {
     const float* B; long long ldb; int b_t, b_div, b_vec, n0, n_lim;
     int Kc, NT;                 // contraction range [k_begin, Kc)
     int k_begin = 0;
+    int pdl = 0;                // launched as a programmatic dependent: griddepcontrol.wait before the first A access
     int dbg = 0;                // tuning experiments (CHROMO_TG_DBG): 1 = no loads, 2 = no conversion / stores
 };
 
@@ -196,9 +197,12 @@ __device__ __forceinline__ void contract_tile(const Operands& o, uint8_t* smem, 
         uint8_t* sB = sA + TG_A_BYTES;
         if (g >= 2) mbar_wait(&bars[st], ((g >> 1) - 1) & 1);           // the MMAs of chunk g-2 have left this stage
         const int kc0 = o.k_begin + ci * TG_KCH;
-        stage_operand(sA, o.A, o.lda, o.a_t, o.a_div, 128, o.m0, o.m_lim, kc0, o.Kc, o.a_vec, warp, lane, o.dbg);
-        if (ci == 0 && trace && tid == 0) trace[2] = clock64();
+        // B first: in tc_gemm_kernel it is a parameter / position table, independent of the kernel in front, so its staging
+        // (like everything above) runs under that kernel's tail; A is the first dependent access (programmatic dependent launch)
         stage_operand(sB, o.B, o.ldb, o.b_t, o.b_div, o.NT, o.n0, o.n_lim, kc0, o.Kc, o.b_vec, warp, lane, o.dbg);
+        if (ci == 0 && trace && tid == 0) trace[2] = clock64();
+        if (ci == 0 && o.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
+        stage_operand(sA, o.A, o.lda, o.a_t, o.a_div, 128, o.m0, o.m_lim, kc0, o.Kc, o.a_vec, warp, lane, o.dbg);
         if (ci == 0 && trace && tid == 0) trace[3] = clock64();
         fence_async_smem();
         __syncthreads();
@@ -281,6 +285,7 @@ __device__ __forceinline__ void add_tile_f32(float* stage, const float* v, float
 
 __global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a, long long* trace_buf, int dbg) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    asm volatile("griddepcontrol.launch_dependents;");     // the next kernel of the chain may start its own prologue
     long long* trace = (trace_buf && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? trace_buf : nullptr;
     const int NT = a.NT;
     const uint32_t stage_bytes = TG_A_BYTES + (uint32_t)NT * TG_KCH * 2;
@@ -309,7 +314,7 @@ __global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a, lon
     o.B = a.B + z * a.b_z; o.ldb = a.ldb; o.b_t = a.b_t; o.b_div = a.b_div; o.n0 = n0; o.n_lim = a.N;
     o.a_vec = ((reinterpret_cast<uintptr_t>(o.A) & 15) == 0 && (a.lda & 3) == 0) ? 1 : 0;
     o.b_vec = ((reinterpret_cast<uintptr_t>(o.B) & 15) == 0 && (a.ldb & 3) == 0) ? 1 : 0;
-    o.Kc = a.Kc; o.NT = NT; o.dbg = dbg;
+    o.Kc = a.Kc; o.NT = NT; o.dbg = dbg; o.pdl = 1;
     if (a.ksplit > 1) {
         const int per = ((a.Kc + TG_KCH - 1) / TG_KCH + a.ksplit - 1) / a.ksplit * TG_KCH;
         o.k_begin = split * per;
@@ -600,7 +605,19 @@ int tc_gemm_launch(const TcGemm& in, int nz, cudaStream_t st) {
     }
     dim3 grid(a.N / a.NT, (a.M + 127) / 128, nz * a.ksplit);
     const char* dbg = getenv("CHROMO_TG_DBG");
-    tc_gemm_kernel<<<grid, TG_THREADS, smem, st>>>(a, g_tg_trace ? g_tg_trace + 2048 : nullptr, dbg ? atoi(dbg) : 0);
+    {
+        static const bool no_pdl = getenv("CHROMO_NO_PDL") != nullptr;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid; cfg.blockDim = dim3(TG_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = no_pdl ? 0 : 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        long long* tb = g_tg_trace ? g_tg_trace + 2048 : nullptr;
+        const int dbgv = dbg ? atoi(dbg) : 0;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel, a, tb, dbgv);
+        if (e != cudaSuccess) { set_error("tc_gemm launch: %s", cudaGetErrorString(e)); return CHROMO_ECUDA; }
+    }
     CHROMO_CHECK_LAUNCH("tc_gemm");
     return CHROMO_OK;
 }

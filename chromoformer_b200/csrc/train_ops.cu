@@ -6,6 +6,7 @@ namespace chromo {
 // MSELoss, mean reduction: loss = mean((y - t)^2); dy = 2 (y - t) / count * grad_scale.
 __global__ void mse_loss_kernel(const float* __restrict__ y, const float* __restrict__ t, int count,
                                 float grad_scale, float* loss, float* dy) {
+    CHROMO_PDL_ENTER();
     __shared__ float red[32];
     float s = 0.f;
     const float inv = 1.f / (float)count;
@@ -27,6 +28,7 @@ __global__ void mse_loss_kernel(const float* __restrict__ y, const float* __rest
 // CrossEntropyLoss, mean reduction over the batch: log-softmax + NLL.
 __global__ void ce_loss_kernel(const float* __restrict__ y, const int64_t* __restrict__ lab, int batch,
                                int C, float grad_scale, float* loss, float* dy) {
+    CHROMO_PDL_ENTER();
     __shared__ float red[32];
     float s = 0.f;
     const float inv = 1.f / (float)batch;
@@ -92,7 +94,7 @@ extern "C" {
 int chromo_mse_loss(const float* logits, const float* target, int32_t count, float grad_scale, float* loss,
                     float* dlogits, void* stream) {
     if (!logits || !target || !loss || !dlogits || count < 1) { set_error("mse_loss: bad argument"); return CHROMO_EINVAL; }
-    mse_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, target, count, grad_scale, loss, dlogits);
+    launch_pdl(mse_loss_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, logits, target, count, grad_scale, loss, dlogits);
     CHROMO_CHECK_LAUNCH("mse_loss");
     return CHROMO_OK;
 }
@@ -100,7 +102,7 @@ int chromo_mse_loss(const float* logits, const float* target, int32_t count, flo
 int chromo_ce_loss(const float* logits, const int64_t* labels, int32_t batch, int32_t n_classes,
                    float grad_scale, float* loss, float* dlogits, void* stream) {
     if (!logits || !labels || !loss || !dlogits || batch < 1 || n_classes < 2) { set_error("ce_loss: bad argument"); return CHROMO_EINVAL; }
-    ce_loss_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(logits, labels, batch, n_classes, grad_scale, loss, dlogits);
+    launch_pdl(ce_loss_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, logits, labels, batch, n_classes, grad_scale, loss, dlogits);
     CHROMO_CHECK_LAUNCH("ce_loss");
     return CHROMO_OK;
 }
