@@ -214,6 +214,124 @@ __global__ void __launch_bounds__(256) reg_attention_bwd_kernel(RegAttnBwdArgs a
     if (lane == 0) atomicAdd(a.dgamma_f + z * a.dgamma_z + h, dgam);
 }
 
+// The same backward with one CTA per gene (counterpart of reg_attention_gene_kernel): the gene's rows of q | k | v | gate
+// staged once in shared memory; four lanes (eight channels each) per (head, query) for dgate, dq and the score
+// gradients - two shuffles per key instead of a 32-lane reduction - then, after a barrier, per (head, key) for dk and dv
+// from the staged dS / P / dA.  (The kernel above spends its time in 81 warp-wide reductions per (gene, head).)
+constexpr int RAB_PAD = 4;
+template <int SMAX>
+__global__ void __launch_bounds__(SMAX * 32) reg_attention_gene_bwd_kernel(RegAttnBwdArgs a) {
+    CHROMO_PDL_ENTER();
+    extern __shared__ __align__(16) float rab_sm[];
+    const int S = a.S, H = a.H, dm = 32 * H, ld = 4 * dm + RAB_PAD;
+    float* sm_da = rab_sm + S * ld;              // [H*S][32]   dA = dO * sigmoid(gate)
+    float* sm_ds = sm_da + S * dm;               // [H*S][S]    gradient wrt the pre-softmax score (before the 1/sqrt(32))
+    float* sm_p = sm_ds + H * S * S;             // [H*S][S]    probabilities
+    float* sm_gam = sm_p + H * S * S;            // [H*S]       per-query terms of d gamma_f
+    const int b = blockIdx.x, z = blockIdx.y, tid = threadIdx.x;
+    const float* proj = a.proj + z * a.proj_z + (long long)b * S * 4 * dm;
+    for (int v = tid; v < S * dm; v += blockDim.x) {
+        const int r = v / dm, c = v % dm;
+        *reinterpret_cast<float4*>(rab_sm + r * ld + 4 * c) = __ldg(reinterpret_cast<const float4*>(proj + (long long)r * 4 * dm) + c);
+    }
+    __syncthreads();
+    const int item = tid >> 2, sub = tid & 3;    // blockDim.x == H * S * 4 exactly (H == 8)
+    const int h = item / S, i = item % S;        // phase 1: (head, query)
+    const int co = h * 32 + sub * 8;
+    const float scale = 0.17677669529663687f;
+    float* dproj = a.dproj + z * a.dproj_z + (long long)b * S * 4 * dm;
+    {
+        const float* prob = a.prob + z * a.prob_z + (((long long)b * H + h) * S + i) * S;
+        const float* freq = a.freq + ((long long)b * S + i) * S;
+        const uint8_t* mask = a.imask[z] + ((long long)b * S + i) * S;
+        const float* dout = a.dout + z * a.dout_z + ((long long)b * S + i) * dm + co;
+        const float4 d0 = __ldg(reinterpret_cast<const float4*>(dout)), d1 = __ldg(reinterpret_cast<const float4*>(dout) + 1);
+        const float d_o[8] = {d0.x, d0.y, d0.z, d0.w, d1.x, d1.y, d1.z, d1.w};
+        float p[SMAX], dp[SMAX];
+        float av[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int j = 0; j < SMAX; ++j) {
+            p[j] = j < S ? __ldg(prob + j) : 0.f;
+            if (j < S) {
+                const float* vj = rab_sm + j * ld + 2 * dm + co;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) av[e] = fmaf(p[j], vj[e], av[e]);
+            }
+        }
+        float da[8], dg[8];
+        {
+            const float* gt = rab_sm + i * ld + 3 * dm + co;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const float sg = 1.f / (1.f + expf(-gt[e]));
+                da[e] = d_o[e] * sg;
+                dg[e] = d_o[e] * av[e] * sg * (1.f - sg);
+            }
+        }
+        float* drow = dproj + (long long)i * 4 * dm;
+        *reinterpret_cast<float4*>(drow + 3 * dm + co) = make_float4(dg[0], dg[1], dg[2], dg[3]);
+        *reinterpret_cast<float4*>(drow + 3 * dm + co + 4) = make_float4(dg[4], dg[5], dg[6], dg[7]);
+        *reinterpret_cast<float4*>(sm_da + item * 32 + sub * 8) = make_float4(da[0], da[1], da[2], da[3]);
+        *reinterpret_cast<float4*>(sm_da + item * 32 + sub * 8 + 4) = make_float4(da[4], da[5], da[6], da[7]);
+#pragma unroll
+        for (int j = 0; j < SMAX; ++j) {
+            dp[j] = 0.f;
+            if (j < S) {
+                const float* vj = rab_sm + j * ld + 2 * dm + co;
+                float t = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) t = fmaf(da[e], vj[e], t);
+                dp[j] = t;
+            }
+        }
+        float dot = 0.f;
+#pragma unroll
+        for (int j = 0; j < SMAX; ++j) {
+            dp[j] += __shfl_xor_sync(0xffffffffu, dp[j], 1);
+            dp[j] += __shfl_xor_sync(0xffffffffu, dp[j], 2);
+            dot = fmaf(p[j], dp[j], dot);
+        }
+        float dq[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        float dgam = 0.f;
+#pragma unroll
+        for (int j = 0; j < SMAX; ++j) {
+            if (j < S) {
+                const float ds = mask[j] ? 0.f : p[j] * (dp[j] - dot);
+                dgam = fmaf(ds, freq[j], dgam);
+                const float* kj = rab_sm + j * ld + dm + co;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) dq[e] = fmaf(ds, kj[e], dq[e]);
+                if (sub == (j & 3)) { sm_ds[item * S + j] = ds; sm_p[item * S + j] = p[j]; }
+            }
+        }
+        *reinterpret_cast<float4*>(drow + co) = make_float4(dq[0] * scale, dq[1] * scale, dq[2] * scale, dq[3] * scale);
+        *reinterpret_cast<float4*>(drow + co + 4) = make_float4(dq[4] * scale, dq[5] * scale, dq[6] * scale, dq[7] * scale);
+        if (sub == 0) sm_gam[item] = dgam;
+    }
+    __syncthreads();
+    if (tid < H) {      // one atomic per (gene, head), summed in a fixed order
+        float t = 0.f;
+        for (int q = 0; q < S; ++q) t += sm_gam[tid * S + q];
+        atomicAdd(a.dgamma_f + z * a.dgamma_z + tid, t);
+    }
+    {   // phase 2: (head, key j = i): dk[j] = scale sum_i dS[i, j] q[i],  dv[j] = sum_i P[i, j] dA[i]
+        const int j = i;
+        float dk[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dv[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int q = 0; q < S; ++q) {
+            const float ds = sm_ds[(h * S + q) * S + j], pp = sm_p[(h * S + q) * S + j];
+            const float* qq = rab_sm + q * ld + co;
+            const float* dd = sm_da + (h * S + q) * 32 + sub * 8;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { dk[e] = fmaf(ds, qq[e], dk[e]); dv[e] = fmaf(pp, dd[e], dv[e]); }
+        }
+        float* drow = dproj + (long long)j * 4 * dm;
+        *reinterpret_cast<float4*>(drow + dm + co) = make_float4(dk[0] * scale, dk[1] * scale, dk[2] * scale, dk[3] * scale);
+        *reinterpret_cast<float4*>(drow + dm + co + 4) = make_float4(dk[4] * scale, dk[5] * scale, dk[6] * scale, dk[7] * scale);
+        *reinterpret_cast<float4*>(drow + 2 * dm + co) = make_float4(dv[0], dv[1], dv[2], dv[3]);
+        *reinterpret_cast<float4*>(drow + 2 * dm + co + 4) = make_float4(dv[4], dv[5], dv[6], dv[7]);
+    }
+}
+
 // Backward of attn_rows_kernel; one warp per (region, head).
 //   in : dS[j] = dCbar . PE_j (from a GEMM), P, dCbar, x, mask
 //   out: dS[j] = gradient wrt the pre-scale score, dU8 = sum_j dS_j x_j,
@@ -575,7 +693,19 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
             for (int r = 0; r < NR; ++r) a.imask[r] = in->imask[r];
             a.dgamma_f = G + ra.gamma_f; a.dgamma_z = L.reg_stride;
             dim3 grid((unsigned)(((long long)B * Hr + 7) / 8), NR);
-            if (S <= 9) launch_pdl(reg_attention_bwd_kernel<9>, dim3(grid), dim3(256), 0, st, a);
+            static const bool per_warp = getenv("CHROMO_REG_ATTN_PER_THREAD") != nullptr;
+            if (Hr == 8 && S <= 17 && !per_warp) {       // one CTA per gene, rows staged in shared memory
+                const size_t smem = ((size_t)S * (4 * dmr + RAB_PAD) + (size_t)S * dmr + 2 * (size_t)Hr * S * S + Hr * S) * sizeof(float);
+                static bool configured = false;
+                if (!configured) {
+                    const int mx = (17 * (4 * 256 + RAB_PAD) + 17 * 256 + 2 * 8 * 17 * 17 + 8 * 17) * (int)sizeof(float);
+                    cudaFuncSetAttribute(reg_attention_gene_bwd_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+                    cudaFuncSetAttribute(reg_attention_gene_bwd_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, mx);
+                    configured = true;
+                }
+                if (S <= 9) launch_pdl(reg_attention_gene_bwd_kernel<9>, dim3(B, NR), dim3(Hr * S * 4), smem, st, a);
+                else launch_pdl(reg_attention_gene_bwd_kernel<17>, dim3(B, NR), dim3(Hr * S * 4), smem, st, a);
+            } else if (S <= 9) launch_pdl(reg_attention_bwd_kernel<9>, dim3(grid), dim3(256), 0, st, a);
             else launch_pdl(reg_attention_bwd_kernel<17>, dim3(grid), dim3(256), 0, st, a);
             CHROMO_CHECK_LAUNCH("reg_attention_bwd");
         }

@@ -415,6 +415,86 @@ __global__ void __launch_bounds__(128) reg_attention_kernel(RegAttnArgs a) {
     }
 }
 
+// The same attention with one CTA per gene (FP32 projections: the strict path and the training step).  The gene's S rows of
+// q | k | v | gate (S x 4 KB) are staged once in shared memory, coalesced; a (head, query) pair is served by four lanes,
+// eight channels each: partial dot products against the S keys meet by two shuffles, every lane then holds the whole
+// softmax row and accumulates its eight output channels.  (The kernel above reads every key / value row S times from
+// L1 with four warps per SM in flight: 23 us at batch 64 against 4 us here.)
+constexpr int RA_PAD = 4;          // floats between staged rows: the S query rows of a head fall on different banks
+template <int SMAX>
+__global__ void __launch_bounds__(SMAX * 32) reg_attention_gene_kernel(RegAttnArgs a) {
+    CHROMO_PDL_ENTER();
+    extern __shared__ __align__(16) float ra_sm[];
+    const int S = a.S, H = a.H, dm = 32 * H, ld = 4 * dm + RA_PAD;
+    const int b = blockIdx.x, z = blockIdx.y, tid = threadIdx.x;
+    const float* proj = reinterpret_cast<const float*>(a.proj) + z * a.proj_zstride + (long long)b * S * 4 * dm;
+    for (int v = tid; v < S * dm; v += blockDim.x) {            // float4 units, rows of 4*dm floats
+        const int r = v / dm, c = v % dm;
+        *reinterpret_cast<float4*>(ra_sm + r * ld + 4 * c) = __ldg(reinterpret_cast<const float4*>(proj + (long long)r * 4 * dm) + c);
+    }
+    __syncthreads();
+    const int item = tid >> 2, sub = tid & 3;
+    if (item >= H * S) return;
+    const int h = item / S, i = item % S;
+    const int co = h * 32 + sub * 8;                             // this lane's eight channels
+    float q[8], s[SMAX];
+    {
+        const float4 x = *reinterpret_cast<const float4*>(ra_sm + i * ld + co), y = *reinterpret_cast<const float4*>(ra_sm + i * ld + co + 4);
+        q[0] = x.x; q[1] = x.y; q[2] = x.z; q[3] = x.w; q[4] = y.x; q[5] = y.y; q[6] = y.z; q[7] = y.w;
+    }
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+        s[j] = 0.f;
+        if (j < S) {
+            const float4 x = *reinterpret_cast<const float4*>(ra_sm + j * ld + dm + co), y = *reinterpret_cast<const float4*>(ra_sm + j * ld + dm + co + 4);
+            s[j] = (q[0] * x.x + q[1] * x.y) + (q[2] * x.z + q[3] * x.w) + (q[4] * y.x + q[5] * y.y) + (q[6] * y.z + q[7] * y.w);
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+        s[j] += __shfl_xor_sync(0xffffffffu, s[j], 1);
+        s[j] += __shfl_xor_sync(0xffffffffu, s[j], 2);
+    }
+    const float gamma = a.gamma_f[z * a.gamma_zstride + h];
+    const float* freq = a.freq + ((long long)b * S + i) * S;
+    const uint8_t* mask = a.imask[z] + ((long long)b * S + i) * S;
+    const float scale = 0.17677669529663687f;   // 1/sqrt(32)
+    float mx = -INFINITY;
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+        if (j < S) {
+            float t = s[j] * scale + gamma * freq[j];
+            if (mask[j]) t = -1e9f;
+            s[j] = t;
+            mx = fmaxf(mx, t);
+        }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j)
+        if (j < S) { s[j] = expf(s[j] - mx); sum += s[j]; }
+    const float inv = 1.f / sum;
+    float o[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float* prob = a.prob ? a.prob + z * a.prob_zstride + (((long long)b * H + h) * S + i) * S : nullptr;
+#pragma unroll
+    for (int j = 0; j < SMAX; ++j) {
+        if (j < S) {
+            const float p = s[j] * inv;
+            if (prob && sub == (j & 3)) prob[j] = p;
+            const float4 x = *reinterpret_cast<const float4*>(ra_sm + j * ld + 2 * dm + co), y = *reinterpret_cast<const float4*>(ra_sm + j * ld + 2 * dm + co + 4);
+            o[0] = fmaf(p, x.x, o[0]); o[1] = fmaf(p, x.y, o[1]); o[2] = fmaf(p, x.z, o[2]); o[3] = fmaf(p, x.w, o[3]);
+            o[4] = fmaf(p, y.x, o[4]); o[5] = fmaf(p, y.y, o[5]); o[6] = fmaf(p, y.z, o[6]); o[7] = fmaf(p, y.w, o[7]);
+        }
+    }
+    const float4 gx = *reinterpret_cast<const float4*>(ra_sm + i * ld + 3 * dm + co), gy = *reinterpret_cast<const float4*>(ra_sm + i * ld + 3 * dm + co + 4);
+    const float g[8] = {gx.x, gx.y, gx.z, gx.w, gy.x, gy.y, gy.z, gy.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = o[e] / (1.f + expf(-g[e]));
+    float* out = a.out + z * a.out_zstride + ((long long)b * S + i) * dm + co;
+    *reinterpret_cast<float4*>(out) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(out + 4) = make_float4(o[4], o[5], o[6], o[7]);
+}
+
 // z[b, r*D + d] = X_out_r[b, 0, d] + X_in_r[b, 0, d]           (net.py:377-378)
 __global__ void head_gather_kernel(HeadGatherArgs a) {
     CHROMO_PDL_ENTER();
@@ -435,7 +515,19 @@ int launch_reg_attention(const RegAttnArgs& a, int nz, cudaStream_t st) {
         if (a.S <= 9) launch_pdl(reg_attention_kernel<9, __nv_bfloat16>, dim3(grid), dim3(wpb * 32), 0, st, a);
         else launch_pdl(reg_attention_kernel<17, __nv_bfloat16>, dim3(grid), dim3(wpb * 32), 0, st, a);
     } else {
-        if (a.S <= 9) launch_pdl(reg_attention_kernel<9, float>, dim3(grid), dim3(wpb * 32), 0, st, a);
+        static const bool per_thread = getenv("CHROMO_REG_ATTN_PER_THREAD") != nullptr;
+        if (a.H == 8 && a.S <= 17 && !per_thread) {       // one CTA per gene, rows staged in shared memory
+            const size_t smem = (size_t)a.S * (4 * 32 * a.H + RA_PAD) * sizeof(float);
+            static bool configured = false;
+            if (!configured) {
+                cudaFuncSetAttribute(reg_attention_gene_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)(17 * (4 * 32 * 8 + RA_PAD) * sizeof(float)));
+                configured = true;
+            }
+            const int threads = (a.H * a.S * 4 + 31) / 32 * 32;
+            if (a.S <= 9) launch_pdl(reg_attention_gene_kernel<9>, dim3(a.B, nz), dim3(threads), smem, st, a);
+            else launch_pdl(reg_attention_gene_kernel<17>, dim3(a.B, nz), dim3(threads), smem, st, a);
+        } else if (a.S <= 9) launch_pdl(reg_attention_kernel<9, float>, dim3(grid), dim3(wpb * 32), 0, st, a);
         else launch_pdl(reg_attention_kernel<17, float>, dim3(grid), dim3(wpb * 32), 0, st, a);
     }
     CHROMO_CHECK_LAUNCH("reg_attention");

@@ -221,9 +221,9 @@ def test_fused_adamw_resume_matches_stock_adamw():
         run(b_model, b_opt, b)
     for (n1, p1), (_, p2) in zip(ref.named_parameters(), b_model.named_parameters()):
         # two runs of the backward differ in the summation order of their FP32 atomics (~1e-7 relative on a gradient);
-        # Adam's m / sqrt(v) turns that into up to a few per cent of ONE lr-sized step (1e-3) on near-zero gradients.
-        # A lost moment or step count would show as a full step: 1e-3.
-        assert (p1 - p2).abs().max().item() < 5e-5, n1
+        # Adam's m / sqrt(v) turns that into up to ~5 % of ONE lr-sized step (1e-3) on near-zero gradients (measured up
+        # to 5.3e-5).  A lost moment or step count would show as a full step: 1e-3.
+        assert (p1 - p2).abs().max().item() < 2e-4, n1
     # the published state is the live flat buffers (not stale loaded tensors) and carries the step
     sd = b_opt.state_dict()
     assert float(sd["state"][0]["step"]) == 4.0
@@ -240,9 +240,9 @@ def test_fused_adamw_resume_matches_stock_adamw():
     run(c_model, c_opt, batches[0])
     for (n1, p1), (_, p2) in zip(ref.named_parameters(), c_model.named_parameters()):
         # two runs of the backward differ in the summation order of their FP32 atomics (~1e-7 relative on a gradient);
-        # Adam's m / sqrt(v) turns that into up to a few per cent of ONE lr-sized step (1e-3) on near-zero gradients.
-        # A lost moment or step count would show as a full step: 1e-3.
-        assert (p1 - p2).abs().max().item() < 5e-5, n1
+        # Adam's m / sqrt(v) turns that into up to ~5 % of ONE lr-sized step (1e-3) on near-zero gradients (measured up
+        # to 5.3e-5).  A lost moment or step count would show as a full step: 1e-3.
+        assert (p1 - p2).abs().max().item() < 2e-4, n1
 
 
 def _flat(grads, names):
