@@ -14,6 +14,8 @@ MAX_LAYERS = 8
 F_TRAINING = 1
 F_BF16 = 2
 F_PACKED = 4
+F_BWD_HEAD_REG = 16
+F_BWD_REST = 32
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libchromo_b200.so")

@@ -609,7 +609,7 @@ int sqa_bwd(const Ctx& c, const SqaBwd& s) {
 }  // namespace
 
 static int backward_impl(const chromo_config_t* c, const float* P, const chromo_batch_t* in, const float* dlogits,
-                         float* G, float* ws, const WsLayout& w, cudaStream_t st, bool tc) {
+                         float* G, float* ws, const WsLayout& w, cudaStream_t st, bool tc, bool part1, bool part2) {
     const ParamLayout& L = get_layout(c);
     const int B = w.B, I = w.I, S = w.S, R = w.R, T = w.T, D = w.D, F = c->n_feats, NR = c->n_res;
     const long long RS = w.res_stride;
@@ -652,6 +652,10 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
     const int64_t o_dz = take((int64_t)B * NR * D), o_dh1 = take((int64_t)B * c->d_head);
     if (cur > w.total) { set_error("internal: backward scratch exceeds workspace"); return CHROMO_ENOMEM; }
 
+    float* gcur = ws + o_tR0;           // gradient arriving at the layer's output
+    float* gnext = ws + o_tR1;
+    cudaStream_t wst = st;
+    if (part1) {
     // ---- head (net.py:377-380) ------------------------------------------------
     {
         const int dh = c->d_head, no = c->n_out;
@@ -668,8 +672,6 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
     }
 
     // ---- Regulation transformer ------------------------------------------------
-    float* gcur = ws + o_tR0;           // gradient arriving at the layer's output
-    float* gnext = ws + o_tR1;
     for (int l = c->reg_layers - 1; l >= 0; --l) {
         const AttnOff& ra = L.reg[0].att[l];
         const FfnOff& rf = L.reg[0].ffn[l];
@@ -716,14 +718,18 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
     }
     // The Regulation transformer's weight gradients (two thirds of the queue) start now, on a side stream and on two
     // thirds of the SMs, under the Pairwise / Embedding backward; the rest follows at the end.
-    cudaStream_t wst = st;
     if (tc && !getenv("CHROMO_WGRAD_AT_END")) {
         CHROMO_TRY(aux_fork(st, &wst));
         if (wst != st) CHROMO_TRY(queue.flush(wst, 96));
     }
-    float* gR = gcur;                   // dX_in (without the residual of net.py:378)
-    launch_pdl(head_residual_kernel, dim3(dim3((B * D + 255) / 256, NR)), dim3(256), 0, st, gR, GS, ws + o_dz, B, S, D, NR);
+    launch_pdl(head_residual_kernel, dim3(dim3((B * D + 255) / 256, NR)), dim3(256), 0, st, gcur, GS, ws + o_dz, B, S, D, NR);
     CHROMO_CHECK_LAUNCH("head_residual");
+    }   // part1
+    float* gR = gcur;                   // dX_in incl. the residual of net.py:378 (the Regulation loop ends in the buffer it began in)
+    if (!part2) {
+        if (tc) CHROMO_TRY(queue.flush(st));
+        return aux_join(st, wst);
+    }
 
     // ---- Pairwise Interaction transformer ---------------------------------------
     float* pcur = ws + o_tP0;
@@ -854,6 +860,8 @@ extern "C" int chromo_backward(const chromo_config_t* cfg, const float* params, 
         set_error("workspace too small: need %lld floats, got %lld", (long long)w.total, (long long)workspace_floats);
         return CHROMO_ENOMEM;
     }
+    const bool only1 = (flags & CHROMO_F_BWD_HEAD_REG) != 0, only2 = (flags & CHROMO_F_BWD_REST) != 0;
+    if (only1 && only2) { set_error("chromo_backward: CHROMO_F_BWD_HEAD_REG and CHROMO_F_BWD_REST are exclusive"); return CHROMO_EINVAL; }
     return backward_impl(cfg, params, in, dlogits, grads, workspace, w, (cudaStream_t)stream,
-                         (flags & CHROMO_F_BF16) != 0 && !getenv("CHROMO_BWD_FP32"));
+                         (flags & CHROMO_F_BF16) != 0 && !getenv("CHROMO_BWD_FP32"), !only2, !only1);
 }

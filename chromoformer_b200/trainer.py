@@ -3,8 +3,12 @@
 ``TrainStep`` chains, on one stream and without autograd bookkeeping,
     forward (activations kept) -> loss + dlogits kernel -> backward into the flat gradient
     buffer -> [NCCL all-reduce of the gradient-receiving prefix] -> one fused AdamW launch.
-The only collective of the whole path is that all-reduce: one flat FP32 bucket
-of ``model.n_active`` values, summed, with the 1/world mean folded into the AdamW kernel.
+The only collective of the whole path is that all-reduce of the ``model.n_active``
+gradient values, summed, with the 1/world mean folded into the AdamW kernel.  With more than one rank
+it travels as two buckets: the head + Regulation-transformer gradients (78 % of the bytes, a contiguous
+tail of the flat buffer) are final once the first part of the backward (``CHROMO_F_BWD_HEAD_REG``) has
+run, so their all-reduce is issued there and overlaps the Pairwise / Embedding part
+(``CHROMO_F_BWD_REST``); only the small second bucket is exposed.
 """
 import ctypes
 
@@ -49,9 +53,14 @@ class TrainStep:
         self._graphs = {}        # geometry -> captured chain
         self._flat_ptr = flat.data_ptr()
         self.graph_replays = 0
+        # first element of the head + Regulation bucket (parameter layout: embed x3 | pairwise x3 | regulation x3 | head)
+        self.bucket_split = min(off for (name, _, off, _) in model._slots
+                                if off < model.n_active and model._lib_name(name).startswith(("regulation.", "fc_head.")))
+        self.overlap = self.world > 1
 
     # ---- forward + loss + backward into self.grad (everything a CUDA graph may hold) -------------------------
-    def _chain(self, io, target, logits, dlogits):
+    def _chain(self, io, target, logits, dlogits, part=0):
+        """part 0: the whole chain; 1: forward + loss + head / Regulation backward; 2: the rest of the backward."""
         lib = _lib.load()
         model = self.model
         flat = model.flat_params
@@ -59,18 +68,24 @@ class TrainStep:
         ws = self._ws
         cfg = ctypes.byref(io.cfg)
         n_out = int(io.cfg.n_out)
-        _lib.check(lib.chromo_forward(cfg, flat.data_ptr(), ctypes.byref(io.struct), logits.data_ptr(),
-                                      ws.data_ptr(), ws.numel(), self.flags, stream), "chromo_forward")
-        if self.regression:
-            _lib.check(lib.chromo_mse_loss(logits.data_ptr(), target.data_ptr(), io.batch * n_out, 1.0,
-                                           self.loss.data_ptr(), dlogits.data_ptr(), stream), "chromo_mse_loss")
-        else:
-            _lib.check(lib.chromo_ce_loss(logits.data_ptr(), target.data_ptr(), io.batch, n_out, 1.0,
-                                          self.loss.data_ptr(), dlogits.data_ptr(), stream), "chromo_ce_loss")
-        self.grad[:model.n_active].zero_()
+        if part in (0, 1):
+            _lib.check(lib.chromo_forward(cfg, flat.data_ptr(), ctypes.byref(io.struct), logits.data_ptr(),
+                                          ws.data_ptr(), ws.numel(), self.flags, stream), "chromo_forward")
+            if self.regression:
+                _lib.check(lib.chromo_mse_loss(logits.data_ptr(), target.data_ptr(), io.batch * n_out, 1.0,
+                                               self.loss.data_ptr(), dlogits.data_ptr(), stream), "chromo_mse_loss")
+            else:
+                _lib.check(lib.chromo_ce_loss(logits.data_ptr(), target.data_ptr(), io.batch, n_out, 1.0,
+                                              self.loss.data_ptr(), dlogits.data_ptr(), stream), "chromo_ce_loss")
+            self.grad[:model.n_active].zero_()
+        flags = self.flags | {0: 0, 1: _lib.F_BWD_HEAD_REG, 2: _lib.F_BWD_REST}[part]
         _lib.check(lib.chromo_backward(cfg, flat.data_ptr(), ctypes.byref(io.struct), dlogits.data_ptr(),
-                                       self.grad.data_ptr(), ws.data_ptr(), ws.numel(), self.flags, stream),
+                                       self.grad.data_ptr(), ws.data_ptr(), ws.numel(), flags, stream),
                    "chromo_backward")
+
+    def _reduce(self, lo, hi):
+        """Asynchronous SUM all-reduce of grad[lo:hi] (ordered behind the work enqueued so far on the current stream)."""
+        return dist.all_reduce(self.grad[lo:hi], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
 
     def _io(self, batch):
         model = self.model
@@ -97,17 +112,18 @@ class TrainStep:
         io = self._io(static)
         logits = torch.empty(io.batch, int(io.cfg.n_out), dtype=torch.float32, device=dev)
         dlogits = torch.empty_like(logits)
-        graph = torch.cuda.CUDAGraph()
+        graphs = [torch.cuda.CUDAGraph() for _ in range(2 if self.overlap else 1)]
         try:
             torch.cuda.synchronize(dev)
-            with torch.cuda.graph(graph):
-                self._chain(io, tgt, logits, dlogits)
+            for part, graph in enumerate(graphs, 1 if self.overlap else 0):
+                with torch.cuda.graph(graph):
+                    self._chain(io, tgt, logits, dlogits, part)
         except Exception:                      # a driver / toolkit that cannot capture this chain: stay eager
             self.use_graph = False
             torch.cuda.synchronize(dev)
             return None
         self._flat_ptr = self.model.flat_params.data_ptr()
-        ent = {"graph": graph, "static": static, "target": tgt, "io": io, "logits": logits, "dlogits": dlogits}
+        ent = {"graphs": graphs, "static": static, "target": tgt, "io": io, "logits": logits, "dlogits": dlogits}
         self._graphs[key] = ent
         return ent
 
@@ -142,7 +158,11 @@ class TrainStep:
                 else:
                     ent["static"][k].copy_(batch[k], non_blocking=True)
             ent["target"].copy_(target, non_blocking=True)
-            ent["graph"].replay()
+            pending = []
+            for i, graph in enumerate(ent["graphs"]):
+                graph.replay()
+                if self.overlap:               # bucket 1 travels under the second graph, bucket 2 behind it
+                    pending.append(self._reduce(self.bucket_split, model.n_active) if i == 0 else self._reduce(0, self.bucket_split))
             self.graph_replays += 1
             logits = ent["logits"]
         else:
@@ -150,9 +170,22 @@ class TrainStep:
                 self._seen[key] = self._seen.get(key, 0) + 1
             logits = torch.empty(io.batch, int(io.cfg.n_out), dtype=torch.float32, device=dev)
             dlogits = torch.empty_like(logits)
-            self._chain(io, self._target(target), logits, dlogits)
+            tgt = self._target(target)
+            pending = []
+            if self.overlap:
+                self._chain(io, tgt, logits, dlogits, 1)
+                pending.append(self._reduce(self.bucket_split, model.n_active))
+                self._chain(io, tgt, logits, dlogits, 2)
+                pending.append(self._reduce(0, self.bucket_split))
+            else:
+                self._chain(io, tgt, logits, dlogits)
         stream = torch.cuda.current_stream(dev).cuda_stream
-        scale = allreduce_gradients(self.grad, model.n_active, self.group) if self.world > 1 else 1.0
+        if self.overlap:
+            for h in pending:
+                h.wait()                       # (stream-side wait: the host does not block)
+            scale = 1.0 / self.world
+        else:
+            scale = allreduce_gradients(self.grad, model.n_active, self.group) if self.world > 1 else 1.0
         self.step_count += 1
         _lib.check(lib.chromo_adamw(flat.data_ptr(), self.grad.data_ptr(), self.m.data_ptr(), self.v.data_ptr(),
                                     model.n_active, self.lr, self.betas[0], self.betas[1], self.eps, self.wd,

@@ -39,6 +39,12 @@ extern "C" {
 #define CHROMO_F_BF16 2       /* dense projections on tcgen05 (BF16 operands,
                                  FP32 accumulate); default is strict FP32   */
 #define CHROMO_F_REGONLY 8    /* internal */
+#define CHROMO_F_BWD_HEAD_REG 16 /* chromo_backward: only the head + Regulation-transformer part of the pass (their
+                                    gradients - the contiguous tail [first regulation tensor, active) of the flat buffer -
+                                    are final when the call's work completes)                                            */
+#define CHROMO_F_BWD_REST 32     /* chromo_backward: only the Pairwise + Embedding part; needs the other part first.
+                                    Neither bit = the whole pass.  Data-parallel training all-reduces the first bucket
+                                    under the second call (trainer.TrainStep).                                           */
 #define CHROMO_F_PACKED 4     /* with CHROMO_F_BF16: the workspace already holds
                                  the packed BF16 weights of THESE parameters
                                  (left there by a previous call) - skip packing */

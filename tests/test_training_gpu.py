@@ -316,3 +316,43 @@ def test_bf16_training_follows_the_fp32_trajectory():
     a, b = curves["fp32"], curves["bf16"]
     assert b[-1] < 0.5 * b[0], (b[0], b[-1])
     assert max(abs(x - y) / max(abs(x), 1e-6) for x, y in zip(a, b)) < 3e-2, list(zip(a, b))[-3:]
+
+
+def test_two_bucket_backward_matches_the_single_pass():
+    """Data-parallel path of TrainStep on one rank (single-process NCCL group): the backward runs as two C-ABI calls
+    (CHROMO_F_BWD_HEAD_REG, CHROMO_F_BWD_REST), each followed by the all-reduce of its bucket, eagerly for two steps and
+    from two captured graphs afterwards.  Losses and parameters must follow the single-call step."""
+    import torch.distributed as dist
+    from chromoformer_b200.trainer import TrainStep
+    own_group = not dist.is_initialized()
+    if own_group:
+        dist.init_process_group("nccl", init_method="tcp://127.0.0.1:29541", rank=0, world_size=1)
+    try:
+        batch = synthetic.make_batch(16, ragged=True, seed=51)
+        dev = {k: ({b: t.cuda() for b, t in v.items()} if isinstance(v, dict) else v.cuda()) for k, v in batch.items()}
+        target = dev["labels_reg"].view(-1, 1)
+        runs = {}
+        for overlap in (False, True):
+            m = _mk(ChromoformerRegressor, seed=9).cuda().train()
+            m.precision = "bf16"
+            step = TrainStep(m, lr=1e-4, regression=True, distributed=True)
+            assert step.world == 1 and 0 < step.bucket_split < m.n_active
+            step.overlap = overlap
+            step(dev, target)
+            g1 = step.grad[:m.n_active].clone()              # gradient of the first step: same parameters in both runs
+            losses = [float(step.loss.item())] + [float(step(dev, target).item()) for _ in range(4)]
+            assert step.graph_replays == 3
+            runs[overlap] = (losses, g1)
+        (la, ga), (lb, gb) = runs[False], runs[True]
+        # the two calls compute what the single call computes: only the order of FP32 atomics differs
+        assert (ga - gb).abs().max().item() < 1e-4 * ga.abs().max().item()
+        assert la[0] == lb[0]
+        # later steps: Adam turns reordered sums into small parameter differences, BF16 operand rounding into loss noise
+        assert max(abs(x - y) / abs(x) for x, y in zip(la, lb)) < 2e-2, (la, lb)
+        assert lb[-1] < 0.7 * lb[0]
+        # the bucket boundary is the first Regulation tensor
+        names = {off: name for (name, _, off, _) in m._slots}
+        assert names[step.bucket_split].startswith("regulation.")
+    finally:
+        if own_group:
+            dist.destroy_process_group()
