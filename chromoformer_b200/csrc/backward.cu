@@ -655,6 +655,7 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
     float* gcur = ws + o_tR0;           // gradient arriving at the layer's output
     float* gnext = ws + o_tR1;
     cudaStream_t wst = st;
+    static const bool wgrad_at_end = getenv("CHROMO_WGRAD_AT_END") != nullptr;
     if (part1) {
     // ---- head (net.py:377-380) ------------------------------------------------
     {
@@ -715,13 +716,14 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
         DataEpi resid; resid.res = gC;
         CHROMO_TRY(bwd_data(cx, dProj, 4 * dmr, GS, P + ra.att, L.reg_stride, gcur, D, GS, T, 4 * dmr, D, resid, NR));
         // gcur = dX of this layer = the gradient arriving at the output of layer l-1; gnext is free again
+        // this layer's weight gradients start now, on the side stream and on 64 SMs, under the next layer's chain
+        if (tc && !wgrad_at_end) {
+            CHROMO_TRY(aux_fork(st, &wst));
+            if (wst != st) CHROMO_TRY(queue.flush(wst, 64));
+        }
     }
     // The Regulation transformer's weight gradients (two thirds of the queue) start now, on a side stream and on two
     // thirds of the SMs, under the Pairwise / Embedding backward; the rest follows at the end.
-    if (tc && !getenv("CHROMO_WGRAD_AT_END")) {
-        CHROMO_TRY(aux_fork(st, &wst));
-        if (wst != st) CHROMO_TRY(queue.flush(wst, 96));
-    }
     launch_pdl(head_residual_kernel, dim3(dim3((B * D + 255) / 256, NR)), dim3(256), 0, st, gcur, GS, ws + o_dz, B, S, D, NR);
     CHROMO_CHECK_LAUNCH("head_residual");
     }   // part1
@@ -787,10 +789,9 @@ static int backward_impl(const chromo_config_t* c, const float* P, const chromo_
         CHROMO_TRY(gemm_auto(g, true, false, NR, st, tc));
     }
 
-    if (wst != st) {     // the Pairwise weight gradients follow on the side stream (its operands are final: order them behind st)
-        cudaStream_t again = st;
-        CHROMO_TRY(aux_fork(st, &again));
-        CHROMO_TRY(queue.flush(again, 64));
+    if (tc && !wgrad_at_end) {     // the Pairwise weight gradients follow on the side stream (ordered behind st)
+        CHROMO_TRY(aux_fork(st, &wst));
+        if (wst != st) CHROMO_TRY(queue.flush(wst, 64));
     }
 
     // ---- Embedding transformer ----------------------------------------------------

@@ -11,6 +11,11 @@ from chromoformer_b200.trainer import TrainStep  # noqa: E402
 
 prec = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 graph = (sys.argv[2] if len(sys.argv) > 2 else "graph") == "graph"
+from chromoformer_b200.parallel import init_distributed  # noqa: E402
+
+rank, local, world = init_distributed()
+if world > 1:
+    torch.cuda.set_device(local)
 lib = _lib.load()
 reg = ChromoformerRegressor(seed=123).cuda().train()
 reg.precision = prec
@@ -31,4 +36,10 @@ for _ in range(50):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / 50
-print(f"{prec} {'graph' if graph else 'eager'}: {ms:.3f} ms/step = {64 / ms * 1e3:.0f} samples/s, {launches} launches, loss {step.loss.item():.4f}")
+if world > 1:
+    import torch.distributed as dist
+    t = torch.tensor([ms], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+if rank == 0:
+    print(f"world {world} overlap {step.overlap} {prec} {'graph' if graph else 'eager'}: {ms:.3f} ms/step = {world * 64 / ms * 1e3:.0f} samples/s, {launches} launches, loss {step.loss.item():.4f}")
