@@ -155,13 +155,17 @@ class TrainStep:
             if self.use_graph and seen >= self.GRAPH_AFTER:
                 ent = self._capture(key, batch, target)
         if ent is not None:
+            # the captured chain reads its own input buffers; a caller that already wrote the batch into them
+            # (`input_buffers`, e.g. as the destination of its host->device copies) pays no copy here
             for k in FORWARD_KEYS:
                 if isinstance(batch[k], dict):
                     for b, t in batch[k].items():
-                        ent["static"][k][b].copy_(t, non_blocking=True)
-                else:
+                        if t.data_ptr() != ent["static"][k][b].data_ptr():
+                            ent["static"][k][b].copy_(t, non_blocking=True)
+                elif batch[k].data_ptr() != ent["static"][k].data_ptr():
                     ent["static"][k].copy_(batch[k], non_blocking=True)
-            ent["target"].copy_(target, non_blocking=True)
+            if target.data_ptr() != ent["target"].data_ptr():
+                ent["target"].copy_(target, non_blocking=True)
             pending = []
             for i, graph in enumerate(ent["graphs"]):
                 graph.replay()
@@ -197,6 +201,16 @@ class TrainStep:
         model.mark_parameters_changed()
         self.logits = logits
         return self.loss
+
+    def input_buffers(self, batch, target):
+        """The device buffers the captured chain of this batch geometry reads: (batch dict, target), or None while the
+        geometry still runs eagerly.  Filling them directly (they are the natural destination of the host->device copies of
+        the next batch) and passing them to `__call__` removes the per-step device-to-device copies."""
+        ent = self._graphs.get(self._geometry(batch, target)) if self.use_graph else None
+        if ent is None:
+            return None
+        tgt = ent["target"]
+        return dict(ent["static"]), tgt.view(target.shape) if tgt.numel() == target.numel() else tgt
 
     def set_lr(self, lr):
         """StepLR hook (train.py:158,344)."""

@@ -356,3 +356,33 @@ def test_two_bucket_backward_matches_the_single_pass():
     finally:
         if own_group:
             dist.destroy_process_group()
+
+
+def test_train_step_input_buffers_skip_the_copies():
+    """After the chain of a geometry has been captured, TrainStep.input_buffers() hands out the buffers the graph reads;
+    a batch written into them in place and passed back gives the step of that batch (no device-to-device copies)."""
+    from chromoformer_b200.trainer import TrainStep
+    mk = lambda seed: {k: ({b: t.cuda() for b, t in v.items()} if isinstance(v, dict) else v.cuda())
+                       for k, v in synthetic.make_batch(8, ragged=True, seed=seed).items()}
+    b1, b2 = mk(61), mk(62)
+    ref = _mk(ChromoformerRegressor, seed=2).cuda().train()
+    got = _mk(ChromoformerRegressor, seed=2).cuda().train()
+    s_ref = TrainStep(ref, lr=1e-4, regression=True, use_graph=False)
+    s_got = TrainStep(got, lr=1e-4, regression=True, use_graph=True)
+    assert s_got.input_buffers(b1, b1["labels_reg"].view(-1, 1)) is None
+    for _ in range(3):
+        la = s_ref(b1, b1["labels_reg"].view(-1, 1)).item()
+        lb = s_got(b1, b1["labels_reg"].view(-1, 1)).item()
+        assert abs(la - lb) < 1e-5
+    bufs, tgt = s_got.input_buffers(b1, b1["labels_reg"].view(-1, 1))
+    for k in synthetic.FORWARD_KEYS:                         # the next batch, written where the graph reads
+        if isinstance(bufs[k], dict):
+            for b in bufs[k]:
+                bufs[k][b].copy_(b2[k][b])
+        else:
+            bufs[k].copy_(b2[k])
+    tgt.copy_(b2["labels_reg"].view(-1, 1))
+    replays = s_got.graph_replays
+    la = s_ref(b2, b2["labels_reg"].view(-1, 1)).item()
+    lb = s_got(bufs, tgt).item()
+    assert s_got.graph_replays == replays + 1 and abs(la - lb) < 2e-5, (la, lb)
