@@ -269,7 +269,7 @@ def cpu_baseline_subprocess(steps=3, warmup=1, train=True):
 
 def workload_config(args):
     return {"workload": "Chromoformer-clf default config (i_max=8, binsizes 2000/500/100, 7 marks) inference over "
-                        "18,955 synthetic genes per GPU", "genes_per_gpu": N_GENES, "chunk": args.chunk,
+                        "18,955 synthetic genes per GPU", "genes_per_gpu": N_GENES, "chunk": args.chunk, "e2e_chunk": args.e2e_chunk,
             "i_max": 8, "l2_policy": "inputs (2.5 GB/GPU) larger than L2; no flush needed",
             "precision": args.precision}
 
@@ -282,7 +282,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--mode", choices=["infer", "train"], default="infer")
     ap.add_argument("--impl", choices=["b200", "reference"], default="b200")
-    ap.add_argument("--chunk", type=int, default=4096)
+    ap.add_argument("--chunk", type=int, default=N_GENES,
+                    help="genes per launch chain of the device-resident sweep (default: the whole sweep; measured on one B200 "
+                         "4096: 2.98, 6216: 3.07, 9478: 3.25, 18955: 3.38 M genes/s, tools/chunk_sweep.py)")
+    ap.add_argument("--e2e-chunk", type=int, default=4096, help="genes per host->device copy / forward chunk of the e2e arm")
     ap.add_argument("--precision", choices=["fp32", "bf16"], default="bf16")
     ap.add_argument("--train-precision", choices=["fp32", "bf16"], default="bf16")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -402,6 +405,8 @@ def main():
     wire = pack_wire(host)
     h2d = wire_nbytes(wire)
     e2e_steps = max(2, args.steps // 2)
+    eng_res = eng
+    eng = InferenceEngine(model, chunk=args.e2e_chunk)      # chunks: the copy of chunk i+1 runs under the forward of chunk i
     ms_e2e = timed(lambda: eng.predict_wire(wire), e2e_steps, 3)
     e2e = {"value": world * N_GENES / (ms_e2e * 1e-3), "unit": "genes/s", "h2d_bytes_per_step": h2d,
            "d2h_bytes_per_step": N_GENES * 2 * 4, "ms_per_step": ms_e2e, "api": "InferenceEngine.predict_wire(pack_wire(batch))",
@@ -449,7 +454,7 @@ def main():
     # BF16: the fused Regulation layer (reg_layer_fused_kernel, 1/3 of the step); FP32: the batched projection GEMM.
     st = torch.cuda.current_stream().cuda_stream
     flags = _lib.F_BF16 if args.precision == "bf16" else 0
-    Bk = args.chunk
+    Bk = min(args.chunk, N_GENES)
     T = Bk * 9
     if args.precision == "bf16":
         cfgk = _lib.Config.from_buffer_copy(model._cfg)
@@ -592,7 +597,8 @@ def main():
     sweep = None
     if not args.no_sweep:
         from chromoformer_b200.sweep import EnsembleSweep
-        es = EnsembleSweep(model, chunk=args.chunk)
+        # (two chunks per checkpoint on several ranks: 88 units split evenly over 2, 4 and 8 ranks)
+        es = EnsembleSweep(model, chunk=args.chunk if world == 1 else (N_GENES + 1) // 2)
         base = model.flat_params.detach().clone()
         gsw = torch.Generator(device=dev).manual_seed(1)
         for ck in range(44):                                  # 44 distinct random-init "checkpoints" (no weights offline)
