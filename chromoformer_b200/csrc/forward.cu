@@ -29,18 +29,31 @@ namespace chromo {
 // --------------------------------------------------------------- kernels ----
 
 // Hc[b,:] = W_lp x_p[b,c,:] + PE[c,:]        (net.py:42,47-53 at the centre bin)
-__global__ void centre_embed_kernel(CentreEmbedArgs a) {
+// One thread per output channel, 32 genes per block: the channel's F weights and its position-table entry sit in
+// registers, a gene's F features arrive as one broadcast read, the row leaves as 512 contiguous bytes.
+constexpr int CE_GENES = 32;
+__global__ void __launch_bounds__(128) centre_embed_kernel(CentreEmbedArgs a) {
     CHROMO_PDL_ENTER();
     const int r = blockIdx.y;
     const int n = a.n[r], c = n / 2, D = a.D, F = a.F;
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.B * D) return;
-    const int b = idx / D, d = idx % D;
-    const float* x = a.x[r] + ((long long)b * n + c) * F;
-    const float* w = a.w + r * a.w_stride + (long long)d * F;
-    float s = a.pe[r][(long long)c * D + d];
-    for (int f = 0; f < F; ++f) s = fmaf(w[f], x[f], s);
-    a.out[r * a.out_stride + idx] = s;
+    const float* xr = a.x[r];
+    const float* per = a.pe[r];
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+        const float* w = a.w + r * a.w_stride + (long long)d * F;
+        float wv[8];
+#pragma unroll
+        for (int f = 0; f < 8; ++f) wv[f] = f < F ? w[f] : 0.f;
+        const float pe = per[(long long)c * D + d];
+        const int b1 = min(a.B, (int)(blockIdx.x + 1) * CE_GENES);
+        for (int b = blockIdx.x * CE_GENES; b < b1; ++b) {
+            const float* x = xr + ((long long)b * n + c) * F;
+            float s = pe;
+#pragma unroll
+            for (int f = 0; f < 8; ++f)
+                if (f < F) s = fmaf(wv[f], __ldg(x + f), s);
+            a.out[r * a.out_stride + (long long)b * D + d] = s;
+        }
+    }
 }
 
 // Single-query attention row (one warp per (region, head)):
@@ -774,8 +787,8 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         for (int r = 0; r < NR; ++r) { a.x[r] = in->x_p[r]; a.pe[r] = in->pos_enc[r]; a.n[r] = c->n_bins[r]; }
         a.w = P + L.embed[0].lin_proj; a.w_stride = L.embed_stride;
         a.out = ws + w.e_hc; a.out_stride = RS;
-        dim3 grid((B * D + 255) / 256, NR);
-        launch_pdl(centre_embed_kernel, dim3(grid), dim3(256), 0, st, a);
+        dim3 grid((B + CE_GENES - 1) / CE_GENES, NR);
+        launch_pdl(centre_embed_kernel, dim3(grid), dim3(128), 0, st, a);
         CHROMO_CHECK_LAUNCH("centre_embed");
     }
     const AttnOff& ea = L.embed[0].att[0];

@@ -3,9 +3,14 @@
 //   U = LN(res + Cbar N^T + b_o)          N = [W_o[:,h] W_v[h]]_h  ([128, 256], modules.py:29-30 / 150-152)
 //   Y = LN(U + W_2 relu(W_1 U + b_1) + b_2)                        (modules.py:100-101)
 //
-// Same machinery as reg_fused.cu (driver warp: TMA weight ring + tcgen05.mma; 8 compute warps:
+// Same machinery as reg_fused.cu (driver warp: TMA weight stage + tcgen05.mma; 8 compute warps:
 // TMEM epilogues), without the attention: a 128-row tile of Cbar goes in, the layer output comes
 // out; U and the FFN hidden activations never leave the SM.
+//
+// The phases of a tile are strictly serial (MMA -> epilogue -> MMA ...), so the tile is kept SMALL instead of fast: one
+// 64 KB operand buffer that holds Cbar, then U (over its first half), then the hidden activations; one 32 KB weight stage;
+// 256 TMEM columns (the out-projection / FFN-2 accumulator under the FFN-1 one).  Two CTAs then share an SM (104 KB of
+// shared memory, 256 columns each) and one tile's epilogues run under the other's MMAs and weight copies.
 #include "common.cuh"
 #include "kernels.cuh"
 #include "reg_fused.cuh"
@@ -16,13 +21,14 @@ namespace chromo {
 namespace {
 
 constexpr int RT_THREADS = 288;
-constexpr int RT_NSTAGE = 3;
+constexpr int RT_NSTAGE = 1;
 constexpr int RT_CHUNK_ELEMS = 128 * 128;
 constexpr uint32_t RT_CHUNK_BYTES = RT_CHUNK_ELEMS * 2;
 
-constexpr uint32_t RT_OFF_U = 0;                              // [128 x 128] BF16 operand (U)
-constexpr uint32_t RT_OFF_A = 32768;                          // [128 x 256] BF16 operand (Cbar, then F, then store staging)
-constexpr uint32_t RT_OFF_STAGE = RT_OFF_A + 65536;           // 3 x 32 KB weight ring
+constexpr uint32_t RT_OFF_A = 0;                              // [128 x 256] BF16 operand (Cbar, then F, then store staging)
+constexpr uint32_t RT_OFF_U = RT_OFF_A;                       // [128 x 128] BF16 operand (U) over the dead Cbar tile
+constexpr uint32_t RT_OFF_STAGE = RT_OFF_A + 65536;           // 32 KB weight stage
+constexpr uint32_t RT_TMEM_COLS = 256;
 constexpr uint32_t RT_OFF_PRM = RT_OFF_STAGE + RT_NSTAGE * RT_CHUNK_BYTES;   // 1024 floats of parameters
 constexpr uint32_t RT_OFF_RED = RT_OFF_PRM + 4096;            // 2 x 512 floats of LayerNorm partials
 constexpr uint32_t RT_OFF_CTL = RT_OFF_RED + 4096;
@@ -45,7 +51,7 @@ __device__ __forceinline__ uint32_t t_chunk(int row, int kc, int K) {
 
 }  // namespace
 
-__global__ void __launch_bounds__(RT_THREADS, 1) row_tail_fused_kernel(const RowTailArgs a) {
+__global__ void __maxnreg__(96) row_tail_fused_kernel(const RowTailArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + RT_OFF_CTL);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + T_COUNT);
@@ -54,9 +60,8 @@ __global__ void __launch_bounds__(RT_THREADS, 1) row_tail_fused_kernel(const Row
     const int m0 = blockIdx.x * 128;
     const int rows_valid = min(128, a.M - m0);
     const int nff = a.dff / 128;                              // 1 or 2 chunks per FFN matrix
-    const int nchunk = 2 + 2 * nff;
 
-    if (warp == 0) tmem_alloc(tmem_slot, 512);
+    if (warp == 0) tmem_alloc(tmem_slot, RT_TMEM_COLS);
     if (tid == 0) {
         for (int i = 0; i < RT_NSTAGE; ++i) { mbar_init(&bars[T_FULL0 + i], 1); mbar_init(&bars[T_FREE0 + i], 1); }
         mbar_init(&bars[T_AREADY], 8); mbar_init(&bars[T_UREADY], 8); mbar_init(&bars[T_FREADY], 8);
@@ -90,18 +95,30 @@ __global__ void __launch_bounds__(RT_THREADS, 1) row_tail_fused_kernel(const Row
                 for (int k = 0; k < 8; ++k)
                     umma_bf16(tmem + col, ad + 16 * k, bd + 16 * k, idesc, (accumulate || k > 0) ? 1u : 0u);
                 umma_commit(&bars[T_FREE0 + st]);
-                if (c + 2 < nchunk && c >= 1) issue_load(c + 2);
             };
-            for (int c = 0; c < 3 && c < nchunk; ++c) issue_load(c);
+            // one weight stage: the copy of chunk c+1 is issued as soon as the MMAs of chunk c have left the stage - after
+            // the phase's commit, so that the epilogue warps are released first; the chunk that opens the next phase
+            // travels under this phase's epilogue
+            int next = 0;
+            issue_load(next++);
             mbar_wait(&bars[T_AREADY], 0);
             consume(0, s_a, 4096, 0, false);                    // folded out-projection, K halves
+            issue_load(next++);
             consume(1, s_a + 2048, 4096, 0, true);
             umma_commit(&bars[T_ACCO]);
+            issue_load(next++);
             mbar_wait(&bars[T_UREADY], 0);
-            for (int h = 0; h < nff; ++h) consume(2 + h, s_u, 2048, 256 + 128 * h, false);   // FFN-1, N halves
+            for (int h = 0; h < nff; ++h) {                     // FFN-1, N halves, over the (read-out) out-projection accumulator
+                consume(2 + h, s_u, 2048, 128 * h, false);
+                if (h + 1 < nff) issue_load(next++);
+            }
             umma_commit(&bars[T_ACCF1]);
+            issue_load(next++);
             mbar_wait(&bars[T_FREADY], 0);
-            for (int h = 0; h < nff; ++h) consume(2 + nff + h, s_a + 2048 * h, (uint32_t)a.dff * 16, 0, h > 0);   // FFN-2, K halves
+            for (int h = 0; h < nff; ++h) {                     // FFN-2, K halves, over the (read-out) FFN-1 accumulator
+                consume(2 + nff + h, s_a + 2048 * h, (uint32_t)a.dff * 16, 0, h > 0);
+                if (h + 1 < nff) issue_load(next++);
+            }
             umma_commit(&bars[T_ACCF2]);
         }
     } else {
@@ -237,7 +254,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) row_tail_fused_kernel(const Row
             const float* b1 = prm + 768;
             for (int ci = 0; ci < 2 * nff; ++ci) {
                 const int c = (2 * ci + ch) * 32;
-                tmem_ld32(trow + 256 + c, v);
+                tmem_ld32(trow + c, v);
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
                     float r[8];
@@ -309,7 +326,7 @@ __global__ void __launch_bounds__(RT_THREADS, 1) row_tail_fused_kernel(const Row
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    if (warp == 0) tmem_dealloc(tmem, RT_TMEM_COLS);
 }
 
 // Weight stream of one tail: [N K-half 0, N K-half 1, W1 N-halves.., W2 K-halves..], each [128 x 128] BF16 tiles.
@@ -342,6 +359,8 @@ int launch_row_tail_fused(const RowTailArgs& a, int n_res, cudaStream_t st) {
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(row_tail_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RT_SMEM);
         if (e != cudaSuccess) { set_error("row_tail smem attribute: %s", cudaGetErrorString(e)); return CHROMO_ECUDA; }
+        // two CTAs per SM: 2 x 104 KB of shared memory, 2 x 256 TMEM columns, 18 warps x 96 registers (5 warps per scheduler)
+        cudaFuncSetAttribute(row_tail_fused_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
         configured = true;
     }
     if (a.dff != 128 && a.dff != 256) { set_error("row_tail_fused: d_ff must be 128 or 256"); return CHROMO_EINVAL; }
