@@ -244,6 +244,7 @@ __global__ void __launch_bounds__(UTHREADS) umma_linear_kernel(const UmmaArgs a)
             store_tile_f32(stage, v, C, &crow, g.ldc, c, 32, lane, rowmask);
         }
     } else {
+        const bool sqa_staged = g.c_sqa_tiles && K >= 96;        // (UM + NT) * K * 2 >= 64 KB of dead operand space
         for (int c = ch * 32; c < NT; c += 64) {
             tmem_ld32(trow + c, v);          // columns beyond NT (NT % 32 != 0) are dropped below
             const int ncols = min(32, NT - c);
@@ -260,8 +261,25 @@ __global__ void __launch_bounds__(UTHREADS) umma_linear_kernel(const UmmaArgs a)
                     }
                 }
             }
-            if (g.c_sqa_tiles) {
-                // QK operand tiles of sqa_fused: row 2m + head of the 128-row tiles, 16-byte chunks of 8 channels
+            if (g.c_sqa_tiles && sqa_staged) {
+                // QK operand tiles of sqa_fused: row 2m + head of the 128-row tiles, 16-byte chunks of 8 channels.  The 128
+                // rows of this CTA fill exactly two consecutive tiles (64 KB contiguous in HBM): composed in shared memory
+                // (the operands are dead), then written as full lines by everybody (rows past M as zeros)
+                const int head = (n0 + c) >> 7, kc0 = ((n0 + c) & 127) >> 3;
+                const int Rl = 2 * (lq * 32 + lane) + head, r = Rl & 127;
+                uint8_t* sp = smem + (Rl >> 7) * 32768 + (r >> 3) * 2048 + (r & 7) * 16;
+#pragma unroll
+                for (int j = 0; j < 32; j += 8) {
+                    uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                    if (ok) {
+                        __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                        __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                        pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                        pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                    }
+                    *reinterpret_cast<uint4*>(sp + (kc0 + (j >> 3)) * 128) = pk;
+                }
+            } else if (g.c_sqa_tiles) {
                 if (ok) {
                     const int head = (n0 + c) >> 7, kc0 = ((n0 + c) & 127) >> 3;
                     const long long R = 2LL * m + head;
@@ -319,6 +337,15 @@ __global__ void __launch_bounds__(UTHREADS) umma_linear_kernel(const UmmaArgs a)
                 }
             }
         }
+    }
+    if (g.c_sqa_tiles && K >= 96) {
+        __syncthreads();
+        uint8_t* out = reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(g.C) + z1 * g.sC1 + z2 * g.sC2) +
+                       (long long)blockIdx.y * 65536;
+        const int tiles = (2 * g.M - 2 * m0 + 127) / 128;       // 1 when the last CTA's rows end in its first tile
+        const int n16 = (tiles >= 2 ? 2 : 1) * 2048;
+        for (int i = tid; i < n16; i += UTHREADS)
+            reinterpret_cast<uint4*>(out)[i] = reinterpret_cast<const uint4*>(smem)[i];
     }
     tc_fence_before();
     __syncthreads();
