@@ -13,6 +13,7 @@
 //   epilogue (bias / ReLU / bias+residual+LayerNorm) straight from registers.
 // K is small (128..400) on this path, so there is no K pipeline inside a CTA; overlap comes
 // from two resident CTAs per SM (A/B staging of one under the MMA/epilogue of the other).
+#include <algorithm>
 #include <cuda_bf16.h>
 #include <stdlib.h>
 
@@ -352,6 +353,125 @@ __global__ void __launch_bounds__(UTHREADS) umma_linear_kernel(const UmmaArgs a)
     if (warp == 0) tmem_dealloc(tmem_base, a.tmem_cols);
 }
 
+// ---------------------------------------------------------------- the query GEMM of a single-query-attention stage ----
+// QK[m, (h, :)] = A[m / a_div, :] . M^T  (K = 128, N = 256 = two heads), written as the BF16 operand tiles sqa_fused pulls
+// in by TMA.  Persistent: a CTA keeps the 64 KB weight tile and its TMEM / barriers for all its row tiles (the one-tile
+// kernel above pays ~11 us of set-up and latency per tile: 137 us for 1185 tiles against 45 us of HBM time); two CTAs per
+// SM, so that one's staging / epilogue runs under the other's MMAs.  Per tile the 128 rows fill two consecutive 32 KB
+// operand tiles (row 2m + head): each is composed in the dead A operand and leaves as full lines.
+constexpr int QK_THREADS = 512;      // 16 warps: staging and epilogue are latency chains per warp (two CTAs x 16 warps x 64 registers)
+__global__ void __launch_bounds__(QK_THREADS, 2) qk_tiles_kernel(const UmmaArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const GemmArgs& g = a.g;
+    constexpr int K = 128, NT = 256, KC = K / 8;
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + UM * K * 2;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (UM + NT) * K * 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int z1 = blockIdx.y;
+    const float* A = g.A + z1 * g.sA1;
+    const __nv_bfloat16* Bp = a.Bp + z1 * g.sB1;
+    uint8_t* out_z = reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(g.C) + z1 * g.sC1);
+
+    if (warp == 0) tmem_alloc(tmem_slot, NT);
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    if (tid == 0) {
+        mbar_expect_tx(&bars[0], NT * K * 2);
+        tma_bulk_g2s(sB, Bp, NT * K * 2, &bars[0]);
+    }
+    const int lq = warp & 3, ch = warp >> 2;
+    const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16);
+    const uint32_t idesc = umma_idesc_bf16(UM, NT);
+    const int m_tiles = (g.M + UM - 1) / UM;
+    uint32_t it = 0;
+    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+        const int m0 = mt * UM;
+        // A: FP32 -> BF16 into the canonical K-major layout, all 16 loads of a thread in flight
+        {
+            float4 x[4][2];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int u = warp + q * 16;                      // 64 units: 16 row groups x 4 column groups
+                const int r = (u & 15) * 8 + (lane >> 2), kc = (u >> 4) * 4 + (lane & 3);
+                const int m = m0 + r;
+                x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (m < g.M) {
+                    const float* p = A + (long long)(m / g.a_div) * g.lda + kc * 8;
+                    x[q][0] = __ldg(reinterpret_cast<const float4*>(p));
+                    x[q][1] = __ldg(reinterpret_cast<const float4*>(p + 4));
+                }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int u = warp + q * 16;
+                const int r = (u & 15) * 8 + (lane >> 2), kc = (u >> 4) * 4 + (lane & 3);
+                __nv_bfloat162 b0 = __floats2bfloat162_rn(x[q][0].x, x[q][0].y), b1 = __floats2bfloat162_rn(x[q][0].z, x[q][0].w);
+                __nv_bfloat162 b2 = __floats2bfloat162_rn(x[q][1].x, x[q][1].y), b3 = __floats2bfloat162_rn(x[q][1].z, x[q][1].w);
+                uint4 pk;
+                pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
+                pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
+                *reinterpret_cast<uint4*>(sA + ((size_t)(r >> 3) * KC + kc) * 128 + (r & 7) * 16) = pk;
+            }
+        }
+        fence_async_smem();
+        __syncthreads();
+        if (tid == 0) {
+            if (it == 0) mbar_wait(&bars[0], 0);
+            tc_fence_after();
+            const uint64_t ad = umma_smem_desc(smem_u32(sA), 128, K * 16), bd = umma_smem_desc(smem_u32(sB), 128, K * 16);
+#pragma unroll
+            for (int k = 0; k < K / 16; ++k) umma_bf16(tmem_base, ad + 16 * k, bd + 16 * k, idesc, k > 0 ? 1u : 0u);
+            umma_commit(&bars[1]);
+        }
+        __syncwarp();
+        mbar_wait(&bars[1], it & 1);
+        tc_fence_after();
+        const bool ok = m0 + lq * 32 + lane < g.M;
+        const int tiles = min(2, (2 * g.M - 2 * m0 + 127) / 128);
+        for (int t = 0; t < tiles; ++t) {
+            if ((lq >> 1) == t) {
+                float v[32];
+#pragma unroll 1
+                for (int c = ch * 32; c < NT; c += 128) {
+                    tmem_ld32(trow + c, v);
+                    const int head = c >> 7, kc0 = (c & 127) >> 3;
+                    const int r = 2 * ((lq & 1) * 32 + lane) + head;
+                    uint8_t* sp = sA + (r >> 3) * 2048 + (r & 7) * 16;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 8) {
+                        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                        if (ok) {
+                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
+                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
+                            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                            pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                        }
+                        *reinterpret_cast<uint4*>(sp + (kc0 + (j >> 3)) * 128) = pk;
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncthreads();
+            uint4* out = reinterpret_cast<uint4*>(out_z + ((long long)mt * 2 + t) * 32768);
+#pragma unroll
+            for (int i = 0; i < 2048 / QK_THREADS; ++i) out[tid + i * QK_THREADS] = reinterpret_cast<const uint4*>(sA)[tid + i * QK_THREADS];
+            __syncthreads();
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem_base, NT);
+}
+
 static size_t umma_smem_bytes(int nt, int K) {
     size_t operands = (size_t)(UM + nt) * K * 2;
     const size_t staging = (size_t)(UTHREADS / 32) * 32 * STAGE_LD * 4;      // reuses the operand area
@@ -401,6 +521,27 @@ int umma_launch(const GemmArgs& g, const __nv_bfloat16* Bp, int nz, cudaStream_t
         cudaError_t e = cudaFuncSetAttribute(umma_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UMMA_SMEM_MAX);
         if (e != cudaSuccess) { set_error("umma smem attribute: %s", cudaGetErrorString(e)); return CHROMO_ECUDA; }
         configured = UMMA_SMEM_MAX;
+    }
+    if (g.c_sqa_tiles && g.K == 128 && g.N == 256 && a.NT == 256 && g.zdiv == 1 && (g.M + UM - 1) / UM >= 8 &&
+        !getenv("CHROMO_QK_ONE_TILE")) {
+        static bool qk_configured = false;
+        const size_t qsmem = (size_t)(UM + 256) * 128 * 2 + 64;
+        if (!qk_configured) {
+            cudaFuncSetAttribute(qk_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
+            cudaFuncSetAttribute(qk_tiles_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+            qk_configured = true;
+        }
+        int sms = 148;
+        {
+            int dev = 0;
+            cudaGetDevice(&dev);
+            cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        }
+        const int m_tiles = (g.M + UM - 1) / UM;
+        const int per_z = std::min(m_tiles, std::max(1, (2 * sms + nz - 1) / nz));
+        qk_tiles_kernel<<<dim3(per_z, nz), QK_THREADS, qsmem, st>>>(a);
+        CHROMO_CHECK_LAUNCH("qk_tiles");
+        return CHROMO_OK;
     }
     dim3 grid(g.N / a.NT, (g.M + UM - 1) / UM, nz);
     umma_linear_kernel<<<grid, UTHREADS, smem, st>>>(a);
