@@ -628,17 +628,22 @@ static_assert(C_COUNT * 8 + 8 <= 256, "control block");
 
 // timeline hook: traced threads of CTA (0,0) (dense issuer, one score warp, one value warp) append
 // (event id << 48 | clock64) to their own 512-entry lane of a.trace
+// (compiled out of the production instantiation: the test of `p` alone, made by every thread at every hand-off, was 7 % of
+// the kernel's issued warp instructions)
+template <bool ON>
 struct Tracer {
     long long* p; int n;
     __device__ __forceinline__ void operator()(int id) {
-        if (p && n < 512) { p[n++] = ((long long)id << 48) | (clock64() & 0xFFFFFFFFFFFFll); }
+        if (ON) {
+            if (p && n < 512) { p[n++] = ((long long)id << 48) | (clock64() & 0xFFFFFFFFFFFFll); }
+        }
     }
 };
 __device__ __forceinline__ void all_compute_barrier() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 // the four warps that share a TMEM lane quarter (the four column quarters of the same 32 rows)
 __device__ __forceinline__ void quarter_barrier(int lq) { asm volatile("bar.sync %0, 128;" ::"r"(4 + lq) : "memory"); }
 
-template <int SMAX>
+template <int SMAX, bool TRACE>
 __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const RegFusedArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_CTL);
@@ -717,7 +722,7 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             const uint32_t s_xb = smem_u32(smem + OFF_XB), s_att = smem_u32(smem + OFF_ATT);
             const uint64_t xd = umma_smem_desc(s_xb, 128, 2048), attd = umma_smem_desc(s_att, 128, 4096);
             const uint64_t stage_d = umma_smem_desc(smem_u32(smem + OFF_STAGE), 128, 2048);   // + st * 2048 per ring stage
-            Tracer tr{(a.trace && tile == 0 && z == 0) ? a.trace : nullptr, 0};
+            Tracer<TRACE> tr{(a.trace && tile == 0 && z == 0) ? a.trace : nullptr, 0};
             auto consume = [&](int c, uint64_t ad, uint32_t col, bool accumulate) {
                 const int st = c % RF_NSTAGE;
                 mbar_wait(&bars[C_FULL0 + st], (c / RF_NSTAGE) & 1);
@@ -841,7 +846,7 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
         uint8_t* sv = smem + OFF_V + ch * 8192;
         const uint32_t pb = trow + 256;
         // traced threads: warp 0 lane 0 (score warp, lane 1 of the buffer), warp 8 lane 0 (value warp, lane 2)
-        Tracer tr{(a.trace && tile == 0 && z == 0 && lane == 0 && (warp == 0 || warp == 8)) ? a.trace + (warp == 0 ? 512 : 1024) : nullptr, 0};
+        Tracer<TRACE> tr{(a.trace && tile == 0 && z == 0 && lane == 0 && (warp == 0 || warp == 8)) ? a.trace + (warp == 0 ? 512 : 1024) : nullptr, 0};
 
         for (int li = 0; li < a.n_layers; ++li) {
         const uint32_t lp = li & 1;
@@ -1274,9 +1279,11 @@ int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st) {
     if (!configured) {
         cudaError_t e1 = cudaFuncSetAttribute(reg_layer_cc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
         cudaError_t e2 = cudaFuncSetAttribute(reg_layer_cc_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
-        cudaError_t e3 = cudaFuncSetAttribute(reg_layer_fused_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
-        cudaError_t e4 = cudaFuncSetAttribute(reg_layer_fused_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
-        for (cudaError_t e : {e1, e2, e3, e4})
+        cudaError_t e3 = cudaFuncSetAttribute(reg_layer_fused_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaError_t e4 = cudaFuncSetAttribute(reg_layer_fused_kernel<17, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaError_t e5 = cudaFuncSetAttribute(reg_layer_fused_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaError_t e6 = cudaFuncSetAttribute(reg_layer_fused_kernel<17, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        for (cudaError_t e : {e1, e2, e3, e4, e5, e6})
             if (e != cudaSuccess) { set_error("reg_fused smem attribute: %s", cudaGetErrorString(e)); return CHROMO_ECUDA; }
         configured = true;
     }
@@ -1288,9 +1295,11 @@ int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st) {
     // probabilities, one layer per launch).
     const int tc = reg_fused_tensor_attention() ? 1 : 0;
     if (a.n_layers < 1 || (a.n_layers > 1 && !tc)) { set_error("reg_layer_fused: multi-layer launches need the tensor-pipe attention"); return CHROMO_EINVAL; }
-    if (a.S == 9 && tc) reg_layer_fused_kernel<9><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
+    if (a.S == 9 && tc && at.trace) reg_layer_fused_kernel<9, true><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
+    else if (a.S == 17 && tc && at.trace) reg_layer_fused_kernel<17, true><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
+    else if (a.S == 9 && tc) reg_layer_fused_kernel<9, false><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
     else if (a.S == 9) reg_layer_cc_kernel<9><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
-    else if (a.S == 17 && tc) reg_layer_fused_kernel<17><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
+    else if (a.S == 17 && tc) reg_layer_fused_kernel<17, false><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
     else if (a.S == 17) reg_layer_cc_kernel<17><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
     else { set_error("reg_layer_fused: tokens per gene must be 9 or 17"); return CHROMO_EINVAL; }
     CHROMO_CHECK_LAUNCH("reg_layer_fused");
