@@ -355,52 +355,63 @@ __global__ void __launch_bounds__(UTHREADS) umma_linear_kernel(const UmmaArgs a)
 
 // ---------------------------------------------------------------- the query GEMM of a single-query-attention stage ----
 // QK[m, (h, :)] = A[m / a_div, :] . M^T  (K = 128, N = 256 = two heads), written as the BF16 operand tiles sqa_fused pulls
-// in by TMA.  Persistent: a CTA keeps the 64 KB weight tile and its TMEM / barriers for all its row tiles (the one-tile
-// kernel above pays ~11 us of set-up and latency per tile: 137 us for 1185 tiles against 45 us of HBM time); two CTAs per
-// SM, so that one's staging / epilogue runs under the other's MMAs.  Per tile the 128 rows fill two consecutive 32 KB
-// operand tiles (row 2m + head): each is composed in the dead A operand and leaves as full lines.
-constexpr int QK_THREADS = 512;      // 16 warps: staging and epilogue are latency chains per warp (two CTAs x 16 warps x 64 registers)
-__global__ void __launch_bounds__(QK_THREADS, 2) qk_tiles_kernel(const UmmaArgs a) {
+// in by TMA (row 2m + head of 128-row tiles: the 128 rows of a step fill two consecutive 32 KB tiles).
+// Persistent and warp-specialised, one CTA per SM: the 64 KB weight tile, the barriers and all 512 TMEM columns (two
+// accumulators) live for the whole launch;
+//   warps 8..15  producers: FP32 rows -> BF16 canonical K-major A stage (two stages), all loads of a thread in flight
+//   warp 16      one thread issues the 8 tcgen05.mma (M = 128, N = 256) of a stage and commits them to the barriers
+//   warps 0..7   epilogue: accumulator (lane quarter = warp % 4, head = warp / 4) -> BF16 -> 16-byte chunks straight to HBM
+// so the staging of tile i+1 and the epilogue of tile i-1 run under the MMAs of tile i.  (The serial one-CTA-per-tile form
+// of this GEMM spent ~11 us per tile on set-up and barrier round trips: 1.4 TB/s of output; two such CTAs per SM with 16
+// warps each did not change that.)
+constexpr int QK_THREADS = 544;
+enum { QB_W = 0, QB_AFULL0, QB_AFREE0 = QB_AFULL0 + 2, QB_DFULL0 = QB_AFREE0 + 2, QB_DFREE0 = QB_DFULL0 + 2, QB_COUNT = QB_DFREE0 + 2 };
+__device__ __forceinline__ void qk_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__global__ void __launch_bounds__(QK_THREADS, 1) qk_tiles_kernel(const UmmaArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const GemmArgs& g = a.g;
     constexpr int K = 128, NT = 256, KC = K / 8;
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + UM * K * 2;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (UM + NT) * K * 2);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2);
+    uint8_t* sB = smem;                                   // 64 KB
+    uint8_t* sA = smem + NT * K * 2;                      // 2 x 32 KB
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + NT * K * 2 + 2 * UM * K * 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + QB_COUNT);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int z1 = blockIdx.y;
     const float* A = g.A + z1 * g.sA1;
     const __nv_bfloat16* Bp = a.Bp + z1 * g.sB1;
     uint8_t* out_z = reinterpret_cast<uint8_t*>(reinterpret_cast<__nv_bfloat16*>(g.C) + z1 * g.sC1);
 
-    if (warp == 0) tmem_alloc(tmem_slot, NT);
+    if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
-        mbar_init(&bars[0], 1);
-        mbar_init(&bars[1], 1);
+        mbar_init(&bars[QB_W], 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bars[QB_AFULL0 + i], 8);           // one arrival per producer warp
+            mbar_init(&bars[QB_AFREE0 + i], 1);           // tcgen05.commit
+            mbar_init(&bars[QB_DFULL0 + i], 1);           // tcgen05.commit
+            mbar_init(&bars[QB_DFREE0 + i], 8);           // one arrival per epilogue warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    if (tid == 0) {
-        mbar_expect_tx(&bars[0], NT * K * 2);
-        tma_bulk_g2s(sB, Bp, NT * K * 2, &bars[0]);
-    }
-    const int lq = warp & 3, ch = warp >> 2;
-    const uint32_t trow = tmem_base + ((uint32_t)(lq * 32) << 16);
-    const uint32_t idesc = umma_idesc_bf16(UM, NT);
     const int m_tiles = (g.M + UM - 1) / UM;
-    uint32_t it = 0;
-    for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
-        const int m0 = mt * UM;
-        // A: FP32 -> BF16 into the canonical K-major layout, all 16 loads of a thread in flight
-        {
-            float4 x[4][2];
+
+    if (warp >= 8 && warp < 16) {
+        // ================================================= producers ====
+        const int pw = warp - 8;
+        uint32_t it = 0;
+        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+            const int st = it & 1, m0 = mt * UM;
+            if (it >= 2) mbar_wait(&bars[QB_AFREE0 + st], ((it >> 1) - 1) & 1);
+            uint8_t* dst = sA + st * (UM * K * 2);
+            float4 x[8][2];
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int u = warp + q * 16;                      // 64 units: 16 row groups x 4 column groups
+            for (int q = 0; q < 8; ++q) {
+                const int u = pw + q * 8;                         // 64 units: 16 row groups x 4 column groups
                 const int r = (u & 15) * 8 + (lane >> 2), kc = (u >> 4) * 4 + (lane & 3);
                 const int m = m0 + r;
                 x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -411,65 +422,87 @@ __global__ void __launch_bounds__(QK_THREADS, 2) qk_tiles_kernel(const UmmaArgs 
                 }
             }
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const int u = warp + q * 16;
+            for (int q = 0; q < 8; ++q) {
+                const int u = pw + q * 8;
                 const int r = (u & 15) * 8 + (lane >> 2), kc = (u >> 4) * 4 + (lane & 3);
                 __nv_bfloat162 b0 = __floats2bfloat162_rn(x[q][0].x, x[q][0].y), b1 = __floats2bfloat162_rn(x[q][0].z, x[q][0].w);
                 __nv_bfloat162 b2 = __floats2bfloat162_rn(x[q][1].x, x[q][1].y), b3 = __floats2bfloat162_rn(x[q][1].z, x[q][1].w);
                 uint4 pk;
                 pk.x = *reinterpret_cast<uint32_t*>(&b0); pk.y = *reinterpret_cast<uint32_t*>(&b1);
                 pk.z = *reinterpret_cast<uint32_t*>(&b2); pk.w = *reinterpret_cast<uint32_t*>(&b3);
-                *reinterpret_cast<uint4*>(sA + ((size_t)(r >> 3) * KC + kc) * 128 + (r & 7) * 16) = pk;
+                *reinterpret_cast<uint4*>(dst + ((size_t)(r >> 3) * KC + kc) * 128 + (r & 7) * 16) = pk;
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) qk_arrive(&bars[QB_AFULL0 + st]);
+        }
+    } else if (warp == 16) {
+        // ================================================= MMA issuer ====
+        if (lane == 0) {
+            mbar_expect_tx(&bars[QB_W], NT * K * 2);
+            tma_bulk_g2s(sB, Bp, NT * K * 2, &bars[QB_W]);
+            const uint32_t idesc = umma_idesc_bf16(UM, NT);
+            const uint64_t bd = umma_smem_desc(smem_u32(sB), 128, K * 16);
+            mbar_wait(&bars[QB_W], 0);
+            uint32_t it = 0;
+            for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+                const int st = it & 1;
+                mbar_wait(&bars[QB_AFULL0 + st], (it >> 1) & 1);
+                if (it >= 2) mbar_wait(&bars[QB_DFREE0 + st], ((it >> 1) - 1) & 1);
+                tc_fence_after();
+                const uint64_t ad = umma_smem_desc(smem_u32(sA + st * (UM * K * 2)), 128, K * 16);
+#pragma unroll
+                for (int k = 0; k < K / 16; ++k) umma_bf16(tmem_base + 256 * st, ad + 16 * k, bd + 16 * k, idesc, k > 0 ? 1u : 0u);
+                umma_commit(&bars[QB_AFREE0 + st]);
+                umma_commit(&bars[QB_DFULL0 + st]);
             }
         }
-        fence_async_smem();
-        __syncthreads();
-        if (tid == 0) {
-            if (it == 0) mbar_wait(&bars[0], 0);
+    } else if (warp < 8) {
+        // ================================================= epilogue ====
+        const int lq = warp & 3, head = warp >> 2;
+        const int row = lq * 32 + lane;
+        const int r = (2 * row + head) & 127, t = row >> 6;
+        uint32_t it = 0;
+        for (int mt = blockIdx.x; mt < m_tiles; mt += gridDim.x, ++it) {
+            const int st = it & 1, m0 = mt * UM;
+            mbar_wait(&bars[QB_DFULL0 + st], (it >> 1) & 1);
             tc_fence_after();
-            const uint64_t ad = umma_smem_desc(smem_u32(sA), 128, K * 16), bd = umma_smem_desc(smem_u32(sB), 128, K * 16);
+            const uint32_t trow = tmem_base + 256 * st + 128 * head + ((uint32_t)(lq * 32) << 16);
+            const bool ok = m0 + row < g.M;
+            const bool tile_ok = 2 * m0 + 128 * t < 2 * g.M;     // (the second tile of the last step may not exist)
+            uint8_t* out = out_z + ((long long)mt * 2 + t) * 32768 + (r >> 3) * 2048 + (r & 7) * 16;
+            float v[32], w[32];
 #pragma unroll
-            for (int k = 0; k < K / 16; ++k) umma_bf16(tmem_base, ad + 16 * k, bd + 16 * k, idesc, k > 0 ? 1u : 0u);
-            umma_commit(&bars[1]);
-        }
-        __syncwarp();
-        mbar_wait(&bars[1], it & 1);
-        tc_fence_after();
-        const bool ok = m0 + lq * 32 + lane < g.M;
-        const int tiles = min(2, (2 * g.M - 2 * m0 + 127) / 128);
-        for (int t = 0; t < tiles; ++t) {
-            if ((lq >> 1) == t) {
-                float v[32];
-#pragma unroll 1
-                for (int c = ch * 32; c < NT; c += 128) {
-                    tmem_ld32(trow + c, v);
-                    const int head = c >> 7, kc0 = (c & 127) >> 3;
-                    const int r = 2 * ((lq & 1) * 32 + lane) + head;
-                    uint8_t* sp = sA + (r >> 3) * 2048 + (r & 7) * 16;
+            for (int c2 = 0; c2 < 2; ++c2) {
+                tmem_ld32_pair(trow + 64 * c2, v, trow + 64 * c2 + 32, w);
+                if (c2 == 1) {                                   // every load of this warp has landed: the accumulator may go
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) qk_arrive(&bars[QB_DFREE0 + st]);
+                }
+                if (tile_ok) {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 8) {
-                        uint4 pk = make_uint4(0u, 0u, 0u, 0u);
-                        if (ok) {
-                            __nv_bfloat162 p0 = __floats2bfloat162_rn(v[j], v[j + 1]), p1 = __floats2bfloat162_rn(v[j + 2], v[j + 3]);
-                            __nv_bfloat162 p2 = __floats2bfloat162_rn(v[j + 4], v[j + 5]), p3 = __floats2bfloat162_rn(v[j + 6], v[j + 7]);
-                            pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
-                            pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                    for (int hf = 0; hf < 2; ++hf) {
+                        const float* s = hf ? w : v;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            uint4 pk = make_uint4(0u, 0u, 0u, 0u);
+                            if (ok) {
+                                __nv_bfloat162 p0 = __floats2bfloat162_rn(s[j], s[j + 1]), p1 = __floats2bfloat162_rn(s[j + 2], s[j + 3]);
+                                __nv_bfloat162 p2 = __floats2bfloat162_rn(s[j + 4], s[j + 5]), p3 = __floats2bfloat162_rn(s[j + 6], s[j + 7]);
+                                pk.x = *reinterpret_cast<uint32_t*>(&p0); pk.y = *reinterpret_cast<uint32_t*>(&p1);
+                                pk.z = *reinterpret_cast<uint32_t*>(&p2); pk.w = *reinterpret_cast<uint32_t*>(&p3);
+                            }
+                            *reinterpret_cast<uint4*>(out + (8 * c2 + 4 * hf + (j >> 3)) * 128) = pk;
                         }
-                        *reinterpret_cast<uint4*>(sp + (kc0 + (j >> 3)) * 128) = pk;
                     }
                 }
             }
-            tc_fence_before();
-            __syncthreads();
-            uint4* out = reinterpret_cast<uint4*>(out_z + ((long long)mt * 2 + t) * 32768);
-#pragma unroll
-            for (int i = 0; i < 2048 / QK_THREADS; ++i) out[tid + i * QK_THREADS] = reinterpret_cast<const uint4*>(sA)[tid + i * QK_THREADS];
-            __syncthreads();
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem_base, NT);
+    if (warp == 0) tmem_dealloc(tmem_base, 512);
 }
 
 static size_t umma_smem_bytes(int nt, int K) {
@@ -525,7 +558,7 @@ int umma_launch(const GemmArgs& g, const __nv_bfloat16* Bp, int nz, cudaStream_t
     if (g.c_sqa_tiles && g.K == 128 && g.N == 256 && a.NT == 256 && g.zdiv == 1 && (g.M + UM - 1) / UM >= 8 &&
         !getenv("CHROMO_QK_ONE_TILE")) {
         static bool qk_configured = false;
-        const size_t qsmem = (size_t)(UM + 256) * 128 * 2 + 64;
+        const size_t qsmem = (size_t)(2 * UM + 256) * 128 * 2 + 128;
         if (!qk_configured) {
             cudaFuncSetAttribute(qk_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)qsmem);
             cudaFuncSetAttribute(qk_tiles_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
@@ -538,7 +571,7 @@ int umma_launch(const GemmArgs& g, const __nv_bfloat16* Bp, int nz, cudaStream_t
             cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         }
         const int m_tiles = (g.M + UM - 1) / UM;
-        const int per_z = std::min(m_tiles, std::max(1, (2 * sms + nz - 1) / nz));
+        const int per_z = std::min(m_tiles, std::max(1, sms / nz));
         qk_tiles_kernel<<<dim3(per_z, nz), QK_THREADS, qsmem, st>>>(a);
         CHROMO_CHECK_LAUNCH("qk_tiles");
         return CHROMO_OK;
