@@ -39,15 +39,6 @@ constexpr uint32_t TG_A_BYTES = 128 * TG_KCH * 2;
 constexpr int TG_UNR = 8;                      // 32-byte runs per thread in flight
 constexpr int STAGE_LD = 33;                   // padded row of the per-warp 32 x 32 epilogue staging tile
 
-// round half up on the integer pipe (tuning experiment: F2FP is a low-rate instruction)
-__device__ __forceinline__ uint32_t pack2_int(float lo, float hi) {
-    return __byte_perm(__float_as_uint(lo) + 0x8000u, __float_as_uint(hi) + 0x8000u, 0x7632);
-}
-__device__ __forceinline__ uint4 pack8_int(const float4& a, const float4& b) {
-    uint4 pk;
-    pk.x = pack2_int(a.x, a.y); pk.y = pack2_int(a.z, a.w); pk.z = pack2_int(b.x, b.y); pk.w = pack2_int(b.z, b.w);
-    return pk;
-}
 __device__ __forceinline__ uint4 pack8(const float4& a, const float4& b) {
     __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
     __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
@@ -114,7 +105,7 @@ __device__ __noinline__ void stage_operand_generic(uint8_t* dst, const float* __
 // two 16-byte loads, four conversions and one 16-byte store per run - all loads ahead of the first conversion.
 __device__ __forceinline__ void stage_operand(uint8_t* dst, const float* __restrict__ src, long long ld, int mn_major, int div,
                                               int rows, int mn0, int mn_lim, int kc0, int kc_lim, bool vec, int warp,
-                                              int lane, int dbg = 0) {
+                                              int lane) {
     const int rg_n = (rows + 31) >> 5;
     if (div != 1 || (mn_major && (TG_WARPS % rg_n) != 0)) {
         stage_operand_generic(dst, src, ld, mn_major, div, rows, mn0, mn_lim, kc0, kc_lim, vec, warp, lane);
@@ -139,8 +130,6 @@ __device__ __forceinline__ void stage_operand(uint8_t* dst, const float* __restr
         nvalid = mn_lim - (mn0 + r8 * 8);
     }
     nvalid = nvalid < 0 ? 0 : (nvalid > 8 ? 8 : nvalid);
-    if (dbg & 1) ilim = 0;
-    if (dbg & 2) nq = 0;
     const bool full = vec && nvalid == 8;
     for (int q0 = 0; q0 < nq; q0 += TG_UNR) {
         float4 x[TG_UNR][2];
@@ -163,15 +152,9 @@ __device__ __forceinline__ void stage_operand(uint8_t* dst, const float* __restr
                 if (q < nq && idx + q * istride < ilim && nvalid > 0) load8(p + q * pstride, nvalid, false, x[j][0], x[j][1]);
             }
         }
-        if (dbg & 4) {
 #pragma unroll
-            for (int j = 0; j < TG_UNR; ++j)
-                if (q0 + j < nq) *reinterpret_cast<uint4*>(dst + off + (uint32_t)(q0 + j) * ostride) = pack8_int(x[j][0], x[j][1]);
-        } else {
-#pragma unroll
-            for (int j = 0; j < TG_UNR; ++j)
-                if (q0 + j < nq) *reinterpret_cast<uint4*>(dst + off + (uint32_t)(q0 + j) * ostride) = pack8(x[j][0], x[j][1]);
-        }
+        for (int j = 0; j < TG_UNR; ++j)
+            if (q0 + j < nq) *reinterpret_cast<uint4*>(dst + off + (uint32_t)(q0 + j) * ostride) = pack8(x[j][0], x[j][1]);
     }
 }
 
@@ -181,7 +164,6 @@ struct Operands {
     int Kc, NT;                 // contraction range [k_begin, Kc)
     int k_begin = 0;
     int pdl = 0;                // launched as a programmatic dependent: griddepcontrol.wait before the first A access
-    int dbg = 0;                // tuning experiments (CHROMO_TG_DBG): 1 = no loads, 2 = no conversion / stores
 };
 
 // The contraction of one output tile into TMEM columns [0, NT).  `g` counts the chunks this CTA has pushed through the
@@ -199,10 +181,10 @@ __device__ __forceinline__ void contract_tile(const Operands& o, uint8_t* smem, 
         const int kc0 = o.k_begin + ci * TG_KCH;
         // B first: in tc_gemm_kernel it is a parameter / position table, independent of the kernel in front, so its staging
         // (like everything above) runs under that kernel's tail; A is the first dependent access (programmatic dependent launch)
-        stage_operand(sB, o.B, o.ldb, o.b_t, o.b_div, o.NT, o.n0, o.n_lim, kc0, o.Kc, o.b_vec, warp, lane, o.dbg);
+        stage_operand(sB, o.B, o.ldb, o.b_t, o.b_div, o.NT, o.n0, o.n_lim, kc0, o.Kc, o.b_vec, warp, lane);
         if (ci == 0 && trace && tid == 0) trace[2] = clock64();
         if (ci == 0 && o.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");
-        stage_operand(sA, o.A, o.lda, o.a_t, o.a_div, 128, o.m0, o.m_lim, kc0, o.Kc, o.a_vec, warp, lane, o.dbg);
+        stage_operand(sA, o.A, o.lda, o.a_t, o.a_div, 128, o.m0, o.m_lim, kc0, o.Kc, o.a_vec, warp, lane);
         if (ci == 0 && trace && tid == 0) trace[3] = clock64();
         fence_async_smem();
         __syncthreads();
@@ -283,7 +265,7 @@ __device__ __forceinline__ void add_tile_f32(float* stage, const float* v, float
 
 #define TG_MARK(i) do { if (trace && tid == 0) trace[i] = clock64(); } while (0)
 
-__global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a, long long* trace_buf, int dbg) {
+__global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a, long long* trace_buf) {
     extern __shared__ __align__(1024) uint8_t smem[];
     asm volatile("griddepcontrol.launch_dependents;");     // the next kernel of the chain may start its own prologue
     long long* trace = (trace_buf && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) ? trace_buf : nullptr;
@@ -314,7 +296,7 @@ __global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a, lon
     o.B = a.B + z * a.b_z; o.ldb = a.ldb; o.b_t = a.b_t; o.b_div = a.b_div; o.n0 = n0; o.n_lim = a.N;
     o.a_vec = ((reinterpret_cast<uintptr_t>(o.A) & 15) == 0 && (a.lda & 3) == 0) ? 1 : 0;
     o.b_vec = ((reinterpret_cast<uintptr_t>(o.B) & 15) == 0 && (a.ldb & 3) == 0) ? 1 : 0;
-    o.Kc = a.Kc; o.NT = NT; o.dbg = dbg; o.pdl = 1;
+    o.Kc = a.Kc; o.NT = NT; o.pdl = 1;
     if (a.ksplit > 1) {
         const int per = ((a.Kc + TG_KCH - 1) / TG_KCH + a.ksplit - 1) / a.ksplit * TG_KCH;
         o.k_begin = split * per;
@@ -415,13 +397,6 @@ __global__ void __launch_bounds__(TG_THREADS) tc_gemm_kernel(const TcGemm a, lon
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (j < ncols) atomicAdd(out + j, v[j]);
-                }
-            } else if (dbg & 8) {
-                if (ok) {
-                    float* out = C + crow * a.ldc + n0 + c;
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4)
-                        if (j < ncols) *reinterpret_cast<float4*>(out + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
             } else {
                 store_tile_f32(stage, v, C, crow, a.ldc, n0 + c, ncols, lane, rowmask);
@@ -604,7 +579,6 @@ int tc_gemm_launch(const TcGemm& in, int nz, cudaStream_t st) {
         }
     }
     dim3 grid(a.N / a.NT, (a.M + 127) / 128, nz * a.ksplit);
-    const char* dbg = getenv("CHROMO_TG_DBG");
     {
         static const bool no_pdl = getenv("CHROMO_NO_PDL") != nullptr;
         cudaLaunchConfig_t cfg = {};
@@ -614,8 +588,7 @@ int tc_gemm_launch(const TcGemm& in, int nz, cudaStream_t st) {
         attr[0].val.programmaticStreamSerializationAllowed = no_pdl ? 0 : 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
         long long* tb = g_tg_trace ? g_tg_trace + 2048 : nullptr;
-        const int dbgv = dbg ? atoi(dbg) : 0;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel, a, tb, dbgv);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, tc_gemm_kernel, a, tb);
         if (e != cudaSuccess) { set_error("tc_gemm launch: %s", cudaGetErrorString(e)); return CHROMO_ECUDA; }
     }
     CHROMO_CHECK_LAUNCH("tc_gemm");
