@@ -122,6 +122,7 @@ struct WsLayout {
     int64_t tail_stream;    // packed weight streams of the fused Embedding/Pairwise tails (float offset)
     int tail_fused;         // 1 when the fused row-tail kernel applies
     int reg_fused;          // 1 when the fused Regulation-layer kernel applies to this configuration
+    int64_t rg_plan;        // ragged plan of the batch (ragged.cu; float offset, 0 = none)
     // backward scratch (training only)
     int64_t g_base;
     int64_t total;

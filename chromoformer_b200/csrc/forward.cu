@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "gemm_simt.cuh"
 #include "kernels.cuh"
+#include "ragged.cuh"
 #include "reg_fused.cuh"
 #include "sqa_fused.cuh"
 #include "gemm_dispatch.cuh"
@@ -798,7 +799,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     // fused single-query attention core (sqa_fused.cu): all resolutions of a stage in one launch
     auto sqa_fused = [&](int regions, int H, const float* const* x, const uint8_t* const* mask, const int64_t* mstride,
                          const int64_t* moff, int64_t w_in, long long w_in_z, int stage, int dm, float* qk, float* qkt,
-                         float* cbar, bool cbar_bf16, bool probe, bool have_tiles, bool* done) -> int {
+                         float* cbar, bool cbar_bf16, bool probe, bool have_tiles, bool* done, const RaggedPlan* rp = nullptr) -> int {
         *done = false;
         if (!fold) return CHROMO_OK;
         SqaFusedArgs f;
@@ -816,6 +817,10 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         if (cbar_bf16) f.cbar_bf16 = reinterpret_cast<__nv_bfloat16*>(cbar);   // same buffer, BF16 rows (the fused tail reads them)
         f.w_in = P + w_in; f.w_in_z = w_in_z;
         f.scale = 1.f / sqrtf((float)(dm / H));
+        if (rp) {
+            f.perm = rp->perm; f.live = rp->live;
+            for (int r = 0; r < NR; ++r) { f.tile_k0[r] = rp->tile_k0[r]; f.tile_ns[r] = rp->tile_ns[r]; }
+        }
         if (!sqa_fused_supported(f, H, F, D)) return CHROMO_OK;
         *done = true;
         if (probe) return CHROMO_OK;
@@ -834,8 +839,35 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             t.c_sqa_tiles = 1; t.C = qkt; t.sC1 = 2 * RS;
             if (umma_supported(t)) { *tiles = true; return lin(t, NR); }
         }
+        if (g.a_rows || g.m_dev) { set_error("internal: ragged plan without the persistent query GEMM"); return CHROMO_EINVAL; }
         return lin(g, NR);
     };
+    // Ragged plan (ragged.cu): the Pairwise stage runs over the live pCRE slots only, sorted by valid length, each tile
+    // of the attention over its own key window.  Needs the fused kernels of the stage (they take the row maps).
+    RaggedPlan plan;
+    RaggedArgs ra;
+    bool ragged = false;
+    cudaStream_t plan_stream = st;
+    if (tail && w.rg_plan && c->pw_layers > 0 && c->pw_heads * D == 256 && D == 128 && (R + 127) / 128 >= 8 && !getenv("CHROMO_NO_RAGGED") &&
+        !getenv("CHROMO_QK_FP32") && !getenv("CHROMO_QK_ONE_TILE")) {
+        bool ok = false;
+        CHROMO_TRY(sqa_fused(R, c->pw_heads, in->x_pcre, in->mask_pcre, in->mask_pcre_stride, in->mask_pcre_row_offset,
+                             L.pw[0].lin_proj_pcre, L.pw_stride, 1, c->pw_d_model, ws + w.p_qk, ws + w.p_qkt, ws + w.p_cbar, cb16, true, false, &ok));
+        if (ok) {
+            ra.B = B; ra.I = I; ra.n_res = NR;
+            for (int r = 0; r < NR; ++r) {
+                ra.n[r] = c->n_bins[r]; ra.ns[r] = c->n_bins[r] <= 32 ? 32 : c->n_bins[r];
+                ra.mask[r] = in->mask_pcre[r]; ra.mask_stride[r] = in->mask_pcre_stride[r]; ra.mask_row_offset[r] = in->mask_pcre_row_offset[r];
+                ra.imask[r] = in->imask[r];
+            }
+            ra.xin = ws + w.r_xin; ra.xin_z = RS;
+            // on a side stream next to the Embedding stage: forked here, launched behind that stage's kernels (which then
+            // come first for the block scheduler; the plan's small latency-bound kernels fill the room they leave), joined
+            // in front of the Pairwise stage
+            CHROMO_TRY(aux_fork(st, &plan_stream));
+            ragged = true;
+        }
+    }
     bool e_fused = false, e_tiles = false;
     CHROMO_TRY(sqa_fused(B, c->embed_heads, in->x_p, in->mask_p, in->mask_p_stride, in->mask_p_row_offset,
                          L.embed[0].lin_proj, L.embed_stride, 0, dme, ws + w.e_qk, ws + w.e_qkt, ws + w.e_cbar, cb16, true, false,
@@ -939,6 +971,11 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         g.M = B; g.N = D; g.K = D;
         CHROMO_TRY(lin(g, NR));
     }
+    if (ragged) {
+        CHROMO_TRY(build_ragged_plan(ra, ws + w.rg_plan, &plan, plan_stream));
+        CHROMO_TRY(aux_join(st, plan_stream));
+    }
+    const RaggedPlan* rp = ragged ? &plan : nullptr;
     for (int l = 0; l < c->pw_layers; ++l) {
         const AttnOff& pa = L.pw[0].att[l];
         const FfnOff& pf = L.pw[0].ffn[l];
@@ -956,6 +993,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             g.B = ws + w.fold_f32 + w.fold_slot[1 + l]; g.ldb = D; g.sB1 = w.fold_stride;
             g.C = ws + w.p_qk + so; g.ldc = Hp * D; g.sC1 = RS;
             g.M = R; g.N = Hp * D; g.K = D;
+            if (rp) { g.m_dev = rp->live; g.a_rows = l == 0 ? rp->perm : nullptr; }   // (later layers read the compacted rows)
             CHROMO_TRY(qk_gemm(g, ws + w.p_qkt + so, p_fused, &p_tiles));
         } else {      // Q = P_l W_q^T                             modules.py:159
             GemmArgs g = gemm_args();
@@ -967,7 +1005,8 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
         }
         CHROMO_TRY(sqa_fused(R, Hp, in->x_pcre, in->mask_pcre, in->mask_pcre_stride, in->mask_pcre_row_offset,
                              L.pw[0].lin_proj_pcre, L.pw_stride, 1, dmp, ws + w.p_qk + so, ws + w.p_qkt + so, ws + w.p_cbar + so,
-                             cb16, false, p_tiles, &p_fused));
+                             cb16, false, p_tiles, &p_fused, rp));
+        if (rp && !(p_fused && p_tiles)) { set_error("internal: ragged plan without the fused single-query attention"); return CHROMO_EINVAL; }
         ResStreams prs;
         if (!p_fused) CHROMO_TRY(res_fork(st, NR, prs));
         for (int r = 0; r < NR && !p_fused; ++r) {
@@ -1002,6 +1041,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             t.wstream = reinterpret_cast<const __nv_bfloat16*>(ws + w.tail_stream) + (1 + l) * TAIL_SLOT_ELEMS; t.w_z = tail_z;
             t.bo = P + pa.ffb; t.ln1w = P + pa.lnw; t.ln1b = P + pa.lnb; t.b1 = P + pf.l1b; t.b2 = P + pf.l2b;
             t.ln2w = P + pf.lnw; t.ln2b = P + pf.lnb; t.p_z = L.pw_stride;
+            if (rp) { t.m_dev = rp->live; t.res_rows = l == 0 ? rp->perm : nullptr; t.y_rows = last ? rp->y_rows : nullptr; }
             CHROMO_TRY(launch_row_tail_fused(t, NR, st));
             continue;
         }

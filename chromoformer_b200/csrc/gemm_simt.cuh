@@ -43,6 +43,9 @@ struct GemmArgs {
     int c_sqa_tiles;                           // tensor path only: C [M, 256] = QK of (region m, head n / 128) written as the
                                                //   BF16 operand tiles of sqa_fused (row 2m + head, 128-row tiles in the
                                                //   canonical K-major layout); sC1 in BF16 elements
+    // ragged plan (query GEMM of a pairwise stage, qk_tiles_kernel only): row m reads A row a_rows[m] / a_div, and only
+    // the first *m_dev rows exist (both device pointers, nullptr = off)
+    const int* a_rows; const int* m_dev;
 };
 
 static inline GemmArgs gemm_args() {

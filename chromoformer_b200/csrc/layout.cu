@@ -10,6 +10,7 @@
 #include <algorithm>
 
 #include "common.cuh"
+#include "ragged.cuh"
 #include "reg_fused.cuh"
 #include "train_gemm.cuh"
 
@@ -290,6 +291,7 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
     }
     w.h_z = take((int64_t)B * c->n_res * D);
     w.h_h1 = take((int64_t)B * c->d_head);
+    if (w.tail_fused) w.rg_plan = take(ragged_plan_floats(B, I, c->n_res));
     w.g_base = cur;
     if (w.training) {
         // backward scratch, carved up in backward.cu: every gradient tensor of every layer has its own buffer (the

@@ -38,6 +38,9 @@ struct RowTailArgs {
     const __nv_bfloat16* wstream; long long w_z;
     const float* bo; const float* ln1w; const float* ln1b; const float* b1; const float* b2;
     const float* ln2w; const float* ln2b; long long p_z;
+    // ragged plan (device pointers, nullptr = off): only the first *m_dev rows exist; row m takes its residual from row
+    // res_rows[m] / res_div and writes output row y_rows[m] (instead of the c_div / c_mul / c_add map)
+    const int* m_dev = nullptr; const int* res_rows = nullptr; const int* y_rows = nullptr;
 };
 struct TailStreamArgs {
     const float* nfold; long long nfold_z;  // folded out-projection N [128, 256] FP32

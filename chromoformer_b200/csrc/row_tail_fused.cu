@@ -58,7 +58,8 @@ __global__ void __maxnreg__(96) row_tail_fused_kernel(const RowTailArgs a) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int z = blockIdx.y;
     const int m0 = blockIdx.x * 128;
-    const int rows_valid = min(128, a.M - m0);
+    const int rows_valid = min(128, (a.m_dev ? *a.m_dev : a.M) - m0);
+    if (rows_valid <= 0) return;                              // ragged plan: a tile past the live rows
     const int nff = a.dff / 128;                              // 1 or 2 chunks per FFN matrix
 
     if (warp == 0) tmem_alloc(tmem_slot, RT_TMEM_COLS);
@@ -189,7 +190,7 @@ __global__ void __maxnreg__(96) row_tail_fused_kernel(const RowTailArgs a) {
         float u_keep[2][32];
         {
             // residual rows first: their (row-strided) loads overlap the out-projection MMA
-            const float* res = a.res + z * a.res_z + (valid ? (long long)(m / a.res_div) * 128 : 0);
+            const float* res = a.res + z * a.res_z + (valid ? (long long)((a.res_rows ? a.res_rows[m] : m) / a.res_div) * 128 : 0);
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci) {
                 const int c = (2 * ci + ch) * 32;
@@ -316,7 +317,8 @@ __global__ void __maxnreg__(96) row_tail_fused_kernel(const RowTailArgs a) {
                     const int trw = lq * 32 + r;
                     if (trw < rows_valid) {
                         const int mm = m0 + trw;
-                        const long long yrow = (long long)(mm / a.c_div) * a.c_mul + (mm % a.c_div) + a.c_add;
+                        const long long yrow = a.y_rows ? (long long)a.y_rows[mm]
+                                                        : (long long)(mm / a.c_div) * a.c_mul + (mm % a.c_div) + a.c_add;
                         *reinterpret_cast<float4*>(Y + yrow * 128 + c + cq) = make_float4(sp[0], sp[1], sp[2], sp[3]);
                     }
                 }

@@ -144,7 +144,7 @@ __device__ __forceinline__ void cp_async_wait0() { asm volatile("cp.async.wait_g
 // key-chunk split of a table of ns keys (ns % 16 == 0): CA chunks for the first half (even, >= half), rest second
 __device__ __forceinline__ int first_half_chunks(int ns) { return ((ns >> 4) + 1) & ~1; }
 
-__global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFusedArgs a, int tiles_per_res, float tau) {
+__global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const __grid_constant__ SqaFusedArgs a, int tiles_per_res, float tau) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_CTL);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + B_COUNT);
@@ -165,8 +165,9 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
+    if (a.live) tiles_per_res = a.live[1];                    // ragged plan: the live tiles only
     const int total = tiles_per_res * a.n_res;
-    const int rows_total = a.regions * 2;
+    const int rows_total = (a.live ? a.live[0] : a.regions) * 2;
 
     if (warp == 8) {
         // ===================================================== driver: table loads + MMA issue ====
@@ -177,12 +178,14 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
             uint32_t pe_par = 0;
             for (int g = blockIdx.x; g < total; g += gridDim.x, ++it) {
                 const int res = a.order[g / tiles_per_res];
-                const int ns = a.ns[res];
+                // key window of the tile: keys [k0, k0 + ns) of the table (the whole table without a ragged plan)
+                const int k0 = a.tile_k0[res] ? a.tile_k0[res][g % tiles_per_res] : 0;
+                const int ns = a.tile_ns[res] ? a.tile_ns[res][g % tiles_per_res] : a.ns[res];
                 const int CA = first_half_chunks(ns), CB = (ns >> 3) - CA;
                 if (res != cur) {
                     if (it > 0) mbar_wait(&bars[B_O], (it - 1) & 1);               // MMA 2 of the last tile is done with the table
-                    mbar_expect_tx(&bars[B_PE], (uint32_t)ns * 256u + 4096u);
-                    tma_bulk_g2s(smem + OFF_PE, a.pe_pk[res], (uint32_t)ns * 256u, &bars[B_PE]);
+                    mbar_expect_tx(&bars[B_PE], (uint32_t)a.ns[res] * 256u + 4096u);
+                    tma_bulk_g2s(smem + OFF_PE, a.pe_pk[res], (uint32_t)a.ns[res] * 256u, &bars[B_PE]);
                     tma_bulk_g2s(smem + OFF_WB, a.w_in_pk + res * a.w_in_pk_z, 4096u, &bars[B_PE]);
                     mbar_wait(&bars[B_PE], pe_par);
                     pe_par ^= 1;
@@ -201,7 +204,7 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
                 for (int n0 = 0; n0 < ns; n0 += 256) {                             // S = QK PE^T, N in parts of <= 256
                     const int np = min(256, ns - n0);
                     const uint32_t idesc = umma_idesc_bf16(128, np);
-                    const uint64_t pd = umma_smem_desc(s_pe + (n0 >> 3) * 2048, 128, 2048);
+                    const uint64_t pd = umma_smem_desc(s_pe + ((k0 + n0) >> 3) * 2048, 128, 2048);
 #pragma unroll
                     for (int k = 0; k < 8; ++k)
                         umma_bf16(tmem + n0, qd + 16 * k, pd + 16 * k, idesc, k > 0 ? 1u : 0u);
@@ -226,13 +229,13 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
                 if (CB > 0) {
                     mbar_wait(&bars[B_PB], it & 1);
                     tc_fence_after();
-                    const uint64_t ob = umma_smem_desc(s_pe + (CA / 2) * 4096, 2048, 128);
+                    const uint64_t ob = umma_smem_desc(s_pe + (k0 >> 3) * 2048 + (CA / 2) * 4096, 2048, 128);
                     for (int k = 0; k < CB / 2; ++k)
                         umma_bf16_ts(tmem + OB_COL, tmem + P_B_COL + 8 * k, ob + 256 * k, idesc_o, k > 0 ? 1u : 0u);
                 }
                 mbar_wait(&bars[B_PA], it & 1);
                 tc_fence_after();
-                const uint64_t oa = umma_smem_desc(s_pe, 2048, 128);
+                const uint64_t oa = umma_smem_desc(s_pe + (k0 >> 3) * 2048, 2048, 128);
                 for (int k = 0; k < CA / 2; ++k)
                     umma_bf16_ts(tmem + OA_COL, tmem + 8 * k, oa + 256 * k, idesc_o, k > 0 ? 1u : 0u);
                 umma_commit(&bars[B_O]);
@@ -255,34 +258,42 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
         int it = 0;
         for (int g = blockIdx.x; g < total; g += gridDim.x, ++it) {
             const int res = a.order[g / tiles_per_res], tile = g % tiles_per_res;
-            const int n = a.n[res], ns = a.ns[res];
+            // key window [k0, k0 + ns) of the tile; n, nF, X and MK are relative to its first key
+            const int k0 = a.tile_k0[res] ? a.tile_k0[res][tile] : 0;
+            const int ns = a.tile_ns[res] ? a.tile_ns[res][tile] : a.ns[res];
+            const int n = a.n[res] - k0;
             const int CA = first_half_chunks(ns), CB = (ns >> 3) - CA;
             const int row0 = tile * 128;
             const int rows_valid = min(128, rows_total - row0);
             const int region0 = row0 >> 1;
-            const float* X = a.x[res];
-            const uint8_t* MK = a.mask[res] + a.mask_row_offset[res];
+            const float* X = a.x[res] + k0 * SQ_F;
+            const uint8_t* MK = a.mask[res] + a.mask_row_offset[res] + k0;
             const long long mstride = a.mask_stride[res];
             const float* W = a.w_in + res * a.w_in_z;
             const int c_begin = half ? CA : 0, c_cnt = half ? CB : CA;
             const int nF = n * SQ_F;
+            const long long rstride = (long long)a.n[res] * SQ_F;     // floats between regions
 
             // ring: chunk idx of this half (8 keys x 7 features per region, and the 8 mask bytes).  Copy plan: the 16
             // threads ht/16*16.. move the fourteen 16-byte parts of ONE 224-byte chunk row (contiguous in HBM), regions
             // ht/16 + 8k for k = 0..7; x_row_off(r0 + 8k) = x_row_off(r0) + 1792 k + 16 (k & 1) + 32 (k >> 1).
             const int fr0 = ht >> 4, fpart = ht & 15;
             const bool fact = fpart < 14;
-            const float* fsrc = X + (long long)(region0 + fr0) * nF + fpart * 4;
-            const long long fstep = 8LL * nF;
+            uint32_t fsrc[8];                                  // the thread's eight region rows (permuted under a ragged plan),
+#pragma unroll                                                 // in float4 units from X (n % 4 == 0)
+            for (int k = 0; k < 8; ++k) {
+                const int rr = region0 + fr0 + 8 * k;
+                const bool rv = 2 * (fr0 + 8 * k) < rows_valid;
+                fsrc[k] = (uint32_t)(((long long)(rv ? (a.perm ? a.perm[rr] : rr) : 0) * rstride) >> 2) + fpart;
+            }
             const uint32_t fdst = s_ring + half * SQ_HALF_X + x_row_off(fr0) + fpart * 16;
             const int mreg = ht >> 1, modd = ht & 1;
             const bool mvalid = 2 * mreg < rows_valid;
-            const uint8_t* msrc = MK + (long long)(region0 + (mvalid ? mreg : 0)) * mstride + modd * 4;
+            const uint8_t* msrc = MK + (long long)(mvalid ? (a.perm ? a.perm[region0 + mreg] : region0 + mreg) : 0) * mstride + modd * 4;
             const uint32_t mdst = s_ring + SQ_STAGE_X + half * 512 + mreg * 8 + modd * 4;
             auto fetch = [&](int idx, int stage) {
                 if (idx < c_cnt) {
                     const int cg = c_begin + idx;
-                    const float* src = fsrc + cg * SQ_XROW;
                     const uint32_t so = stage * SQ_STAGE;
                     const bool full = cg * 8 + 8 <= n;         // (uniform) every key of the chunk exists
                     const bool pok = fact && (full || cg * SQ_XROW + fpart * 4 + 3 < nF);
@@ -290,7 +301,7 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const SqaFused
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const bool ok = pok && 2 * (fr0 + 8 * k) < rows_valid;
-                            cp_async16(fdst + so + k * 1792 + 16 * (k & 1) + 32 * (k >> 1), ok ? src + k * fstep : X, ok);
+                            cp_async16(fdst + so + k * 1792 + 16 * (k & 1) + 32 * (k >> 1), ok ? reinterpret_cast<const float4*>(X) + fsrc[k] + cg * (SQ_XROW / 4) : reinterpret_cast<const float4*>(X), ok);
                         }
                     }
                     const bool okm = mvalid && (full || cg * 8 + modd * 4 < n);

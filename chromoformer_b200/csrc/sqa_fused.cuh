@@ -23,6 +23,13 @@ struct SqaFusedArgs {
     float scale;
     float* cbar; long long cbar_z;            // [regions*2, 128]  sum_j p_j (W_in x_j + PE_j)
     __nv_bfloat16* cbar_bf16 = nullptr;       // set: the result is written here in BF16 instead (dense rows; resolution stride 2 * cbar_z elements)
+    // ragged plan (ragged.cu), all optional: tile row 2m + head belongs to region perm[m]; only the first live[0] rows /
+    // live[1] tiles exist; tile t of resolution r walks the keys [tile_k0[r][t], + tile_ns[r][t]) (a multiple of 8 / of 16):
+    // every key outside that window is masked for all 64 regions of the tile
+    const int* perm = nullptr;
+    const int* live = nullptr;
+    const int* tile_k0[CHROMO_MAX_RES] = {};
+    const int* tile_ns[CHROMO_MAX_RES] = {};
 };
 
 int sqa_pack_qk(const float* qk, long long qk_z, __nv_bfloat16* tiles, long long tz, int rows, int n_res, cudaStream_t st);

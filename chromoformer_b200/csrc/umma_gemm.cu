@@ -398,7 +398,8 @@ __global__ void __launch_bounds__(QK_THREADS, 1) qk_tiles_kernel(const UmmaArgs 
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const int m_tiles = (g.M + UM - 1) / UM;
+    const int M = g.m_dev ? *g.m_dev : g.M;               // ragged plan: the live rows only
+    const int m_tiles = (M + UM - 1) / UM;
 
     if (warp >= 8 && warp < 16) {
         // ================================================= producers ====
@@ -415,8 +416,8 @@ __global__ void __launch_bounds__(QK_THREADS, 1) qk_tiles_kernel(const UmmaArgs 
                 const int r = (u & 15) * 8 + (lane >> 2), kc = (u >> 4) * 4 + (lane & 3);
                 const int m = m0 + r;
                 x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (m < g.M) {
-                    const float* p = A + (long long)(m / g.a_div) * g.lda + kc * 8;
+                if (m < M) {
+                    const float* p = A + (long long)((g.a_rows ? g.a_rows[m] : m) / g.a_div) * g.lda + kc * 8;
                     x[q][0] = __ldg(reinterpret_cast<const float4*>(p));
                     x[q][1] = __ldg(reinterpret_cast<const float4*>(p + 4));
                 }
@@ -468,8 +469,8 @@ __global__ void __launch_bounds__(QK_THREADS, 1) qk_tiles_kernel(const UmmaArgs 
             mbar_wait(&bars[QB_DFULL0 + st], (it >> 1) & 1);
             tc_fence_after();
             const uint32_t trow = tmem_base + 256 * st + 128 * head + ((uint32_t)(lq * 32) << 16);
-            const bool ok = m0 + row < g.M;
-            const bool tile_ok = 2 * m0 + 128 * t < 2 * g.M;     // (the second tile of the last step may not exist)
+            const bool ok = m0 + row < M;
+            const bool tile_ok = 2 * m0 + 128 * t < 2 * M;       // (the second tile of the last step may not exist)
             uint8_t* out = out_z + ((long long)mt * 2 + t) * 32768 + (r >> 3) * 2048 + (r & 7) * 16;
             float v[32], w[32];
 #pragma unroll
@@ -537,6 +538,11 @@ bool umma_supported(const GemmArgs& g) {
     return true;
 }
 
+// the persistent query GEMM (qk_tiles_kernel) takes this call: the only GEMM that honours a ragged plan
+bool umma_qk_persistent(const GemmArgs& g) {
+    return g.c_sqa_tiles && g.K == 128 && g.N == 256 && g.zdiv == 1 && (g.M + UM - 1) / UM >= 8 && !getenv("CHROMO_QK_ONE_TILE");
+}
+
 int umma_launch(const GemmArgs& g, const __nv_bfloat16* Bp, int nz, cudaStream_t st) {
     static int direct = -1;
     if (direct < 0) {
@@ -555,8 +561,9 @@ int umma_launch(const GemmArgs& g, const __nv_bfloat16* Bp, int nz, cudaStream_t
         if (e != cudaSuccess) { set_error("umma smem attribute: %s", cudaGetErrorString(e)); return CHROMO_ECUDA; }
         configured = UMMA_SMEM_MAX;
     }
-    if (g.c_sqa_tiles && g.K == 128 && g.N == 256 && a.NT == 256 && g.zdiv == 1 && (g.M + UM - 1) / UM >= 8 &&
-        !getenv("CHROMO_QK_ONE_TILE")) {
+    const bool qk_persistent = umma_qk_persistent(g);
+    if ((g.a_rows || g.m_dev) && !qk_persistent) { set_error("internal: ragged plan on a GEMM that does not take it"); return CHROMO_EINVAL; }
+    if (qk_persistent) {
         static bool qk_configured = false;
         const size_t qsmem = (size_t)(2 * UM + 256) * 128 * 2 + 128;
         if (!qk_configured) {

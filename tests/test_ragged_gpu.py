@@ -1,0 +1,115 @@
+"""Ragged plan of the BF16 inference path (csrc/ragged.cu): dead pCRE slots and padded bins are not computed.
+
+The plan only uses what the masks themselves guarantee (data.py:156-203: centred valid spans, dummy slots behind a
+block-form interaction mask), so its results must agree with the CPU oracle - which computes every slot and every bin as
+the reference does - within the BF16 tolerance, and with the same kernels run without the plan (CHROMO_NO_RAGGED=1) to
+rounding noise.  The adversarial cases are the ones where an elimination would be WRONG if the plan trusted the data
+layout instead of the masks."""
+import os
+
+import pytest
+import torch
+
+from _util import KWS
+from chromoformer_b200 import ChromoformerClassifier, synthetic
+from chromoformer_b200.engine import InferenceEngine
+from oracle import chromoformer_oracle as oracle
+
+pytestmark = pytest.mark.gpu
+BF16_TOL = 1e-2
+
+
+def _mk(seed=123):
+    return ChromoformerClassifier(7, 128, 128, dict(KWS[0]), dict(KWS[1]), dict(KWS[2]), seed=seed)
+
+
+def _oracle_logits(sd, batch, idx):
+    part = {}
+    for key, v in batch.items():
+        part[key] = {b: t[idx] for b, t in v.items()} if isinstance(v, dict) else v[idx]
+    part = synthetic.expand_full_masks(part)
+    with torch.no_grad():
+        return oracle.chromoformer_forward(sd, *synthetic.forward_args(part))
+
+
+def _run(model, batch, ragged):
+    if ragged:
+        os.environ.pop("CHROMO_NO_RAGGED", None)
+    else:
+        os.environ["CHROMO_NO_RAGGED"] = "1"
+    try:
+        eng = InferenceEngine(model, chunk=batch["interaction_freq"].size(0))
+        return eng.predict_device(eng.to_device(batch)).cpu()
+    finally:
+        os.environ.pop("CHROMO_NO_RAGGED", None)
+
+
+def test_ragged_batch_with_and_without_plan():
+    """configs[3]: pCRE counts of the demo histogram, log-normal pCRE lengths.  1200 genes = 75 tiles of 128 rows."""
+    n = 1200
+    model = _mk()
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = synthetic.make_batch(n, ragged=True, seed=5)
+    model.cuda().eval()
+    model.precision = "bf16"
+    got = _run(model, batch, True)
+    ref = _run(model, batch, False)
+    assert torch.isfinite(got).all()
+    # same kernels, other tile composition and key windows: the online softmax rounds P against another running maximum
+    assert (got - ref).abs().max().item() < 5e-3
+    idx = torch.cat([torch.arange(0, 48), torch.arange(n - 48, n)])
+    want = _oracle_logits(sd, batch, idx)
+    assert (got[idx] - want).abs().max().item() < BF16_TOL
+    # every pCRE count of the histogram is in the checked genes
+    assert set(batch["n_partners"][idx].tolist()) >= {0, 1, 8}
+
+
+def test_dense_batch_keeps_its_numbers():
+    """All slots live, all spans full: the stable sort keeps the order and every window is the whole table - bit-identical
+    to the run without the plan."""
+    n = 256
+    model = _mk(seed=3)
+    batch = synthetic.make_batch(n, ragged=False, seed=2)
+    model.cuda().eval()
+    model.precision = "bf16"
+    assert torch.equal(_run(model, batch, True), _run(model, batch, False))
+
+
+def test_masks_decide_not_the_layout():
+    """Batches the reference's Dataset never produces but its forward accepts."""
+    n = 320
+    model = _mk(seed=11)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = synthetic.make_batch(n, ragged=True, seed=9)
+    gen = torch.Generator().manual_seed(1)
+    k = batch["n_partners"]
+    S = 9
+    for b in (2000, 500, 100):
+        nb = 40000 // b
+        mc = batch["pcre_pad_masks"][b]                      # [B, 8, n] centre rows, True = padded
+        xc = batch["pcre_feats"][b]
+        im = batch["interaction_masks"][b]                   # [B, 1, S, S]
+        # (a) genes 0..15: arbitrary interaction masks (not block form): every slot stays live
+        im[:16, 0] = torch.rand(16, S, S, generator=gen) < 0.4
+        im[:16, 0, :, 0] = False
+        # (b) genes 16..31: a LIVE slot whose pad row is fully masked (uniform softmax over all bins in the reference)
+        mc[16:32, 0] = True
+        # (c) genes 32..47: holes inside the valid span, and a second island far from the centre
+        mc[32:48, 0, ::3] = True
+        mc[32:48, 1, :2] = False
+        mc[32:48, 1, nb - 1] = False
+        # (d) genes 48..63: dead slots (behind the block mask) with unmasked bins and data in them
+        mc[48:64, 7] = False
+        xc[48:64, 7] = torch.rand(16, nb, 7, generator=gen)
+        # (e) genes 64..79: the pad mask says "valid" over zero-feature bins beyond the span of live slots
+        mc[64:80, 0] = False
+    model.cuda().eval()
+    model.precision = "bf16"
+    got = _run(model, batch, True)
+    ref = _run(model, batch, False)
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() < 5e-3
+    idx = torch.arange(0, 80)
+    want = _oracle_logits(sd, batch, idx)
+    assert (got[idx] - want).abs().max().item() < BF16_TOL
+    assert (k[idx] < 8).any()

@@ -11,11 +11,12 @@ from chromoformer_b200.engine import InferenceEngine  # noqa: E402
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 mode = sys.argv[2] if len(sys.argv) > 2 else "infer"
 precision = sys.argv[3] if len(sys.argv) > 3 else "fp32"
+ragged = len(sys.argv) > 4 and sys.argv[4] == "ragged"
 if mode == "infer":
     model = ChromoformerClassifier(seed=123).cuda().eval()
     model.precision = precision
     eng = InferenceEngine(model, chunk=n)
-    batch = eng.to_device(synthetic.make_batch(n, ragged=False, seed=0))
+    batch = eng.to_device(synthetic.make_batch(n, ragged=ragged, seed=0))
     for _ in range(2):
         eng.predict_device(batch)
 else:
