@@ -14,6 +14,7 @@ MAX_LAYERS = 8
 F_TRAINING = 1
 F_BF16 = 2
 F_PACKED = 4
+F_DENSE = 64
 F_BWD_HEAD_REG = 16
 F_BWD_REST = 32
 

@@ -780,6 +780,8 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     const bool reg_fp32 = getenv("CHROMO_REG_FP32") != nullptr, head_fp32 = getenv("CHROMO_HEAD_FP32") != nullptr;
     auto lin_fp32 = [&](const GemmArgs& g, int nz) -> int { return gemm_launch(g, true, true, nz, st); };
 
+    RaggedPlan plan;                            // (ragged.cu; built next to the Embedding stage when the fused kernels run)
+    bool ragged = false, reg_plan = false;
     if (!only) {
     // ---------------- Embedding transformer, centre query (net.py:31-59) ----
     {
@@ -844,11 +846,9 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     };
     // Ragged plan (ragged.cu): the Pairwise stage runs over the live pCRE slots only, sorted by valid length, each tile
     // of the attention over its own key window.  Needs the fused kernels of the stage (they take the row maps).
-    RaggedPlan plan;
     RaggedArgs ra;
-    bool ragged = false;
     cudaStream_t plan_stream = st;
-    if (tail && w.rg_plan && c->pw_layers > 0 && c->pw_heads * D == 256 && D == 128 && (R + 127) / 128 >= 8 && !getenv("CHROMO_NO_RAGGED") &&
+    if (tail && w.rg_plan && c->pw_layers > 0 && c->pw_heads * D == 256 && D == 128 && (R + 127) / 128 >= 8 && !(flags & CHROMO_F_DENSE) && !getenv("CHROMO_NO_RAGGED") &&
         !getenv("CHROMO_QK_FP32") && !getenv("CHROMO_QK_ONE_TILE")) {
         bool ok = false;
         CHROMO_TRY(sqa_fused(R, c->pw_heads, in->x_pcre, in->mask_pcre, in->mask_pcre_stride, in->mask_pcre_row_offset,
@@ -1107,12 +1107,20 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
             if (all && l > 0) continue;
             RegFusedArgs a;
             a.B = B; a.S = S; a.G = 128 / S; a.n_tiles = (B + a.G - 1) / a.G;
+            if (ragged && all && !getenv("CHROMO_NO_RAGGED_REG")) {
+                // token classes of the plan: a tile holds genes of one class with their live tokens only
+                a.plan_tiles = plan.reg_tiles; a.plan_rows = plan.reg_rows; a.n_tiles = plan.reg_tiles_max;
+                reg_plan = true;
+            }
             a.x = xin; a.x_z = x_z; a.y = xout; a.y_z = y_z;
             a.n_layers = 1; a.y_mid = nullptr; a.y_mid_z = 0; a.y_l = 0; a.p_l = 0;
             if (all) {
                 a.n_layers = c->reg_layers;
                 a.y_mid = ws + w.r_out; a.y_mid_z = RS; a.y_l = w.rslots > 1 ? w.r_slot : 0;
                 if (!only) a.y = ws + w.r_out + (long long)w.rslot(c->reg_layers - 1) * w.r_slot;
+                // under a plan a tile's rows are scattered over the [B*S, 128] layout, where the rows of the last layer
+                // must not land in another tile's parking block: they go to the (unused) attention buffer of the layer path
+                if (reg_plan) a.y = ws + w.r_att;
                 a.p_l = c->reg_layers > 1 ? L.reg[0].att[1].gamma_f - L.reg[0].att[0].gamma_f : 0;
             }
             a.wstream = reinterpret_cast<const __nv_bfloat16*>(ws + w.reg_stream) + (long long)l * reg_stream_elems_per_layer();
@@ -1184,7 +1192,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     {
         HeadGatherArgs a;
         a.B = B; a.S = S; a.D = D; a.n_res = NR;
-        a.xout = ws + w.r_out + (long long)w.rslot(c->reg_layers - 1) * w.r_slot;
+        a.xout = reg_plan ? ws + w.r_att : ws + w.r_out + (long long)w.rslot(c->reg_layers - 1) * w.r_slot;
         a.xin = ws + w.r_xin; a.zstride = RS; a.z = ws + w.h_z;
         launch_pdl(head_gather_kernel, dim3((B * NR * D + 255) / 256), dim3(256), 0, st, a);
         CHROMO_CHECK_LAUNCH("head_gather");

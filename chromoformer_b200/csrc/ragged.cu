@@ -12,6 +12,7 @@
 // tile share one key window; dead slots last, their X_in rows zeroed (they stay masked keys of the Regulation layers and
 // must be finite).  A gene whose interaction mask is not in block form keeps all its slots; a live region without any
 // unmasked key keeps the whole table (the reference's uniform softmax over the masked row).
+#include <cub/block/block_scan.cuh>
 #include <cub/device/device_radix_sort.cuh>
 
 #include <algorithm>
@@ -25,7 +26,7 @@ namespace {
 constexpr int DEAD_KEY = 255;
 
 struct Carve {
-    int* k_gene; int* keys_in; int* keys_out; int* vals_in; int* span[CHROMO_MAX_RES];
+    int* cls_cnt; int* k_gene; int* keys_in; int* keys_out; int* vals_in; int* span[CHROMO_MAX_RES];
     void* temp; size_t temp_bytes;
 };
 
@@ -34,7 +35,24 @@ inline long long temp_ints(long long R) { return 4 * R + 65536; }
 
 // n_partners of every gene from its interaction masks: k such that mask[j][i] == !(j <= k && i <= k) at every
 // resolution (the largest k over the resolutions); I (every slot live) when a mask has another form.  One warp per gene.
-__global__ void ragged_gene_kernel(RaggedArgs a, int* __restrict__ k_gene) {
+constexpr int NCLS = 6;
+// token classes of the Regulation stage by descending token count: S, then 9 5 3 2 1 below it (0 = class does not exist)
+__host__ __device__ __forceinline__ int class_tokens(int c, int S) {
+    const int below[5] = {9, 5, 3, 2, 1};
+    if (c == 0) return S;
+    int seen = 0;
+    for (int i = 0; i < 5; ++i)
+        if (below[i] < S && ++seen == c) return below[i];
+    return 0;
+}
+__host__ __device__ __forceinline__ int class_of(int k, int S) {   // the smallest class that holds the 1 + k live tokens
+    int c = 0;
+    for (int i = 1; i < NCLS; ++i)
+        if (class_tokens(i, S) >= k + 1) c = i;
+    return c;
+}
+
+__global__ void ragged_gene_kernel(RaggedArgs a, int* __restrict__ k_gene, int* __restrict__ cls_cnt) {
     const int b = (int)(((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5), lane = threadIdx.x & 31;
     if (b >= a.B) return;
     const int S = a.I + 1, SS = S * S;
@@ -51,7 +69,10 @@ __global__ void ragged_gene_kernel(RaggedArgs a, int* __restrict__ k_gene) {
         }
         k = max(k, __all_sync(0xffffffffu, ok) ? kr : a.I);
     }
-    if (lane == 0) k_gene[b] = k;
+    if (lane == 0) {
+        k_gene[b] = k;
+        atomicAdd(&cls_cnt[(b >> 10) * NCLS + class_of(k, S)], 1);      // genes per (run of 1024 genes, class)
+    }
 }
 
 // one warp per four pCRE regions: [first, last + 1) unmasked bin per resolution, sort key of the region (8 bits: one pass
@@ -181,16 +202,81 @@ __global__ void ragged_tile_kernel(RaggedArgs a, Carve c, RaggedPlan p) {
     }
 }
 
+// Token classes of the Regulation stage: genes grouped by class (stable), tiles of floor(128 / S_c) genes per class.
+// Block j ranks its run of 1024 genes; the counts per (run, class) come from ragged_gene_kernel.
+__global__ void __launch_bounds__(1024) ragged_class_kernel(int B, int I, const int* __restrict__ k_gene,
+                                                            const int* __restrict__ cls_cnt, RaggedPlan p) {
+    using Scan = cub::BlockScan<int, 1024>;
+    __shared__ typename Scan::TempStorage tmp;
+    __shared__ int tot[NCLS], pre[NCLS], start[NCLS], tile0[NCLS + 1];
+    const int t = threadIdx.x, S = I + 1, n_blk = gridDim.x;
+    if (t < NCLS) {
+        int all = 0, before = 0;
+        for (int j = 0; j < n_blk; ++j) {
+            const int v = cls_cnt[j * NCLS + t];
+            all += v;
+            if (j < (int)blockIdx.x) before += v;
+        }
+        tot[t] = all; pre[t] = before;
+    }
+    __syncthreads();
+    if (t == 0) {
+        int s0 = 0, n_t = 0;
+        for (int c = 0; c < NCLS; ++c) {
+            start[c] = s0; s0 += tot[c];
+            tile0[c] = n_t;
+            const int Sc = class_tokens(c, S);
+            if (Sc > 0) n_t += (tot[c] + 128 / Sc - 1) / (128 / Sc);
+        }
+        tile0[NCLS] = n_t;
+        if (blockIdx.x == 0) p.reg_n[0] = n_t;
+    }
+    __syncthreads();
+    const int g = blockIdx.x * 1024 + t;
+    const int c = g < B ? class_of(k_gene[g], S) : -1;
+#pragma unroll
+    for (int i = 0; i < NCLS; ++i) {
+        int rank;
+        Scan(tmp).ExclusiveSum(c == i ? 1 : 0, rank);
+        if (c == i) p.gene_list[start[i] + pre[i] + rank] = g;
+        __syncthreads();
+    }
+    if (blockIdx.x == 0)
+        for (int i = t; i < p.reg_tiles_max; i += 1024) {
+            int4 e = make_int4(0, 0, S, 0);                    // (unused tile)
+            if (i < tile0[NCLS]) {
+                int cc = 0;
+                while (i >= tile0[cc + 1]) ++cc;
+                const int Sc = class_tokens(cc, S), G = 128 / Sc, j = i - tile0[cc];
+                e = make_int4(start[cc] + j * G, min(G, tot[cc] - j * G), Sc, 0);
+            }
+            p.reg_tiles[i] = e;
+        }
+}
+
+// row of the [B*S, 128] layout behind every row of every Regulation tile (one block per tile)
+__global__ void __launch_bounds__(128) ragged_rows_kernel(int I, RaggedPlan p) {
+    const int4 e = p.reg_tiles[blockIdx.x];
+    const int r = threadIdx.x;
+    p.reg_rows[blockIdx.x * 128 + r] = r < e.y * e.z ? p.gene_list[e.x + r / e.z] * (I + 1) + r % e.z : 0;
+}
+
 Carve carve(const RaggedArgs& a, float* ws, RaggedPlan* p) {
     const long long R = (long long)a.B * a.I, T = (R + 63) / 64;
     int* cur = reinterpret_cast<int*>(ws);
     auto take = [&](long long n) { int* o = cur; cur += a4(n); return o; };
     Carve c;
+    c.cls_cnt = take((long long)((a.B + 1023) / 1024) * NCLS);
     c.k_gene = take(a.B);
     c.keys_in = take(R); c.keys_out = take(R); c.vals_in = take(R);
     p->perm = take(R); p->y_rows = take(R);
     for (int r = 0; r < a.n_res; ++r) { c.span[r] = take(R); p->tile_k0[r] = take(T); p->tile_ns[r] = take(T); }
     p->live = take(4);
+    p->gene_list = take(a.B);
+    p->reg_n = take(4);
+    p->reg_tiles_max = ragged_reg_tiles_max(a.B, a.I);
+    p->reg_tiles = reinterpret_cast<int4*>(take(4LL * p->reg_tiles_max));
+    p->reg_rows = take(128LL * p->reg_tiles_max);
     uintptr_t t = (reinterpret_cast<uintptr_t>(cur) + 255) & ~uintptr_t(255);
     c.temp = reinterpret_cast<void*>(t);
     c.temp_bytes = (size_t)(temp_ints(R) - 64) * 4;
@@ -199,9 +285,14 @@ Carve carve(const RaggedArgs& a, float* ws, RaggedPlan* p) {
 
 }  // namespace
 
+int ragged_reg_tiles_max(int B, int I) {
+    const int G = 128 / (I + 1) > 0 ? 128 / (I + 1) : 1;            // a class has at least this many genes per tile,
+    return (B + G - 1) / G + NCLS;                                  // and at most one partly filled tile
+}
+
 long long ragged_plan_floats(int B, int I, int n_res) {
     const long long R = (long long)B * I, T = (R + 63) / 64;
-    return a4(B) + 5 * a4(R) + n_res * (a4(R) + 2 * a4(T)) + 4 + temp_ints(R);
+    return a4((long long)((B + 1023) / 1024) * NCLS) + 2 * a4(B) + 5 * a4(R) + n_res * (a4(R) + 2 * a4(T)) + 8 + 132LL * ragged_reg_tiles_max(B, I) + temp_ints(R);
 }
 
 int build_ragged_plan(const RaggedArgs& a, float* ws, RaggedPlan* plan, cudaStream_t st) {
@@ -211,8 +302,14 @@ int build_ragged_plan(const RaggedArgs& a, float* ws, RaggedPlan* plan, cudaStre
     for (int r = 1; r < a.n_res; ++r)
         if (a.n[r] > a.n[r_fine]) r_fine = r;
     if (a.n[r_fine] > 512) { set_error("ragged plan: more than 512 bins per region"); return CHROMO_EINVAL; }
-    ragged_gene_kernel<<<(unsigned)(((long long)a.B * 32 + 255) / 256), 256, 0, st>>>(a, c.k_gene);
+    const int n_blk = (a.B + 1023) / 1024;
+    if (cudaMemsetAsync(c.cls_cnt, 0, (size_t)n_blk * NCLS * sizeof(int), st) != cudaSuccess) { set_error("ragged plan: memset failed"); return CHROMO_ECUDA; }
+    ragged_gene_kernel<<<(unsigned)(((long long)a.B * 32 + 255) / 256), 256, 0, st>>>(a, c.k_gene, c.cls_cnt);
     CHROMO_CHECK_LAUNCH("ragged_gene");
+    ragged_class_kernel<<<n_blk, 1024, 0, st>>>(a.B, a.I, c.k_gene, c.cls_cnt, *plan);
+    CHROMO_CHECK_LAUNCH("ragged_class");
+    ragged_rows_kernel<<<plan->reg_tiles_max, 128, 0, st>>>(a.I, *plan);
+    CHROMO_CHECK_LAUNCH("ragged_rows");
     ragged_span_kernel<<<(unsigned)(((long long)(R + SPAN_RPW - 1) / SPAN_RPW * 32 + 255) / 256), 256, 0, st>>>(a, c.k_gene, c.keys_in, c.vals_in, c, r_fine);
     CHROMO_CHECK_LAUNCH("ragged_span");
     size_t need = 0;

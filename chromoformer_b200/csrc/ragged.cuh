@@ -13,6 +13,13 @@ struct RaggedPlan {
     int* y_rows = nullptr;                   // [R] token row of region perm[m] in X_in: gene * S + slot + 1
     int* tile_k0[CHROMO_MAX_RES] = {};       // [ceil(R / 64)] first key of tile t's key window (multiple of 8)
     int* tile_ns[CHROMO_MAX_RES] = {};       //                its width (multiple of 16, >= 16)
+    // Regulation stage: genes grouped by token class (the smallest S_c of {1, 2, 3, 5, 9, 17} that holds the
+    // 1 + n_partners live tokens of the gene); a tile holds floor(128 / S_c) genes of one class, S_c tokens each
+    int* gene_list = nullptr;                // [B] gene ids by class (largest class first, stable inside a class)
+    int4* reg_tiles = nullptr;               // [reg_tiles_max] (first entry of gene_list, genes, S_c, 0) per tile; genes = 0: unused
+    int* reg_rows = nullptr;                 // [reg_tiles_max][128] row of the [B*S, 128] layout behind every tile row
+    int* reg_n = nullptr;                    // [0] tiles in use
+    int reg_tiles_max = 0;
 };
 
 struct RaggedArgs {
@@ -24,6 +31,7 @@ struct RaggedArgs {
 };
 
 long long ragged_plan_floats(int B, int I, int n_res);            // workspace the plan needs (floats)
+int ragged_reg_tiles_max(int B, int I);                           // upper bound of the Regulation tiles of a plan
 // carves the plan out of `ws` (ragged_plan_floats floats, 16-byte aligned) and builds it on `st`
 int build_ragged_plan(const RaggedArgs& a, float* ws, RaggedPlan* plan, cudaStream_t st);
 

@@ -40,7 +40,9 @@ constexpr uint32_t OFF_STAGE = OFF_ATT + 65536;             // 3 x 32 KB weight 
 constexpr uint32_t OFF_K = OFF_STAGE + RF_NSTAGE * RF_CHUNK_BYTES;   // [128 x 64] BF16, 16-byte chunks XOR-swizzled by row
 constexpr uint32_t OFF_V = OFF_K + 16384;
 constexpr uint32_t OFF_CTL = OFF_V + 16384;                 // mbarriers + TMEM slot
-constexpr uint32_t RF_SMEM = OFF_CTL + 256;
+constexpr uint32_t OFF_ROWMAP = OFF_CTL + 256;              // ragged plan: [B*S, 128]-layout row of every tile row (128 ints)
+constexpr uint32_t RF_SMEM = OFF_ROWMAP + 512;
+static_assert(RF_SMEM <= 227 * 1024, "shared memory budget");
 
 enum { B_FULL0 = 0, B_FREE0 = 3, B_ACCQ0 = 6, B_ACCQFREE0 = 8, B_XREADY = 10, B_ATTREADY, B_UREADY, B_FREADY,
        B_ACCO, B_ACCF1, B_ACCF2, B_QKVR0, B_SR0 = B_QKVR0 + 2, B_PR0 = B_SR0 + 2, B_OR0 = B_PR0 + 2, B_QKFREE = B_OR0 + 2, B_ACCVG, B_COUNT };
@@ -643,17 +645,95 @@ __device__ __forceinline__ void all_compute_barrier() { asm volatile("bar.sync 1
 // the four warps that share a TMEM lane quarter (the four column quarters of the same 32 rows)
 __device__ __forceinline__ void quarter_barrier(int lq) { asm volatile("bar.sync %0, 128;" ::"r"(4 + lq) : "memory"); }
 
-template <int SMAX, bool TRACE>
+// Score warps of one layer's attention (four head pairs): scores of a row against the S keys of its own gene -> softmax
+// -> P (BF16) over the S tile.  S = tokens per gene in this tile (compile time: the window arithmetic below).
+template <int S, int SMAX, bool TRACE>
+__device__ __forceinline__ void score_rows(uint64_t* bars, uint32_t trow, int ch, int lq, int lane, int gl, const float* fr,
+                                           unsigned mbits, const float* gam, Tracer<TRACE>& tr) {
+    const float scale = 0.17677669529663687f;            // 1/sqrt(32)
+    {
+            // a window of the S tile that starts at the first gene touched by this warp (register indices stay
+            // compile-time, the column is warp-uniform)
+            constexpr int NC = (31 + S - 1) / S + 1;             // genes a 32-row warp can touch
+            constexpr int NW = NC * S;                            // window width in keys (<= 64)
+            const int g_lo = (32 * lq) / S;
+            const int cand = gl - g_lo;                           // 0 .. NC-1
+#pragma unroll 1
+            for (int t = 0; t < 4; ++t) {
+                const float gamma = t == 0 ? gam[0] : t == 1 ? gam[1] : t == 2 ? gam[2] : gam[3];
+                float w[64];
+                mbar_wait(&bars[C_SR0 + ch], t & 1);
+                tr(24);
+                tc_fence_after();
+                {
+                    const uint32_t sc0 = trow + 128 * ch + S * g_lo;
+                    if (NW > 48) tmem_ld32_pair(sc0, w, sc0 + 32, w + 32);
+                    else { tmem_ld32(sc0, w); tmem_ld16(sc0 + 32, w + 32); }
+                }
+                tc_fence_before();
+                {   // zeros over the P columns of the tile while the scores are being reduced
+                    uint32_t Z[32];
+#pragma unroll
+                    for (int m = 0; m < 32; ++m) Z[m] = 0u;
+                    tmem_st32(trow + 128 * ch, Z);
+                    tmem_st32(trow + 128 * ch + 32, Z);
+                }
+                float s[S];
+                float mx = -INFINITY;
+#pragma unroll
+                for (int j = 0; j < S; ++j) {
+                    float sc = w[j];
+#pragma unroll
+                    for (int c = 1; c < NC; ++c)
+                        if (cand == c) sc = w[c * S + j];
+                    sc = fmaf(gamma, fr[j], sc * scale);
+                    if ((mbits >> j) & 1u) sc = -1e9f;
+                    s[j] = sc;
+                    mx = fmaxf(mx, sc);
+                }
+                float sum = 0.f;
+#pragma unroll
+                for (int j = 0; j < S; ++j) { s[j] = __expf(s[j] - mx); sum += s[j]; }
+                const float inv = 1.f / sum;
+#pragma unroll
+                for (int j = 0; j < S; ++j) s[j] *= inv;
+                {   // P (BF16 pairs) over the first 64 columns of the S tile: this warp's window over the zeros
+                    uint32_t W[32];
+                    const int kb = S * g_lo;
+                    if (kb & 1) build_p_window<S, NC, 1>(s, cand, W);
+                    else build_p_window<S, NC, 0>(s, cand, W);
+                    tmem_st_wait();                                 // (the zeros have landed)
+                    tmem_st32(trow + 128 * ch + (kb >> 1), W);
+                    tmem_st_wait();
+                    tc_fence_before();
+                    warp_arrive(&bars[C_PST0 + ch], lane);          // P(t) of this warp's rows is in place
+                    tr(25);
+                }
+            }
+    }
+}
+
+template <int SMAX, bool TRACE, bool PLAN>
 __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const RegFusedArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_CTL);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + C_COUNT);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int z = blockIdx.y, tile = blockIdx.x;
-    constexpr int S = SMAX;                                   // exact tokens per gene: no per-key predicates
-    const int G = a.G;
-    const long long row0 = (long long)tile * G * S;            // first token row of this tile
-    const int rows_valid = min((long long)G * S, (long long)a.B * S - row0);
+    // tokens per gene in this tile: SMAX, or the tile's token class under a ragged plan (then the tile's rows are gathered
+    // through `rowmap`: row of the [B*SMAX, 128] layout per tile row)
+    int S = SMAX, G = a.G;
+    long long row0 = (long long)tile * G * S;                  // first token row of this tile (without a plan)
+    int rows_valid = min((long long)G * S, (long long)a.B * S - row0);
+    const int* rowmap = reinterpret_cast<const int*>(smem + OFF_ROWMAP);
+    if (PLAN) {
+        int r = 0;
+        if (tid < 128) r = __ldg(a.plan_rows + tile * 128 + tid);   // (both loads in flight)
+        const int4 tt = __ldg(a.plan_tiles + tile);
+        if (tt.y == 0) return;                                // (the grid is an upper bound)
+        G = tt.y; S = tt.z; rows_valid = G * S; row0 = 0;
+        if (tid < 128) reinterpret_cast<int*>(smem + OFF_ROWMAP)[tid] = r;
+    }
 
     if (warp == 0) tmem_alloc(tmem_slot, 512);
     if (tid == 0) {
@@ -793,7 +873,7 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
         const int cq = role;                                 // column quarter (epilogues)
         const int row = lq * 32 + lane;                      // tile row == TMEM lane
         const bool valid = row < rows_valid;
-        const long long grow = row0 + row;
+        const long long grow = PLAN ? (long long)rowmap[row] : row0 + row;   // row of the [B*SMAX, 128] layout
         const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
         const float* X = a.x + z * a.x_z;
         float v[32];
@@ -809,7 +889,7 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                 kc_[q] = (u >> 4) * 4 + (lane & 3);
                 x[q][0] = x[q][1] = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (r_[q] < rows_valid) {
-                    const float* p = X + (row0 + r_[q]) * 128 + kc_[q] * 8;
+                    const float* p = X + (PLAN ? (long long)rowmap[r_[q]] : row0 + r_[q]) * 128 + kc_[q] * 8;
                     x[q][0] = __ldg(reinterpret_cast<const float4*>(p));
                     x[q][1] = __ldg(reinterpret_cast<const float4*>(p + 4));
                 }
@@ -825,18 +905,17 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             warp_arrive(&bars[C_XREADY], lane);
         }
 
-        const int gl = row / S, qi = row % S;                 // gene within tile, query token
-        const long long gene = (long long)tile * G + gl;
-        const float scale = 0.17677669529663687f;            // 1/sqrt(32)
+        const int gl = row / S;                               // gene within tile
         float fr[SMAX];
         unsigned mbits = 0;
         if (score_warp) {
-            const float* freq = a.freq + (valid ? (gene * S + qi) * S : 0);
-            const uint8_t* mask = a.imask[z] + (valid ? (gene * S + qi) * S : 0);
+            // (grow = gene * SMAX + query token: row `grow` of the [B, SMAX, SMAX] bias and mask tensors)
+            const float* freq = a.freq + (valid ? grow * SMAX : 0);
+            const uint8_t* mask = a.imask[z] + (valid ? grow * SMAX : 0);
 #pragma unroll
             for (int j = 0; j < SMAX; ++j) {
                 fr[j] = 0.f;
-                if (valid) {
+                if (valid && j < S) {
                     fr[j] = freq[j];
                     if (mask[j]) mbits |= 1u << j;
                 }
@@ -858,62 +937,16 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             float gam[4];
 #pragma unroll
             for (int t = 0; t < 4; ++t) gam[t] = a.gamma_f[po + 2 * t + ch];
-            // a window of the S tile that starts at the first gene touched by this warp (register indices stay
-            // compile-time, the column is warp-uniform)
-            constexpr int NC = (31 + S - 1) / S + 1;             // genes a 32-row warp can touch
-            constexpr int NW = NC * S;                            // window width in keys (<= 64)
-            const int g_lo = (32 * lq) / S;
-            const int cand = gl - g_lo;                           // 0 .. NC-1
-#pragma unroll 1
-            for (int t = 0; t < 4; ++t) {
-                const float gamma = t == 0 ? gam[0] : t == 1 ? gam[1] : t == 2 ? gam[2] : gam[3];
-                float w[64];
-                mbar_wait(&bars[C_SR0 + ch], t & 1);
-                tr(24);
-                tc_fence_after();
-                {
-                    const uint32_t sc0 = trow + 128 * ch + S * g_lo;
-                    if (NW > 48) tmem_ld32_pair(sc0, w, sc0 + 32, w + 32);
-                    else { tmem_ld32(sc0, w); tmem_ld16(sc0 + 32, w + 32); }
-                }
-                tc_fence_before();
-                {   // zeros over the P columns of the tile while the scores are being reduced
-                    uint32_t Z[32];
-#pragma unroll
-                    for (int m = 0; m < 32; ++m) Z[m] = 0u;
-                    tmem_st32(trow + 128 * ch, Z);
-                    tmem_st32(trow + 128 * ch + 32, Z);
-                }
-                float s[SMAX];
-                float mx = -INFINITY;
-#pragma unroll
-                for (int j = 0; j < S; ++j) {
-                    float sc = w[j];
-#pragma unroll
-                    for (int c = 1; c < NC; ++c)
-                        if (cand == c) sc = w[c * S + j];
-                    sc = fmaf(gamma, fr[j], sc * scale);
-                    if ((mbits >> j) & 1u) sc = -1e9f;
-                    s[j] = sc;
-                    mx = fmaxf(mx, sc);
-                }
-                float sum = 0.f;
-#pragma unroll
-                for (int j = 0; j < S; ++j) { s[j] = __expf(s[j] - mx); sum += s[j]; }
-                const float inv = 1.f / sum;
-#pragma unroll
-                for (int j = 0; j < S; ++j) s[j] *= inv;
-                {   // P (BF16 pairs) over the first 64 columns of the S tile: this warp's window over the zeros
-                    uint32_t W[32];
-                    const int kb = S * g_lo;
-                    if (kb & 1) build_p_window<S, NC, 1>(s, cand, W);
-                    else build_p_window<S, NC, 0>(s, cand, W);
-                    tmem_st_wait();                                 // (the zeros have landed)
-                    tmem_st32(trow + 128 * ch + (kb >> 1), W);
-                    tmem_st_wait();
-                    tc_fence_before();
-                    warp_arrive(&bars[C_PST0 + ch], lane);          // P(t) of this warp's rows is in place
-                    tr(25);
+            if (!PLAN) score_rows<SMAX, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr);
+            else {
+                // one instantiation per token class of the plan (the window arithmetic wants S at compile time)
+                switch (S) {
+                    case 1: score_rows<1, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 2: score_rows<2, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 3: score_rows<3, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 5: score_rows<5, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 9: score_rows<(SMAX >= 9 ? 9 : SMAX), SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    default: score_rows<SMAX, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
                 }
             }
         } else {
@@ -1216,7 +1249,7 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                     const float* sp = stage + r * 33 + cc;
                     const int trw = lq * 32 + r;
                     if (trw < rows_valid)
-                        *reinterpret_cast<float4*>(Y + (row0 + trw) * 128 + c0 + cc) = make_float4(sp[0], sp[1], sp[2], sp[3]);
+                        *reinterpret_cast<float4*>(Y + (PLAN ? (long long)rowmap[trw] : row0 + trw) * 128 + c0 + cc) = make_float4(sp[0], sp[1], sp[2], sp[3]);
                 }
             }
         }
@@ -1279,11 +1312,13 @@ int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st) {
     if (!configured) {
         cudaError_t e1 = cudaFuncSetAttribute(reg_layer_cc_kernel<9>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
         cudaError_t e2 = cudaFuncSetAttribute(reg_layer_cc_kernel<17>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
-        cudaError_t e3 = cudaFuncSetAttribute(reg_layer_fused_kernel<9, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
-        cudaError_t e4 = cudaFuncSetAttribute(reg_layer_fused_kernel<17, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
-        cudaError_t e5 = cudaFuncSetAttribute(reg_layer_fused_kernel<9, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
-        cudaError_t e6 = cudaFuncSetAttribute(reg_layer_fused_kernel<17, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
-        for (cudaError_t e : {e1, e2, e3, e4, e5, e6})
+        cudaError_t e3 = cudaFuncSetAttribute(reg_layer_fused_kernel<9, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaError_t e4 = cudaFuncSetAttribute(reg_layer_fused_kernel<17, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaError_t e5 = cudaFuncSetAttribute(reg_layer_fused_kernel<9, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaError_t e6 = cudaFuncSetAttribute(reg_layer_fused_kernel<17, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaError_t e7 = cudaFuncSetAttribute(reg_layer_fused_kernel<9, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        cudaError_t e8 = cudaFuncSetAttribute(reg_layer_fused_kernel<17, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RF_SMEM);
+        for (cudaError_t e : {e1, e2, e3, e4, e5, e6, e7, e8})
             if (e != cudaSuccess) { set_error("reg_fused smem attribute: %s", cudaGetErrorString(e)); return CHROMO_ECUDA; }
         configured = true;
     }
@@ -1295,11 +1330,16 @@ int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st) {
     // probabilities, one layer per launch).
     const int tc = reg_fused_tensor_attention() ? 1 : 0;
     if (a.n_layers < 1 || (a.n_layers > 1 && !tc)) { set_error("reg_layer_fused: multi-layer launches need the tensor-pipe attention"); return CHROMO_EINVAL; }
-    if (a.S == 9 && tc && at.trace) reg_layer_fused_kernel<9, true><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
-    else if (a.S == 17 && tc && at.trace) reg_layer_fused_kernel<17, true><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
-    else if (a.S == 9 && tc) reg_layer_fused_kernel<9, false><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
+    const bool plan = a.plan_tiles != nullptr;
+    if (plan && !(tc && (a.S == 9 || a.S == 17) && a.plan_rows)) { set_error("reg_layer_fused: ragged plan without the tensor-pipe attention"); return CHROMO_EINVAL; }
+    if (plan) at.trace = nullptr;
+    if (a.S == 9 && plan) reg_layer_fused_kernel<9, false, true><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
+    else if (a.S == 17 && plan) reg_layer_fused_kernel<17, false, true><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
+    else if (a.S == 9 && tc && at.trace) reg_layer_fused_kernel<9, true, false><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
+    else if (a.S == 17 && tc && at.trace) reg_layer_fused_kernel<17, true, false><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
+    else if (a.S == 9 && tc) reg_layer_fused_kernel<9, false, false><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
     else if (a.S == 9) reg_layer_cc_kernel<9><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
-    else if (a.S == 17 && tc) reg_layer_fused_kernel<17, false><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
+    else if (a.S == 17 && tc) reg_layer_fused_kernel<17, false, false><<<grid, RF2_THREADS, RF_SMEM, st>>>(at);
     else if (a.S == 17) reg_layer_cc_kernel<17><<<grid, RF_THREADS, RF_SMEM, st>>>(a);
     else { set_error("reg_layer_fused: tokens per gene must be 9 or 17"); return CHROMO_EINVAL; }
     CHROMO_CHECK_LAUNCH("reg_layer_fused");

@@ -19,6 +19,10 @@ struct RegFusedArgs {
     const float* freq;                      // [B,S,S]
     const uint8_t* imask[CHROMO_MAX_RES];   // [B,S,S] per resolution
     long long* trace = nullptr;             // profiling hook (chromo_debug_trace): CTA (0,0) logs (event << 48 | clock64) here
+    // ragged plan (ragged.cu; tensor-pipe attention only): tile t holds plan_tiles[t].y genes (0: the tile is unused - the
+    // grid is an upper bound) with their first plan_tiles[t].z tokens each (the others are masked for every token that
+    // reaches the head); its rows are gathered from / scattered to rows plan_rows[t][0..128) of the [B*S, 128] layout
+    const int4* plan_tiles = nullptr; const int* plan_rows = nullptr;
 };
 
 struct RegStreamArgs {

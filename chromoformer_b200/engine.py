@@ -115,9 +115,13 @@ class InferenceEngine:
         self._stage = None
 
     def to_device(self, batch):
+        """The forward arguments in HBM.  Also notes (on the host, once) whether the batch carries any padding at all: a
+        batch without dummy pCRE slots and padded bins is run with CHROMO_F_DENSE (no ragged plan; same results)."""
         mv = lambda t: t.to(self.device).contiguous()
-        return {k: ({b: mv(t) for b, t in batch[k].items()} if isinstance(batch[k], dict) else mv(batch[k]))
-                for k in _KEYS}
+        dev = {k: ({b: mv(t) for b, t in batch[k].items()} if isinstance(batch[k], dict) else mv(batch[k]))
+               for k in _KEYS}
+        dev["dense"] = not any(bool(t.any()) for k in ("pcre_pad_masks", "interaction_masks") for t in batch[k].values())
+        return dev
 
     @torch.no_grad()
     def predict_device(self, batch, out=None):
@@ -127,7 +131,7 @@ class InferenceEngine:
             out = torch.empty(n, int(self.model._cfg.n_out), dtype=torch.float32, device=self.device)
         for lo in range(0, n, self.device_chunk):
             hi = min(n, lo + self.device_chunk)
-            out[lo:hi] = self.model.forward_batch(_slice(batch, lo, hi))
+            out[lo:hi] = self.model.forward_batch(_slice(batch, lo, hi), dense=bool(batch.get("dense", False)))
         return out
 
     def _staging(self, batch):

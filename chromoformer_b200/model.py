@@ -393,7 +393,7 @@ class _ChromoformerCore(nn.Module):
         n = _lib.check(lib.chromo_workspace_floats(ctypes.byref(cfg), batch, flags), "chromo_workspace_floats")
         if not cached:
             return torch.empty(n, dtype=torch.float32, device=self._flat.device)
-        key = (str(self._flat.device), flags)
+        key = (str(self._flat.device), flags & ~_lib.F_DENSE)      # (the hint does not change the layout)
         ws = self._ws_cache.get(key)
         if ws is None or ws.numel() < n:
             ws = torch.empty(n, dtype=torch.float32, device=self._flat.device)
@@ -471,21 +471,22 @@ class _ChromoformerCore(nn.Module):
             self.mark_parameters_changed()
         return out
 
-    def forward_batch(self, batch):
+    def forward_batch(self, batch, dense=False):
         """Forward from a dict of the six arguments keyed like the reference's collated items (dicts by int bin size):
-        the one calling convention `InferenceEngine` / `EnsembleSweep` use for the flat and the dict API alike."""
+        the one calling convention `InferenceEngine` / `EnsembleSweep` use for the flat and the dict API alike.
+        `dense`: hint that the batch carries no padding (CHROMO_F_DENSE: the ragged plan is not built; same results)."""
         def pick(d, b):
             return d[b] if b in d else d[str(b)]
         bs = self.binsizes
         return self._run([pick(batch["promoter_feats"], b) for b in bs], [pick(batch["promoter_pad_masks"], b) for b in bs],
                          [pick(batch["pcre_feats"], b) for b in bs], [pick(batch["pcre_pad_masks"], b) for b in bs],
-                         [pick(batch["interaction_masks"], b) for b in bs], batch["interaction_freq"])
+                         [pick(batch["interaction_masks"], b) for b in bs], batch["interaction_freq"], dense=dense)
 
-    def _run(self, x_p, mask_p, x_pcre, mask_pcre, imask, freq):
+    def _run(self, x_p, mask_p, x_pcre, mask_pcre, imask, freq, dense=False):
         io = _BatchIO(self, x_p, mask_p, x_pcre, mask_pcre, imask, freq)
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return _ChromoFunction.apply(self._anchor, self, io)
-        logits, _ = self._launch_forward(io, self._precision_flag())
+        logits, _ = self._launch_forward(io, self._precision_flag() | (_lib.F_DENSE if dense else 0))
         return logits
 
 

@@ -48,6 +48,11 @@ extern "C" {
 #define CHROMO_F_PACKED 4     /* with CHROMO_F_BF16: the workspace already holds
                                  the packed BF16 weights of THESE parameters
                                  (left there by a previous call) - skip packing */
+#define CHROMO_F_DENSE 64     /* hint: the batch carries no padding to speak of (every pCRE slot
+                                 live, every bin valid), so the ragged plan of the BF16 inference
+                                 path - dummy slots of data.py:175-203 leave the Pairwise and
+                                 Regulation stages, padded bins of data.py:86-97 leave the attention
+                                 windows - is not built.  Results do not depend on the hint.     */
 
 /* Hyper-parameters: the config.yaml schema of chromoformer/configs/default.yaml:11-32
  * plus the number of bins per resolution (w_max // binsize, data.py:140).     */

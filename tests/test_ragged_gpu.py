@@ -32,14 +32,16 @@ def _oracle_logits(sd, batch, idx):
         return oracle.chromoformer_forward(sd, *synthetic.forward_args(part))
 
 
-def _run(model, batch, ragged):
+def _run(model, batch, ragged, hint=False):
     if ragged:
         os.environ.pop("CHROMO_NO_RAGGED", None)
     else:
         os.environ["CHROMO_NO_RAGGED"] = "1"
     try:
         eng = InferenceEngine(model, chunk=batch["interaction_freq"].size(0))
-        return eng.predict_device(eng.to_device(batch)).cpu()
+        dev = eng.to_device(batch)
+        dev["dense"] = hint            # (to_device sets the CHROMO_F_DENSE hint for batches without padding: plan not built)
+        return eng.predict_device(dev).cpu()
     finally:
         os.environ.pop("CHROMO_NO_RAGGED", None)
 
@@ -73,6 +75,12 @@ def test_dense_batch_keeps_its_numbers():
     model.cuda().eval()
     model.precision = "bf16"
     assert torch.equal(_run(model, batch, True), _run(model, batch, False))
+    # the engine recognises such a batch on the host and passes the hint; the hint itself never changes results
+    eng = InferenceEngine(model, chunk=n)
+    assert eng.to_device(batch)["dense"] is True
+    rag = synthetic.make_batch(n, ragged=True, seed=2)
+    assert eng.to_device(rag)["dense"] is False
+    assert torch.equal(_run(model, rag, True, hint=True), _run(model, rag, False))
 
 
 def test_masks_decide_not_the_layout():

@@ -39,7 +39,7 @@ def test_headline_bf16_dense_sweep_vs_oracle():
     batch = synthetic.make_batch(n, ragged=False, seed=0)
     model.cuda().eval()
     model.precision = "bf16"
-    eng = InferenceEngine(model, chunk=4096)
+    eng = InferenceEngine(model, chunk=4096, device_chunk=4096)
     dev = eng.to_device(batch)
     got = eng.predict_device(dev).cpu()
     whole = InferenceEngine(model, chunk=n).predict_device(dev).cpu()        # the whole sweep as one launch chain
