@@ -121,3 +121,31 @@ def test_masks_decide_not_the_layout():
     want = _oracle_logits(sd, batch, idx)
     assert (got[idx] - want).abs().max().item() < BF16_TOL
     assert (k[idx] < 8).any()
+
+
+def test_ragged_imax16_token_classes():
+    """i_max = 16: 17-token Regulation tiles, token classes 17 / 9 / 5 / 3 / 2 / 1."""
+    n = 700
+    model = ChromoformerClassifier(7, 128, 128, dict(KWS[0]), dict(KWS[1]), dict(KWS[2]), seed=21, i_max=16)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = synthetic.make_batch(n, i_max=16, ragged=True, seed=13)
+    # spread the pCRE counts over every class (the synthetic histogram only knows 0..8 and 16)
+    gen = torch.Generator().manual_seed(2)
+    k = torch.randint(0, 17, (n,), generator=gen)
+    idx = torch.arange(17)
+    inside = (idx.view(1, 17, 1) <= k.view(n, 1, 1)) & (idx.view(1, 1, 17) <= k.view(n, 1, 1))
+    for b in (2000, 500, 100):
+        batch["interaction_masks"][b] = (~inside).unsqueeze(1)
+        live = (torch.arange(16).view(1, 16) < k.view(n, 1))
+        batch["pcre_pad_masks"][b] = batch["pcre_pad_masks"][b] | ~live.unsqueeze(2)
+    batch["n_partners"] = k
+    model.cuda().eval()
+    model.precision = "bf16"
+    got = _run(model, batch, True)
+    ref = _run(model, batch, False)
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() < 5e-3
+    sel = torch.arange(0, 40)
+    want = _oracle_logits(sd, batch, sel)
+    assert (got[sel] - want).abs().max().item() < BF16_TOL
+    assert len(set(k[sel].tolist())) >= 10

@@ -25,7 +25,7 @@ def test_wire_path_equals_device_path_on_fp16_features(precision, ragged):
     rounded = dict(batch)
     for key in ("promoter_feats", "pcre_feats"):
         rounded[key] = {b: t.half().float() for b, t in batch[key].items()}
-    eng = InferenceEngine(model, chunk=256)                      # 256, 256, 188: two staging sets + a short tail
+    eng = InferenceEngine(model, chunk=256, device_chunk=256)    # 256, 256, 188: two staging sets + a short tail; same chunks on both paths
     want = eng.predict_device(eng.to_device(rounded)).cpu()
     wire = pack_wire(batch)
     assert wire_nbytes(wire) < 0.5 * batch_nbytes(batch)
