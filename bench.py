@@ -445,6 +445,20 @@ def main():
                                              "what": "the reference DataLoader's own collation (FP32 + [B,8,1,n,n] boolean masks), "
                                                      f"{n_full}-gene sample in chunks of 256"}
     del full, eng_full
+    # ragged genes (configs[3]) end to end: the compact wire ships only the valid bins of the live pCRE slots
+    # (data.py:86-97,175-177 pads everything else with zeros), the forward runs under the ragged plan
+    rag_host = synthetic.make_batch(N_GENES, ragged=True, seed=1000 + rank)
+    for key, compact in (("ragged_fp16_spans", False), ("ragged_compact_wire", True)):
+        rw = pack_wire(rag_host, compact=compact)
+        ms_v = timed(lambda: eng.predict_wire(rw), max(2, e2e_steps // 2), 2)
+        e2e["variants"][key] = {"value": world * N_GENES / (ms_v * 1e-3), "unit": "genes/s", "ms_per_step": ms_v,
+                                "h2d_bytes_per_gene": wire_nbytes(rw) / N_GENES,
+                                "h2d_gbs": world * wire_nbytes(rw) / (ms_v * 1e-3) / 1e9,
+                                "what": "ragged genes (pCRE count ~ demo histogram, ~63 of 400 valid 100-bp bins), " +
+                                        ("valid bins only (engine.pack_wire(compact=True) -> chromo_unpack_compact)" if compact
+                                         else "the same FP16 + span wire as the headline")}
+        del rw
+    del rag_host
     demo_dir = os.path.join(ROOT, "baseline", "_ref", "demo")
     if os.path.exists(os.path.join(demo_dir, "demo_meta_head.csv")) and rank == 0:
         import pandas as pd

@@ -95,6 +95,8 @@ EXPORTS = {
                                c_float, c_float, c_int32, c_float, c_void_p]),
     "chromo_unpack_wire": (c_int32, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int32,
                                      POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32), c_void_p]),
+    "chromo_unpack_compact": (c_int32, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int32),
+                                        POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32), c_int32, c_void_p]),
     "chromo_bin_regions": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(c_int32),
                                      POINTER(c_int32), POINTER(c_void_p), c_void_p, c_void_p]),
 }

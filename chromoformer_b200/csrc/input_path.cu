@@ -337,7 +337,45 @@ __global__ void __launch_bounds__(256) unpack_wire_kernel(const WireArgs a) {
     }
 }
 
+// Compact wire of ragged genes: only the valid bins of a region travel (data.py:86-97 pads the rest with zeros).  One warp
+// per region row: the row's [lo, lo + cnt) bins come from the FP16 stream at the region's offset, everything else is zero.
+struct CompactArgs {
+    int n_sets, F;
+    const __half* src[WIRE_MAX]; const int* spans[WIRE_MAX]; const int* off[WIRE_MAX]; int base[WIRE_MAX];
+    float* dst[WIRE_MAX]; int rows[WIRE_MAX]; int n[WIRE_MAX];
+};
+__global__ void __launch_bounds__(256) unpack_compact_kernel(const CompactArgs a) {
+    const int set = blockIdx.y, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= a.rows[set]) return;
+    const int F = a.F, nF = a.n[set] * F;
+    const int lo = a.spans[set][2 * row] * F, hi = lo + a.spans[set][2 * row + 1] * F;
+    const __half* src = a.src[set] + (long long)(a.off[set][row] - a.base[set]) * F - lo;
+    float* dst = a.dst[set] + (long long)row * nF;
+    for (int e = lane; e < nF; e += 32) dst[e] = (e >= lo && e < hi) ? __half2float(src[e]) : 0.f;
+}
+
 }  // namespace chromo
+
+extern "C" int chromo_unpack_compact(int32_t n_sets, const uint16_t* const* src, const int32_t* const* spans,
+                                     const int32_t* const* offsets, const int32_t* base, float* const* dst,
+                                     const int32_t* rows, const int32_t* n_bins, int32_t n_feats, void* stream) {
+    using namespace chromo;
+    if (n_sets < 1 || n_sets > WIRE_MAX || n_feats < 1) { set_error("unpack_compact: 1..%d sets", WIRE_MAX); return CHROMO_EINVAL; }
+    CompactArgs a;
+    a.n_sets = n_sets; a.F = n_feats;
+    int most = 0;
+    for (int i = 0; i < n_sets; ++i) {
+        if (!src[i] || !spans[i] || !offsets[i] || !dst[i] || rows[i] < 0 || n_bins[i] < 1) { set_error("unpack_compact: bad set %d", i); return CHROMO_EINVAL; }
+        a.src[i] = reinterpret_cast<const __half*>(src[i]); a.spans[i] = spans[i]; a.off[i] = offsets[i]; a.base[i] = base[i];
+        a.dst[i] = dst[i]; a.rows[i] = rows[i]; a.n[i] = n_bins[i];
+        most = rows[i] > most ? rows[i] : most;
+    }
+    if (most == 0) return CHROMO_OK;
+    unpack_compact_kernel<<<dim3((unsigned)((most + 7) / 8), n_sets), 256, 0, (cudaStream_t)stream>>>(a);
+    CHROMO_CHECK_LAUNCH("unpack_compact");
+    return CHROMO_OK;
+}
 
 extern "C" int chromo_unpack_wire(int32_t n_seg, const uint16_t* const* src, float* const* dst, const int64_t* counts,
                                   int32_t n_sets, const int32_t* const* spans, uint8_t* const* masks,

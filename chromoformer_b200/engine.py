@@ -66,18 +66,25 @@ def _spans_of(rows):
     return torch.stack([lo, cnt], -1).to(torch.int32).contiguous(), exact
 
 
-def pack_wire(batch, pin=True):
+def pack_wire(batch, pin=True, compact=False):
     """Forward arguments (host tensors, reference layout) -> the FP16 / span wire format in (pinned) host memory.
     This is producer-side work (a DataLoader collate_fn or `GeneBatcher` would emit it directly); it is NOT part of
-    the transport being timed."""
+    the transport being timed.
+
+    `compact`: pCRE features travel as their valid bins only (`xc_flat` [bins, F] FP16 in (gene, slot, bin) order + `off_c`
+    [B*I + 1] first bin of every region): data.py:86-97 pads every pCRE to w_max / bin_size bins with zeros and
+    data.py:175-177 fills dummy slots with zeros, so nothing else carries information - 14 kB instead of 64 kB per gene of
+    the demo set.  Falls back to the full tensors for a resolution whose masks are not spans or whose padded bins are not
+    all zero."""
     fin = (lambda t: t.contiguous().pin_memory()) if pin else (lambda t: t.contiguous())
     bins = list(batch["promoter_feats"].keys())
-    wire = {_WIRE_BINS: bins, "xp": {}, "xc": {}, "span_p": {}, "span_c": {}, "rows_p": {}, "rows_c": {}, "imask": {}}
+    wire = {_WIRE_BINS: bins, "xp": {}, "xc": {}, "span_p": {}, "span_c": {}, "rows_p": {}, "rows_c": {}, "imask": {},
+            "xc_flat": {}, "off_c": {}}
     for b in bins:
         xp, xc = batch["promoter_feats"][b], batch["pcre_feats"][b]
         n = xp.size(-2)
         wire["xp"][b] = fin(xp.to(torch.float16))
-        wire["xc"][b] = fin(xc.to(torch.float16))
+        done = False
         for key, src in (("p", batch["promoter_pad_masks"][b]), ("c", batch["pcre_pad_masks"][b])):
             rows = _centre_rows(src.bool(), n)
             spans, exact = _spans_of(rows)
@@ -85,15 +92,25 @@ def pack_wire(batch, pin=True):
                 wire["span_" + key][b] = fin(spans)
             else:                                   # arbitrary mask: ship the centre rows as bytes
                 wire["rows_" + key][b] = fin(rows.contiguous())
+            if key == "c" and compact and exact and not bool((xc * rows.unsqueeze(-1)).any()):
+                valid = ~rows                                            # [B, I, n]
+                wire["xc_flat"][b] = fin(xc[valid].to(torch.float16))     # (gene, slot, bin) order
+                off = torch.zeros(valid.size(0) * valid.size(1) + 1, dtype=torch.int64)
+                off[1:] = valid.sum(-1).reshape(-1).cumsum(0)
+                wire["off_c"][b] = fin(off.to(torch.int32))
+                done = True
+        if not done:
+            wire["xc"][b] = fin(xc.to(torch.float16))
         wire["imask"][b] = fin(batch["interaction_masks"][b].bool())
     wire["freq"] = fin(batch["interaction_freq"].to(torch.float32))
+    wire["_shape_c"] = [(b, tuple(batch["pcre_feats"][b].shape[1:])) for b in bins]     # [I, n, F] of every resolution
     return wire
 
 
 def wire_nbytes(wire):
     tot = 0
     for k, v in wire.items():
-        if k == _WIRE_BINS:
+        if k == _WIRE_BINS or k.startswith("_"):
             continue
         for t in (v.values() if isinstance(v, dict) else (v,)):
             tot += t.numel() * t.element_size()
@@ -190,35 +207,57 @@ class InferenceEngine:
 
     # ---- FP16 / span wire ------------------------------------------------------------------------------------
     def _wire_staging(self, wire):
+        shape_c = dict(wire["_shape_c"])
+        # compact pCRE streams: a staging set holds the longest chunk of THIS wire
+        caps = {}
+        for b, off in wire["off_c"].items():
+            I = shape_c[b][0]
+            n = (off.numel() - 1) // I
+            edges = off[torch.arange(0, n + self.chunk, self.chunk).clamp(max=n) * I].long()
+            caps[b] = int((edges[1:] - edges[:-1]).max().item()) if n else 0
         sig = tuple((k, b, tuple(t.shape[1:]), t.dtype) for k, v in wire.items() if isinstance(v, dict)
-                    for b, t in v.items()) + (tuple(wire["freq"].shape[1:]),)
+                    for b, t in v.items()) + (tuple(wire["freq"].shape[1:]), tuple(sorted(caps.items())))
         if getattr(self, "_wstage", None) is not None and self._wstage[0] == sig:
             return self._wstage[1], self._wstage[2]
         mk = lambda t, dt=None: torch.empty((self.chunk,) + tuple(t.shape[1:]), dtype=dt or t.dtype, device=self.device)
         sets = []
         for _ in range(2):
-            st = {k: {b: mk(t) for b, t in v.items()} for k, v in wire.items() if isinstance(v, dict)}
+            st = {k: {b: mk(t) for b, t in v.items()} for k, v in wire.items() if isinstance(v, dict) and k not in ("xc_flat", "off_c")}
+            st["xc_flat"] = {b: torch.empty((max(caps[b], 1),) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
+                             for b, t in wire["xc_flat"].items()}
+            st["off_c"] = {b: torch.empty(self.chunk * shape_c[b][0] + 1, dtype=torch.int32, device=self.device)
+                           for b in wire["off_c"]}
             st["freq"] = mk(wire["freq"])
             sets.append(st)
         wide = {"promoter_feats": {b: mk(t, torch.float32) for b, t in wire["xp"].items()},
-                "pcre_feats": {b: mk(t, torch.float32) for b, t in wire["xc"].items()},
+                "pcre_feats": {b: torch.empty((self.chunk,) + shape_c[b], dtype=torch.float32, device=self.device)
+                               for b in wire[_WIRE_BINS]},
                 "promoter_pad_masks": {}, "pcre_pad_masks": {}}
         for b in wire[_WIRE_BINS]:
             n = wire["xp"][b].size(-2)
-            for key, name, reg in (("p", "promoter_pad_masks", 1), ("c", "pcre_pad_masks", wire["xc"][b].size(1))):
+            for key, name, reg in (("p", "promoter_pad_masks", 1), ("c", "pcre_pad_masks", shape_c[b][0])):
                 if b in wire["span_" + key]:
                     wide[name][b] = torch.empty(self.chunk, reg, n, dtype=torch.bool, device=self.device)
         self._wstage = (sig, sets, wide)
         return sets, wide
 
-    def _unpack(self, st, wide, m, bins):
-        """One chromo_unpack_wire launch: FP16 -> FP32 features, spans -> centre-row masks, for the first m genes."""
+    def _unpack(self, st, wide, m, bins, base=None):
+        """One chromo_unpack_wire launch: FP16 -> FP32 features, spans -> centre-row masks, for the first m genes; compact
+        pCRE streams (valid bins only, `base[b]` = stream position the staged chunk starts at) by chromo_unpack_compact."""
         lib = _lib.load()
         src, dst, cnt, spans, masks, rows, nb = [], [], [], [], [], [], []
+        c_src, c_sp, c_off, c_base, c_dst, c_rows, c_nb, feats = [], [], [], [], [], [], [], 0
         for b in bins:
             for k16, k32 in (("xp", "promoter_feats"), ("xc", "pcre_feats")):
+                if b not in st[k16]:
+                    continue
                 t = st[k16][b]
                 src.append(t.data_ptr()); dst.append(wide[k32][b].data_ptr()); cnt.append(m * t[0].numel())
+            if b in st["xc_flat"]:
+                w = wide["pcre_feats"][b]
+                c_src.append(st["xc_flat"][b].data_ptr()); c_sp.append(st["span_c"][b].data_ptr())
+                c_off.append(st["off_c"][b].data_ptr()); c_base.append(int(base[b])); c_dst.append(w.data_ptr())
+                c_rows.append(m * w.size(1)); c_nb.append(w.size(2)); feats = w.size(3)
             for key, name in (("p", "promoter_pad_masks"), ("c", "pcre_pad_masks")):
                 if b in st["span_" + key]:
                     sp = st["span_" + key][b]
@@ -230,6 +269,11 @@ class InferenceEngine:
                                           arr(ctypes.c_int64, cnt), len(spans), arr(ctypes.c_void_p, spans),
                                           arr(ctypes.c_void_p, masks), arr(ctypes.c_int32, rows), arr(ctypes.c_int32, nb),
                                           stream), "chromo_unpack_wire")
+        if c_src:
+            _lib.check(lib.chromo_unpack_compact(len(c_src), arr(ctypes.c_void_p, c_src), arr(ctypes.c_void_p, c_sp),
+                                                 arr(ctypes.c_void_p, c_off), arr(ctypes.c_int32, c_base),
+                                                 arr(ctypes.c_void_p, c_dst), arr(ctypes.c_int32, c_rows),
+                                                 arr(ctypes.c_int32, c_nb), int(feats), stream), "chromo_unpack_compact")
 
     @torch.no_grad()
     def predict_wire(self, wire):
@@ -246,6 +290,9 @@ class InferenceEngine:
         bounds = [(lo, min(n, lo + self.chunk)) for lo in range(0, n, self.chunk)]
         copied = [torch.cuda.Event() for _ in bounds]
         freed = [torch.cuda.Event() for _ in bounds]
+        shape_c = dict(wire["_shape_c"])
+        # stream positions of the chunk boundaries of every compact pCRE stream (host integers, once per call)
+        edges = {b: off[torch.tensor([lo for lo, _ in bounds] + [n]) * shape_c[b][0]].tolist() for b, off in wire["off_c"].items()}
 
         def upload(i):
             lo, hi = bounds[i]
@@ -256,9 +303,15 @@ class InferenceEngine:
                 cs.wait_stream(main)
             with torch.cuda.stream(cs):
                 for k, v in wire.items():
-                    if isinstance(v, dict):
+                    if isinstance(v, dict) and k not in ("xc_flat", "off_c"):
                         for b, t in v.items():
                             dst[k][b][:hi - lo].copy_(t[lo:hi], non_blocking=True)
+                for b, off in wire["off_c"].items():                 # compact pCRE stream: the chunk's slice of it
+                    I = shape_c[b][0]
+                    r0, r1 = edges[b][i], edges[b][i + 1]
+                    dst["off_c"][b][:(hi - lo) * I + 1].copy_(off[lo * I:hi * I + 1], non_blocking=True)
+                    if r1 > r0:
+                        dst["xc_flat"][b][:r1 - r0].copy_(wire["xc_flat"][b][r0:r1], non_blocking=True)
                 dst["freq"][:hi - lo].copy_(wire["freq"][lo:hi], non_blocking=True)
                 copied[i].record(cs)
 
@@ -268,7 +321,7 @@ class InferenceEngine:
                 upload(i + 1)
             main.wait_event(copied[i])
             st, m = sets[i % 2], hi - lo
-            self._unpack(st, wide, m, bins)
+            self._unpack(st, wide, m, bins, base={b: edges[b][i] for b in edges})
             batch = {"promoter_feats": {b: wide["promoter_feats"][b][:m] for b in bins},
                      "pcre_feats": {b: wide["pcre_feats"][b][:m] for b in bins},
                      "promoter_pad_masks": {b: (wide["promoter_pad_masks"][b][:m] if b in st["span_p"] else st["rows_p"][b][:m])

@@ -235,6 +235,17 @@ int chromo_unpack_wire(int32_t n_seg, const uint16_t* const* src /* fp16 bits */
                        const int64_t* counts, int32_t n_sets, const int32_t* const* spans,
                        uint8_t* const* masks, const int32_t* rows, const int32_t* n_bins, void* stream);
 
+/* Compact wire for ragged genes (run_demo.py:100-105 again): data.py:86-97 pads every region to
+ * w_max / bin_size bins with zeros, so only the valid bins need to cross PCIe - 14 kB per gene of the demo
+ * set instead of 64 kB.  For each of n_sets feature tensors: `src` holds the valid bins of its regions
+ * back to back (FP16 [bins, n_feats], region order), `offsets[row]` the first bin of region `row` in the
+ * whole stream and `base` the stream position `src` starts at (a chunk of a longer stream), `spans`
+ * ([rows,2] int32: first valid bin, count) where the bins belong.  `dst` (FP32 [rows, n_bins, n_feats]) is
+ * written completely: the bins at their place, zeros elsewhere.                                  */
+int chromo_unpack_compact(int32_t n_sets, const uint16_t* const* src /* fp16 bits */, const int32_t* const* spans,
+                          const int32_t* const* offsets, const int32_t* base, float* const* dst,
+                          const int32_t* rows, const int32_t* n_bins, int32_t n_feats, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

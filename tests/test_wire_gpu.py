@@ -65,3 +65,34 @@ def test_wire_falls_back_to_mask_bytes_for_arbitrary_masks():
         rounded[key] = {b: t.half().float() for b, t in batch[key].items()}
     eng = InferenceEngine(model, chunk=16)
     assert torch.equal(eng.predict_wire(wire), eng.predict_device(eng.to_device(rounded)).cpu())
+
+
+def test_compact_wire_ships_valid_bins_only():
+    """engine.pack_wire(compact=True): pCRE features as their valid bins (chromo_unpack_compact puts them back between
+    zeros) - bit-identical to the ordinary path, a quarter of the bytes; a resolution whose padded bins are NOT all zero
+    keeps the full tensor."""
+    model = _mk(seed=4).cuda().eval()
+    model.precision = "bf16"
+    n = 700
+    batch = synthetic.make_batch(n, ragged=True, seed=31, stress=True)
+    rounded = dict(batch)
+    for key in ("promoter_feats", "pcre_feats"):
+        rounded[key] = {b: t.half().float() for b, t in batch[key].items()}
+    eng = InferenceEngine(model, chunk=256, device_chunk=256)
+    want = eng.predict_device(eng.to_device(rounded)).cpu()
+    wire = pack_wire(batch, compact=True)
+    assert set(wire["xc_flat"]) == set(BINS) and not wire["xc"]
+    assert wire_nbytes(wire) < 0.3 * wire_nbytes(pack_wire(batch))
+    got = eng.predict_wire(wire)
+    assert torch.equal(got, want)
+    # a second wire with other chunk lengths through the same engine (staging is re-sized, offsets are per chunk)
+    part = synthetic.slice_batch(batch, 100, 700)
+    part_r = synthetic.slice_batch(rounded, 100, 700)
+    assert torch.equal(eng.predict_wire(pack_wire(part, compact=True)), eng.predict_device(eng.to_device(part_r)).cpu())
+    # data in a padded bin: that resolution travels as the full tensor
+    batch["pcre_feats"][500][3, 2, 0, 1] = 0.5
+    assert bool(batch["pcre_pad_masks"][500][3, 2, 0])
+    wire2 = pack_wire(batch, compact=True)
+    assert set(wire2["xc_flat"]) == {2000, 100} and set(wire2["xc"]) == {500}
+    rounded["pcre_feats"][500] = batch["pcre_feats"][500].half().float()
+    assert torch.equal(eng.predict_wire(wire2), eng.predict_device(eng.to_device(rounded)).cpu())
