@@ -42,7 +42,9 @@ constexpr uint32_t OFF_Q = OFF_PE + SQ_MAX_NS * 256;         // [128 x 128] BF16
 constexpr uint32_t OFF_X = OFF_Q + 32768;                    // ring; after the pass: store staging + row exchange area
 constexpr uint32_t OFF_WB = OFF_X + SQ_NSTAGE * SQ_STAGE;    // W_in as a BF16 operand [16 x 128] (rows 7.. are zero)
 constexpr uint32_t OFF_CTL = OFF_WB + 4096;
-constexpr uint32_t SQ_SMEM = OFF_CTL + 128;
+constexpr uint32_t OFF_META = OFF_CTL + 128;                 // 2 x (64 region rows + key window) of the tile after this one
+constexpr uint32_t SQ_META = 66 * 4;
+constexpr uint32_t SQ_SMEM = OFF_META + 2 * SQ_META;
 constexpr uint32_t SQ_XCH = 4 * 32 * 132 * 4;                // exchange area inside the ring, behind the store staging
 static_assert(SQ_SMEM <= 227 * 1024, "shared memory budget");
 constexpr uint32_t QX_MAX = 0, QX_SUM = 1024, QX_XB = 2048, QX_XBAR = 2048 + 8192;
@@ -255,12 +257,28 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const __grid_c
         float* red_xb = reinterpret_cast<float*>(smem + OFF_X + SQ_XCH + QX_XB);
         float* xbar_s = reinterpret_cast<float*>(smem + OFF_X + SQ_XCH + QX_XBAR);
         const float scale2 = a.scale * 1.4426950408889634f;  // softmax in base 2
+        const int fr0 = ht >> 4, fpart = ht & 15;             // copy plan of the ring (below)
+        const int mreg = ht >> 1, modd = ht & 1;
+        // What a tile needs before its first copy can be issued - key window and the 64 region rows of the tile (permuted
+        // under a ragged plan) - is loaded a tile ahead into shared memory (two slots): dependent L2 round trips in front
+        // of the first HBM access of the tile otherwise.
+        auto tile_meta = [&](int g, int slot) {              // (threads 0..65 of the compute warps)
+            int* m = reinterpret_cast<int*>(smem + OFF_META + slot * SQ_META);
+            const int res = a.order[g / tiles_per_res], tile = g % tiles_per_res;
+            if (tid < 64) {
+                const int rr = tile * 64 + tid;
+                m[tid] = 2 * rr < rows_total ? (a.perm ? a.perm[rr] : rr) : 0;
+            } else if (tid == 64) m[64] = a.tile_k0[res] ? a.tile_k0[res][tile] : 0;
+            else if (tid == 65) m[65] = a.tile_ns[res] ? a.tile_ns[res][tile] : a.ns[res];
+        };
+        if ((int)blockIdx.x < total) tile_meta(blockIdx.x, 0);
+        compute_barrier();
         int it = 0;
         for (int g = blockIdx.x; g < total; g += gridDim.x, ++it) {
             const int res = a.order[g / tiles_per_res], tile = g % tiles_per_res;
             // key window [k0, k0 + ns) of the tile; n, nF, X and MK are relative to its first key
-            const int k0 = a.tile_k0[res] ? a.tile_k0[res][tile] : 0;
-            const int ns = a.tile_ns[res] ? a.tile_ns[res][tile] : a.ns[res];
+            const int* meta = reinterpret_cast<const int*>(smem + OFF_META + (it & 1) * SQ_META);
+            const int k0 = meta[64], ns = meta[65];
             const int n = a.n[res] - k0;
             const int CA = first_half_chunks(ns), CB = (ns >> 3) - CA;
             const int row0 = tile * 128;
@@ -277,19 +295,13 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const __grid_c
             // ring: chunk idx of this half (8 keys x 7 features per region, and the 8 mask bytes).  Copy plan: the 16
             // threads ht/16*16.. move the fourteen 16-byte parts of ONE 224-byte chunk row (contiguous in HBM), regions
             // ht/16 + 8k for k = 0..7; x_row_off(r0 + 8k) = x_row_off(r0) + 1792 k + 16 (k & 1) + 32 (k >> 1).
-            const int fr0 = ht >> 4, fpart = ht & 15;
             const bool fact = fpart < 14;
-            uint32_t fsrc[8];                                  // the thread's eight region rows (permuted under a ragged plan),
-#pragma unroll                                                 // in float4 units from X (n % 4 == 0)
-            for (int k = 0; k < 8; ++k) {
-                const int rr = region0 + fr0 + 8 * k;
-                const bool rv = 2 * (fr0 + 8 * k) < rows_valid;
-                fsrc[k] = (uint32_t)(((long long)(rv ? (a.perm ? a.perm[rr] : rr) : 0) * rstride) >> 2) + fpart;
-            }
+            uint32_t fsrc[8];                                  // the thread's eight region rows, in float4 units from X (n % 4 == 0)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) fsrc[k] = (uint32_t)(((long long)meta[fr0 + 8 * k] * rstride) >> 2) + fpart;
             const uint32_t fdst = s_ring + half * SQ_HALF_X + x_row_off(fr0) + fpart * 16;
-            const int mreg = ht >> 1, modd = ht & 1;
             const bool mvalid = 2 * mreg < rows_valid;
-            const uint8_t* msrc = MK + (long long)(mvalid ? (a.perm ? a.perm[region0 + mreg] : region0 + mreg) : 0) * mstride + modd * 4;
+            const uint8_t* msrc = MK + (long long)meta[mreg] * mstride + modd * 4;
             const uint32_t mdst = s_ring + SQ_STAGE_X + half * 512 + mreg * 8 + modd * 4;
             auto fetch = [&](int idx, int stage) {
                 if (idx < c_cnt) {
@@ -311,6 +323,8 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const __grid_c
             };
             fetch(0, 0);
             fetch(1, 1);
+            // the tile after this one: its slot was last read at the top of the previous tile, a barrier ago
+            if (g + (int)gridDim.x < total) tile_meta(g + gridDim.x, (it + 1) & 1);
 
             mbar_wait(&bars[B_S], it & 1);
             tc_fence_after();
@@ -406,6 +420,12 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const __grid_c
             tmem_st_wait();
             tc_fence_before();
             warp_arrive(&bars[half ? B_PB : B_PA], lane);
+            // W_in rows of the thread's four output channels: used in the epilogue, in flight under the exchange and MMA 2
+            float w4[4][SQ_F];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+#pragma unroll
+                for (int f = 0; f < SQ_F; ++f) w4[e][f] = __ldg(W + (4 * lane + e) * SQ_F + f);
 
             // ---- exchange the halves: common maximum, 1 / sum, xbar per row (in the ring, once every warp has left it) ----
             compute_barrier();
@@ -459,11 +479,6 @@ __global__ void __launch_bounds__(SQ_THREADS, 1) sqa_fused_kernel(const __grid_c
             warp_arrive(&bars[B_EPI], lane);
             compute_barrier();                                // staging + xbar_s complete
             {
-                float w4[4][SQ_F];
-#pragma unroll
-                for (int e = 0; e < 4; ++e)
-#pragma unroll
-                    for (int f = 0; f < SQ_F; ++f) w4[e][f] = __ldg(W + (4 * lane + e) * SQ_F + f);
                 float* C = a.cbar + res * a.cbar_z + (long long)row0 * 128;
                 __nv_bfloat16* Cb = a.cbar_bf16 ? a.cbar_bf16 + 2 * res * a.cbar_z + (long long)row0 * 128 : nullptr;   // (same byte stride as the FP32 view)
 #pragma unroll 4
