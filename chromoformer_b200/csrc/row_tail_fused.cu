@@ -32,7 +32,8 @@ constexpr uint32_t RT_TMEM_COLS = 256;
 constexpr uint32_t RT_OFF_PRM = RT_OFF_STAGE + RT_NSTAGE * RT_CHUNK_BYTES;   // 1024 floats of parameters
 constexpr uint32_t RT_OFF_RED = RT_OFF_PRM + 4096;            // 2 x 512 floats of LayerNorm partials
 constexpr uint32_t RT_OFF_CTL = RT_OFF_RED + 4096;
-constexpr uint32_t RT_SMEM = RT_OFF_CTL + 256;
+constexpr uint32_t RT_OFF_YROW = RT_OFF_CTL + 256;            // output row of every tile row (128 ints)
+constexpr uint32_t RT_SMEM = RT_OFF_YROW + 512;
 
 enum { T_FULL0 = 0, T_FREE0 = 3, T_AREADY = 6, T_UREADY, T_FREADY, T_ACCO, T_ACCF1, T_ACCF2, T_COUNT };
 
@@ -131,6 +132,9 @@ __global__ void __maxnreg__(96) row_tail_fused_kernel(const RowTailArgs a) {
         float v[32];
         float* prm = reinterpret_cast<float*>(smem + RT_OFF_PRM);
         float* red = reinterpret_cast<float*>(smem + RT_OFF_RED);
+        int* yrow_s = reinterpret_cast<int*>(smem + RT_OFF_YROW);
+        // residual row of this thread's tile row (a gather under a ragged plan): the lookup travels under phase 0
+        const int res_m = valid ? (a.res_rows ? a.res_rows[m] : m) / a.res_div : 0;
 
         // ---- phase 0: parameters -> shared;  Cbar tile (FP32 [128 x 256]) -> BF16 operand
         {
@@ -140,6 +144,10 @@ __global__ void __maxnreg__(96) row_tail_fused_kernel(const RowTailArgs a) {
             for (int k = 0; k < 6; ++k)
                 if (ct < 128) prm[k * 128 + ct] = srcs[k][z * a.p_z + ct];
             if (ct < a.dff) prm[768 + ct] = a.b1[z * a.p_z + ct];
+            if (ct < 128) {                                     // output rows (remapped / scattered), once per tile row
+                const int mm = m0 + ct;
+                yrow_s[ct] = ct < rows_valid ? (a.y_rows ? a.y_rows[mm] : (mm / a.c_div) * a.c_mul + (mm % a.c_div) + a.c_add) : 0;
+            }
             const float* A = a.a + z * a.a_z;
             if (a.a_bf16) {                                     // BF16 rows: 16-byte chunks go straight into the operand
                 const __nv_bfloat16* Ab = a.a_bf16 + 2 * z * a.a_z;   // (same byte stride as the FP32 view)
@@ -190,7 +198,7 @@ __global__ void __maxnreg__(96) row_tail_fused_kernel(const RowTailArgs a) {
         float u_keep[2][32];
         {
             // residual rows first: their (row-strided) loads overlap the out-projection MMA
-            const float* res = a.res + z * a.res_z + (valid ? (long long)((a.res_rows ? a.res_rows[m] : m) / a.res_div) * 128 : 0);
+            const float* res = a.res + z * a.res_z + (long long)res_m * 128;
 #pragma unroll
             for (int ci = 0; ci < 2; ++ci) {
                 const int c = (2 * ci + ch) * 32;
@@ -315,12 +323,8 @@ __global__ void __maxnreg__(96) row_tail_fused_kernel(const RowTailArgs a) {
                     const int r = it * 4 + (lane >> 3);
                     const float* sp = stage + r * 33 + cq;
                     const int trw = lq * 32 + r;
-                    if (trw < rows_valid) {
-                        const int mm = m0 + trw;
-                        const long long yrow = a.y_rows ? (long long)a.y_rows[mm]
-                                                        : (long long)(mm / a.c_div) * a.c_mul + (mm % a.c_div) + a.c_add;
-                        *reinterpret_cast<float4*>(Y + yrow * 128 + c + cq) = make_float4(sp[0], sp[1], sp[2], sp[3]);
-                    }
+                    if (trw < rows_valid)
+                        *reinterpret_cast<float4*>(Y + (long long)yrow_s[trw] * 128 + c + cq) = make_float4(sp[0], sp[1], sp[2], sp[3]);
                 }
                 __syncwarp();
             }
