@@ -781,7 +781,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     auto lin_fp32 = [&](const GemmArgs& g, int nz) -> int { return gemm_launch(g, true, true, nz, st); };
 
     RaggedPlan plan;                            // (ragged.cu; built next to the Embedding stage when the fused kernels run)
-    bool ragged = false, reg_plan = false;
+    bool ragged = false, reg_plan = false, reg_y_att = false;
     if (!only) {
     // ---------------- Embedding transformer, centre query (net.py:31-59) ----
     {
@@ -1118,9 +1118,10 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
                 a.n_layers = c->reg_layers;
                 a.y_mid = ws + w.r_out; a.y_mid_z = RS; a.y_l = w.rslots > 1 ? w.r_slot : 0;
                 if (!only) a.y = ws + w.r_out + (long long)w.rslot(c->reg_layers - 1) * w.r_slot;
-                // under a plan a tile's rows are scattered over the [B*S, 128] layout, where the rows of the last layer
-                // must not land in another tile's parking block: they go to the (unused) attention buffer of the layer path
-                if (reg_plan) a.y = ws + w.r_att;
+                // the rows of the last layer must not land in a parking block of the scratch slots (a persistent CTA parks
+                // in the block of its own index, and under a plan a tile's rows are scattered over the [B*S, 128] layout):
+                // they go to the (otherwise unused) attention buffer of the layer-by-layer path
+                if (!only) { a.y = ws + w.r_att; reg_y_att = true; }
                 a.p_l = c->reg_layers > 1 ? L.reg[0].att[1].gamma_f - L.reg[0].att[0].gamma_f : 0;
             }
             a.wstream = reinterpret_cast<const __nv_bfloat16*>(ws + w.reg_stream) + (long long)l * reg_stream_elems_per_layer();
@@ -1192,7 +1193,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
     {
         HeadGatherArgs a;
         a.B = B; a.S = S; a.D = D; a.n_res = NR;
-        a.xout = reg_plan ? ws + w.r_att : ws + w.r_out + (long long)w.rslot(c->reg_layers - 1) * w.r_slot;
+        a.xout = reg_y_att ? ws + w.r_att : ws + w.r_out + (long long)w.rslot(c->reg_layers - 1) * w.r_slot;
         a.xin = ws + w.r_xin; a.zstride = RS; a.z = ws + w.h_z;
         launch_pdl(head_gather_kernel, dim3((B * NR * D + 255) / 256), dim3(256), 0, st, a);
         CHROMO_CHECK_LAUNCH("head_gather");
