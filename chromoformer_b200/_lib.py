@@ -82,7 +82,6 @@ EXPORTS = {
     "chromo_pack_linear_weight": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int64, c_void_p]),
     "chromo_launch_counter": (c_int64, [c_int32]),
     "chromo_debug_trace": (c_int32, [c_void_p]),
-    "chromo_debug_umma_probe": (c_int32, [c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p]),
     "chromo_backward": (c_int32, [POINTER(Config), c_void_p, POINTER(Batch), c_void_p, c_void_p, c_void_p,
                                   c_int64, c_int32, c_void_p]),
     "chromo_matmul": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_int32,

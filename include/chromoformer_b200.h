@@ -151,9 +151,6 @@ int chromo_linear(const float* x, const float* w, const float* bias, float* y, i
 int chromo_pack_linear_weight(const float* w, uint16_t* packed, int32_t n, int32_t k, int32_t batches,
                               int64_t w_stride, void* stream);
 
-/* Test-only hardware-semantics probe (MN-major B operand, A operand in TMEM); see csrc/umma_probe.cu. */
-int chromo_debug_umma_probe(int32_t mode, const float* a, const float* b, float* d, int32_t n, int32_t k, void* stream);
-
 /* Profiling hook: while `buf` (device memory, 1536 int64, zero-filled by the caller) is set, CTA (0,0) of every fused
  * Regulation launch logs (event id << 48 | clock64) for its driver thread ([0,512)), one score warp ([512,1024)) and one
  * value warp ([1024,1536)); NULL switches it off.  tools/reg_timeline.py prints the timeline. */

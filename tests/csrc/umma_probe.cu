@@ -1,9 +1,11 @@
 // Hardware-semantics probes for the next step of the fused Regulation kernel (attention on the tensor
 // pipe): (1) B operand in MN-major shared-memory layout, (2) A operand in TMEM written by tcgen05.st.
 // D[128, N] = A[128, K] * B  with B given as [K, N] row-major FP32; M = 128, N % 16 == 0, K % 16 == 0.
-// Test-only entry point (tests/test_umma_probe_gpu.py); nothing in the product path calls it.
-#include "common.cuh"
-#include "umma_ptx.cuh"
+// Test-only: built into tests/libchromo_probe.so (not into the product library) by __graft_entry__.build().
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../chromoformer_b200/csrc/umma_ptx.cuh"
 
 namespace chromo {
 
@@ -107,10 +109,9 @@ using namespace chromo;
 
 extern "C" int chromo_debug_umma_probe(int32_t mode, const float* A, const float* B, float* D, int32_t n, int32_t k,
                                        void* stream) {
-    if (!A || !B || !D || n < 16 || n > 256 || n % 16 || k < 16 || k > 256 || k % 16) { set_error("umma_probe: bad argument"); return CHROMO_EINVAL; }
+    if (!A || !B || !D || n < 16 || n > 256 || n % 16 || k < 16 || k > 256 || k % 16) return -1;
     const size_t smem = (size_t)(128 + n) * k * 2 + 64;
     cudaFuncSetAttribute(umma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     umma_probe_kernel<<<1, 128, smem, (cudaStream_t)stream>>>(mode, A, B, D, n, k);
-    CHROMO_CHECK_LAUNCH("umma_probe");
-    return CHROMO_OK;
+    return cudaGetLastError() == cudaSuccess ? 0 : -3;
 }
