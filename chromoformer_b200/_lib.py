@@ -96,6 +96,8 @@ EXPORTS = {
                                      POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32), c_void_p]),
     "chromo_unpack_compact": (c_int32, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int32),
                                         POINTER(c_void_p), POINTER(c_int32), POINTER(c_int32), c_int32, c_void_p]),
+    "chromo_unpack_sparse": (c_int32, [c_int32, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int32),
+                                       POINTER(c_void_p), POINTER(c_int64), c_void_p]),
     "chromo_bin_regions": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, POINTER(c_int32),
                                      POINTER(c_int32), POINTER(c_void_p), c_void_p, c_void_p]),
 }

@@ -355,7 +355,74 @@ __global__ void __launch_bounds__(256) unpack_compact_kernel(const CompactArgs a
     for (int e = lane; e < nF; e += 32) dst[e] = (e >= lo && e < hi) ? __half2float(src[e]) : 0.f;
 }
 
+// Zero-suppressed wire: ln(mean + 1) of binned read depth is exactly zero wherever no read fell (37 % of the demo's bins),
+// so a feature tensor travels as an occupancy bitmap (one bit per value) + its non-zero FP16 values + the running count of
+// non-zeros at every block of 1024 values.  One warp per block: lane = bitmap word, its values start at the block's count
+// plus the popcounts of the lanes in front.
+struct SparseArgs {
+    int n_seg;
+    const uint32_t* bits[WIRE_MAX]; const __half* vals[WIRE_MAX]; const int* off[WIRE_MAX]; int base[WIRE_MAX];
+    float* dst[WIRE_MAX]; long long count[WIRE_MAX];
+};
+__global__ void __launch_bounds__(256) unpack_sparse_kernel(const SparseArgs a) {
+    const int seg = blockIdx.y, lane = threadIdx.x & 31;
+    const long long count = a.count[seg], n_blk = (count + 1023) >> 10;
+    const long long stride = (long long)gridDim.x * 8;
+    for (long long blk = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); blk < n_blk; blk += stride) {
+        const long long v0 = (blk << 10) + 32 * lane;                     // first value of this lane's word
+        const uint32_t word = v0 < count ? __ldg(a.bits[seg] + (blk << 5) + lane) : 0u;
+        int before = __popc(word);
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, before, o);
+            if (lane >= o) before += t;
+        }
+        before -= __popc(word);                                            // exclusive
+        const __half* src = a.vals[seg] + (long long)(__ldg(a.off[seg] + blk) - a.base[seg]) + before;
+        float out[32];
+        int k = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const bool on = (word >> j) & 1u;
+            out[j] = on ? __half2float(src[k]) : 0.f;
+            k += on;
+        }
+        float* dst = a.dst[seg] + v0;
+        if (v0 + 32 <= count) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(out[j], out[j + 1], out[j + 2], out[j + 3]);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+                if (v0 + j < count) dst[j] = out[j];
+        }
+    }
+}
+
 }  // namespace chromo
+
+extern "C" int chromo_unpack_sparse(int32_t n_seg, const uint32_t* const* bits, const uint16_t* const* vals,
+                                    const int32_t* const* offsets, const int32_t* base, float* const* dst,
+                                    const int64_t* counts, void* stream) {
+    using namespace chromo;
+    if (n_seg < 1 || n_seg > WIRE_MAX) { set_error("unpack_sparse: 1..%d segments", WIRE_MAX); return CHROMO_EINVAL; }
+    SparseArgs a;
+    a.n_seg = n_seg;
+    long long most = 0;
+    for (int i = 0; i < n_seg; ++i) {
+        if (!bits[i] || !vals[i] || !offsets[i] || !dst[i] || counts[i] < 0) { set_error("unpack_sparse: bad segment %d", i); return CHROMO_EINVAL; }
+        if (reinterpret_cast<uintptr_t>(dst[i]) & 15) { set_error("unpack_sparse: segment %d is not 16-byte aligned", i); return CHROMO_EINVAL; }
+        a.bits[i] = bits[i]; a.vals[i] = reinterpret_cast<const __half*>(vals[i]); a.off[i] = offsets[i]; a.base[i] = base[i];
+        a.dst[i] = dst[i]; a.count[i] = counts[i];
+        most = counts[i] > most ? counts[i] : most;
+    }
+    if (most == 0) return CHROMO_OK;
+    long long blocks = ((most + 1023) / 1024 + 7) / 8;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    unpack_sparse_kernel<<<dim3((unsigned)blocks, n_seg), 256, 0, (cudaStream_t)stream>>>(a);
+    CHROMO_CHECK_LAUNCH("unpack_sparse");
+    return CHROMO_OK;
+}
 
 extern "C" int chromo_unpack_compact(int32_t n_sets, const uint16_t* const* src, const int32_t* const* spans,
                                      const int32_t* const* offsets, const int32_t* base, float* const* dst,

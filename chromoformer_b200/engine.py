@@ -66,7 +66,23 @@ def _spans_of(rows):
     return torch.stack([lo, cnt], -1).to(torch.int32).contiguous(), exact
 
 
-def pack_wire(batch, pin=True, compact=False):
+def _sparse_pack(t16, fin):
+    """FP16 tensor -> (occupancy bitmap as int32 words, its non-zero values in order, non-zeros in front of every block of
+    1024 values [blocks + 1]) for chromo_unpack_sparse."""
+    import numpy as np
+    flat = t16.reshape(-1)
+    nz = (flat != 0)
+    total = flat.numel()
+    n_blk = (total + 1023) // 1024
+    pad = torch.zeros(n_blk * 1024, dtype=torch.bool)
+    pad[:total] = nz
+    bits = torch.from_numpy(np.packbits(pad.numpy(), bitorder="little").view(np.int32).copy())
+    off = torch.zeros(n_blk + 1, dtype=torch.int64)
+    off[1:] = pad.view(n_blk, 1024).sum(1).cumsum(0)
+    return fin(bits), fin(flat[nz]), fin(off.to(torch.int32))
+
+
+def pack_wire(batch, pin=True, compact=False, sparse=False):
     """Forward arguments (host tensors, reference layout) -> the FP16 / span wire format in (pinned) host memory.
     This is producer-side work (a DataLoader collate_fn or `GeneBatcher` would emit it directly); it is NOT part of
     the transport being timed.
@@ -75,15 +91,25 @@ def pack_wire(batch, pin=True, compact=False):
     [B*I + 1] first bin of every region): data.py:86-97 pads every pCRE to w_max / bin_size bins with zeros and
     data.py:175-177 fills dummy slots with zeros, so nothing else carries information - 14 kB instead of 64 kB per gene of
     the demo set.  Falls back to the full tensors for a resolution whose masks are not spans or whose padded bins are not
-    all zero."""
+    all zero.
+
+    `sparse`: zero-suppressed features (`*_bits` occupancy bitmap, `*_vals` non-zero FP16 values, `*_off` running counts per
+    1024 values; chromo_unpack_sparse): ln(mean + 1) is exactly 0 wherever no read fell (data.py:75-80), 37 % of the demo's
+    bins.  Lossless."""
     fin = (lambda t: t.contiguous().pin_memory()) if pin else (lambda t: t.contiguous())
     bins = list(batch["promoter_feats"].keys())
     wire = {_WIRE_BINS: bins, "xp": {}, "xc": {}, "span_p": {}, "span_c": {}, "rows_p": {}, "rows_c": {}, "imask": {},
             "xc_flat": {}, "off_c": {}}
+    for k in ("xp", "xc"):
+        for suffix in ("_bits", "_vals", "_off"):
+            wire[k + suffix] = {}
     for b in bins:
         xp, xc = batch["promoter_feats"][b], batch["pcre_feats"][b]
         n = xp.size(-2)
-        wire["xp"][b] = fin(xp.to(torch.float16))
+        if sparse:
+            wire["xp_bits"][b], wire["xp_vals"][b], wire["xp_off"][b] = _sparse_pack(xp.to(torch.float16), fin)
+        else:
+            wire["xp"][b] = fin(xp.to(torch.float16))
         done = False
         for key, src in (("p", batch["promoter_pad_masks"][b]), ("c", batch["pcre_pad_masks"][b])):
             rows = _centre_rows(src.bool(), n)
@@ -99,11 +125,14 @@ def pack_wire(batch, pin=True, compact=False):
                 off[1:] = valid.sum(-1).reshape(-1).cumsum(0)
                 wire["off_c"][b] = fin(off.to(torch.int32))
                 done = True
-        if not done:
+        if not done and sparse:
+            wire["xc_bits"][b], wire["xc_vals"][b], wire["xc_off"][b] = _sparse_pack(xc.to(torch.float16), fin)
+        elif not done:
             wire["xc"][b] = fin(xc.to(torch.float16))
         wire["imask"][b] = fin(batch["interaction_masks"][b].bool())
     wire["freq"] = fin(batch["interaction_freq"].to(torch.float32))
     wire["_shape_c"] = [(b, tuple(batch["pcre_feats"][b].shape[1:])) for b in bins]     # [I, n, F] of every resolution
+    wire["_shape_p"] = [(b, tuple(batch["promoter_feats"][b].shape[1:])) for b in bins]
     return wire
 
 
@@ -206,8 +235,34 @@ class InferenceEngine:
         return host
 
     # ---- FP16 / span wire ------------------------------------------------------------------------------------
+    def _sparse_slices(self, wire, n):
+        """Per zero-suppressed tensor (key, bin): values per gene and, for every chunk, (first block, last block + 1, first
+        value, last value + 1) of its slice of the stream."""
+        import math
+        out = {}
+        shapes = {"xp": dict(wire["_shape_p"]), "xc": dict(wire["_shape_c"])}
+        for k in ("xp", "xc"):
+            for b, off in wire[k + "_off"].items():
+                V = math.prod(shapes[k][b])
+                if (self.chunk * V) % 1024 and n > self.chunk:
+                    raise ValueError(f"zero-suppressed wire: chunk * {V} values per gene must be a multiple of 1024")
+                rows = []
+                for lo in range(0, n, self.chunk):
+                    hi = min(n, lo + self.chunk)
+                    b0, b1 = lo * V // 1024, (hi * V + 1023) // 1024
+                    rows.append((b0, b1))
+                idx = torch.tensor([r[0] for r in rows] + [rows[-1][1]])
+                cnt = off[idx].tolist()
+                out[(k, b)] = (V, [(b0, b1, cnt[i], off[b1].item() if i + 1 == len(rows) else cnt[i + 1])
+                                   for i, (b0, b1) in enumerate(rows)])
+        return out
+
     def _wire_staging(self, wire):
         shape_c = dict(wire["_shape_c"])
+        shape_p = dict(wire["_shape_p"])
+        n_genes = wire["freq"].size(0)
+        sparse = self._sparse_slices(wire, n_genes)
+        sp_caps = {kb: max(max(v1 - v0 for (_, _, v0, v1) in rows), 1) for kb, (V, rows) in sparse.items()}
         # compact pCRE streams: a staging set holds the longest chunk of THIS wire
         caps = {}
         for b, off in wire["off_c"].items():
@@ -216,32 +271,42 @@ class InferenceEngine:
             edges = off[torch.arange(0, n + self.chunk, self.chunk).clamp(max=n) * I].long()
             caps[b] = int((edges[1:] - edges[:-1]).max().item()) if n else 0
         sig = tuple((k, b, tuple(t.shape[1:]), t.dtype) for k, v in wire.items() if isinstance(v, dict)
-                    for b, t in v.items()) + (tuple(wire["freq"].shape[1:]), tuple(sorted(caps.items())))
+                    for b, t in v.items()) + (tuple(wire["freq"].shape[1:]), tuple(sorted(caps.items())),
+                                              tuple(sorted(sp_caps.items())))
         if getattr(self, "_wstage", None) is not None and self._wstage[0] == sig:
             return self._wstage[1], self._wstage[2]
         mk = lambda t, dt=None: torch.empty((self.chunk,) + tuple(t.shape[1:]), dtype=dt or t.dtype, device=self.device)
         sets = []
         for _ in range(2):
-            st = {k: {b: mk(t) for b, t in v.items()} for k, v in wire.items() if isinstance(v, dict) and k not in ("xc_flat", "off_c")}
+            st = {k: {b: mk(t) for b, t in v.items()} for k, v in wire.items()
+                  if isinstance(v, dict) and k not in ("xc_flat", "off_c") and not k.endswith(("_bits", "_vals", "_off"))}
+            for k in ("xp", "xc"):
+                st[k + "_bits"], st[k + "_vals"], st[k + "_off"] = {}, {}, {}
+            for (k, b), (V, rows) in sparse.items():
+                nb = (self.chunk * V + 1023) // 1024 + 1
+                st[k + "_bits"][b] = torch.empty(nb * 32, dtype=torch.int32, device=self.device)
+                st[k + "_off"][b] = torch.empty(nb + 1, dtype=torch.int32, device=self.device)
+                st[k + "_vals"][b] = torch.empty(sp_caps[(k, b)], dtype=torch.float16, device=self.device)
             st["xc_flat"] = {b: torch.empty((max(caps[b], 1),) + tuple(t.shape[1:]), dtype=t.dtype, device=self.device)
                              for b, t in wire["xc_flat"].items()}
             st["off_c"] = {b: torch.empty(self.chunk * shape_c[b][0] + 1, dtype=torch.int32, device=self.device)
                            for b in wire["off_c"]}
             st["freq"] = mk(wire["freq"])
             sets.append(st)
-        wide = {"promoter_feats": {b: mk(t, torch.float32) for b, t in wire["xp"].items()},
+        wide = {"promoter_feats": {b: torch.empty((self.chunk,) + shape_p[b], dtype=torch.float32, device=self.device)
+                                   for b in wire[_WIRE_BINS]},
                 "pcre_feats": {b: torch.empty((self.chunk,) + shape_c[b], dtype=torch.float32, device=self.device)
                                for b in wire[_WIRE_BINS]},
                 "promoter_pad_masks": {}, "pcre_pad_masks": {}}
         for b in wire[_WIRE_BINS]:
-            n = wire["xp"][b].size(-2)
+            n = shape_p[b][-2]
             for key, name, reg in (("p", "promoter_pad_masks", 1), ("c", "pcre_pad_masks", shape_c[b][0])):
                 if b in wire["span_" + key]:
                     wide[name][b] = torch.empty(self.chunk, reg, n, dtype=torch.bool, device=self.device)
         self._wstage = (sig, sets, wide)
         return sets, wide
 
-    def _unpack(self, st, wide, m, bins, base=None):
+    def _unpack(self, st, wide, m, bins, base=None, sparse_base=None):
         """One chromo_unpack_wire launch: FP16 -> FP32 features, spans -> centre-row masks, for the first m genes; compact
         pCRE streams (valid bins only, `base[b]` = stream position the staged chunk starts at) by chromo_unpack_compact."""
         lib = _lib.load()
@@ -269,6 +334,19 @@ class InferenceEngine:
                                           arr(ctypes.c_int64, cnt), len(spans), arr(ctypes.c_void_p, spans),
                                           arr(ctypes.c_void_p, masks), arr(ctypes.c_int32, rows), arr(ctypes.c_int32, nb),
                                           stream), "chromo_unpack_wire")
+        s_bits, s_vals, s_off, s_base, s_dst, s_cnt = [], [], [], [], [], []
+        for k16, k32 in (("xp", "promoter_feats"), ("xc", "pcre_feats")):
+            for b in st[k16 + "_bits"]:
+                w = wide[k32][b]
+                s_bits.append(st[k16 + "_bits"][b].data_ptr()); s_vals.append(st[k16 + "_vals"][b].data_ptr())
+                s_off.append(st[k16 + "_off"][b].data_ptr()); s_base.append(int(sparse_base[(k16, b)]))
+                s_dst.append(w.data_ptr()); s_cnt.append(m * w[0].numel())
+        for i in range(0, len(s_bits), 8):                      # (at most 8 segments per launch)
+            j = slice(i, i + 8)
+            _lib.check(lib.chromo_unpack_sparse(len(s_bits[j]), arr(ctypes.c_void_p, s_bits[j]), arr(ctypes.c_void_p, s_vals[j]),
+                                                arr(ctypes.c_void_p, s_off[j]), arr(ctypes.c_int32, s_base[j]),
+                                                arr(ctypes.c_void_p, s_dst[j]), arr(ctypes.c_int64, s_cnt[j]), stream),
+                       "chromo_unpack_sparse")
         if c_src:
             _lib.check(lib.chromo_unpack_compact(len(c_src), arr(ctypes.c_void_p, c_src), arr(ctypes.c_void_p, c_sp),
                                                  arr(ctypes.c_void_p, c_off), arr(ctypes.c_int32, c_base),
@@ -291,6 +369,7 @@ class InferenceEngine:
         copied = [torch.cuda.Event() for _ in bounds]
         freed = [torch.cuda.Event() for _ in bounds]
         shape_c = dict(wire["_shape_c"])
+        sparse = self._sparse_slices(wire, n)
         # stream positions of the chunk boundaries of every compact pCRE stream (host integers, once per call)
         edges = {b: off[torch.tensor([lo for lo, _ in bounds] + [n]) * shape_c[b][0]].tolist() for b, off in wire["off_c"].items()}
 
@@ -303,9 +382,15 @@ class InferenceEngine:
                 cs.wait_stream(main)
             with torch.cuda.stream(cs):
                 for k, v in wire.items():
-                    if isinstance(v, dict) and k not in ("xc_flat", "off_c"):
+                    if isinstance(v, dict) and k not in ("xc_flat", "off_c") and not k.endswith(("_bits", "_vals", "_off")):
                         for b, t in v.items():
                             dst[k][b][:hi - lo].copy_(t[lo:hi], non_blocking=True)
+                for (k, b), (V, rows) in sparse.items():             # zero-suppressed features: the chunk's blocks
+                    b0, b1, v0, v1 = rows[i]
+                    dst[k + "_bits"][b][:(b1 - b0) * 32].copy_(wire[k + "_bits"][b][b0 * 32:b1 * 32], non_blocking=True)
+                    dst[k + "_off"][b][:b1 - b0 + 1].copy_(wire[k + "_off"][b][b0:b1 + 1], non_blocking=True)
+                    if v1 > v0:
+                        dst[k + "_vals"][b][:v1 - v0].copy_(wire[k + "_vals"][b][v0:v1], non_blocking=True)
                 for b, off in wire["off_c"].items():                 # compact pCRE stream: the chunk's slice of it
                     I = shape_c[b][0]
                     r0, r1 = edges[b][i], edges[b][i + 1]
@@ -321,7 +406,8 @@ class InferenceEngine:
                 upload(i + 1)
             main.wait_event(copied[i])
             st, m = sets[i % 2], hi - lo
-            self._unpack(st, wide, m, bins, base={b: edges[b][i] for b in edges})
+            self._unpack(st, wide, m, bins, base={b: edges[b][i] for b in edges},
+                         sparse_base={kb: rows[i][2] for kb, (V, rows) in sparse.items()})
             batch = {"promoter_feats": {b: wide["promoter_feats"][b][:m] for b in bins},
                      "pcre_feats": {b: wide["pcre_feats"][b][:m] for b in bins},
                      "promoter_pad_masks": {b: (wide["promoter_pad_masks"][b][:m] if b in st["span_p"] else st["rows_p"][b][:m])

@@ -96,3 +96,28 @@ def test_compact_wire_ships_valid_bins_only():
     assert set(wire2["xc_flat"]) == {2000, 100} and set(wire2["xc"]) == {500}
     rounded["pcre_feats"][500] = batch["pcre_feats"][500].half().float()
     assert torch.equal(eng.predict_wire(wire2), eng.predict_device(eng.to_device(rounded)).cpu())
+
+
+@pytest.mark.parametrize("ragged", [False, True])
+def test_zero_suppressed_wire_is_lossless(ragged):
+    """engine.pack_wire(sparse=True): occupancy bitmap + non-zero FP16 values (chromo_unpack_sparse) - bit-identical to the
+    ordinary path, fewer bytes in proportion to the exact zeros of ln(mean + 1)."""
+    model = _mk(seed=6).cuda().eval()
+    model.precision = "bf16"
+    n = 700
+    batch = synthetic.make_batch(n, ragged=ragged, seed=41, stress=True)
+    rounded = dict(batch)
+    for key in ("promoter_feats", "pcre_feats"):
+        rounded[key] = {b: t.half().float() for b, t in batch[key].items()}
+    eng = InferenceEngine(model, chunk=256, device_chunk=256)
+    want = eng.predict_device(eng.to_device(rounded)).cpu()
+    wire = pack_wire(batch, sparse=True)
+    assert not wire["xp"] and not wire["xc"] and set(wire["xc_bits"]) == set(BINS)
+    assert wire_nbytes(wire) < 0.75 * wire_nbytes(pack_wire(batch))
+    assert torch.equal(eng.predict_wire(wire), want)
+    # together with the compact pCRE stream of ragged genes (promoters zero-suppressed, pCREs as valid bins)
+    both = pack_wire(batch, sparse=True, compact=True)
+    assert torch.equal(eng.predict_wire(both), want)
+    # a chunk whose value count is not a multiple of 1024 is refused, not mis-sliced
+    with pytest.raises(ValueError):
+        InferenceEngine(model, chunk=100).predict_wire(wire)
