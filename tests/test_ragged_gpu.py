@@ -64,6 +64,10 @@ def test_ragged_batch_with_and_without_plan():
     assert (got[idx] - want).abs().max().item() < BF16_TOL
     # every pCRE count of the histogram is in the checked genes
     assert set(batch["n_partners"][idx].tolist()) >= {0, 1, 8}
+    # the reference DataLoader's own collation ([B,I,1,n,n] masks: the plan reads the centre rows through the stride)
+    sub = synthetic.slice_batch(batch, 0, 256)
+    full = synthetic.expand_full_masks(sub)
+    assert torch.equal(_run(model, full, True), _run(model, sub, True))
 
 
 def test_dense_batch_keeps_its_numbers():
@@ -149,3 +153,38 @@ def test_ragged_imax16_token_classes():
     want = _oracle_logits(sd, batch, sel)
     assert (got[sel] - want).abs().max().item() < BF16_TOL
     assert len(set(k[sel].tolist())) >= 10
+
+
+def test_plan_is_capturable_into_a_cuda_graph():
+    """The plan is built on a library-owned side stream (fork / join by events) with a cub sort and a memset in it: all of
+    that must be legal inside a stream capture, and a replay must rebuild the plan from the CURRENT contents of the inputs."""
+    n = 512
+    model = _mk(seed=17).cuda().eval()
+    model.precision = "bf16"
+    eng = InferenceEngine(model, chunk=n)
+    a = eng.to_device(synthetic.make_batch(n, ragged=True, seed=51))
+    b = eng.to_device(synthetic.make_batch(n, ragged=True, seed=52))
+    a["dense"] = b["dense"] = False
+    keys = [k for k in a if k != "dense"]
+    with torch.no_grad():
+        want_a = model.forward_batch(a).clone()
+        want_b = model.forward_batch(b).clone()
+        static = {k: ({bb: t.clone() for bb, t in a[k].items()} if isinstance(a[k], dict) else a[k].clone()) for k in keys}
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            model.forward_batch(static)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = model.forward_batch(static)
+        g.replay()
+        assert torch.equal(out, want_a)
+        for k in keys:                                   # other genes, other plan, same graph
+            if isinstance(static[k], dict):
+                for bb in static[k]:
+                    static[k][bb].copy_(b[k][bb])
+            else:
+                static[k].copy_(b[k])
+        g.replay()
+        assert torch.equal(out, want_b)
