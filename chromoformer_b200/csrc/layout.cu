@@ -273,7 +273,7 @@ WsLayout make_ws_layout(const chromo_config_t* c, int batch, int flags) {
         w.r_preY = take((int64_t)T * D);
         {   // (the fused multi-layer kernel parks whole 128-row tiles of floor(128 / S) genes here between layers)
             const int64_t G = 128 / S > 0 ? 128 / S : 1;
-            const int64_t tiles = (B + G - 1) / G + 8;        // (+ the partly filled tiles of a ragged plan's token classes)
+            const int64_t tiles = (B + G - 1) / G + 16;       // (+ the partly filled tiles of a ragged plan's token classes)
             w.r_out = take(std::max((int64_t)T * D, tiles * 128 * D));
         }
         w.r_slot = cur - s0;

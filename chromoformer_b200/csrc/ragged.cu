@@ -35,15 +35,13 @@ inline long long temp_ints(long long R) { return 4 * R + 65536; }
 
 // n_partners of every gene from its interaction masks: k such that mask[j][i] == !(j <= k && i <= k) at every
 // resolution (the largest k over the resolutions); I (every slot live) when a mask has another form.  One warp per gene.
-constexpr int NCLS = 6;
-// token classes of the Regulation stage by descending token count: S, then 9 5 3 2 1 below it (0 = class does not exist)
+constexpr int NCLS = 10;
+// token classes of the Regulation stage by descending token count: S, then 9 8 ... 1 below it (0 = class does not exist)
 __host__ __device__ __forceinline__ int class_tokens(int c, int S) {
-    const int below[5] = {9, 5, 3, 2, 1};
     if (c == 0) return S;
-    int seen = 0;
-    for (int i = 0; i < 5; ++i)
-        if (below[i] < S && ++seen == c) return below[i];
-    return 0;
+    const int top = S - 1 < 9 ? S - 1 : 9;                        // largest class below S
+    const int t = top - (c - 1);
+    return t >= 1 ? t : 0;
 }
 __host__ __device__ __forceinline__ int class_of(int k, int S) {   // the smallest class that holds the 1 + k live tokens
     int c = 0;

@@ -13,7 +13,7 @@ struct RaggedPlan {
     int* y_rows = nullptr;                   // [R] token row of region perm[m] in X_in: gene * S + slot + 1
     int* tile_k0[CHROMO_MAX_RES] = {};       // [ceil(R / 64)] first key of tile t's key window (multiple of 8)
     int* tile_ns[CHROMO_MAX_RES] = {};       //                its width (multiple of 16, >= 16)
-    // Regulation stage: genes grouped by token class (the smallest S_c of {1, 2, 3, 5, 9, 17} that holds the
+    // Regulation stage: genes grouped by token class (the smallest S_c of {1 .. 9, i_max + 1} that holds the
     // 1 + n_partners live tokens of the gene); a tile holds floor(128 / S_c) genes of one class, S_c tokens each
     int* gene_list = nullptr;                // [B] gene ids by class (largest class first, stable inside a class)
     int4* reg_tiles = nullptr;               // [reg_tiles_max] (first entry of gene_list, genes, S_c, 0) per tile; genes = 0: unused

@@ -944,7 +944,11 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                     case 1: score_rows<1, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
                     case 2: score_rows<2, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
                     case 3: score_rows<3, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 4: score_rows<4, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
                     case 5: score_rows<5, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 6: score_rows<6, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 7: score_rows<7, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 8: score_rows<8, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
                     case 9: score_rows<(SMAX >= 9 ? 9 : SMAX), SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
                     default: score_rows<SMAX, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
                 }
