@@ -713,6 +713,14 @@ __device__ __forceinline__ void score_rows(uint64_t* bars, uint32_t trow, int ch
     }
 }
 
+// the token classes below SMAX (ragged plan): real calls, so that their window arithmetic does not weigh on the register
+// allocation of the full-size class
+template <int S, int SMAX, bool TRACE>
+__device__ __noinline__ void score_rows_call(uint64_t* bars, uint32_t trow, int ch, int lq, int lane, int gl, const float* fr,
+                                             unsigned mbits, const float* gam, Tracer<TRACE>& tr) {
+    score_rows<S, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr);
+}
+
 template <int SMAX, bool TRACE, bool PLAN>
 __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const RegFusedArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -941,15 +949,15 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             else {
                 // one instantiation per token class of the plan (the window arithmetic wants S at compile time)
                 switch (S) {
-                    case 1: score_rows<1, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
-                    case 2: score_rows<2, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
-                    case 3: score_rows<3, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
-                    case 4: score_rows<4, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
-                    case 5: score_rows<5, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
-                    case 6: score_rows<6, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
-                    case 7: score_rows<7, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
-                    case 8: score_rows<8, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
-                    case 9: score_rows<(SMAX >= 9 ? 9 : SMAX), SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 1: score_rows_call<1, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 2: score_rows_call<2, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 3: score_rows_call<3, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 4: score_rows_call<4, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 5: score_rows_call<5, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 6: score_rows_call<6, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 7: score_rows_call<7, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 8: score_rows_call<8, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
+                    case 9: if (SMAX > 9) score_rows_call<(SMAX >= 9 ? 9 : SMAX), SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); else score_rows<(SMAX >= 9 ? 9 : SMAX), SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
                     default: score_rows<SMAX, SMAX, TRACE>(bars, trow, ch, lq, lane, gl, fr, mbits, gam, tr); break;
                 }
             }

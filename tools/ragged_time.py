@@ -20,6 +20,7 @@ for name, ragged in (("dense", False), ("ragged", True)):
     out = torch.empty(N, 2, device="cuda")
     outs = {}
     for plan in (True, False):
+        res["dense"] = False                     # (no CHROMO_F_DENSE hint: the plan is built whenever it is switched on)
         if plan:
             os.environ.pop("CHROMO_NO_RAGGED", None)
         else:
