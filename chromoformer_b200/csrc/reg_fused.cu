@@ -1151,11 +1151,11 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             tc_fence_after();
             const float* b1 = prm + 768;
             const int h0 = 64 * cq;
-            float v2[32];
-            tmem_ld32_pair(trow + 256 + h0, v, trow + 256 + h0 + 32, v2);
 #pragma unroll
             for (int half = 0; half < 2; ++half) {
-                const float* vv = half ? v2 : v;
+                // (one 32-column load at a time: with the residual row live next to it a pair does not fit the 96 registers)
+                tmem_ld32(trow + 256 + h0 + 32 * half, v);
+                const float* vv = v;
                 const int c = h0 + 32 * half;
 #pragma unroll
                 for (int j = 0; j < 32; j += 8) {
