@@ -51,7 +51,7 @@ class EnsembleSweep:
             if ck != active:
                 self._activate(ck)
                 active = ck
-            out.append(self.model.forward_batch(_slice(batch, g0, g1)))
+            out.append(self.model.forward_batch(_slice(batch, g0, g1), dense=bool(batch.get("dense", False))))
         return mine, out
 
     @staticmethod
