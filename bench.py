@@ -32,14 +32,17 @@ BINS = (2000, 500, 100)
 
 def ncu_traffic(kernel="reg_layer_fused_kernel"):
     """dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant kernel, from the committed export of the
-    `ncu --set full` capture (profiles/r02_ncu_metrics.json, written by tools/ncu_extract.py); None if absent."""
-    path = os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")
+    `ncu --set full` capture (profiles/r03_dense_ncu_metrics.json: the 18,955-gene launch of the final build, written by
+    tools/ncu_extract.py; the 4096-gene capture of profiles/r02_ncu_metrics.json before it); None if absent."""
+    path = os.path.join(ROOT, "profiles", "r03_dense_ncu_metrics.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "r02_ncu_metrics.json")
     try:
         d = json.load(open(path))[kernel]
         unit = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         rd = d["dram__bytes_read.sum"] * unit[d["dram__bytes_read.sum#unit"]]
         wr = d["dram__bytes_write.sum"] * unit[d["dram__bytes_write.sum#unit"]]
-        return {"bytes": rd + wr, "read": rd, "write": wr, "source": "profiles/r02_ncu_metrics.json (" + d.get("report", "?") + ")",
+        return {"bytes": rd + wr, "read": rd, "write": wr, "source": "profiles/" + os.path.basename(path) + " (" + d.get("report", "?") + ")",
                 "tensor_pipe_active_pct": max([v for k, v in d.items() if k.startswith("sm__pipe_tensor") and
                                                k.endswith("pct_of_peak_sustained_active") and isinstance(v, float)] or [None])}
     except (OSError, KeyError, ValueError):

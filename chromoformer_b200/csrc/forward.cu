@@ -1121,7 +1121,7 @@ static int forward_impl(const chromo_config_t* c, const float* P, const chromo_b
                 // the rows of the last layer must not land in a parking block of the scratch slots (a persistent CTA parks
                 // in the block of its own index, and under a plan a tile's rows are scattered over the [B*S, 128] layout):
                 // they go to the (otherwise unused) attention buffer of the layer-by-layer path
-                if (!only) { a.y = ws + w.r_att; reg_y_att = true; }
+                if (!only) { a.y = ws + w.r_att; reg_y_att = true; a.y_head_only = 1; }   // (head_gather reads token 0 only)
                 a.p_l = c->reg_layers > 1 ? L.reg[0].att[1].gamma_f - L.reg[0].att[0].gamma_f : 0;
             }
             a.wstream = reinterpret_cast<const __nv_bfloat16*>(ws + w.reg_stream) + (long long)l * reg_stream_elems_per_layer();

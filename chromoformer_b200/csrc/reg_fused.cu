@@ -885,6 +885,14 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
         const uint32_t trow = tmem + ((uint32_t)(lq * 32) << 16);
         const float* X = a.x + z * a.x_z;
         float v[32];
+        // Parking block of the FP32 residual rows between layers: the block of this SM (one CTA per SM is resident, so the
+        // same 148 x 64 KB per slot are written and read back by tile after tile and stay in L2) when the slot has that many
+        // blocks, else the tile's own.  (Read where it is used: a value held across the layers costs a register there.)
+        auto park_block = [&]() -> long long {
+            int idx = tile;
+            if (a.park_by_sm) asm volatile("mov.u32 %0, %%smid;" : "=r"(idx));
+            return (long long)idx * 4096;
+        };
 
         // ---- phase 0 (first layer only; later layers get their operand from phase 4): X -> BF16 operand
         {
@@ -1053,7 +1061,7 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
             }
         } else {
             const float4* park = reinterpret_cast<const float4*>(a.y_mid + z * a.y_mid_z + ((li - 1) & 1) * a.y_l) +
-                                 (long long)tile * 4096 + row;
+                                 park_block() + row;
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
                 const float4 r4 = __ldcg(park + (cq * 8 + (j >> 2)) * 128);
@@ -1242,7 +1250,7 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                 fence_async_smem();
                 warp_arrive(&bars[C_XREADY], lane);
                 tr(48);
-                float4* park = reinterpret_cast<float4*>(a.y_mid + z * a.y_mid_z + (li & 1) * a.y_l) + (long long)tile * 4096 + row;
+                float4* park = reinterpret_cast<float4*>(a.y_mid + z * a.y_mid_z + (li & 1) * a.y_l) + park_block() + row;
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     __stcg(park + (cq * 8 + (j >> 2)) * 128, make_float4(u_keep[j], u_keep[j + 1], u_keep[j + 2], u_keep[j + 3]));
@@ -1260,7 +1268,10 @@ __global__ void __launch_bounds__(RF2_THREADS, 1) reg_layer_fused_kernel(const R
                     const int r = it * 4 + (lane >> 3);
                     const float* sp = stage + r * 33 + cc;
                     const int trw = lq * 32 + r;
-                    if (trw < rows_valid)
+                    // (token 0 of a gene: tile rows are whole genes, row0 is a multiple of S)
+                    const bool head_row = PLAN ? rowmap[trw] % SMAX == 0 : trw % SMAX == 0;
+                    // (under a plan only: in the other instantiation the extra test costs more in registers than the rows in bytes)
+                    if (trw < rows_valid && (head_row || !PLAN || !a.y_head_only))
                         *reinterpret_cast<float4*>(Y + (PLAN ? (long long)rowmap[trw] : row0 + trw) * 128 + c0 + cc) = make_float4(sp[0], sp[1], sp[2], sp[3]);
                 }
             }
@@ -1337,6 +1348,14 @@ int launch_reg_layer_fused(const RegFusedArgs& a, int n_res, cudaStream_t st) {
     dim3 grid(a.n_tiles, n_res);
     RegFusedArgs at = a;
     at.trace = g_trace;
+    {
+        static int sms = 0;
+        if (!sms) {
+            int dev = 0;
+            if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms < 1) sms = 1 << 30;
+        }
+        at.park_by_sm = (a.n_layers > 1 && a.n_tiles >= sms && !getenv("CHROMO_REG_PARK_BY_TILE")) ? 1 : 0;   // (%smid < SM count)
+    }
     // Attention on the tensor pipe (block-diagonal Q K^T / P V with Q and P rounded to BF16, as in every flash-attention
     // kernel) is the default (profiles/r01_precision.md).  CHROMO_REG_TC=0 selects the CUDA-core variant (FP32 q and
     // probabilities, one layer per launch).

@@ -19,6 +19,8 @@ struct RegFusedArgs {
     const float* freq;                      // [B,S,S]
     const uint8_t* imask[CHROMO_MAX_RES];   // [B,S,S] per resolution
     long long* trace = nullptr;             // profiling hook (chromo_debug_trace): CTA (0,0) logs (event << 48 | clock64) here
+    int y_head_only = 0;                    // 1 (with a plan): only token 0 of every gene is stored by the last layer (what fc_head consumes, net.py:377)
+    int park_by_sm = 0;                     // 1: a CTA parks its rows in the block of its SM (set by the launcher when the slots allow)
     // ragged plan (ragged.cu; tensor-pipe attention only): tile t holds plan_tiles[t].y genes (0: the tile is unused - the
     // grid is an upper bound) with their first plan_tiles[t].z tokens each (the others are masked for every token that
     // reaches the head); its rows are gathered from / scattered to rows plan_rows[t][0..128) of the [B*S, 128] layout
