@@ -7,9 +7,10 @@ computes every bin of every slot, as the reference does) - no GPU, no plan invol
      features nor its pad mask nor its interaction_freq entry.
 
 Both are asserted bit-for-bit: the plan's eliminations are exact, not approximate."""
+import pytest
 import torch
 
-from _util import KWS
+from _util import KWS, import_reference, reference_available
 from chromoformer_b200 import ChromoformerClassifier, synthetic
 from oracle import chromoformer_oracle as oracle
 
@@ -19,14 +20,9 @@ def _logits(sd, batch):
         return oracle.chromoformer_forward(sd, *synthetic.forward_args(synthetic.expand_full_masks(batch)))
 
 
-def test_masked_bins_and_dummy_slots_cannot_reach_the_logits():
-    torch.manual_seed(0)
-    model = ChromoformerClassifier(7, 128, 128, dict(KWS[0]), dict(KWS[1]), dict(KWS[2]), seed=5)
-    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
-    batch = synthetic.make_batch(6, ragged=True, seed=77)
+def _perturbed(batch):
+    """The same genes with junk under every pad mask of a live slot and junk everywhere in the dummy slots."""
     k = batch["n_partners"]
-    assert (k < 8).any() and (k > 0).any()
-    want = _logits(sd, batch)
 
     gen = torch.Generator().manual_seed(1)
     other = {key: ({b: t.clone() for b, t in v.items()} if isinstance(v, dict) else v.clone()) for key, v in batch.items()}
@@ -44,5 +40,26 @@ def test_masked_bins_and_dummy_slots_cannot_reach_the_logits():
     f = other["interaction_freq"]
     dead_tok = torch.arange(9).view(1, 9) > k.view(-1, 1)                    # tokens of dummy slots
     f[:] = torch.where(dead_tok.unsqueeze(1) | dead_tok.unsqueeze(2), 3.0 * torch.rand(f.shape, generator=gen), f)
-    got = _logits(sd, other)
+    return other
+
+
+def test_masked_bins_and_dummy_slots_cannot_reach_the_logits():
+    model = ChromoformerClassifier(7, 128, 128, dict(KWS[0]), dict(KWS[1]), dict(KWS[2]), seed=5)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    batch = synthetic.make_batch(6, ragged=True, seed=77)
+    k = batch["n_partners"]
+    assert (k < 8).any() and (k > 0).any()
+    assert torch.equal(_logits(sd, _perturbed(batch)), _logits(sd, batch))
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not mounted (GPU box)")
+def test_same_facts_on_the_unmodified_reference():
+    """The reference's own forward (imported from /root/reference, CPU) gives identical logits for the two batches."""
+    net, _ = import_reference()
+    ref = net.ChromoformerClassifier(7, 128, 128, dict(KWS[0]), dict(KWS[1]), dict(KWS[2]), seed=5).eval()
+    batch = synthetic.make_batch(6, ragged=True, seed=77)
+    assert (batch["n_partners"] < 8).any()
+    with torch.no_grad():
+        want = ref(*synthetic.forward_args(synthetic.expand_full_masks(batch)))
+        got = ref(*synthetic.forward_args(synthetic.expand_full_masks(_perturbed(batch))))
     assert torch.equal(got, want)
